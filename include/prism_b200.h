@@ -1,0 +1,303 @@
+/*
+ * prism_b200.h -- C ABI of libprism_b200.so (hand-written sm_100a CUDA).
+ *
+ * Drop-in boundary for the learner-side hot path of AechPro/Prism.  The
+ * reference is 100 % Python and has no FFI of its own; the only native code it
+ * touches is torchrl's segment tree (a pybind C++ extension inside a
+ * third-party wheel).  Each entry point below therefore cites the reference
+ * *call site* it replaces (paths relative to the reference repository).
+ *
+ * Conventions
+ *   - every function returns int: 0 ok, <0 argument error (PB_E_*), >0 a
+ *     cudaError_t.  Nothing throws, nothing synchronises the stream, nothing
+ *     allocates device memory: the caller (PyTorch) owns every buffer and the
+ *     library borrows raw pointers for the duration of the stream-ordered call.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - all entry points are CUDA-graph capturable (no host reads of device data).
+ *   - pointers are DEVICE pointers unless the name ends in _h (host).
+ *   - thread-compatible: no globals except a launch counter (atomic).
+ */
+#ifndef PRISM_B200_H
+#define PRISM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_ABI_VERSION 1
+
+enum {
+    PB_OK = 0,
+    PB_E_ARG = -1,          /* null pointer / negative size / unsupported shape */
+    PB_E_CAPACITY = -2,     /* capacity not a power of two or size > capacity   */
+    PB_E_UNSUPPORTED = -3,  /* dtype / option not implemented                   */
+    PB_E_POOL = -4          /* aux observation pool exhausted (host planner)    */
+};
+
+/* device-side status bits accumulated in pb_per_state.status */
+enum {
+    PB_ST_EMPTY = 1,        /* sample on an empty shard        (torchrl: RuntimeError) */
+    PB_ST_PSUM_NONPOS = 2,  /* p_sum <= 0                      (torchrl: RuntimeError) */
+    PB_ST_PMIN_NONPOS = 4   /* p_min <= 0                      (torchrl: RuntimeError) */
+};
+
+int         pb_abi_version(void);
+const char *pb_error_string(int code);
+/* number of kernels this library has launched in this process (bench: gpu_launches) */
+long long   pb_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * Prioritized replay: sum-tree + min-tree priority store.
+ * Replaces torchrl.data.PrioritizedReplayBuffer's sampler as constructed at
+ * prism/factory/exp_buffer_factory.py:22-28.
+ * Layout: level-ordered (heap) fp32 arrays of 2*capacity floats, node i has
+ * children 2i and 2i+1, leaves at [capacity, 2*capacity).  Every internal node
+ * is fl32(left + right) / min(left, right): the reference's add order.
+ * ------------------------------------------------------------------------- */
+
+/* 64-byte device-resident state block of one shard */
+typedef struct pb_per_state {
+    long long len;           /* filled slots                                   */
+    long long seq;           /* number of transitions ever written (cursor = seq % size) */
+    float     max_priority;  /* torchrl _max_priority, starts at 1             */
+    float     p_sum;         /* query_sum(0, len), refreshed by every mutation */
+    float     p_min;         /* query_min(0, len)                              */
+    int       status;        /* PB_ST_* bits (sticky)                          */
+    float     batch_max;     /* scratch: max priority of the batch in flight   */
+    int       owned_lo;      /* global sampling: first stratum owned by this rank */
+    int       owned_n;       /* global sampling: number of strata owned        */
+    int       pad[5];
+} pb_per_state;
+
+typedef struct pb_tree {
+    float        *sum;       /* 2*capacity floats */
+    float        *min;       /* 2*capacity floats */
+    int          *owner;     /* capacity ints, all -1 between calls (dedup scratch) */
+    pb_per_state *state;
+    long long     capacity;  /* power of two */
+    long long     size;      /* addressable slots N <= capacity */
+    float         alpha;     /* priority exponent (0.5 in every reference config) */
+    float         eps_f32;   /* eps as torch adds it to an fp32 tensor */
+    double        eps_f64;   /* eps as python adds it to a float */
+    int           weight_eps_in_denominator; /* w = (p/(p_min+eps))^-beta variant */
+    int           default_priority_fp64;     /* (max_p+eps)^alpha in double, then cast */
+} pb_tree;
+
+/* zero the trees (sum 0, min +inf), owner = -1, state = {len 0, max_priority 1} */
+int pb_tree_init(const pb_tree *t, void *stream);
+
+/* bulk load n post-pow fp32 leaves (rest padded with the identity) and rebuild
+ * every internal node pairwise; sets len=min(n,size), seq=n.  Streaming kernel. */
+int pb_tree_build(const pb_tree *t, const float *leaves, long long n, void *stream);
+
+/* recompute state->p_sum / p_min = query(0, len) exactly as torchrl's interval
+ * walk associates them (timestep_buffer.py:37 -> PrioritizedSampler.sample) */
+int pb_tree_stats(const pb_tree *t, void *stream);
+
+/* raw leaf write + ancestor recompute (both trees).  Duplicates: last wins,
+ * like the sequential reference loop.  sorted!=0 promises idx is non-decreasing
+ * (true for stratified samples) and skips the owner-scratch pass. */
+int pb_tree_set_leaves(const pb_tree *t, long long n, const long long *idx,
+                       const float *leaves, int sorted, void *stream);
+
+/* TimestepBuffer.update_priority (prism/experience/timestep_buffer.py:53-54,
+ * called from prism/learner.py:119-120): max_priority = max(max_priority, max p);
+ * leaf = (p + eps)^alpha in fp32; ancestors; refreshes p_sum/p_min.
+ * No device->host copy (the reference syncs here). */
+int pb_tree_update_priority(const pb_tree *t, long long n, const long long *idx,
+                            const float *priority, int sorted, void *stream);
+
+/* TimestepBuffer.extend (timestep_buffer.py:32-33): the n slots starting at the
+ * ring cursor get the default priority (max_priority+eps)^alpha; advances
+ * seq/len.  idx_out (optional) receives the slots written. */
+int pb_tree_extend(const pb_tree *t, long long n, long long *idx_out, void *stream);
+
+/* scan_lower_bound on injected fp32 masses (parity entry point) */
+int pb_tree_scan(const pb_tree *t, long long n, const float *mass, long long *idx_out,
+                 void *stream);
+
+/* PrioritizedSampler.sample (timestep_buffer.py:37): u are fp64 uniforms in [0,1).
+ * mode 0 iid: mass = p_sum*u (numpy uniform(0,p_sum)); mode 1 stratified:
+ * mass = (k+u_k)/n * p_sum.  idx clamped to len-1; weight=(leaf/p_min)^-beta.
+ * mass_out optional. */
+int pb_tree_sample(const pb_tree *t, long long n, const double *u, int mode, float beta,
+                   long long *idx_out, float *weight_out, float *mass_out, void *stream);
+
+/* Sharded global stratified sampling (new design).  Every rank holds
+ * one shard; all_* are the all-gathered {p_sum, p_min, len} of the G shards
+ * (G a power of two).  The G shard roots form the virtual top of one tree of
+ * G*capacity leaves, summed pairwise in fp32.  Each rank evaluates all n_global
+ * strata, keeps the contiguous run that lands in its shard and descends its own
+ * tree with the residual mass.  Outputs are compacted to [0, owned_n);
+ * state->owned_lo / owned_n report the run.  Rows >= owned_n get idx 0, weight 0. */
+int pb_tree_sample_global(const pb_tree *t, int n_ranks, int rank, const float *all_psum,
+                          const float *all_pmin, const long long *all_len,
+                          long long n_global, const double *u, float beta,
+                          long long *idx_out, float *weight_out, long long *stratum_out,
+                          void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Transition ring (replaces the linked list of Timestep objects,
+ * prism/experience/timestep.py:12-28, and ListStorage).
+ * SoA; slot = seq % size; links hold sequence numbers and die on overwrite
+ * exactly like the reference's weakrefs.
+ * ------------------------------------------------------------------------- */
+typedef struct pb_store {
+    void      *obs;        /* [size][obs_elems] of obs_dtype            */
+    void      *aux_obs;    /* [aux_size][obs_elems]: in-flight / truncated-final observations */
+    int       *action;     /* [size] */
+    float     *reward;     /* [size] */
+    uint8_t   *done;       /* [size] */
+    uint8_t   *trunc;      /* [size] */
+    long long *slot_seq;   /* [size], -1 = empty */
+    long long *next_link;  /* [size]: >=0 seq of successor; -1 none; <=-2 aux row -(v+2) */
+    long long *prev_link;  /* [size]: >=0 seq of predecessor; -1 none */
+    long long  size;
+    long long  aux_size;
+    int        obs_elems;  /* elements of ONE frame */
+    int        obs_dtype;  /* 0 fp32, 1 uint8 */
+    int        obs_scale;  /* uint8 only: 0 -> (float)v, 1 -> (float)v / 255.0f */
+    int        frame_stack;
+    int        n_step;
+    int        pad;
+    double     gamma;
+} pb_store;
+
+/* per-step flags handed to the host planner */
+enum { PB_STEP_DONE = 1, PB_STEP_TRUNC = 2, PB_STEP_NO_NEXT = 4 };
+
+/* HOST planner for TimestepBuffer.extend: turns n new steps (in arrival order,
+ * each tagged with its collector stream) into slot/link values, following the
+ * link rules of multiprocessing_experience_collection/collector_process_interface.py:146-173
+ * (done -> no next; truncated -> next is the final observation, never stored;
+ * else prev/next neighbours).  All arrays are HOST memory.
+ *   stream_last_h[n_streams]  in/out: seq of the newest stored step of each stream, -1 none
+ *   seq0                      seq of the first new step
+ *   trunc_cursor_h            in/out: next free row of the truncated-obs pool
+ *                             (rows [n_streams, aux_size) of aux_obs, used as a ring)
+ *   trunc_owner_h[aux_size-n_streams] in/out: seq of the step owning each pool row (-1 free);
+ *                             recycling a row whose owner is still stored returns PB_E_POOL
+ *                             with no side effect (the caller grows the pool and retries)
+ * outputs (host, length n): seq_h, prev_link_h, next_link_h, aux_row_h (row of
+ * aux_obs that receives next_obs[j], -1 = discard), patch_slot_h / patch_val_h
+ * (next_link fix-ups of already-stored predecessors, -1 = none). */
+int pb_store_extend_plan(long long size, long long aux_size, int n_streams, long long n,
+                         long long seq0, const int *stream_id_h, const uint8_t *flags_h,
+                         long long *stream_last_h,
+                         long long *trunc_cursor_h, long long *trunc_owner_h, long long *seq_h,
+                         long long *prev_link_h,
+                         long long *next_link_h, long long *aux_row_h,
+                         long long *patch_slot_h, long long *patch_val_h);
+
+/* device scatter of n planned steps: obs rows -> ring, next_obs rows -> aux pool,
+ * metadata, link patches.  obs/next_obs are device staging buffers
+ * [n][obs_elems] of the store dtype. */
+int pb_store_scatter(const pb_store *s, long long n, const void *obs, const void *next_obs,
+                     const int *action, const float *reward, const uint8_t *done,
+                     const uint8_t *trunc, const long long *seq, const long long *prev_link,
+                     const long long *next_link, const long long *aux_row,
+                     const long long *patch_slot, const long long *patch_val, void *stream);
+
+/* TimestepBuffer._timesteps_to_batch + _compute_n_step + _stack_obs_into
+ * (prism/experience/timestep_buffer.py:79-257) fused: for each sampled slot walk
+ * <= n_step links (fp64 return accumulation), resolve the successor observation,
+ * and write the static batch with 128-bit coalesced row copies (uint8 widened
+ * on the fly).  Rows with idx < 0 are skipped.
+ *   obs_out/next_obs_out  [n][frame_stack][obs_elems] fp32
+ *   ret_out [n] fp32, gamma_out [n] fp32, nonterm_out [n] u8 (torch.bool),
+ *   action_out [n] int64 */
+int pb_store_gather(const pb_store *s, long long n, const long long *idx, float *obs_out,
+                    float *next_obs_out, float *ret_out, float *gamma_out,
+                    uint8_t *nonterm_out, long long *action_out, void *stream);
+
+/* n-step metadata only (parity entry point): same walk, no observation traffic */
+int pb_store_nstep(const pb_store *s, long long n, const long long *idx, float *ret_out,
+                   float *gamma_out, uint8_t *done_out, long long *last_out,
+                   long long *succ_out, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Agent-side fused kernels
+ * ------------------------------------------------------------------------- */
+
+/* IQNModel._embed_quantiles basis (prism/agents/models/iqn_model.py:89-92):
+ * out[r][i] = cos(fl32(fl32(tau[r] * (i+1)) * pi)), i in [0, n_basis) */
+int pb_iqn_cos_basis(long long n_rows, int n_basis, const float *tau, float *out, void *stream);
+
+/* IQNModel.get_loss (prism/agents/models/iqn_model.py:110-201) from the three
+ * quantile tables, fused with its own backward:
+ *   z_cur   [T*B][A]  online Z(s, tau_i)   (quantile-major rows: r = i*B + b)
+ *   tau     [T*B]
+ *   z_next_online / z_next_target [Tp*B][A]  (same pointer when not double-Q)
+ *   a* = argmax_a mean_j z_next_online; y_bj = R_b + gdn_b * z_next_target[j,b,a*]
+ *   delta = y_bj - theta_bi; Huber(kappa); rho = |tau_bi - 1{delta<0}| * L / kappa
+ *   loss_b = loss_weight * mean_j sum_i rho
+ * grad_z_cur [T*B][A] = grad_scale * row_weight[b] * d loss_b / d z_cur (zero outside the
+ * taken action; row_weight NULL = 1).  With row_weight = PER weights and grad_scale = 1/B
+ * this is d mean(loss*w) / d z_cur (prism/agents/agent.py:58-60). */
+int pb_iqn_qh_loss(int B, int T, int Tp, int A, const float *z_cur, const float *tau,
+                   const float *z_next_online, const float *z_next_target,
+                   const long long *action, const float *ret, const float *gdn, float kappa,
+                   float loss_weight, const float *row_weight, float grad_scale, float *loss_out,
+                   float *grad_z_cur, void *stream);
+
+/* QEnsemble.get_loss (prism/agents/models/q_ensemble.py:50-92) without the
+ * Theil term: tables are head-major [K][B][A].
+ *   a*_k = argmax_a q_next_online[k,b,:]; y_k = R + gdn * q_next_target[k,b,a*_k]
+ *   loss_b = loss_weight * mean_k (q_cur[k,b,a_b] - y_k)^2;  grad_q_cur [K][B][A] */
+int pb_ens_q_loss(int B, int A, int K, const float *q_cur, const float *q_next_online,
+                  const float *q_next_target, const long long *action, const float *ret,
+                  const float *gdn, float loss_weight, const float *row_weight, float grad_scale,
+                  float *loss_out, float *grad_q_cur, void *stream);
+
+/* IDSActionSelector.generate_action_probs + select_action
+ * (prism/agents/action_selectors.py:125-176), deterministic branch.
+ *   q [K][N][A] head-major ensemble values, z [Nq][N][A] quantile values.
+ *   action_out [N] int64; scores_out optional [N][A]. Reproduces the reference's
+ *   std-for-variance / sqrt(std)-for-std naming quirk. */
+int pb_ids_select(int N, int A, int K, int Nq, const float *q, const float *z, float lambda,
+                  float eps, float rho_lower_bound, long long *action_out, float *scores_out,
+                  void *stream);
+
+/* GreedyActionSelector (action_selectors.py:70-82): argmax_a mean_k q */
+int pb_greedy_select(int N, int A, int K, const float *q, long long *action_out, void *stream);
+
+/* Agent._update_without_cuda_graph tail (prism/agents/agent.py:71-74):
+ * clip_grad_norm_(max_norm) + Adam (torch.optim.Adam semantics, factory/agent_factory.py:44-47)
+ * over ONE flat fp32 parameter arena -- two launches instead of ~10 per parameter tensor.
+ *
+ * pb_pack_grads: gather autograd's per-parameter gradients into the flat arena, multiplied by
+ *   `scale` (1/world_size under data parallelism), folding in the per-CTA sum of squares.
+ *   table (device) = n_tensors x {grad pointer (0 = no grad), arena offset, numel} as int64.
+ *   step_count (device int64, optional) is incremented.  n_partials_out_h (host) receives the
+ *   number of partial sums written to partial_scratch (>= 4096 floats).
+ * pb_grad_sumsq: same partial sums for a gradient that is already flat (after an all-reduce).
+ * pb_adam_clip_apply: total_norm = sqrt(sum partials); coef = min(1, max_norm/(norm+1e-6));
+ *   g *= coef; Adam with bias correction from *step_count.  norm_out (optional, device
+ *   float[2]) = {total_norm, coef}.
+ * pb_adam_clip_step = pb_grad_sumsq + pb_adam_clip_apply. */
+#define PB_ADAM_MAX_PARTIALS 4096
+int pb_pack_grads(int n_tensors, const long long *table, float scale, float *flat,
+                  float *partial_scratch, long long *step_count, int *n_partials_out_h,
+                  void *stream);
+int pb_grad_sumsq(long long n, const float *grad, float *partial_scratch, long long *step_count,
+                  int *n_partials_out_h, void *stream);
+int pb_adam_clip_apply(long long n, float *param, const float *grad, float *exp_avg,
+                       float *exp_avg_sq, const long long *step_count, float lr, float beta1,
+                       float beta2, float adam_eps, float max_grad_norm,
+                       const float *partial_scratch, int n_partials, float *norm_out,
+                       void *stream);
+int pb_adam_clip_step(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
+                      long long *step_count, float lr, float beta1, float beta2, float adam_eps,
+                      float max_grad_norm, float *norm_out, float *partial_scratch, void *stream);
+
+/* total_loss = mean_b(dist*w) + mean_b(q*w);  td_b = 0.5*dist + 0.5*q | dist | |q|
+ * (composite_model.py:135-142, agent.py:58-64).  dist or q may be NULL; w NULL = 1. */
+int pb_loss_combine(int B, const float *dist, const float *q, const float *w, float *total_out,
+                    float *td_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRISM_B200_H */

@@ -1,0 +1,133 @@
+"""ctypes binding of libprism_b200.so -- mirrors include/prism_b200.h one-to-one.
+
+There is no CPU fallback: if the CUDA library cannot be found or built, importing a
+product code path raises.  (The CPU oracle lives under oracle/ and is never imported
+from this package.)
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+
+class PbError(RuntimeError):
+    pass
+
+
+class pb_per_state(C.Structure):
+    _fields_ = [
+        ("len", C.c_longlong), ("seq", C.c_longlong), ("max_priority", C.c_float), ("p_sum", C.c_float),
+        ("p_min", C.c_float), ("status", C.c_int), ("batch_max", C.c_float), ("owned_lo", C.c_int),
+        ("owned_n", C.c_int), ("pad", C.c_int * 5),
+    ]
+
+
+class pb_tree(C.Structure):
+    _fields_ = [
+        ("sum", C.c_void_p), ("min", C.c_void_p), ("owner", C.c_void_p), ("state", C.c_void_p),
+        ("capacity", C.c_longlong), ("size", C.c_longlong), ("alpha", C.c_float), ("eps_f32", C.c_float),
+        ("eps_f64", C.c_double), ("weight_eps_in_denominator", C.c_int), ("default_priority_fp64", C.c_int),
+    ]
+
+
+class pb_store(C.Structure):
+    _fields_ = [
+        ("obs", C.c_void_p), ("aux_obs", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p),
+        ("done", C.c_void_p), ("trunc", C.c_void_p), ("slot_seq", C.c_void_p), ("next_link", C.c_void_p),
+        ("prev_link", C.c_void_p), ("size", C.c_longlong), ("aux_size", C.c_longlong), ("obs_elems", C.c_int),
+        ("obs_dtype", C.c_int), ("obs_scale", C.c_int), ("frame_stack", C.c_int), ("n_step", C.c_int),
+        ("pad", C.c_int), ("gamma", C.c_double),
+    ]
+
+
+assert C.sizeof(pb_per_state) == 64
+
+_P = C.c_void_p
+_LL = C.c_longlong
+_I = C.c_int
+_F = C.c_float
+_TREE = C.POINTER(pb_tree)
+_STORE = C.POINTER(pb_store)
+
+# name -> argtypes (every function returns int unless listed in _RESTYPES)
+SIGNATURES = {
+    "pb_abi_version": [],
+    "pb_error_string": [_I],
+    "pb_launch_count": [],
+    "pb_tree_init": [_TREE, _P],
+    "pb_tree_build": [_TREE, _P, _LL, _P],
+    "pb_tree_stats": [_TREE, _P],
+    "pb_tree_set_leaves": [_TREE, _LL, _P, _P, _I, _P],
+    "pb_tree_update_priority": [_TREE, _LL, _P, _P, _I, _P],
+    "pb_tree_extend": [_TREE, _LL, _P, _P],
+    "pb_tree_scan": [_TREE, _LL, _P, _P, _P],
+    "pb_tree_sample": [_TREE, _LL, _P, _I, _F, _P, _P, _P, _P],
+    "pb_tree_sample_global": [_TREE, _I, _I, _P, _P, _P, _LL, _P, _F, _P, _P, _P, _P],
+    "pb_store_extend_plan": [_LL, _LL, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "pb_store_scatter": [_STORE, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "pb_store_gather": [_STORE, _LL, _P, _P, _P, _P, _P, _P, _P, _P],
+    "pb_store_nstep": [_STORE, _LL, _P, _P, _P, _P, _P, _P, _P],
+    "pb_iqn_cos_basis": [_LL, _I, _P, _P, _P],
+    "pb_iqn_qh_loss": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _P, _F, _P, _P, _P],
+    "pb_ens_q_loss": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _F, _P, _F, _P, _P, _P],
+    "pb_ids_select": [_I, _I, _I, _I, _P, _P, _F, _F, _F, _P, _P, _P],
+    "pb_greedy_select": [_I, _I, _I, _P, _P, _P],
+    "pb_adam_clip_step": [_LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
+    "pb_pack_grads": [_I, _P, _F, _P, _P, _P, _P, _P],
+    "pb_grad_sumsq": [_LL, _P, _P, _P, _P, _P],
+    "pb_adam_clip_apply": [_LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _I, _P, _P],
+    "pb_loss_combine": [_I, _P, _P, _P, _P, _P, _P],
+}
+_RESTYPES = {"pb_error_string": C.c_char_p, "pb_launch_count": C.c_longlong}
+
+PB_E_POOL = -4
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if needed) libprism_b200.so.  Raises if unavailable."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.build()
+    if not os.path.exists(path):
+        raise PbError("libprism_b200.so missing at %s and could not be built" % path)
+    lib = C.CDLL(path)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError = ABI drift, fail loudly
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    if lib.pb_abi_version() != 1:
+        raise PbError("libprism_b200.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().pb_error_string(rc).decode()
+        raise PbError("%s failed: %s (code %d)" % (what or "libprism_b200 call", msg, rc))
+
+
+def ptr(t):
+    """Raw device/host pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def cur_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(load().pb_launch_count())
+
+
+def require_cuda(t, name="tensor"):
+    if not t.is_cuda:
+        raise PbError("%s must live on a CUDA device: libprism_b200 has no CPU path" % name)

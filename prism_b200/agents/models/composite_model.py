@@ -1,0 +1,116 @@
+"""CompositeModel -- embedding -> {IQN head, Q ensemble}; builds the per-row losses and the new
+PER priorities.  Same surface as the reference (prism/agents/models/composite_model.py:7-154):
+``forward(x, for_action=True) -> (q (N,A,K), z (Nq,N,A))``, ``get_losses(batch, target_model) ->
+(dist (B,), q (B,), td (B,))``, attributes ``embedding_model / distribution_model /
+q_function_model / device / should_build_forward_cuda_graph``.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .iqn_model import IQNModel
+
+
+class CompositeModel(nn.Module):
+    def __init__(self, embedding_model, distribution_model, q_function_model, device="cpu", use_cuda_graph=False):
+        super().__init__()
+        self.embedding_model = embedding_model
+        self.distribution_model = distribution_model
+        self.q_function_model = q_function_model
+        self.device = device
+        self.use_cuda_graph = use_cuda_graph
+        self.should_build_forward_cuda_graph = use_cuda_graph
+        self._forward_cuda_graph = None
+        self._static_input = None
+        self._static_q = None
+        self._static_z = None
+        self.loggables = {}
+
+    # ---- acting ---------------------------------------------------------------------
+    def forward(self, x, for_action=True):
+        if not isinstance(x, torch.Tensor):
+            x = torch.from_numpy(np.asarray(x, dtype=np.float32))
+        x = x.float().to(self.device)
+        if for_action and self.use_cuda_graph:
+            return self._forward_with_cuda_graph(x)
+        return self._forward_without_cuda_graph(x, for_action=for_action)
+
+    def _forward_without_cuda_graph(self, x, for_action=True):
+        emb = self.embedding_model(x) if self.embedding_model is not None else x
+        z = self.distribution_model(emb, for_action=for_action) if self.distribution_model is not None else None
+        if self.q_function_model is not None:
+            q = self.q_function_model(emb)
+        elif for_action and type(self.distribution_model) is IQNModel:
+            q = z.mean(dim=0).unsqueeze(-1)
+        else:
+            q = None
+        return q, z
+
+    @torch.no_grad()
+    def _forward_with_cuda_graph(self, x):
+        if self._forward_cuda_graph is None or self._static_input.shape != x.shape:
+            if not self.should_build_forward_cuda_graph:
+                return self._forward_without_cuda_graph(x)
+            self._build_forward_cuda_graph(x)
+        self._static_input.copy_(x)
+        self._forward_cuda_graph.replay()
+        q = None if self._static_q is None else self._static_q.clone()
+        z = None if self._static_z is None else self._static_z.clone()
+        return q, z
+
+    @torch.no_grad()
+    def _build_forward_cuda_graph(self, x):
+        self._static_input = x.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._forward_without_cuda_graph(self._static_input, for_action=True)
+        torch.cuda.current_stream().wait_stream(side)
+        self._forward_cuda_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._forward_cuda_graph):
+            self._static_q, self._static_z = self._forward_without_cuda_graph(self._static_input, for_action=True)
+
+    # ---- learning -------------------------------------------------------------------
+    def get_losses(self, batch, target_model):
+        obs = batch["observation"]
+        next_obs = batch["next"]["observation"]
+        if obs.shape[1] == 1:                      # frame_stack == 1: drop the stack axis (:97-99)
+            obs = obs.squeeze(1)
+            next_obs = next_obs.squeeze(1)
+        returns = batch["next"]["reward"].flatten()
+        nonterminal = batch["nonterminal"].flatten().float()
+        gammas = batch["gamma"].flatten().float()
+        act = batch["action"]
+        if act.dim() == 2 and act.shape[-1] != 1:
+            act = act.argmax(dim=-1)
+        acts = act.flatten().long()
+        dones_and_gamma = gammas * nonterminal
+
+        emb = self.embedding_model(obs)
+        with torch.no_grad():
+            if target_model is not None:
+                emb_next = target_model.embedding_model(next_obs)
+                dist_target, q_target = target_model.distribution_model, target_model.q_function_model
+            else:
+                emb_next = self.embedding_model(next_obs)
+                dist_target = q_target = None
+
+        dist_loss = q_loss = td = None
+        if self.distribution_model is not None:
+            dist_loss = self.distribution_model.get_loss(emb, emb_next, acts, returns, dones_and_gamma,
+                                                         target_model=dist_target)
+        if self.q_function_model is not None:
+            q_loss = self.q_function_model.get_loss(emb, emb_next, acts, returns, dones_and_gamma,
+                                                    target_model=q_target)
+        if dist_loss is not None or q_loss is not None:
+            with torch.no_grad():
+                _, td = ops.loss_combine(None if dist_loss is None else dist_loss.detach(),
+                                         None if q_loss is None else q_loss.detach(), None)
+        return dist_loss, q_loss, td
+
+    def log(self, logger):
+        for m in (self.embedding_model, self.distribution_model, self.q_function_model):
+            if m is not None:
+                m.log(logger)

@@ -1,0 +1,150 @@
+"""torch.autograd bridges to the fused CUDA kernels of libprism_b200 (csrc/agent_kernels.cu).
+
+Every function here launches hand-written sm_100a kernels through the C ABI on the current
+torch stream; inputs must be CUDA tensors (no CPU path -- the CPU restatement lives in
+oracle/ and is only ever used by tests and the bench's cpu_baseline leg).
+"""
+import torch
+
+from .. import _lib
+
+
+def _c(t, dtype=torch.float32):
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def cos_basis(tau, n_basis):
+    """cos(pi * i * tau), i = 1..n_basis  ->  (rows, n_basis).  tau carries no gradient
+    (prism/agents/models/iqn_model.py:89-92)."""
+    _lib.require_cuda(tau, "tau")
+    tau = _c(tau.detach()).view(-1)
+    out = torch.empty(tau.numel(), n_basis, dtype=torch.float32, device=tau.device)
+    _lib.check(_lib.load().pb_iqn_cos_basis(tau.numel(), int(n_basis), tau.data_ptr(), out.data_ptr(), _stream(tau)),
+               "pb_iqn_cos_basis")
+    return out
+
+
+class _QuantileHuberLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z_cur, tau, z_next_online, z_next_target, action, ret, gdn, B, T, Tp, kappa, loss_weight):
+        _lib.require_cuda(z_cur, "z_cur")
+        A = z_cur.shape[-1]
+        z_cur_c, tau_c = _c(z_cur), _c(tau).view(-1)
+        zo, zt = _c(z_next_online), _c(z_next_target)
+        action_c, ret_c, gdn_c = _c(action, torch.int64).view(-1), _c(ret).view(-1), _c(gdn).view(-1)
+        loss = torch.empty(B, dtype=torch.float32, device=z_cur.device)
+        grad = torch.empty_like(z_cur_c)
+        _lib.check(_lib.load().pb_iqn_qh_loss(
+            B, T, Tp, A, z_cur_c.data_ptr(), tau_c.data_ptr(), zo.data_ptr(), zt.data_ptr(), action_c.data_ptr(),
+            ret_c.data_ptr(), gdn_c.data_ptr(), float(kappa), float(loss_weight), None, 1.0, loss.data_ptr(),
+            grad.data_ptr(), _stream(z_cur)), "pb_iqn_qh_loss")
+        ctx.save_for_backward(grad)
+        ctx.dims = (B, T, A)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        (grad,) = ctx.saved_tensors
+        B, T, A = ctx.dims
+        # rows are quantile-major (r = i*B + b): scale row b of every quantile by dL/dloss_b
+        gz = (grad.view(T, B, A) * grad_loss.view(1, B, 1)).view(T * B, A)
+        return (gz,) + (None,) * 11
+
+
+def quantile_huber_loss(z_cur, tau, z_next_online, z_next_target, action, ret, gdn, n_cur, n_next, kappa=1.0,
+                        loss_weight=1.0):
+    """IQN loss per batch row, (B,) -- target build, pairwise quantile-Huber and its gradient in
+    one kernel (prism/agents/models/iqn_model.py:110-201)."""
+    B = action.numel()
+    return _QuantileHuberLoss.apply(z_cur, tau, z_next_online, z_next_target, action, ret, gdn, B, int(n_cur),
+                                    int(n_next), kappa, loss_weight)
+
+
+class _EnsembleQLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q_cur, q_next_online, q_next_target, action, ret, gdn, loss_weight):
+        _lib.require_cuda(q_cur, "q_cur")
+        K, B, A = q_cur.shape
+        qc, qo, qt = _c(q_cur), _c(q_next_online), _c(q_next_target)
+        action_c, ret_c, gdn_c = _c(action, torch.int64).view(-1), _c(ret).view(-1), _c(gdn).view(-1)
+        loss = torch.empty(B, dtype=torch.float32, device=q_cur.device)
+        grad = torch.empty_like(qc)
+        _lib.check(_lib.load().pb_ens_q_loss(
+            B, A, K, qc.data_ptr(), qo.data_ptr(), qt.data_ptr(), action_c.data_ptr(), ret_c.data_ptr(),
+            gdn_c.data_ptr(), float(loss_weight), None, 1.0, loss.data_ptr(), grad.data_ptr(), _stream(q_cur)),
+            "pb_ens_q_loss")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        (grad,) = ctx.saved_tensors
+        return (grad * grad_loss.view(1, -1, 1),) + (None,) * 6
+
+
+def ensemble_q_loss(q_cur, q_next_online, q_next_target, action, ret, gdn, loss_weight=1.0):
+    """Mean-over-heads MSE with per-head double-Q targets, (B,).  Tables are head-major (K, B, A)
+    (prism/agents/models/q_ensemble.py:62-84)."""
+    return _EnsembleQLoss.apply(q_cur, q_next_online, q_next_target, action, ret, gdn, loss_weight)
+
+
+def ids_select(q_kna, z_qna, lmbda, eps, rho_lower_bound, return_scores=False):
+    """IDS information-ratio argmin (prism/agents/action_selectors.py:125-176).
+    q_kna: (K, N, A) head-major ensemble values; z_qna: (Nq, N, A)."""
+    _lib.require_cuda(q_kna, "q")
+    K, N, A = q_kna.shape
+    Nq = z_qna.shape[0]
+    q, z = _c(q_kna), _c(z_qna)
+    act = torch.empty(N, dtype=torch.int64, device=q.device)
+    scores = torch.empty(N, A, dtype=torch.float32, device=q.device) if return_scores else None
+    _lib.check(_lib.load().pb_ids_select(N, A, K, Nq, q.data_ptr(), z.data_ptr(), float(lmbda), float(eps),
+                                         float(rho_lower_bound), act.data_ptr(), _lib.ptr(scores), _stream(q)),
+               "pb_ids_select")
+    return (act, scores) if return_scores else act
+
+
+def greedy_select(q_kna):
+    _lib.require_cuda(q_kna, "q")
+    K, N, A = q_kna.shape
+    q = _c(q_kna)
+    act = torch.empty(N, dtype=torch.int64, device=q.device)
+    _lib.check(_lib.load().pb_greedy_select(N, A, K, q.data_ptr(), act.data_ptr(), _stream(q)), "pb_greedy_select")
+    return act
+
+
+class _LossCombine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dist, q, w):
+        ref = dist if dist is not None else q
+        _lib.require_cuda(ref, "loss")
+        B = ref.numel()
+        total = torch.empty((), dtype=torch.float32, device=ref.device)
+        td = torch.empty(B, dtype=torch.float32, device=ref.device)
+        dist_c = None if dist is None else _c(dist)
+        q_c = None if q is None else _c(q)
+        w_c = None if w is None else _c(w).view(-1)
+        _lib.check(_lib.load().pb_loss_combine(B, _lib.ptr(dist_c), _lib.ptr(q_c), _lib.ptr(w_c), total.data_ptr(),
+                                               td.data_ptr(), _stream(ref)), "pb_loss_combine")
+        ctx.B = B
+        ctx.has = (dist is not None, q is not None)
+        ctx.save_for_backward(w_c if w_c is not None else torch.empty(0, device=ref.device))
+        ctx.mark_non_differentiable(td)
+        return total, td
+
+    @staticmethod
+    def backward(ctx, g_total, _g_td):
+        (w,) = ctx.saved_tensors
+        row = (w / ctx.B) * g_total if w.numel() else torch.full((ctx.B,), 1.0 / ctx.B, device=g_total.device) * g_total
+        return (row if ctx.has[0] else None, row if ctx.has[1] else None, None)
+
+
+def loss_combine(dist_loss, q_loss, per_weights):
+    """total = mean(dist*w) + mean(q*w); td = 0.5 dist + 0.5 q | dist | |q|
+    (prism/agents/agent.py:58-64, prism/agents/models/composite_model.py:135-142)."""
+    return _LossCombine.apply(dist_loss, q_loss, per_weights)

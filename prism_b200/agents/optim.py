@@ -1,0 +1,144 @@
+"""FlatAdam -- clip_grad_norm_ + Adam over one flat fp32 parameter arena.
+
+Replaces ``torch.nn.utils.clip_grad_norm_`` + ``torch.optim.Adam.step`` of the reference update
+(prism/agents/agent.py:73-74; optimiser built at prism/factory/agent_factory.py:44-47) with two
+launches per step (csrc/agent_kernels.cu): a multi-tensor gather of autograd's gradients into the
+arena with the squared norm folded in, and one fused clip+Adam sweep.  All model parameters are
+re-pointed at views of the arena at construction, so
+  * the target-network sync is one device copy,
+  * the data-parallel gradient all-reduce is ONE NCCL call on the flat gradient.
+The step counter lives on the device: the whole step is CUDA-graph capturable.
+"""
+import torch
+
+from .. import _lib
+
+
+def flatten_parameters(module):
+    """Re-point every parameter of ``module`` at a view of one flat fp32 arena (16-byte aligned
+    slices, registration order).  Returns (arena, offsets); also stored as ``module._flat_arena`` /
+    ``module._flat_offsets``.  Two modules of the same architecture get identical layouts, which
+    makes the target-network sync a single copy."""
+    params = [p for p in module.parameters()]
+    dev = params[0].device
+    offsets, off = [], 0
+    for p in params:
+        offsets.append(off)
+        off += (p.numel() + 3) // 4 * 4
+    arena = torch.zeros(off, dtype=torch.float32, device=dev)
+    with torch.no_grad():
+        for p, o in zip(params, offsets):
+            view = arena[o:o + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+    module._flat_arena, module._flat_offsets = arena, offsets
+    return arena, offsets
+
+
+class FlatAdam(object):
+    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=0.0, arena=None):
+        self._lib = _lib.load()
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no parameters")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise _lib.PbError("FlatAdam needs CUDA parameters (no CPU path)")
+        self.device = dev
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.max_grad_norm = float(max_grad_norm) if max_grad_norm else 0.0
+        if arena is not None:
+            # parameters were already flattened (flatten_parameters): adopt that arena
+            self.arena, self.offsets = arena
+            off = self.arena.numel()
+            for p, o in zip(self.params, self.offsets):
+                if p.data_ptr() != self.arena.data_ptr() + 4 * o:
+                    raise _lib.PbError("parameter is not a view of the given arena")
+        else:
+            # arena layout: every tensor starts on a 16-byte boundary
+            self.offsets, off = [], 0
+            for p in self.params:
+                self.offsets.append(off)
+                off += (p.numel() + 3) // 4 * 4
+            self.arena = torch.zeros(off, dtype=torch.float32, device=dev)
+            with torch.no_grad():
+                for p, o in zip(self.params, self.offsets):
+                    view = self.arena[o:o + p.numel()].view_as(p)
+                    view.copy_(p.data)
+                    p.data = view
+        self.numel = off
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.partials = torch.zeros(4096, dtype=torch.float32, device=dev)
+        self.norm_out = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.table = torch.zeros(len(self.params) * 3, dtype=torch.int64, device=dev)
+        self._table_host = torch.zeros(len(self.params) * 3, dtype=torch.int64).pin_memory()
+        self._table_key = None
+        self.grad_scale = 1.0           # 1/world_size under data parallelism
+        self.allreduce = None           # callable(flat_grad) inserted between gather and Adam
+
+    # ---- torch.optim-like surface ------------------------------------------------------
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def refresh_grad_table(self):
+        """Re-read the addresses of autograd's gradient tensors (static under a CUDA graph)."""
+        key = tuple(0 if p.grad is None else p.grad.data_ptr() for p in self.params)
+        if key == self._table_key:
+            return
+        t = self._table_host
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            g = p.grad
+            if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
+                raise _lib.PbError("gradients must be contiguous fp32")
+            t[3 * i + 0] = 0 if g is None else g.data_ptr()
+            t[3 * i + 1] = o
+            t[3 * i + 2] = p.numel()
+        self.table.copy_(t, non_blocking=True)
+        self._table_key = key
+
+    def step(self, refresh_table=True):
+        if refresh_table:
+            self.refresh_grad_table()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        import ctypes
+        n_part = ctypes.c_int(0)
+        if self.allreduce is None:
+            _lib.check(self._lib.pb_pack_grads(len(self.params), self.table.data_ptr(), self.grad_scale,
+                                               self.grad.data_ptr(), self.partials.data_ptr(),
+                                               self.step_count.data_ptr(), ctypes.byref(n_part), stream),
+                       "pb_pack_grads")
+        else:
+            _lib.check(self._lib.pb_pack_grads(len(self.params), self.table.data_ptr(), self.grad_scale,
+                                               self.grad.data_ptr(), None, None, None, stream), "pb_pack_grads")
+            self.allreduce(self.grad)
+            _lib.check(self._lib.pb_grad_sumsq(self.numel, self.grad.data_ptr(), self.partials.data_ptr(),
+                                               self.step_count.data_ptr(), ctypes.byref(n_part), stream),
+                       "pb_grad_sumsq")
+        _lib.check(self._lib.pb_adam_clip_apply(self.numel, self.arena.data_ptr(), self.grad.data_ptr(),
+                                                self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                                self.step_count.data_ptr(), self.lr, self.betas[0], self.betas[1],
+                                                self.eps, self.max_grad_norm, self.partials.data_ptr(), n_part.value,
+                                                self.norm_out.data_ptr(), stream), "pb_adam_clip_apply")
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg.cpu(), "exp_avg_sq": self.exp_avg_sq.cpu(),
+                "step": self.step_count.cpu(), "lr": self.lr, "betas": self.betas, "eps": self.eps}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"]); self.step_count.copy_(sd["step"])
+        self.lr, self.betas, self.eps = sd["lr"], tuple(sd["betas"]), sd["eps"]
+
+    # ---- helpers -------------------------------------------------------------------------
+    def snapshot(self):
+        return (self.arena.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_count.clone())
+
+    def restore(self, snap):
+        self.arena.copy_(snap[0]); self.exp_avg.copy_(snap[1]); self.exp_avg_sq.copy_(snap[2])
+        self.step_count.copy_(snap[3])

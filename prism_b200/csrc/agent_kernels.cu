@@ -1,0 +1,498 @@
+// agent_kernels.cu -- fused warp-level kernels of the learner update and of acting (sm_100a).
+//
+//   pb_iqn_cos_basis   IQNModel._embed_quantiles basis      prism/agents/models/iqn_model.py:89-92
+//   pb_iqn_qh_loss     IQNModel.get_loss target+loss+grad   prism/agents/models/iqn_model.py:110-201
+//   pb_ens_q_loss      QEnsemble.get_loss (MSE, double-Q)   prism/agents/models/q_ensemble.py:50-92
+//   pb_ids_select      IDSActionSelector                    prism/agents/action_selectors.py:125-176
+//   pb_greedy_select   GreedyActionSelector                 prism/agents/action_selectors.py:70-82
+//   pb_loss_combine    PER-weighted total + new priorities  prism/agents/agent.py:58-66, composite_model.py:135-142
+//   pb_adam_clip_step  clip_grad_norm_ + Adam               prism/agents/agent.py:73-74, factory/agent_factory.py:44-47
+//
+// The reference runs each of these as 10-30 tiny ATen kernels (plus their autograd
+// mirrors) with B*T'*T temporaries; here each is one launch, one warp per batch row,
+// everything in registers/shared memory, forward and backward in the same pass.
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+using namespace pb;
+
+// ---------------------------------------------------------------------------------
+__global__ void cos_basis_kernel(long long n_rows, int n_basis, const float *__restrict__ tau,
+                                 float *__restrict__ out)
+{
+    const long long total = n_rows * n_basis;
+    const float pi = 3.14159265358979323846f;  // np.pi rounded to fp32, as torch does for a python scalar
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / n_basis;
+        const int i = (int)(e - r * n_basis);
+        // (tile(tau) * arange(1..n)) * pi, each product rounded to fp32 (iqn_model.py:90-91)
+        const float x = __fmul_rn(__fmul_rn(tau[r], (float)(i + 1)), pi);
+        out[e] = cosf(x);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// quantile-Huber loss: one warp per batch row.  smem per warp: y[Tp], theta[T], tq[T].
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) qh_loss_kernel(int B, int T, int Tp, int A, const float *__restrict__ z_cur,
+                                                      const float *__restrict__ tau,
+                                                      const float *__restrict__ z_next_online,
+                                                      const float *__restrict__ z_next_target,
+                                                      const long long *__restrict__ action,
+                                                      const float *__restrict__ ret, const float *__restrict__ gdn,
+                                                      float kappa, float loss_weight,
+                                                      const float *__restrict__ row_weight, float grad_scale,
+                                                      float *__restrict__ loss_out, float *__restrict__ grad_z)
+{
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int b = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= B) return;
+    float *y = smem + (size_t)warp * (Tp + 2 * T);
+    float *theta = y + Tp;
+    float *tq = theta + T;
+
+    // a* = argmax_a mean_j Z_online(s', tau'_j)[a]   (iqn_model.py:129-133), first index on ties
+    int best_a = 0;
+    float best_v = -INFINITY;
+    for (int a = 0; a < A; ++a) {
+        float acc = 0.0f;
+        for (int j = lane; j < Tp; j += 32) acc += z_next_online[((size_t)j * B + b) * A + a];
+        acc = warp_sum(acc) / (float)Tp;
+        if (acc > best_v) { best_v = acc; best_a = a; }
+    }
+    // y_j = R + gamma^k * nonterminal * Z_target(s', tau'_j)[a*]   (:136-145)
+    const float R = ret[b], g = gdn[b];
+    for (int j = lane; j < Tp; j += 32)
+        y[j] = __fadd_rn(R, __fmul_rn(z_next_target[((size_t)j * B + b) * A + best_a], g));
+    const int act = (int)action[b];
+    for (int i = lane; i < T; i += 32) {
+        theta[i] = z_cur[((size_t)i * B + b) * A + act];
+        tq[i] = tau[(size_t)i * B + b];
+    }
+    __syncwarp();
+
+    const float w_row = (row_weight ? row_weight[b] : 1.0f) * grad_scale * loss_weight / (float)Tp;
+    float loss_acc = 0.0f;
+    for (int i = lane; i < T; i += 32) {
+        const float th = theta[i], tqi = tq[i];
+        float li = 0.0f, gi = 0.0f;
+        for (int j = 0; j < Tp; ++j) {
+            const float d = y[j] - th;                           // (:171)
+            const float ad = fabsf(d);
+            const bool quad = ad <= kappa;                       // (:174-178)
+            const float hub = quad ? 0.5f * d * d : kappa * (ad - 0.5f * kappa);
+            const float dh = quad ? d : (d > 0.0f ? kappa : -kappa);
+            const float wq = fabsf(tqi - (d < 0.0f ? 1.0f : 0.0f));  // (:191-193)
+            li += wq * hub;
+            gi -= wq * dh;                                       // d/d theta = - d/d delta
+        }
+        loss_acc += li / kappa;
+        gi = gi / kappa * w_row;
+        float *grow = grad_z + ((size_t)i * B + b) * A;
+        for (int a = 0; a < A; ++a) grow[a] = (a == act) ? gi : 0.0f;
+    }
+    loss_acc = warp_sum(loss_acc);
+    if (lane == 0) loss_out[b] = loss_acc / (float)Tp * loss_weight;  // (:196-201)
+}
+
+// ---------------------------------------------------------------------------------
+// ensemble MSE loss: one warp per batch row, lanes over heads.  tables are [K][B][A].
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ens_loss_kernel(int B, int A, int K, const float *__restrict__ q_cur,
+                                                       const float *__restrict__ q_next_online,
+                                                       const float *__restrict__ q_next_target,
+                                                       const long long *__restrict__ action,
+                                                       const float *__restrict__ ret, const float *__restrict__ gdn,
+                                                       float loss_weight, const float *__restrict__ row_weight,
+                                                       float grad_scale, float *__restrict__ loss_out,
+                                                       float *__restrict__ grad_q)
+{
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int b = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= B) return;
+    const int act = (int)action[b];
+    const float R = ret[b], g = gdn[b];
+    const float gs = (row_weight ? row_weight[b] : 1.0f) * grad_scale * loss_weight * 2.0f / (float)K;
+    float acc = 0.0f;
+    for (int k = lane; k < K; k += 32) {
+        const size_t row = ((size_t)k * B + b) * A;
+        int best = 0;
+        float bv = q_next_online[row];
+        for (int a = 1; a < A; ++a) {
+            float v = q_next_online[row + a];
+            if (v > bv) { bv = v; best = a; }                    // argmax(dim=-2), first index (q_ensemble.py:70)
+        }
+        const float yk = __fadd_rn(R, __fmul_rn(q_next_target[row + best], g));  // (:80)
+        const float diff = q_cur[row + act] - yk;
+        acc += diff * diff;                                      // MSELoss(reduction='none') (:84)
+        for (int a = 0; a < A; ++a) grad_q[row + a] = (a == act) ? gs * diff : 0.0f;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) loss_out[b] = acc / (float)K * loss_weight;
+}
+
+// ---------------------------------------------------------------------------------
+// IDS: one warp per state, lane = action (A <= 32).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ids_select_kernel(int N, int A, int K, int Nq, const float *__restrict__ q,
+                                                         const float *__restrict__ z, float lambda, float eps,
+                                                         float rho_lb, long long *__restrict__ action_out,
+                                                         float *__restrict__ scores_out)
+{
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int n = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (n >= N) return;
+    const bool on = lane < A;
+    // mean / unbiased std over heads (action_selectors.py:132-135; "variance" is std, "std" is sqrt(std))
+    double mu = 0.0;
+    if (on) for (int k = 0; k < K; ++k) mu += (double)q[((size_t)k * N + n) * A + lane];
+    mu /= (double)K;
+    double ss = 0.0;
+    if (on) for (int k = 0; k < K; ++k) { double d = (double)q[((size_t)k * N + n) * A + lane] - mu; ss += d * d; }
+    const float mean = (float)mu;
+    const float s1 = (float)sqrt(ss / (double)(K - 1));          // torch.std (unbiased); K==1 -> nan like torch
+    const float s2 = sqrtf(s1);
+    // regret (:137-139)
+    float ub = on ? mean + lambda * s2 : -INFINITY;
+    const float best = warp_max(ub);
+    float regret = best - (mean - lambda * s2);
+    const float regret_sq = regret * regret;
+    // unbiased variance of the return distribution over quantile samples (:141)
+    double zm = 0.0;
+    if (on) for (int j = 0; j < Nq; ++j) zm += (double)z[((size_t)j * N + n) * A + lane];
+    zm /= (double)Nq;
+    double zs = 0.0;
+    if (on) for (int j = 0; j < Nq; ++j) { double d = (double)z[((size_t)j * N + n) * A + lane] - zm; zs += d * d; }
+    const float var_z = (float)(zs / (double)(Nq - 1));
+    const float mean_var = warp_sum(on ? var_z : 0.0f) / (float)A;
+    const float normalized = var_z / (eps + mean_var);           // (:142)
+    const float rho = fmaxf(normalized, rho_lb);                 // (:143)
+    const float info_gain = logf(1.0f + s1 / rho) + eps;         // (:146)
+    float score = regret_sq / info_gain;                         // (:148)
+    if (scores_out && on) scores_out[(size_t)n * A + lane] = score;
+    // argmin, first index on ties; NaN never wins (torch.argmin would pick a NaN: flagged in DESIGN.md)
+    float bs = on ? score : INFINITY;
+    int bi = on ? lane : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float os = __shfl_xor_sync(FULL, bs, o);
+        int oi = __shfl_xor_sync(FULL, bi, o);
+        if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+    }
+    if (lane == 0) action_out[n] = (bi == 0x7fffffff) ? 0 : bi;
+}
+
+__global__ void __launch_bounds__(128) greedy_select_kernel(int N, int A, int K, const float *__restrict__ q,
+                                                            long long *__restrict__ action_out)
+{
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int n = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (n >= N) return;
+    const bool on = lane < A;
+    float acc = 0.0f;
+    if (on) for (int k = 0; k < K; ++k) acc += q[((size_t)k * N + n) * A + lane];
+    float bs = on ? acc / (float)K : -INFINITY;
+    int bi = on ? lane : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float os = __shfl_xor_sync(FULL, bs, o);
+        int oi = __shfl_xor_sync(FULL, bi, o);
+        if (os > bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+    }
+    if (lane == 0) action_out[n] = (bi == 0x7fffffff) ? 0 : bi;
+}
+
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) loss_combine_kernel(int B, const float *__restrict__ dist,
+                                                            const float *__restrict__ q, const float *__restrict__ w,
+                                                            float *__restrict__ total_out, float *__restrict__ td_out)
+{
+    __shared__ float part[32];
+    float acc = 0.0f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const float wb = w ? w[b] : 1.0f;
+        const float d = dist ? dist[b] : 0.0f, qq = q ? q[b] : 0.0f;
+        acc += d * wb + qq * wb;
+        if (td_out) td_out[b] = (dist && q) ? (d * 0.5f + qq * 0.5f) : (dist ? d : fabsf(qq));
+    }
+    acc = warp_sum(acc);
+    if (lane_id() == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0 && total_out) *total_out = v / (float)B;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// clip_grad_norm_ + Adam over one flat arena.  Kernel 1: per-CTA partial sum of squares
+// (fp64 accumulate of fp32 squares is overkill; fp32 per thread, fp64 across), step++.
+// Kernel 2: every CTA re-reduces the <=1024 partials, derives the clip coefficient and
+// applies the update with 128-bit accesses.
+// ---------------------------------------------------------------------------------
+constexpr int ADAM_THREADS = 256;
+constexpr int ADAM_MAX_PARTIALS = 4096;
+constexpr int PACK_BLOCKS_PER_TENSOR = 16;
+
+// multi-tensor gather of autograd's per-parameter gradients into the flat arena (scaled), with the
+// sum of squares of the scaled values folded in.  table[t] = {grad pointer, arena offset, numel}.
+__global__ void __launch_bounds__(ADAM_THREADS) pack_grads_kernel(const long long *__restrict__ table, float scale,
+                                                                  float *__restrict__ flat,
+                                                                  float *__restrict__ partial,
+                                                                  long long *__restrict__ step_count)
+{
+    __shared__ double part[ADAM_THREADS / 32];
+    const int t = blockIdx.y;
+    const float *__restrict__ src = reinterpret_cast<const float *>(table[3 * t + 0]);
+    float *__restrict__ dst = flat + table[3 * t + 1];
+    const long long n = table[3 * t + 2];
+    double acc = 0.0;
+    if (src != nullptr) {
+        const bool vec = ((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0;
+        const long long n4 = vec ? (n >> 2) : 0;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+            float4 v = reinterpret_cast<const float4 *>(src)[i];
+            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+            reinterpret_cast<float4 *>(dst)[i] = v;
+            acc += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+        }
+        for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+             i += (long long)gridDim.x * blockDim.x) {
+            float v = src[i] * scale;
+            dst[i] = v;
+            acc += (double)v * (double)v;
+        }
+    } else {
+        // parameter that received no gradient this step: zero its slice
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+            dst[i] = 0.0f;
+    }
+    acc = warp_sum(acc);
+    if (lane_id() == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int k = 0; k < ADAM_THREADS / 32; ++k) tot += part[k];
+        if (partial) partial[blockIdx.y * gridDim.x + blockIdx.x] = (float)tot;
+        if (blockIdx.x == 0 && blockIdx.y == 0 && step_count) *step_count += 1;
+    }
+}
+
+__global__ void __launch_bounds__(ADAM_THREADS) grad_sumsq_kernel(long long n, const float *__restrict__ grad,
+                                                                  float *__restrict__ partial,
+                                                                  long long *__restrict__ step_count)
+{
+    __shared__ double part[ADAM_THREADS / 32];
+    double acc = 0.0;
+    const long long n4 = n >> 2;
+    const float4 *g4 = reinterpret_cast<const float4 *>(grad);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = g4[i];
+        acc += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+    }
+    if (blockIdx.x == 0)
+        for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) acc += (double)grad[i] * (double)grad[i];
+    acc = warp_sum(acc);
+    if (lane_id() == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < ADAM_THREADS / 32; ++k) t += part[k];
+        partial[blockIdx.x] = (float)t;
+        if (blockIdx.x == 0 && step_count) *step_count += 1;
+    }
+}
+
+__global__ void __launch_bounds__(ADAM_THREADS) adam_clip_kernel(long long n, float *__restrict__ param,
+                                                                 const float *__restrict__ grad,
+                                                                 float *__restrict__ exp_avg,
+                                                                 float *__restrict__ exp_avg_sq,
+                                                                 const long long *__restrict__ step_count, float lr,
+                                                                 float beta1, float beta2, float adam_eps,
+                                                                 float max_grad_norm, const float *__restrict__ partial,
+                                                                 int n_partials, float *__restrict__ norm_out)
+{
+    __shared__ double red[ADAM_THREADS / 32];
+    __shared__ float s_coef;
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < n_partials; k += blockDim.x) acc += (double)partial[k];
+    acc = warp_sum(acc);
+    if (lane_id() == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < ADAM_THREADS / 32; ++k) t += red[k];
+        const float total_norm = (float)sqrt(t);
+        // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
+        float coef = max_grad_norm / (total_norm + 1e-6f);
+        coef = coef > 1.0f ? 1.0f : coef;
+        if (!(max_grad_norm > 0.0f)) coef = 1.0f;
+        s_coef = coef;
+        if (blockIdx.x == 0 && norm_out) { norm_out[0] = total_norm; norm_out[1] = coef; }
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    const double step = (double)(*step_count);
+    const float bc1 = (float)(1.0 - pow((double)beta1, step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
+    const float step_size = lr / bc1;
+    auto upd = [&](float &p, float g, float &m, float &v) {
+        g *= coef;
+        m = m + (g - m) * (1.0f - beta1);                        // exp_avg.lerp_(grad, 1-beta1)
+        v = v * beta2 + (1.0f - beta2) * g * g;                  // mul_(beta2).addcmul_(g, g, 1-beta2)
+        const float denom = sqrtf(v) / bc2_sqrt + adam_eps;
+        p = p - step_size * (m / denom);                         // addcdiv_(exp_avg, denom, -step_size)
+    };
+    const long long n4 = n >> 2;
+    float4 *p4 = reinterpret_cast<float4 *>(param);
+    const float4 *g4 = reinterpret_cast<const float4 *>(grad);
+    float4 *m4 = reinterpret_cast<float4 *>(exp_avg);
+    float4 *v4 = reinterpret_cast<float4 *>(exp_avg_sq);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 p = p4[i], g = g4[i], m = m4[i], v = v4[i];
+        upd(p.x, g.x, m.x, v.x); upd(p.y, g.y, m.y, v.y); upd(p.z, g.z, m.z, v.z); upd(p.w, g.w, m.w, v.w);
+        p4[i] = p; m4[i] = m; v4[i] = v;
+    }
+    if (blockIdx.x == 0)
+        for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x)
+            upd(param[i], grad[i], exp_avg[i], exp_avg_sq[i]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pb_iqn_cos_basis(long long n_rows, int n_basis, const float *tau, float *out, void *stream)
+{
+    if (n_rows < 0 || n_basis <= 0) return PB_E_ARG;
+    if (n_rows == 0) return PB_OK;
+    if (!tau || !out) return PB_E_ARG;
+    const long long total = n_rows * n_basis;
+    long long nb = (total + 255) / 256;
+    const long long cap = (long long)pb_sm_count() * 16;
+    if (nb > cap) nb = cap;
+    PB_LAUNCH(cos_basis_kernel, (unsigned)nb, 256, 0, stream, n_rows, n_basis, tau, out);
+    return PB_OK;
+}
+
+int pb_iqn_qh_loss(int B, int T, int Tp, int A, const float *z_cur, const float *tau, const float *z_next_online,
+                   const float *z_next_target, const long long *action, const float *ret, const float *gdn,
+                   float kappa, float loss_weight, const float *row_weight, float grad_scale, float *loss_out,
+                   float *grad_z_cur, void *stream)
+{
+    if (B < 0 || T <= 0 || Tp <= 0 || A <= 0 || !(kappa > 0.0f)) return PB_E_ARG;
+    if (B == 0) return PB_OK;
+    if (!z_cur || !tau || !z_next_online || !z_next_target || !action || !ret || !gdn || !loss_out || !grad_z_cur)
+        return PB_E_ARG;
+    const int warps = 4;
+    const size_t smem = sizeof(float) * warps * (size_t)(Tp + 2 * T);
+    if (smem > 48 * 1024) return PB_E_UNSUPPORTED;
+    PB_LAUNCH(qh_loss_kernel, (unsigned)((B + warps - 1) / warps), warps * 32, smem, stream, B, T, Tp, A, z_cur, tau,
+              z_next_online, z_next_target, action, ret, gdn, kappa, loss_weight, row_weight, grad_scale, loss_out,
+              grad_z_cur);
+    return PB_OK;
+}
+
+int pb_ens_q_loss(int B, int A, int K, const float *q_cur, const float *q_next_online, const float *q_next_target,
+                  const long long *action, const float *ret, const float *gdn, float loss_weight,
+                  const float *row_weight, float grad_scale, float *loss_out, float *grad_q_cur, void *stream)
+{
+    if (B < 0 || A <= 0 || K <= 0) return PB_E_ARG;
+    if (B == 0) return PB_OK;
+    if (!q_cur || !q_next_online || !q_next_target || !action || !ret || !gdn || !loss_out || !grad_q_cur)
+        return PB_E_ARG;
+    PB_LAUNCH(ens_loss_kernel, (unsigned)((B + 3) / 4), 128, 0, stream, B, A, K, q_cur, q_next_online, q_next_target,
+              action, ret, gdn, loss_weight, row_weight, grad_scale, loss_out, grad_q_cur);
+    return PB_OK;
+}
+
+int pb_ids_select(int N, int A, int K, int Nq, const float *q, const float *z, float lambda, float eps,
+                  float rho_lower_bound, long long *action_out, float *scores_out, void *stream)
+{
+    if (N < 0 || A <= 0 || K <= 0 || Nq <= 0) return PB_E_ARG;
+    if (A > 32) return PB_E_UNSUPPORTED;
+    if (N == 0) return PB_OK;
+    if (!q || !z || !action_out) return PB_E_ARG;
+    PB_LAUNCH(ids_select_kernel, (unsigned)((N + 3) / 4), 128, 0, stream, N, A, K, Nq, q, z, lambda, eps,
+              rho_lower_bound, action_out, scores_out);
+    return PB_OK;
+}
+
+int pb_greedy_select(int N, int A, int K, const float *q, long long *action_out, void *stream)
+{
+    if (N < 0 || A <= 0 || K <= 0) return PB_E_ARG;
+    if (A > 32) return PB_E_UNSUPPORTED;
+    if (N == 0) return PB_OK;
+    if (!q || !action_out) return PB_E_ARG;
+    PB_LAUNCH(greedy_select_kernel, (unsigned)((N + 3) / 4), 128, 0, stream, N, A, K, q, action_out);
+    return PB_OK;
+}
+
+int pb_loss_combine(int B, const float *dist, const float *q, const float *w, float *total_out, float *td_out,
+                    void *stream)
+{
+    if (B <= 0 || (!dist && !q)) return PB_E_ARG;
+    PB_LAUNCH(loss_combine_kernel, 1, 1024, 0, stream, B, dist, q, w, total_out, td_out);
+    return PB_OK;
+}
+
+int pb_pack_grads(int n_tensors, const long long *table, float scale, float *flat, float *partial_scratch,
+                  long long *step_count, int *n_partials_out_h, void *stream)
+{
+    if (n_tensors <= 0 || !table || !flat) return PB_E_ARG;
+    if ((long long)n_tensors * PACK_BLOCKS_PER_TENSOR > ADAM_MAX_PARTIALS) return PB_E_UNSUPPORTED;
+    dim3 grid(PACK_BLOCKS_PER_TENSOR, (unsigned)n_tensors);
+    PB_LAUNCH(pack_grads_kernel, grid, ADAM_THREADS, 0, stream, table, scale, flat, partial_scratch, step_count);
+    if (n_partials_out_h) *n_partials_out_h = n_tensors * PACK_BLOCKS_PER_TENSOR;
+    return PB_OK;
+}
+
+int pb_grad_sumsq(long long n, const float *grad, float *partial_scratch, long long *step_count,
+                  int *n_partials_out_h, void *stream)
+{
+    if (n <= 0 || !grad || !partial_scratch) return PB_E_ARG;
+    if (((uintptr_t)grad) & 15) return PB_E_ARG;
+    long long nb = ((n >> 2) + ADAM_THREADS - 1) / ADAM_THREADS;
+    if (nb < 1) nb = 1;
+    const long long cap = (long long)pb_sm_count() * 4;
+    if (nb > cap) nb = cap;
+    if (nb > ADAM_MAX_PARTIALS) nb = ADAM_MAX_PARTIALS;
+    PB_LAUNCH(grad_sumsq_kernel, (unsigned)nb, ADAM_THREADS, 0, stream, n, grad, partial_scratch, step_count);
+    if (n_partials_out_h) *n_partials_out_h = (int)nb;
+    return PB_OK;
+}
+
+int pb_adam_clip_apply(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
+                       const long long *step_count, float lr, float beta1, float beta2, float adam_eps,
+                       float max_grad_norm, const float *partial_scratch, int n_partials, float *norm_out,
+                       void *stream)
+{
+    if (n <= 0 || !param || !grad || !exp_avg || !exp_avg_sq || !step_count || !partial_scratch) return PB_E_ARG;
+    if (n_partials <= 0 || n_partials > ADAM_MAX_PARTIALS) return PB_E_ARG;
+    if ((((uintptr_t)param) | ((uintptr_t)grad) | ((uintptr_t)exp_avg) | ((uintptr_t)exp_avg_sq)) & 15) return PB_E_ARG;
+    long long nb = ((n >> 2) + ADAM_THREADS - 1) / ADAM_THREADS;
+    if (nb < 1) nb = 1;
+    const long long cap = (long long)pb_sm_count() * 4;
+    if (nb > cap) nb = cap;
+    PB_LAUNCH(adam_clip_kernel, (unsigned)nb, ADAM_THREADS, 0, stream, n, param, grad, exp_avg, exp_avg_sq, step_count,
+              lr, beta1, beta2, adam_eps, max_grad_norm, partial_scratch, n_partials, norm_out);
+    return PB_OK;
+}
+
+int pb_adam_clip_step(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
+                      long long *step_count, float lr, float beta1, float beta2, float adam_eps,
+                      float max_grad_norm, float *norm_out, float *partial_scratch, void *stream)
+{
+    int n_partials = 0;
+    int rc = pb_grad_sumsq(n, grad, partial_scratch, step_count, &n_partials, stream);
+    if (rc) return rc;
+    return pb_adam_clip_apply(n, param, grad, exp_avg, exp_avg_sq, step_count, lr, beta1, beta2, adam_eps,
+                              max_grad_norm, partial_scratch, n_partials, norm_out, stream);
+}
+
+}  // extern "C"

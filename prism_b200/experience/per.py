@@ -1,0 +1,184 @@
+"""Device-resident prioritized-replay priority store (sum-tree + min-tree).
+
+Stands in for the sampler half of torchrl's ``PrioritizedReplayBuffer`` that the reference
+builds at prism/factory/exp_buffer_factory.py:22-28 and drives from
+prism/experience/timestep_buffer.py:33,37,54 and prism/learner.py:100-107,119-120.
+All arithmetic runs in libprism_b200 (csrc/per_tree.cu); this class only owns the
+tensors and forwards raw pointers.  There is no CPU path.
+"""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+
+
+def _pow2_ceil(n):
+    c = 1
+    while c < n:
+        c <<= 1
+    return c
+
+
+class PrioritizedTree:
+    """Sum/min segment trees over ``size`` slots, level-ordered fp32 arrays in HBM.
+
+    Attribute names follow torchrl's PrioritizedSampler where the reference pokes at
+    them (``_beta`` is written by prism/learner.py:107; ``_alpha``, ``_eps``).
+    """
+
+    MODE_IID = 0          # torchrl: mass ~ U(0, p_sum) iid
+    MODE_STRATIFIED = 1   # north star: mass_k = (k + u_k)/B * p_sum
+
+    def __init__(self, size, alpha=0.5, beta=0.5, eps=1e-8, device="cuda:0", mode="iid",
+                 weight_eps_in_denominator=False, default_priority_fp64=True):
+        self._lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.PbError("PrioritizedTree needs a CUDA device (no CPU fallback); got %s" % device)
+        self.size = int(size)
+        if self.size <= 0:
+            raise ValueError("size must be positive")
+        self.capacity = max(32, _pow2_ceil(self.size))
+        self._alpha = float(alpha)
+        self._beta = float(beta)
+        self._eps = float(eps)
+        self.mode = self.MODE_STRATIFIED if mode in ("stratified", 1) else self.MODE_IID
+        self.sum = torch.empty(2 * self.capacity, dtype=torch.float32, device=self.device)
+        self.min = torch.empty(2 * self.capacity, dtype=torch.float32, device=self.device)
+        self.owner = torch.empty(self.capacity, dtype=torch.int32, device=self.device)
+        self.state = torch.zeros(64, dtype=torch.uint8, device=self.device)
+        self._c = _lib.pb_tree(
+            sum=self.sum.data_ptr(), min=self.min.data_ptr(), owner=self.owner.data_ptr(),
+            state=self.state.data_ptr(), capacity=self.capacity, size=self.size,
+            alpha=self._alpha, eps_f32=self._eps, eps_f64=self._eps,
+            weight_eps_in_denominator=int(bool(weight_eps_in_denominator)),
+            default_priority_fp64=int(bool(default_priority_fp64)))
+        self._ref = C.byref(self._c)
+        self.reset()
+
+    # -- helpers -----------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _i64(self, t):
+        t = torch.as_tensor(t)
+        if t.device != self.device or t.dtype != torch.int64 or not t.is_contiguous():
+            t = t.to(device=self.device, dtype=torch.int64, non_blocking=True).contiguous()
+        return t.view(-1)
+
+    def _f32(self, t):
+        t = torch.as_tensor(t)
+        if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        return t.view(-1)
+
+    # -- mutation ----------------------------------------------------------------
+    def reset(self):
+        _lib.check(self._lib.pb_tree_init(self._ref, self._stream()), "pb_tree_init")
+
+    def build(self, leaves):
+        """Bulk-load post-pow fp32 leaves for slots [0, n) and rebuild every node."""
+        leaves = self._f32(leaves)
+        _lib.check(self._lib.pb_tree_build(self._ref, leaves.data_ptr(), leaves.numel(), self._stream()),
+                   "pb_tree_build")
+
+    def extend(self, n, idx_out=None):
+        """n new slots at the ring cursor get the default priority (max_priority+eps)^alpha."""
+        if idx_out is not None:
+            assert idx_out.dtype == torch.int64 and idx_out.is_cuda and idx_out.numel() >= n
+        _lib.check(self._lib.pb_tree_extend(self._ref, int(n), _lib.ptr(idx_out), self._stream()),
+                   "pb_tree_extend")
+
+    def update_priority(self, index, priority, sorted=False):
+        index = self._i64(index)
+        priority = self._f32(priority)
+        assert index.numel() == priority.numel()
+        _lib.check(self._lib.pb_tree_update_priority(self._ref, index.numel(), index.data_ptr(),
+                                                     priority.data_ptr(), int(bool(sorted)), self._stream()),
+                   "pb_tree_update_priority")
+
+    def set_leaves(self, index, leaves, sorted=False):
+        index = self._i64(index)
+        leaves = self._f32(leaves)
+        assert index.numel() == leaves.numel()
+        _lib.check(self._lib.pb_tree_set_leaves(self._ref, index.numel(), index.data_ptr(), leaves.data_ptr(),
+                                                int(bool(sorted)), self._stream()), "pb_tree_set_leaves")
+
+    def refresh_stats(self):
+        _lib.check(self._lib.pb_tree_stats(self._ref, self._stream()), "pb_tree_stats")
+
+    # -- sampling ----------------------------------------------------------------
+    def scan(self, mass, out=None):
+        mass = self._f32(mass)
+        if out is None:
+            out = torch.empty(mass.numel(), dtype=torch.int64, device=self.device)
+        _lib.check(self._lib.pb_tree_scan(self._ref, mass.numel(), mass.data_ptr(), out.data_ptr(),
+                                          self._stream()), "pb_tree_scan")
+        return out
+
+    def sample(self, n, u=None, mode=None, beta=None, idx_out=None, weight_out=None, mass_out=None):
+        """Draw n indices.  ``u``: fp64 uniforms in [0,1) (device); drawn with the device
+        Philox generator when omitted."""
+        n = int(n)
+        if u is None:
+            u = torch.rand(n, dtype=torch.float64, device=self.device)
+        else:
+            u = torch.as_tensor(u)
+            if u.device != self.device or u.dtype != torch.float64 or not u.is_contiguous():
+                u = u.to(device=self.device, dtype=torch.float64, non_blocking=True).contiguous()
+        if idx_out is None:
+            idx_out = torch.empty(n, dtype=torch.int64, device=self.device)
+        if weight_out is None:
+            weight_out = torch.empty(n, dtype=torch.float32, device=self.device)
+        mode = self.mode if mode is None else (self.MODE_STRATIFIED if mode in ("stratified", 1) else self.MODE_IID)
+        beta = self._beta if beta is None else float(beta)
+        _lib.check(self._lib.pb_tree_sample(self._ref, n, u.data_ptr(), mode, beta, idx_out.data_ptr(),
+                                            weight_out.data_ptr(), _lib.ptr(mass_out), self._stream()),
+                   "pb_tree_sample")
+        return idx_out, weight_out
+
+    def sample_global(self, n_ranks, rank, all_psum, all_pmin, all_len, n_global, u, beta=None,
+                      idx_out=None, weight_out=None, stratum_out=None):
+        """Sharded global stratified sampling: every rank evaluates all strata and keeps its run."""
+        n_global = int(n_global)
+        if idx_out is None:
+            idx_out = torch.empty(n_global, dtype=torch.int64, device=self.device)
+        if weight_out is None:
+            weight_out = torch.empty(n_global, dtype=torch.float32, device=self.device)
+        beta = self._beta if beta is None else float(beta)
+        assert all_psum.dtype == torch.float32 and all_pmin.dtype == torch.float32 and all_len.dtype == torch.int64
+        assert u.dtype == torch.float64 and u.is_cuda
+        _lib.check(self._lib.pb_tree_sample_global(self._ref, int(n_ranks), int(rank), all_psum.data_ptr(),
+                                                   all_pmin.data_ptr(), all_len.data_ptr(), n_global, u.data_ptr(),
+                                                   beta, idx_out.data_ptr(), weight_out.data_ptr(),
+                                                   _lib.ptr(stratum_out), self._stream()), "pb_tree_sample_global")
+        return idx_out, weight_out
+
+    # -- host-visible state (synchronises; not on the hot path) -------------------
+    def state_host(self):
+        raw = self.state.cpu().numpy().tobytes()
+        s = _lib.pb_per_state.from_buffer_copy(raw)
+        return {"len": s.len, "seq": s.seq, "max_priority": s.max_priority, "p_sum": s.p_sum, "p_min": s.p_min,
+                "status": s.status, "owned_lo": s.owned_lo, "owned_n": s.owned_n}
+
+    def stats_tensor(self):
+        """{p_sum, p_min} as a 2-float device view of the state block (feeds the all-gather)."""
+        return self.state.view(torch.float32)[5:7]
+
+    def len_tensor(self):
+        return self.state.view(torch.int64)[0:1]
+
+    @property
+    def _max_priority(self):
+        return self.state_host()["max_priority"]
+
+    def state_dict(self):
+        return {"sum": self.sum.cpu(), "min": self.min.cpu(), "state": self.state.cpu(), "size": self.size,
+                "alpha": self._alpha, "beta": self._beta, "eps": self._eps}
+
+    def load_state_dict(self, sd):
+        assert sd["size"] == self.size
+        self.sum.copy_(sd["sum"]); self.min.copy_(sd["min"]); self.state.copy_(sd["state"])
+        self.owner.fill_(-1)
+        self._beta = sd["beta"]

@@ -1,0 +1,266 @@
+"""Device-resident transition ring (struct-of-arrays) with pinned-host ingest staging.
+
+Replaces the reference's ``ListStorage`` of linked ``Timestep`` objects
+(prism/experience/timestep.py:12-28; links built at
+multiprocessing_experience_collection/collector_process_interface.py:146-173) and the
+Python batch loop of prism/experience/timestep_buffer.py:79-257.  Kernels: csrc/store.cu.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+STEP_DONE, STEP_TRUNC, STEP_NO_NEXT = 1, 2, 4
+
+
+class TransitionRing:
+    def __init__(self, size, obs_shape, frame_stack=1, n_step=3, gamma=0.99, storage_dtype=torch.float32,
+                 obs_scale=False, max_streams=256, trunc_pool=None, staging_rows=256, device="cuda:0"):
+        self._lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.PbError("TransitionRing needs a CUDA device (no CPU fallback); got %s" % device)
+        self.size = int(size)
+        self.obs_shape = tuple(int(s) for s in obs_shape)
+        self.obs_elems = int(np.prod(self.obs_shape)) if len(self.obs_shape) else 1
+        self.frame_stack = int(frame_stack)
+        self.n_step = int(n_step)
+        self.gamma = float(gamma)
+        if storage_dtype not in (torch.float32, torch.uint8):
+            raise ValueError("storage_dtype must be float32 or uint8")
+        self.storage_dtype = storage_dtype
+        self.obs_scale = bool(obs_scale)
+        self.max_streams = int(max_streams)
+        pool = int(trunc_pool) if trunc_pool is not None else max(64, self.size // 64)
+        self.aux_size = self.max_streams + pool
+        self.staging_rows = int(min(staging_rows, self.size))
+        d = self.device
+        self.obs = torch.zeros((self.size, self.obs_elems), dtype=storage_dtype, device=d)
+        self.aux_obs = torch.zeros((self.aux_size, self.obs_elems), dtype=storage_dtype, device=d)
+        self.action = torch.zeros(self.size, dtype=torch.int32, device=d)
+        self.reward = torch.zeros(self.size, dtype=torch.float32, device=d)
+        self.done = torch.zeros(self.size, dtype=torch.uint8, device=d)
+        self.trunc = torch.zeros(self.size, dtype=torch.uint8, device=d)
+        self.slot_seq = torch.full((self.size,), -1, dtype=torch.int64, device=d)
+        self.next_link = torch.full((self.size,), -1, dtype=torch.int64, device=d)
+        self.prev_link = torch.full((self.size,), -1, dtype=torch.int64, device=d)
+        self._make_desc()
+        # host-side planner state (mirrors what the collector knows about its streams)
+        self.seq = 0
+        self.stream_last = np.full(self.max_streams, -1, dtype=np.int64)
+        self.trunc_cursor = np.zeros(1, dtype=np.int64)
+        self.trunc_owner = np.full(pool, -1, dtype=np.int64)
+        self._alloc_staging()
+
+    # ---------------------------------------------------------------------------
+    def _make_desc(self):
+        self._c = _lib.pb_store(
+            obs=self.obs.data_ptr(), aux_obs=self.aux_obs.data_ptr(), action=self.action.data_ptr(),
+            reward=self.reward.data_ptr(), done=self.done.data_ptr(), trunc=self.trunc.data_ptr(),
+            slot_seq=self.slot_seq.data_ptr(), next_link=self.next_link.data_ptr(),
+            prev_link=self.prev_link.data_ptr(), size=self.size, aux_size=self.aux_size,
+            obs_elems=self.obs_elems, obs_dtype=0 if self.storage_dtype == torch.float32 else 1,
+            obs_scale=int(self.obs_scale), frame_stack=self.frame_stack, n_step=self.n_step, pad=0,
+            gamma=self.gamma)
+        self._ref = C.byref(self._c)
+
+    def _alloc_staging(self):
+        S = self.staging_rows
+        # rows: [2][S][obs_elems] pinned + device mirror; meta: one packed byte block
+        self.h_rows = torch.zeros((2, S, self.obs_elems), dtype=self.storage_dtype).pin_memory()
+        self.d_rows = torch.zeros((2, S, self.obs_elems), dtype=self.storage_dtype, device=self.device)
+        off = 0
+        self._meta_off = {}
+        for name, width in (("seq", 8), ("prev", 8), ("next", 8), ("aux", 8), ("pslot", 8), ("pval", 8),
+                            ("reward", 4), ("action", 4), ("done", 1), ("trunc", 1)):
+            self._meta_off[name] = off
+            off += ((S * width + 15) // 16) * 16
+        self.h_meta = torch.zeros(off, dtype=torch.uint8).pin_memory()
+        self.d_meta = torch.zeros(off, dtype=torch.uint8, device=self.device)
+        hm = self.h_meta.numpy()
+        o = self._meta_off
+
+        def view(name, dtype):
+            return hm[o[name]:o[name] + S * np.dtype(dtype).itemsize].view(dtype)
+
+        self.m_seq, self.m_prev, self.m_next = view("seq", np.int64), view("prev", np.int64), view("next", np.int64)
+        self.m_aux, self.m_pslot, self.m_pval = view("aux", np.int64), view("pslot", np.int64), view("pval", np.int64)
+        self.m_reward, self.m_action = view("reward", np.float32), view("action", np.int32)
+        self.m_done, self.m_trunc = view("done", np.uint8), view("trunc", np.uint8)
+        self.h_rows_np = self.h_rows.numpy()
+        self.m_stream = np.zeros(S, dtype=np.int32)
+        self.m_flags = np.zeros(S, dtype=np.uint8)
+        self.n_staged = 0
+
+    def _dmeta(self, name):
+        return self.d_meta.data_ptr() + self._meta_off[name]
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def __len__(self):
+        return min(self.seq, self.size)
+
+    # ---------------------------------------------------------------------------
+    def stage(self, stream_id, obs, action, reward, done, trunc, next_obs):
+        """Stage ONE step on the pinned host block (no device work).  Returns True when
+        the staging block is full and must be flushed."""
+        j = self.n_staged
+        if j == 0:
+            self.wait_staging()
+        row = self.h_rows_np[0, j]
+        row[...] = np.asarray(obs, dtype=row.dtype).reshape(-1)
+        flags = (STEP_DONE if done else 0) | (STEP_TRUNC if trunc else 0)
+        if next_obs is None:
+            if not done:
+                flags |= STEP_NO_NEXT
+        else:
+            nrow = self.h_rows_np[1, j]
+            nrow[...] = np.asarray(next_obs, dtype=nrow.dtype).reshape(-1)
+        self.m_stream[j] = stream_id
+        self.m_flags[j] = flags
+        self.m_action[j] = int(action)
+        self.m_reward[j] = float(reward)
+        self.m_done[j] = 1 if done else 0
+        self.m_trunc[j] = 1 if trunc else 0
+        self.n_staged = j + 1
+        return self.n_staged >= self.staging_rows
+
+    def stage_batch(self, stream_ids, obs, action, reward, done, trunc, next_obs):
+        """Stage up to staging_rows steps at once from host arrays; returns how many were taken."""
+        j = self.n_staged
+        n = min(len(stream_ids), self.staging_rows - j)
+        if n <= 0:
+            return 0
+        if j == 0:
+            self.wait_staging()
+        sl = slice(j, j + n)
+        self.h_rows_np[0, sl] = np.asarray(obs[:n]).reshape(n, -1)
+        self.h_rows_np[1, sl] = np.asarray(next_obs[:n]).reshape(n, -1)
+        d = np.asarray(done[:n]).astype(np.uint8)
+        t = np.asarray(trunc[:n]).astype(np.uint8)
+        self.m_stream[sl] = stream_ids[:n]
+        self.m_flags[sl] = d * STEP_DONE + t * STEP_TRUNC
+        self.m_action[sl] = action[:n]
+        self.m_reward[sl] = reward[:n]
+        self.m_done[sl] = d
+        self.m_trunc[sl] = t
+        self.n_staged = j + n
+        return n
+
+    def flush(self):
+        """Plan links on the host, copy the staged block host->device (3 async copies from
+        pinned memory) and scatter it into the ring.  Returns the number of steps written."""
+        n = self.n_staged
+        if n == 0:
+            return 0
+        while True:
+            rc = self._lib.pb_store_extend_plan(
+                self.size, self.aux_size, self.max_streams, n, self.seq, self.m_stream.ctypes.data,
+                self.m_flags.ctypes.data, self.stream_last.ctypes.data, self.trunc_cursor.ctypes.data,
+                self.trunc_owner.ctypes.data, self.m_seq.ctypes.data, self.m_prev.ctypes.data,
+                self.m_next.ctypes.data, self.m_aux.ctypes.data, self.m_pslot.ctypes.data, self.m_pval.ctypes.data)
+            if rc == _lib.PB_E_POOL:
+                self._grow_trunc_pool()
+                continue
+            _lib.check(rc, "pb_store_extend_plan")
+            break
+        self.d_rows[0, :n].copy_(self.h_rows[0, :n], non_blocking=True)
+        self.d_rows[1, :n].copy_(self.h_rows[1, :n], non_blocking=True)
+        self.d_meta.copy_(self.h_meta, non_blocking=True)
+        # the pinned block is reused by the next stage(): remember when the copies are done
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._copy_event = ev
+        _lib.check(self._lib.pb_store_scatter(
+            self._ref, n, self.d_rows[0].data_ptr(), self.d_rows[1].data_ptr(), self._dmeta("action"),
+            self._dmeta("reward"), self._dmeta("done"), self._dmeta("trunc"), self._dmeta("seq"),
+            self._dmeta("prev"), self._dmeta("next"), self._dmeta("aux"), self._dmeta("pslot"), self._dmeta("pval"),
+            self._stream()), "pb_store_scatter")
+        self.seq += n
+        self.n_staged = 0
+        return n
+
+    def wait_staging(self):
+        ev = getattr(self, "_copy_event", None)
+        if ev is not None:
+            ev.synchronize()
+            self._copy_event = None
+
+    def bytes_staged_per_row(self):
+        return 2 * self.obs_elems * self.h_rows.element_size()
+
+    def _grow_trunc_pool(self):
+        old_pool = self.aux_size - self.max_streams
+        new_pool = old_pool * 2
+        aux = torch.zeros((self.max_streams + new_pool, self.obs_elems), dtype=self.storage_dtype, device=self.device)
+        aux[:self.aux_size].copy_(self.aux_obs)
+        # unroll the ring so that live rows keep their index and the cursor points at fresh rows
+        owner = np.full(new_pool, -1, dtype=np.int64)
+        owner[:old_pool] = self.trunc_owner
+        self.trunc_owner = owner
+        self.trunc_cursor[0] = old_pool
+        self.aux_obs = aux
+        self.aux_size = self.max_streams + new_pool
+        self._make_desc()
+
+    # ---------------------------------------------------------------------------
+    def gather(self, idx, obs_out, next_obs_out, ret_out, gamma_out, nonterm_out, action_out):
+        n = idx.numel()
+        _lib.check(self._lib.pb_store_gather(
+            self._ref, n, idx.data_ptr(), obs_out.data_ptr(), next_obs_out.data_ptr(), ret_out.data_ptr(),
+            gamma_out.data_ptr(), nonterm_out.data_ptr(), action_out.data_ptr(), self._stream()),
+            "pb_store_gather")
+
+    def nstep(self, idx):
+        n = idx.numel()
+        d = self.device
+        ret = torch.empty(n, dtype=torch.float32, device=d)
+        gam = torch.empty(n, dtype=torch.float32, device=d)
+        done = torch.empty(n, dtype=torch.uint8, device=d)
+        last = torch.empty(n, dtype=torch.int64, device=d)
+        succ = torch.empty(n, dtype=torch.int64, device=d)
+        _lib.check(self._lib.pb_store_nstep(self._ref, n, idx.data_ptr(), ret.data_ptr(), gam.data_ptr(),
+                                            done.data_ptr(), last.data_ptr(), succ.data_ptr(), self._stream()),
+                   "pb_store_nstep")
+        return ret, gam, done, last, succ
+
+    def clear(self):
+        self.slot_seq.fill_(-1)
+        self.next_link.fill_(-1)
+        self.prev_link.fill_(-1)
+        self.seq = 0
+        self.stream_last[:] = -1
+        self.trunc_cursor[0] = 0
+        self.trunc_owner[:] = -1
+        self.n_staged = 0
+
+    def state_dict(self):
+        n = len(self)
+        return {"obs": self.obs[:n].cpu(), "aux_obs": self.aux_obs.cpu(), "action": self.action[:n].cpu(),
+                "reward": self.reward[:n].cpu(), "done": self.done[:n].cpu(), "trunc": self.trunc[:n].cpu(),
+                "slot_seq": self.slot_seq[:n].cpu(), "next_link": self.next_link[:n].cpu(),
+                "prev_link": self.prev_link[:n].cpu(), "seq": self.seq, "stream_last": self.stream_last.copy(),
+                "trunc_cursor": int(self.trunc_cursor[0]), "trunc_owner": self.trunc_owner.copy(),
+                "size": self.size, "obs_shape": self.obs_shape}
+
+    def load_state_dict(self, sd):
+        assert sd["size"] == self.size and tuple(sd["obs_shape"]) == self.obs_shape
+        n = sd["obs"].shape[0]
+        while self.aux_size < sd["aux_obs"].shape[0]:
+            self._grow_trunc_pool()
+        self.clear()
+        self.obs[:n].copy_(sd["obs"]); self.aux_obs[:sd["aux_obs"].shape[0]].copy_(sd["aux_obs"])
+        self.action[:n].copy_(sd["action"]); self.reward[:n].copy_(sd["reward"])
+        self.done[:n].copy_(sd["done"]); self.trunc[:n].copy_(sd["trunc"])
+        self.slot_seq[:n].copy_(sd["slot_seq"]); self.next_link[:n].copy_(sd["next_link"])
+        self.prev_link[:n].copy_(sd["prev_link"])
+        self.seq = sd["seq"]
+        # collector state cannot be recovered after a reload: every stream restarts
+        # (the reference truncates in-flight trajectories on save for the same reason,
+        # prism/experience/timestep_buffer.py:274-297)
+        self.stream_last[:] = -1
+        self.trunc_cursor[0] = sd["trunc_cursor"]
+        self.trunc_owner[:len(sd["trunc_owner"])] = sd["trunc_owner"]
