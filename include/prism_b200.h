@@ -126,17 +126,17 @@ int pb_tree_sample(const pb_tree *t, long long n, const double *u, int mode, flo
                    long long *idx_out, float *weight_out, float *mass_out, void *stream);
 
 /* Sharded global stratified sampling (new design).  Every rank holds
- * one shard; all_* are the all-gathered {p_sum, p_min, len} of the G shards
- * (G a power of two).  The G shard roots form the virtual top of one tree of
+ * one shard; all_state is the all-gathered array of the G shards' 64-byte state
+ * blocks (one NCCL all-gather; only p_sum, p_min and len are read; G a power of two).  The G shard roots form the virtual top of one tree of
  * G*capacity leaves, summed pairwise in fp32.  Each rank evaluates all n_global
  * strata, keeps the contiguous run that lands in its shard and descends its own
  * tree with the residual mass.  Outputs are compacted to [0, owned_n);
- * state->owned_lo / owned_n report the run.  Rows >= owned_n get idx 0, weight 0. */
-int pb_tree_sample_global(const pb_tree *t, int n_ranks, int rank, const float *all_psum,
-                          const float *all_pmin, const long long *all_len,
-                          long long n_global, const double *u, float beta,
-                          long long *idx_out, float *weight_out, long long *stratum_out,
-                          void *stream);
+ * state->owned_lo / owned_n report the run.  Rows >= owned_n get idx -1 (skipped by
+ * pb_store_gather and pb_tree_update_priority) and weight 0. */
+int pb_tree_sample_global(const pb_tree *t, int n_ranks, int rank,
+                          const pb_per_state *all_state, long long n_global, const double *u,
+                          float beta, long long *idx_out, float *weight_out,
+                          long long *stratum_out, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * Transition ring (replaces the linked list of Timestep objects,
@@ -168,11 +168,26 @@ typedef struct pb_store {
 /* per-step flags handed to the host planner */
 enum { PB_STEP_DONE = 1, PB_STEP_TRUNC = 2, PB_STEP_NO_NEXT = 4 };
 
-/* HOST planner for TimestepBuffer.extend: turns n new steps (in arrival order,
- * each tagged with its collector stream) into slot/link values, following the
- * link rules of multiprocessing_experience_collection/collector_process_interface.py:146-173
- * (done -> no next; truncated -> next is the final observation, never stored;
- * else prev/next neighbours).  All arrays are HOST memory.
+/* one staged step: 64 bytes, filled on pinned host memory and copied to the device in one piece */
+typedef struct pb_step_meta {
+    long long seq;         /* planner: global sequence number (slot = seq % size)            */
+    long long prev_link;   /* planner */
+    long long next_link;   /* planner */
+    long long aux_row;     /* planner: aux_obs row that receives next_obs[j], -1 = discard    */
+    long long patch_slot;  /* planner: already-stored predecessor whose next_link is fixed up */
+    long long patch_val;   /* planner */
+    float     reward;      /* caller */
+    int       action;      /* caller */
+    uint8_t   done;        /* caller */
+    uint8_t   trunc;       /* caller */
+    uint8_t   pad[6];
+} pb_step_meta;
+
+/* HOST planner for TimestepBuffer.extend: turns n new steps (in arrival order, each tagged
+ * with its collector stream) into slot/link values, following the link rules of
+ * multiprocessing_experience_collection/collector_process_interface.py:146-173
+ * (done -> no next; truncated -> next is the final observation, never stored; else prev/next
+ * neighbours).  All arrays are HOST memory.
  *   stream_last_h[n_streams]  in/out: seq of the newest stored step of each stream, -1 none
  *   seq0                      seq of the first new step
  *   trunc_cursor_h            in/out: next free row of the truncated-obs pool
@@ -180,25 +195,17 @@ enum { PB_STEP_DONE = 1, PB_STEP_TRUNC = 2, PB_STEP_NO_NEXT = 4 };
  *   trunc_owner_h[aux_size-n_streams] in/out: seq of the step owning each pool row (-1 free);
  *                             recycling a row whose owner is still stored returns PB_E_POOL
  *                             with no side effect (the caller grows the pool and retries)
- * outputs (host, length n): seq_h, prev_link_h, next_link_h, aux_row_h (row of
- * aux_obs that receives next_obs[j], -1 = discard), patch_slot_h / patch_val_h
- * (next_link fix-ups of already-stored predecessors, -1 = none). */
+ *   meta_h[n]                 out: the six planner fields of every step */
 int pb_store_extend_plan(long long size, long long aux_size, int n_streams, long long n,
                          long long seq0, const int *stream_id_h, const uint8_t *flags_h,
-                         long long *stream_last_h,
-                         long long *trunc_cursor_h, long long *trunc_owner_h, long long *seq_h,
-                         long long *prev_link_h,
-                         long long *next_link_h, long long *aux_row_h,
-                         long long *patch_slot_h, long long *patch_val_h);
+                         long long *stream_last_h, long long *trunc_cursor_h,
+                         long long *trunc_owner_h, pb_step_meta *meta_h);
 
-/* device scatter of n planned steps: obs rows -> ring, next_obs rows -> aux pool,
- * metadata, link patches.  obs/next_obs are device staging buffers
- * [n][obs_elems] of the store dtype. */
+/* device scatter of n planned steps: obs rows -> ring, next_obs rows -> aux pool, metadata,
+ * link patches.  obs/next_obs are device staging buffers [n][obs_elems] of the store dtype,
+ * meta the device copy of the planned pb_step_meta array. */
 int pb_store_scatter(const pb_store *s, long long n, const void *obs, const void *next_obs,
-                     const int *action, const float *reward, const uint8_t *done,
-                     const uint8_t *trunc, const long long *seq, const long long *prev_link,
-                     const long long *next_link, const long long *aux_row,
-                     const long long *patch_slot, const long long *patch_val, void *stream);
+                     const pb_step_meta *meta, void *stream);
 
 /* TimestepBuffer._timesteps_to_batch + _compute_n_step + _stack_obs_into
  * (prism/experience/timestep_buffer.py:79-257) fused: for each sampled slot walk

@@ -42,6 +42,11 @@ class pb_store(C.Structure):
     ]
 
 
+# numpy view of pb_step_meta (64 bytes per staged step)
+STEP_META_DTYPE = [("seq", "<i8"), ("prev_link", "<i8"), ("next_link", "<i8"), ("aux_row", "<i8"),
+                   ("patch_slot", "<i8"), ("patch_val", "<i8"), ("reward", "<f4"), ("action", "<i4"),
+                   ("done", "u1"), ("trunc", "u1"), ("pad", "u1", (6,))]
+
 assert C.sizeof(pb_per_state) == 64
 
 _P = C.c_void_p
@@ -64,9 +69,9 @@ SIGNATURES = {
     "pb_tree_extend": [_TREE, _LL, _P, _P],
     "pb_tree_scan": [_TREE, _LL, _P, _P, _P],
     "pb_tree_sample": [_TREE, _LL, _P, _I, _F, _P, _P, _P, _P],
-    "pb_tree_sample_global": [_TREE, _I, _I, _P, _P, _P, _LL, _P, _F, _P, _P, _P, _P],
-    "pb_store_extend_plan": [_LL, _LL, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
-    "pb_store_scatter": [_STORE, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "pb_tree_sample_global": [_TREE, _I, _I, _P, _LL, _P, _F, _P, _P, _P, _P],
+    "pb_store_extend_plan": [_LL, _LL, _I, _LL, _LL, _P, _P, _P, _P, _P, _P],
+    "pb_store_scatter": [_STORE, _LL, _P, _P, _P, _P],
     "pb_store_gather": [_STORE, _LL, _P, _P, _P, _P, _P, _P, _P, _P],
     "pb_store_nstep": [_STORE, _LL, _P, _P, _P, _P, _P, _P, _P],
     "pb_iqn_cos_basis": [_LL, _I, _P, _P, _P],

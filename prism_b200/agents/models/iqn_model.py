@@ -54,6 +54,9 @@ class IQNModel(nn.Module):
             self.embedding_to_quantile_layer = nn.Sequential(nn.LayerNorm(width), nn.Linear(width, n_actions)).to(device)
         else:
             self.embedding_to_quantile_layer = nn.Linear(width, n_actions, device=device)
+        # injected quantile draws, consumed in call order (parity tests replay the reference's torch.rand
+        # stream through this; production draws from the device Philox generator)
+        self.tau_queue = []
 
     # ------------------------------------------------------------------
     def forward(self, x, n_quantile_samples=None, for_action=False, static_quantiles=None):
@@ -68,11 +71,13 @@ class IQNModel(nn.Module):
             n_quantile_samples = self.n_quantile_samples_per_action
         n = int(n_quantile_samples)
 
-        if static_quantiles is None:
-            # same shape, dtype and generator as the reference draw (:64-66)
-            quantiles = torch.rand([n * n_rows, 1], device=self.device).float()
-        else:
+        if static_quantiles is not None:
             quantiles = static_quantiles
+        elif self.tau_queue:
+            quantiles = self.tau_queue.pop(0).to(self.device).float().view(n * n_rows, 1)
+        else:
+            # same shape and dtype as the reference draw (:64-66), from the device generator
+            quantiles = torch.rand([n * n_rows, 1], device=self.device).float()
 
         basis = ops.cos_basis(quantiles, self.n_basis_elements)            # (n*rows, n_basis)
         phi = self.phi(basis)                                              # (n*rows, F)

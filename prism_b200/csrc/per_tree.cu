@@ -449,17 +449,17 @@ struct GlobalTop {
 };
 
 // every CTA rebuilds the virtual top from the all-gathered shard stats (device memory)
-__device__ __forceinline__ void build_top(GlobalTop *g, const float *all_psum, const float *all_pmin, int G)
+__device__ __forceinline__ void build_top(GlobalTop *g, const pb_per_state *all_state, int G)
 {
-    if (threadIdx.x < G) g->psum[G + threadIdx.x] = all_psum[threadIdx.x];
+    if (threadIdx.x < G) g->psum[G + threadIdx.x] = all_state[threadIdx.x].p_sum;
     __syncthreads();
     for (int n = G >> 1; n >= 1; n >>= 1) {
         if (threadIdx.x < n) g->psum[n + threadIdx.x] = op_sum(g->psum[2 * (n + threadIdx.x)], g->psum[2 * (n + threadIdx.x) + 1]);
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        float m = all_pmin[0];
-        for (int r = 1; r < G; ++r) m = op_min(m, all_pmin[r]);
+        float m = all_state[0].p_min;
+        for (int r = 1; r < G; ++r) m = op_min(m, all_state[r].p_min);
         g->pmin = m;
     }
     __syncthreads();
@@ -483,11 +483,11 @@ __device__ __forceinline__ int route_stratum(const GlobalTop &g, int G, long lon
     return node - G;
 }
 
-__global__ void __launch_bounds__(256) global_count_kernel(TreeView t, const float *all_psum, const float *all_pmin,
+__global__ void __launch_bounds__(256) global_count_kernel(TreeView t, const pb_per_state *all_state,
                                                            int G, int rank, long long n_global, const double *u)
 {
     __shared__ GlobalTop g;
-    build_top(&g, all_psum, all_pmin, G);
+    build_top(&g, all_state, G);
     long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int lo = 0, mine = 0;
     if (k < n_global) {
@@ -503,25 +503,24 @@ __global__ void __launch_bounds__(256) global_count_kernel(TreeView t, const flo
     }
 }
 
-__global__ void __launch_bounds__(256) global_sample_kernel(TreeView t, const float *all_psum, const float *all_pmin,
-                                                            const long long *all_len, int G, int rank,
+__global__ void __launch_bounds__(256) global_sample_kernel(TreeView t, const pb_per_state *all_state, int G, int rank,
                                                             long long n_global, const double *u, float beta,
                                                             long long *idx_out, float *w_out, long long *stratum_out)
 {
     __shared__ GlobalTop g;
-    build_top(&g, all_psum, all_pmin, G);
+    build_top(&g, all_state, G);
     const long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (k >= n_global) return;
     const int lane = lane_id();
     const int lo = t.st->owned_lo, cnt = t.st->owned_n;
-    if (k >= cnt && lane == 0) {  // padding rows of the static batch
-        idx_out[k] = 0; w_out[k] = 0.0f;
+    if (k >= cnt && lane == 0) {  // padding rows of the static batch: idx -1 is skipped downstream
+        idx_out[k] = -1; w_out[k] = 0.0f;
         if (stratum_out) stratum_out[k] = -1;
     }
     float res;
     int owner = route_stratum(g, G, k, n_global, u[k], &res);
     if (owner != rank) return;
-    const long long len = all_len[rank];
+    const long long len = all_state[rank].len;
     if (len <= 0 || !(g.psum[1] > 0.0f) || !(g.pmin > 0.0f)) {
         if (lane == 0 && k == lo) atomicOr(&t.st->status, len <= 0 ? PB_ST_EMPTY : (!(g.psum[1] > 0.0f) ? PB_ST_PSUM_NONPOS : PB_ST_PMIN_NONPOS));
     }
@@ -691,23 +690,22 @@ int pb_tree_sample(const pb_tree *t, long long n, const double *u, int mode, flo
     return PB_OK;
 }
 
-int pb_tree_sample_global(const pb_tree *t, int n_ranks, int rank, const float *all_psum,
-                          const float *all_pmin, const long long *all_len, long long n_global,
-                          const double *u, float beta, long long *idx_out, float *weight_out,
-                          long long *stratum_out, void *stream)
+int pb_tree_sample_global(const pb_tree *t, int n_ranks, int rank, const pb_per_state *all_state,
+                          long long n_global, const double *u, float beta, long long *idx_out,
+                          float *weight_out, long long *stratum_out, void *stream)
 {
     TreeView v;
     int rc = make_view(t, &v);
     if (rc) return rc;
     if (n_ranks < 1 || n_ranks > MAX_RANKS || !pb_is_pow2(n_ranks) || rank < 0 || rank >= n_ranks) return PB_E_ARG;
-    if (!all_psum || !all_pmin || !all_len || n_global < 0) return PB_E_ARG;
+    if (!all_state || n_global < 0) return PB_E_ARG;
     if (n_global > 0 && (!u || !idx_out || !weight_out)) return PB_E_ARG;
     PB_LAUNCH(global_reset_kernel, 1, 1, 0, stream, v);
     if (n_global == 0) return PB_OK;
-    PB_LAUNCH(global_count_kernel, (unsigned)((n_global + 255) / 256), 256, 0, stream, v, all_psum, all_pmin,
+    PB_LAUNCH(global_count_kernel, (unsigned)((n_global + 255) / 256), 256, 0, stream, v, all_state,
               n_ranks, rank, n_global, u);
-    PB_LAUNCH(global_sample_kernel, (unsigned)((n_global + 7) / 8), 256, 0, stream, v, all_psum, all_pmin,
-              all_len, n_ranks, rank, n_global, u, beta, idx_out, weight_out, stratum_out);
+    PB_LAUNCH(global_sample_kernel, (unsigned)((n_global + 7) / 8), 256, 0, stream, v, all_state,
+              n_ranks, rank, n_global, u, beta, idx_out, weight_out, stratum_out);
     return PB_OK;
 }
 

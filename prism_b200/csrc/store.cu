@@ -69,31 +69,25 @@ __device__ __forceinline__ void copy_row_bytes(uint8_t *dst, const uint8_t *src,
 }
 
 __global__ void __launch_bounds__(128) store_scatter_kernel(StoreView s, long long n, const uint8_t *obs,
-                                                            const uint8_t *next_obs, const int *action,
-                                                            const float *reward, const uint8_t *done,
-                                                            const uint8_t *trunc, const long long *seq,
-                                                            const long long *prev_link, const long long *next_link,
-                                                            const long long *aux_row, const long long *patch_slot,
-                                                            const long long *patch_val)
+                                                            const uint8_t *next_obs, const pb_step_meta *meta)
 {
     const long long j = blockIdx.x;
-    const long long sq = seq[j];
-    const long long slot = sq % s.size;
+    const pb_step_meta m = meta[j];
+    const long long slot = m.seq % s.size;
     if (blockIdx.y == 0) {
         copy_row_bytes(s.obs_w + slot * s.row_bytes, obs + j * s.row_bytes, s.row_bytes);
         if (threadIdx.x == 0) {
-            s.action[slot] = action[j];
-            s.reward[slot] = reward[j];
-            s.done[slot] = done[j];
-            s.trunc[slot] = trunc[j];
-            s.slot_seq[slot] = sq;
-            s.prev_link[slot] = prev_link[j];
-            s.next_link[slot] = next_link[j];
-            const long long ps = patch_slot[j];
-            if (ps >= 0) s.next_link[ps] = patch_val[j];
+            s.action[slot] = m.action;
+            s.reward[slot] = m.reward;
+            s.done[slot] = m.done;
+            s.trunc[slot] = m.trunc;
+            s.slot_seq[slot] = m.seq;
+            s.prev_link[slot] = m.prev_link;
+            s.next_link[slot] = m.next_link;
+            if (m.patch_slot >= 0) s.next_link[m.patch_slot] = m.patch_val;
         }
     } else {
-        const long long row = aux_row[j];
+        const long long row = m.aux_row;
         if (row >= 0 && row < s.aux_size && next_obs)
             copy_row_bytes(s.aux_w + row * s.row_bytes, next_obs + j * s.row_bytes, s.row_bytes);
     }
@@ -249,15 +243,12 @@ __global__ void store_nstep_kernel(StoreView s, long long n, const long long *id
 extern "C" {
 
 int pb_store_extend_plan(long long size, long long aux_size, int n_streams, long long n, long long seq0,
-                         const int *stream_id_h, const uint8_t *flags_h, long long *stream_last_h, long long *trunc_cursor_h, long long *trunc_owner_h,
-                         long long *seq_h, long long *prev_link_h, long long *next_link_h, long long *aux_row_h,
-                         long long *patch_slot_h, long long *patch_val_h)
+                         const int *stream_id_h, const uint8_t *flags_h, long long *stream_last_h,
+                         long long *trunc_cursor_h, long long *trunc_owner_h, pb_step_meta *meta_h)
 {
     if (size <= 0 || n < 0 || n > size || n_streams <= 0 || aux_size < n_streams) return PB_E_ARG;
     if (n == 0) return PB_OK;
-    if (!stream_id_h || !flags_h || !stream_last_h || !trunc_cursor_h || !seq_h || !prev_link_h ||
-        !next_link_h || !aux_row_h || !patch_slot_h || !patch_val_h)
-        return PB_E_ARG;
+    if (!stream_id_h || !flags_h || !stream_last_h || !trunc_cursor_h || !meta_h) return PB_E_ARG;
     const long long pool = aux_size - n_streams;
     // dry run (no side effects on failure): stream ids valid; every truncated-pool row this
     // batch would recycle must belong to a step that has already left the ring
@@ -281,56 +272,51 @@ int pb_store_extend_plan(long long size, long long aux_size, int n_streams, long
     for (long long j = 0; j < n; ++j) {
         const int sid = stream_id_h[j];
         const long long s = seq0 + j;
-        seq_h[j] = s;
-        patch_slot_h[j] = -1; patch_val_h[j] = -1;
+        meta_h[j].seq = s;
+        meta_h[j].patch_slot = -1; meta_h[j].patch_val = -1;
         const long long prev = stream_last_h[sid];
-        prev_link_h[j] = prev;
+        meta_h[j].prev_link = prev;
         if (prev >= 0) {
             if (prev >= seq0) {                       // predecessor is in this batch: link directly
-                next_link_h[prev - seq0] = s;
-                aux_row_h[prev - seq0] = -1;          // its in-flight row is superseded by this step
+                meta_h[prev - seq0].next_link = s;
+                meta_h[prev - seq0].aux_row = -1;     // its in-flight row is superseded by this step
             } else if (end_seq - prev < size) {       // still stored after this batch lands
-                patch_slot_h[j] = prev % size;
-                patch_val_h[j] = s;
+                meta_h[j].patch_slot = prev % size;
+                meta_h[j].patch_val = s;
             }
         }
         if (flags_h[j] & PB_STEP_DONE) {
             // collector_process_interface.py:167: done -> no next link
-            next_link_h[j] = -1; aux_row_h[j] = -1; stream_last_h[sid] = -1;
+            meta_h[j].next_link = -1; meta_h[j].aux_row = -1; stream_last_h[sid] = -1;
         } else if (flags_h[j] & PB_STEP_NO_NEXT) {
             // a step handed over before its successor observation exists (hand-linked chains):
             // no next yet; the stream stays open so a later step can still link to it
-            next_link_h[j] = -1; aux_row_h[j] = -1; stream_last_h[sid] = (flags_h[j] & PB_STEP_TRUNC) ? -1 : s;
+            meta_h[j].next_link = -1; meta_h[j].aux_row = -1; stream_last_h[sid] = (flags_h[j] & PB_STEP_TRUNC) ? -1 : s;
         } else if (flags_h[j] & PB_STEP_TRUNC) {
             // :155-165: truncated -> next is the final observation, held only by this step
             const long long row = n_streams + *trunc_cursor_h;
             trunc_owner_h[*trunc_cursor_h] = s;
             *trunc_cursor_h = (*trunc_cursor_h + 1) % pool;
-            next_link_h[j] = -(row + 2); aux_row_h[j] = row; stream_last_h[sid] = -1;
+            meta_h[j].next_link = -(row + 2); meta_h[j].aux_row = row; stream_last_h[sid] = -1;
         } else {
             // :168-169: successor is the in-flight step (observation only) of the same stream
-            next_link_h[j] = -((long long)sid + 2); aux_row_h[j] = sid; stream_last_h[sid] = s;
+            meta_h[j].next_link = -((long long)sid + 2); meta_h[j].aux_row = sid; stream_last_h[sid] = s;
         }
     }
     return PB_OK;
 }
 
-int pb_store_scatter(const pb_store *st, long long n, const void *obs, const void *next_obs, const int *action,
-                     const float *reward, const uint8_t *done, const uint8_t *trunc, const long long *seq,
-                     const long long *prev_link, const long long *next_link, const long long *aux_row,
-                     const long long *patch_slot, const long long *patch_val, void *stream)
+int pb_store_scatter(const pb_store *st, long long n, const void *obs, const void *next_obs,
+                     const pb_step_meta *meta, void *stream)
 {
     StoreView v;
     int rc = make_store(st, &v);
     if (rc) return rc;
     if (n < 0 || n > v.size) return PB_E_ARG;
     if (n == 0) return PB_OK;
-    if (!obs || !action || !reward || !done || !trunc || !seq || !prev_link || !next_link || !aux_row ||
-        !patch_slot || !patch_val)
-        return PB_E_ARG;
+    if (!obs || !meta) return PB_E_ARG;
     dim3 grid((unsigned)n, 2);
-    PB_LAUNCH(store_scatter_kernel, grid, 128, 0, stream, v, n, (const uint8_t *)obs, (const uint8_t *)next_obs,
-              action, reward, done, trunc, seq, prev_link, next_link, aux_row, patch_slot, patch_val);
+    PB_LAUNCH(store_scatter_kernel, grid, 128, 0, stream, v, n, (const uint8_t *)obs, (const uint8_t *)next_obs, meta);
     return PB_OK;
 }
 

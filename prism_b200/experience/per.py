@@ -138,19 +138,20 @@ class PrioritizedTree:
                    "pb_tree_sample")
         return idx_out, weight_out
 
-    def sample_global(self, n_ranks, rank, all_psum, all_pmin, all_len, n_global, u, beta=None,
+    def sample_global(self, n_ranks, rank, all_state, n_global, u, beta=None,
                       idx_out=None, weight_out=None, stratum_out=None):
-        """Sharded global stratified sampling: every rank evaluates all strata and keeps its run."""
+        """Sharded global stratified sampling: every rank evaluates all strata and keeps its
+        run.  ``all_state``: (n_ranks, 64) uint8, the all-gathered shard state blocks."""
         n_global = int(n_global)
         if idx_out is None:
             idx_out = torch.empty(n_global, dtype=torch.int64, device=self.device)
         if weight_out is None:
             weight_out = torch.empty(n_global, dtype=torch.float32, device=self.device)
         beta = self._beta if beta is None else float(beta)
-        assert all_psum.dtype == torch.float32 and all_pmin.dtype == torch.float32 and all_len.dtype == torch.int64
+        assert all_state.dtype == torch.uint8 and all_state.numel() == 64 * n_ranks and all_state.is_contiguous()
         assert u.dtype == torch.float64 and u.is_cuda
-        _lib.check(self._lib.pb_tree_sample_global(self._ref, int(n_ranks), int(rank), all_psum.data_ptr(),
-                                                   all_pmin.data_ptr(), all_len.data_ptr(), n_global, u.data_ptr(),
+        _lib.check(self._lib.pb_tree_sample_global(self._ref, int(n_ranks), int(rank), all_state.data_ptr(),
+                                                   n_global, u.data_ptr(),
                                                    beta, idx_out.data_ptr(), weight_out.data_ptr(),
                                                    _lib.ptr(stratum_out), self._stream()), "pb_tree_sample_global")
         return idx_out, weight_out

@@ -68,34 +68,17 @@ class TransitionRing:
 
     def _alloc_staging(self):
         S = self.staging_rows
-        # rows: [2][S][obs_elems] pinned + device mirror; meta: one packed byte block
+        # rows: [2][S][obs_elems] pinned + device mirror; meta: S packed 64-byte pb_step_meta records
         self.h_rows = torch.zeros((2, S, self.obs_elems), dtype=self.storage_dtype).pin_memory()
         self.d_rows = torch.zeros((2, S, self.obs_elems), dtype=self.storage_dtype, device=self.device)
-        off = 0
-        self._meta_off = {}
-        for name, width in (("seq", 8), ("prev", 8), ("next", 8), ("aux", 8), ("pslot", 8), ("pval", 8),
-                            ("reward", 4), ("action", 4), ("done", 1), ("trunc", 1)):
-            self._meta_off[name] = off
-            off += ((S * width + 15) // 16) * 16
-        self.h_meta = torch.zeros(off, dtype=torch.uint8).pin_memory()
-        self.d_meta = torch.zeros(off, dtype=torch.uint8, device=self.device)
-        hm = self.h_meta.numpy()
-        o = self._meta_off
-
-        def view(name, dtype):
-            return hm[o[name]:o[name] + S * np.dtype(dtype).itemsize].view(dtype)
-
-        self.m_seq, self.m_prev, self.m_next = view("seq", np.int64), view("prev", np.int64), view("next", np.int64)
-        self.m_aux, self.m_pslot, self.m_pval = view("aux", np.int64), view("pslot", np.int64), view("pval", np.int64)
-        self.m_reward, self.m_action = view("reward", np.float32), view("action", np.int32)
-        self.m_done, self.m_trunc = view("done", np.uint8), view("trunc", np.uint8)
+        self.h_meta = torch.zeros(S * 64, dtype=torch.uint8).pin_memory()
+        self.d_meta = torch.zeros(S * 64, dtype=torch.uint8, device=self.device)
+        self.meta = self.h_meta.numpy().view(np.dtype(_lib.STEP_META_DTYPE))
+        assert self.meta.dtype.itemsize == 64 and self.meta.shape == (S,)
         self.h_rows_np = self.h_rows.numpy()
         self.m_stream = np.zeros(S, dtype=np.int32)
         self.m_flags = np.zeros(S, dtype=np.uint8)
         self.n_staged = 0
-
-    def _dmeta(self, name):
-        return self.d_meta.data_ptr() + self._meta_off[name]
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -121,10 +104,11 @@ class TransitionRing:
             nrow[...] = np.asarray(next_obs, dtype=nrow.dtype).reshape(-1)
         self.m_stream[j] = stream_id
         self.m_flags[j] = flags
-        self.m_action[j] = int(action)
-        self.m_reward[j] = float(reward)
-        self.m_done[j] = 1 if done else 0
-        self.m_trunc[j] = 1 if trunc else 0
+        rec = self.meta[j]
+        rec["action"] = int(action)
+        rec["reward"] = float(reward)
+        rec["done"] = 1 if done else 0
+        rec["trunc"] = 1 if trunc else 0
         self.n_staged = j + 1
         return self.n_staged >= self.staging_rows
 
@@ -143,10 +127,10 @@ class TransitionRing:
         t = np.asarray(trunc[:n]).astype(np.uint8)
         self.m_stream[sl] = stream_ids[:n]
         self.m_flags[sl] = d * STEP_DONE + t * STEP_TRUNC
-        self.m_action[sl] = action[:n]
-        self.m_reward[sl] = reward[:n]
-        self.m_done[sl] = d
-        self.m_trunc[sl] = t
+        self.meta["action"][sl] = action[:n]
+        self.meta["reward"][sl] = reward[:n]
+        self.meta["done"][sl] = d
+        self.meta["trunc"][sl] = t
         self.n_staged = j + n
         return n
 
@@ -160,8 +144,7 @@ class TransitionRing:
             rc = self._lib.pb_store_extend_plan(
                 self.size, self.aux_size, self.max_streams, n, self.seq, self.m_stream.ctypes.data,
                 self.m_flags.ctypes.data, self.stream_last.ctypes.data, self.trunc_cursor.ctypes.data,
-                self.trunc_owner.ctypes.data, self.m_seq.ctypes.data, self.m_prev.ctypes.data,
-                self.m_next.ctypes.data, self.m_aux.ctypes.data, self.m_pslot.ctypes.data, self.m_pval.ctypes.data)
+                self.trunc_owner.ctypes.data, self.h_meta.data_ptr())
             if rc == _lib.PB_E_POOL:
                 self._grow_trunc_pool()
                 continue
@@ -169,16 +152,14 @@ class TransitionRing:
             break
         self.d_rows[0, :n].copy_(self.h_rows[0, :n], non_blocking=True)
         self.d_rows[1, :n].copy_(self.h_rows[1, :n], non_blocking=True)
-        self.d_meta.copy_(self.h_meta, non_blocking=True)
+        self.d_meta[:n * 64].copy_(self.h_meta[:n * 64], non_blocking=True)
         # the pinned block is reused by the next stage(): remember when the copies are done
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self._copy_event = ev
-        _lib.check(self._lib.pb_store_scatter(
-            self._ref, n, self.d_rows[0].data_ptr(), self.d_rows[1].data_ptr(), self._dmeta("action"),
-            self._dmeta("reward"), self._dmeta("done"), self._dmeta("trunc"), self._dmeta("seq"),
-            self._dmeta("prev"), self._dmeta("next"), self._dmeta("aux"), self._dmeta("pslot"), self._dmeta("pval"),
-            self._stream()), "pb_store_scatter")
+        _lib.check(self._lib.pb_store_scatter(self._ref, n, self.d_rows[0].data_ptr(), self.d_rows[1].data_ptr(),
+                                              self.d_meta.data_ptr(), self._stream()), "pb_store_scatter")
+        self.last_flush_h2d_bytes = n * (2 * self.obs_elems * self.h_rows.element_size() + 64)
         self.seq += n
         self.n_staged = 0
         return n

@@ -1,0 +1,137 @@
+"""LearnerStep -- one iteration of the reference's hot loop as ONE CUDA graph.
+
+The reference learner (prism/learner.py:95-125) runs, strictly serially and with a device->host
+sync in the middle:
+    batch, info = buffer.sample(return_info=True)            # CPU tree + Python batch loop + H2D
+    td = agent.update(batch, info['_weight'].to(device))     # CUDA graph of ~100 small kernels
+    buffer.update_priority(info['index'], td.abs())          # D2H sync + CPU tree
+Here the same three calls never leave the device: sample (Philox uniforms -> tree descent -> fused
+n-step/gather into the agent's static batch), update (fused loss heads, clip+Adam) and the
+priority write-back are captured into a single graph, replayed once per iteration.
+
+Data parallel: every rank owns a shard (ring + trees) fed by its own collectors.
+Per iteration: one NCCL all-gather of the 64-byte shard state blocks, global stratified sampling
+with owner-computes placement (no transition crosses NVLink), one NCCL all-reduce of the flat
+gradient arena.
+"""
+import torch
+
+from . import _lib
+from .agents.optim import FlatAdam
+from .experience.per import PrioritizedTree
+
+
+class LearnerStep:
+    def __init__(self, buffer, agent, batch_size=None, use_cuda_graph=True, process_group=None,
+                 rank=0, world_size=1, pad_slack=None):
+        self.buffer, self.agent = buffer, agent
+        self.tree = buffer.buffer._sampler
+        self.ring = buffer.buffer._storage
+        if self.ring is None or self.tree is None:
+            raise _lib.PbError("LearnerStep needs a prioritized buffer that already holds transitions")
+        self.device = torch.device(buffer.device)
+        self.B = int(batch_size or buffer.buffer._batch_size)
+        self.world_size, self.rank, self.pg = int(world_size), int(rank), process_group
+        self.use_cuda_graph = use_cuda_graph
+        self.graph = None
+        d = self.device
+        if self.world_size > 1:
+            if self.world_size & (self.world_size - 1):
+                raise ValueError("sharded sampling needs a power-of-two number of ranks")
+            self.B_global = self.B * self.world_size
+            slack = pad_slack if pad_slack is not None else max(16, int(4 * (self.B ** 0.5)))
+            self.B_pad = self.B + slack                      # static rows per rank (zero-weight padding)
+            self.all_state = torch.zeros(self.world_size, 64, dtype=torch.uint8, device=d)
+            self.stratum = torch.empty(self.B_global, dtype=torch.int64, device=d)
+            n_rows = self.B_global
+        else:
+            self.B_global = self.B_pad = self.B
+            n_rows = self.B
+        self.u = torch.empty(self.B_global, dtype=torch.float64, device=d)
+        self.idx = torch.zeros(n_rows, dtype=torch.int64, device=d)
+        self.weight = torch.zeros(n_rows, dtype=torch.float32, device=d)
+        self.td = None
+        self.sorted = self.world_size > 1 or self.tree.mode == PrioritizedTree.MODE_STRATIFIED
+        # static batch, shared by the buffer (writes) and the agent (reads)
+        buffer._flush()
+        if buffer._batch is None or buffer._obs.shape[0] != self.B_pad:
+            buffer._batch = None
+            buffer._alloc_static_batch(self.B_pad, self.ring)
+        self.batch = buffer.get_static_batch()
+        agent.set_static_batch(self.batch)
+        opt = agent.optimizer
+        if self.world_size > 1:
+            if not isinstance(opt, FlatAdam):
+                raise _lib.PbError("data parallel needs the FlatAdam arena (one all-reduce per step)")
+            import torch.distributed as dist
+            opt.grad_scale = float(self.B_pad) / float(self.B_global)   # local mean over B_pad -> global mean
+            opt.allreduce = lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+        self.launches_per_step = None
+
+    # ------------------------------------------------------------------------------------
+    def _body(self, refresh_table, draw):
+        tree, ring, agent, b = self.tree, self.ring, self.agent, self.buffer
+        if draw:
+            torch.rand(self.u.shape, dtype=torch.float64, device=self.device, out=self.u)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.all_state.view(-1), tree.state, group=self.pg)
+            tree.sample_global(self.world_size, self.rank, self.all_state, self.B_global, self.u,
+                               idx_out=self.idx, weight_out=self.weight, stratum_out=self.stratum)
+        else:
+            tree.sample(self.B, u=self.u, idx_out=self.idx, weight_out=self.weight)
+        # rows past the strata this rank owns have idx -1 / weight 0: skipped by gather and update
+        idx, w = self.idx[:self.B_pad], self.weight[:self.B_pad]
+        ring.gather(idx, b._obs, b._next_obs, b._reward, b._gamma, b._nonterminal, b._action)
+        dl, ql, total, td = agent._loss_and_backward(self.batch, w, agent.target_model)
+        agent._static_distribution_loss, agent._static_q_loss, agent._static_total_loss = dl, ql, total
+        agent._optimizer_step(refresh_table=refresh_table)
+        self.td = td
+        tree.update_priority(idx, td.abs(), sorted=self.sorted)
+        return total
+
+    def step(self, u=None):
+        """Run one iteration.  ``u`` (optional): fp64 uniforms (device or pinned-host tensor, B_global
+        values) used instead of the device Philox generator."""
+        self.buffer._flush()
+        draw = u is None
+        if not draw:
+            self.u.copy_(u, non_blocking=True)
+        if not self.use_cuda_graph:
+            total = self._body(refresh_table=True, draw=draw)
+            self.agent.n_updates += 1
+            return total
+        if self.graph is None or draw != self._graph_draws:
+            self._capture(draw)
+        self.graph.replay()
+        self.agent.n_updates += 1
+        return self.agent._static_total_loss
+
+    def _capture(self, draw):
+        opt = self.agent.optimizer
+        flat = isinstance(opt, FlatAdam)
+        # warm-up on a side stream; it must neither train nor disturb the priorities
+        snap = opt.snapshot() if flat else None
+        tree_snap = (self.tree.sum.clone(), self.tree.min.clone(), self.tree.state.clone())
+        u_snap = self.u.clone()
+        rng = torch.cuda.get_rng_state(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._body(refresh_table=True, draw=draw)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        if flat:
+            opt.restore(snap)
+        self.tree.sum.copy_(tree_snap[0]); self.tree.min.copy_(tree_snap[1]); self.tree.state.copy_(tree_snap[2])
+        self.u.copy_(u_snap)
+        torch.cuda.set_rng_state(rng, self.device)
+        self._graph_draws = draw
+        opt.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self._body(refresh_table=False, draw=draw)
+        self.launches_per_step = _lib.launch_count() - before
+        if flat:
+            opt.refresh_grad_table()

@@ -1,0 +1,236 @@
+"""GPU parity of the agent-side kernels and of the drop-in Agent update against the REFERENCE
+outputs frozen in tests/golden/agent_*.npz / ids.npz and against the CPU oracle.
+Bar (north star): loss and gradients within 1e-4 relative; IDS / greedy actions identical."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (cfg_from_fixture, fixture_batch, fixture_state_dict, fixture_taus, load_golden, rel_err,
+                     target_transform)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+CASES = ["agent_ids_iqn_ln_target", "agent_ids_iqn_double", "agent_dqn_double", "agent_iqn_self"]
+
+
+def build_product_agent(fx, use_cuda_graph=False):
+    import prism_b200
+    cfg = cfg_from_fixture(fx, DEV)
+    cfg.use_cuda_graph = use_cuda_graph
+    agent = prism_b200.build_agent(cfg, tuple(fx["obs_shape"].tolist()), int(fx["n_actions"]))
+    sd = fixture_state_dict(fx)
+    agent.model.load_state_dict(sd, strict=True)
+    if agent.target_model is not None:
+        agent.target_model.load_state_dict({k: target_transform(v) for k, v in sd.items()}, strict=True)
+    return cfg, agent
+
+
+def inject_taus(cfg, agent, taus):
+    taus = [torch.as_tensor(t, dtype=torch.float32) for t in taus]
+    d = agent.model.distribution_model
+    if d is None:
+        return
+    if agent.target_model is None:
+        d.tau_queue = list(taus)
+    elif cfg.use_double_q_learning:
+        d.tau_queue = [taus[0], taus[1]]
+        agent.target_model.distribution_model.tau_queue = [taus[2]]
+    else:
+        d.tau_queue = [taus[0]]
+        agent.target_model.distribution_model.tau_queue = [taus[1]]
+
+
+def reference_named_grads(agent):
+    """Gradients keyed like the reference's named_parameters (un-stacking the ensemble heads)."""
+    out = {}
+    for name, p in agent.model.named_parameters():
+        if ".stacked." in name:
+            prefix, pos = name.split(".stacked.")
+            ens = agent.model.q_function_model
+            (seq_idx, pname), = [k for k, v in ens._slot.items() if v == int(pos)]
+            for k in range(ens.n_heads):
+                out[prefix + "." + ens._ref_key(k, seq_idx, pname)] = p.grad[k]
+        else:
+            out[name] = p.grad
+    return out
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_update_matches_reference_golden(name):
+    fx = load_golden(name)
+    cfg, agent = build_product_agent(fx)
+    inject_taus(cfg, agent, fixture_taus(fx))
+    td = agent.update(fixture_batch(fx, DEV), torch.from_numpy(fx["per_weights"]).to(DEV))
+    torch.cuda.synchronize()
+    if "out.dist" in fx:
+        assert rel_err(agent._static_distribution_loss.detach().cpu().numpy(), fx["out.dist"]) < 1e-4
+    if "out.q" in fx:
+        assert rel_err(agent._static_q_loss.detach().cpu().numpy(), fx["out.q"]) < 1e-4
+    assert rel_err(td.cpu().numpy(), fx["out.td"]) < 1e-4
+    assert rel_err(agent._static_total_loss.detach().cpu().numpy(), fx["out.total"]) < 1e-4
+    coef = float(agent.optimizer.norm_out[1])
+    for k, g in reference_named_grads(agent).items():
+        assert rel_err(g.cpu().numpy() * coef, fx["grad_clipped." + k]) < 1e-4, k
+    after = agent.model.state_dict()
+    for k, v in after.items():
+        assert rel_err(v.cpu().numpy(), fx["param_after." + k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if "iqn" in c])
+def test_acting_matches_reference_golden(name):
+    fx = load_golden(name)
+    cfg, agent = build_product_agent(fx)
+    agent.model.load_state_dict(fixture_state_dict(fx, "param_after."))
+    obs = torch.from_numpy(fx["batch.observation"][:, 0]).to(DEV)
+    agent.model.distribution_model.tau_queue = [torch.from_numpy(fx["act.tau_model"])]
+    with torch.no_grad():
+        q, z = agent.model(obs, for_action=True)
+    assert rel_err(z.cpu().numpy(), fx["act.z"]) < 1e-4
+    if "act.q" in fx:
+        assert tuple(q.shape) == fx["act.q"].shape
+        assert rel_err(q.cpu().numpy(), fx["act.q"]) < 1e-4
+    agent.model.distribution_model.tau_queue = [torch.from_numpy(fx["act.tau_agent"])]
+    act = agent.forward(obs)
+    assert act.dtype == torch.int64
+    assert np.array_equal(act.cpu().numpy(), fx["act.action"])
+
+
+def test_ids_and_greedy_kernels_match_reference_golden():
+    from prism_b200.agents import ops
+    fx = load_golden("ids")
+    for tag in "abc":
+        q = torch.from_numpy(fx[tag + ".q"]).to(DEV)      # (N, A, K)
+        z = torch.from_numpy(fx[tag + ".z"]).to(DEV)      # (Nq, N, A)
+        act, scores = ops.ids_select(q.permute(2, 0, 1), z, 0.1, 1e-10, 0.25, return_scores=True)
+        assert np.array_equal(act.cpu().numpy(), fx[tag + ".action"]), tag
+        assert np.allclose(scores.cpu().numpy(), fx[tag + ".scores"], rtol=2e-4, equal_nan=True)
+        assert np.array_equal(ops.greedy_select(q.permute(2, 0, 1)).cpu().numpy(), fx[tag + ".greedy"])
+
+
+@pytest.mark.parametrize("B,T,Tp,A", [(64, 32, 32, 3), (512, 64, 64, 18), (7, 8, 12, 5), (33, 200, 8, 6)])
+def test_quantile_huber_kernel_vs_oracle_math(B, T, Tp, A):
+    """pb_iqn_qh_loss (loss + gradient in one pass) against the oracle's broadcasted formula + autograd."""
+    from prism_b200.agents import ops
+    g = torch.Generator().manual_seed(B * 31 + T)
+    z_cur = torch.randn(T * B, A, generator=g) * 2
+    tau = torch.rand(T * B, 1, generator=g)
+    z_on, z_tg = torch.randn(Tp * B, A, generator=g), torch.randn(Tp * B, A, generator=g) * 3
+    act = torch.randint(0, A, (B,), generator=g)
+    ret, gdn = torch.randn(B, generator=g), torch.rand(B, generator=g)
+    gdn[::5] = 0.0
+    w = torch.rand(B, generator=g)
+    # oracle math (iqn_model.py:129-201) on the CPU
+    zc = z_cur.clone().requires_grad_(True)
+    best = z_on.view(Tp, B, A).mean(0).argmax(-1)
+    y = (torch.tile(ret.view(-1, 1), [Tp, 1]) + torch.gather(z_tg, 1, torch.tile(best.view(-1, 1), [Tp, 1])) *
+         torch.tile(gdn.view(-1, 1), [Tp, 1])).view(Tp, B, 1).transpose(1, 0)
+    theta = torch.gather(zc, 1, torch.tile(act.view(-1, 1), [T, 1])).view(T, B, 1).transpose(1, 0)
+    d = y[:, :, None] - theta[:, None, :]
+    small = (d.abs() <= 1.0).float()
+    hub = small * 0.5 * d.square() + (1 - small) * (d.abs() - 0.5)
+    rho = (tau.view(T, B, 1).transpose(1, 0)[:, None] - (d < 0).float()).abs() * hub
+    loss_ref = rho.sum(2).mean(1).view(-1)
+    (loss_ref * w).mean().backward()
+    zg = z_cur.to(DEV).requires_grad_(True)
+    loss = ops.quantile_huber_loss(zg, tau.to(DEV), z_on.to(DEV), z_tg.to(DEV), act.to(DEV), ret.to(DEV), gdn.to(DEV),
+                                   T, Tp, kappa=1.0)
+    (loss * w.to(DEV)).mean().backward()
+    assert rel_err(loss.detach().cpu().numpy(), loss_ref.detach().numpy()) < 1e-4
+    assert rel_err(zg.grad.cpu().numpy(), zc.grad.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("B,A,K", [(256, 4, 1), (64, 3, 10), (9, 18, 10)])
+def test_ensemble_loss_kernel_vs_oracle_math(B, A, K):
+    from prism_b200.agents import ops
+    g = torch.Generator().manual_seed(B + K)
+    qc, qo, qt = (torch.randn(K, B, A, generator=g) for _ in range(3))
+    act = torch.randint(0, A, (B,), generator=g)
+    ret, gdn, w = torch.randn(B, generator=g), torch.rand(B, generator=g), torch.rand(B, generator=g)
+    q = qc.clone().requires_grad_(True)
+    best = qo.argmax(-1)                                          # (K, B)
+    y = ret.view(1, B) + torch.gather(qt, 2, best.unsqueeze(-1)).squeeze(-1) * gdn.view(1, B)
+    loss_ref = (torch.gather(q, 2, act.view(1, B, 1).expand(K, B, 1)).squeeze(-1) - y).square().mean(0)
+    (loss_ref * w).mean().backward()
+    qg = qc.to(DEV).requires_grad_(True)
+    loss = ops.ensemble_q_loss(qg, qo.to(DEV), qt.to(DEV), act.to(DEV), ret.to(DEV), gdn.to(DEV))
+    (loss * w.to(DEV)).mean().backward()
+    assert rel_err(loss.detach().cpu().numpy(), loss_ref.detach().numpy()) < 1e-5
+    assert rel_err(qg.grad.cpu().numpy(), q.grad.numpy()) < 1e-5
+
+
+def test_cos_basis_kernel():
+    from prism_b200.agents import ops
+    tau = torch.rand(4096, 1)
+    want = torch.cos(torch.tile(tau, [1, 64]) * torch.arange(1, 65) * np.pi)
+    got = ops.cos_basis(tau.to(DEV), 64).cpu()
+    assert float((got - want).abs().max()) < 2e-6
+
+
+def test_flat_adam_matches_torch_adam_over_steps():
+    """clip_grad_norm_ + torch.optim.Adam (agent.py:73-74) vs the fused flat kernels, 20 steps."""
+    from prism_b200.agents.optim import FlatAdam
+    torch.manual_seed(0)
+    shapes = [(64, 33), (33,), (7, 5, 3), (1,), (130,)]
+    ref_p = [torch.randn(s, dtype=torch.float32).requires_grad_(True) for s in shapes]
+    dev_p = [p.detach().clone().to(DEV).requires_grad_(True) for p in ref_p]
+    ref_opt = torch.optim.Adam(ref_p, lr=1e-3, betas=(0.9, 0.999), eps=1.5e-4)
+    opt = FlatAdam(dev_p, lr=1e-3, betas=(0.9, 0.999), eps=1.5e-4, max_grad_norm=2.0)
+    for step in range(20):
+        grads = [torch.randn(s) * (3.0 if step % 3 == 0 else 0.05) for s in shapes]
+        for p, g in zip(ref_p, grads):
+            p.grad = g.clone()
+        total = torch.nn.utils.clip_grad_norm_(ref_p, 2.0)
+        ref_opt.step()
+        for p, g in zip(dev_p, grads):
+            p.grad = g.to(DEV)
+        opt.step()
+        assert abs(float(opt.norm_out[0]) - float(total)) / float(total) < 1e-5
+    for a, b in zip(dev_p, ref_p):
+        assert rel_err(a.detach().cpu().numpy(), b.detach().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["agent_ids_iqn_ln_target", "agent_dqn_double"])
+def test_cuda_graph_update_equals_eager(name):
+    """The captured update (agent.py:81-147) must give the eager result and, unlike the reference,
+    keep bootstrapping from the TARGET network."""
+    fx = load_golden(name)
+    batch = fixture_batch(fx, DEV)
+    w = torch.from_numpy(fx["per_weights"]).to(DEV)
+    taus = fixture_taus(fx)
+    results = []
+    for graph in (False, True):
+        cfg, agent = build_product_agent(fx, use_cuda_graph=graph)
+        d = agent.model.distribution_model
+        if d is not None:
+            # pin the quantiles for every call so eager and replayed draws coincide
+            fixed = [torch.as_tensor(t, dtype=torch.float32, device=DEV).view(-1, 1) for t in taus]
+            calls = {"n": 0}
+            models = [agent.model.distribution_model] + ([agent.target_model.distribution_model]
+                                                         if agent.target_model is not None else [])
+            for m in models:
+                orig = m.forward
+
+                def fwd(x, n_quantile_samples=None, for_action=False, static_quantiles=None, _o=orig, _m=m):
+                    rows = (n_quantile_samples or 0) * x.shape[0]
+                    sq = next((t for t in fixed if t.numel() == rows), None)
+                    return _o(x, n_quantile_samples=n_quantile_samples, for_action=for_action, static_quantiles=sq)
+                m.forward = fwd
+        outs = []
+        for _ in range(3):
+            outs.append(agent.update(batch, w).clone())
+        torch.cuda.synchronize()
+        results.append((outs, {k: v.clone() for k, v in agent.model.state_dict().items()}))
+    for a, b in zip(results[0][0], results[1][0]):
+        assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-5
+    for k in results[0][1]:
+        assert rel_err(results[1][1][k].cpu().numpy(), results[0][1][k].cpu().numpy()) < 1e-5, k
+
+
+def test_target_sync_is_one_copy():
+    fx = load_golden("agent_dqn_double")
+    cfg, agent = build_product_agent(fx)
+    agent.sync_target_model()
+    for (k, a), (_, b) in zip(agent.model.state_dict().items(), agent.target_model.state_dict().items()):
+        assert torch.equal(a, b), k

@@ -1,0 +1,149 @@
+"""oracle/buffer_oracle.py (linked-object restatement) and the array n-step restatement in
+oracle/per_oracle.c must reproduce the REFERENCE TimestepBuffer outputs frozen in
+tests/golden/nstep_gather_*.npz; the host link planner of the product library (pure host code,
+runs without a GPU) must produce links that lead to the same answers."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import load_golden, replay_script_oracle, script_from_fixture, script_successor_obs
+
+
+@pytest.mark.parametrize("name", ["nstep_gather_fs1", "nstep_gather_fs4"])
+def test_oracle_buffer_matches_reference(name):
+    fx = load_golden(name)
+    buf, linkers, done = None, None, 0
+    for cp in fx["checkpoints"].tolist():
+        buf, linkers = replay_script_oracle(fx, upto=cp, buf=buf, linkers=linkers, start=done)
+        done = cp
+        idx = fx["cp%d.index" % cp]
+        batch = buf.batch_from([buf.storage[i] for i in idx])
+        tag = "cp%d." % cp
+        assert np.array_equal(batch["observation"], fx[tag + "observation"])
+        assert np.array_equal(batch["next"]["observation"], fx[tag + "next_observation"])
+        assert np.array_equal(batch["action"], fx[tag + "action"])
+        assert np.array_equal(batch["nonterminal"], fx[tag + "nonterminal"])
+        # n-step returns within 1e-6 relative (north star); identical fp64 accumulation -> exact here
+        assert np.array_equal(batch["next"]["reward"], fx[tag + "reward"])
+        assert np.array_equal(batch["gamma"], fx[tag + "gamma"])
+
+
+def plan_script(fx, upto, staging=7):
+    """Run the product's HOST planner (pb_store_extend_plan) over the trace and apply its output to
+    numpy mirrors of the ring arrays -- what pb_store_scatter does on the device."""
+    from prism_b200 import _lib
+    lib = _lib.load()
+    S = script_from_fixture(fx)
+    size = int(fx["capacity"])
+    n_streams, pool = 4, 16
+    aux_size = n_streams + pool
+    E = S["obs"].shape[1]
+    ring = {"obs": np.zeros((size, E), np.float32), "aux": np.zeros((aux_size, E), np.float32),
+            "action": np.zeros(size, np.int32), "reward": np.zeros(size, np.float32),
+            "done": np.zeros(size, np.uint8), "trunc": np.zeros(size, np.uint8),
+            "slot_seq": np.full(size, -1, np.int64), "next_link": np.full(size, -1, np.int64),
+            "prev_link": np.full(size, -1, np.int64)}
+    stream_last = np.full(n_streams, -1, np.int64)
+    cursor = np.zeros(1, np.int64)
+    owner = np.full(pool, -1, np.int64)
+    seq0 = 0
+    P = lambda a: a.ctypes.data
+    while seq0 < upto:
+        n = min(staging, upto - seq0)
+        sl = slice(seq0, seq0 + n)
+        sid = np.ascontiguousarray(S["stream"][sl], np.int32)
+        flags = (S["done"][sl].astype(np.uint8) * 1 + S["trunc"][sl].astype(np.uint8) * 2).astype(np.uint8)
+        meta = np.zeros(n, dtype=np.dtype(_lib.STEP_META_DTYPE))
+        rc = lib.pb_store_extend_plan(size, aux_size, n_streams, n, seq0, P(sid), P(flags), P(stream_last), P(cursor),
+                                      P(owner), P(meta))
+        assert rc == 0
+        seq, prev, nxt, aux, ps, pv = (meta[k] for k in ("seq", "prev_link", "next_link", "aux_row", "patch_slot",
+                                                         "patch_val"))
+        for j in range(n):
+            t = seq0 + j
+            slot = seq[j] % size
+            ring["obs"][slot] = S["obs"][t]
+            ring["action"][slot], ring["reward"][slot] = S["action"][t], S["reward"][t]
+            ring["done"][slot], ring["trunc"][slot] = S["done"][t], S["trunc"][t]
+            ring["slot_seq"][slot], ring["prev_link"][slot], ring["next_link"][slot] = seq[j], prev[j], nxt[j]
+            if ps[j] >= 0:
+                ring["next_link"][ps[j]] = pv[j]
+            if aux[j] >= 0:
+                ring["aux"][aux[j]] = script_successor_obs(S, t)
+        seq0 += n
+    return ring, size
+
+
+def assemble_from_arrays(ring, size, idx, fs, n_step, gamma, obs_shape):
+    """numpy model of pb_store_gather on top of the C n-step restatement."""
+    from oracle.per_oracle import nstep_arrays
+    ret, gam, done, last, succ = nstep_arrays(size, n_step, gamma, ring["slot_seq"], ring["next_link"],
+                                              ring["reward"], ring["done"], ring["trunc"], idx)
+    B, E = len(idx), ring["obs"].shape[1]
+    obs = np.zeros((B, fs, E), np.float32)
+    nobs = np.zeros((B, fs, E), np.float32)
+
+    def alive(link):
+        return link >= 0 and ring["slot_seq"][link % size] == link
+
+    def walk(slot, hops):
+        for _ in range(hops):
+            pl = ring["prev_link"][slot]
+            if not alive(pl):
+                return None
+            slot = pl % size
+        return slot
+
+    for b, start in enumerate(idx):
+        for c in range(fs):
+            cur = walk(start, c)
+            if cur is None:
+                continue
+            obs[b, fs - 1 - c] = ring["obs"][cur]
+            if succ[b] == -1:
+                nobs[b, fs - 1 - c] = ring["obs"][cur]
+            elif c == 0:
+                nobs[b, fs - 1] = ring["obs"][succ[b] % size] if succ[b] >= 0 else ring["aux"][-succ[b] - 2]
+            else:
+                c2 = walk(last[b], c - 1)
+                if c2 is not None:
+                    nobs[b, fs - 1 - c] = ring["obs"][c2]
+    shape = (B, fs) + tuple(obs_shape)
+    return obs.reshape(shape), nobs.reshape(shape), ret, gam, done, ring["action"][idx]
+
+
+@pytest.mark.parametrize("name", ["nstep_gather_fs1", "nstep_gather_fs4"])
+def test_host_planner_and_array_model_match_reference(name):
+    fx = load_golden(name)
+    fs, obs_shape = int(fx["frame_stack"]), tuple(fx["obs_shape"].tolist())
+    for cp in fx["checkpoints"].tolist():
+        ring, size = plan_script(fx, cp)
+        idx = fx["cp%d.index" % cp]
+        obs, nobs, ret, gam, done, act = assemble_from_arrays(ring, size, idx, fs, int(fx["n_step"]),
+                                                              float(fx["gamma"]), obs_shape)
+        tag = "cp%d." % cp
+        assert np.array_equal(obs, fx[tag + "observation"])
+        assert np.array_equal(nobs, fx[tag + "next_observation"])
+        assert np.array_equal(ret, fx[tag + "reward"].reshape(-1))
+        assert np.array_equal(gam, fx[tag + "gamma"].reshape(-1))
+        assert np.array_equal(done == 0, fx[tag + "nonterminal"].reshape(-1))
+        assert np.array_equal(act, fx[tag + "action"].reshape(-1))
+
+
+def test_planner_pool_exhaustion_is_side_effect_free():
+    from prism_b200 import _lib
+    lib = _lib.load()
+    size, n_streams, pool = 64, 2, 2
+    stream_last = np.full(n_streams, -1, np.int64)
+    cursor = np.zeros(1, np.int64)
+    owner = np.full(pool, -1, np.int64)
+    n = 3
+    sid = np.zeros(n, np.int32)
+    flags = np.full(n, 2, np.uint8)            # three truncations, two pool rows
+    meta = np.zeros(n, dtype=np.dtype(_lib.STEP_META_DTYPE))
+    P = lambda a: a.ctypes.data
+    rc = lib.pb_store_extend_plan(size, n_streams + pool, n_streams, n, 0, P(sid), P(flags), P(stream_last), P(cursor),
+                                  P(owner), P(meta))
+    assert rc == _lib.PB_E_POOL
+    assert (stream_last == -1).all() and cursor[0] == 0 and (owner == -1).all()
