@@ -82,6 +82,7 @@ class TimestepBuffer(object):
         self._idx = None
         self._weight = None
         self._free_streams = None
+        self._stream_tail = {}
         self._last_sorted = False
         self._injected_u = None
 
@@ -129,8 +130,12 @@ class TimestepBuffer(object):
                           None if next_obs is None else _to_numpy(next_obs))
         if done or trunc:
             self._free_streams.append(sid)
+            self._stream_tail.pop(sid, None)
         else:
             timestep._pb_stream = sid
+            # the reference's ListStorage keeps every stored Timestep alive, so the collector's weak
+            # `prev` link of the NEXT step resolves; here only the newest step of a stream must stay alive
+            self._stream_tail[sid] = timestep
         if full:
             self._flush()
         return ring.seq + ring.n_staged - 1
@@ -248,6 +253,7 @@ class TimestepBuffer(object):
         if ring is not None:
             ring.clear()
             self._free_streams = list(range(ring.max_streams - 1, -1, -1))
+            self._stream_tail = {}
         if self.buffer._sampler is not None:
             self.buffer._sampler.reset()
 
