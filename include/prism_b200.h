@@ -299,6 +299,21 @@ int pb_adam_clip_step(long long n, float *param, const float *grad, float *exp_a
                       long long *step_count, float lr, float beta1, float beta2, float adam_eps,
                       float max_grad_norm, float *norm_out, float *partial_scratch, void *stream);
 
+/* Dense layers of the Q heads / IQN MLP (nn.Linear inside nn.Sequential in the reference:
+ * prism/agents/models/ffnn_model.py:61-76, q_ensemble.py:26-48, iqn_model.py:30-46), one launch
+ * each, batched over K heads, fp32 FFMA, split-K across a thread-block cluster (DSMEM reduce).
+ *   fwd:        Y[k] (M x N) = act(X[k] (M x J) . W[k]^T (N x J) + b[k]);  act 0 none / 1 ReLU;
+ *               x_head_stride = 0 shares one X between all heads
+ *   bwd_input:  dX[k] (M x J) = (dY[k] . [Ymask[k] > 0]) . W[k];  Ymask NULL = no activation;
+ *               sum_heads != 0: one dX = sum over heads (X was shared)
+ *   bwd_weight: dW[k] (N x J) = (dY[k] . mask)^T . X[k];  db[k] (N) = column sums (optional) */
+int pb_linear_fwd(int K, int M, int N, int J, const float *X, long long x_head_stride, const float *W,
+                  const float *b, int act, float *Y, void *stream);
+int pb_linear_bwd_input(int K, int M, int N, int J, const float *dY, const float *Ymask, const float *W,
+                        int sum_heads, float *dX, void *stream);
+int pb_linear_bwd_weight(int K, int M, int N, int J, const float *dY, const float *Ymask, const float *X,
+                         long long x_head_stride, float *dW, float *db, void *stream);
+
 /* total_loss = mean_b(dist*w) + mean_b(q*w);  td_b = 0.5*dist + 0.5*q | dist | |q|
  * (composite_model.py:135-142, agent.py:58-64).  dist or q may be NULL; w NULL = 1. */
 int pb_loss_combine(int B, const float *dist, const float *q, const float *w, float *total_out,

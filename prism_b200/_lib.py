@@ -84,6 +84,9 @@ SIGNATURES = {
     "pb_grad_sumsq": [_LL, _P, _P, _P, _P, _P],
     "pb_adam_clip_apply": [_LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _I, _P, _P],
     "pb_loss_combine": [_I, _P, _P, _P, _P, _P, _P],
+    "pb_linear_fwd": [_I, _I, _I, _I, _P, _LL, _P, _P, _I, _P, _P],
+    "pb_linear_bwd_input": [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P],
+    "pb_linear_bwd_weight": [_I, _I, _I, _I, _P, _P, _P, _LL, _P, _P, _P],
 }
 _RESTYPES = {"pb_error_string": C.c_char_p, "pb_launch_count": C.c_longlong}
 

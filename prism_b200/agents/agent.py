@@ -118,6 +118,9 @@ class Agent(object):
 
         flat = isinstance(self.optimizer, FlatAdam)
         snap = self.optimizer.snapshot() if flat else None
+        # no autograd graph from an earlier (eager, other-stream) update may stay alive across the capture
+        self._static_total_loss = self._static_distribution_loss = self._static_q_loss = None
+        self.optimizer.zero_grad(set_to_none=True)
         rng_state = torch.cuda.get_rng_state(dev)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

@@ -80,18 +80,19 @@ class IQNModel(nn.Module):
             quantiles = torch.rand([n * n_rows, 1], device=self.device).float()
 
         basis = ops.cos_basis(quantiles, self.n_basis_elements)            # (n*rows, n_basis)
-        phi = self.phi(basis)                                              # (n*rows, F)
+        phi = ops.run_sequential(self.phi, basis)                          # (n*rows, F): Linear + ReLU, one launch
         # quantile-major rows (r = q*rows + b): broadcast the state embedding over q
         h = (phi.view(n, n_rows, -1) * x.unsqueeze(0)).view(n * n_rows, -1)
         if self.model is not None:
             h = self.model(h)
-        z = self.embedding_to_quantile_layer(h)
+        head = self.embedding_to_quantile_layer
+        z = ops.run_sequential(head, h) if isinstance(head, nn.Sequential) else ops.linear(h, head.weight, head.bias)
         if for_action:
             return z.view(n, -1, self.n_actions)
         return z, quantiles
 
     def _embed_quantiles(self, quantiles):
-        return self.phi(ops.cos_basis(quantiles, self.n_basis_elements))
+        return ops.run_sequential(self.phi, ops.cos_basis(quantiles, self.n_basis_elements))
 
     # ------------------------------------------------------------------
     def get_loss(self, embedded_obs, embedded_next_obs, batch_acts, batch_returns, dones_and_gamma, target_model=None):

@@ -101,18 +101,23 @@ class QEnsemble(nn.Module):
             x = torch.as_tensor(x, dtype=torch.float32, device=self.device)
         x = x.view(x.shape[0], -1)
         h = None  # (K, B, width) once the heads have diverged; x is shared before that
-        for kind, i in self._plan:
+        plan, n, i = self._plan, len(self._plan), 0
+        while i < n:
+            kind, si = plan[i]
             if kind == "ln":
-                w, b = self._p(i, "weight"), self._p(i, "bias")
+                w, b = self._p(si, "weight"), self._p(si, "bias")
                 src = x if h is None else h
                 normed = F.layer_norm(src, (src.shape[-1],))            # statistics are head-independent for x
                 h = torch.addcmul(b.unsqueeze(1), normed if h is not None else normed.unsqueeze(0), w.unsqueeze(1))
             elif kind == "linear":
-                w, b = self._p(i, "weight"), self._p(i, "bias")          # (K, out, in), (K, out)
-                src = x.unsqueeze(0).expand(self.n_heads, -1, -1) if h is None else h
-                h = torch.baddbmm(b.unsqueeze(1), src, w.transpose(1, 2))
+                w, b = self._p(si, "weight"), self._p(si, "bias")        # (K, out, in), (K, out)
+                fuse = i + 1 < n and plan[i + 1][0] == "act" and isinstance(self.act, nn.ReLU)
+                h = ops.linear_heads(x if h is None else h, w, b, relu=fuse)   # one launch for all K heads
+                if fuse:
+                    i += 1
             else:
                 h = self.act(h)
+            i += 1
         return h
 
     def forward(self, x):
@@ -134,13 +139,15 @@ class QEnsemble(nn.Module):
 
         q_loss = ops.ensemble_q_loss(q_cur, q_next_online, q_next_target, batch_acts.view(-1), batch_returns,
                                      dones_and_gamma, loss_weight=1.0)
+        theil = self.theil
         if self.ensemble_variation_coef != 0:
             # Theil index of the heads' parameter L2 norms (:86-90); stacked params make it 1 reduction per tensor
             sq = sum(p.square().flatten(1).sum(dim=1) for p in self.stacked)
             l2_set = sq.sqrt()
             ratio = l2_set / l2_set.mean()
-            self.theil = (ratio * torch.log(ratio)).mean()
-        return self.q_loss_weight * (q_loss - self.theil * self.ensemble_variation_coef)
+            theil = (ratio * torch.log(ratio)).mean()
+            self.theil = theil.detach()          # logged value only: never keep an autograd graph on the module
+        return self.q_loss_weight * (q_loss - theil * self.ensemble_variation_coef)
 
     def log(self, logger):
         logger.log_data(data=self.theil.item(), group_name="Debug/Q Ensemble", var_name="Variation Loss")

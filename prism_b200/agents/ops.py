@@ -148,3 +148,70 @@ def loss_combine(dist_loss, q_loss, per_weights):
     """total = mean(dist*w) + mean(q*w); td = 0.5 dist + 0.5 q | dist | |q|
     (prism/agents/agent.py:58-64, prism/agents/models/composite_model.py:135-142)."""
     return _LossCombine.apply(dist_loss, q_loss, per_weights)
+
+
+class _Linear(torch.autograd.Function):
+    """Y = act(X W^T + b), batched over heads.  X: (M, J) shared or (K, M, J); W: (K, N, J); b: (K, N)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        _lib.require_cuda(x, "x")
+        K, N, J = w.shape
+        shared = x.dim() == 2
+        M = x.shape[-2]
+        xc, wc, bc = _c(x), _c(w), (None if b is None else _c(b))
+        y = torch.empty(K, M, N, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().pb_linear_fwd(K, M, N, J, xc.data_ptr(), 0 if shared else M * J, wc.data_ptr(),
+                                             _lib.ptr(bc), int(act), y.data_ptr(), _stream(x)), "pb_linear_fwd")
+        ctx.act, ctx.shared, ctx.dims, ctx.has_bias = int(act), shared, (K, M, N, J), b is not None
+        ctx.save_for_backward(xc, wc, y if act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, wc, y = ctx.saved_tensors
+        K, M, N, J = ctx.dims
+        dy = _c(dy)
+        lib, stream = _lib.load(), _stream(dy)
+        mask = _lib.ptr(y) if ctx.act else None
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, J) if ctx.shared else (K, M, J), dtype=torch.float32, device=dy.device)
+            _lib.check(lib.pb_linear_bwd_input(K, M, N, J, dy.data_ptr(), mask, wc.data_ptr(), int(ctx.shared),
+                                               dx.data_ptr(), stream), "pb_linear_bwd_input")
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.empty(K, N, J, dtype=torch.float32, device=dy.device)
+            db = torch.empty(K, N, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+            _lib.check(lib.pb_linear_bwd_weight(K, M, N, J, dy.data_ptr(), mask, xc.data_ptr(),
+                                                0 if ctx.shared else M * J, dw.data_ptr(), _lib.ptr(db), stream),
+                       "pb_linear_bwd_weight")
+        return dx, dw, db, None
+
+
+def linear_heads(x, w, b, relu=False):
+    """Stacked-head dense layer: x (M, J) shared by all heads or (K, M, J); w (K, N, J); b (K, N) -> (K, M, N)."""
+    return _Linear.apply(x, w, b, 1 if relu else 0)
+
+
+def linear(x, weight, bias, relu=False):
+    """nn.Linear (+ optional fused ReLU) on a 2-D input through the fused kernel."""
+    b = None if bias is None else bias.unsqueeze(0)
+    return _Linear.apply(x, weight.unsqueeze(0), b, 1 if relu else 0).squeeze(0)
+
+
+def run_sequential(seq, x):
+    """Evaluate an nn.Sequential of Linear / ReLU / LayerNorm / ... modules, routing every Linear (with a
+    directly following ReLU fused in) through the fused kernel.  Other modules run as they are."""
+    import torch.nn as nn
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, nn.Linear) and x.dim() == 2 and x.is_cuda:
+            fuse = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+            x = linear(x, m.weight, m.bias, relu=fuse)
+            i += 2 if fuse else 1
+        else:
+            x = m(x)
+            i += 1
+    return x

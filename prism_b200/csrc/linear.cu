@@ -1,0 +1,310 @@
+// linear.cu -- dense layers of the Q heads / IQN MLP as one fused launch each (sm_100a).
+//
+// The reference evaluates its heads with nn.Linear inside nn.Sequential
+// (prism/agents/models/ffnn_model.py:61-76, q_ensemble.py:26-48, iqn_model.py:30-46): per layer a
+// cuBLAS sgemm + bias add + activation, and autograd mirrors.  At learner batch sizes (64-512 rows)
+// cuBLAS picks a 32x32 SIMT tile on <= 64 CTAs (29 us per layer on a B200, profiles/launches_r01_step.txt)
+// and the element-wise glue costs as much again.  Here one kernel does
+//     forward   Y = act(X W^T + b)                       (bias + ReLU fused)
+//     backward  dX = (dY . relu') W,  dW = (dY . relu')^T X,  db = colsum(dY . relu')   (mask fused on load,
+//               bias gradient fused into the dW launch)
+// batched over the K ensemble heads, fp32 FFMA (the reference's math: parity 1e-4 needs fp32 products),
+// and fills the chip on small problems with split-K over a THREAD-BLOCK CLUSTER: the S CTAs of a
+// cluster each reduce a slice of the inner dimension and combine their 64x64 partial tiles through
+// distributed shared memory in a fixed order -- deterministic, no atomics, no workspace, one launch.
+#include "common.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+using namespace pb;
+
+constexpr int TM = 64, TN = 64, TK = 16, PAD = 4;
+
+struct GemmArgs {
+    const float *A, *B, *bias, *mask;
+    float *C, *colsum;
+    long long a_bs, b_bs, c_bs, bias_bs, colsum_bs;     // batch (head) strides, elements
+    long long a_ss, b_ss;                               // segment strides (inner dimension made of n_seg pieces)
+    int lda, ldb, ldc;
+    int M, N, K;                                        // C is M x N, inner dimension K per segment
+    int n_seg, splits, act, m_tiles;
+};
+
+template <bool KMAJOR>
+__device__ __forceinline__ void load_tile(float (&r)[4], const float *__restrict__ P, const float *__restrict__ mask,
+                                          int ld, int row0, int k0, int rows, int kmax, int t)
+{
+    // tile is [TK][64] in smem (k-major).  KMAJOR: memory contiguous along k -> thread owns 4 consecutive k of one row.
+    // else: memory contiguous along the row index -> thread owns 4 consecutive rows of one k.
+    int row, k;
+    if (KMAJOR) { row = row0 + (t >> 2); k = k0 + ((t & 3) << 2); }
+    else        { k = k0 + (t >> 4); row = row0 + ((t & 15) << 2); }
+    const bool vec_ok = (ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(P) & 15) == 0);
+    if (KMAJOR) {
+        const long long off = (long long)row * ld + k;
+        if (vec_ok && row < rows && k + 3 < kmax && (k & 3) == 0) {
+            float4 v = *reinterpret_cast<const float4 *>(P + off);
+            r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+            if (mask) {
+                float4 m = *reinterpret_cast<const float4 *>(mask + off);
+                r[0] = m.x > 0.f ? r[0] : 0.f; r[1] = m.y > 0.f ? r[1] : 0.f;
+                r[2] = m.z > 0.f ? r[2] : 0.f; r[3] = m.w > 0.f ? r[3] : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float v = 0.f;
+                if (row < rows && k + q < kmax) {
+                    v = P[off + q];
+                    if (mask && !(mask[off + q] > 0.f)) v = 0.f;
+                }
+                r[q] = v;
+            }
+        }
+    } else {
+        const long long off = (long long)k * ld + row;
+        if (vec_ok && k < kmax && row + 3 < rows && (row & 3) == 0) {
+            float4 v = *reinterpret_cast<const float4 *>(P + off);
+            r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+            if (mask) {
+                float4 m = *reinterpret_cast<const float4 *>(mask + off);
+                r[0] = m.x > 0.f ? r[0] : 0.f; r[1] = m.y > 0.f ? r[1] : 0.f;
+                r[2] = m.z > 0.f ? r[2] : 0.f; r[3] = m.w > 0.f ? r[3] : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float v = 0.f;
+                if (k < kmax && row + q < rows) {
+                    v = P[off + q];
+                    if (mask && !(mask[off + q] > 0.f)) v = 0.f;
+                }
+                r[q] = v;
+            }
+        }
+    }
+}
+
+template <bool KMAJOR>
+__device__ __forceinline__ void store_tile(float (*S)[TM + PAD], const float (&r)[4], int t)
+{
+    if (KMAJOR) {
+        const int row = t >> 2, k = (t & 3) << 2;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) S[k + q][row] = r[q];
+    } else {
+        const int k = t >> 4, row = (t & 15) << 2;
+        *reinterpret_cast<float4 *>(&S[k][row]) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+}
+
+// C[i][j] = epilogue( sum_seg sum_k A(i,k) B(k,j) )   grid: (n tiles, m tiles * batch, splits); cluster (1,1,splits)
+template <bool A_KMAJOR, bool B_KMAJOR, bool ROWSUM>
+__global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g)
+{
+    __shared__ __align__(16) float As[2][TK][TM + PAD];
+    __shared__ __align__(16) float Bs[2][TK][TN + PAD];
+    __shared__ __align__(16) float Cs[TM][TN + PAD];
+    __shared__ float Rs[TM];
+
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const int batch = blockIdx.y / g.m_tiles, mt = blockIdx.y % g.m_tiles;
+    const int i0 = mt * TM, j0 = blockIdx.x * TN;
+    const int split = blockIdx.z;
+    const float *A = g.A + batch * g.a_bs, *B = g.B + batch * g.b_bs;
+    const float *mask = g.mask ? g.mask + batch * g.a_bs : nullptr;
+
+    // iteration space: n_seg segments x ceil(K/TK) chunks, dealt to the splits in contiguous ranges
+    const int chunks_per_seg = (g.K + TK - 1) / TK;
+    const int total = g.n_seg * chunks_per_seg;
+    const int per = (total + g.splits - 1) / g.splits;
+    const int it0 = split * per, it1 = min(total, it0 + per);
+
+    float acc[4][4] = {};
+    float rs[4] = {};
+    float ra[4], rb[4];
+    const bool want_rowsum = ROWSUM && g.colsum != nullptr && blockIdx.x == 0;
+
+    auto fetch = [&](int it) {
+        const int seg = it / chunks_per_seg, k0 = (it % chunks_per_seg) * TK;
+        load_tile<A_KMAJOR>(ra, A + seg * g.a_ss, mask ? mask + seg * g.a_ss : nullptr, g.lda, i0, k0, g.M, g.K, t);
+        load_tile<B_KMAJOR>(rb, B + seg * g.b_ss, nullptr, g.ldb, j0, k0, g.N, g.K, t);
+    };
+    int buf = 0;
+    if (it0 < it1) {
+        fetch(it0);
+        store_tile<A_KMAJOR>(As[0], ra, t);
+        store_tile<B_KMAJOR>(Bs[0], rb, t);
+    }
+    __syncthreads();
+    for (int it = it0; it < it1; ++it) {
+        const bool more = it + 1 < it1;
+        if (more) fetch(it + 1);
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+            const float4 a = *reinterpret_cast<const float4 *>(&As[buf][k][ty << 2]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx << 2]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+                if (ROWSUM) rs[r] += av[r];
+            }
+        }
+        if (more) {
+            store_tile<A_KMAJOR>(As[buf ^ 1], ra, t);
+            store_tile<B_KMAJOR>(Bs[buf ^ 1], rb, t);
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+
+    float *C = g.C + batch * g.c_bs;
+    const float *bias = g.bias ? g.bias + batch * g.bias_bs : nullptr;
+    auto emit = [&](int i, int j, float v) {
+        if (i < g.M && j < g.N) {
+            if (bias) v += bias[j];
+            if (g.act == 1) v = fmaxf(v, 0.f);
+            C[(long long)i * g.ldc + j] = v;
+        }
+    };
+    if (g.splits == 1) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = i0 + (ty << 2) + r, j = j0 + (tx << 2);
+            if (i < g.M && j + 3 < g.N && (g.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+                float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                if (bias) { v.x += bias[j]; v.y += bias[j + 1]; v.z += bias[j + 2]; v.w += bias[j + 3]; }
+                if (g.act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                *reinterpret_cast<float4 *>(C + (long long)i * g.ldc + j) = v;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) emit(i, j + c, acc[r][c]);
+            }
+        }
+        if (want_rowsum && tx == 0) {
+            float *cs = g.colsum + batch * g.colsum_bs;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) if (i0 + (ty << 2) + r < g.M) cs[i0 + (ty << 2) + r] = rs[r];
+        }
+        return;
+    }
+
+    // split-K: partial tiles meet in distributed shared memory, summed in rank order (deterministic)
+    cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        *reinterpret_cast<float4 *>(&Cs[(ty << 2) + r][tx << 2]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    if (tx == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) Rs[(ty << 2) + r] = rs[r];
+    }
+    cluster.sync();
+    const int S = g.splits, rank = (int)cluster.block_rank();
+    const int rows_per = TM / S;                           // S in {2,4,8}
+    for (int e = t; e < rows_per * TN; e += 256) {
+        const int r = rank * rows_per + e / TN, c = e % TN;
+        float v = 0.f;
+        for (int s = 0; s < S; ++s) {
+            const float *remote = cluster.map_shared_rank(&Cs[0][0], s);
+            v += remote[r * (TN + PAD) + c];
+        }
+        emit(i0 + r, j0 + c, v);
+    }
+    if (want_rowsum && t < rows_per) {
+        const int r = rank * rows_per + t;
+        float v = 0.f;
+        for (int s = 0; s < S; ++s) v += cluster.map_shared_rank(&Rs[0], s)[r];
+        if (i0 + r < g.M) g.colsum[batch * g.colsum_bs + i0 + r] = v;
+    }
+    cluster.sync();                                        // nobody exits while its tile is still being read
+}
+
+int pick_splits(long long tiles, int total_chunks)
+{
+    const int sms = pb_sm_count();
+    int s = 1;
+    while (s < 8 && tiles * (s * 2) <= 2LL * sms && total_chunks / (s * 2) >= 2) s *= 2;
+    return s;
+}
+
+template <bool AK, bool BK, bool ROWSUM>
+int launch_gemm(GemmArgs g, int batch, void *stream)
+{
+    g.m_tiles = (g.M + TM - 1) / TM;
+    const int n_tiles = (g.N + TN - 1) / TN;
+    const int total_chunks = g.n_seg * ((g.K + TK - 1) / TK);
+    g.splits = pick_splits((long long)g.m_tiles * n_tiles * batch, total_chunks);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_tiles, (unsigned)(g.m_tiles * batch), (unsigned)g.splits);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)g.splits;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<AK, BK, ROWSUM>, g);
+    g_pb_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaGetLastError();
+    return e == cudaSuccess ? PB_OK : (int)e;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Y[k] (M x N) = act(X[k] (M x J) W[k]^T (N x J) + b[k]);  x_head_stride 0 = one X shared by every head
+int pb_linear_fwd(int K, int M, int N, int J, const float *X, long long x_head_stride, const float *W,
+                  const float *b, int act, float *Y, void *stream)
+{
+    if (K <= 0 || M <= 0 || N <= 0 || J <= 0 || !X || !W || !Y || (act != 0 && act != 1)) return PB_E_ARG;
+    GemmArgs g = {};
+    g.A = X; g.a_bs = x_head_stride; g.lda = J;
+    g.B = W; g.b_bs = (long long)N * J; g.ldb = J;
+    g.C = Y; g.c_bs = (long long)M * N; g.ldc = N;
+    g.bias = b; g.bias_bs = N; g.act = act;
+    g.M = M; g.N = N; g.K = J; g.n_seg = 1;
+    return launch_gemm<true, true, false>(g, K, stream);
+}
+
+// dX[k] (M x J) = (dY[k] . [Ymask[k] > 0]) (M x N) W[k] (N x J).
+// sum_heads != 0: ONE dX (M x J) = sum over the K heads (X was shared): heads become segments of the inner dimension.
+int pb_linear_bwd_input(int K, int M, int N, int J, const float *dY, const float *Ymask, const float *W,
+                        int sum_heads, float *dX, void *stream)
+{
+    if (K <= 0 || M <= 0 || N <= 0 || J <= 0 || !dY || !W || !dX) return PB_E_ARG;
+    GemmArgs g = {};
+    g.A = dY; g.mask = Ymask; g.lda = N;
+    g.B = W; g.ldb = J;
+    g.C = dX; g.ldc = J;
+    g.M = M; g.N = J; g.K = N;
+    if (sum_heads) {
+        g.n_seg = K; g.a_ss = (long long)M * N; g.b_ss = (long long)N * J;
+        return launch_gemm<true, false, false>(g, 1, stream);
+    }
+    g.n_seg = 1; g.a_bs = (long long)M * N; g.b_bs = (long long)N * J; g.c_bs = (long long)M * J;
+    return launch_gemm<true, false, false>(g, K, stream);
+}
+
+// dW[k] (N x J) = (dY[k] . mask)^T X[k];  db[k] (N) = column sums of (dY[k] . mask)   (db optional)
+int pb_linear_bwd_weight(int K, int M, int N, int J, const float *dY, const float *Ymask, const float *X,
+                         long long x_head_stride, float *dW, float *db, void *stream)
+{
+    if (K <= 0 || M <= 0 || N <= 0 || J <= 0 || !dY || !X || !dW) return PB_E_ARG;
+    GemmArgs g = {};
+    g.A = dY; g.mask = Ymask; g.lda = N; g.a_bs = (long long)M * N;      // A(i = n, k = m): contiguous along i
+    g.B = X; g.ldb = J; g.b_bs = x_head_stride;                          // B(k = m, j): contiguous along j
+    g.C = dW; g.ldc = J; g.c_bs = (long long)N * J;
+    g.colsum = db; g.colsum_bs = N;
+    g.M = N; g.N = J; g.K = M; g.n_seg = 1;
+    return db ? launch_gemm<false, false, true>(g, K, stream) : launch_gemm<false, false, false>(g, K, stream);
+}
+
+}  // extern "C"

@@ -110,6 +110,12 @@ class LearnerStep:
     def _capture(self, draw):
         opt = self.agent.optimizer
         flat = isinstance(opt, FlatAdam)
+        # drop every reference to autograd graphs built on another stream (an eager update leaves its
+        # loss tensors on the agent): their AccumulateGrad nodes would tie the capture to that stream
+        ag = self.agent
+        ag._static_total_loss = ag._static_distribution_loss = ag._static_q_loss = None
+        self.td = None
+        opt.zero_grad(set_to_none=True)
         # warm-up on a side stream; it must neither train nor disturb the priorities
         snap = opt.snapshot() if flat else None
         tree_snap = (self.tree.sum.clone(), self.tree.min.clone(), self.tree.state.clone())

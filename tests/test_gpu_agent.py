@@ -234,3 +234,67 @@ def test_target_sync_is_one_copy():
     agent.sync_target_model()
     for (k, a), (_, b) in zip(agent.model.state_dict().items(), agent.target_model.state_dict().items()):
         assert torch.equal(a, b), k
+
+
+def test_learner_step_graph_after_eager_update():
+    """An eager update on the default stream followed by a captured LearnerStep (what smoke() does):
+    capture must not inherit autograd state from the default stream, and the graph must train."""
+    import prism_b200
+    from prism_b200.learner_step import LearnerStep
+    from oracle.gen_golden import make_script
+    cap, B, obs_shape, A = 256, 16, (10, 10, 4), 3
+    cfg = prism_b200.minatar_ids_iqn_config(device=DEV, experience_replay_capacity=cap, batch_size=B,
+                                            iqn_n_current_state_quantile_samples=8,
+                                            iqn_n_next_state_quantile_samples=8, iqn_quantile_samples_per_action=8,
+                                            iqn_quantile_model_feature_dim=32, ids_q_head_feature_dim=16,
+                                            ids_n_q_heads=3, use_cuda_graph=False, replay_max_streams=4,
+                                            replay_staging_rows=32)
+    torch.manual_seed(0)
+    agent = prism_b200.build_agent(cfg, obs_shape, A)
+    buf = prism_b200.build_exp_buffer(cfg)
+    S = make_script(3, n_streams=4, n_steps=300, obs_shape=obs_shape, p_done=0.05, p_trunc=0.02, n_actions=A)
+    succ = np.where(S["trunc"][:, None], S["final_obs"], S["next_obs"])
+    buf.extend_batch(S["stream"], S["obs"].reshape((-1,) + obs_shape), S["action"], S["reward"], S["done"],
+                     S["trunc"], succ.reshape((-1,) + obs_shape))
+    batch, info = buf.sample(return_info=True)
+    td = agent.update(batch, info["_weight"])                       # eager, default stream
+    buf.update_priority(info["index"], td.abs())
+    before = agent.optimizer.arena.clone()
+    step = LearnerStep(buf, agent, batch_size=B, use_cuda_graph=True)
+    losses = [float(step.step()) for _ in range(5)]
+    torch.cuda.synchronize()
+    assert all(np.isfinite(losses))
+    assert int(agent.optimizer.step_count) == 1 + 5                  # warm-up iterations did not train
+    assert not torch.equal(before, agent.optimizer.arena)
+    assert step.launches_per_step is not None and step.launches_per_step > 0
+    st = buf.buffer._sampler.state_host()
+    assert st["status"] == 0 and st["len"] == cap
+
+
+@pytest.mark.parametrize("K,M,N,J,shared,relu", [
+    (1, 256, 256, 1024, True, True), (1, 256, 4, 256, False, False), (10, 64, 256, 1024, True, True),
+    (10, 64, 3, 256, False, False), (3, 37, 19, 50, False, True), (1, 2048, 256, 1024, True, True),
+    (4, 5, 7, 3, True, False), (1, 512, 512, 3136, True, True)])
+def test_fused_linear_matches_torch(K, M, N, J, shared, relu):
+    """pb_linear_{fwd,bwd_input,bwd_weight} (cluster split-K SIMT GEMM with fused bias/ReLU/mask/bias-grad)
+    against torch fp64 math; tolerance 1e-5 relative of the tensor's max (fp32 accumulation order)."""
+    from prism_b200.agents import ops
+    g = torch.Generator().manual_seed(K * 1000 + M + N + J)
+    x = torch.randn((M, J) if shared else (K, M, J), generator=g)
+    w = torch.randn(K, N, J, generator=g) / J ** 0.5
+    b = torch.randn(K, N, generator=g)
+    gy = torch.randn(K, M, N, generator=g)
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    xe = xr.unsqueeze(0).expand(K, M, J) if shared else xr
+    yr = torch.baddbmm(br.unsqueeze(1), xe, wr.transpose(1, 2))
+    if relu:
+        yr = yr.relu()
+    yr.backward(gy.double())
+    xd, wd, bd = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    y = ops.linear_heads(xd, wd, bd, relu=relu)
+    y.backward(gy.to(DEV))
+    torch.cuda.synchronize()
+    assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) < 2e-5
+    assert rel_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 2e-5
+    assert rel_err(wd.grad.cpu().numpy(), wr.grad.numpy()) < 2e-5
+    assert rel_err(bd.grad.cpu().numpy(), br.grad.numpy()) < 2e-5
