@@ -434,9 +434,7 @@ def run_ours(args):
            "host_wall_s": round(wall, 4), "loss": float(loss_host)}
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        _finish(world, dist)
         return
     # ---------------- roofline + extras + CPU baseline (rank 0) ---------------------------------
     roof, ktable = kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src)
@@ -463,9 +461,19 @@ def run_ours(args):
         "extras": extras,
     }
     print(json.dumps(line))
+    _finish(world, dist)
+
+
+def _finish(world, dist):
+    """Leave together.  The captured graph holds NCCL work: tearing the process group down under it
+    can block, so ranks synchronise once more and exit without the teardown."""
+    sys.stdout.flush()
     if world > 1:
+        import torch
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_reference(args):

@@ -240,14 +240,17 @@ int pb_iqn_cos_basis(long long n_rows, int n_basis, const float *tau, float *out
  *   a* = argmax_a mean_j z_next_online; y_bj = R_b + gdn_b * z_next_target[j,b,a*]
  *   delta = y_bj - theta_bi; Huber(kappa); rho = |tau_bi - 1{delta<0}| * L / kappa
  *   loss_b = loss_weight * mean_j sum_i rho
+ *   nonterminal (optional, torch.bool bytes): the bootstrap factor is gdn_b * nonterminal_b, i.e.
+ *   gdn = gamma^k alone (composite_model.py:110 fused in); NULL = gdn already holds the product.
  * grad_z_cur [T*B][A] = grad_scale * row_weight[b] * d loss_b / d z_cur (zero outside the
  * taken action; row_weight NULL = 1).  With row_weight = PER weights and grad_scale = 1/B
  * this is d mean(loss*w) / d z_cur (prism/agents/agent.py:58-60). */
 int pb_iqn_qh_loss(int B, int T, int Tp, int A, const float *z_cur, const float *tau,
                    const float *z_next_online, const float *z_next_target,
-                   const long long *action, const float *ret, const float *gdn, float kappa,
-                   float loss_weight, const float *row_weight, float grad_scale, float *loss_out,
-                   float *grad_z_cur, void *stream);
+                   const long long *action, const float *ret, const float *gdn,
+                   const uint8_t *nonterminal, float kappa, float loss_weight,
+                   const float *row_weight, float grad_scale, float *loss_out, float *grad_z_cur,
+                   void *stream);
 
 /* QEnsemble.get_loss (prism/agents/models/q_ensemble.py:50-92) without the
  * Theil term: tables are head-major [K][B][A].
@@ -255,8 +258,9 @@ int pb_iqn_qh_loss(int B, int T, int Tp, int A, const float *z_cur, const float 
  *   loss_b = loss_weight * mean_k (q_cur[k,b,a_b] - y_k)^2;  grad_q_cur [K][B][A] */
 int pb_ens_q_loss(int B, int A, int K, const float *q_cur, const float *q_next_online,
                   const float *q_next_target, const long long *action, const float *ret,
-                  const float *gdn, float loss_weight, const float *row_weight, float grad_scale,
-                  float *loss_out, float *grad_q_cur, void *stream);
+                  const float *gdn, const uint8_t *nonterminal, float loss_weight,
+                  const float *row_weight, float grad_scale, float *loss_out, float *grad_q_cur,
+                  void *stream);
 
 /* IDSActionSelector.generate_action_probs + select_action
  * (prism/agents/action_selectors.py:125-176), deterministic branch.
@@ -299,6 +303,18 @@ int pb_adam_clip_step(long long n, float *param, const float *grad, float *exp_a
                       long long *step_count, float lr, float beta1, float beta2, float adam_eps,
                       float max_grad_norm, float *norm_out, float *partial_scratch, void *stream);
 
+/* MinAtarModel embedding (prism/agents/models/minatar_cnn_model.py:13-18, 41-44) in one launch:
+ * x (B, H, W, C) channels-last fp32 -> conv3x3 stride 1 no padding (weight (OC, C, 3, 3), torch layout)
+ * + bias + ReLU -> out (B, OC*(H-2)*(W-2)) in NCHW-flatten order.
+ * Backward (observations need no gradient): dw (OC, C, 3, 3), db (OC) from dout masked by out > 0;
+ * partial_scratch holds pb_conv3x3_relu_bwd_groups(B) * (OC*C*9 + OC) floats. */
+int pb_conv3x3_relu_fwd(int B, int H, int W, int C, int OC, const float *x, const float *w,
+                        const float *bias, float *out, void *stream);
+int pb_conv3x3_relu_bwd_groups(int B);
+int pb_conv3x3_relu_bwd(int B, int H, int W, int C, int OC, const float *x, const float *out,
+                        const float *dout, float *partial_scratch, float *dw, float *db,
+                        void *stream);
+
 /* Dense layers of the Q heads / IQN MLP (nn.Linear inside nn.Sequential in the reference:
  * prism/agents/models/ffnn_model.py:61-76, q_ensemble.py:26-48, iqn_model.py:30-46), one launch
  * each, batched over K heads, fp32 FFMA, split-K across a thread-block cluster (DSMEM reduce).
@@ -314,10 +330,12 @@ int pb_linear_bwd_input(int K, int M, int N, int J, const float *dY, const float
 int pb_linear_bwd_weight(int K, int M, int N, int J, const float *dY, const float *Ymask, const float *X,
                          long long x_head_stride, float *dW, float *db, void *stream);
 
-/* total_loss = mean_b(dist*w) + mean_b(q*w);  td_b = 0.5*dist + 0.5*q | dist | |q|
- * (composite_model.py:135-142, agent.py:58-64).  dist or q may be NULL; w NULL = 1. */
-int pb_loss_combine(int B, const float *dist, const float *q, const float *w, float *total_out,
-                    float *td_out, void *stream);
+/* total_loss = mean_b(dist*w) + mean_b(q'*w);  td_b = 0.5*dist + 0.5*q' | dist | |q'|
+ * (composite_model.py:135-142, agent.py:58-64) with q' = q_scale * (q - *q_offset)
+ * (q_ensemble.py:92: q_loss_weight * (q_loss - theil * coef); q_offset NULL = 0).
+ * dist or q may be NULL; w NULL = 1. */
+int pb_loss_combine(int B, const float *dist, const float *q, const float *w, float q_scale,
+                    const float *q_offset, float *total_out, float *td_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -75,15 +75,18 @@ SIGNATURES = {
     "pb_store_gather": [_STORE, _LL, _P, _P, _P, _P, _P, _P, _P, _P],
     "pb_store_nstep": [_STORE, _LL, _P, _P, _P, _P, _P, _P, _P],
     "pb_iqn_cos_basis": [_LL, _I, _P, _P, _P],
-    "pb_iqn_qh_loss": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _P, _F, _P, _P, _P],
-    "pb_ens_q_loss": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _F, _P, _F, _P, _P, _P],
+    "pb_iqn_qh_loss": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _P, _F, _P, _P, _P],
+    "pb_ens_q_loss": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _F, _P, _F, _P, _P, _P],
     "pb_ids_select": [_I, _I, _I, _I, _P, _P, _F, _F, _F, _P, _P, _P],
     "pb_greedy_select": [_I, _I, _I, _P, _P, _P],
     "pb_adam_clip_step": [_LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
     "pb_pack_grads": [_I, _P, _F, _P, _P, _P, _P, _P],
     "pb_grad_sumsq": [_LL, _P, _P, _P, _P, _P],
     "pb_adam_clip_apply": [_LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _I, _P, _P],
-    "pb_loss_combine": [_I, _P, _P, _P, _P, _P, _P],
+    "pb_loss_combine": [_I, _P, _P, _P, _F, _P, _P, _P, _P],
+    "pb_conv3x3_relu_fwd": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "pb_conv3x3_relu_bwd_groups": [_I],
+    "pb_conv3x3_relu_bwd": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "pb_linear_fwd": [_I, _I, _I, _I, _P, _LL, _P, _P, _I, _P, _P],
     "pb_linear_bwd_input": [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P],
     "pb_linear_bwd_weight": [_I, _I, _I, _I, _P, _P, _P, _LL, _P, _P, _P],

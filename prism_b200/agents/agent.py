@@ -65,13 +65,19 @@ class Agent(object):
         return new_per_weights
 
     def _loss_and_backward(self, batch, per_weights, target_model):
-        dist_loss, q_loss, td = self.model.get_losses(batch, target_model)
-        if dist_loss is None and q_loss is None:
-            return None, None, None, 0
-        w = per_weights if isinstance(per_weights, torch.Tensor) else None
-        total, _ = ops.loss_combine(dist_loss, q_loss, w)       # mean(dist*w) + mean(q*w)  (agent.py:58-64)
-        if w is None and per_weights != 1:
-            total = total * per_weights
+        if hasattr(self.model, "losses_total"):
+            # fused head: loss kernels emit PER-weighted gradients directly (agent.py:58-64 folded in)
+            dist_loss, q_loss, total, td = self.model.losses_total(batch, target_model, per_weights)
+            if total is None:
+                return None, None, None, 0
+        else:
+            dist_loss, q_loss, td = self.model.get_losses(batch, target_model)
+            if dist_loss is None and q_loss is None:
+                return None, None, None, 0
+            w = per_weights if isinstance(per_weights, torch.Tensor) else None
+            total, _ = ops.loss_combine(dist_loss, q_loss, w)   # mean(dist*w) + mean(q*w)  (agent.py:58-64)
+            if w is None and per_weights != 1:
+                total = total * per_weights
         self.optimizer.zero_grad(set_to_none=True)
         total.backward()
         return dist_loss, q_loss, total, td

@@ -41,6 +41,10 @@ class MinAtarModel(nn.Module):
 
     def forward(self, x):
         # MinAtar observations are channels-last (10, 10, C)
+        conv = self.model[0]
+        if x.is_cuda and isinstance(self.model[1], nn.ReLU) and x.dim() == 4 and x.shape[1] <= 16 and x.shape[2] <= 16:
+            from .. import ops
+            return ops.conv3x3_relu_flatten(x.float(), conv.weight, conv.bias)   # conv+bias+ReLU+flatten: one launch
         return self.model(x.permute(0, 3, 1, 2).float())
 
     def log(self, logger):

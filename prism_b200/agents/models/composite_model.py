@@ -110,6 +110,60 @@ class CompositeModel(nn.Module):
                                          None if q_loss is None else q_loss.detach(), None)
         return dist_loss, q_loss, td
 
+    def losses_total(self, batch, target_model, per_weights=None):
+        """get_losses + the PER-weighted total of Agent.update (agent.py:58-64) as one fused head:
+        returns (dist_loss, q_loss, total, td).  Same math as get_losses followed by
+        mean(dist*w) + mean(q*w); the bootstrap factor gamma^k * nonterminal, both loss heads, the TD mix
+        and the gradients w.r.t. the network outputs come out of three launches."""
+        obs = batch["observation"]
+        next_obs = batch["next"]["observation"]
+        if obs.shape[1] == 1:
+            obs, next_obs = obs.squeeze(1), next_obs.squeeze(1)
+        returns = batch["next"]["reward"].flatten()
+        gamma = batch["gamma"].flatten()
+        nonterm = batch["nonterminal"].flatten()
+        act = batch["action"]
+        if act.dim() == 2 and act.shape[-1] != 1:
+            act = act.argmax(dim=-1)
+        acts = act.flatten()
+        if nonterm.dtype != torch.bool:
+            gamma, nonterm = gamma.float() * nonterm.float(), None
+
+        emb = self.embedding_model(obs)
+        with torch.no_grad():
+            if target_model is not None:
+                emb_next = target_model.embedding_model(next_obs)
+                dist_target, q_target = target_model.distribution_model, target_model.q_function_model
+            else:
+                emb_next = self.embedding_model(next_obs)
+                dist_target = q_target = None
+        iqn, ens = self.distribution_model, self.q_function_model
+        if iqn is None and ens is None:
+            return None, None, None, None
+        z_cur = tau = z_on = z_tg = q_cur = q_on = q_tg = None
+        T = Tp = 0
+        kappa = dist_w = q_w = 1.0
+        theil = None
+        if iqn is not None:
+            z_cur, tau, z_on, z_tg = iqn.quantile_tables(emb, emb_next, dist_target)
+            T, Tp, kappa, dist_w = (iqn.n_current_quantile_samples, iqn.n_next_quantile_samples, iqn.huber_k,
+                                    iqn.distributional_loss_weight)
+        if ens is not None:
+            q_cur, q_on, q_tg = ens.q_tables(emb, emb_next, q_target)
+            q_w = ens.q_loss_weight
+            theil = ens.theil_index()
+        w = per_weights if isinstance(per_weights, torch.Tensor) else None
+        off = None if theil is None else (theil.detach() * ens.ensemble_variation_coef).float()
+        total, dist, mse, td = ops.fused_total_loss(z_cur, q_cur, tau, z_on, z_tg, q_on, q_tg, acts, returns, gamma,
+                                                    nonterm, w, off, T, Tp, kappa, dist_w, q_w)
+        if theil is not None:
+            # the regulariser's own gradient: d total / d theil = -q_w * coef * mean(w)
+            mean_w = w.mean() if w is not None else 1.0
+            total = total + (theil - theil.detach()) * (-(q_w * ens.ensemble_variation_coef) * mean_w)
+        if w is None and not isinstance(per_weights, torch.Tensor) and per_weights not in (None, 1):
+            total = total * per_weights
+        return (dist if iqn is not None else None), (mse if ens is not None else None), total, td
+
     def log(self, logger):
         for m in (self.embedding_model, self.distribution_model, self.q_function_model):
             if m is not None:

@@ -95,15 +95,15 @@ class IQNModel(nn.Module):
         return ops.run_sequential(self.phi, ops.cos_basis(quantiles, self.n_basis_elements))
 
     # ------------------------------------------------------------------
-    def get_loss(self, embedded_obs, embedded_next_obs, batch_acts, batch_returns, dones_and_gamma, target_model=None):
+    def quantile_tables(self, embedded_obs, embedded_next_obs, target_model=None):
+        """(z_cur, tau, z_next_online, z_next_target): the three forward passes of get_loss, in the
+        reference's draw order -- tau (current), tau' (online next), tau' (target next)  (:104-126)."""
         if not self.propagate_grad:
             embedded_obs = embedded_obs.detach()
             embedded_next_obs = embedded_next_obs.detach()
         if target_model is None:
             target_model = self
         T, Tp = self.n_current_quantile_samples, self.n_next_quantile_samples
-
-        # draw order: tau (current), tau' (online next), tau' (target next)  -- as the reference
         z_cur, tau = self.forward(embedded_obs, n_quantile_samples=T)
         with torch.no_grad():
             if target_model is self:
@@ -115,9 +115,13 @@ class IQNModel(nn.Module):
             else:
                 z_next_target = target_model.forward(embedded_next_obs, n_quantile_samples=Tp)[0]
                 z_next_online = z_next_target
+        return z_cur, tau, z_next_online, z_next_target
 
+    def get_loss(self, embedded_obs, embedded_next_obs, batch_acts, batch_returns, dones_and_gamma, target_model=None):
+        z_cur, tau, z_next_online, z_next_target = self.quantile_tables(embedded_obs, embedded_next_obs, target_model)
         return ops.quantile_huber_loss(z_cur, tau, z_next_online, z_next_target, batch_acts, batch_returns,
-                                       dones_and_gamma, T, Tp, kappa=self.huber_k,
+                                       dones_and_gamma, self.n_current_quantile_samples,
+                                       self.n_next_quantile_samples, kappa=self.huber_k,
                                        loss_weight=self.distributional_loss_weight)
 
     def log(self, logger):

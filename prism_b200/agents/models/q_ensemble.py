@@ -124,7 +124,8 @@ class QEnsemble(nn.Module):
         return self.forward_heads(x).permute(1, 2, 0)                    # (B, A, K) like torch.stack(..., dim=-1)
 
     # ---- loss ---------------------------------------------------------------------------
-    def get_loss(self, embedded_obs, embedded_next_obs, batch_acts, batch_returns, dones_and_gamma, target_model=None):
+    def q_tables(self, embedded_obs, embedded_next_obs, target_model=None):
+        """(q_cur, q_next_online, q_next_target), head-major (K, B, A)  (:60-68)."""
         if target_model is None:
             target_model = self
         q_cur = self.forward_heads(embedded_obs)
@@ -136,17 +137,27 @@ class QEnsemble(nn.Module):
                 q_next_target = target_model.forward_heads(embedded_next_obs)
             else:
                 q_next_target = q_next_online = target_model.forward_heads(embedded_next_obs)
+        return q_cur, q_next_online, q_next_target
 
+    def theil_index(self):
+        """Theil index of the heads' parameter L2 norms (:86-90); stacked params make it one reduction per
+        tensor.  Returns None when the regulariser is off."""
+        if self.ensemble_variation_coef == 0:
+            return None
+        sq = sum(p.square().flatten(1).sum(dim=1) for p in self.stacked)
+        l2_set = sq.sqrt()
+        ratio = l2_set / l2_set.mean()
+        theil = (ratio * torch.log(ratio)).mean()
+        self.theil = theil.detach()              # logged value only: never keep an autograd graph on the module
+        return theil
+
+    def get_loss(self, embedded_obs, embedded_next_obs, batch_acts, batch_returns, dones_and_gamma, target_model=None):
+        q_cur, q_next_online, q_next_target = self.q_tables(embedded_obs, embedded_next_obs, target_model)
         q_loss = ops.ensemble_q_loss(q_cur, q_next_online, q_next_target, batch_acts.view(-1), batch_returns,
                                      dones_and_gamma, loss_weight=1.0)
-        theil = self.theil
-        if self.ensemble_variation_coef != 0:
-            # Theil index of the heads' parameter L2 norms (:86-90); stacked params make it 1 reduction per tensor
-            sq = sum(p.square().flatten(1).sum(dim=1) for p in self.stacked)
-            l2_set = sq.sqrt()
-            ratio = l2_set / l2_set.mean()
-            theil = (ratio * torch.log(ratio)).mean()
-            self.theil = theil.detach()          # logged value only: never keep an autograd graph on the module
+        theil = self.theil_index()
+        if theil is None:
+            return q_loss if self.q_loss_weight == 1 else self.q_loss_weight * q_loss
         return self.q_loss_weight * (q_loss - theil * self.ensemble_variation_coef)
 
     def log(self, logger):

@@ -42,7 +42,7 @@ class _QuantileHuberLoss(torch.autograd.Function):
         grad = torch.empty_like(z_cur_c)
         _lib.check(_lib.load().pb_iqn_qh_loss(
             B, T, Tp, A, z_cur_c.data_ptr(), tau_c.data_ptr(), zo.data_ptr(), zt.data_ptr(), action_c.data_ptr(),
-            ret_c.data_ptr(), gdn_c.data_ptr(), float(kappa), float(loss_weight), None, 1.0, loss.data_ptr(),
+            ret_c.data_ptr(), gdn_c.data_ptr(), None, float(kappa), float(loss_weight), None, 1.0, loss.data_ptr(),
             grad.data_ptr(), _stream(z_cur)), "pb_iqn_qh_loss")
         ctx.save_for_backward(grad)
         ctx.dims = (B, T, A)
@@ -77,7 +77,7 @@ class _EnsembleQLoss(torch.autograd.Function):
         grad = torch.empty_like(qc)
         _lib.check(_lib.load().pb_ens_q_loss(
             B, A, K, qc.data_ptr(), qo.data_ptr(), qt.data_ptr(), action_c.data_ptr(), ret_c.data_ptr(),
-            gdn_c.data_ptr(), float(loss_weight), None, 1.0, loss.data_ptr(), grad.data_ptr(), _stream(q_cur)),
+            gdn_c.data_ptr(), None, float(loss_weight), None, 1.0, loss.data_ptr(), grad.data_ptr(), _stream(q_cur)),
             "pb_ens_q_loss")
         ctx.save_for_backward(grad)
         return loss
@@ -129,8 +129,8 @@ class _LossCombine(torch.autograd.Function):
         dist_c = None if dist is None else _c(dist)
         q_c = None if q is None else _c(q)
         w_c = None if w is None else _c(w).view(-1)
-        _lib.check(_lib.load().pb_loss_combine(B, _lib.ptr(dist_c), _lib.ptr(q_c), _lib.ptr(w_c), total.data_ptr(),
-                                               td.data_ptr(), _stream(ref)), "pb_loss_combine")
+        _lib.check(_lib.load().pb_loss_combine(B, _lib.ptr(dist_c), _lib.ptr(q_c), _lib.ptr(w_c), 1.0, None,
+                                               total.data_ptr(), td.data_ptr(), _stream(ref)), "pb_loss_combine")
         ctx.B = B
         ctx.has = (dist is not None, q is not None)
         ctx.save_for_backward(w_c if w_c is not None else torch.empty(0, device=ref.device))
@@ -215,3 +215,96 @@ def run_sequential(seq, x):
             x = m(x)
             i += 1
     return x
+
+
+class _FusedTotalLoss(torch.autograd.Function):
+    """total = mean(dist*w) + mean(q'*w) straight from the quantile / ensemble tables: loss heads, PER
+    weighting, TD mix and the gradients w.r.t. z_cur / q_cur (already scaled by w_b/B) in 3 launches;
+    backward is one scalar multiply per table.  q' = q_weight * (mse - q_offset)."""
+
+    @staticmethod
+    def forward(ctx, z_cur, q_cur, tau, z_on, z_tg, q_on, q_tg, action, ret, gamma, nonterm, w, q_offset, T, Tp,
+                kappa, dist_weight, q_weight):
+        ref = z_cur if z_cur is not None else q_cur
+        _lib.require_cuda(ref, "tables")
+        lib, stream, dev = _lib.load(), _stream(ref), ref.device
+        B = action.numel()
+        action_c, ret_c, gamma_c = _c(action, torch.int64).view(-1), _c(ret).view(-1), _c(gamma).view(-1)
+        nt = None if nonterm is None else nonterm.contiguous().view(-1).view(torch.uint8)
+        w_c = None if w is None else _c(w).view(-1)
+        dist = mse = gz = gq = None
+        if z_cur is not None:
+            zc = _c(z_cur)
+            dist = torch.empty(B, dtype=torch.float32, device=dev)
+            gz = torch.empty_like(zc)
+            _lib.check(lib.pb_iqn_qh_loss(B, T, Tp, zc.shape[-1], zc.data_ptr(), _c(tau).view(-1).data_ptr(),
+                                          _c(z_on).data_ptr(), _c(z_tg).data_ptr(), action_c.data_ptr(),
+                                          ret_c.data_ptr(), gamma_c.data_ptr(), _lib.ptr(nt), float(kappa),
+                                          float(dist_weight), _lib.ptr(w_c), 1.0 / B, dist.data_ptr(), gz.data_ptr(),
+                                          stream), "pb_iqn_qh_loss")
+        if q_cur is not None:
+            qc = _c(q_cur)
+            K, _, A = qc.shape
+            mse = torch.empty(B, dtype=torch.float32, device=dev)
+            gq = torch.empty_like(qc)
+            _lib.check(lib.pb_ens_q_loss(B, A, K, qc.data_ptr(), _c(q_on).data_ptr(), _c(q_tg).data_ptr(),
+                                         action_c.data_ptr(), ret_c.data_ptr(), gamma_c.data_ptr(), _lib.ptr(nt), 1.0,
+                                         _lib.ptr(w_c), float(q_weight) / B, mse.data_ptr(), gq.data_ptr(), stream),
+                       "pb_ens_q_loss")
+        total = torch.empty((), dtype=torch.float32, device=dev)
+        td = torch.empty(B, dtype=torch.float32, device=dev)
+        _lib.check(lib.pb_loss_combine(B, _lib.ptr(dist), _lib.ptr(mse), _lib.ptr(w_c), float(q_weight),
+                                       _lib.ptr(q_offset), total.data_ptr(), td.data_ptr(), stream), "pb_loss_combine")
+        ctx.save_for_backward(gz, gq)
+        outs = (total, dist if dist is not None else td.new_empty(0), mse if mse is not None else td.new_empty(0), td)
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_total, *_):
+        gz, gq = ctx.saved_tensors
+        return (None if gz is None else gz * g_total, None if gq is None else gq * g_total) + (None,) * 16
+
+
+def fused_total_loss(z_cur, q_cur, tau, z_on, z_tg, q_on, q_tg, action, ret, gamma, nonterm, w, q_offset, T, Tp,
+                     kappa, dist_weight, q_weight):
+    return _FusedTotalLoss.apply(z_cur, q_cur, tau, z_on, z_tg, q_on, q_tg, action, ret, gamma, nonterm, w, q_offset,
+                                 T, Tp, kappa, dist_weight, q_weight)
+
+
+class _ConvEmbed(torch.autograd.Function):
+    """MinAtar embedding: channels-last obs -> conv3x3 + bias + ReLU -> NCHW flatten, one launch
+    (prism/agents/models/minatar_cnn_model.py:13-18,41-44); backward = dW, db only."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _lib.require_cuda(x, "x")
+        B, H, W, C = x.shape
+        OC = weight.shape[0]
+        xc, wc, bc = _c(x), _c(weight), (None if bias is None else _c(bias))
+        out = torch.empty(B, OC * (H - 2) * (W - 2), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().pb_conv3x3_relu_fwd(B, H, W, C, OC, xc.data_ptr(), wc.data_ptr(), _lib.ptr(bc),
+                                                   out.data_ptr(), _stream(x)), "pb_conv3x3_relu_fwd")
+        ctx.dims = (B, H, W, C, OC)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(xc, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xc, out = ctx.saved_tensors
+        B, H, W, C, OC = ctx.dims
+        lib = _lib.load()
+        dout = _c(dout)
+        groups = lib.pb_conv3x3_relu_bwd_groups(B)
+        scratch = torch.empty(groups * (OC * C * 9 + OC), dtype=torch.float32, device=dout.device)
+        dw = torch.empty(OC, C, 3, 3, dtype=torch.float32, device=dout.device)
+        db = torch.empty(OC, dtype=torch.float32, device=dout.device) if ctx.has_bias else None
+        _lib.check(lib.pb_conv3x3_relu_bwd(B, H, W, C, OC, xc.data_ptr(), out.data_ptr(), dout.data_ptr(),
+                                           scratch.data_ptr(), dw.data_ptr(), _lib.ptr(db), _stream(dout)),
+                   "pb_conv3x3_relu_bwd")
+        return None, dw, db
+
+
+def conv3x3_relu_flatten(x, weight, bias):
+    return _ConvEmbed.apply(x, weight, bias)

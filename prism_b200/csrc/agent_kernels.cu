@@ -43,9 +43,10 @@ __global__ void __launch_bounds__(128) qh_loss_kernel(int B, int T, int Tp, int 
                                                       const float *__restrict__ z_next_target,
                                                       const long long *__restrict__ action,
                                                       const float *__restrict__ ret, const float *__restrict__ gdn,
-                                                      float kappa, float loss_weight,
-                                                      const float *__restrict__ row_weight, float grad_scale,
-                                                      float *__restrict__ loss_out, float *__restrict__ grad_z)
+                                                      const uint8_t *__restrict__ nonterm, float kappa,
+                                                      float loss_weight, const float *__restrict__ row_weight,
+                                                      float grad_scale, float *__restrict__ loss_out,
+                                                      float *__restrict__ grad_z)
 {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = lane_id();
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(128) qh_loss_kernel(int B, int T, int Tp, int 
         if (acc > best_v) { best_v = acc; best_a = a; }
     }
     // y_j = R + gamma^k * nonterminal * Z_target(s', tau'_j)[a*]   (:136-145)
-    const float R = ret[b], g = gdn[b];
+    const float R = ret[b], g = nonterm ? __fmul_rn(gdn[b], nonterm[b] ? 1.0f : 0.0f) : gdn[b];
     for (int j = lane; j < Tp; j += 32)
         y[j] = __fadd_rn(R, __fmul_rn(z_next_target[((size_t)j * B + b) * A + best_a], g));
     const int act = (int)action[b];
@@ -107,15 +108,15 @@ __global__ void __launch_bounds__(128) ens_loss_kernel(int B, int A, int K, cons
                                                        const float *__restrict__ q_next_target,
                                                        const long long *__restrict__ action,
                                                        const float *__restrict__ ret, const float *__restrict__ gdn,
-                                                       float loss_weight, const float *__restrict__ row_weight,
-                                                       float grad_scale, float *__restrict__ loss_out,
-                                                       float *__restrict__ grad_q)
+                                                       const uint8_t *__restrict__ nonterm, float loss_weight,
+                                                       const float *__restrict__ row_weight, float grad_scale,
+                                                       float *__restrict__ loss_out, float *__restrict__ grad_q)
 {
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int b = blockIdx.x * (blockDim.x >> 5) + warp;
     if (b >= B) return;
     const int act = (int)action[b];
-    const float R = ret[b], g = gdn[b];
+    const float R = ret[b], g = nonterm ? __fmul_rn(gdn[b], nonterm[b] ? 1.0f : 0.0f) : gdn[b];
     const float gs = (row_weight ? row_weight[b] : 1.0f) * grad_scale * loss_weight * 2.0f / (float)K;
     float acc = 0.0f;
     for (int k = lane; k < K; k += 32) {
@@ -209,13 +210,15 @@ __global__ void __launch_bounds__(128) greedy_select_kernel(int N, int A, int K,
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) loss_combine_kernel(int B, const float *__restrict__ dist,
                                                             const float *__restrict__ q, const float *__restrict__ w,
+                                                            float q_scale, const float *__restrict__ q_offset,
                                                             float *__restrict__ total_out, float *__restrict__ td_out)
 {
     __shared__ float part[32];
     float acc = 0.0f;
+    const float off = q_offset ? *q_offset : 0.0f;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         const float wb = w ? w[b] : 1.0f;
-        const float d = dist ? dist[b] : 0.0f, qq = q ? q[b] : 0.0f;
+        const float d = dist ? dist[b] : 0.0f, qq = q ? q_scale * (q[b] - off) : 0.0f;
         acc += d * wb + qq * wb;
         if (td_out) td_out[b] = (dist && q) ? (d * 0.5f + qq * 0.5f) : (dist ? d : fabsf(qq));
     }
@@ -382,8 +385,8 @@ int pb_iqn_cos_basis(long long n_rows, int n_basis, const float *tau, float *out
 
 int pb_iqn_qh_loss(int B, int T, int Tp, int A, const float *z_cur, const float *tau, const float *z_next_online,
                    const float *z_next_target, const long long *action, const float *ret, const float *gdn,
-                   float kappa, float loss_weight, const float *row_weight, float grad_scale, float *loss_out,
-                   float *grad_z_cur, void *stream)
+                   const uint8_t *nonterminal, float kappa, float loss_weight, const float *row_weight,
+                   float grad_scale, float *loss_out, float *grad_z_cur, void *stream)
 {
     if (B < 0 || T <= 0 || Tp <= 0 || A <= 0 || !(kappa > 0.0f)) return PB_E_ARG;
     if (B == 0) return PB_OK;
@@ -393,21 +396,22 @@ int pb_iqn_qh_loss(int B, int T, int Tp, int A, const float *z_cur, const float 
     const size_t smem = sizeof(float) * warps * (size_t)(Tp + 2 * T);
     if (smem > 48 * 1024) return PB_E_UNSUPPORTED;
     PB_LAUNCH(qh_loss_kernel, (unsigned)((B + warps - 1) / warps), warps * 32, smem, stream, B, T, Tp, A, z_cur, tau,
-              z_next_online, z_next_target, action, ret, gdn, kappa, loss_weight, row_weight, grad_scale, loss_out,
-              grad_z_cur);
+              z_next_online, z_next_target, action, ret, gdn, nonterminal, kappa, loss_weight, row_weight, grad_scale,
+              loss_out, grad_z_cur);
     return PB_OK;
 }
 
 int pb_ens_q_loss(int B, int A, int K, const float *q_cur, const float *q_next_online, const float *q_next_target,
-                  const long long *action, const float *ret, const float *gdn, float loss_weight,
-                  const float *row_weight, float grad_scale, float *loss_out, float *grad_q_cur, void *stream)
+                  const long long *action, const float *ret, const float *gdn, const uint8_t *nonterminal,
+                  float loss_weight, const float *row_weight, float grad_scale, float *loss_out, float *grad_q_cur,
+                  void *stream)
 {
     if (B < 0 || A <= 0 || K <= 0) return PB_E_ARG;
     if (B == 0) return PB_OK;
     if (!q_cur || !q_next_online || !q_next_target || !action || !ret || !gdn || !loss_out || !grad_q_cur)
         return PB_E_ARG;
     PB_LAUNCH(ens_loss_kernel, (unsigned)((B + 3) / 4), 128, 0, stream, B, A, K, q_cur, q_next_online, q_next_target,
-              action, ret, gdn, loss_weight, row_weight, grad_scale, loss_out, grad_q_cur);
+              action, ret, gdn, nonterminal, loss_weight, row_weight, grad_scale, loss_out, grad_q_cur);
     return PB_OK;
 }
 
@@ -433,11 +437,11 @@ int pb_greedy_select(int N, int A, int K, const float *q, long long *action_out,
     return PB_OK;
 }
 
-int pb_loss_combine(int B, const float *dist, const float *q, const float *w, float *total_out, float *td_out,
-                    void *stream)
+int pb_loss_combine(int B, const float *dist, const float *q, const float *w, float q_scale, const float *q_offset,
+                    float *total_out, float *td_out, void *stream)
 {
     if (B <= 0 || (!dist && !q)) return PB_E_ARG;
-    PB_LAUNCH(loss_combine_kernel, 1, 1024, 0, stream, B, dist, q, w, total_out, td_out);
+    PB_LAUNCH(loss_combine_kernel, 1, 1024, 0, stream, B, dist, q, w, q_scale, q_offset, total_out, td_out);
     return PB_OK;
 }
 

@@ -40,6 +40,7 @@ struct TreeView {
 enum { MODE_RAW = 0, MODE_PRIORITY = 1, MODE_EXTEND = 2 };
 constexpr int TOP_MAX = 14;       // top kernel holds depths [0, T], T <= 14 -> 2^(T+1)*4 B = 128 KB smem
 constexpr int STAGE_TILE = 2048;  // bulk build: source nodes per CTA (11 levels)
+constexpr long long THREAD_MODE_MIN = 16384;  // samples per call from which one-thread-per-sample wins
 
 __device__ __forceinline__ float op_sum(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float op_min(float a, float b) { return fminf(a, b); }
@@ -75,7 +76,7 @@ __device__ __forceinline__ float entry_leaf(const TreeView &t, const float *val,
                                             float defp)
 {
     if (mode == MODE_RAW) return val[j];
-    if (mode == MODE_PRIORITY) return pow_leaf(val[j], t);
+    if (mode == MODE_PRIORITY) return pow_leaf(fabsf(val[j]), t);   // learner.py:120 passes |td|; idempotent
     return defp;
 }
 
@@ -272,7 +273,7 @@ __global__ void upd_mark_kernel(TreeView t, long long n, const long long *idx, c
         long long i = entry_index(t, idx, j, mode);
         if (i >= 0 && i < t.size) {
             atomicMax(&t.owner[i], (int)j);
-            if (mode == MODE_PRIORITY) bm = fmaxf(val[j], 0.0f);
+            if (mode == MODE_PRIORITY) bm = fabsf(val[j]);
         }
     }
     if (mode == MODE_PRIORITY) {
@@ -295,6 +296,32 @@ __global__ void upd_leaf_kernel(TreeView t, long long n, const long long *idx, c
     t.sum[t.cap + i] = v;
     t.min[t.cap + i] = v;
     t.owner[i] = -1;
+}
+
+// dense path, sorted input: the last entry of every run of equal indices writes the leaf
+__global__ void upd_leaf_sorted_kernel(TreeView t, long long n, const long long *idx, const float *val, int mode,
+                                       long long *idx_out)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float bm = 0.0f;
+    if (j < n) {
+        const long long i = entry_index(t, idx, j, mode);
+        if (idx_out) idx_out[j] = i;
+        if (i >= 0 && i < t.size) {
+            if (mode == MODE_PRIORITY) bm = fabsf(val[j]);
+            const long long nx = (j + 1 < n) ? entry_index(t, idx, j + 1, mode) : -1;
+            if (nx != i) {
+                const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
+                const float v = entry_leaf(t, val, j, mode, defp);
+                t.sum[t.cap + i] = v;
+                t.min[t.cap + i] = v;
+            }
+        }
+    }
+    if (mode == MODE_PRIORITY) {
+        bm = warp_max(bm);
+        if (lane_id() == 0 && bm > 0.0f) atomicMax(reinterpret_cast<int *>(&t.st->batch_max), __float_as_int(bm));
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -330,7 +357,7 @@ __global__ void __launch_bounds__(256) upd_sparse_kernel(TreeView t, long long n
             long long ii = entry_index(t, idx, jj, mode);
             if (ii < 0 || ii >= t.size || (ii >> 5) != g) break;
             float v = entry_leaf(t, val, jj, mode, defp);
-            if (mode == MODE_PRIORITY) bm = fmaxf(bm, val[jj]);
+            if (mode == MODE_PRIORITY) bm = fmaxf(bm, fabsf(val[jj]));
             if (lane == (int)(ii & 31)) { vs = v; vm = v; touched = true; }
             if (idx_out && lane == 0) idx_out[jj] = ii;
         }
@@ -385,6 +412,47 @@ __device__ __forceinline__ long long warp_descend(const float *__restrict__ sum,
     return node ^ (1LL << L);
 }
 
+// ---------------------------------------------------------------------------------
+// throughput mode (large batches): one THREAD per sample, the top levels staged in shared
+// memory.  Same comparisons in the same order as warp_descend (and as the reference loop), so
+// the two modes return identical indices; with stratified (sorted) masses neighbouring threads
+// walk neighbouring paths, so the per-level loads of a warp coalesce into a few sectors.
+// ---------------------------------------------------------------------------------
+constexpr int STAGE_LEVELS = 11;   // nodes [1, 2^11) = 8 KB of shared memory per CTA
+
+__device__ __forceinline__ void stage_top(const float *__restrict__ sum, int L, float *sm)
+{
+    const int S = L < STAGE_LEVELS ? L : STAGE_LEVELS;
+    const int n = 1 << S;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = sum[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ long long thread_descend(const float *__restrict__ sum, const float *sm, int L,
+                                                    long long size, float m)
+{
+    if (m > sm[1]) return size;
+    const int S = L < STAGE_LEVELS ? L : STAGE_LEVELS;
+    const long long staged = 1LL << S;
+    long long node = 1;
+    for (int d = 0; d < L; ++d) {
+        node <<= 1;
+        const float left = node < staged ? sm[node] : __ldg(sum + node);
+        if (m > left) { m = __fsub_rn(m, left); node |= 1; }
+    }
+    return node ^ (1LL << L);
+}
+
+__global__ void __launch_bounds__(256) tree_scan_thread_kernel(TreeView t, long long n, const float *mass,
+                                                               long long *idx_out)
+{
+    __shared__ float sm[1 << STAGE_LEVELS];
+    stage_top(t.sum, t.L, sm);
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    idx_out[k] = thread_descend(t.sum, sm, t.L, t.size, mass[k]);
+}
+
 __global__ void __launch_bounds__(256) tree_scan_kernel(TreeView t, long long n, const float *mass,
                                                         long long *idx_out)
 {
@@ -435,6 +503,37 @@ __global__ void __launch_bounds__(256) tree_sample_kernel(TreeView t, long long 
         w_out[k] = is_weight(leaf, p_min, beta, t);
         if (mass_out) mass_out[k] = m;
     }
+}
+
+__global__ void __launch_bounds__(256) tree_sample_thread_kernel(TreeView t, long long n, const double *u, int mode,
+                                                                 float beta, long long *idx_out, float *w_out,
+                                                                 float *mass_out)
+{
+    __shared__ float sm[1 << STAGE_LEVELS];
+    stage_top(t.sum, t.L, sm);
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const long long len = t.st->len;
+    const float p_sum = t.st->p_sum, p_min = t.st->p_min;
+    int bad = 0;
+    if (len <= 0) bad = PB_ST_EMPTY;
+    else if (!(p_sum > 0.0f)) bad = PB_ST_PSUM_NONPOS;
+    else if (!(p_min > 0.0f)) bad = PB_ST_PMIN_NONPOS;
+    if (bad) {
+        idx_out[k] = 0; w_out[k] = 0.0f;
+        if (mass_out) mass_out[k] = 0.0f;
+        if (k == 0) atomicOr(&t.st->status, bad);
+        return;
+    }
+    const double uk = u[k];
+    const double m64 = (mode == 0) ? (0.0 + ((double)p_sum - 0.0) * uk)
+                                   : __dmul_rn(__ddiv_rn(__dadd_rn((double)k, uk), (double)n), (double)p_sum);
+    const float m = (float)m64;
+    long long i = thread_descend(t.sum, sm, t.L, t.size, m);
+    if (i > len - 1) i = len - 1;
+    idx_out[k] = i;
+    w_out[k] = is_weight(__ldg(t.sum + t.cap + i), p_min, beta, t);
+    if (mass_out) mass_out[k] = m;
 }
 
 // ---------------------------------------------------------------------------------
@@ -583,6 +682,25 @@ int launch_update(const pb_tree *t, long long n, const long long *idx, const flo
         sorted = (n + 64 <= v.size);  // contiguous run, except when it can wrap onto its own line
     }
     const int P = sparse_phases(v.L);
+    // dense path: when the batch touches a sizeable part of the tree, scatter the leaves and rebuild
+    // every level with the streaming build kernels (2 x 12 B x cap of traffic, independent of n)
+    if (P > 0 && n * 128 >= v.cap && v.L >= 11) {
+        const int nb = (int)((n + 255) / 256);
+        if (sorted) {
+            PB_LAUNCH(upd_leaf_sorted_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out);
+        } else {
+            if (!v.owner) return PB_E_ARG;
+            PB_LAUNCH(upd_mark_kernel, nb, 256, 0, stream, v, n, idx, val, mode);
+            PB_LAUNCH(upd_leaf_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out);
+        }
+        int d = v.L;
+        while (d > TOP_MAX) {
+            dim3 g2((unsigned)((1LL << d) / STAGE_TILE), 2);
+            PB_LAUNCH(tree_reduce11_kernel<false>, g2, 256, 0, stream, v, d, (const float *)nullptr, 0LL);
+            d -= 11;
+        }
+        return launch_top(v, d, mode, n, -1, stream);
+    }
     const bool fused = sorted && P > 0;
     if (!fused) {
         if (!v.owner) return PB_E_ARG;
@@ -673,7 +791,10 @@ int pb_tree_scan(const pb_tree *t, long long n, const float *mass, long long *id
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!mass || !idx_out))) return PB_E_ARG;
     if (n == 0) return PB_OK;
-    PB_LAUNCH(tree_scan_kernel, (unsigned)((n + 7) / 8), 256, 0, stream, v, n, mass, idx_out);
+    if (n >= THREAD_MODE_MIN)
+        PB_LAUNCH(tree_scan_thread_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, v, n, mass, idx_out);
+    else
+        PB_LAUNCH(tree_scan_kernel, (unsigned)((n + 7) / 8), 256, 0, stream, v, n, mass, idx_out);
     return PB_OK;
 }
 
@@ -685,8 +806,12 @@ int pb_tree_sample(const pb_tree *t, long long n, const double *u, int mode, flo
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!u || !idx_out || !weight_out)) || (mode != 0 && mode != 1)) return PB_E_ARG;
     if (n == 0) return PB_OK;
-    PB_LAUNCH(tree_sample_kernel, (unsigned)((n + 7) / 8), 256, 0, stream, v, n, u, mode, beta, idx_out,
-              weight_out, mass_out);
+    if (n >= THREAD_MODE_MIN)
+        PB_LAUNCH(tree_sample_thread_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, v, n, u, mode, beta,
+                  idx_out, weight_out, mass_out);
+    else
+        PB_LAUNCH(tree_sample_kernel, (unsigned)((n + 7) / 8), 256, 0, stream, v, n, u, mode, beta, idx_out,
+                  weight_out, mass_out);
     return PB_OK;
 }
 

@@ -87,7 +87,7 @@ class LearnerStep:
         agent._static_distribution_loss, agent._static_q_loss, agent._static_total_loss = dl, ql, total
         agent._optimizer_step(refresh_table=refresh_table)
         self.td = td
-        tree.update_priority(idx, td.abs(), sorted=self.sorted)
+        tree.update_priority(idx, td, sorted=self.sorted)      # |td| is taken inside the kernel (learner.py:120)
         return total
 
     def step(self, u=None):

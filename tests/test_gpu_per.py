@@ -66,7 +66,7 @@ def test_scan_lower_bound_is_bit_exact(N, kind):
     assert got[2] == N       # mass > root -> size, as the reference
 
 
-@pytest.mark.parametrize("N,B", [(1000, 64), (100_000, 256), (1 << 20, 4096)])
+@pytest.mark.parametrize("N,B", [(1000, 64), (100_000, 256), (1 << 20, 4096), (1 << 20, 65536), (300_000, 20_000)])
 @pytest.mark.parametrize("mode", ["iid", "stratified"])
 def test_sample_matches_oracle(N, B, mode):
     rng = np.random.default_rng(11)
@@ -138,6 +138,35 @@ def test_partial_fill_extend_and_interval_walk(N):
         oi2, ow, _, _, _ = o.sample(u)
         assert np.array_equal(gi.cpu().numpy(), oi2)
         assert np.allclose(gw.cpu().numpy(), ow, rtol=1e-6)
+
+
+@pytest.mark.parametrize("N", [70_000, 1 << 20])
+def test_large_batches_take_the_dense_path_bit_exact(N):
+    """n >= cap/128: leaves are scattered and every level rebuilt by the streaming kernels; the
+    thread-per-sample descent serves the large sample.  Same trees, same indices as the oracle."""
+    rng = np.random.default_rng(17)
+    g, o = _trees(N, mode="stratified")
+    g.extend(N); o.extend(N)
+    for it, B in enumerate([N // 16, N // 3, 40_000]):
+        u = rng.random(B)
+        gi, gw = g.sample(B, u=torch.from_numpy(u).to(DEV))
+        oi, ow, _, _, _ = o.sample(u, 0.5, mode=1)
+        assert np.array_equal(gi.cpu().numpy(), oi)
+        assert np.allclose(gw.cpu().numpy(), ow, rtol=1e-6)
+        prio = rng.exponential(1.5, B).astype(np.float32)
+        if it == 1:                                   # unsorted with duplicates -> owner-scratch dedup + dense rebuild
+            perm = rng.permutation(B)
+            idx, prio = oi[perm], prio[perm]
+            g.update_priority(torch.from_numpy(idx).to(DEV), torch.from_numpy(prio).to(DEV), sorted=False)
+            o.update_priority(idx, prio)
+        else:
+            g.update_priority(gi, torch.from_numpy(prio).to(DEV), sorted=True)
+            o.update_priority(oi, prio)
+        _assert_same_tree(g, o)
+        st = g.state_host()
+        assert st["max_priority"] == np.float32(o.max_priority) and st["p_sum"] == o.sum[1]
+    mass = (rng.random(50_000) * o.sum[1]).astype(np.float32)
+    assert np.array_equal(g.scan(torch.from_numpy(mass).to(DEV)).cpu().numpy(), o.scan(mass))
 
 
 def test_frozen_vectors_on_gpu():
