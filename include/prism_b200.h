@@ -68,7 +68,7 @@ typedef struct pb_per_state {
     float     batch_max;     /* scratch: max priority of the batch in flight   */
     int       owned_lo;      /* global sampling: first stratum owned by this rank */
     int       owned_n;       /* global sampling: number of strata owned        */
-    int       pad[5];
+    int       pad[5];        /* [0] top-kernel ticket, [1] rng ticket, [2] rng call number, [3] rng seed, [4] spare */
 } pb_per_state;
 
 typedef struct pb_tree {
@@ -118,7 +118,10 @@ int pb_tree_extend(const pb_tree *t, long long n, long long *idx_out, void *stre
 int pb_tree_scan(const pb_tree *t, long long n, const float *mass, long long *idx_out,
                  void *stream);
 
-/* PrioritizedSampler.sample (timestep_buffer.py:37): u are fp64 uniforms in [0,1).
+/* PrioritizedSampler.sample (timestep_buffer.py:37): u are fp64 uniforms in [0,1); u == NULL draws them
+ * on the device (Philox4x32-10 keyed by state->pad[3], counter = (k, state->pad[2]); the call number
+ * advances by one per launch, so graph replays see fresh numbers and all ranks of a sharded buffer
+ * that share a seed draw identical strata).
  * mode 0 iid: mass = p_sum*u (numpy uniform(0,p_sum)); mode 1 stratified:
  * mass = (k+u_k)/n * p_sum.  idx clamped to len-1; weight=(leaf/p_min)^-beta.
  * mass_out optional. */

@@ -256,6 +256,7 @@ class _FusedTotalLoss(torch.autograd.Function):
         _lib.check(lib.pb_loss_combine(B, _lib.ptr(dist), _lib.ptr(mse), _lib.ptr(w_c), float(q_weight),
                                        _lib.ptr(q_offset), total.data_ptr(), td.data_ptr(), stream), "pb_loss_combine")
         ctx.save_for_backward(gz, gq)
+        ctx.set_materialize_grads(False)      # no zero-fill launches for the non-differentiable outputs
         outs = (total, dist if dist is not None else td.new_empty(0), mse if mse is not None else td.new_empty(0), td)
         ctx.mark_non_differentiable(*outs[1:])
         return outs
@@ -263,6 +264,8 @@ class _FusedTotalLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_total, *_):
         gz, gq = ctx.saved_tensors
+        if g_total is None:
+            return (None,) * 18
         return (None if gz is None else gz * g_total, None if gq is None else gq * g_total) + (None,) * 16
 
 

@@ -21,30 +21,51 @@ constexpr int MAX_OUT = 32 * 14 * 14;
 
 struct ConvDims { int B, H, W, C, OC, OH, OW; };
 
+// One CTA per observation.  Shared memory: the frame (H*W*C) and the filter bank transposed to
+// [c][ky][kx][oc] so that a thread reads the OCG = 8 consecutive output channels of one tap as two
+// float4.  Thread = (output position, group of 8 output channels): 1 frame load feeds 8 FMAs.
+constexpr int OCG = 8;
+
 __global__ void __launch_bounds__(256) conv3x3_relu_fwd_kernel(ConvDims d, const float *__restrict__ x,
                                                                const float *__restrict__ w,
                                                                const float *__restrict__ bias, float *__restrict__ out)
 {
-    extern __shared__ float sm[];
-    float *sx = sm, *sw = sm + d.H * d.W * d.C;
+    extern __shared__ __align__(16) float sm[];
+    const int nx = d.H * d.W * d.C, ocp = (d.OC + OCG - 1) / OCG * OCG, taps = d.C * 9;
+    float *sw = sm, *sx = sm + taps * ocp;               // sw first: keeps it 16-byte aligned
     const int b = blockIdx.x;
-    const int nx = d.H * d.W * d.C, nw = d.OC * d.C * 9;
     const float *xb = x + (size_t)b * nx;
     for (int i = threadIdx.x; i < nx; i += blockDim.x) sx[i] = xb[i];
-    for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < taps * ocp; i += blockDim.x) {
+        const int tap = i / ocp, oc = i - tap * ocp;     // tap = c*9 + ky*3 + kx
+        sw[i] = oc < d.OC ? w[oc * taps + tap] : 0.0f;
+    }
     __syncthreads();
-    const int plane = d.OH * d.OW, n_out = d.OC * plane;
-    float *ob = out + (size_t)b * n_out;
-    for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
-        const int oc = o / plane, p = o - oc * plane, y = p / d.OW, xx = p - y * d.OW;
-        float acc = bias ? bias[oc] : 0.0f;
-        const float *wo = sw + oc * d.C * 9;
+    const int plane = d.OH * d.OW, groups = ocp / OCG;
+    float *ob = out + (size_t)b * d.OC * plane;
+    for (int item = threadIdx.x; item < plane * groups; item += blockDim.x) {
+        const int g = item / plane, p = item - g * plane, y = p / d.OW, xx = p - y * d.OW;
+        float acc[OCG];
+#pragma unroll
+        for (int q = 0; q < OCG; ++q) acc[q] = 0.0f;
         for (int ky = 0; ky < 3; ++ky)
             for (int kx = 0; kx < 3; ++kx) {
                 const float *px = sx + ((y + ky) * d.W + (xx + kx)) * d.C;
-                for (int c = 0; c < d.C; ++c) acc = fmaf(px[c], wo[c * 9 + ky * 3 + kx], acc);
+                for (int c = 0; c < d.C; ++c) {
+                    const float v = px[c];
+                    const float4 *wv = reinterpret_cast<const float4 *>(sw + (c * 9 + ky * 3 + kx) * ocp + g * OCG);
+                    const float4 w0 = wv[0], w1 = wv[1];
+                    acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+                    acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+                    acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+                    acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+                }
             }
-        ob[o] = fmaxf(acc, 0.0f);
+#pragma unroll
+        for (int q = 0; q < OCG; ++q) {
+            const int oc = g * OCG + q;
+            if (oc < d.OC) ob[oc * plane + p] = fmaxf(acc[q] + (bias ? bias[oc] : 0.0f), 0.0f);
+        }
     }
 }
 
@@ -93,14 +114,19 @@ __global__ void __launch_bounds__(256) conv3x3_relu_bwd_kernel(ConvDims d, const
     }
 }
 
-__global__ void conv_bwd_reduce_kernel(int n_groups, int nw, int n_bias, const float *__restrict__ partial,
-                                       float *__restrict__ dw, float *__restrict__ db)
+// one warp per gradient element: lanes stride over the per-CTA partials, fixed-order shuffle reduction
+__global__ void __launch_bounds__(256) conv_bwd_reduce_kernel(int n_groups, int nw, int n_bias,
+                                                              const float *__restrict__ partial,
+                                                              float *__restrict__ dw, float *__restrict__ db)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x, ne = nw + n_bias;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, ne = nw + n_bias;
     if (e >= ne) return;
     float a = 0.0f;
-    for (int g = 0; g < n_groups; ++g) a += partial[(size_t)g * ne + e];
-    if (e < nw) dw[e] = a; else if (db) db[e - nw] = a;
+    for (int g = lane_id(); g < n_groups; g += 32) a += partial[(size_t)g * ne + e];
+    a = warp_sum(a);
+    if (lane_id() == 0) {
+        if (e < nw) dw[e] = a; else if (db) db[e - nw] = a;
+    }
 }
 
 int check_dims(const ConvDims &d)
@@ -122,12 +148,16 @@ int pb_conv3x3_relu_fwd(int B, int H, int W, int C, int OC, const float *x, cons
     int rc = check_dims(d);
     if (rc) return rc;
     if (!x || !w || !out) return PB_E_ARG;
-    const size_t smem = sizeof(float) * (size_t)(H * W * C + OC * C * 9);
-    PB_LAUNCH(conv3x3_relu_fwd_kernel, (unsigned)B, 256, smem, stream, d, x, w, bias, out);
+    const int ocp = (OC + 7) / 8 * 8;
+    const size_t smem = sizeof(float) * (size_t)(H * W * C + ocp * C * 9);
+    if (smem > 48 * 1024) return PB_E_UNSUPPORTED;
+    const int items = d.OH * d.OW * (ocp / 8);
+    const int threads = items >= 256 ? 256 : (items + 31) / 32 * 32;
+    PB_LAUNCH(conv3x3_relu_fwd_kernel, (unsigned)B, threads, smem, stream, d, x, w, bias, out);
     return PB_OK;
 }
 
-int pb_conv3x3_relu_bwd_groups(int B) { return B < 128 ? B : 128; }
+int pb_conv3x3_relu_bwd_groups(int B) { return B < 296 ? B : 296; }
 
 int pb_conv3x3_relu_bwd(int B, int H, int W, int C, int OC, const float *x, const float *out, const float *dout,
                         float *partial_scratch, float *dw, float *db, void *stream)
@@ -141,7 +171,7 @@ int pb_conv3x3_relu_bwd(int B, int H, int W, int C, int OC, const float *x, cons
     if (smem > 48 * 1024) return PB_E_UNSUPPORTED;
     PB_LAUNCH(conv3x3_relu_bwd_kernel, (unsigned)groups, 256, smem, stream, d, x, out, dout, partial_scratch);
     const int ne = OC * C * 9 + OC;
-    PB_LAUNCH(conv_bwd_reduce_kernel, (unsigned)((ne + 255) / 256), 256, 0, stream, groups, OC * C * 9, OC,
+    PB_LAUNCH(conv_bwd_reduce_kernel, (unsigned)((ne + 7) / 8), 256, 0, stream, groups, OC * C * 9, OC,
               partial_scratch, dw, db);
     return PB_OK;
 }

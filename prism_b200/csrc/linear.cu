@@ -21,7 +21,7 @@ namespace {
 
 using namespace pb;
 
-constexpr int TM = 64, TN = 64, TK = 16, PAD = 4;
+constexpr int TM = 64, TN = 64, TK = 32, PAD = 4;   // 2 x (A,B) stages of 32 x 68 floats = 34 KB; C tile aliases them
 
 struct GemmArgs {
     const float *A, *B, *bias, *mask;
@@ -35,13 +35,13 @@ struct GemmArgs {
 
 template <bool KMAJOR>
 __device__ __forceinline__ void load_tile(float (&r)[4], const float *__restrict__ P, const float *__restrict__ mask,
-                                          int ld, int row0, int k0, int rows, int kmax, int t)
+                                          int ld, int row0, int k0, int rows, int kmax, int t, int half)
 {
-    // tile is [TK][64] in smem (k-major).  KMAJOR: memory contiguous along k -> thread owns 4 consecutive k of one row.
-    // else: memory contiguous along the row index -> thread owns 4 consecutive rows of one k.
+    // tile is [TK][64] in smem (k-major), fetched as two halves of 16 k.  KMAJOR: memory contiguous along k ->
+    // thread owns 4 consecutive k of one row.  else: contiguous along the row index -> 4 consecutive rows of one k.
     int row, k;
-    if (KMAJOR) { row = row0 + (t >> 2); k = k0 + ((t & 3) << 2); }
-    else        { k = k0 + (t >> 4); row = row0 + ((t & 15) << 2); }
+    if (KMAJOR) { row = row0 + (t >> 2); k = k0 + half * 16 + ((t & 3) << 2); }
+    else        { k = k0 + half * 16 + (t >> 4); row = row0 + ((t & 15) << 2); }
     const bool vec_ok = (ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(P) & 15) == 0);
     if (KMAJOR) {
         const long long off = (long long)row * ld + k;
@@ -89,14 +89,14 @@ __device__ __forceinline__ void load_tile(float (&r)[4], const float *__restrict
 }
 
 template <bool KMAJOR>
-__device__ __forceinline__ void store_tile(float (*S)[TM + PAD], const float (&r)[4], int t)
+__device__ __forceinline__ void store_tile(float (*S)[TM + PAD], const float (&r)[4], int t, int half)
 {
     if (KMAJOR) {
-        const int row = t >> 2, k = (t & 3) << 2;
+        const int row = t >> 2, k = half * 16 + ((t & 3) << 2);
 #pragma unroll
         for (int q = 0; q < 4; ++q) S[k + q][row] = r[q];
     } else {
-        const int k = t >> 4, row = (t & 15) << 2;
+        const int k = half * 16 + (t >> 4), row = (t & 15) << 2;
         *reinterpret_cast<float4 *>(&S[k][row]) = make_float4(r[0], r[1], r[2], r[3]);
     }
 }
@@ -105,10 +105,11 @@ __device__ __forceinline__ void store_tile(float (*S)[TM + PAD], const float (&r
 template <bool A_KMAJOR, bool B_KMAJOR, bool ROWSUM>
 __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g)
 {
-    __shared__ __align__(16) float As[2][TK][TM + PAD];
-    __shared__ __align__(16) float Bs[2][TK][TN + PAD];
-    __shared__ __align__(16) float Cs[TM][TN + PAD];
+    __shared__ __align__(16) float tiles[2 * 2 * TK * (TM + PAD)];
     __shared__ float Rs[TM];
+    float (*As)[TK][TM + PAD] = reinterpret_cast<float (*)[TK][TM + PAD]>(tiles);
+    float (*Bs)[TK][TN + PAD] = reinterpret_cast<float (*)[TK][TN + PAD]>(tiles + 2 * TK * (TM + PAD));
+    float (*Cs)[TN + PAD] = reinterpret_cast<float (*)[TN + PAD]>(tiles);      // reused once the K loop is over
 
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
     const int batch = blockIdx.y / g.m_tiles, mt = blockIdx.y % g.m_tiles;
@@ -125,19 +126,28 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g)
 
     float acc[4][4] = {};
     float rs[4] = {};
-    float ra[4], rb[4];
+    float ra[2][4], rb[2][4];
     const bool want_rowsum = ROWSUM && g.colsum != nullptr && blockIdx.x == 0;
 
     auto fetch = [&](int it) {
         const int seg = it / chunks_per_seg, k0 = (it % chunks_per_seg) * TK;
-        load_tile<A_KMAJOR>(ra, A + seg * g.a_ss, mask ? mask + seg * g.a_ss : nullptr, g.lda, i0, k0, g.M, g.K, t);
-        load_tile<B_KMAJOR>(rb, B + seg * g.b_ss, nullptr, g.ldb, j0, k0, g.N, g.K, t);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            load_tile<A_KMAJOR>(ra[h], A + seg * g.a_ss, mask ? mask + seg * g.a_ss : nullptr, g.lda, i0, k0, g.M, g.K, t, h);
+            load_tile<B_KMAJOR>(rb[h], B + seg * g.b_ss, nullptr, g.ldb, j0, k0, g.N, g.K, t, h);
+        }
+    };
+    auto stash = [&](int b) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            store_tile<A_KMAJOR>(As[b], ra[h], t, h);
+            store_tile<B_KMAJOR>(Bs[b], rb[h], t, h);
+        }
     };
     int buf = 0;
     if (it0 < it1) {
         fetch(it0);
-        store_tile<A_KMAJOR>(As[0], ra, t);
-        store_tile<B_KMAJOR>(Bs[0], rb, t);
+        stash(0);
     }
     __syncthreads();
     for (int it = it0; it < it1; ++it) {
@@ -155,10 +165,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g)
                 if (ROWSUM) rs[r] += av[r];
             }
         }
-        if (more) {
-            store_tile<A_KMAJOR>(As[buf ^ 1], ra, t);
-            store_tile<B_KMAJOR>(Bs[buf ^ 1], rb, t);
-        }
+        if (more) stash(buf ^ 1);
         __syncthreads();
         buf ^= 1;
     }

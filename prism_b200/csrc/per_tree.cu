@@ -470,39 +470,76 @@ __device__ __forceinline__ float is_weight(float leaf, float p_min, float beta, 
     return (float)pow((double)ratio, -(double)beta);
 }
 
+// ---------------------------------------------------------------------------------
+// device-side uniforms: Philox4x32-10 keyed by the shard seed, counter = (stratum, call number).
+// Every rank of a sharded buffer draws the same u_k without communication; the call number lives in
+// the state block and is advanced by the last CTA of the launch (ticket), so a replayed CUDA graph
+// gets fresh numbers every iteration with no extra launch.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double philox_uniform(unsigned seed, unsigned call, unsigned long long k)
+{
+    unsigned c0 = (unsigned)k, c1 = (unsigned)(k >> 32), c2 = call, c3 = 0x50455221u;
+    unsigned k0 = seed, k1 = 0x9E3779B9u ^ seed;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    // 53 random bits -> [0, 1)
+    return ((double)(c0 >> 5) * 67108864.0 + (double)(c1 >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ void rng_advance(const TreeView &t)
+{
+    // call after a __syncthreads(): every thread of this CTA has read the call number
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int ticket = atomicAdd(&t.st->pad[1], 1);
+        if (ticket == (int)(gridDim.x * gridDim.y) - 1) {
+            t.st->pad[2] += 1;
+            t.st->pad[1] = 0;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) tree_sample_kernel(TreeView t, long long n, const double *u, int mode,
                                                           float beta, long long *idx_out, float *w_out,
                                                           float *mass_out)
 {
     const long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (k >= n) return;
     const int lane = lane_id();
-    const long long len = t.st->len;
-    const float p_sum = t.st->p_sum, p_min = t.st->p_min;
-    int bad = 0;
-    if (len <= 0) bad = PB_ST_EMPTY;
-    else if (!(p_sum > 0.0f)) bad = PB_ST_PSUM_NONPOS;
-    else if (!(p_min > 0.0f)) bad = PB_ST_PMIN_NONPOS;
-    if (bad) {
-        if (lane == 0) {
-            idx_out[k] = 0; w_out[k] = 0.0f;
-            if (mass_out) mass_out[k] = 0.0f;
-            if (k == 0) atomicOr(&t.st->status, bad);
+    const unsigned call = (unsigned)t.st->pad[2], seed = (unsigned)t.st->pad[3];
+    if (k < n) {
+        const long long len = t.st->len;
+        const float p_sum = t.st->p_sum, p_min = t.st->p_min;
+        int bad = 0;
+        if (len <= 0) bad = PB_ST_EMPTY;
+        else if (!(p_sum > 0.0f)) bad = PB_ST_PSUM_NONPOS;
+        else if (!(p_min > 0.0f)) bad = PB_ST_PMIN_NONPOS;
+        if (bad) {
+            if (lane == 0) {
+                idx_out[k] = 0; w_out[k] = 0.0f;
+                if (mass_out) mass_out[k] = 0.0f;
+                if (k == 0) atomicOr(&t.st->status, bad);
+            }
+        } else {
+            const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
+            const double m64 = (mode == 0) ? (0.0 + ((double)p_sum - 0.0) * uk)
+                                           : __dmul_rn(__ddiv_rn(__dadd_rn((double)k, uk), (double)n), (double)p_sum);
+            const float m = (float)m64;
+            long long i = warp_descend(t.sum, t.L, t.size, m);
+            if (i > len - 1) i = len - 1;
+            if (lane == 0) {
+                float leaf = t.sum[t.cap + i];
+                idx_out[k] = i;
+                w_out[k] = is_weight(leaf, p_min, beta, t);
+                if (mass_out) mass_out[k] = m;
+            }
         }
-        return;
     }
-    const double uk = u[k];
-    const double m64 = (mode == 0) ? (0.0 + ((double)p_sum - 0.0) * uk)
-                                   : __dmul_rn(__ddiv_rn(__dadd_rn((double)k, uk), (double)n), (double)p_sum);
-    const float m = (float)m64;
-    long long i = warp_descend(t.sum, t.L, t.size, m);
-    if (i > len - 1) i = len - 1;
-    if (lane == 0) {
-        float leaf = t.sum[t.cap + i];
-        idx_out[k] = i;
-        w_out[k] = is_weight(leaf, p_min, beta, t);
-        if (mass_out) mass_out[k] = m;
-    }
+    if (!u) { __syncthreads(); rng_advance(t); }
 }
 
 __global__ void __launch_bounds__(256) tree_sample_thread_kernel(TreeView t, long long n, const double *u, int mode,
@@ -510,30 +547,33 @@ __global__ void __launch_bounds__(256) tree_sample_thread_kernel(TreeView t, lon
                                                                  float *mass_out)
 {
     __shared__ float sm[1 << STAGE_LEVELS];
+    const unsigned call = (unsigned)t.st->pad[2], seed = (unsigned)t.st->pad[3];
     stage_top(t.sum, t.L, sm);
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const long long len = t.st->len;
-    const float p_sum = t.st->p_sum, p_min = t.st->p_min;
-    int bad = 0;
-    if (len <= 0) bad = PB_ST_EMPTY;
-    else if (!(p_sum > 0.0f)) bad = PB_ST_PSUM_NONPOS;
-    else if (!(p_min > 0.0f)) bad = PB_ST_PMIN_NONPOS;
-    if (bad) {
-        idx_out[k] = 0; w_out[k] = 0.0f;
-        if (mass_out) mass_out[k] = 0.0f;
-        if (k == 0) atomicOr(&t.st->status, bad);
-        return;
+    if (k < n) {
+        const long long len = t.st->len;
+        const float p_sum = t.st->p_sum, p_min = t.st->p_min;
+        int bad = 0;
+        if (len <= 0) bad = PB_ST_EMPTY;
+        else if (!(p_sum > 0.0f)) bad = PB_ST_PSUM_NONPOS;
+        else if (!(p_min > 0.0f)) bad = PB_ST_PMIN_NONPOS;
+        if (bad) {
+            idx_out[k] = 0; w_out[k] = 0.0f;
+            if (mass_out) mass_out[k] = 0.0f;
+            if (k == 0) atomicOr(&t.st->status, bad);
+        } else {
+            const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
+            const double m64 = (mode == 0) ? (0.0 + ((double)p_sum - 0.0) * uk)
+                                           : __dmul_rn(__ddiv_rn(__dadd_rn((double)k, uk), (double)n), (double)p_sum);
+            const float m = (float)m64;
+            long long i = thread_descend(t.sum, sm, t.L, t.size, m);
+            if (i > len - 1) i = len - 1;
+            idx_out[k] = i;
+            w_out[k] = is_weight(__ldg(t.sum + t.cap + i), p_min, beta, t);
+            if (mass_out) mass_out[k] = m;
+        }
     }
-    const double uk = u[k];
-    const double m64 = (mode == 0) ? (0.0 + ((double)p_sum - 0.0) * uk)
-                                   : __dmul_rn(__ddiv_rn(__dadd_rn((double)k, uk), (double)n), (double)p_sum);
-    const float m = (float)m64;
-    long long i = thread_descend(t.sum, sm, t.L, t.size, m);
-    if (i > len - 1) i = len - 1;
-    idx_out[k] = i;
-    w_out[k] = is_weight(__ldg(t.sum + t.cap + i), p_min, beta, t);
-    if (mass_out) mass_out[k] = m;
+    if (!u) { __syncthreads(); rng_advance(t); }
 }
 
 // ---------------------------------------------------------------------------------
@@ -591,7 +631,8 @@ __global__ void __launch_bounds__(256) global_count_kernel(TreeView t, const pb_
     int lo = 0, mine = 0;
     if (k < n_global) {
         float res;
-        int owner = route_stratum(g, G, k, n_global, u[k], &res);
+        const double uk = u ? u[k] : philox_uniform((unsigned)t.st->pad[3], (unsigned)t.st->pad[2], (unsigned long long)k);
+        int owner = route_stratum(g, G, k, n_global, uk, &res);
         lo = owner < rank;
         mine = owner == rank;
     }
@@ -609,30 +650,36 @@ __global__ void __launch_bounds__(256) global_sample_kernel(TreeView t, const pb
     __shared__ GlobalTop g;
     build_top(&g, all_state, G);
     const long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (k >= n_global) return;
     const int lane = lane_id();
-    const int lo = t.st->owned_lo, cnt = t.st->owned_n;
-    if (k >= cnt && lane == 0) {  // padding rows of the static batch: idx -1 is skipped downstream
-        idx_out[k] = -1; w_out[k] = 0.0f;
-        if (stratum_out) stratum_out[k] = -1;
+    const unsigned call = (unsigned)t.st->pad[2], seed = (unsigned)t.st->pad[3];
+    if (k < n_global) {
+        const int lo = t.st->owned_lo, cnt = t.st->owned_n;
+        if (k >= cnt && lane == 0) {  // padding rows of the static batch: idx -1 is skipped downstream
+            idx_out[k] = -1; w_out[k] = 0.0f;
+            if (stratum_out) stratum_out[k] = -1;
+        }
+        float res;
+        const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
+        const int owner = route_stratum(g, G, k, n_global, uk, &res);
+        if (owner == rank) {
+            const long long len = all_state[rank].len;
+            if (len <= 0 || !(g.psum[1] > 0.0f) || !(g.pmin > 0.0f)) {
+                if (lane == 0 && k == lo)
+                    atomicOr(&t.st->status, len <= 0 ? PB_ST_EMPTY : (!(g.psum[1] > 0.0f) ? PB_ST_PSUM_NONPOS : PB_ST_PMIN_NONPOS));
+            }
+            long long i = warp_descend(t.sum, t.L, t.size, res);
+            if (i > len - 1) i = len - 1;
+            if (i < 0) i = 0;
+            if (lane == 0) {
+                const long long pos = k - lo;
+                float leaf = t.sum[t.cap + i];
+                idx_out[pos] = i;
+                w_out[pos] = is_weight(leaf, g.pmin, beta, t);
+                if (stratum_out) stratum_out[pos] = k;
+            }
+        }
     }
-    float res;
-    int owner = route_stratum(g, G, k, n_global, u[k], &res);
-    if (owner != rank) return;
-    const long long len = all_state[rank].len;
-    if (len <= 0 || !(g.psum[1] > 0.0f) || !(g.pmin > 0.0f)) {
-        if (lane == 0 && k == lo) atomicOr(&t.st->status, len <= 0 ? PB_ST_EMPTY : (!(g.psum[1] > 0.0f) ? PB_ST_PSUM_NONPOS : PB_ST_PMIN_NONPOS));
-    }
-    long long i = warp_descend(t.sum, t.L, t.size, res);
-    if (i > len - 1) i = len - 1;
-    if (i < 0) i = 0;
-    if (lane == 0) {
-        const long long pos = k - lo;
-        float leaf = t.sum[t.cap + i];
-        idx_out[pos] = i;
-        w_out[pos] = is_weight(leaf, g.pmin, beta, t);
-        if (stratum_out) stratum_out[pos] = k;
-    }
+    if (!u) { __syncthreads(); rng_advance(t); }
 }
 
 __global__ void global_reset_kernel(TreeView t) { t.st->owned_lo = 0; t.st->owned_n = 0; }
@@ -804,7 +851,7 @@ int pb_tree_sample(const pb_tree *t, long long n, const double *u, int mode, flo
     TreeView v;
     int rc = make_view(t, &v);
     if (rc) return rc;
-    if (n < 0 || (n > 0 && (!u || !idx_out || !weight_out)) || (mode != 0 && mode != 1)) return PB_E_ARG;
+    if (n < 0 || (n > 0 && (!idx_out || !weight_out)) || (mode != 0 && mode != 1)) return PB_E_ARG;
     if (n == 0) return PB_OK;
     if (n >= THREAD_MODE_MIN)
         PB_LAUNCH(tree_sample_thread_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, v, n, u, mode, beta,
@@ -824,7 +871,7 @@ int pb_tree_sample_global(const pb_tree *t, int n_ranks, int rank, const pb_per_
     if (rc) return rc;
     if (n_ranks < 1 || n_ranks > MAX_RANKS || !pb_is_pow2(n_ranks) || rank < 0 || rank >= n_ranks) return PB_E_ARG;
     if (!all_state || n_global < 0) return PB_E_ARG;
-    if (n_global > 0 && (!u || !idx_out || !weight_out)) return PB_E_ARG;
+    if (n_global > 0 && (!idx_out || !weight_out)) return PB_E_ARG;
     PB_LAUNCH(global_reset_kernel, 1, 1, 0, stream, v);
     if (n_global == 0) return PB_OK;
     PB_LAUNCH(global_count_kernel, (unsigned)((n_global + 255) / 256), 256, 0, stream, v, all_state,

@@ -56,6 +56,7 @@ class PrioritizedTree:
             default_priority_fp64=int(bool(default_priority_fp64)))
         self._ref = C.byref(self._c)
         self.reset()
+        self.seed(0x5EED)
 
     # -- helpers -----------------------------------------------------------------
     def _stream(self):
@@ -76,6 +77,8 @@ class PrioritizedTree:
     # -- mutation ----------------------------------------------------------------
     def reset(self):
         _lib.check(self._lib.pb_tree_init(self._ref, self._stream()), "pb_tree_init")
+        if getattr(self, "_seed", None) is not None:
+            self.seed(self._seed)
 
     def build(self, leaves):
         """Bulk-load post-pow fp32 leaves for slots [0, n) and rebuild every node."""
@@ -118,12 +121,10 @@ class PrioritizedTree:
         return out
 
     def sample(self, n, u=None, mode=None, beta=None, idx_out=None, weight_out=None, mass_out=None):
-        """Draw n indices.  ``u``: fp64 uniforms in [0,1) (device); drawn with the device
-        Philox generator when omitted."""
+        """Draw n indices.  ``u``: fp64 uniforms in [0,1) (device); drawn inside the kernel (Philox4x32-10
+        keyed by ``seed()``) when omitted."""
         n = int(n)
-        if u is None:
-            u = torch.rand(n, dtype=torch.float64, device=self.device)
-        else:
+        if u is not None:
             u = torch.as_tensor(u)
             if u.device != self.device or u.dtype != torch.float64 or not u.is_contiguous():
                 u = u.to(device=self.device, dtype=torch.float64, non_blocking=True).contiguous()
@@ -133,7 +134,7 @@ class PrioritizedTree:
             weight_out = torch.empty(n, dtype=torch.float32, device=self.device)
         mode = self.mode if mode is None else (self.MODE_STRATIFIED if mode in ("stratified", 1) else self.MODE_IID)
         beta = self._beta if beta is None else float(beta)
-        _lib.check(self._lib.pb_tree_sample(self._ref, n, u.data_ptr(), mode, beta, idx_out.data_ptr(),
+        _lib.check(self._lib.pb_tree_sample(self._ref, n, _lib.ptr(u), mode, beta, idx_out.data_ptr(),
                                             weight_out.data_ptr(), _lib.ptr(mass_out), self._stream()),
                    "pb_tree_sample")
         return idx_out, weight_out
@@ -149,12 +150,19 @@ class PrioritizedTree:
             weight_out = torch.empty(n_global, dtype=torch.float32, device=self.device)
         beta = self._beta if beta is None else float(beta)
         assert all_state.dtype == torch.uint8 and all_state.numel() == 64 * n_ranks and all_state.is_contiguous()
-        assert u.dtype == torch.float64 and u.is_cuda
+        assert u is None or (u.dtype == torch.float64 and u.is_cuda)
         _lib.check(self._lib.pb_tree_sample_global(self._ref, int(n_ranks), int(rank), all_state.data_ptr(),
-                                                   n_global, u.data_ptr(),
+                                                   n_global, _lib.ptr(u),
                                                    beta, idx_out.data_ptr(), weight_out.data_ptr(),
                                                    _lib.ptr(stratum_out), self._stream()), "pb_tree_sample_global")
         return idx_out, weight_out
+
+    def seed(self, seed, call=0):
+        """Key of the in-kernel Philox generator (all ranks of a sharded buffer must share it)."""
+        self._seed = int(seed) & 0x7FFFFFFF
+        words = self.state.view(torch.int32)
+        words[13] = int(call) & 0x7FFFFFFF
+        words[14] = self._seed
 
     # -- host-visible state (synchronises; not on the hot path) -------------------
     def state_host(self):

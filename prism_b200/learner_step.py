@@ -71,15 +71,14 @@ class LearnerStep:
     # ------------------------------------------------------------------------------------
     def _body(self, refresh_table, draw):
         tree, ring, agent, b = self.tree, self.ring, self.agent, self.buffer
-        if draw:
-            torch.rand(self.u.shape, dtype=torch.float64, device=self.device, out=self.u)
+        u = None if draw else self.u            # None: uniforms are drawn inside the sampling kernel
         if self.world_size > 1:
             import torch.distributed as dist
             dist.all_gather_into_tensor(self.all_state.view(-1), tree.state, group=self.pg)
-            tree.sample_global(self.world_size, self.rank, self.all_state, self.B_global, self.u,
+            tree.sample_global(self.world_size, self.rank, self.all_state, self.B_global, u,
                                idx_out=self.idx, weight_out=self.weight, stratum_out=self.stratum)
         else:
-            tree.sample(self.B, u=self.u, idx_out=self.idx, weight_out=self.weight)
+            tree.sample(self.B, u=u, idx_out=self.idx, weight_out=self.weight)
         # rows past the strata this rank owns have idx -1 / weight 0: skipped by gather and update
         idx, w = self.idx[:self.B_pad], self.weight[:self.B_pad]
         ring.gather(idx, b._obs, b._next_obs, b._reward, b._gamma, b._nonterminal, b._action)

@@ -260,3 +260,29 @@ def test_sharded_global_sampling_equals_one_big_tree():
         assert float(w[n:].abs().sum()) == 0.0
     assert np.array_equal(got_idx, oi)
     assert np.allclose(got_w, ow, rtol=1e-6)
+
+
+def test_device_philox_uniforms():
+    """u = None: uniforms are drawn inside the sampling kernel (Philox keyed by the shard seed, counter =
+    (stratum, call number)); the call number advances per launch, equal seeds give equal draws."""
+    from prism_b200 import PrioritizedTree
+    N, B = 1 << 16, 2048
+    leaves = torch.rand(N, device=DEV) + 0.1
+    a, b = PrioritizedTree(N, device=DEV, mode="stratified"), PrioritizedTree(N, device=DEV, mode="stratified")
+    a.build(leaves); b.build(leaves)
+    a.seed(77); b.seed(77)
+    m1 = torch.empty(B, device=DEV); m2 = torch.empty(B, device=DEV); m3 = torch.empty(B, device=DEV)
+    i1, _ = a.sample(B, mass_out=m1)
+    i1 = i1.clone()
+    i2, _ = a.sample(B, mass_out=m2)
+    i3, _ = b.sample(B, mass_out=m3)
+    assert torch.equal(i1, i3) and torch.equal(m1, m3)        # same seed, same call number
+    assert not torch.equal(m1, m2)                            # the call number advanced
+    total = float(a.sum[1])
+    k = torch.arange(B, device=DEV, dtype=torch.float64)
+    u1 = m1.double() / total * B - k                           # recover u_k from the stratified mass
+    assert float(u1.min()) > -1e-3 and float(u1.max()) < 1 + 1e-3
+    assert 0.4 < float(u1.mean()) < 0.6 and 0.2 < float(u1.std()) < 0.4
+    big, _ = a.sample(1 << 16)                                 # thread-per-sample kernel, same generator
+    assert int(big.min()) >= 0 and int(big.max()) < N and bool((big[1:] >= big[:-1]).all())
+    assert a.state_host()["status"] == 0
