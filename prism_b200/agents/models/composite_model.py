@@ -110,6 +110,12 @@ class CompositeModel(nn.Module):
                                          None if q_loss is None else q_loss.detach(), None)
         return dist_loss, q_loss, td
 
+    def _side_streams(self, device):
+        ss = getattr(self, "_streams", None)
+        if ss is None:
+            ss = self._streams = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+        return ss
+
     def losses_total(self, batch, target_model, per_weights=None):
         """get_losses + the PER-weighted total of Agent.update (agent.py:58-64) as one fused head:
         returns (dist_loss, q_loss, total, td).  Same math as get_losses followed by
@@ -129,27 +135,59 @@ class CompositeModel(nn.Module):
         if nonterm.dtype != torch.bool:
             gamma, nonterm = gamma.float() * nonterm.float(), None
 
-        emb = self.embedding_model(obs)
-        with torch.no_grad():
-            if target_model is not None:
-                emb_next = target_model.embedding_model(next_obs)
-                dist_target, q_target = target_model.distribution_model, target_model.q_function_model
-            else:
-                emb_next = self.embedding_model(next_obs)
-                dist_target = q_target = None
         iqn, ens = self.distribution_model, self.q_function_model
         if iqn is None and ens is None:
             return None, None, None, None
+        tgt = target_model if target_model is not None else self
+        iqn_t, ens_t = tgt.distribution_model, tgt.q_function_model
         z_cur = tau = z_on = z_tg = q_cur = q_on = q_tg = None
         T = Tp = 0
         kappa = dist_w = q_w = 1.0
-        theil = None
         if iqn is not None:
-            z_cur, tau, z_on, z_tg = iqn.quantile_tables(emb, emb_next, dist_target)
             T, Tp, kappa, dist_w = (iqn.n_current_quantile_samples, iqn.n_next_quantile_samples, iqn.huber_k,
                                     iqn.distributional_loss_weight)
+        # which next-state passes exist (iqn_model.py:110-126, q_ensemble.py:62-68)
+        iqn_online_next = iqn is not None and (tgt is self or iqn.use_double_q_learning)
+        ens_online_next = ens is not None and (tgt is self or ens.use_double_q_learning)
+
+        # The bootstrap passes (no_grad) are independent of the online pass on the current observations:
+        # they run on side streams -- parallel branches of the captured graph -- and join before the loss.
+        cur = torch.cuda.current_stream(obs.device)
+        s1, s2 = self._side_streams(obs.device)
+        self._keepalive = keep = []          # side-stream tensors stay referenced until the next call
+        s1.wait_stream(cur)
+        with torch.cuda.stream(s1), torch.no_grad():
+            emb_next = tgt.embedding_model(next_obs)
+            emb_ready = torch.cuda.Event()
+            emb_ready.record(s1)
+            if tgt is not self:
+                if iqn is not None:
+                    z_tg = iqn_t.forward(emb_next, n_quantile_samples=Tp)[0]
+                if ens is not None:
+                    q_tg = ens_t.forward_heads(emb_next)
+        emb = self.embedding_model(obs)
+        if iqn is not None:
+            z_cur, tau = iqn.forward(emb, n_quantile_samples=T)
         if ens is not None:
-            q_cur, q_on, q_tg = ens.q_tables(emb, emb_next, q_target)
+            q_cur = ens.forward_heads(emb)
+        if iqn_online_next or ens_online_next:
+            s2.wait_event(emb_ready)
+            with torch.cuda.stream(s2), torch.no_grad():
+                if iqn_online_next:
+                    z_on = iqn.forward(emb_next, n_quantile_samples=Tp)[0]
+                if ens_online_next:
+                    q_on = ens.forward_heads(emb_next)
+            cur.wait_stream(s2)
+        cur.wait_stream(s1)
+        if iqn is not None:
+            z_tg = z_on if z_tg is None else z_tg
+            z_on = z_tg if z_on is None else z_on
+        if ens is not None:
+            q_tg = q_on if q_tg is None else q_tg
+            q_on = q_tg if q_on is None else q_on
+        keep.extend(t for t in (emb_next, z_on, z_tg, q_on, q_tg) if t is not None)
+        theil = None
+        if ens is not None:
             q_w = ens.q_loss_weight
             theil = ens.theil_index()
         w = per_weights if isinstance(per_weights, torch.Tensor) else None

@@ -14,6 +14,7 @@
 // distributed shared memory in a fixed order -- deterministic, no atomics, no workspace, one launch.
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -233,6 +234,9 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g)
 
 int pick_splits(long long tiles, int total_chunks)
 {
+    static int forced = -1;                         // PB_GEMM_SPLITS=n pins the split factor (tuning experiments)
+    if (forced < 0) { const char *e = getenv("PB_GEMM_SPLITS"); forced = e ? atoi(e) : 0; }
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return total_chunks >= forced ? forced : 1;
     const int sms = pb_sm_count();
     int s = 1;
     while (s < 8 && tiles * (s * 2) <= 2LL * sms && total_chunks / (s * 2) >= 2) s *= 2;
