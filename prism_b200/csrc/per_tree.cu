@@ -331,12 +331,9 @@ __global__ void upd_leaf_sorted_kernel(TreeView t, long long n, const long long 
 // its run (sequentially -> last wins) before reducing.
 // ---------------------------------------------------------------------------------
 template <bool FUSED>
-__global__ void __launch_bounds__(256) upd_sparse_kernel(TreeView t, long long n, const long long *idx,
-                                                         const float *val, int mode, int p, int sorted,
-                                                         long long *idx_out)
+__device__ __forceinline__ void sparse_entry(const TreeView &t, long long n, const long long *idx, const float *val,
+                                             int mode, int p, int sorted, long long *idx_out, long long j)
 {
-    const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j >= n) return;
     const int lane = lane_id();
     const int sh = 5 * p + 5;
     const long long i = entry_index(t, idx, j, mode);
@@ -375,6 +372,100 @@ __global__ void __launch_bounds__(256) upd_sparse_kernel(TreeView t, long long n
             t.sum[node] = vs;
             t.min[node] = vm;
         }
+    }
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(256) upd_sparse_kernel(TreeView t, long long n, const long long *idx,
+                                                         const float *val, int mode, int p, int sorted,
+                                                         long long *idx_out)
+{
+    const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= n) return;
+    sparse_entry<FUSED>(t, n, idx, val, mode, p, sorted, idx_out, j);
+}
+
+// ---------------------------------------------------------------------------------
+// latency mode (n <= 64: the handful of new transitions of one learner iteration): the whole update -- dedup,
+// leaves, every sparse phase, the top levels of both trees, the state block -- in ONE single-CTA launch,
+// phases separated by __syncthreads instead of kernel boundaries.
+// ---------------------------------------------------------------------------------
+constexpr int SMALL_MAX = 64;      // beyond ~2 entries per warp the serial in-CTA loop loses to 3 wide launches (measured: 29 vs 17 us at n=256)
+constexpr int SMALL_TOP = 12;      // both trees' top levels in shared memory: 2 * 2^(12+1) * 4 B = 64 KB
+
+__global__ void __launch_bounds__(1024) upd_small_kernel(TreeView t, long long n, const long long *idx,
+                                                         const float *val, int mode, int sorted, int P, int T,
+                                                         long long *idx_out)
+{
+    extern __shared__ float sm[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const bool fused = sorted && P > 0;
+    if (!fused) {
+        float bm = 0.0f;
+        for (long long j = tid; j < n; j += blockDim.x) {
+            const long long i = entry_index(t, idx, j, mode);
+            if (i >= 0 && i < t.size) {
+                atomicMax(&t.owner[i], (int)j);
+                if (mode == MODE_PRIORITY) bm = fmaxf(bm, fabsf(val[j]));
+            }
+        }
+        if (mode == MODE_PRIORITY) {
+            bm = warp_max(bm);
+            if (lane_id() == 0 && bm > 0.0f) atomicMax(reinterpret_cast<int *>(&t.st->batch_max), __float_as_int(bm));
+        }
+        __syncthreads();
+        const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
+        for (long long j = tid; j < n; j += blockDim.x) {
+            const long long i = entry_index(t, idx, j, mode);
+            if (idx_out) idx_out[j] = i;
+            if (i < 0 || i >= t.size || t.owner[i] != (int)j) continue;
+            const float v = entry_leaf(t, val, j, mode, defp);
+            t.sum[t.cap + i] = v;
+            t.min[t.cap + i] = v;
+            t.owner[i] = -1;
+        }
+        __syncthreads();
+    }
+    for (int p = 0; p < P; ++p) {
+        for (long long j = warp; j < n; j += (blockDim.x >> 5)) {
+            if (p == 0 && fused) sparse_entry<true>(t, n, idx, val, mode, p, 1, idx_out, j);
+            else sparse_entry<false>(t, n, idx, val, mode, p, fused ? 1 : 0, nullptr, j);
+        }
+        __syncthreads();
+    }
+    // top levels: threads [0, 512) own the sum tree, [512, 1024) the min tree
+    const bool is_min = tid >= 512;
+    const int gt = tid & 511;
+    float *tree = is_min ? t.min : t.sum;
+    float *s = sm + (is_min ? (2 << T) : 0);
+    const int n_top = 1 << T;
+    for (int i = gt; i < n_top; i += 512) s[n_top + i] = tree[n_top + i];
+    __syncthreads();
+    for (int d = T - 1; d >= 0; --d) {
+        const int n_d = 1 << d;
+        for (int i = gt; i < n_d; i += 512) {
+            const float l = s[2 * (n_d + i)], r = s[2 * (n_d + i) + 1];
+            s[n_d + i] = is_min ? op_min(l, r) : op_sum(l, r);
+        }
+        __syncthreads();
+    }
+    for (int i = gt + 1; i < n_top; i += 512) tree[i] = s[i];
+    __syncthreads();
+    if (tid >= 32) return;
+    long long len = t.st->len;
+    if (mode == MODE_EXTEND) len = len + n < t.size ? len + n : t.size;
+    const float ps = tree_query_prefix<false>(t, len);
+    const float pm = tree_query_prefix<true>(t, len);
+    if (tid == 0) {
+        pb_per_state *st = t.st;
+        if (mode == MODE_EXTEND) st->seq += n;
+        st->len = len;
+        if (mode == MODE_PRIORITY) {
+            const float bm = st->batch_max;
+            if (bm > st->max_priority) st->max_priority = bm;
+        }
+        st->batch_max = 0.0f;
+        st->p_sum = ps; st->p_min = pm;
     }
 }
 
@@ -747,6 +838,22 @@ int launch_update(const pb_tree *t, long long n, const long long *idx, const flo
             d -= 11;
         }
         return launch_top(v, d, mode, n, -1, stream);
+    }
+    if (n <= SMALL_MAX && v.L >= 5) {
+        // latency mode: one single-CTA launch
+        const int Ps = v.L <= SMALL_TOP ? 0 : (v.L - SMALL_TOP + 4) / 5;
+        const int Ts = v.L - 5 * Ps;
+        if (!(sorted && Ps > 0) && !v.owner) return PB_E_ARG;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(upd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(sizeof(float) * 2 * (2ull << SMALL_TOP)));
+            if (e != cudaSuccess) return (int)e;
+            attr_set = true;
+        }
+        const size_t smem = sizeof(float) * 2 * (2ull << Ts);
+        PB_LAUNCH(upd_small_kernel, 1, 1024, smem, stream, v, n, idx, val, mode, sorted, Ps, Ts, idx_out);
+        return PB_OK;
     }
     const bool fused = sorted && P > 0;
     if (!fused) {

@@ -164,6 +164,9 @@ class TransitionRing:
         self.n_staged = 0
         return n
 
+    def make_ingest_slot(self, n):
+        return IngestSlot(self, n)
+
     def wait_staging(self):
         ev = getattr(self, "_copy_event", None)
         if ev is not None:
@@ -245,3 +248,59 @@ class TransitionRing:
         self.stream_last[:] = -1
         self.trunc_cursor[0] = sd["trunc_cursor"]
         self.trunc_owner[:len(sd["trunc_owner"])] = sd["trunc_owner"]
+
+
+class IngestSlot:
+    """Fixed-size ingest block (n steps per push) whose device half -- three pinned->device copies and the
+    scatter kernel -- has static addresses, so it can be captured in a CUDA graph and replayed once per
+    learner iteration (the reference collects `timesteps_per_iteration` = 4 steps per iteration).
+    Host half: fill() writes the pinned block and runs the link planner."""
+
+    def __init__(self, ring, n):
+        self.ring, self.n = ring, int(n)
+        E, dt, dev = ring.obs_elems, ring.storage_dtype, ring.device
+        esz = torch.empty(0, dtype=dt).element_size()
+        rows_bytes = 2 * self.n * E * esz
+        rows_bytes_al = (rows_bytes + 63) // 64 * 64
+        # ONE pinned block [obs rows | next_obs rows | pb_step_meta records] and its device mirror: one H2D copy
+        self.h_block = torch.zeros(rows_bytes_al + self.n * 64, dtype=torch.uint8).pin_memory()
+        self.d_block = torch.zeros_like(self.h_block, device=dev)
+        self.h_rows = self.h_block[:rows_bytes].view(dt).view(2, self.n, E)
+        self.d_rows = self.d_block[:rows_bytes].view(dt).view(2, self.n, E)
+        self.h_meta = self.h_block[rows_bytes_al:]
+        self.d_meta = self.d_block[rows_bytes_al:]
+        self.meta = self.h_meta.numpy().view(np.dtype(_lib.STEP_META_DTYPE))
+        self.rows_np = self.h_rows.numpy()
+        self.stream = np.zeros(self.n, dtype=np.int32)
+        self.flags = np.zeros(self.n, dtype=np.uint8)
+        self.h2d_bytes = self.h_block.numel()
+
+    def fill(self, stream_ids, obs, action, reward, done, trunc, next_obs):
+        ring, n = self.ring, self.n
+        self.rows_np[0] = np.asarray(obs).reshape(n, -1)
+        self.rows_np[1] = np.asarray(next_obs).reshape(n, -1)
+        d = np.asarray(done).astype(np.uint8)
+        t = np.asarray(trunc).astype(np.uint8)
+        self.stream[:] = stream_ids
+        self.flags[:] = d * STEP_DONE + t * STEP_TRUNC
+        m = self.meta
+        m["action"] = action
+        m["reward"] = reward
+        m["done"] = d
+        m["trunc"] = t
+        rc = ring._lib.pb_store_extend_plan(
+            ring.size, ring.aux_size, ring.max_streams, n, ring.seq, self.stream.ctypes.data, self.flags.ctypes.data,
+            ring.stream_last.ctypes.data, ring.trunc_cursor.ctypes.data, ring.trunc_owner.ctypes.data,
+            self.h_meta.data_ptr())
+        if rc == _lib.PB_E_POOL:
+            raise _lib.PbError("truncated-observation pool exhausted under a captured ingest graph: "
+                               "construct the ring with a larger trunc_pool")
+        _lib.check(rc, "pb_store_extend_plan")
+        ring.seq += n
+
+    def enqueue(self):
+        """Device half (capturable): H2D of the block, then the scatter kernel."""
+        ring = self.ring
+        self.d_block.copy_(self.h_block, non_blocking=True)
+        _lib.check(ring._lib.pb_store_scatter(ring._ref, self.n, self.d_rows[0].data_ptr(), self.d_rows[1].data_ptr(),
+                                              self.d_meta.data_ptr(), ring._stream()), "pb_store_scatter")

@@ -155,6 +155,12 @@ class TimestepBuffer(object):
                 self._flush()
         return n
 
+    def ingest_graph(self, n):
+        """A replayable ingest of exactly ``n`` steps per call (H2D + scatter + default priorities as ONE
+        CUDA graph): ``push = buffer.ingest_graph(4); push(stream_ids, obs, action, reward, done, trunc,
+        next_obs)``.  The host only writes pinned memory, plans links and replays."""
+        return _IngestGraph(self, n)
+
     def _flush(self):
         ring = self.buffer._storage
         if ring is None or ring.n_staged == 0:
@@ -288,3 +294,40 @@ def _to_numpy(x):
     if isinstance(x, torch.Tensor):
         return x.detach().cpu().numpy()
     return np.asarray(x)
+
+
+class _IngestGraph:
+    def __init__(self, buffer, n):
+        ring = buffer.buffer._storage
+        if ring is None:
+            raise _lib.PbError("ingest_graph needs the ring to exist (extend at least one step first)")
+        self.buffer, self.ring, self.n = buffer, ring, int(n)
+        self.slot = ring.make_ingest_slot(n)
+        self.tree = buffer.buffer._sampler
+        self.done = None
+        dev = ring.device
+        buffer._flush()
+        # the warm-up below really ingests: feed it a harmless terminal step per row on stream 0 ... no:
+        # warm up the copies only (no state change), then capture copies + scatter + tree extend
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self.slot.d_block.copy_(self.slot.h_block, non_blocking=True)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.slot.enqueue()
+            if self.tree is not None:
+                self.tree.extend(self.n)
+        self.h2d_bytes = self.slot.h2d_bytes
+
+    def __call__(self, stream_ids, obs, action, reward, done, trunc, next_obs):
+        self.buffer._flush()
+        if self.done is not None:
+            self.done.synchronize()          # the previous replay has consumed the pinned block
+        self.slot.fill(stream_ids, obs, action, reward, done, trunc, next_obs)
+        self.graph.replay()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.ring.device))
+        self.done = ev

@@ -197,3 +197,28 @@ def test_empty_buffer_raises_like_torchrl():
     tb = _product_buffer(32, 1)
     with pytest.raises(RuntimeError):
         tb.sample()
+
+
+@pytest.mark.parametrize("name,n", [("nstep_gather_fs1", 2), ("nstep_gather_fs4", 1)])
+def test_graph_captured_ingest_matches_reference_golden(name, n):
+    """ingest_graph(n): pinned staging -> H2D -> scatter -> default priorities replayed as one CUDA graph
+    must build exactly the same buffer as the eager ingest."""
+    fx = load_golden(name)
+    S = script_from_fixture(fx)
+    obs_shape = tuple(fx["obs_shape"].tolist())
+    tb = _product_buffer(int(fx["capacity"]), int(fx["frame_stack"]))
+    total = len(S["stream"])
+    succ = np.stack([script_successor_obs(S, t) for t in range(total)])
+    first = n                                                        # the ring must exist before capture
+    tb.extend_batch(S["stream"][:first], S["obs"][:first].reshape((-1,) + obs_shape), S["action"][:first],
+                    S["reward"][:first], S["done"][:first], S["trunc"][:first], succ[:first].reshape((-1,) + obs_shape))
+    push = tb.ingest_graph(n)
+    cps = set(fx["checkpoints"].tolist())
+    for t in range(first, total - total % n, n):
+        sl = slice(t, t + n)
+        push(S["stream"][sl], S["obs"][sl], S["action"][sl], S["reward"][sl], S["done"][sl], S["trunc"][sl], succ[sl])
+        for cp in range(t + 1, t + n + 1):
+            if cp in cps and cp == t + n:
+                _check_against_fixture(fx, cp, _gather_all(tb, fx["cp%d.index" % cp]))
+    st = tb.buffer._sampler.state_host()
+    assert st["seq"] == total - total % n and st["len"] == min(st["seq"], int(fx["capacity"]))
