@@ -98,7 +98,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -272,6 +272,54 @@ def per_microbench(device, torch, hbm_gbs):
     return out
 
 
+def config_extras(device, torch):
+    """The other BASELINE model configurations as learner steps (same LearnerStep graph), short runs:
+    configs[0] MinAtar Breakout IDS+IQN+LayerNorm+3-step+target+PER (B=64) and configs[4] IQN 64x64 + IDS on
+    Atari-shaped 84x84x4 transitions (B=512, uint8 frame storage)."""
+    import prism_b200
+    from prism_b200.learner_step import LearnerStep
+    out = {}
+    specs = {
+        "configs[0] minatar_ids_iqn_B64": (prism_b200.minatar_ids_iqn_config(
+            device=device, experience_replay_capacity=1 << 18, per_sampling="stratified", replay_max_streams=32,
+            replay_staging_rows=32768, use_cuda_graph=False), (10, 10, 4), 3, 1 << 17, 200, np.float32),
+        "configs[4] atari_iqn64x64_ids_B512": (prism_b200.atari_iqn_ids_config(
+            device=device, experience_replay_capacity=1 << 16, per_sampling="stratified", replay_max_streams=32,
+            replay_staging_rows=8192, replay_storage_dtype="uint8", replay_obs_scale_255=True, use_cuda_graph=False),
+            (84, 84), 18, 1 << 15, 10, np.uint8),
+    }
+    for name, (cfg, obs_shape, A, fill, steps, dt) in specs.items():
+        torch.manual_seed(123)
+        agent = prism_b200.build_agent(cfg, obs_shape if len(obs_shape) == 3 else (cfg.frame_stack_size,) + obs_shape, A)
+        buf = prism_b200.build_exp_buffer(cfg)
+        rng = np.random.default_rng(5)
+        E = int(np.prod(obs_shape))
+        done_n = 0
+        while done_n < fill:
+            n = min(8192, fill - done_n)
+            if dt == np.uint8:
+                frames = rng.integers(0, 256, (n + 32, E), dtype=np.uint8)
+            else:
+                frames = (rng.random((n + 32, E), dtype=np.float32) < 0.1).astype(np.float32)
+            sid = ((done_n + np.arange(n)) % 32).astype(np.int32)
+            buf.extend_batch(sid, frames[:n].reshape((n,) + obs_shape), rng.integers(0, A, n).astype(np.int32),
+                             (rng.random(n) < 0.05).astype(np.float32), rng.random(n) < (1 / 500), np.zeros(n, bool),
+                             frames[32:32 + n].reshape((n,) + obs_shape))
+            done_n += n
+        buf._flush()
+        step = LearnerStep(buf, agent, batch_size=cfg.batch_size, use_cuda_graph=True)
+        for _ in range(3):
+            step.step()
+        sec = time_kernel(step.step, steps, torch)
+        n_params = agent.optimizer.numel
+        out[name] = {"ms_per_update": round(sec * 1e3, 4), "updates_per_s": round(1.0 / sec, 2),
+                     "transitions_per_s": round(cfg.batch_size / sec, 1), "batch": cfg.batch_size,
+                     "parameters": int(n_params), "launches_per_step_ours": step.launches_per_step}
+        del step, agent, buf
+        torch.cuda.empty_cache()
+    return out
+
+
 def cpu_baseline(steps, fill, budget_s=25.0):
     """The oracle port (reference algorithm restated for the CPU) on the host cores: Python linked-list
     buffer + C sum-tree (1 thread, like torchrl) + PyTorch CPU agent (all intra-op threads)."""
@@ -363,6 +411,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident metric: W warm-up + K timed graph replays -----------------
+    # clocks are sampled from before the warm-up until the end of the e2e region (the timed regions last
+    # ~0.1 s each; nvidia-smi's first sample arrives late)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     graph_ok = True
     try:
         for _ in range(max(3, args.warmup)):
@@ -375,9 +428,6 @@ def run_ours(args):
                            world_size=world)
         for _ in range(max(3, args.warmup)):
             step.step()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     barrier()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -387,7 +437,6 @@ def run_ours(args):
     ev1.record()
     barrier()
     sec = ev0.elapsed_time(ev1) * 1e-3
-    clk = clocks.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([sec], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -430,6 +479,7 @@ def run_ours(args):
     barrier()
     e2e_sec = max(ev0.elapsed_time(ev1) * 1e-3, 0.0)
     wall = time.perf_counter() - t0
+    clk = clocks.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([e2e_sec], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -450,6 +500,12 @@ def run_ours(args):
     if world == 1 and not args.quick:
         del step
         extras["per_microbench"] = per_microbench(device, torch, hbm_gbs)
+        del agent, buf
+        torch.cuda.empty_cache()
+        try:
+            extras["other_configs"] = config_extras(device, torch)
+        except Exception as e:                       # never lose the headline line to an extra
+            extras["other_configs"] = {"error": repr(e)[:300]}
         cpu = cpu_baseline(steps=400, fill=50_000)
     line = {
         "metric": "PER sampled transitions/s (sample -> 3-step gather -> DQN update -> priority write-back)",

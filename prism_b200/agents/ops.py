@@ -188,13 +188,27 @@ class _Linear(torch.autograd.Function):
         return dx, dw, db, None
 
 
+# Above this many rows the fused split-K SIMT kernel loses to a plain library SGEMM (measured on B200,
+# profiles/microbench_r01.txt: 2048 x 256 x 1024 -> 46 us vs cuBLAS 34 us; 256 rows -> 14 us vs 22 us).
+# Learner-batch-sized layers (Q heads, ensemble) stay on the fused kernel; the (T*B)-row IQN layers are plain
+# library GEMMs until the tcgen05 3xTF32 kernel lands.
+FUSED_LINEAR_MAX_ROWS = 512
+
+
 def linear_heads(x, w, b, relu=False):
     """Stacked-head dense layer: x (M, J) shared by all heads or (K, M, J); w (K, N, J); b (K, N) -> (K, M, N)."""
+    if x.shape[-2] > FUSED_LINEAR_MAX_ROWS:
+        xe = x.unsqueeze(0).expand(w.shape[0], -1, -1) if x.dim() == 2 else x
+        y = torch.baddbmm(b.unsqueeze(1), xe, w.transpose(1, 2)) if b is not None else torch.bmm(xe, w.transpose(1, 2))
+        return torch.relu(y) if relu else y
     return _Linear.apply(x, w, b, 1 if relu else 0)
 
 
 def linear(x, weight, bias, relu=False):
     """nn.Linear (+ optional fused ReLU) on a 2-D input through the fused kernel."""
+    if x.shape[0] > FUSED_LINEAR_MAX_ROWS:
+        y = torch.nn.functional.linear(x, weight, bias)
+        return torch.relu(y) if relu else y
     b = None if bias is None else bias.unsqueeze(0)
     return _Linear.apply(x, weight.unsqueeze(0), b, 1 if relu else 0).squeeze(0)
 
