@@ -88,30 +88,81 @@ class Trace:
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed regions: NVML polled from a thread every 5 ms
+    (the timed regions last a fraction of a second -- nvidia-smi -lms starts too slowly for that); falls back
+    to an nvidia-smi loop when the NVML binding is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+            "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.proc, self.nvml, self.stop_flag = gpu_index, [], None, None, False
+        self.sm, self.mask, self.sm_max, self.source = [], 0, None, None
+        self.active = True       # window(False) pauses sampling between the timed regions
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip()]
+        if ids and all(v.strip().isdigit() for v in ids) and self.idx < len(ids):
+            return int(ids[self.idx])
+        return self.idx
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, "nvml"
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            if not self.active:
+                time.sleep(0.002)
+                continue
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def window(self, on):
+        self.active = bool(on)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.th.join(timeout=1.0)
+            reasons = sorted(n for n, bit in self.BITS.items() if self.mask & bit)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                    "reasons": reasons, "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -123,7 +174,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -411,11 +462,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident metric: W warm-up + K timed graph replays -----------------
-    # clocks are sampled from before the warm-up until the end of the e2e region (the timed regions last
-    # ~0.1 s each; nvidia-smi's first sample arrives late)
+    # clocks are sampled (NVML, every 5 ms) only inside the two timed regions (device-resident and e2e)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+        clocks.window(False)
     graph_ok = True
     try:
         for _ in range(max(3, args.warmup)):
@@ -431,11 +482,13 @@ def run_ours(args):
     barrier()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.window(True)
     ev0.record()
     for _ in range(args.steps):
         step.step()
     ev1.record()
     barrier()
+    clocks.window(False)
     sec = ev0.elapsed_time(ev1) * 1e-3
     if world > 1:
         t = torch.tensor([sec], device=device, dtype=torch.float64)
@@ -472,11 +525,13 @@ def run_ours(args):
         e2e_one()
     barrier()
     t0 = time.perf_counter()
+    clocks.window(True)
     ev0.record()
     for _ in range(e2e_steps):
         e2e_one()
     ev1.record()
     barrier()
+    clocks.window(False)
     e2e_sec = max(ev0.elapsed_time(ev1) * 1e-3, 0.0)
     wall = time.perf_counter() - t0
     clk = clocks.stop() if rank == 0 else None
@@ -564,7 +619,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="skip extras and the CPU baseline (profiling runs)")

@@ -333,6 +333,15 @@ int pb_linear_bwd_input(int K, int M, int N, int J, const float *dY, const float
 int pb_linear_bwd_weight(int K, int M, int N, int J, const float *dY, const float *Ymask, const float *X,
                          long long x_head_stride, float *dW, float *db, void *stream);
 
+/* The same forward layer on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulator in
+ * TMEM): every fp32 operand is split into TF32 hi + lo parts and each product issued as hi.hi + hi.lo +
+ * lo.hi (3xTF32), which keeps fp32-level accuracy (parity bar 1e-4) at tensor-core speed.  Used for the
+ * (T*B)-row IQN layers and the batch-512 ensemble.  Shapes: J % 32 == 0, N % 64 == 0
+ * (pb_linear_fwd_tc_supported), 16-byte aligned pointers. */
+int pb_linear_fwd_tc_supported(int M, int N, int J);
+int pb_linear_fwd_tc(int K, int M, int N, int J, const float *X, long long x_head_stride, const float *W,
+                     const float *b, int act, float *Y, void *stream);
+
 /* total_loss = mean_b(dist*w) + mean_b(q'*w);  td_b = 0.5*dist + 0.5*q' | dist | |q'|
  * (composite_model.py:135-142, agent.py:58-64) with q' = q_scale * (q - *q_offset)
  * (q_ensemble.py:92: q_loss_weight * (q_loss - theil * coef); q_offset NULL = 0).

@@ -195,8 +195,48 @@ class _Linear(torch.autograd.Function):
 FUSED_LINEAR_MAX_ROWS = 512
 
 
+class _LinearTC(torch.autograd.Function):
+    """Forward on the tensor cores (tcgen05 3xTF32, csrc/tc_gemm.cu); backward through library GEMMs for now."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        K, N, J = w.shape
+        shared = x.dim() == 2
+        M = x.shape[-2]
+        xc, wc, bc = _c(x), _c(w), (None if b is None else _c(b))
+        y = torch.empty(K, M, N, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().pb_linear_fwd_tc(K, M, N, J, xc.data_ptr(), 0 if shared else M * J, wc.data_ptr(),
+                                                _lib.ptr(bc), int(act), y.data_ptr(), _stream(x)), "pb_linear_fwd_tc")
+        ctx.act, ctx.shared, ctx.has_bias = int(act), shared, b is not None
+        ctx.save_for_backward(xc, wc, y if act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, wc, y = ctx.saved_tensors
+        dz = dy * (y > 0) if ctx.act else dy
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.bmm(dz, wc)                                   # (K, M, J)
+            if ctx.shared:
+                dx = dx.sum(dim=0)
+        if ctx.needs_input_grad[1]:
+            xe = xc.unsqueeze(0).expand(wc.shape[0], -1, -1) if ctx.shared else xc
+            dw = torch.bmm(dz.transpose(1, 2), xe)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dz.sum(dim=1)
+        return dx, dw, db, None
+
+
+TENSOR_CORE_LINEAR = False     # v1 kernel (2-stage, SIMT-fed) is slower than the library SGEMM on most shapes; v2 (TMA pipeline) replaces it
+
+
 def linear_heads(x, w, b, relu=False):
     """Stacked-head dense layer: x (M, J) shared by all heads or (K, M, J); w (K, N, J); b (K, N) -> (K, M, N)."""
+    M, (Kh, N, J) = x.shape[-2], w.shape
+    if (TENSOR_CORE_LINEAR and x.is_cuda and M >= 128 and M * Kh > FUSED_LINEAR_MAX_ROWS
+            and _lib.load().pb_linear_fwd_tc_supported(M, N, J)):
+        return _LinearTC.apply(x, w, b, 1 if relu else 0)
     if x.shape[-2] > FUSED_LINEAR_MAX_ROWS:
         xe = x.unsqueeze(0).expand(w.shape[0], -1, -1) if x.dim() == 2 else x
         y = torch.baddbmm(b.unsqueeze(1), xe, w.transpose(1, 2)) if b is not None else torch.bmm(xe, w.transpose(1, 2))
@@ -207,6 +247,9 @@ def linear_heads(x, w, b, relu=False):
 def linear(x, weight, bias, relu=False):
     """nn.Linear (+ optional fused ReLU) on a 2-D input through the fused kernel."""
     if x.shape[0] > FUSED_LINEAR_MAX_ROWS:
+        if TENSOR_CORE_LINEAR and x.is_cuda and _lib.load().pb_linear_fwd_tc_supported(x.shape[0], *weight.shape):
+            b = None if bias is None else bias.unsqueeze(0)
+            return _LinearTC.apply(x, weight.unsqueeze(0), b, 1 if relu else 0).squeeze(0)
         y = torch.nn.functional.linear(x, weight, bias)
         return torch.relu(y) if relu else y
     b = None if bias is None else bias.unsqueeze(0)

@@ -60,5 +60,24 @@ def main():
     print("conv fwd+bwd B256: %.2f us" % graph_time(lambda: torch.autograd.grad(ops.conv3x3_relu_flatten(xo, cw, cb), (cw, cb), gy)))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--tc" not in sys.argv:
     main()
+
+
+def tc_bench():
+    """tcgen05 3xTF32 forward vs the library SGEMM at the IQN / ensemble shapes."""
+    for (K, M, N, J) in [(1, 2048, 256, 1024), (1, 32768, 512, 3136), (1, 32768, 3136, 64), (10, 512, 512, 3136)]:
+        x = torch.randn(K, M, J, device=dev)
+        w = torch.randn(K, N, J, device=dev)
+        b = torch.randn(K, N, device=dev)
+        reps = 20 if M < 10000 else 3
+        with torch.no_grad():
+            t_tc = graph_time(lambda: ops._LinearTC.apply(x, w, b, 1), reps=reps)
+            t_lib = graph_time(lambda: torch.relu(torch.baddbmm(b.unsqueeze(1), x, w.transpose(1, 2))), reps=reps)
+        fl = 2.0 * K * M * N * J
+        print("tc_linear K%d M%d N%d J%d: tcgen05 3xTF32 %9.2f us (%.1f TFLOP/s fp32-equivalent)   cuBLAS fp32 %9.2f us (%.1f TFLOP/s)"
+              % (K, M, N, J, t_tc, fl / t_tc / 1e6, t_lib, fl / t_lib / 1e6))
+
+
+if __name__ == "__main__" and "--tc" in sys.argv:
+    tc_bench()

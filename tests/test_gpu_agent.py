@@ -298,3 +298,33 @@ def test_fused_linear_matches_torch(K, M, N, J, shared, relu):
     assert rel_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 2e-5
     assert rel_err(wd.grad.cpu().numpy(), wr.grad.numpy()) < 2e-5
     assert rel_err(bd.grad.cpu().numpy(), br.grad.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("K,M,N,J,shared,relu", [
+    (1, 2048, 256, 1024, True, True), (1, 2048, 1024, 64, True, True), (1, 300, 64, 32, True, False),
+    (10, 512, 512, 3136, False, True), (2, 1000, 128, 96, True, False)])
+def test_tensor_core_linear_matches_fp64(K, M, N, J, shared, relu):
+    """pb_linear_fwd_tc (tcgen05 3xTF32, TMEM accumulator) must hold fp32-level accuracy: 2e-5 of the
+    tensor's max against fp64 math (single-pass TF32 would sit at ~1e-3)."""
+    from prism_b200.agents import ops
+    g = torch.Generator().manual_seed(K * 7 + M + N + J)
+    x = torch.randn((M, J) if shared else (K, M, J), generator=g)
+    w = torch.randn(K, N, J, generator=g) / J ** 0.5
+    b = torch.randn(K, N, generator=g)
+    gy = torch.randn(K, M, N, generator=g)
+    xd, wd, bd = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    y = ops._LinearTC.apply(xd, wd, bd, 1 if relu else 0)
+    y.backward(gy.to(DEV))
+    torch.cuda.synchronize()
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    xe = xr.unsqueeze(0).expand(K, M, J) if shared else xr
+    yr = torch.baddbmm(br.unsqueeze(1), xe, wr.transpose(1, 2))
+    if relu:
+        # the ReLU gate is discontinuous: outputs within rounding of 0 may gate differently in fp32 and fp64.
+        # Judge the gradients with the gate the kernel actually produced.
+        yr = yr * (y.detach().cpu() > 0)
+    yr.backward(gy.double())
+    assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) < 2e-5
+    assert rel_err(wd.grad.cpu().numpy(), wr.grad.numpy()) < 1e-4
+    assert rel_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 1e-4
+    assert rel_err(bd.grad.cpu().numpy(), br.grad.numpy()) < 1e-4
