@@ -333,11 +333,30 @@ int pb_linear_bwd_input(int K, int M, int N, int J, const float *dY, const float
 int pb_linear_bwd_weight(int K, int M, int N, int J, const float *dY, const float *Ymask, const float *X,
                          long long x_head_stride, float *dW, float *db, void *stream);
 
-/* The same forward layer on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulator in
- * TMEM): every fp32 operand is split into TF32 hi + lo parts and each product issued as hi.hi + hi.lo +
- * lo.hi (3xTF32), which keeps fp32-level accuracy (parity bar 1e-4) at tensor-core speed.  Used for the
- * (T*B)-row IQN layers and the batch-512 ensemble.  Shapes: J % 32 == 0, N % 64 == 0
- * (pb_linear_fwd_tc_supported), 16-byte aligned pointers. */
+/* Dense layers on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, operands
+ * staged by TMA; csrc/tc_gemm.cu).  Every fp32 operand is split on the fly into TF32 hi + lo parts and each
+ * product issued as lo.hi + hi.lo + hi.hi (3xTF32), which keeps fp32-level accuracy (parity bar 1e-4) at
+ * tensor-core speed.  Replaces the nn.Linear GEMMs of the (T*B)-row IQN layers and of the K-head ensemble
+ * (iqn_model.py:30-46,89-93; ffnn_model.py:61-76; q_ensemble.py:26-48) and their autograd transposes.
+ *
+ *   C[b] (M x N, row stride ldc) = act( sum_k A[b](m,k) B[b](n,k) + bias[b](n) ),   b < batch
+ *
+ * a_major / b_major: 0 = the operand is stored row-major [M or N][K] (row stride lda/ldb); 1 = it is stored
+ * row-major [K][M or N] -- the transposed view the backward GEMMs need (dX = dZ W: b_major 1; dW = dZ^T X:
+ * both 1).  a_bs / b_bs: batch strides in floats (0 = shared by every batch).  kbatches > 1 (batch must be 1):
+ * the K loop also runs over kbatches operand batches, i.e. C = sum_h A[h] B[h]^T (input gradient of a layer
+ * whose input is shared by all heads).  workspace: optional scratch for split-K partials (the kernel picks the
+ * split so that batch*splits*M*N <= workspace_floats).  split_mode 0: hi = the raw fp32 word (the tensor core
+ * reads its upper 19 bits); 1: hi = cvt.rna.tf32.  Requirements: 16-byte aligned A/B, lda/ldb/a_bs/b_bs % 4 == 0
+ * (PB_E_UNSUPPORTED / PB_E_ARG otherwise).  act: 0 none, 1 ReLU. */
+int pb_tc_gemm_supported(int M, int N, int K, long long lda, long long ldb, long long ldc);
+int pb_tc_gemm(int batch, int kbatches, int M, int N, int K,
+               const float *A, int a_major, long long lda, long long a_bs,
+               const float *B, int b_major, long long ldb, long long b_bs,
+               const float *bias, long long bias_bs, int act,
+               float *C, long long ldc, long long c_bs,
+               float *workspace, long long workspace_floats, int split_mode, void *stream);
+/* nn.Linear forward through pb_tc_gemm: Y[k] (M x N) = act(X[k] (M x J) W[k]^T + b[k]), J % 4 == 0. */
 int pb_linear_fwd_tc_supported(int M, int N, int J);
 int pb_linear_fwd_tc(int K, int M, int N, int J, const float *X, long long x_head_stride, const float *W,
                      const float *b, int act, float *Y, void *stream);

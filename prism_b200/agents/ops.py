@@ -195,8 +195,36 @@ class _Linear(torch.autograd.Function):
 FUSED_LINEAR_MAX_ROWS = 512
 
 
+_TC_WORKSPACE = {}
+TC_WORKSPACE_FLOATS = 32 * 1024 * 1024      # split-K partials (128 MB), allocated on first use per device
+TC_SPLIT_MODE = 0                           # 0: hi = raw fp32 word (hardware reads its top 19 bits); 1: cvt.rna hi
+
+
+def _tc_workspace(device):
+    ws = _TC_WORKSPACE.get(device)
+    if ws is None:
+        ws = _TC_WORKSPACE[device] = torch.empty(TC_WORKSPACE_FLOATS, dtype=torch.float32, device=device)
+    return ws
+
+
+def tc_gemm(out, a, a_major, lda, a_bs, b, b_major, ldb, b_bs, batch, M, N, K, bias=None, bias_bs=0, act=0,
+            kbatches=1, ldc=None, c_bs=None):
+    """out[b] (M x N) = act(A[b] . B[b]^T + bias[b]) on the tensor cores (pb_tc_gemm, 3xTF32).  See
+    include/prism_b200.h for the operand conventions (major 1 = the transposed view)."""
+    _lib.require_cuda(out, "out")
+    ws = _tc_workspace(out.device)
+    _lib.check(_lib.load().pb_tc_gemm(int(batch), int(kbatches), int(M), int(N), int(K),
+                                      a.data_ptr(), int(a_major), int(lda), int(a_bs),
+                                      b.data_ptr(), int(b_major), int(ldb), int(b_bs),
+                                      _lib.ptr(bias), int(bias_bs), int(act),
+                                      out.data_ptr(), int(N if ldc is None else ldc), int(M * N if c_bs is None else c_bs),
+                                      ws.data_ptr(), ws.numel(), int(TC_SPLIT_MODE), _stream(out)), "pb_tc_gemm")
+    return out
+
+
 class _LinearTC(torch.autograd.Function):
-    """Forward on the tensor cores (tcgen05 3xTF32, csrc/tc_gemm.cu); backward through library GEMMs for now."""
+    """Y = act(X W^T + b) with forward, input-gradient and weight-gradient GEMMs all on the tensor cores
+    (tcgen05 3xTF32, csrc/tc_gemm.cu).  X: (M, J) shared by the heads or (K, M, J); W: (K, N, J); b: (K, N)."""
 
     @staticmethod
     def forward(ctx, x, w, b, act):
@@ -205,37 +233,47 @@ class _LinearTC(torch.autograd.Function):
         M = x.shape[-2]
         xc, wc, bc = _c(x), _c(w), (None if b is None else _c(b))
         y = torch.empty(K, M, N, dtype=torch.float32, device=x.device)
-        _lib.check(_lib.load().pb_linear_fwd_tc(K, M, N, J, xc.data_ptr(), 0 if shared else M * J, wc.data_ptr(),
-                                                _lib.ptr(bc), int(act), y.data_ptr(), _stream(x)), "pb_linear_fwd_tc")
-        ctx.act, ctx.shared, ctx.has_bias = int(act), shared, b is not None
+        tc_gemm(y, xc, 0, J, 0 if shared else M * J, wc, 0, J, N * J, K, M, N, J, bias=bc, bias_bs=N, act=int(act))
+        ctx.act, ctx.shared, ctx.has_bias, ctx.dims = int(act), shared, b is not None, (K, M, N, J)
         ctx.save_for_backward(xc, wc, y if act else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         xc, wc, y = ctx.saved_tensors
-        dz = dy * (y > 0) if ctx.act else dy
+        K, M, N, J = ctx.dims
+        dz = _c(dy * (y > 0) if ctx.act else dy)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = torch.bmm(dz, wc)                                   # (K, M, J)
+            # dX (M x J) = dZ (M x N) . W (N x J): B operand is W read as its transpose (b_major 1)
             if ctx.shared:
-                dx = dx.sum(dim=0)
+                dx = torch.empty(M, J, dtype=torch.float32, device=dz.device)
+                tc_gemm(dx, dz, 0, N, M * N, wc, 1, J, N * J, 1, M, J, N, kbatches=K)
+            else:
+                dx = torch.empty(K, M, J, dtype=torch.float32, device=dz.device)
+                tc_gemm(dx, dz, 0, N, M * N, wc, 1, J, N * J, K, M, J, N)
         if ctx.needs_input_grad[1]:
-            xe = xc.unsqueeze(0).expand(wc.shape[0], -1, -1) if ctx.shared else xc
-            dw = torch.bmm(dz.transpose(1, 2), xe)
+            # dW (N x J) = dZ^T (N x M) . X (M x J): both operands read as transposes
+            dw = torch.empty(K, N, J, dtype=torch.float32, device=dz.device)
+            tc_gemm(dw, dz, 1, N, M * N, xc, 1, J, 0 if ctx.shared else M * J, K, N, J, M)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dz.sum(dim=1)
         return dx, dw, db, None
 
 
-TENSOR_CORE_LINEAR = False     # v1 kernel (2-stage, SIMT-fed) is slower than the library SGEMM on most shapes; v2 (TMA pipeline) replaces it
+TENSOR_CORE_LINEAR = True      # module switch for A/B timing; the tcgen05 path is the default for large layers
+TC_MIN_FLOPS = 2.0e9           # below this a layer is launch-bound and stays on the fused SIMT kernel / library
+
+
+def _tc_eligible(x, M, Kh, N, J):
+    return (TENSOR_CORE_LINEAR and x.is_cuda and (J % 4) == 0 and (N % 4) == 0
+            and 2.0 * M * Kh * N * J >= TC_MIN_FLOPS)
 
 
 def linear_heads(x, w, b, relu=False):
     """Stacked-head dense layer: x (M, J) shared by all heads or (K, M, J); w (K, N, J); b (K, N) -> (K, M, N)."""
     M, (Kh, N, J) = x.shape[-2], w.shape
-    if (TENSOR_CORE_LINEAR and x.is_cuda and M >= 128 and M * Kh > FUSED_LINEAR_MAX_ROWS
-            and _lib.load().pb_linear_fwd_tc_supported(M, N, J)):
+    if _tc_eligible(x, M, Kh, N, J):
         return _LinearTC.apply(x, w, b, 1 if relu else 0)
     if x.shape[-2] > FUSED_LINEAR_MAX_ROWS:
         xe = x.unsqueeze(0).expand(w.shape[0], -1, -1) if x.dim() == 2 else x
@@ -247,7 +285,7 @@ def linear_heads(x, w, b, relu=False):
 def linear(x, weight, bias, relu=False):
     """nn.Linear (+ optional fused ReLU) on a 2-D input through the fused kernel."""
     if x.shape[0] > FUSED_LINEAR_MAX_ROWS:
-        if TENSOR_CORE_LINEAR and x.is_cuda and _lib.load().pb_linear_fwd_tc_supported(x.shape[0], *weight.shape):
+        if _tc_eligible(x, x.shape[0], 1, *weight.shape):
             b = None if bias is None else bias.unsqueeze(0)
             return _LinearTC.apply(x, weight.unsqueeze(0), b, 1 if relu else 0).squeeze(0)
         y = torch.nn.functional.linear(x, weight, bias)

@@ -1,31 +1,37 @@
-// tc_gemm.cu -- tcgen05 (5th-gen tensor core) GEMM with fp32-level accuracy for the IQN / ensemble
-// dense layers (sm_100a only).
+// tc_gemm.cu -- tcgen05 (5th-gen tensor core) GEMM with fp32-level accuracy for the IQN / ensemble dense
+// layers, forward and backward (sm_100a only).
 //
-//     C[b] (M x N) = act( A[b] (M x K) . B[b]^T (N x K) + bias[b] )          fp32 in, fp32 out
+//     C[b] (M x N) = act( sum_kb  A[kb|b] (M x K) . B[kb|b]^T (N x K)  + bias[b] )        fp32 in, fp32 out
 //
 // The reference computes these layers in fp32 (nn.Linear, prism/agents/models/ffnn_model.py:61-76,
 // iqn_model.py:30-46, 89-93, q_ensemble.py:26-48) and parity is judged at 1e-4 relative on losses and
 // gradients, which a single TF32 or BF16 pass (~1e-3) cannot hold.  So every operand is split on the fly
-// into a TF32 "hi" part and a TF32 "lo" residual (x = hi + lo exactly) and each product is issued as three
-// tensor-core MMAs  hi.hi + hi.lo + lo.hi  accumulating in fp32 in TENSOR MEMORY -- error ~1e-6, at a third
-// of the TF32 rate, i.e. several times the SIMT fp32 rate the reference's cuBLAS path gets.
+// into a TF32 "hi" part and a TF32 "lo" residual and each product is issued as three tensor-core MMAs
+// lo.hi + hi.lo + hi.hi accumulating in fp32 in TENSOR MEMORY -- error ~1e-6 at a third of the TF32 rate.
 //
-// Structure (one CTA = one 128 x BN output tile, 128 threads):
-//   * all four warps stream the fp32 operand tiles from global memory (128-bit loads), split them and
-//     write the hi / lo tiles to shared memory in the canonical K-major no-swizzle UMMA layout
-//     (8-row x 16-byte core matrices);
-//   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = BN, K = 8 per instruction)
-//     from shared-memory descriptors; the accumulator (128 lanes x BN columns) lives in TMEM;
-//   * tcgen05.commit -> mbarrier tells the loaders when a stage may be overwritten (2 stages: the tensor
-//     core works on stage s while the warps fill stage s^1);
-//   * epilogue: tcgen05.ld 32x32b (each warp its own 32 TMEM lanes) -> bias + ReLU -> global.
+// Structure: persistent, warp-specialised, one CTA per SM, 320 threads:
+//   warp 0      TMA producer: cp.async.bulk.tensor (128-byte swizzle) of the raw fp32 A (128 x 32) and
+//               B (BN x 32) tiles into a ring of shared-memory stages, completion on mbarriers;
+//   warps 2-5   splitters: one element-wise pass over the landed stage, lo = x - tf32(x) written to a twin
+//               tile at the SAME swizzled offset (layout-agnostic, bank-conflict-free); the raw tile itself
+//               is the "hi" operand (the tensor core reads only the upper 19 bits of each fp32 word; mode 1
+//               rewrites it in place with the round-to-nearest TF32 value instead);
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M 128, N BN, K 8) from
+//               shared-memory descriptors, 12 per stage; tcgen05.commit frees the stage / publishes the tile;
+//   warps 6-9   epilogue: tcgen05.ld 32x32b of the finished accumulator (double-buffered in TMEM, so the next
+//               tile's MMAs overlap), + bias, ReLU, store (or a split-K partial to the workspace).
+// Operands may be K-major (row-major M x K) or MN-major (row-major K x M, i.e. the transposed view), which
+// is what the backward GEMMs need (dX = dZ W, dW = dZ^T X) -- no transposed copies are ever made.
 #include "common.cuh"
+#include <cuda.h>
 
 namespace {
 
 using namespace pb;
 
-constexpr int BM = 128, BK = 32, STAGES = 2;
+constexpr int BM = 128, BK = 32;
+constexpr int NUM_THREADS = 320;
+constexpr int SMEM_BUDGET = 200 * 1024;          // operand stages; barriers live in static shared memory
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -44,6 +50,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -53,22 +72,29 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// shared-memory matrix descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 B (rows 16 B apart);
-// SBO = byte distance between 8-row groups, LBO = byte distance between the two 16-byte K chunks of one MMA
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+// Shared-memory matrix descriptor, descriptor version 1 (sm_100).
+//   K-major tile  (rows x 32 floats, row = 128 B), layout 2 = SWIZZLE_128B (16-byte chunks, 8-row atom):
+//       SBO = 1024 (next 8 rows), LBO unused
+//   MN-major tile (groups of [32 K-rows x 32 M/N floats], K-row = 128 B), layout 1 = SWIZZLE_128B_BASE32B
+//   (32-byte chunks, 4-row atom) -- the only swizzle the tensor core accepts for MN-major 32-bit operands
+//   (TMA side: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
+//       SBO = 512 (next 4 K-rows), LBO = 4096 (next 32 M/N)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout)
 {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;                       // descriptor version for sm_100
-    return d;                                     // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
 }
 
-// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = BN
-__host__ __device__ constexpr uint32_t make_idesc(int n)
+// instruction descriptor: D fp32, A/B tf32, M = 128, N = n; major bits: 0 = K-major, 1 = MN-major
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn, int b_mn)
 {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -81,177 +107,447 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint
                  : "memory");
 }
 
-__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo)
-{
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));     // round-to-nearest TF32 (low 13 mantissa bits zero)
-    hi = __uint_as_float(h);
-    lo = x - hi;                                            // exact; the tensor core truncates it to TF32
-}
-
-struct TcArgs {
-    const float *A, *B, *bias;
+struct TcParams {
     float *C;
-    long long a_bs, b_bs, c_bs, bias_bs;
-    int M, N, K, act;
+    const float *bias;
+    float *ws;                     // split-K partials [batch][splits][M][N] (splits > 1)
+    long long c_bs, bias_bs;
+    int ldc;
+    int M, N;
+    int kblocks;                   // 32-wide K blocks per K batch
+    int kbatches;                  // operand batches summed into one output (shared-input dgrad); else 1
+    int batch;                     // output batches
+    int a_batched, b_batched;
+    int tiles_m, tiles_n, splits, kb_per_split;
+    int act;                       // 0 none, 1 ReLU
+    int split_mode;                // 0: hi = raw word (hardware truncation); 1: hi rewritten as cvt.rna.tf32
 };
 
-// tile of R rows x BK floats: chunk c (16 B = 4 floats of K) of row r lives at c*(R*16) + r*16
-template <int R>
-__device__ __forceinline__ void fill_tile(float *hi_tile, float *lo_tile, const float *__restrict__ src, int ld,
-                                          int row0, int rows, int k0, int t)
+struct Unit { int b, tm, tn, sp, kb0, kb1; };
+
+__device__ __forceinline__ Unit decode_unit(const TcParams &g, int u)
 {
-#pragma unroll
-    for (int i = 0; i < R * (BK / 4) / 128; ++i) {
-        const int e = t + i * 128, r = e >> 3, c = e & 7;           // 8 threads cover one row's 128 bytes
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row0 + r < rows) v = *reinterpret_cast<const float4 *>(src + (size_t)(row0 + r) * ld + k0 + c * 4);
-        float4 h, l;
-        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-        const int off = c * (R * 4) + r * 4;                         // in floats
-        *reinterpret_cast<float4 *>(hi_tile + off) = h;
-        *reinterpret_cast<float4 *>(lo_tile + off) = l;
-    }
+    Unit w;
+    w.tn = u % g.tiles_n; u /= g.tiles_n;
+    w.sp = u % g.splits;  u /= g.splits;
+    w.tm = u % g.tiles_m; w.b = u / g.tiles_m;
+    const int kb_total = g.kblocks * g.kbatches;
+    w.kb0 = w.sp * g.kb_per_split;
+    w.kb1 = min(kb_total, w.kb0 + g.kb_per_split);
+    return w;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(128) tc_gemm_kernel(TcArgs g)
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams g)
 {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    constexpr int A_TILE = BM * BK, B_TILE = BN * BK;               // floats
-    float *tiles = reinterpret_cast<float *>(smem_raw);
-    // per stage: A_hi | A_lo | B_hi | B_lo
-    constexpr int STAGE_FLOATS = 2 * A_TILE + 2 * B_TILE;
-    __shared__ uint64_t bar_free[STAGES];
-    __shared__ uint64_t bar_done;
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, RAW_BYTES = A_BYTES + B_BYTES;
+    constexpr int STAGE_BYTES = 2 * RAW_BYTES;                       // raw (hi) | lo
+    constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
+    constexpr int ACC = (2 * BN <= 512) ? 2 : 1;
+    constexpr uint32_t TMEM_COLS = (uint32_t)(ACC * BN);
+    static_assert(STAGES >= 2, "pipeline needs two stages");
+    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32 && TMEM_COLS <= 512, "TMEM columns");
+
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar_full[STAGES], bar_ready[STAGES], bar_empty[STAGES];
+    __shared__ uint64_t bar_acc_full[ACC], bar_acc_empty[ACC];
     __shared__ uint32_t tmem_base_slot;
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, batch = blockIdx.z;
-    const float *A = g.A + batch * g.a_bs, *B = g.B + batch * g.b_bs;
-    float *C = g.C + batch * g.c_bs;
-    const float *bias = g.bias ? g.bias + batch * g.bias_bs : nullptr;
+    const int n_units = g.batch * g.tiles_m * g.tiles_n * g.splits;
 
     if (t == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&bar_free[s], 1);
-        mbar_init(&bar_done, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_ready[s], 4); mbar_init(&bar_empty[s], 1); }
+        for (int a = 0; a < ACC; ++a) { mbar_init(&bar_acc_full[a], 1); mbar_init(&bar_acc_empty[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     }
-    if (warp == 0) {
+    if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                     "r"((uint32_t)BN) : "memory");
+                     "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_c = tmem_base_slot;
-    constexpr uint32_t idesc = make_idesc(BN);
+    const uint32_t tmem_base = tmem_base_slot;
 
-    const int n_kb = g.K / BK;
-    for (int kb = 0; kb < n_kb; ++kb) {
-        const int s = kb % STAGES, use = kb / STAGES;
-        if (use > 0) mbar_wait(&bar_free[s], (uint32_t)((use - 1) & 1));   // the MMAs that read this stage are done
-        float *a_hi = tiles + s * STAGE_FLOATS, *a_lo = a_hi + A_TILE, *b_hi = a_lo + A_TILE, *b_lo = b_hi + B_TILE;
-        fill_tile<BM>(a_hi, a_lo, A, g.K, m0, g.M, kb * BK, t);
-        fill_tile<BN>(b_hi, b_lo, B, g.K, n0, g.N, kb * BK, t);
-        fence_async_smem();                                         // generic-proxy writes -> visible to the tensor core
-        __syncthreads();
-        if (t == 0) {
-            tc_fence_after();
-            const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const Unit w = decode_unit(g, u);
+                const int m0 = w.tm * BM, n0 = w.tn * BN;
+                for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&bar_empty[s], ((it / STAGES) & 1) ^ 1);
+                    const int kbatch = kb / g.kblocks, k0 = (kb % g.kblocks) * BK;
+                    const int zb = g.kbatches > 1 ? kbatch : w.b;
+                    const int za = g.a_batched ? zb : 0, zbb = g.b_batched ? zb : 0;
+                    const uint32_t a_dst = smem_u32(smem + s * STAGE_BYTES), b_dst = a_dst + A_BYTES;
+                    mbar_expect_tx(&bar_full[s], RAW_BYTES);
+                    if (A_MN) {
 #pragma unroll
-            for (int ks = 0; ks < BK / 8; ++ks) {
-                const uint32_t ao = 2 * ks * (BM * 16), bo = 2 * ks * (BN * 16);     // two 16-byte K chunks per MMA
-                const uint64_t dah = make_desc(ah + ao, BM * 16, 128), dal = make_desc(al + ao, BM * 16, 128);
-                const uint64_t dbh = make_desc(bh + bo, BN * 16, 128), dbl = make_desc(bl + bo, BN * 16, 128);
-                umma_tf32(tmem_c, dal, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);    // small terms first
-                umma_tf32(tmem_c, dah, dbl, idesc, 1u);
-                umma_tf32(tmem_c, dah, dbh, idesc, 1u);
-            }
-            umma_commit(&bar_free[s]);                              // arrives when the MMAs above have finished
-            if (kb == n_kb - 1) umma_commit(&bar_done);
-        }
-    }
-    mbar_wait(&bar_done, 0);
-    tc_fence_after();
-
-    // epilogue: warp w owns TMEM lanes [32w, 32w+32) = output rows m0 + 32w + lane
-    const int row = m0 + warp * 32 + lane;
-#pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_c + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 32);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
-                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
-                     " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                       "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                     : "r"(taddr) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < g.M) {
-            float *crow = C + (size_t)row * g.N + n0 + cc * 32;
+                        for (int gI = 0; gI < BM / 32; ++gI) tma_load_3d(a_dst + gI * 4096, &tmA, &bar_full[s], m0 + gI * 32, k0, za);
+                    } else {
+                        tma_load_3d(a_dst, &tmA, &bar_full[s], k0, m0, za);
+                    }
+                    if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                       __uint_as_float(r[j + 3]));
-                if (bias) {
-                    const float4 bb = *reinterpret_cast<const float4 *>(bias + n0 + cc * 32 + j);
-                    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                        for (int gI = 0; gI < BN / 32; ++gI) tma_load_3d(b_dst + gI * 4096, &tmB, &bar_full[s], n0 + gI * 32, k0, zbb);
+                    } else {
+                        tma_load_3d(b_dst, &tmB, &bar_full[s], k0, n0, zbb);
+                    }
                 }
-                if (g.act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                *reinterpret_cast<float4 *>(crow + j) = v;
             }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+            constexpr uint32_t A_LBO = A_MN ? 4096 : 16, B_LBO = B_MN ? 4096 : 16;
+            constexpr uint32_t A_SBO = A_MN ? 512 : 1024, B_SBO = B_MN ? 512 : 1024;
+            constexpr uint32_t A_LAY = A_MN ? 1 : 2, B_LAY = B_MN ? 1 : 2;
+            constexpr uint32_t A_KSTEP = A_MN ? 1024 : 32, B_KSTEP = B_MN ? 1024 : 32;   // bytes per K = 8
+            uint32_t it = 0, ui = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+                const Unit w = decode_unit(g, u);
+                const int acc = ui % ACC;
+                mbar_wait(&bar_acc_empty[acc], ((ui / ACC) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_c = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&bar_full[s], ph);
+                    mbar_wait(&bar_ready[s], ph);
+                    tc_fence_after();
+                    const uint32_t ah = smem_u32(smem + s * STAGE_BYTES), bh = ah + A_BYTES;
+                    const uint32_t al = ah + RAW_BYTES, bl = bh + RAW_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint64_t dah = make_desc(ah + ks * A_KSTEP, A_LBO, A_SBO, A_LAY);
+                        const uint64_t dal = make_desc(al + ks * A_KSTEP, A_LBO, A_SBO, A_LAY);
+                        const uint64_t dbh = make_desc(bh + ks * B_KSTEP, B_LBO, B_SBO, B_LAY);
+                        const uint64_t dbl = make_desc(bl + ks * B_KSTEP, B_LBO, B_SBO, B_LAY);
+                        umma_tf32(tmem_c, dal, dbh, idesc, (kb > w.kb0 || ks > 0) ? 1u : 0u);   // small terms first
+                        umma_tf32(tmem_c, dah, dbl, idesc, 1u);
+                        umma_tf32(tmem_c, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(&bar_empty[s]);                       // stage reusable once these MMAs retire
+                }
+                umma_commit(&bar_acc_full[acc]);                      // accumulator complete
+            }
+        }
+    } else if (warp < 6) {
+        // ------------------------------------------------------------------ splitters (128 threads)
+        const int st = t - 64;
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const Unit w = decode_unit(g, u);
+            for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&bar_full[s], (it / STAGES) & 1);
+                float4 *raw = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
+                float4 *lo = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + RAW_BYTES);
+                constexpr int N4 = RAW_BYTES / 16, PER = N4 / 128;
+                static_assert(N4 % 128 == 0 && PER % 4 == 0, "split loop shape");
+                if (g.split_mode == 0) {
+#pragma unroll
+                    for (int j0 = 0; j0 < PER; j0 += 4) {
+                        float4 v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = raw[st + (j0 + j) * 128];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float4 l;
+                            l.x = v[j].x - __uint_as_float(__float_as_uint(v[j].x) & 0xFFFFE000u);
+                            l.y = v[j].y - __uint_as_float(__float_as_uint(v[j].y) & 0xFFFFE000u);
+                            l.z = v[j].z - __uint_as_float(__float_as_uint(v[j].z) & 0xFFFFE000u);
+                            l.w = v[j].w - __uint_as_float(__float_as_uint(v[j].w) & 0xFFFFE000u);
+                            lo[st + (j0 + j) * 128] = l;
+                        }
+                    }
+                } else {
+#pragma unroll 2
+                    for (int j = 0; j < PER; ++j) {
+                        const float4 v = raw[st + j * 128];
+                        float4 h, l;
+                        uint32_t r;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v.x)); h.x = __uint_as_float(r); l.x = v.x - h.x;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v.y)); h.y = __uint_as_float(r); l.y = v.y - h.y;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v.z)); h.z = __uint_as_float(r); l.z = v.z - h.z;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v.w)); h.w = __uint_as_float(r); l.w = v.w - h.w;
+                        raw[st + j * 128] = h;
+                        lo[st + j * 128] = l;
+                    }
+                }
+                fence_async_smem();                                   // generic-proxy writes -> tensor-core (async) proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_ready[s]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 6-9)
+        const int q = warp & 3;                                       // TMEM lane quarter this warp may access
+        uint32_t ui = 0;
+        const bool vec_ok = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.c_bs % 4 == 0) &&
+                            (!g.bias || (((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) && (g.bias_bs % 4 == 0)));
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+            const Unit w = decode_unit(g, u);
+            const int acc = ui % ACC;
+            mbar_wait(&bar_acc_full[acc], (ui / ACC) & 1);
+            tc_fence_after();
+            const int row = w.tm * BM + q * 32 + lane, n0 = w.tn * BN;
+            const bool partial = g.splits > 1;
+            float *crow;
+            if (partial) crow = g.ws + ((size_t)(w.b * g.splits + w.sp) * g.M + row) * g.N;
+            else crow = g.C + (size_t)w.b * g.c_bs + (size_t)row * g.ldc;
+            const bool pvec = partial ? (g.N % 4 == 0) : vec_ok;
+            const float *bias = (g.bias && !partial) ? g.bias + (size_t)w.b * g.bias_bs : nullptr;
+            const bool relu = g.act == 1 && !partial;
+#pragma unroll 1
+            for (int cc = 0; cc < BN / 32; ++cc) {
+                const int c0 = n0 + cc * 32;
+                if (c0 >= g.N) break;                                 // warp-uniform
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cc * 32);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+                             " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                               "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                             : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < g.M) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int col = c0 + j;
+                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                               __uint_as_float(r[j + 3]));
+                        if (pvec && col + 3 < g.N) {
+                            if (bias) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col));
+                                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                            }
+                            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            *reinterpret_cast<float4 *>(crow + col) = v;
+                        } else {
+                            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                if (col + i < g.N) {
+                                    float x = e[i] + (bias ? __ldg(bias + col + i) : 0.f);
+                                    crow[col + i] = relu ? fmaxf(x, 0.f) : x;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_acc_empty[acc]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_c), "r"((uint32_t)BN) : "memory");
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
 }
 
-template <int BN>
-int launch_tc(const TcArgs &g, int batch, void *stream)
+// out[b][m][n] = act(sum_s ws[b][s][m][n] + bias[b][n])
+__global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(TcParams g)
+{
+    const long long per = (long long)g.M * g.N, total = per * g.batch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per);
+        const long long r = i - (long long)b * per;
+        const int m = (int)(r / g.N), n = (int)(r - (long long)m * g.N);
+        const float *p = g.ws + (size_t)b * g.splits * per + r;
+        float a = 0.f;
+        for (int s = 0; s < g.splits; ++s) a += p[(size_t)s * per];
+        if (g.bias) a += g.bias[(size_t)b * g.bias_bs + n];
+        if (g.act == 1) a = fmaxf(a, 0.f);
+        g.C[(size_t)b * g.c_bs + (size_t)m * g.ldc + n] = a;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// operand with logical shape rows x kdim (x nbatch).  major 0: stored row-major [rows][kdim] (ld floats);
+// major 1: stored row-major [kdim][rows] (ld floats).  Box = 32 floats along the contiguous dimension.
+int make_map(CUtensorMap *map, const float *ptr, int major, long long rows, long long kdim, long long ld, long long bs,
+             long long nbatch, int tile_rows)
+{
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return PB_E_UNSUPPORTED;
+    if ((ld % 4) != 0 || (bs % 4) != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15)) return PB_E_ARG;
+    cuuint64_t dims[3], strides[2];
+    cuuint32_t box[3], estr[3] = {1, 1, 1};
+    const long long outer_rows = major ? kdim : rows;
+    dims[0] = (cuuint64_t)(major ? rows : kdim);
+    dims[1] = (cuuint64_t)outer_rows;
+    dims[2] = (cuuint64_t)(nbatch > 0 ? nbatch : 1);
+    strides[0] = (cuuint64_t)ld * 4;
+    strides[1] = (cuuint64_t)((nbatch > 1 && bs > 0) ? bs : outer_rows * ld) * 4;
+    box[0] = 32;
+    box[1] = (cuuint32_t)(major ? BK : tile_rows);
+    box[2] = 1;
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PB_OK : PB_E_ARG;
+}
+
+template <int BN, int A_MN, int B_MN>
+int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &g, int grid, void *stream)
 {
     static bool attr_set = false;
-    const size_t smem = sizeof(float) * STAGES * (2 * BM * BK + 2 * BN * BK);
+    const int smem = SMEM_BUDGET / (2 * (BM + BN) * BK * 4) * (2 * (BM + BN) * BK * 4) + 1024;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    dim3 grid((unsigned)(g.N / BN), (unsigned)((g.M + BM - 1) / BM), (unsigned)batch);
-    PB_LAUNCH(tc_gemm_kernel<BN>, grid, 128, smem, stream, g);
+    PB_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN>), grid, NUM_THREADS, smem, stream, ta, tb, g);
     return PB_OK;
+}
+
+template <int BN>
+int launch_bn(int a_mn, int b_mn, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &g, int grid, void *stream)
+{
+    if (!a_mn && !b_mn) return launch_cfg<BN, 0, 0>(ta, tb, g, grid, stream);
+    if (!a_mn && b_mn) return launch_cfg<BN, 0, 1>(ta, tb, g, grid, stream);
+    if (a_mn && b_mn) return launch_cfg<BN, 1, 1>(ta, tb, g, grid, stream);
+    return launch_cfg<BN, 1, 0>(ta, tb, g, grid, stream);
+}
+
+// modelled cost (SM clocks) of one K block and one epilogue at tile width bn: the MMA time and the shared-memory
+// traffic (12 operand reads + the split pass) whichever is larger -- see DESIGN.md section 4
+double kb_clocks(int bn)
+{
+    const double mma = 12.0 * bn / 2.0;
+    const double smem = (12.0 * (4096 + bn * 32) + 2.0 * (BM + bn) * 128) / 128.0;
+    return mma > smem ? mma : smem;
 }
 
 }  // namespace
 
 extern "C" {
 
-// 1 when pb_linear_fwd_tc accepts the shape (K % 32 == 0, N % 64 == 0, 16-byte aligned rows)
-int pb_linear_fwd_tc_supported(int M, int N, int J)
+int pb_tc_gemm_supported(int M, int N, int K, long long lda, long long ldb, long long ldc)
 {
-    return (M > 0 && N > 0 && J > 0 && (J % BK) == 0 && (N % 64) == 0) ? 1 : 0;
+    return (M > 0 && N > 0 && K > 0 && (lda % 4) == 0 && (ldb % 4) == 0 && ldc >= N) ? 1 : 0;
 }
 
-// Y[k] (M x N) = act(X[k] (M x J) W[k]^T (N x J) + b[k]) on the tensor cores (3xTF32, fp32-level accuracy)
+// C[b] = act(sum over K (and over kbatches operand batches) A . B^T + bias[b]); see the header.
+int pb_tc_gemm(int batch, int kbatches, int M, int N, int K,
+               const float *A, int a_major, long long lda, long long a_bs,
+               const float *B, int b_major, long long ldb, long long b_bs,
+               const float *bias, long long bias_bs, int act,
+               float *C, long long ldc, long long c_bs,
+               float *workspace, long long workspace_floats, int split_mode, void *stream)
+{
+    if (batch <= 0 || kbatches <= 0 || !A || !B || !C || (act != 0 && act != 1)) return PB_E_ARG;
+    if (kbatches > 1 && batch != 1) return PB_E_ARG;
+    if (!pb_tc_gemm_supported(M, N, K, lda, ldb, ldc)) return PB_E_UNSUPPORTED;
+    if (split_mode != 0 && split_mode != 1) return PB_E_ARG;
+    const int sms = pb_sm_count();
+    TcParams g = {};
+    g.C = C; g.bias = bias; g.ws = workspace;
+    g.c_bs = c_bs; g.bias_bs = bias_bs; g.ldc = (int)ldc;
+    g.M = M; g.N = N;
+    g.kblocks = (K + BK - 1) / BK;
+    g.kbatches = kbatches;
+    g.batch = batch;
+    g.a_batched = a_bs != 0; g.b_batched = b_bs != 0;
+    g.tiles_m = (M + BM - 1) / BM;
+    g.act = act; g.split_mode = split_mode;
+    const int kb_total = g.kblocks * kbatches;
+
+    // tile width and split-K factor: minimise modelled waves x (K blocks x clocks + epilogue) + split-K reduction
+    int best_bn = 64, best_s = 1;
+    double best = 1e300;
+    const int bns[3] = {256, 128, 64};
+    for (int bi = 0; bi < 3; ++bi) {
+        const int bn = bns[bi];
+        if (bn > 64 && bn / 2 >= N) continue;                          // tile twice as wide as the matrix
+        const long long tiles = (long long)batch * g.tiles_m * ((N + bn - 1) / bn);
+        for (int s = 1; s <= 16 && s <= kb_total; ++s) {
+            const int per = (kb_total + s - 1) / s;
+            const int s_eff = (kb_total + per - 1) / per;
+            if (s_eff != s) continue;
+            if (s > 1 && (!workspace || (long long)batch * s * M * N > workspace_floats)) continue;
+            const long long units = tiles * s;
+            const long long waves = (units + sms - 1) / sms;
+            double cost = (double)waves * (per * kb_clocks(bn) + 22.0 * bn + 1500.0);
+            if (s > 1) cost += (double)(s + 1) * batch * M * N * 4.0 / 3000.0 + 4000.0;
+            if (cost < best) { best = cost; best_bn = bn; best_s = s; }
+        }
+    }
+    g.tiles_n = (N + best_bn - 1) / best_bn;
+    g.splits = best_s;
+    g.kb_per_split = (kb_total + best_s - 1) / best_s;
+
+    CUtensorMap ta, tb;
+    const long long nb = kbatches > 1 ? kbatches : batch;
+    int rc = make_map(&ta, A, a_major, M, K, lda, a_bs, g.a_batched ? nb : 1, BM);
+    if (rc != PB_OK) return rc;
+    rc = make_map(&tb, B, b_major, N, K, ldb, b_bs, g.b_batched ? nb : 1, best_bn);
+    if (rc != PB_OK) return rc;
+
+    const long long units = (long long)batch * g.tiles_m * g.tiles_n * g.splits;
+    const int grid = (int)(units < sms ? units : sms);
+    if (best_bn == 256) rc = launch_bn<256>(a_major, b_major, ta, tb, g, grid, stream);
+    else if (best_bn == 128) rc = launch_bn<128>(a_major, b_major, ta, tb, g, grid, stream);
+    else rc = launch_bn<64>(a_major, b_major, ta, tb, g, grid, stream);
+    if (rc != PB_OK) return rc;
+    if (g.splits > 1) {
+        const long long total = (long long)batch * M * N;
+        long long blocks = (total + 255) / 256;
+        if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+        PB_LAUNCH(tc_splitk_reduce_kernel, (unsigned)blocks, 256, 0, stream, g);
+    }
+    return PB_OK;
+}
+
+// Forward dense layer on the tensor cores: Y[k] (M x N) = act(X[k] (M x J) W[k]^T (N x J) + b[k]).
+int pb_linear_fwd_tc_supported(int M, int N, int J)
+{
+    return (M > 0 && N > 0 && J > 0 && (J % 4) == 0) ? 1 : 0;
+}
+
 int pb_linear_fwd_tc(int K, int M, int N, int J, const float *X, long long x_head_stride, const float *W,
                      const float *b, int act, float *Y, void *stream)
 {
-    if (K <= 0 || !X || !W || !Y || (act != 0 && act != 1)) return PB_E_ARG;
-    if (!pb_linear_fwd_tc_supported(M, N, J)) return PB_E_UNSUPPORTED;
-    if ((((uintptr_t)X) | ((uintptr_t)W) | ((uintptr_t)Y) | ((uintptr_t)b)) & 15) return PB_E_ARG;
-    TcArgs g = {};
-    g.A = X; g.a_bs = x_head_stride;
-    g.B = W; g.b_bs = (long long)N * J;
-    g.C = Y; g.c_bs = (long long)M * N;
-    g.bias = b; g.bias_bs = N;
-    g.M = M; g.N = N; g.K = J; g.act = act;
-    if (N % 128 == 0) return launch_tc<128>(g, K, stream);
-    return launch_tc<64>(g, K, stream);
+    return pb_tc_gemm(K, 1, M, N, J, X, 0, J, x_head_stride, W, 0, J, (long long)N * J, b, N, act, Y, N,
+                      (long long)M * N, nullptr, 0, 0, stream);
 }
 
 }  // extern "C"

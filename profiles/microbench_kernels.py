@@ -65,18 +65,31 @@ if __name__ == "__main__" and "--tc" not in sys.argv:
 
 
 def tc_bench():
-    """tcgen05 3xTF32 forward vs the library SGEMM at the IQN / ensemble shapes."""
-    for (K, M, N, J) in [(1, 2048, 256, 1024), (1, 32768, 512, 3136), (1, 32768, 3136, 64), (10, 512, 512, 3136)]:
+    """tcgen05 3xTF32 GEMMs (forward, input gradient, weight gradient) vs the library SGEMM at the IQN / ensemble
+    shapes of configs[0] and configs[4]."""
+    shapes = [(1, 2048, 256, 1024), (1, 2048, 1024, 64), (1, 32768, 512, 3136), (1, 32768, 3136, 64), (10, 512, 512, 3136),
+              (1, 8192, 1024, 1024)]
+    for (K, M, N, J) in shapes:
         x = torch.randn(K, M, J, device=dev)
         w = torch.randn(K, N, J, device=dev)
         b = torch.randn(K, N, device=dev)
-        reps = 20 if M < 10000 else 3
-        with torch.no_grad():
-            t_tc = graph_time(lambda: ops._LinearTC.apply(x, w, b, 1), reps=reps)
-            t_lib = graph_time(lambda: torch.relu(torch.baddbmm(b.unsqueeze(1), x, w.transpose(1, 2))), reps=reps)
+        dz = torch.randn(K, M, N, device=dev)
+        y, dx, dw = torch.empty(K, M, N, device=dev), torch.empty(K, M, J, device=dev), torch.empty(K, N, J, device=dev)
+        reps = 20 if M * N * J * K < 2e10 else 3
         fl = 2.0 * K * M * N * J
-        print("tc_linear K%d M%d N%d J%d: tcgen05 3xTF32 %9.2f us (%.1f TFLOP/s fp32-equivalent)   cuBLAS fp32 %9.2f us (%.1f TFLOP/s)"
-              % (K, M, N, J, t_tc, fl / t_tc / 1e6, t_lib, fl / t_lib / 1e6))
+        rows = [
+            ("fwd  ", lambda: ops.tc_gemm(y, x, 0, J, M * J, w, 0, J, N * J, K, M, N, J, bias=b, bias_bs=N, act=1),
+             lambda: torch.relu(torch.baddbmm(b.unsqueeze(1), x, w.transpose(1, 2)))),
+            ("dgrad", lambda: ops.tc_gemm(dx, dz, 0, N, M * N, w, 1, J, N * J, K, M, J, N), lambda: torch.bmm(dz, w)),
+            ("wgrad", lambda: ops.tc_gemm(dw, dz, 1, N, M * N, x, 1, J, M * J, K, N, J, M),
+             lambda: torch.bmm(dz.transpose(1, 2), x)),
+        ]
+        for name, f_tc, f_lib in rows:
+            with torch.no_grad():
+                t_tc = graph_time(f_tc, reps=reps)
+                t_lib = graph_time(f_lib, reps=reps)
+            print("tc_gemm %s K%d M%d N%d J%d: tcgen05 3xTF32 %9.2f us (%6.1f TFLOP/s fp32-equivalent)   cuBLAS fp32 %9.2f us (%5.1f TFLOP/s)"
+                  % (name, K, M, N, J, t_tc, fl / t_tc / 1e6, t_lib, fl / t_lib / 1e6), flush=True)
 
 
 if __name__ == "__main__" and "--tc" in sys.argv:

@@ -300,6 +300,52 @@ def test_fused_linear_matches_torch(K, M, N, J, shared, relu):
     assert rel_err(bd.grad.cpu().numpy(), br.grad.numpy()) < 2e-5
 
 
+@pytest.mark.parametrize("split_mode", [0, 1])
+@pytest.mark.parametrize("batch,kbatches,M,N,K,a_major,b_major,act", [
+    (1, 1, 128, 64, 32, 0, 0, 0),            # one tile, one K block
+    (1, 1, 128, 64, 32, 1, 0, 0),            # MN-major A
+    (1, 1, 128, 64, 32, 0, 1, 0),            # MN-major B
+    (1, 1, 300, 72, 100, 0, 0, 1),           # ragged M / N / K (TMA zero fill), bias + ReLU
+    (1, 1, 300, 72, 100, 1, 1, 0),           # weight-gradient form, ragged
+    (3, 1, 260, 200, 96, 0, 1, 0),           # batched input-gradient form
+    (1, 4, 256, 320, 64, 0, 1, 0),           # K loop over 4 operand batches (shared-input gradient)
+    (1, 1, 512, 3136, 64, 0, 0, 1),          # cos-embedding layer shape (config 5 columns)
+    (1, 1, 256, 512, 8192, 1, 1, 0),         # long K: split-K partials + reduction
+    (2, 1, 1024, 256, 1024, 0, 0, 1),        # persistent loop: several tiles per CTA, both accumulators
+])
+def test_tc_gemm_matches_fp64(batch, kbatches, M, N, K, a_major, b_major, act, split_mode):
+    """pb_tc_gemm (tcgen05 3xTF32, TMA-fed, TMEM accumulators) against fp64 math, every operand orientation:
+    2e-5 of the output's max (single-pass TF32 sits at ~1e-3)."""
+    from prism_b200.agents import ops
+    g = torch.Generator().manual_seed(batch * 7 + M + N + K + a_major * 3 + b_major * 5)
+    nb = kbatches if kbatches > 1 else batch
+    a = torch.randn((nb, K, M) if a_major else (nb, M, K), generator=g)
+    b = torch.randn((nb, K, N) if b_major else (nb, N, K), generator=g) / K ** 0.5
+    bias = torch.randn(batch, N, generator=g) if act else None
+    ad, bd = a.to(DEV), b.to(DEV)
+    out = torch.full((batch, M, N), float("nan"), device=DEV)
+    old = ops.TC_SPLIT_MODE
+    ops.TC_SPLIT_MODE = split_mode
+    try:
+        ops.tc_gemm(out, ad, a_major, M if a_major else K, M * K, bd, b_major, N if b_major else K, N * K, batch, M, N, K,
+                    bias=None if bias is None else bias.to(DEV), bias_bs=N, act=act, kbatches=kbatches)
+        torch.cuda.synchronize()
+    finally:
+        ops.TC_SPLIT_MODE = old
+    al = (a.transpose(1, 2) if a_major else a).double()
+    bl = (b.transpose(1, 2) if b_major else b).double()
+    ref = torch.bmm(al, bl.transpose(1, 2))
+    if kbatches > 1:
+        ref = ref.sum(dim=0, keepdim=True)
+    if bias is not None:
+        ref = ref + bias.double().unsqueeze(1)
+    if act:
+        ref = torch.relu(ref)
+    got = out.cpu().double()
+    assert torch.isfinite(got).all()
+    assert rel_err(got.numpy(), ref.numpy()) < 2e-5
+
+
 @pytest.mark.parametrize("K,M,N,J,shared,relu", [
     (1, 2048, 256, 1024, True, True), (1, 2048, 1024, 64, True, True), (1, 300, 64, 32, True, False),
     (10, 512, 512, 3136, False, True), (2, 1000, 128, 96, True, False)])
