@@ -348,18 +348,28 @@ int pb_linear_bwd_weight(int K, int M, int N, int J, const float *dY, const floa
  * whose input is shared by all heads).  workspace: optional scratch for split-K partials (the kernel picks the
  * split so that batch*splits*M*N <= workspace_floats).  split_mode 0: hi = the raw fp32 word (the tensor core
  * reads its upper 19 bits); 1: hi = cvt.rna.tf32.  Requirements: 16-byte aligned A/B, lda/ldb/a_bs/b_bs % 4 == 0
- * (PB_E_UNSUPPORTED / PB_E_ARG otherwise).  act: 0 none, 1 ReLU. */
+ * (PB_E_UNSUPPORTED / PB_E_ARG otherwise).  act: 0 none, 1 ReLU.  mul (optional): after bias and activation
+ * every output is multiplied by mul[(m % mul_rows) * ld_mul + n] -- the IQN product phi(tau) (.) x with the
+ * state embedding x broadcast over the quantile-major rows (iqn_model.py:70-71), fused into the phi GEMM. */
 int pb_tc_gemm_supported(int M, int N, int K, long long lda, long long ldb, long long ldc);
 int pb_tc_gemm(int batch, int kbatches, int M, int N, int K,
                const float *A, int a_major, long long lda, long long a_bs,
                const float *B, int b_major, long long ldb, long long b_bs,
                const float *bias, long long bias_bs, int act,
+               const float *mul, int mul_rows, long long ld_mul,
                float *C, long long ldc, long long c_bs,
                float *workspace, long long workspace_floats, int split_mode, void *stream);
 /* nn.Linear forward through pb_tc_gemm: Y[k] (M x N) = act(X[k] (M x J) W[k]^T + b[k]), J % 4 == 0. */
 int pb_linear_fwd_tc_supported(int M, int N, int J);
 int pb_linear_fwd_tc(int K, int M, int N, int J, const float *X, long long x_head_stride, const float *W,
                      const float *b, int act, float *Y, void *stream);
+
+/* Backward of the IQN product h[q,b,:] = relu(pre[q,b,:]) (.) x[b,:]  (iqn_model.py:70-71, 89-93; rows are
+ * quantile-major r = q*B + b) in one pass: dpre = dh * x * [phi > 0], dx[b] = sum_q dh * phi,
+ * dbias_partial[b] = sum_q dpre (the bias gradient is its column sum over b).  F % 4 == 0, 16-byte aligned
+ * pointers; dx may be NULL. */
+int pb_iqn_phi_bwd(int n, int B, int F, const float *dh, const float *phi, const float *x, float *dpre, float *dx,
+                   float *dbias_partial, void *stream);
 
 /* total_loss = mean_b(dist*w) + mean_b(q'*w);  td_b = 0.5*dist + 0.5*q' | dist | |q'|
  * (composite_model.py:135-142, agent.py:58-64) with q' = q_scale * (q - *q_offset)

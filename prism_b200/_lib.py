@@ -88,8 +88,9 @@ SIGNATURES = {
     "pb_conv3x3_relu_bwd_groups": [_I],
     "pb_conv3x3_relu_bwd": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "pb_linear_fwd": [_I, _I, _I, _I, _P, _LL, _P, _P, _I, _P, _P],
+    "pb_iqn_phi_bwd": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "pb_tc_gemm_supported": [_I, _I, _I, _LL, _LL, _LL],
-    "pb_tc_gemm": [_I, _I, _I, _I, _I, _P, _I, _LL, _LL, _P, _I, _LL, _LL, _P, _LL, _I, _P, _LL, _LL, _P, _LL, _I, _P],
+    "pb_tc_gemm": [_I, _I, _I, _I, _I, _P, _I, _LL, _LL, _P, _I, _LL, _LL, _P, _LL, _I, _P, _I, _LL, _P, _LL, _LL, _P, _LL, _I, _P],
     "pb_linear_fwd_tc_supported": [_I, _I, _I],
     "pb_linear_fwd_tc": [_I, _I, _I, _I, _P, _LL, _P, _P, _I, _P, _P],
     "pb_linear_bwd_input": [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P],

@@ -80,9 +80,9 @@ class IQNModel(nn.Module):
             quantiles = torch.rand([n * n_rows, 1], device=self.device).float()
 
         basis = ops.cos_basis(quantiles, self.n_basis_elements)            # (n*rows, n_basis)
-        phi = ops.run_sequential(self.phi, basis)                          # (n*rows, F): Linear + ReLU, one launch
-        # quantile-major rows (r = q*rows + b): broadcast the state embedding over q
-        h = (phi.view(n, n_rows, -1) * x.unsqueeze(0)).view(n * n_rows, -1)
+        # phi(tau) (.) x with quantile-major rows (r = q*rows + b): the state embedding is broadcast over q inside
+        # the phi GEMM's epilogue (large layers) or by a broadcasting multiply (small ones)
+        h = ops.phi_times_x(self.phi, basis, x, n)
         if self.model is not None:
             h = self.model(h)
         head = self.embedding_to_quantile_layer

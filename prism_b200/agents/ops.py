@@ -208,7 +208,7 @@ def _tc_workspace(device):
 
 
 def tc_gemm(out, a, a_major, lda, a_bs, b, b_major, ldb, b_bs, batch, M, N, K, bias=None, bias_bs=0, act=0,
-            kbatches=1, ldc=None, c_bs=None):
+            kbatches=1, ldc=None, c_bs=None, mul=None):
     """out[b] (M x N) = act(A[b] . B[b]^T + bias[b]) on the tensor cores (pb_tc_gemm, 3xTF32).  See
     include/prism_b200.h for the operand conventions (major 1 = the transposed view)."""
     _lib.require_cuda(out, "out")
@@ -217,6 +217,8 @@ def tc_gemm(out, a, a_major, lda, a_bs, b, b_major, ldb, b_bs, batch, M, N, K, b
                                       a.data_ptr(), int(a_major), int(lda), int(a_bs),
                                       b.data_ptr(), int(b_major), int(ldb), int(b_bs),
                                       _lib.ptr(bias), int(bias_bs), int(act),
+                                      _lib.ptr(mul), 0 if mul is None else int(mul.shape[0]),
+                                      0 if mul is None else int(mul.stride(0)),
                                       out.data_ptr(), int(N if ldc is None else ldc), int(M * N if c_bs is None else c_bs),
                                       ws.data_ptr(), ws.numel(), int(TC_SPLIT_MODE), _stream(out)), "pb_tc_gemm")
     return out
@@ -262,12 +264,69 @@ class _LinearTC(torch.autograd.Function):
 
 
 TENSOR_CORE_LINEAR = True      # module switch for A/B timing; the tcgen05 path is the default for large layers
-TC_MIN_FLOPS = 2.0e9           # below this a layer is launch-bound and stays on the fused SIMT kernel / library
+TC_MIN_ROWS = 256              # an M = 128 tile needs rows to fill it
+TC_MIN_FLOPS = 2.0e8           # below this a layer is launch-bound and stays on the fused SIMT kernel / library
 
 
 def _tc_eligible(x, M, Kh, N, J):
-    return (TENSOR_CORE_LINEAR and x.is_cuda and (J % 4) == 0 and (N % 4) == 0
+    return (TENSOR_CORE_LINEAR and x.is_cuda and (J % 4) == 0 and (N % 4) == 0 and M >= TC_MIN_ROWS
             and 2.0 * M * Kh * N * J >= TC_MIN_FLOPS)
+
+
+class _PhiTimesX(torch.autograd.Function):
+    """h[q*B + b, :] = relu(basis[q*B + b, :] W^T + bias) * x[b, :]   (iqn_model.py:70-71, 89-93).
+
+    Forward: the broadcast product is fused into the tensor-core GEMM's epilogue, so the (n*B, F) tensor phi is
+    only materialised when a gradient is needed (a second pass of the K = 64 GEMM is cheaper than an element-wise
+    kernel reading and writing (n*B, F)).  Backward: one fused element-wise pass (pb_iqn_phi_bwd) + the
+    weight-gradient GEMM."""
+
+    @staticmethod
+    def forward(ctx, basis, w, b, x):
+        M, J = basis.shape
+        F_ = w.shape[0]
+        B = x.shape[0]
+        basis_c, wc, bc, xc = _c(basis), _c(w), _c(b), _c(x)
+        h = torch.empty(M, F_, dtype=torch.float32, device=x.device)
+        tc_gemm(h, basis_c, 0, J, 0, wc, 0, J, 0, 1, M, F_, J, bias=bc, bias_bs=0, act=1, mul=xc)
+        if any(ctx.needs_input_grad[1:]):
+            phi = torch.empty(M, F_, dtype=torch.float32, device=x.device)
+            tc_gemm(phi, basis_c, 0, J, 0, wc, 0, J, 0, 1, M, F_, J, bias=bc, bias_bs=0, act=1)
+            ctx.save_for_backward(basis_c, phi, xc)
+            ctx.dims = (M, J, F_, B)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        basis_c, phi, xc = ctx.saved_tensors
+        M, J, F_, B = ctx.dims
+        n = M // B
+        dh = _c(dh)
+        dpre = torch.empty_like(phi)
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[3] else None
+        dbp = torch.empty_like(xc)
+        _lib.check(_lib.load().pb_iqn_phi_bwd(n, B, F_, dh.data_ptr(), phi.data_ptr(), xc.data_ptr(), dpre.data_ptr(),
+                                              _lib.ptr(dx), dbp.data_ptr(), _stream(dh)), "pb_iqn_phi_bwd")
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty(F_, J, dtype=torch.float32, device=dh.device)
+            # dW (F x J) = dpre^T (F x M) . basis (M x J): both operands read as transposes
+            tc_gemm(dw, dpre, 1, F_, 0, basis_c, 1, J, 0, 1, F_, J, M)
+        db = dbp.sum(dim=0) if ctx.needs_input_grad[2] else None
+        return None, dw, db, dx
+
+
+def phi_times_x(phi_seq, basis, x, n):
+    """IQN quantile embedding times the state embedding: (n*B, n_basis), (B, F) -> (n*B, F)."""
+    import torch.nn as nn
+    lin = phi_seq[0]
+    M, J = basis.shape
+    F_ = lin.weight.shape[0]
+    if (len(phi_seq) == 2 and isinstance(lin, nn.Linear) and isinstance(phi_seq[1], nn.ReLU) and lin.bias is not None
+            and x.dim() == 2 and x.shape[1] == F_ and (F_ % 4) == 0 and _tc_eligible(x, M, 1, F_, J)):
+        return _PhiTimesX.apply(basis, lin.weight, lin.bias, x)
+    phi = run_sequential(phi_seq, basis)
+    return (phi.view(n, x.shape[0], -1) * x.unsqueeze(0)).view(n * x.shape[0], -1)
 
 
 def linear_heads(x, w, b, relu=False):

@@ -258,7 +258,20 @@ __global__ void __launch_bounds__(ADAM_THREADS) pack_grads_kernel(const long lon
     if (src != nullptr) {
         const bool vec = ((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0;
         const long long n4 = vec ? (n >> 2) : 0;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n4; i += 4 * stride) {               // 4 independent 128-bit loads in flight
+            float4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = reinterpret_cast<const float4 *>(src)[i + k * stride];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[k].x *= scale; v[k].y *= scale; v[k].z *= scale; v[k].w *= scale;
+                reinterpret_cast<float4 *>(dst)[i + k * stride] = v[k];
+                acc += (double)(v[k].x * v[k].x + v[k].y * v[k].y) + (double)(v[k].z * v[k].z + v[k].w * v[k].w);
+            }
+        }
+        for (; i < n4; i += stride) {
             float4 v = reinterpret_cast<const float4 *>(src)[i];
             v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
             reinterpret_cast<float4 *>(dst)[i] = v;
@@ -450,9 +463,14 @@ int pb_pack_grads(int n_tensors, const long long *table, float scale, float *fla
 {
     if (n_tensors <= 0 || !table || !flat) return PB_E_ARG;
     if ((long long)n_tensors * PACK_BLOCKS_PER_TENSOR > ADAM_MAX_PARTIALS) return PB_E_UNSUPPORTED;
-    dim3 grid(PACK_BLOCKS_PER_TENSOR, (unsigned)n_tensors);
+    // as many blocks per tensor as the partial-sum table allows (blocks of small tensors exit at once; the
+    // multi-million-element tensors need the whole machine)
+    int per = ADAM_MAX_PARTIALS / n_tensors;
+    if (per > 128) per = 128;
+    if (per < PACK_BLOCKS_PER_TENSOR) per = PACK_BLOCKS_PER_TENSOR;
+    dim3 grid((unsigned)per, (unsigned)n_tensors);
     PB_LAUNCH(pack_grads_kernel, grid, ADAM_THREADS, 0, stream, table, scale, flat, partial_scratch, step_count);
-    if (n_partials_out_h) *n_partials_out_h = n_tensors * PACK_BLOCKS_PER_TENSOR;
+    if (n_partials_out_h) *n_partials_out_h = n_tensors * per;
     return PB_OK;
 }
 

@@ -63,6 +63,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -110,7 +116,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint
 struct TcParams {
     float *C;
     const float *bias;
-    float *ws;                     // split-K partials [batch][splits][M][N] (splits > 1)
+    float *ws;                     // stream-K partial tiles [2 * grid][128][BN] (two per CTA at most)
     long long c_bs, bias_bs;
     int ldc;
     int M, N;
@@ -118,28 +124,52 @@ struct TcParams {
     int kbatches;                  // operand batches summed into one output (shared-input dgrad); else 1
     int batch;                     // output batches
     int a_batched, b_batched;
-    int tiles_m, tiles_n, splits, kb_per_split;
+    int tiles_m, tiles_n;
+    int bn;                        // tile width of this launch (fix-up kernel)
+    long long work, per_cta;       // stream-K: work = tiles * kb_total K blocks, dealt out in equal contiguous ranges
     int act;                       // 0 none, 1 ReLU
     int split_mode;                // 0: hi = raw word (hardware truncation); 1: hi rewritten as cvt.rna.tf32
+    const float *mul;              // optional epilogue multiplier: out *= mul[(row % mul_rows) * ld_mul + col]
+    int mul_rows, ld_mul;
+    int tma_store;                 // 1: epilogue stores through shared memory + cp.async.bulk.tensor (tmC)
 };
 
-struct Unit { int b, tm, tn, sp, kb0, kb1; };
+// Stream-K schedule: the (tile, K block) work items are numbered tile-major (tn fastest, then tm, then batch)
+// and CTA c owns the contiguous range [c * per_cta, (c + 1) * per_cta).  A range is cut into segments at tile
+// boundaries; a segment covering all of a tile's K blocks is finished by the epilogue directly, any other
+// segment leaves a raw partial tile in the workspace (slot 2c for the CTA's first segment, 2c + 1 for its
+// last -- the segments in between are whole tiles) and tc_streamk_fixup_kernel sums the cut tiles.
+struct Seg { int b, tm, tn, kb0, kb1, slot; bool whole; };
 
-__device__ __forceinline__ Unit decode_unit(const TcParams &g, int u)
-{
-    Unit w;
-    w.tn = u % g.tiles_n; u /= g.tiles_n;
-    w.sp = u % g.splits;  u /= g.splits;
-    w.tm = u % g.tiles_m; w.b = u / g.tiles_m;
-    const int kb_total = g.kblocks * g.kbatches;
-    w.kb0 = w.sp * g.kb_per_split;
-    w.kb1 = min(kb_total, w.kb0 + g.kb_per_split);
-    return w;
-}
+struct SegIter {
+    long long pos, end, start;
+    int kb_total;
+    __device__ __forceinline__ SegIter(const TcParams &g)
+    {
+        start = pos = (long long)blockIdx.x * g.per_cta;
+        end = min(g.work, pos + g.per_cta);
+        kb_total = g.kblocks * g.kbatches;
+    }
+    __device__ __forceinline__ bool next(const TcParams &g, Seg &w)
+    {
+        if (pos >= end) return false;
+        const long long t = pos / kb_total;
+        w.kb0 = (int)(pos - t * kb_total);
+        w.kb1 = (int)min((long long)kb_total, w.kb0 + (end - pos));
+        w.whole = (w.kb0 == 0 && w.kb1 == kb_total);
+        w.slot = 2 * (int)blockIdx.x + (pos == start ? 0 : 1);
+        int u = (int)t;
+        w.tn = u % g.tiles_n; u /= g.tiles_n;
+        w.tm = u % g.tiles_m; w.b = u / g.tiles_m;
+        pos += w.kb1 - w.kb0;
+        return true;
+    }
+};
 
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams g)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const TcParams g)
 {
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, RAW_BYTES = A_BYTES + B_BYTES;
     constexpr int STAGE_BYTES = 2 * RAW_BYTES;                       // raw (hi) | lo
@@ -151,12 +181,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     extern __shared__ uint8_t smem_dyn[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint8_t *staging = smem + STAGES * STAGE_BYTES;                  // 4 epilogue warps x 2 x (32 rows x 128 B)
     __shared__ uint64_t bar_full[STAGES], bar_ready[STAGES], bar_empty[STAGES];
     __shared__ uint64_t bar_acc_full[ACC], bar_acc_empty[ACC];
     __shared__ uint32_t tmem_base_slot;
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int n_units = g.batch * g.tiles_m * g.tiles_n * g.splits;
 
     if (t == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_ready[s], 4); mbar_init(&bar_empty[s], 1); }
@@ -164,6 +194,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (g.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
@@ -179,8 +210,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t it = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const Unit w = decode_unit(g, u);
+            SegIter segs(g);
+            Seg w;
+            while (segs.next(g, w)) {
                 const int m0 = w.tm * BM, n0 = w.tn * BN;
                 for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
                     const int s = it % STAGES;
@@ -214,8 +246,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr uint32_t A_LAY = A_MN ? 1 : 2, B_LAY = B_MN ? 1 : 2;
             constexpr uint32_t A_KSTEP = A_MN ? 1024 : 32, B_KSTEP = B_MN ? 1024 : 32;   // bytes per K = 8
             uint32_t it = 0, ui = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
-                const Unit w = decode_unit(g, u);
+            SegIter segs(g);
+            Seg w;
+            for (; segs.next(g, w); ++ui) {
                 const int acc = ui % ACC;
                 mbar_wait(&bar_acc_empty[acc], ((ui / ACC) & 1) ^ 1);
                 tc_fence_after();
@@ -247,8 +280,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ------------------------------------------------------------------ splitters (128 threads)
         const int st = t - 64;
         uint32_t it = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const Unit w = decode_unit(g, u);
+        SegIter segs(g);
+        Seg w;
+        while (segs.next(g, w)) {
             for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&bar_full[s], (it / STAGES) & 1);
@@ -294,26 +328,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ------------------------------------------------------------------ epilogue (warps 6-9)
         const int q = warp & 3;                                       // TMEM lane quarter this warp may access
-        uint32_t ui = 0;
-        const bool vec_ok = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.c_bs % 4 == 0) &&
-                            (!g.bias || (((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) && (g.bias_bs % 4 == 0)));
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
-            const Unit w = decode_unit(g, u);
+        uint32_t ui = 0, chunk = 0;
+        const bool vec_ok = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.c_bs % 4 == 0);
+        const bool bias_vec = g.bias && ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) && (g.bias_bs % 4 == 0);
+        const bool mul_vec = g.mul && ((reinterpret_cast<uintptr_t>(g.mul) & 15) == 0) && (g.ld_mul % 4 == 0);
+        uint8_t *stg = staging + (warp - 6) * 8192;
+        SegIter segs(g);
+        Seg w;
+        for (; segs.next(g, w); ++ui) {
             const int acc = ui % ACC;
             mbar_wait(&bar_acc_full[acc], (ui / ACC) & 1);
             tc_fence_after();
-            const int row = w.tm * BM + q * 32 + lane, n0 = w.tn * BN;
-            const bool partial = g.splits > 1;
-            float *crow;
-            if (partial) crow = g.ws + ((size_t)(w.b * g.splits + w.sp) * g.M + row) * g.N;
-            else crow = g.C + (size_t)w.b * g.c_bs + (size_t)row * g.ldc;
-            const bool pvec = partial ? (g.N % 4 == 0) : vec_ok;
+            const bool partial = !w.whole;
+            const int row0 = w.tm * BM + q * 32, row = row0 + lane, n0 = w.tn * BN;
             const float *bias = (g.bias && !partial) ? g.bias + (size_t)w.b * g.bias_bs : nullptr;
+            const float *mul = (g.mul && !partial) ? g.mul + (size_t)(row % g.mul_rows) * g.ld_mul : nullptr;
             const bool relu = g.act == 1 && !partial;
+            float *crow = g.C + (size_t)w.b * g.c_bs + (size_t)row * g.ldc;
+            float4 *prow = reinterpret_cast<float4 *>(g.ws + ((size_t)w.slot * BM + q * 32 + lane) * BN);
 #pragma unroll 1
             for (int cc = 0; cc < BN / 32; ++cc) {
                 const int c0 = n0 + cc * 32;
-                if (c0 >= g.N) break;                                 // warp-uniform
+                if (c0 >= g.N) break;                                 // warp-uniform (fix-up never reads these columns)
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cc * 32);
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
@@ -325,28 +361,76 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                              : "r"(taddr) : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < g.M) {
+                if (partial) {
+                    // raw partial tile, dense [128][BN] in the workspace: every lane writes 128 contiguous bytes
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        prow[(cc * 32 + j) >> 2] = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                } else if (g.tma_store) {
+                    // bias / ReLU / multiplier in registers, 128-byte-swizzled 32 x 32 tile in shared memory,
+                    // one bulk tensor store per tile (full 128-byte lines; TMA clips rows >= M and columns >= N)
+                    uint8_t *buf = stg + (chunk & 1) * 4096;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    const bool full = c0 + 32 <= g.N;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                               __uint_as_float(r[j + 3]));
+                        const int col = c0 + j;
+                        if (bias) {
+                            if (bias_vec && full) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col));
+                                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                            } else {
+                                if (col < g.N) v.x += __ldg(bias + col);
+                                if (col + 1 < g.N) v.y += __ldg(bias + col + 1);
+                                if (col + 2 < g.N) v.z += __ldg(bias + col + 2);
+                                if (col + 3 < g.N) v.w += __ldg(bias + col + 3);
+                            }
+                        }
+                        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        if (mul) {
+                            if (mul_vec && full) {
+                                const float4 mm = __ldg(reinterpret_cast<const float4 *>(mul + col));
+                                v.x *= mm.x; v.y *= mm.y; v.z *= mm.z; v.w *= mm.w;
+                            } else {
+                                if (col < g.N) v.x *= __ldg(mul + col);
+                                if (col + 1 < g.N) v.y *= __ldg(mul + col + 1);
+                                if (col + 2 < g.N) v.z *= __ldg(mul + col + 2);
+                                if (col + 3 < g.N) v.w *= __ldg(mul + col + 3);
+                            }
+                        }
+                        *reinterpret_cast<float4 *>(buf + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = v;
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tma_store_3d(&tmC, smem_u32(buf), c0, row0, w.b);
+                    ++chunk;
+                } else if (row < g.M) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const int col = c0 + j;
-                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                               __uint_as_float(r[j + 3]));
-                        if (pvec && col + 3 < g.N) {
-                            if (bias) {
-                                const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col));
-                                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-                            }
-                            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                            *reinterpret_cast<float4 *>(crow + col) = v;
-                        } else {
-                            const float e[4] = {v.x, v.y, v.z, v.w};
+                        const float e[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                            __uint_as_float(r[j + 3])};
+                        float o[4];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                if (col + i < g.N) {
-                                    float x = e[i] + (bias ? __ldg(bias + col + i) : 0.f);
-                                    crow[col + i] = relu ? fmaxf(x, 0.f) : x;
-                                }
+                        for (int i = 0; i < 4; ++i) {
+                            float x = e[i];
+                            if (col + i < g.N) {
+                                if (bias) x += __ldg(bias + col + i);
+                                if (relu) x = fmaxf(x, 0.f);
+                                if (mul) x *= __ldg(mul + col + i);
                             }
+                            o[i] = x;
+                        }
+                        if (vec_ok && col + 3 < g.N) {
+                            *reinterpret_cast<float4 *>(crow + col) = make_float4(o[0], o[1], o[2], o[3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (col + i < g.N) crow[col + i] = o[i];
                         }
                     }
                 }
@@ -355,6 +439,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_acc_empty[acc]);
         }
+        if (g.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -364,20 +449,54 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-// out[b][m][n] = act(sum_s ws[b][s][m][n] + bias[b][n])
-__global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(TcParams g)
+// Stream-K fix-up: block (tile, strip of FIX_ROWS rows) sums the partial tiles of a cut tile in CTA order (a
+// fixed order: results do not depend on scheduling), applies bias / ReLU / multiplier and writes C.
+constexpr int FIX_ROWS = 4;
+
+__global__ void __launch_bounds__(256) tc_streamk_fixup_kernel(TcParams g)
 {
-    const long long per = (long long)g.M * g.N, total = per * g.batch;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int b = (int)(i / per);
-        const long long r = i - (long long)b * per;
-        const int m = (int)(r / g.N), n = (int)(r - (long long)m * g.N);
-        const float *p = g.ws + (size_t)b * g.splits * per + r;
-        float a = 0.f;
-        for (int s = 0; s < g.splits; ++s) a += p[(size_t)s * per];
-        if (g.bias) a += g.bias[(size_t)b * g.bias_bs + n];
-        if (g.act == 1) a = fmaxf(a, 0.f);
-        g.C[(size_t)b * g.c_bs + (size_t)m * g.ldc + n] = a;
+    const int kb_total = g.kblocks * g.kbatches;
+    const long long t = blockIdx.x;
+    const long long w0 = t * kb_total, w1 = w0 + kb_total;
+    const int c_first = (int)(w0 / g.per_cta), c_last = (int)((w1 - 1) / g.per_cta);
+    if (c_first == c_last) return;                                    // whole tile: written by the GEMM epilogue
+    int u = (int)t;
+    const int tn = u % g.tiles_n; u /= g.tiles_n;
+    const int tm = u % g.tiles_m, b = u / g.tiles_m;
+    const int bn4 = g.bn >> 2;
+    const float *bias = g.bias ? g.bias + (size_t)b * g.bias_bs : nullptr;
+    const bool cvec = (g.ldc % 4 == 0) && (g.c_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+    const int first_slot = 2 * c_first + ((long long)c_first * g.per_cta < w0 ? 1 : 0);
+    for (int i = threadIdx.x; i < FIX_ROWS * bn4; i += blockDim.x) {
+        const int r = blockIdx.y * FIX_ROWS + i / bn4, c = (i % bn4) << 2;
+        const int row = tm * BM + r, col = tn * g.bn + c;
+        if (row >= g.M || col >= g.N) continue;
+        const size_t off = (size_t)r * g.bn + c, slot_stride = (size_t)BM * g.bn;
+        float4 a = *reinterpret_cast<const float4 *>(g.ws + first_slot * slot_stride + off);
+#pragma unroll 4
+        for (int cta = c_first + 1; cta <= c_last; ++cta) {          // every later CTA reaches this tile as its first segment
+            const float4 v = *reinterpret_cast<const float4 *>(g.ws + (size_t)(2 * cta) * slot_stride + off);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        float o[4] = {a.x, a.y, a.z, a.w};
+        float *dst = g.C + (size_t)b * g.c_bs + (size_t)row * g.ldc + col;
+        const float *mm = g.mul ? g.mul + (size_t)(row % g.mul_rows) * g.ld_mul + col : nullptr;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (col + k < g.N) {
+                float x = o[k];
+                if (bias) x += bias[col + k];
+                if (g.act == 1) x = fmaxf(x, 0.f);
+                if (mm) x *= mm[k];
+                o[k] = x;
+            }
+        }
+        if (cvec && col + 3 < g.N) *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (col + k < g.N) dst[k] = o[k];
+        }
     }
 }
 
@@ -425,27 +544,41 @@ int make_map(CUtensorMap *map, const float *ptr, int major, long long rows, long
     return r == CUDA_SUCCESS ? PB_OK : PB_E_ARG;
 }
 
+// output tile map: row-major [rows][cols] (row stride ld floats) x nbatch, 32 x 32 boxes, 128-byte swizzle
+int make_out_map(CUtensorMap *map, float *ptr, long long rows, long long cols, long long ld, long long bs, long long nbatch)
+{
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return PB_E_UNSUPPORTED;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(nbatch > 0 ? nbatch : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)((nbatch > 1 && bs > 0) ? bs : rows * ld) * 4};
+    cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PB_OK : PB_E_ARG;
+}
+
 template <int BN, int A_MN, int B_MN>
-int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &g, int grid, void *stream)
+int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, const TcParams &g, int grid, void *stream)
 {
     static bool attr_set = false;
-    const int smem = SMEM_BUDGET / (2 * (BM + BN) * BK * 4) * (2 * (BM + BN) * BK * 4) + 1024;
+    const int smem = SMEM_BUDGET / (2 * (BM + BN) * BK * 4) * (2 * (BM + BN) * BK * 4) + 32768 + 1024;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    PB_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN>), grid, NUM_THREADS, smem, stream, ta, tb, g);
+    PB_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN>), grid, NUM_THREADS, smem, stream, ta, tb, tc, g);
     return PB_OK;
 }
 
 template <int BN>
-int launch_bn(int a_mn, int b_mn, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &g, int grid, void *stream)
+int launch_bn(int a_mn, int b_mn, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, const TcParams &g,
+              int grid, void *stream)
 {
-    if (!a_mn && !b_mn) return launch_cfg<BN, 0, 0>(ta, tb, g, grid, stream);
-    if (!a_mn && b_mn) return launch_cfg<BN, 0, 1>(ta, tb, g, grid, stream);
-    if (a_mn && b_mn) return launch_cfg<BN, 1, 1>(ta, tb, g, grid, stream);
-    return launch_cfg<BN, 1, 0>(ta, tb, g, grid, stream);
+    if (!a_mn && !b_mn) return launch_cfg<BN, 0, 0>(ta, tb, tc, g, grid, stream);
+    if (!a_mn && b_mn) return launch_cfg<BN, 0, 1>(ta, tb, tc, g, grid, stream);
+    if (a_mn && b_mn) return launch_cfg<BN, 1, 1>(ta, tb, tc, g, grid, stream);
+    return launch_cfg<BN, 1, 0>(ta, tb, tc, g, grid, stream);
 }
 
 // modelled cost (SM clocks) of one K block and one epilogue at tile width bn: the MMA time and the shared-memory
@@ -471,10 +604,12 @@ int pb_tc_gemm(int batch, int kbatches, int M, int N, int K,
                const float *A, int a_major, long long lda, long long a_bs,
                const float *B, int b_major, long long ldb, long long b_bs,
                const float *bias, long long bias_bs, int act,
+               const float *mul, int mul_rows, long long ld_mul,
                float *C, long long ldc, long long c_bs,
                float *workspace, long long workspace_floats, int split_mode, void *stream)
 {
     if (batch <= 0 || kbatches <= 0 || !A || !B || !C || (act != 0 && act != 1)) return PB_E_ARG;
+    if (mul && (mul_rows <= 0 || ld_mul < N)) return PB_E_ARG;
     if (kbatches > 1 && batch != 1) return PB_E_ARG;
     if (!pb_tc_gemm_supported(M, N, K, lda, ldb, ldc)) return PB_E_UNSUPPORTED;
     if (split_mode != 0 && split_mode != 1) return PB_E_ARG;
@@ -489,31 +624,41 @@ int pb_tc_gemm(int batch, int kbatches, int M, int N, int K,
     g.a_batched = a_bs != 0; g.b_batched = b_bs != 0;
     g.tiles_m = (M + BM - 1) / BM;
     g.act = act; g.split_mode = split_mode;
+    g.mul = mul; g.mul_rows = mul ? mul_rows : 1; g.ld_mul = (int)ld_mul;
     const int kb_total = g.kblocks * kbatches;
 
-    // tile width and split-K factor: minimise modelled waves x (K blocks x clocks + epilogue) + split-K reduction
-    int best_bn = 64, best_s = 1;
+    // tile width and schedule: whole tiles per CTA (data-parallel waves) or equal K-block ranges per CTA
+    // (stream-K: no wave quantisation, but cut tiles pay a partial-tile round trip and the fix-up launch)
+    int best_bn = 64;
+    bool best_sk = false;
     double best = 1e300;
     const int bns[3] = {256, 128, 64};
     for (int bi = 0; bi < 3; ++bi) {
         const int bn = bns[bi];
         if (bn > 64 && bn / 2 >= N) continue;                          // tile twice as wide as the matrix
         const long long tiles = (long long)batch * g.tiles_m * ((N + bn - 1) / bn);
-        for (int s = 1; s <= 16 && s <= kb_total; ++s) {
-            const int per = (kb_total + s - 1) / s;
-            const int s_eff = (kb_total + per - 1) / per;
-            if (s_eff != s) continue;
-            if (s > 1 && (!workspace || (long long)batch * s * M * N > workspace_floats)) continue;
-            const long long units = tiles * s;
-            const long long waves = (units + sms - 1) / sms;
-            double cost = (double)waves * (per * kb_clocks(bn) + 22.0 * bn + 1500.0);
-            if (s > 1) cost += (double)(s + 1) * batch * M * N * 4.0 / 3000.0 + 4000.0;
-            if (cost < best) { best = cost; best_bn = bn; best_s = s; }
-        }
+        const double t_epi = 12.0 * bn + 1500.0;
+        const double dp = (double)((tiles + sms - 1) / sms) * (kb_total * kb_clocks(bn) + t_epi);
+        if (dp < best) { best = dp; best_bn = bn; best_sk = false; }
+        const double work = (double)tiles * kb_total;
+        const double ctas = work / 4 < sms ? (work + 3) / 4 : sms;
+        const bool ws_ok = workspace && 2 * (long long)ctas * BM * bn <= workspace_floats;
+        const double sk = work / ctas * kb_clocks(bn) + (tiles / ctas + 1.0) * t_epi + 2.0 * bn * BM * 4 / 48.0 + 14000.0;
+        if (ws_ok && sk < best) { best = sk; best_bn = bn; best_sk = true; }
     }
+    g.bn = best_bn;
     g.tiles_n = (N + best_bn - 1) / best_bn;
-    g.splits = best_s;
-    g.kb_per_split = (kb_total + best_s - 1) / best_s;
+    const long long tiles = (long long)batch * g.tiles_m * g.tiles_n;
+    g.work = tiles * kb_total;
+    long long grid;
+    if (best_sk) {
+        grid = g.work / 4 < sms ? (g.work + 3) / 4 : sms;
+        g.per_cta = (g.work + grid - 1) / grid;
+    } else {
+        grid = tiles < sms ? tiles : sms;
+        g.per_cta = ((tiles + grid - 1) / grid) * kb_total;
+    }
+    grid = (g.work + g.per_cta - 1) / g.per_cta;
 
     CUtensorMap ta, tb;
     const long long nb = kbatches > 1 ? kbatches : batch;
@@ -521,18 +666,20 @@ int pb_tc_gemm(int batch, int kbatches, int M, int N, int K,
     if (rc != PB_OK) return rc;
     rc = make_map(&tb, B, b_major, N, K, ldb, b_bs, g.b_batched ? nb : 1, best_bn);
     if (rc != PB_OK) return rc;
+    CUtensorMap tc = ta;                                               // placeholder when the direct-store epilogue runs
+    if ((ldc % 4) == 0 && (c_bs % 4) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+        rc = make_out_map(&tc, C, M, N, ldc, c_bs, batch);
+        if (rc != PB_OK) return rc;
+        g.tma_store = 1;
+    }
 
-    const long long units = (long long)batch * g.tiles_m * g.tiles_n * g.splits;
-    const int grid = (int)(units < sms ? units : sms);
-    if (best_bn == 256) rc = launch_bn<256>(a_major, b_major, ta, tb, g, grid, stream);
-    else if (best_bn == 128) rc = launch_bn<128>(a_major, b_major, ta, tb, g, grid, stream);
-    else rc = launch_bn<64>(a_major, b_major, ta, tb, g, grid, stream);
+    if (best_bn == 256) rc = launch_bn<256>(a_major, b_major, ta, tb, tc, g, (int)grid, stream);
+    else if (best_bn == 128) rc = launch_bn<128>(a_major, b_major, ta, tb, tc, g, (int)grid, stream);
+    else rc = launch_bn<64>(a_major, b_major, ta, tb, tc, g, (int)grid, stream);
     if (rc != PB_OK) return rc;
-    if (g.splits > 1) {
-        const long long total = (long long)batch * M * N;
-        long long blocks = (total + 255) / 256;
-        if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
-        PB_LAUNCH(tc_splitk_reduce_kernel, (unsigned)blocks, 256, 0, stream, g);
+    if ((g.per_cta % kb_total) != 0) {                                 // some tile is cut
+        dim3 fgrid((unsigned)tiles, BM / FIX_ROWS);
+        PB_LAUNCH(tc_streamk_fixup_kernel, fgrid, 256, 0, stream, g);
     }
     return PB_OK;
 }
@@ -546,7 +693,7 @@ int pb_linear_fwd_tc_supported(int M, int N, int J)
 int pb_linear_fwd_tc(int K, int M, int N, int J, const float *X, long long x_head_stride, const float *W,
                      const float *b, int act, float *Y, void *stream)
 {
-    return pb_tc_gemm(K, 1, M, N, J, X, 0, J, x_head_stride, W, 0, J, (long long)N * J, b, N, act, Y, N,
+    return pb_tc_gemm(K, 1, M, N, J, X, 0, J, x_head_stride, W, 0, J, (long long)N * J, b, N, act, nullptr, 0, 0, Y, N,
                       (long long)M * N, nullptr, 0, 0, stream);
 }
 

@@ -67,7 +67,7 @@ if __name__ == "__main__" and "--tc" not in sys.argv:
 def tc_bench():
     """tcgen05 3xTF32 GEMMs (forward, input gradient, weight gradient) vs the library SGEMM at the IQN / ensemble
     shapes of configs[0] and configs[4]."""
-    shapes = [(1, 2048, 256, 1024), (1, 2048, 1024, 64), (1, 32768, 512, 3136), (1, 32768, 3136, 64), (10, 512, 512, 3136),
+    shapes = [(1, 256, 256, 1024), (1, 512, 256, 1024), (1, 2048, 256, 1024), (1, 2048, 1024, 64), (1, 32768, 512, 3136), (1, 32768, 3136, 64), (10, 512, 512, 3136),
               (1, 8192, 1024, 1024)]
     for (K, M, N, J) in shapes:
         x = torch.randn(K, M, J, device=dev)

@@ -346,6 +346,23 @@ def test_tc_gemm_matches_fp64(batch, kbatches, M, N, K, a_major, b_major, act, s
     assert rel_err(got.numpy(), ref.numpy()) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K,rows", [(2048, 1024, 64, 64), (640, 328, 64, 10), (384, 18, 512, 384)])
+def test_tc_gemm_fused_multiplier_and_unaligned_output(M, N, K, rows):
+    """Epilogue fusion of iqn_model.py:70-71: out = relu(A B^T + bias) * x[row % rows] (x broadcast over the
+    quantile-major rows).  N = 18 (row stride not 16-byte aligned) exercises the direct-store epilogue."""
+    from prism_b200.agents import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a, b = torch.randn(1, M, K, generator=g), torch.randn(1, N, K, generator=g) / K ** 0.5
+    bias, x = torch.randn(1, N, generator=g), torch.randn(rows, N, generator=g)
+    out = torch.full((1, M, N), float("nan"), device=DEV)
+    ops.tc_gemm(out, a.to(DEV), 0, K, M * K, b.to(DEV), 0, K, N * K, 1, M, N, K, bias=bias.to(DEV), bias_bs=N, act=1,
+                mul=x.to(DEV))
+    torch.cuda.synchronize()
+    ref = torch.relu(torch.bmm(a.double(), b.double().transpose(1, 2)) + bias.double().unsqueeze(1))
+    ref = ref * x.double().repeat(M // rows, 1).unsqueeze(0)
+    assert rel_err(out.cpu().numpy(), ref.numpy()) < 2e-5
+
+
 @pytest.mark.parametrize("K,M,N,J,shared,relu", [
     (1, 2048, 256, 1024, True, True), (1, 2048, 1024, 64, True, True), (1, 300, 64, 32, True, False),
     (10, 512, 512, 3136, False, True), (2, 1000, 128, 96, True, False)])
@@ -374,3 +391,43 @@ def test_tensor_core_linear_matches_fp64(K, M, N, J, shared, relu):
     assert rel_err(wd.grad.cpu().numpy(), wr.grad.numpy()) < 1e-4
     assert rel_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 1e-4
     assert rel_err(bd.grad.cpu().numpy(), br.grad.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("n,B,F_,J", [(8, 64, 1024, 64), (7, 48, 3136, 64)])
+def test_phi_times_x_matches_fp64(n, B, F_, J):
+    """relu(basis W^T + b) (.) x with x broadcast over quantile-major rows (iqn_model.py:70-71, 89-93): fused
+    GEMM epilogue forward, fused element-wise backward + tensor-core weight gradient, against fp64 autograd."""
+    import torch.nn as nn
+    from prism_b200.agents import ops
+    g = torch.Generator().manual_seed(n * 100 + B)
+    basis = torch.randn(n * B, J, generator=g)
+    w, b = torch.randn(F_, J, generator=g) / J ** 0.5, torch.randn(F_, generator=g) * 0.1
+    x = torch.relu(torch.randn(B, F_, generator=g))               # conv embedding after ReLU: exact zeros
+    gh = torch.randn(n * B, F_, generator=g)
+    seq = nn.Sequential(nn.Linear(J, F_), nn.ReLU()).to(DEV)
+    with torch.no_grad():
+        seq[0].weight.copy_(w)
+        seq[0].bias.copy_(b)
+    xd = x.to(DEV).requires_grad_(True)
+    old = ops.TC_MIN_FLOPS
+    ops.TC_MIN_FLOPS = 0.0
+    try:
+        h = ops.phi_times_x(seq, basis.to(DEV), xd, n)
+        assert h.grad_fn is not None and "PhiTimesX" in type(h.grad_fn).__name__
+        h.backward(gh.to(DEV))
+        with torch.no_grad():
+            h_nograd = ops.phi_times_x(seq, basis.to(DEV), xd, n)
+    finally:
+        ops.TC_MIN_FLOPS = old
+    torch.cuda.synchronize()
+    wr, br, xr = w.double().requires_grad_(True), b.double().requires_grad_(True), x.double().requires_grad_(True)
+    pre = basis.double() @ wr.t() + br
+    # the ReLU gate is discontinuous: judge with the gate the kernel's fp32 pre-activation produced
+    gate = (torch.relu(basis @ w.t() + b) > 0).double()
+    href = (pre * gate).view(n, B, F_) * xr.unsqueeze(0)
+    href.view(n * B, F_).backward(gh.double())
+    assert rel_err(h.detach().cpu().numpy(), href.detach().view(n * B, F_).numpy()) < 2e-5
+    assert torch.equal(h_nograd, h.detach())
+    assert rel_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 1e-4
+    assert rel_err(seq[0].weight.grad.cpu().numpy(), wr.grad.numpy()) < 1e-4
+    assert rel_err(seq[0].bias.grad.cpu().numpy(), br.grad.numpy()) < 1e-4
