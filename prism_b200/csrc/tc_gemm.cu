@@ -9,7 +9,7 @@
 // into a TF32 "hi" part and a TF32 "lo" residual and each product is issued as three tensor-core MMAs
 // lo.hi + hi.lo + hi.hi accumulating in fp32 in TENSOR MEMORY -- error ~1e-6 at a third of the TF32 rate.
 //
-// Structure: persistent, warp-specialised, one CTA per SM, 320 threads:
+// Structure: persistent, warp-specialised, one CTA per SM, 448 threads:
 //   warp 0      TMA producer: cp.async.bulk.tensor (128-byte swizzle) of the raw fp32 A (128 x 32) and
 //               B (BN x 32) tiles into a ring of shared-memory stages, completion on mbarriers;
 //   warps 2-5   splitters: one element-wise pass over the landed stage, lo = x - tf32(x) written to a twin
@@ -18,8 +18,11 @@
 //               rewrites it in place with the round-to-nearest TF32 value instead);
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M 128, N BN, K 8) from
 //               shared-memory descriptors, 12 per stage; tcgen05.commit frees the stage / publishes the tile;
-//   warps 6-9   epilogue: tcgen05.ld 32x32b of the finished accumulator (double-buffered in TMEM, so the next
-//               tile's MMAs overlap), + bias, ReLU, store (or a split-K partial to the workspace).
+//   warps 6-13  epilogue: tcgen05.ld 32x32b of the finished accumulator (double-buffered in TMEM for BN <= 128, so
+//               the next tile's MMAs overlap), + bias, ReLU, optional row-broadcast multiplier, 128-byte-swizzled
+//               32 x 32 tile in shared memory, cp.async.bulk.tensor store (or a raw stream-K partial tile).
+// Scheduling is stream-K: equal contiguous ranges of (tile, K block) work per CTA; tiles cut by a range
+// boundary leave partial tiles in a bounded workspace and a fix-up kernel sums them in a fixed order.
 // Operands may be K-major (row-major M x K) or MN-major (row-major K x M, i.e. the transposed view), which
 // is what the backward GEMMs need (dX = dZ W, dW = dZ^T X) -- no transposed copies are ever made.
 #include "common.cuh"
@@ -29,8 +32,8 @@ namespace {
 
 using namespace pb;
 
-constexpr int BM = 128, BK = 32;
-constexpr int NUM_THREADS = 320;
+constexpr int BM = 128;           // K block (BK, template): 32 floats = one 128-byte swizzled row, or 16 = 64-byte rows
+constexpr int NUM_THREADS = 448;           // warp 0 TMA, warp 1 MMA, warps 2-5 splitters, warps 6-13 epilogue
 constexpr int SMEM_BUDGET = 200 * 1024;          // operand stages; barriers live in static shared memory
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -131,7 +134,9 @@ struct TcParams {
     int split_mode;                // 0: hi = raw word (hardware truncation); 1: hi rewritten as cvt.rna.tf32
     const float *mul;              // optional epilogue multiplier: out *= mul[(row % mul_rows) * ld_mul + col]
     int mul_rows, ld_mul;
-    int tma_store;                 // 1: epilogue stores through shared memory + cp.async.bulk.tensor (tmC)
+    int deep_epi;                  // 1: two operand stages + four store buffers per epilogue warp (short K loops)
+    int tma_store;                 // 1: epilogue through a swizzled shared-memory tile + cp.async.bulk.tensor store (tmC);
+                                   // 0: direct per-row stores (C rows not 16-byte aligned)
 };
 
 // Stream-K schedule: the (tile, K block) work items are numbered tile-major (tn fastest, then tm, then batch)
@@ -166,31 +171,38 @@ struct SegIter {
     }
 };
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int BK, int A_MN, int B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const TcParams g)
 {
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, RAW_BYTES = A_BYTES + B_BYTES;
     constexpr int STAGE_BYTES = 2 * RAW_BYTES;                       // raw (hi) | lo
-    constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
+    constexpr int MAX_STAGES = SMEM_BUDGET / STAGE_BYTES;
+    // short K loops (epilogue-bound, e.g. the 64-wide cosine basis) trade operand stages for a deeper ring of
+    // epilogue store buffers: g.deep_epi = 4 x 4 KB per epilogue warp and only two operand stages
+    constexpr bool DEEP_OK = 2 * STAGE_BYTES + 65536 <= MAX_STAGES * STAGE_BYTES + 32768;
+    const bool deep = DEEP_OK && g.deep_epi;
+    const int STAGES = deep ? 2 : MAX_STAGES;
+    const int EPI_BUFS = deep ? 2 : 1;                               // 4 KB store buffers per epilogue warp (8 warps)
     constexpr int ACC = (2 * BN <= 512) ? 2 : 1;
     constexpr uint32_t TMEM_COLS = (uint32_t)(ACC * BN);
-    static_assert(STAGES >= 2, "pipeline needs two stages");
+    static_assert(MAX_STAGES >= 2, "pipeline needs two stages");
     static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32 && TMEM_COLS <= 512, "TMEM columns");
 
     extern __shared__ uint8_t smem_dyn[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    uint8_t *staging = smem + STAGES * STAGE_BYTES;                  // 4 epilogue warps x 2 x (32 rows x 128 B)
-    __shared__ uint64_t bar_full[STAGES], bar_ready[STAGES], bar_empty[STAGES];
+    uint8_t *staging = smem + STAGES * STAGE_BYTES;                  // 8 epilogue warps x EPI_BUFS x (32 rows x 128 B)
+    __shared__ uint64_t bar_full[MAX_STAGES], bar_ready[MAX_STAGES], bar_empty[MAX_STAGES];
     __shared__ uint64_t bar_acc_full[ACC], bar_acc_empty[ACC];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float bias_s[BN];
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
     if (t == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_ready[s], 4); mbar_init(&bar_empty[s], 1); }
-        for (int a = 0; a < ACC; ++a) { mbar_init(&bar_acc_full[a], 1); mbar_init(&bar_acc_empty[a], 4); }
+        for (int a = 0; a < ACC; ++a) { mbar_init(&bar_acc_full[a], 1); mbar_init(&bar_acc_empty[a], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -224,13 +236,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_expect_tx(&bar_full[s], RAW_BYTES);
                     if (A_MN) {
 #pragma unroll
-                        for (int gI = 0; gI < BM / 32; ++gI) tma_load_3d(a_dst + gI * 4096, &tmA, &bar_full[s], m0 + gI * 32, k0, za);
+                        for (int gI = 0; gI < BM / 32; ++gI) tma_load_3d(a_dst + gI * (BK * 128), &tmA, &bar_full[s], m0 + gI * 32, k0, za);
                     } else {
                         tma_load_3d(a_dst, &tmA, &bar_full[s], k0, m0, za);
                     }
                     if (B_MN) {
 #pragma unroll
-                        for (int gI = 0; gI < BN / 32; ++gI) tma_load_3d(b_dst + gI * 4096, &tmB, &bar_full[s], n0 + gI * 32, k0, zbb);
+                        for (int gI = 0; gI < BN / 32; ++gI) tma_load_3d(b_dst + gI * (BK * 128), &tmB, &bar_full[s], n0 + gI * 32, k0, zbb);
                     } else {
                         tma_load_3d(b_dst, &tmB, &bar_full[s], k0, n0, zbb);
                     }
@@ -241,9 +253,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
-            constexpr uint32_t A_LBO = A_MN ? 4096 : 16, B_LBO = B_MN ? 4096 : 16;
-            constexpr uint32_t A_SBO = A_MN ? 512 : 1024, B_SBO = B_MN ? 512 : 1024;
-            constexpr uint32_t A_LAY = A_MN ? 1 : 2, B_LAY = B_MN ? 1 : 2;
+            // K-major rows are BK * 4 bytes: SWIZZLE_128B (layout 2, 8-row group = 1024 B) for BK = 32,
+            // SWIZZLE_64B (layout 4, 8-row group = 512 B) for BK = 16
+            constexpr uint32_t K_LAY = BK == 32 ? 2 : 4, K_SBO = BK * 4 * 8;
+            constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, B_LBO = B_MN ? BK * 128 : 16;
+            constexpr uint32_t A_SBO = A_MN ? 512 : K_SBO, B_SBO = B_MN ? 512 : K_SBO;
+            constexpr uint32_t A_LAY = A_MN ? 1 : K_LAY, B_LAY = B_MN ? 1 : K_LAY;
             constexpr uint32_t A_KSTEP = A_MN ? 1024 : 32, B_KSTEP = B_MN ? 1024 : 32;   // bytes per K = 8
             uint32_t it = 0, ui = 0;
             SegIter segs(g);
@@ -289,15 +304,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float4 *raw = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
                 float4 *lo = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + RAW_BYTES);
                 constexpr int N4 = RAW_BYTES / 16, PER = N4 / 128;
-                static_assert(N4 % 128 == 0 && PER % 4 == 0, "split loop shape");
+                static_assert(N4 % 128 == 0 && PER % 2 == 0, "split loop shape");
                 if (g.split_mode == 0) {
+                    constexpr int UN = (PER % 4 == 0) ? 4 : 2;
 #pragma unroll
-                    for (int j0 = 0; j0 < PER; j0 += 4) {
-                        float4 v[4];
+                    for (int j0 = 0; j0 < PER; j0 += UN) {
+                        float4 v[UN];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = raw[st + (j0 + j) * 128];
+                        for (int j = 0; j < UN; ++j) v[j] = raw[st + (j0 + j) * 128];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int j = 0; j < UN; ++j) {
                             float4 l;
                             l.x = v[j].x - __uint_as_float(__float_as_uint(v[j].x) & 0xFFFFE000u);
                             l.y = v[j].y - __uint_as_float(__float_as_uint(v[j].y) & 0xFFFFE000u);
@@ -326,30 +342,69 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 6-9)
-        const int q = warp & 3;                                       // TMEM lane quarter this warp may access
+        // ------------------------------------------------------------------ epilogue (warps 6-13)
+        // two warps per TMEM lane quarter (a warp may only touch lanes 32 * (warp % 4) ..): one takes the even
+        // 32-column chunks of the tile, the other the odd ones -- twice the loads / stores in flight
+        const int q = warp & 3;
+        const int half = (warp - 6) >> 2;
+        const int et = t - 192;                                       // 0..255 within the epilogue warps
         uint32_t ui = 0, chunk = 0;
         const bool vec_ok = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.c_bs % 4 == 0);
-        const bool bias_vec = g.bias && ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) && (g.bias_bs % 4 == 0);
         const bool mul_vec = g.mul && ((reinterpret_cast<uintptr_t>(g.mul) & 15) == 0) && (g.ld_mul % 4 == 0);
-        uint8_t *stg = staging + (warp - 6) * 8192;
+        const bool staged = g.tma_store != 0;
+        uint8_t *stg = staging + (warp - 6) * (EPI_BUFS * 4096);
         SegIter segs(g);
         Seg w;
         for (; segs.next(g, w); ++ui) {
             const int acc = ui % ACC;
-            mbar_wait(&bar_acc_full[acc], (ui / ACC) & 1);
-            tc_fence_after();
             const bool partial = !w.whole;
             const int row0 = w.tm * BM + q * 32, row = row0 + lane, n0 = w.tn * BN;
-            const float *bias = (g.bias && !partial) ? g.bias + (size_t)w.b * g.bias_bs : nullptr;
-            const float *mul = (g.mul && !partial) ? g.mul + (size_t)(row % g.mul_rows) * g.ld_mul : nullptr;
+            // the tile's bias row goes to shared memory while the MMAs are still running (named barriers among the
+            // four epilogue warps: everyone is done with the previous tile's row / the new row is published)
+            float *bias_t = bias_s;
+            const bool has_bias = g.bias && !partial;
+            if (g.bias) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (has_bias) {
+                    const float *bsrc = g.bias + (size_t)w.b * g.bias_bs;
+                    for (int c = et; c < BN; c += 256) bias_t[c] = (n0 + c < g.N) ? __ldg(bsrc + n0 + c) : 0.f;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            mbar_wait(&bar_acc_full[acc], (ui / ACC) & 1);
+            tc_fence_after();
             const bool relu = g.act == 1 && !partial;
+            const bool use_mul = g.mul && !partial;
             float *crow = g.C + (size_t)w.b * g.c_bs + (size_t)row * g.ldc;
             float4 *prow = reinterpret_cast<float4 *>(g.ws + ((size_t)w.slot * BM + q * 32 + lane) * BN);
+            // multiplier tile of one chunk, COALESCED (lane l: 16-byte chunk (l & 7) of rows 4i + (l >> 3)); requested one
+            // chunk ahead so that its latency hides behind the previous chunk's TMEM load and stores
+            float4 mreg[8], mnext[8];
+            auto load_mul = [&](float4 (&m)[8], int c0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = 4 * i + (lane >> 3), col = c0 + (lane & 7) * 4;
+                    const float *mrow = g.mul + (size_t)((row0 + rr) % g.mul_rows) * g.ld_mul;
+                    if (mul_vec && col + 3 < g.N) m[i] = __ldg(reinterpret_cast<const float4 *>(mrow + col));
+                    else {
+                        m[i].x = col < g.N ? __ldg(mrow + col) : 0.f;
+                        m[i].y = col + 1 < g.N ? __ldg(mrow + col + 1) : 0.f;
+                        m[i].z = col + 2 < g.N ? __ldg(mrow + col + 2) : 0.f;
+                        m[i].w = col + 3 < g.N ? __ldg(mrow + col + 3) : 0.f;
+                    }
+                }
+            };
+            const bool pre_mul = use_mul && staged;
+            if (pre_mul && n0 + half * 32 < g.N) load_mul(mnext, n0 + half * 32);
 #pragma unroll 1
-            for (int cc = 0; cc < BN / 32; ++cc) {
+            for (int cc = half; cc < BN / 32; cc += 2) {
                 const int c0 = n0 + cc * 32;
                 if (c0 >= g.N) break;                                 // warp-uniform (fix-up never reads these columns)
+                if (pre_mul) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) mreg[i] = mnext[i];
+                    if (cc + 2 < BN / 32 && c0 + 64 < g.N) load_mul(mnext, c0 + 64);
+                }
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cc * 32);
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
@@ -367,48 +422,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 32; j += 4)
                         prow[(cc * 32 + j) >> 2] = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                } else if (g.tma_store) {
-                    // bias / ReLU / multiplier in registers, 128-byte-swizzled 32 x 32 tile in shared memory,
-                    // one bulk tensor store per tile (full 128-byte lines; TMA clips rows >= M and columns >= N)
-                    uint8_t *buf = stg + (chunk & 1) * 4096;
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                } else if (staged) {
+                    // bias / ReLU in registers -> 128-byte-swizzled 32 x 32 tile in shared memory -> multiplier pass ->
+                    // one bulk tensor store (full 128-byte lines; TMA clips rows >= M and columns >= N)
+                    uint8_t *buf = stg + (chunk % EPI_BUFS) * 4096;
+                    if (lane == 0) {
+                        if (deep) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
                     __syncwarp();
-                    const bool full = c0 + 32 <= g.N;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                                __uint_as_float(r[j + 3]));
-                        const int col = c0 + j;
-                        if (bias) {
-                            if (bias_vec && full) {
-                                const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col));
-                                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-                            } else {
-                                if (col < g.N) v.x += __ldg(bias + col);
-                                if (col + 1 < g.N) v.y += __ldg(bias + col + 1);
-                                if (col + 2 < g.N) v.z += __ldg(bias + col + 2);
-                                if (col + 3 < g.N) v.w += __ldg(bias + col + 3);
-                            }
+                        if (has_bias) {
+                            const float4 bb = *reinterpret_cast<const float4 *>(bias_t + cc * 32 + j);   // broadcast read
+                            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
                         }
                         if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                        if (mul) {
-                            if (mul_vec && full) {
-                                const float4 mm = __ldg(reinterpret_cast<const float4 *>(mul + col));
-                                v.x *= mm.x; v.y *= mm.y; v.z *= mm.z; v.w *= mm.w;
-                            } else {
-                                if (col < g.N) v.x *= __ldg(mul + col);
-                                if (col + 1 < g.N) v.y *= __ldg(mul + col + 1);
-                                if (col + 2 < g.N) v.z *= __ldg(mul + col + 2);
-                                if (col + 3 < g.N) v.w *= __ldg(mul + col + 3);
-                            }
-                        }
                         *reinterpret_cast<float4 *>(buf + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = v;
+                    }
+                    if (use_mul) {
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = 4 * i + (lane >> 3), ch = lane & 7;
+                            float4 *cell = reinterpret_cast<float4 *>(buf + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                            float4 v = *cell;
+                            v.x *= mreg[i].x; v.y *= mreg[i].y; v.z *= mreg[i].z; v.w *= mreg[i].w;
+                            *cell = v;
+                        }
                     }
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) tma_store_3d(&tmC, smem_u32(buf), c0, row0, w.b);
                     ++chunk;
                 } else if (row < g.M) {
+                    // C rows are not 16-byte aligned (e.g. 18 actions): per-row stores
+                    const float *mul = use_mul ? g.mul + (size_t)(row % g.mul_rows) * g.ld_mul : nullptr;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const int col = c0 + j;
@@ -419,7 +470,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int i = 0; i < 4; ++i) {
                             float x = e[i];
                             if (col + i < g.N) {
-                                if (bias) x += __ldg(bias + col + i);
+                                if (has_bias) x += bias_t[cc * 32 + j + i];
                                 if (relu) x = fmaxf(x, 0.f);
                                 if (mul) x *= __ldg(mul + col + i);
                             }
@@ -439,7 +490,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_acc_empty[acc]);
         }
-        if (g.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (staged && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -521,7 +572,7 @@ EncodeTiledFn encode_fn()
 // operand with logical shape rows x kdim (x nbatch).  major 0: stored row-major [rows][kdim] (ld floats);
 // major 1: stored row-major [kdim][rows] (ld floats).  Box = 32 floats along the contiguous dimension.
 int make_map(CUtensorMap *map, const float *ptr, int major, long long rows, long long kdim, long long ld, long long bs,
-             long long nbatch, int tile_rows)
+             long long nbatch, int tile_rows, int bk)
 {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return PB_E_UNSUPPORTED;
@@ -534,11 +585,12 @@ int make_map(CUtensorMap *map, const float *ptr, int major, long long rows, long
     dims[2] = (cuuint64_t)(nbatch > 0 ? nbatch : 1);
     strides[0] = (cuuint64_t)ld * 4;
     strides[1] = (cuuint64_t)((nbatch > 1 && bs > 0) ? bs : outer_rows * ld) * 4;
-    box[0] = 32;
-    box[1] = (cuuint32_t)(major ? BK : tile_rows);
+    box[0] = (cuuint32_t)(major ? 32 : bk);
+    box[1] = (cuuint32_t)(major ? bk : tile_rows);
     box[2] = 1;
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? PB_OK : PB_E_ARG;
@@ -557,33 +609,45 @@ int make_out_map(CUtensorMap *map, float *ptr, long long rows, long long cols, l
     return r == CUDA_SUCCESS ? PB_OK : PB_E_ARG;
 }
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int BK, int A_MN, int B_MN>
 int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, const TcParams &g, int grid, void *stream)
 {
     static bool attr_set = false;
     const int smem = SMEM_BUDGET / (2 * (BM + BN) * BK * 4) * (2 * (BM + BN) * BK * 4) + 32768 + 1024;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, BK, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    PB_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN>), grid, NUM_THREADS, smem, stream, ta, tb, tc, g);
+    PB_LAUNCH((tc_gemm_kernel<BN, BK, A_MN, B_MN>), grid, NUM_THREADS, smem, stream, ta, tb, tc, g);
     return PB_OK;
 }
 
-template <int BN>
+template <int BN, int BK>
 int launch_bn(int a_mn, int b_mn, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, const TcParams &g,
               int grid, void *stream)
 {
-    if (!a_mn && !b_mn) return launch_cfg<BN, 0, 0>(ta, tb, tc, g, grid, stream);
-    if (!a_mn && b_mn) return launch_cfg<BN, 0, 1>(ta, tb, tc, g, grid, stream);
-    if (a_mn && b_mn) return launch_cfg<BN, 1, 1>(ta, tb, tc, g, grid, stream);
-    return launch_cfg<BN, 1, 0>(ta, tb, tc, g, grid, stream);
+    if (!a_mn && !b_mn) return launch_cfg<BN, BK, 0, 0>(ta, tb, tc, g, grid, stream);
+    if (!a_mn && b_mn) return launch_cfg<BN, BK, 0, 1>(ta, tb, tc, g, grid, stream);
+    if (a_mn && b_mn) return launch_cfg<BN, BK, 1, 1>(ta, tb, tc, g, grid, stream);
+    return launch_cfg<BN, BK, 1, 0>(ta, tb, tc, g, grid, stream);
+}
+
+// K block per tile width.  PB_TC_BK=16|32 overrides (tuning runs).
+int pick_bk(int bn, int K)
+{
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("PB_TC_BK");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 16 || forced == 32) return forced;
+    return (bn == 256 && K >= 256) ? 16 : 32;    // 4 x 48 KB stages instead of 2 x 96 KB once the K loop is long
 }
 
 // modelled cost (SM clocks) of one K block and one epilogue at tile width bn: the MMA time and the shared-memory
 // traffic (12 operand reads + the split pass) whichever is larger -- see DESIGN.md section 4
-double kb_clocks(int bn)
+double kb_clocks(int bn)                       // per 32 floats of K
 {
     const double mma = 12.0 * bn / 2.0;
     const double smem = (12.0 * (4096 + bn * 32) + 2.0 * (BM + bn) * 128) / 128.0;
@@ -618,14 +682,13 @@ int pb_tc_gemm(int batch, int kbatches, int M, int N, int K,
     g.C = C; g.bias = bias; g.ws = workspace;
     g.c_bs = c_bs; g.bias_bs = bias_bs; g.ldc = (int)ldc;
     g.M = M; g.N = N;
-    g.kblocks = (K + BK - 1) / BK;
     g.kbatches = kbatches;
     g.batch = batch;
     g.a_batched = a_bs != 0; g.b_batched = b_bs != 0;
     g.tiles_m = (M + BM - 1) / BM;
     g.act = act; g.split_mode = split_mode;
     g.mul = mul; g.mul_rows = mul ? mul_rows : 1; g.ld_mul = (int)ld_mul;
-    const int kb_total = g.kblocks * kbatches;
+    const int kb32 = ((K + 31) / 32) * kbatches;                       // cost model works in 32-float K blocks
 
     // tile width and schedule: whole tiles per CTA (data-parallel waves) or equal K-block ranges per CTA
     // (stream-K: no wave quantisation, but cut tiles pay a partial-tile round trip and the fix-up launch)
@@ -637,22 +700,30 @@ int pb_tc_gemm(int batch, int kbatches, int M, int N, int K,
         const int bn = bns[bi];
         if (bn > 64 && bn / 2 >= N) continue;                          // tile twice as wide as the matrix
         const long long tiles = (long long)batch * g.tiles_m * ((N + bn - 1) / bn);
-        const double t_epi = 12.0 * bn + 1500.0;
-        const double dp = (double)((tiles + sms - 1) / sms) * (kb_total * kb_clocks(bn) + t_epi);
+        // epilogue ~18 clocks per column of the tile; it overlaps the next tile's K loop only when the two
+        // accumulators fit in TMEM (bn <= 128)
+        const double t_main = kb32 * kb_clocks(bn), t_drain = 18.0 * bn + 600.0;
+        const double t_epi = bn > 128 ? t_drain : (t_drain > t_main ? t_drain - t_main : 0.0) + 500.0;
+        const double dp = (double)((tiles + sms - 1) / sms) * (t_main + t_epi);
         if (dp < best) { best = dp; best_bn = bn; best_sk = false; }
-        const double work = (double)tiles * kb_total;
+        const double work = (double)tiles * kb32;
         const double ctas = work / 4 < sms ? (work + 3) / 4 : sms;
         const bool ws_ok = workspace && 2 * (long long)ctas * BM * bn <= workspace_floats;
         const double sk = work / ctas * kb_clocks(bn) + (tiles / ctas + 1.0) * t_epi + 2.0 * bn * BM * 4 / 48.0 + 14000.0;
         if (ws_ok && sk < best) { best = sk; best_bn = bn; best_sk = true; }
     }
     g.bn = best_bn;
+    const int bk = pick_bk(best_bn, K);
+    g.kblocks = (K + bk - 1) / bk;
+    const int kb_total = g.kblocks * kbatches;
     g.tiles_n = (N + best_bn - 1) / best_bn;
     const long long tiles = (long long)batch * g.tiles_m * g.tiles_n;
     g.work = tiles * kb_total;
     long long grid;
+    g.deep_epi = kb_total * bk <= 256 ? 1 : 0;
     if (best_sk) {
-        grid = g.work / 4 < sms ? (g.work + 3) / 4 : sms;
+        const int min_kb = 128 / bk;                                   // at least 128 floats of K per CTA
+        grid = g.work / min_kb < sms ? (g.work + min_kb - 1) / min_kb : sms;
         g.per_cta = (g.work + grid - 1) / grid;
     } else {
         grid = tiles < sms ? tiles : sms;
@@ -662,9 +733,9 @@ int pb_tc_gemm(int batch, int kbatches, int M, int N, int K,
 
     CUtensorMap ta, tb;
     const long long nb = kbatches > 1 ? kbatches : batch;
-    int rc = make_map(&ta, A, a_major, M, K, lda, a_bs, g.a_batched ? nb : 1, BM);
+    int rc = make_map(&ta, A, a_major, M, K, lda, a_bs, g.a_batched ? nb : 1, BM, bk);
     if (rc != PB_OK) return rc;
-    rc = make_map(&tb, B, b_major, N, K, ldb, b_bs, g.b_batched ? nb : 1, best_bn);
+    rc = make_map(&tb, B, b_major, N, K, ldb, b_bs, g.b_batched ? nb : 1, best_bn, bk);
     if (rc != PB_OK) return rc;
     CUtensorMap tc = ta;                                               // placeholder when the direct-store epilogue runs
     if ((ldc % 4) == 0 && (c_bs % 4) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
@@ -673,9 +744,15 @@ int pb_tc_gemm(int batch, int kbatches, int M, int N, int K,
         g.tma_store = 1;
     }
 
-    if (best_bn == 256) rc = launch_bn<256>(a_major, b_major, ta, tb, tc, g, (int)grid, stream);
-    else if (best_bn == 128) rc = launch_bn<128>(a_major, b_major, ta, tb, tc, g, (int)grid, stream);
-    else rc = launch_bn<64>(a_major, b_major, ta, tb, tc, g, (int)grid, stream);
+    if (bk == 16) {
+        if (best_bn == 256) rc = launch_bn<256, 16>(a_major, b_major, ta, tb, tc, g, (int)grid, stream);
+        else if (best_bn == 128) rc = launch_bn<128, 16>(a_major, b_major, ta, tb, tc, g, (int)grid, stream);
+        else rc = launch_bn<64, 16>(a_major, b_major, ta, tb, tc, g, (int)grid, stream);
+    } else {
+        if (best_bn == 256) rc = launch_bn<256, 32>(a_major, b_major, ta, tb, tc, g, (int)grid, stream);
+        else if (best_bn == 128) rc = launch_bn<128, 32>(a_major, b_major, ta, tb, tc, g, (int)grid, stream);
+        else rc = launch_bn<64, 32>(a_major, b_major, ta, tb, tc, g, (int)grid, stream);
+    }
     if (rc != PB_OK) return rc;
     if ((g.per_cta % kb_total) != 0) {                                 // some tile is cut
         dim3 fgrid((unsigned)tiles, BM / FIX_ROWS);

@@ -84,6 +84,11 @@ def tc_bench():
             ("wgrad", lambda: ops.tc_gemm(dw, dz, 1, N, M * N, x, 1, J, M * J, K, N, J, M),
              lambda: torch.bmm(dz.transpose(1, 2), x)),
         ]
+        if J == 64 and K == 1:
+            emb = torch.randn(512 if M >= 512 else 64, N, device=dev)
+            q = M // emb.shape[0]
+            rows.append(("phi*x", lambda: ops.tc_gemm(y, x, 0, J, M * J, w, 0, J, N * J, K, M, N, J, bias=b, bias_bs=N, act=1, mul=emb),
+                         lambda: (torch.relu(torch.addmm(b[0], x[0], w[0].t())).view(q, emb.shape[0], N) * emb.unsqueeze(0))))
         for name, f_tc, f_lib in rows:
             with torch.no_grad():
                 t_tc = graph_time(f_tc, reps=reps)
