@@ -238,6 +238,7 @@ def kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src):
     prio = torch.rand(B, device=buf.device)
     opt = agent.optimizer
     saved_allreduce, opt.allreduce = opt.allreduce, None      # rank-0-only timing: no collective in here
+    saved_peer, opt.peer = opt.peer, None
     rows = {}
     rows["per_sample (tree_sample_kernel)"] = (time_kernel(lambda: tree.sample(B, u=u, idx_out=idx, weight_out=w), 50, torch),
                                                B * (4 * L + 24))
@@ -251,6 +252,7 @@ def kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src):
                                                   opt.numel * 4 * (2 + 1 + 2 + 2 + 2))   # pack r/w, sumsq fused, p/m/v r+w, g read
     opt.restore(snap)
     opt.allreduce = saved_allreduce
+    opt.peer = saved_peer
     out = {}
     for k, (sec, nbytes) in rows.items():
         gbs = nbytes / sec / 1e9

@@ -371,6 +371,44 @@ int pb_linear_fwd_tc(int K, int M, int N, int J, const float *X, long long x_hea
 int pb_iqn_phi_bwd(int n, int B, int F, const float *dh, const float *phi, const float *x, float *dpre, float *dx,
                    float *dbias_partial, void *stream);
 
+/* ---- data-parallel exchange over NVLink / NVSwitch peer memory (csrc/peer.cu) -----------------------
+ * Replaces, for ranks on one box, the two collectives of the sharded learner step: the all-gather of the 64-byte
+ * shard state blocks and the all-reduce of the flat gradient arena followed by clip + Adam (agent.py:73-74).
+ * Every rank allocates one block with pb_peer_alloc, exports it (pb_peer_export, a 64-byte CUDA IPC handle that
+ * the host side exchanges any way it likes), opens the other ranks' blocks (pb_peer_open) and fills a
+ * pb_peer_group with the per-rank addresses.  All calls are stream-ordered, graph-capturable and must be issued
+ * by every rank in the same order (the barriers are epoch counters in peer memory). */
+#define PB_PEER_MAX 8
+typedef struct pb_peer_group {
+    int world, rank;
+    float *grad[PB_PEER_MAX];                 /* every rank's flat gradient arena (n floats)                         */
+    float *reduced[PB_PEER_MAX];              /* every rank's reduced-gradient buffer (n floats; rank r fills slice r) */
+    unsigned long long *flags[PB_PEER_MAX];   /* every rank's signal pad: flags[dst][src] = last epoch src signalled  */
+    double *norm_parts[PB_PEER_MAX];          /* every rank's [PB_PEER_MAX] slice sums of squares                    */
+    unsigned char *state[PB_PEER_MAX];        /* every rank's gathered shard states [world][64]                      */
+    unsigned long long *epoch;                /* local barrier counter                                               */
+} pb_peer_group;
+int pb_peer_alloc(long long bytes, void **ptr);            /* cudaMalloc + zero fill; blocking                      */
+int pb_peer_free(void *ptr);
+int pb_peer_preload(void);                                  /* load the exchange kernels now (blocking)              */
+int pb_peer_export(const void *ptr, void *handle64);
+int pb_peer_open(const void *handle64, void **ptr);        /* maps a peer block, enabling peer access               */
+int pb_peer_close(void *ptr);
+int pb_peer_barrier(const pb_peer_group *g, void *stream);
+/* state64: this rank's 64-byte tree state block (pb_tree state).  On return (stream order) state[rank] of this
+ * rank holds every rank's block. */
+int pb_peer_state_allgather(const pb_peer_group *g, const void *state64, void *stream);
+long long pb_peer_slice(long long n, int world);           /* floats per rank slice (multiple of 4)                 */
+/* reduced[rank][slice rank] = sum over ranks (rank order) of grad[p][slice]; publishes the slice's sum of squares
+ * to every rank; increments *step_count (may be NULL).  Needs a pb_peer_barrier between the writers of grad and
+ * this call, and another one before pb_peer_adam.  partial_scratch: 4096 floats.  n % 4 == 0. */
+int pb_peer_reduce_scatter(const pb_peer_group *g, long long n, float *partial_scratch, long long *step_count, void *stream);
+/* clip_grad_norm_(max_grad_norm) + Adam over the local replica, reading the reduced gradient slice by slice from its
+ * owner rank.  grad_out (optional): receives the full reduced gradient. */
+int pb_peer_adam(const pb_peer_group *g, long long n, float *param, float *exp_avg, float *exp_avg_sq,
+                 const long long *step_count, float lr, float beta1, float beta2, float adam_eps, float max_grad_norm,
+                 float *norm_out, float *grad_out, void *stream);
+
 /* total_loss = mean_b(dist*w) + mean_b(q'*w);  td_b = 0.5*dist + 0.5*q' | dist | |q'|
  * (composite_model.py:135-142, agent.py:58-64) with q' = q_scale * (q - *q_offset)
  * (q_ensemble.py:92: q_loss_weight * (q_loss - theil * coef); q_offset NULL = 0).

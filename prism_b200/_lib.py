@@ -49,12 +49,23 @@ STEP_META_DTYPE = [("seq", "<i8"), ("prev_link", "<i8"), ("next_link", "<i8"), (
 
 assert C.sizeof(pb_per_state) == 64
 
+PB_PEER_MAX = 8
+
+
+class pb_peer_group(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int),
+                ("grad", C.c_void_p * PB_PEER_MAX), ("reduced", C.c_void_p * PB_PEER_MAX),
+                ("flags", C.c_void_p * PB_PEER_MAX), ("norm_parts", C.c_void_p * PB_PEER_MAX),
+                ("state", C.c_void_p * PB_PEER_MAX), ("epoch", C.c_void_p)]
+
+
 _P = C.c_void_p
 _LL = C.c_longlong
 _I = C.c_int
 _F = C.c_float
 _TREE = C.POINTER(pb_tree)
 _STORE = C.POINTER(pb_store)
+_PEER = C.POINTER(pb_peer_group)
 
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
 SIGNATURES = {
@@ -88,6 +99,17 @@ SIGNATURES = {
     "pb_conv3x3_relu_bwd_groups": [_I],
     "pb_conv3x3_relu_bwd": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "pb_linear_fwd": [_I, _I, _I, _I, _P, _LL, _P, _P, _I, _P, _P],
+    "pb_peer_alloc": [_LL, C.POINTER(C.c_void_p)],
+    "pb_peer_free": [_P],
+    "pb_peer_preload": [],
+    "pb_peer_export": [_P, _P],
+    "pb_peer_open": [_P, C.POINTER(C.c_void_p)],
+    "pb_peer_close": [_P],
+    "pb_peer_barrier": [_PEER, _P],
+    "pb_peer_state_allgather": [_PEER, _P, _P],
+    "pb_peer_slice": [_LL, _I],
+    "pb_peer_reduce_scatter": [_PEER, _LL, _P, _P, _P],
+    "pb_peer_adam": [_PEER, _LL, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
     "pb_iqn_phi_bwd": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "pb_tc_gemm_supported": [_I, _I, _I, _LL, _LL, _LL],
     "pb_tc_gemm": [_I, _I, _I, _I, _I, _P, _I, _LL, _LL, _P, _I, _LL, _LL, _P, _LL, _I, _P, _I, _LL, _P, _LL, _LL, _P, _LL, _I, _P],
@@ -96,7 +118,7 @@ SIGNATURES = {
     "pb_linear_bwd_input": [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P],
     "pb_linear_bwd_weight": [_I, _I, _I, _I, _P, _P, _P, _LL, _P, _P, _P],
 }
-_RESTYPES = {"pb_error_string": C.c_char_p, "pb_launch_count": C.c_longlong}
+_RESTYPES = {"pb_error_string": C.c_char_p, "pb_launch_count": C.c_longlong, "pb_peer_slice": C.c_longlong}
 
 PB_E_POOL = -4
 

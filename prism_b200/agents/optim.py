@@ -77,7 +77,17 @@ class FlatAdam(object):
         self._table_host = torch.zeros(len(self.params) * 3, dtype=torch.int64).pin_memory()
         self._table_key = None
         self.grad_scale = 1.0           # 1/world_size under data parallelism
-        self.allreduce = None           # callable(flat_grad) inserted between gather and Adam
+        self.allreduce = None           # callable(flat_grad) inserted between gather and Adam (library collective)
+        self.peer = None                # PeerGroup: gradient exchange fused with clip + Adam over peer memory
+
+    def attach_peer_group(self, peer):
+        """Route the data-parallel gradient exchange through csrc/peer.cu: the flat gradient arena moves into the
+        rank's peer-mapped block and ``step`` becomes pack -> barrier -> reduce-scatter -> barrier -> fused Adam."""
+        if peer.n != self.numel:
+            raise _lib.PbError("peer group sized for %d parameters, optimizer has %d" % (peer.n, self.numel))
+        self.grad = peer.grad
+        self.peer = peer
+        self.allreduce = None
 
     # ---- torch.optim-like surface ------------------------------------------------------
     def zero_grad(self, set_to_none=True):
@@ -109,6 +119,11 @@ class FlatAdam(object):
         stream = torch.cuda.current_stream(self.device).cuda_stream
         import ctypes
         n_part = ctypes.c_int(0)
+        if self.peer is not None:
+            _lib.check(self._lib.pb_pack_grads(len(self.params), self.table.data_ptr(), self.grad_scale,
+                                               self.grad.data_ptr(), None, None, None, stream), "pb_pack_grads")
+            self.peer.allreduce_adam(self)
+            return
         if self.allreduce is None:
             _lib.check(self._lib.pb_pack_grads(len(self.params), self.table.data_ptr(), self.grad_scale,
                                                self.grad.data_ptr(), self.partials.data_ptr(),

@@ -1,0 +1,275 @@
+// peer.cu -- data-parallel exchange steps over NVLink / NVSwitch PEER MEMORY (sm_100a), no NCCL on the path.
+//
+// the replay buffer shards by collector, so the learner needs exactly two exchanges per step:
+//   1. the 64-byte shard state blocks {len, p_sum, p_min, ...} of every rank (global stratified sampling), and
+//   2. the sum of the flat gradient arenas, followed by the SAME clip + Adam step on every rank
+//      (prism/agents/agent.py:73-74 runs clip_grad_norm_ + Adam.step on one process).
+// Both are latency-bound at these sizes (64 B; 9.5 MB for configs[1]), where a library collective costs tens of
+// microseconds per call inside a CUDA graph.  Here every rank maps every other rank's buffers (CUDA IPC) and
+//   * pb_peer_state_allgather: one 1-block kernel stores the local block into every peer and runs the flag
+//     handshake (release/acquire at system scope);
+//   * pb_peer_reduce_scatter: rank r PULLS slice r of every rank's gradient arena with 128-bit loads, adds in rank
+//     order (one owner per slice: no two ranks ever disagree), keeps the reduced slice locally and publishes the
+//     slice's sum of squares to every peer;
+//   * pb_peer_adam: the fused clip + Adam sweep reads each slice of the reduced gradient straight from its owner
+//     (the all-gather half of the all-reduce is fused into the optimizer kernel), derives the global norm from the
+//     published partial sums in rank order (bit-identical on every rank) and updates the local parameter replica.
+// pb_peer_barrier is a 1-block epoch barrier (flags in peer memory, monotonically increasing: graph-replay safe).
+#include "common.cuh"
+
+namespace {
+
+using namespace pb;
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// peer data is re-written every step by another GPU: never serve it from this SM's L1
+__device__ __forceinline__ float4 ld_peer_f4(const float *p)
+{
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_peer_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// one warp: lane i signals rank i and waits for rank i
+__device__ __forceinline__ void epoch_handshake(const pb_peer_group &g)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned long long e = *g.epoch + 1;
+    __threadfence_system();
+    if (lane < g.world) {
+        st_release_sys(g.flags[lane] + g.rank, e);
+        while (ld_acquire_sys(g.flags[g.rank] + lane) < e) { }
+    }
+    __syncwarp();
+    if (lane == 0) *g.epoch = e;
+}
+
+__global__ void __launch_bounds__(32) peer_barrier_kernel(pb_peer_group g) { epoch_handshake(g); }
+
+__global__ void __launch_bounds__(64) peer_state_allgather_kernel(pb_peer_group g, const unsigned int *__restrict__ state)
+{
+    const int t = threadIdx.x;
+    if (t < 16) {
+        const unsigned int v = state[t];
+        for (int p = 0; p < g.world; ++p) reinterpret_cast<unsigned int *>(g.state[p])[g.rank * 16 + t] = v;
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (t < 32) epoch_handshake(g);
+}
+
+constexpr int RS_THREADS = 256;
+
+__global__ void __launch_bounds__(RS_THREADS) peer_reduce_scatter_kernel(pb_peer_group g, long long n, long long slice,
+                                                                         float *__restrict__ partials,
+                                                                         unsigned int *__restrict__ ticket,
+                                                                         long long *__restrict__ step_count)
+{
+    __shared__ double part[RS_THREADS / 32];
+    __shared__ bool last;
+    const long long lo = (long long)g.rank * slice, hi = min(n, lo + slice);
+    const long long n4 = hi > lo ? (hi - lo) >> 2 : 0;                  // slices are multiples of 4 floats; n % 4 == 0
+    float *out = g.reduced[g.rank];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = lo + (i << 2);
+        float4 s = ld_peer_f4(g.grad[0] + e);
+        for (int p = 1; p < g.world; ++p) {
+            const float4 v = ld_peer_f4(g.grad[p] + e);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        *reinterpret_cast<float4 *>(out + e) = s;
+        acc += (double)(s.x * s.x + s.y * s.y) + (double)(s.z * s.z + s.w * s.w);
+    }
+    acc = warp_sum(acc);
+    if (lane_id() == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < RS_THREADS / 32; ++k) t += part[k];
+        reinterpret_cast<double *>(partials)[blockIdx.x] = t;
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned k = 0; k < gridDim.x; ++k) t += reinterpret_cast<volatile double *>(partials)[k];   // fixed order
+        for (int p = 0; p < g.world; ++p) g.norm_parts[p][g.rank] = t;
+        __threadfence_system();
+        *ticket = 0;
+        if (step_count) *step_count += 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) peer_adam_kernel(pb_peer_group g, long long n, long long slice,
+                                                        float *__restrict__ param, float *__restrict__ exp_avg,
+                                                        float *__restrict__ exp_avg_sq,
+                                                        const long long *__restrict__ step_count, float lr, float beta1,
+                                                        float beta2, float adam_eps, float max_grad_norm,
+                                                        float *__restrict__ norm_out, float *__restrict__ grad_out)
+{
+    double sq = 0.0;
+    for (int r = 0; r < g.world; ++r) sq += ld_peer_f64(g.norm_parts[g.rank] + r);          // rank order: identical everywhere
+    const float total_norm = (float)sqrt(sq);
+    float coef = max_grad_norm / (total_norm + 1e-6f);                                       // clip_grad_norm_
+    coef = coef > 1.0f ? 1.0f : coef;
+    if (!(max_grad_norm > 0.0f)) coef = 1.0f;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && norm_out) { norm_out[0] = total_norm; norm_out[1] = coef; }
+    const double step = (double)(*step_count);
+    const float bc1 = (float)(1.0 - pow((double)beta1, step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
+    const float step_size = lr / bc1;
+    auto upd = [&](float &p, float gg, float &m, float &v) {                                 // same arithmetic as adam_clip_kernel
+        gg *= coef;
+        m = m + (gg - m) * (1.0f - beta1);
+        v = v * beta2 + (1.0f - beta2) * gg * gg;
+        const float denom = sqrtf(v) / bc2_sqrt + adam_eps;
+        p = p - step_size * (m / denom);
+    };
+    const long long n4 = n >> 2;
+    float4 *p4 = reinterpret_cast<float4 *>(param), *m4 = reinterpret_cast<float4 *>(exp_avg),
+           *v4 = reinterpret_cast<float4 *>(exp_avg_sq);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i << 2;
+        const int owner = (int)(e / slice);
+        const float4 gr = ld_peer_f4(g.reduced[owner] + e);                                   // all-gather fused into the sweep
+        float4 p = p4[i], m = m4[i], v = v4[i];
+        upd(p.x, gr.x, m.x, v.x); upd(p.y, gr.y, m.y, v.y); upd(p.z, gr.z, m.z, v.z); upd(p.w, gr.w, m.w, v.w);
+        p4[i] = p; m4[i] = m; v4[i] = v;
+        if (grad_out) *reinterpret_cast<float4 *>(grad_out + e) = gr;
+    }
+}
+
+int check_group(const pb_peer_group *g)
+{
+    if (!g || g->world < 1 || g->world > PB_PEER_MAX || g->rank < 0 || g->rank >= g->world || !g->epoch) return PB_E_ARG;
+    for (int p = 0; p < g->world; ++p)
+        if (!g->flags[p]) return PB_E_ARG;
+    return PB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pb_peer_alloc(long long bytes, void **ptr)
+{
+    if (bytes <= 0 || !ptr) return PB_E_ARG;
+    cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(*ptr, 0, (size_t)bytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceSynchronize();
+    return e == cudaSuccess ? PB_OK : (int)e;
+}
+
+int pb_peer_free(void *ptr) { return ptr ? (int)cudaFree(ptr) : PB_OK; }
+
+// Force the (lazily loaded) exchange kernels into the context.  Loading a kernel can synchronise the device; done
+// up front it can never wait behind a barrier kernel that spins on a rank whose work is not launched yet.
+int pb_peer_preload(void)
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, peer_barrier_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_state_allgather_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_reduce_scatter_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_adam_kernel);
+    return e == cudaSuccess ? PB_OK : (int)e;
+}
+
+int pb_peer_export(const void *ptr, void *handle64)
+{
+    if (!ptr || !handle64) return PB_E_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    return (int)cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle64), const_cast<void *>(ptr));
+}
+
+int pb_peer_open(const void *handle64, void **ptr)
+{
+    if (!handle64 || !ptr) return PB_E_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    return (int)cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+
+int pb_peer_close(void *ptr) { return ptr ? (int)cudaIpcCloseMemHandle(ptr) : PB_OK; }
+
+int pb_peer_barrier(const pb_peer_group *g, void *stream)
+{
+    int rc = check_group(g);
+    if (rc) return rc;
+    PB_LAUNCH(peer_barrier_kernel, 1, 32, 0, stream, *g);
+    return PB_OK;
+}
+
+int pb_peer_state_allgather(const pb_peer_group *g, const void *state64, void *stream)
+{
+    int rc = check_group(g);
+    if (rc) return rc;
+    if (!state64) return PB_E_ARG;
+    for (int p = 0; p < g->world; ++p)
+        if (!g->state[p]) return PB_E_ARG;
+    PB_LAUNCH(peer_state_allgather_kernel, 1, 64, 0, stream, *g, reinterpret_cast<const unsigned int *>(state64));
+    return PB_OK;
+}
+
+long long pb_peer_slice(long long n, int world)
+{
+    if (n <= 0 || world <= 0) return 0;
+    const long long q = ((n + 3) / 4 + world - 1) / world;
+    return q * 4;
+}
+
+int pb_peer_reduce_scatter(const pb_peer_group *g, long long n, float *partial_scratch, long long *step_count, void *stream)
+{
+    int rc = check_group(g);
+    if (rc) return rc;
+    if (n <= 0 || (n % 4) != 0 || !partial_scratch) return PB_E_ARG;
+    for (int p = 0; p < g->world; ++p)
+        if (!g->grad[p] || !g->reduced[p] || !g->norm_parts[p]) return PB_E_ARG;
+    const long long slice = pb_peer_slice(n, g->world);
+    long long nb = ((slice >> 2) + RS_THREADS - 1) / RS_THREADS;
+    const long long cap = (long long)pb_sm_count() * 4;
+    if (nb > cap) nb = cap;
+    if (nb > 1024) nb = 1024;                                          // partial_scratch: 4096 floats = 2040 doubles + ticket
+    if (nb < 1) nb = 1;
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(partial_scratch + 4092);
+    PB_LAUNCH(peer_reduce_scatter_kernel, (unsigned)nb, RS_THREADS, 0, stream, *g, n, slice, partial_scratch, ticket, step_count);
+    return PB_OK;
+}
+
+int pb_peer_adam(const pb_peer_group *g, long long n, float *param, float *exp_avg, float *exp_avg_sq,
+                 const long long *step_count, float lr, float beta1, float beta2, float adam_eps, float max_grad_norm,
+                 float *norm_out, float *grad_out, void *stream)
+{
+    int rc = check_group(g);
+    if (rc) return rc;
+    if (n <= 0 || (n % 4) != 0 || !param || !exp_avg || !exp_avg_sq || !step_count) return PB_E_ARG;
+    if ((((uintptr_t)param) | ((uintptr_t)exp_avg) | ((uintptr_t)exp_avg_sq) | ((uintptr_t)grad_out)) & 15) return PB_E_ARG;
+    const long long slice = pb_peer_slice(n, g->world);
+    long long nb = ((n >> 2) + 255) / 256;
+    const long long cap = (long long)pb_sm_count() * 4;
+    if (nb > cap) nb = cap;
+    PB_LAUNCH(peer_adam_kernel, (unsigned)nb, 256, 0, stream, *g, n, slice, param, exp_avg, exp_avg_sq, step_count, lr, beta1,
+              beta2, adam_eps, max_grad_norm, norm_out, grad_out);
+    return PB_OK;
+}
+
+}  // extern "C"

@@ -11,8 +11,9 @@ priority write-back are captured into a single graph, replayed once per iteratio
 
 Data parallel: every rank owns a shard (ring + trees) fed by its own collectors.
 Per iteration: one NCCL all-gather of the 64-byte shard state blocks, global stratified sampling
-with owner-computes placement (no transition crosses NVLink), one NCCL all-reduce of the flat
-gradient arena.
+with owner-computes placement (no transition crosses NVLink), one all-reduce of the flat gradient
+arena fused with clip + Adam.  Both exchanges run as our own kernels over NVLink peer memory
+(csrc/peer.cu); PB_DP_EXCHANGE=nccl (or ranks that cannot map each other) falls back to NCCL.
 """
 import torch
 
@@ -23,7 +24,7 @@ from .experience.per import PrioritizedTree
 
 class LearnerStep:
     def __init__(self, buffer, agent, batch_size=None, use_cuda_graph=True, process_group=None,
-                 rank=0, world_size=1, pad_slack=None):
+                 rank=0, world_size=1, pad_slack=None, exchange=None):
         self.buffer, self.agent = buffer, agent
         self.tree = buffer.buffer._sampler
         self.ring = buffer.buffer._storage
@@ -60,12 +61,29 @@ class LearnerStep:
         self.batch = buffer.get_static_batch()
         agent.set_static_batch(self.batch)
         opt = agent.optimizer
+        self.peer = None
         if self.world_size > 1:
             if not isinstance(opt, FlatAdam):
-                raise _lib.PbError("data parallel needs the FlatAdam arena (one all-reduce per step)")
+                raise _lib.PbError("data parallel needs the FlatAdam arena (one exchange per step)")
+            import os
+            import sys
             import torch.distributed as dist
             opt.grad_scale = float(self.B_pad) / float(self.B_global)   # local mean over B_pad -> global mean
-            opt.allreduce = lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+            mode = (exchange or os.environ.get("PB_DP_EXCHANGE", "peer")).lower()
+            if mode == "peer":
+                # NVLink / NVSwitch peer memory (csrc/peer.cu): state all-gather and gradient all-reduce + Adam as our
+                # own kernels; torch.distributed only exchanges the IPC handles, once
+                try:
+                    from .peer import PeerGroup
+                    self.peer = PeerGroup.create(self.pg, self.rank, self.world_size, opt.numel, d)
+                    opt.attach_peer_group(self.peer)
+                    self.all_state = self.peer.all_state
+                except Exception as e:                                   # e.g. ranks on different boxes
+                    sys.stderr.write("peer-memory exchange unavailable (%r): using the library collectives\n" % (e,))
+                    self.peer = None
+            if self.peer is None:
+                opt.allreduce = lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+            self.exchange = "peer" if self.peer is not None else "nccl"
         self.launches_per_step = None
 
     # ------------------------------------------------------------------------------------
@@ -73,8 +91,11 @@ class LearnerStep:
         tree, ring, agent, b = self.tree, self.ring, self.agent, self.buffer
         u = None if draw else self.u            # None: uniforms are drawn inside the sampling kernel
         if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(self.all_state.view(-1), tree.state, group=self.pg)
+            if self.peer is not None:
+                self.peer.state_allgather(tree.state)
+            else:
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(self.all_state.view(-1), tree.state, group=self.pg)
             tree.sample_global(self.world_size, self.rank, self.all_state, self.B_global, u,
                                idx_out=self.idx, weight_out=self.weight, stratum_out=self.stratum)
         else:

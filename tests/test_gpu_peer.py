@@ -1,0 +1,86 @@
+"""Peer-memory exchange kernels (csrc/peer.cu) driven in LOOPBACK: `world` ranks inside one process on one GPU,
+each on its own stream with plain pointers to the other ranks' blocks -- same kernels, same flag protocol as the
+multi-process CUDA-IPC set-up of LearnerStep."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class _Opt:
+    """The fields PeerGroup.allreduce_adam reads from FlatAdam."""
+
+    def __init__(self, n, p0, lr=1e-3, max_grad_norm=10.0):
+        self.arena = p0.clone()
+        self.exp_avg = torch.zeros(n, device=DEV)
+        self.exp_avg_sq = torch.zeros(n, device=DEV)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=DEV)
+        self.partials = torch.zeros(4096, device=DEV)
+        self.norm_out = torch.zeros(2, device=DEV)
+        self.lr, self.betas, self.eps, self.max_grad_norm = lr, (0.9, 0.999), 1.5e-4, max_grad_norm
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("n", [4096, 1_000_004])
+def test_peer_allreduce_adam_matches_single_rank_step(world, n):
+    from prism_b200 import _lib
+    from prism_b200.peer import PeerGroup
+    lib = _lib.load()
+    groups = PeerGroup.loopback(world, n, DEV)
+    g = torch.Generator(device=DEV).manual_seed(n + world)
+    p0 = torch.randn(n, device=DEV, generator=g)
+    grads = [torch.randn(n, device=DEV, generator=g) * (3.0 if r == 0 else 1.0) for r in range(world)]
+    opts = [_Opt(n, p0) for _ in range(world)]
+    streams = [torch.cuda.Stream(device=DEV) for _ in range(world)]
+    # every tensor exists before the first barrier kernel spins: a cudaMalloc (device-wide sync) issued by this single
+    # host thread while one loopback rank waits for a rank that is not launched yet would deadlock the test
+    staged = [[grads[r] * (1.0 + it) for r in range(world)] for it in range(3)]
+    torch.cuda.synchronize()
+    for it in range(3):                                       # three steps: epochs, ticket and step counter carry over
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                groups[r].grad.copy_(staged[it][r])
+                groups[r].allreduce_adam(opts[r])
+    torch.cuda.synchronize()
+    # reference: the single-rank fused step on the rank-order fp32 sum
+    ref = _Opt(n, p0)
+    for it in range(3):
+        total = grads[0] * (1.0 + it)
+        for r in range(1, world):
+            total = total + grads[r] * (1.0 + it)
+        _lib.check(lib.pb_adam_clip_step(n, ref.arena.data_ptr(), total.data_ptr(), ref.exp_avg.data_ptr(),
+                                         ref.exp_avg_sq.data_ptr(), ref.step_count.data_ptr(), ref.lr, 0.9, 0.999, ref.eps,
+                                         ref.max_grad_norm, ref.norm_out.data_ptr(), ref.partials.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream), "pb_adam_clip_step")
+    torch.cuda.synchronize()
+    for r in range(world):
+        assert int(opts[r].step_count) == 3
+        assert torch.equal(opts[r].arena, opts[0].arena), "replicas must stay bit-identical"
+        assert torch.equal(opts[r].exp_avg_sq, opts[0].exp_avg_sq)
+    assert rel_err(opts[0].norm_out.cpu().numpy(), ref.norm_out.cpu().numpy()) < 1e-6
+    assert rel_err(opts[0].arena.cpu().numpy(), ref.arena.cpu().numpy()) < 1e-6
+    assert rel_err(opts[0].exp_avg.cpu().numpy(), ref.exp_avg.cpu().numpy()) < 1e-6
+
+
+def test_peer_state_allgather_and_barrier():
+    from prism_b200.peer import PeerGroup
+    world = 4
+    groups = PeerGroup.loopback(world, 1024, DEV)
+    streams = [torch.cuda.Stream(device=DEV) for _ in range(world)]
+    for it in range(5):
+        states = [torch.randint(0, 256, (64,), dtype=torch.uint8, device=DEV) for _ in range(world)]
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                groups[r].state_allgather(states[r])
+                groups[r].barrier()
+        torch.cuda.synchronize()
+        want = torch.stack(states)
+        for r in range(world):
+            assert torch.equal(groups[r].all_state, want)
