@@ -445,6 +445,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     pg = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")             # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(device))
         pg = dist.group.WORLD
     hbm_gbs, peak_src = peaks()

@@ -36,7 +36,7 @@ def _digest():
     files.append(os.path.join(ROOT, "include", "prism_b200.h"))
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())      # not the absolute path: the tree is copied to other boxes
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -51,10 +51,29 @@ def build(force=False, verbose=False):
     """Compile every .cu under csrc/ into lib/libprism_b200.so.  Returns the library path."""
     os.makedirs(LIB_DIR, exist_ok=True)
     digest = _digest()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP):
-        with open(STAMP) as fh:
-            if fh.read().strip() == digest:
-                return LIB_PATH
+
+    def fresh():
+        if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP):
+            with open(STAMP) as fh:
+                return fh.read().strip() == digest
+        return False
+
+    if fresh():
+        return LIB_PATH
+    # one builder at a time (torchrun starts several ranks at once); late-comers find a fresh library
+    import fcntl
+    lock = open(os.path.join(LIB_DIR, ".build.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if fresh():
+            return LIB_PATH
+        return _build_locked(digest, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(digest, verbose):
     nvcc = find_nvcc()
     if nvcc is None:
         if os.path.exists(LIB_PATH):
@@ -77,10 +96,12 @@ def build(force=False, verbose=False):
             print(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
+    tmp = LIB_PATH + ".tmp"
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s" % r.stdout)
+    os.replace(tmp, LIB_PATH)
     with open(STAMP, "w") as fh:
         fh.write(digest)
     return LIB_PATH
