@@ -64,7 +64,9 @@ class Agent(object):
         self.n_updates += 1
         return new_per_weights
 
-    def _loss_and_backward(self, batch, per_weights, target_model):
+    def _loss_and_backward(self, batch, per_weights, target_model, after_loss=None):
+        """``after_loss(td)``: called once the losses / new priorities exist and before the backward pass starts
+        (LearnerStep forks the priority write-back onto a parallel graph branch there)."""
         if hasattr(self.model, "losses_total"):
             # fused head: loss kernels emit PER-weighted gradients directly (agent.py:58-64 folded in)
             dist_loss, q_loss, total, td = self.model.losses_total(batch, target_model, per_weights)
@@ -78,6 +80,8 @@ class Agent(object):
             total, _ = ops.loss_combine(dist_loss, q_loss, w)   # mean(dist*w) + mean(q*w)  (agent.py:58-64)
             if w is None and per_weights != 1:
                 total = total * per_weights
+        if after_loss is not None:
+            after_loss(td)
         self.optimizer.zero_grad(set_to_none=True)
         total.backward()
         return dist_loss, q_loss, total, td

@@ -150,6 +150,17 @@ def loss_combine(dist_loss, q_loss, per_weights):
     return _LossCombine.apply(dist_loss, q_loss, per_weights)
 
 
+PARALLEL_BACKWARD = __import__('os').environ.get('PB_PARALLEL_BACKWARD', '1') != '0'
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    s = _SIDE_STREAMS.get(device)
+    if s is None:
+        s = _SIDE_STREAMS[device] = torch.cuda.Stream(device=device)
+    return s
+
+
 class _Linear(torch.autograd.Function):
     """Y = act(X W^T + b), batched over heads.  X: (M, J) shared or (K, M, J); W: (K, N, J); b: (K, N)."""
 
@@ -175,16 +186,33 @@ class _Linear(torch.autograd.Function):
         lib, stream = _lib.load(), _stream(dy)
         mask = _lib.ptr(y) if ctx.act else None
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
+        want_dx = ctx.needs_input_grad[0]
+        want_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        if want_dx:
             dx = torch.empty((M, J) if ctx.shared else (K, M, J), dtype=torch.float32, device=dy.device)
-            _lib.check(lib.pb_linear_bwd_input(K, M, N, J, dy.data_ptr(), mask, wc.data_ptr(), int(ctx.shared),
-                                               dx.data_ptr(), stream), "pb_linear_bwd_input")
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        if want_dw:
             dw = torch.empty(K, N, J, dtype=torch.float32, device=dy.device)
             db = torch.empty(K, N, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
-            _lib.check(lib.pb_linear_bwd_weight(K, M, N, J, dy.data_ptr(), mask, xc.data_ptr(),
-                                                0 if ctx.shared else M * J, dw.data_ptr(), _lib.ptr(db), stream),
-                       "pb_linear_bwd_weight")
+        # the two gradient GEMMs are independent and each is too small to fill the chip: the weight gradient goes to a
+        # second stream (a parallel branch under CUDA-graph capture) and is joined before the function returns
+        side = _side_stream(dy.device) if (want_dx and want_dw and PARALLEL_BACKWARD) else None
+        if want_dw:
+            if side is not None:
+                cur = torch.cuda.current_stream(dy.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    _lib.check(lib.pb_linear_bwd_weight(K, M, N, J, dy.data_ptr(), mask, xc.data_ptr(),
+                                                        0 if ctx.shared else M * J, dw.data_ptr(), _lib.ptr(db),
+                                                        side.cuda_stream), "pb_linear_bwd_weight")
+            else:
+                _lib.check(lib.pb_linear_bwd_weight(K, M, N, J, dy.data_ptr(), mask, xc.data_ptr(),
+                                                    0 if ctx.shared else M * J, dw.data_ptr(), _lib.ptr(db), stream),
+                           "pb_linear_bwd_weight")
+        if want_dx:
+            _lib.check(lib.pb_linear_bwd_input(K, M, N, J, dy.data_ptr(), mask, wc.data_ptr(), int(ctx.shared),
+                                               dx.data_ptr(), stream), "pb_linear_bwd_input")
+        if side is not None:
+            torch.cuda.current_stream(dy.device).wait_stream(side)
         return dx, dw, db, None
 
 
@@ -265,7 +293,7 @@ class _LinearTC(torch.autograd.Function):
 
 TENSOR_CORE_LINEAR = True      # module switch for A/B timing; the tcgen05 path is the default for large layers
 TC_MIN_ROWS = 256              # an M = 128 tile needs rows to fill it
-TC_MIN_FLOPS = 2.0e8           # below this a layer is launch-bound and stays on the fused SIMT kernel / library
+TC_MIN_FLOPS = float(__import__('os').environ.get('PB_TC_MIN_FLOPS', 2.0e8))           # below this a layer is launch-bound and stays on the fused SIMT kernel / library
 
 
 def _tc_eligible(x, M, Kh, N, J):

@@ -85,6 +85,9 @@ class LearnerStep:
                 opt.allreduce = lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
             self.exchange = "peer" if self.peer is not None else "nccl"
         self.launches_per_step = None
+        self._side = torch.cuda.Stream(device=d)
+        import os as _os
+        self.overlap_write_back = _os.environ.get("PB_OVERLAP_WRITEBACK", "1") != "0"
 
     # ------------------------------------------------------------------------------------
     def _body(self, refresh_table, draw):
@@ -103,11 +106,25 @@ class LearnerStep:
         # rows past the strata this rank owns have idx -1 / weight 0: skipped by gather and update
         idx, w = self.idx[:self.B_pad], self.weight[:self.B_pad]
         ring.gather(idx, b._obs, b._next_obs, b._reward, b._gamma, b._nonterminal, b._action)
-        dl, ql, total, td = agent._loss_and_backward(self.batch, w, agent.target_model)
+        # The priority write-back (learner.py:120) needs the new TD errors only, not the optimizer step: it runs on
+        # a second stream -- a parallel branch of the captured graph -- while backward / (exchange) / Adam proceed.
+        cur = torch.cuda.current_stream(self.device)
+
+        def write_back(td):
+            self.td = td
+            if not self.overlap_write_back:
+                return
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                tree.update_priority(idx, td, sorted=self.sorted)      # |td| is taken inside the kernel
+
+        dl, ql, total, td = agent._loss_and_backward(self.batch, w, agent.target_model, after_loss=write_back)
         agent._static_distribution_loss, agent._static_q_loss, agent._static_total_loss = dl, ql, total
         agent._optimizer_step(refresh_table=refresh_table)
-        self.td = td
-        tree.update_priority(idx, td, sorted=self.sorted)      # |td| is taken inside the kernel (learner.py:120)
+        if self.overlap_write_back:
+            cur.wait_stream(self._side)
+        else:
+            tree.update_priority(idx, self.td, sorted=self.sorted)
         return total
 
     def step(self, u=None):
