@@ -390,6 +390,7 @@ typedef struct pb_peer_group {
 } pb_peer_group;
 int pb_peer_alloc(long long bytes, void **ptr);            /* cudaMalloc + zero fill; blocking                      */
 int pb_peer_free(void *ptr);
+int pb_optimizer_preload(void);                            /* same for pack_grads / grad_sumsq / adam_clip          */
 int pb_peer_preload(void);                                  /* load the exchange kernels now (blocking)              */
 int pb_peer_export(const void *ptr, void *handle64);
 int pb_peer_open(const void *handle64, void **ptr);        /* maps a peer block, enabling peer access               */
@@ -403,6 +404,11 @@ long long pb_peer_slice(long long n, int world);           /* floats per rank sl
  * to every rank; increments *step_count (may be NULL).  Needs a pb_peer_barrier between the writers of grad and
  * this call, and another one before pb_peer_adam.  partial_scratch: 4096 floats.  n % 4 == 0. */
 int pb_peer_reduce_scatter(const pb_peer_group *g, long long n, float *partial_scratch, long long *step_count, void *stream);
+/* One-shot all-reduce for small arenas: reduced[rank] = sum over ranks (rank order) of grad[p], all n floats pulled
+ * by every rank, + per-block sums of squares in partial_scratch (*n_partials_out_h of them) for pb_adam_clip_apply on
+ * (param, reduced[rank]).  One pb_peer_barrier before it, none after. */
+int pb_peer_pull_sum(const pb_peer_group *g, long long n, float *partial_scratch, long long *step_count,
+                     int *n_partials_out_h, void *stream);
 /* clip_grad_norm_(max_grad_norm) + Adam over the local replica, reading the reduced gradient slice by slice from its
  * owner rank.  grad_out (optional): receives the full reduced gradient. */
 int pb_peer_adam(const pb_peer_group *g, long long n, float *param, float *exp_avg, float *exp_avg_sq,

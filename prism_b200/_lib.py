@@ -102,6 +102,7 @@ SIGNATURES = {
     "pb_peer_alloc": [_LL, C.POINTER(C.c_void_p)],
     "pb_peer_free": [_P],
     "pb_peer_preload": [],
+    "pb_optimizer_preload": [],
     "pb_peer_export": [_P, _P],
     "pb_peer_open": [_P, C.POINTER(C.c_void_p)],
     "pb_peer_close": [_P],
@@ -109,6 +110,7 @@ SIGNATURES = {
     "pb_peer_state_allgather": [_PEER, _P, _P],
     "pb_peer_slice": [_LL, _I],
     "pb_peer_reduce_scatter": [_PEER, _LL, _P, _P, _P],
+    "pb_peer_pull_sum": [_PEER, _LL, _P, _P, C.POINTER(C.c_int), _P],
     "pb_peer_adam": [_PEER, _LL, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
     "pb_iqn_phi_bwd": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "pb_tc_gemm_supported": [_I, _I, _I, _LL, _LL, _LL],

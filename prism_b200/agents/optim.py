@@ -79,6 +79,7 @@ class FlatAdam(object):
         self.grad_scale = 1.0           # 1/world_size under data parallelism
         self.allreduce = None           # callable(flat_grad) inserted between gather and Adam (library collective)
         self.peer = None                # PeerGroup: gradient exchange fused with clip + Adam over peer memory
+        self.peer_trailing_barrier = True
 
     def attach_peer_group(self, peer):
         """Route the data-parallel gradient exchange through csrc/peer.cu: the flat gradient arena moves into the
@@ -122,7 +123,7 @@ class FlatAdam(object):
         if self.peer is not None:
             _lib.check(self._lib.pb_pack_grads(len(self.params), self.table.data_ptr(), self.grad_scale,
                                                self.grad.data_ptr(), None, None, None, stream), "pb_pack_grads")
-            self.peer.allreduce_adam(self)
+            self.peer.allreduce_adam(self, trailing_barrier=self.peer_trailing_barrier)
             return
         if self.allreduce is None:
             _lib.check(self._lib.pb_pack_grads(len(self.params), self.table.data_ptr(), self.grad_scale,

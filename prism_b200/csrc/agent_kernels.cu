@@ -506,6 +506,16 @@ int pb_adam_clip_apply(long long n, float *param, const float *grad, float *exp_
     return PB_OK;
 }
 
+// load the optimizer kernels now (see pb_peer_preload)
+int pb_optimizer_preload(void)
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, adam_clip_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pack_grads_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, grad_sumsq_kernel);
+    return e == cudaSuccess ? PB_OK : (int)e;
+}
+
 int pb_adam_clip_step(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
                       long long *step_count, float lr, float beta1, float beta2, float adam_eps,
                       float max_grad_norm, float *norm_out, float *partial_scratch, void *stream)

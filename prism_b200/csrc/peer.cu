@@ -118,6 +118,38 @@ __global__ void __launch_bounds__(RS_THREADS) peer_reduce_scatter_kernel(pb_peer
     }
 }
 
+// One-shot variant for small arenas (latency-bound: n * world * 4 B of NVLink pulls cost less than a second
+// cross-GPU barrier): every rank pulls ALL ranks' gradients, adds them in rank order into its local reduced buffer
+// and leaves per-block sums of squares -- same grid and order on every rank, so the replicas agree bit for bit --
+// for the ordinary single-GPU clip + Adam kernel that follows.
+__global__ void __launch_bounds__(RS_THREADS) peer_pull_sum_kernel(pb_peer_group g, long long n, float *__restrict__ partials,
+                                                                   long long *__restrict__ step_count)
+{
+    __shared__ double part[RS_THREADS / 32];
+    const long long n4 = n >> 2;
+    float *out = g.reduced[g.rank];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i << 2;
+        float4 s = ld_peer_f4(g.grad[0] + e);
+        for (int p = 1; p < g.world; ++p) {
+            const float4 v = ld_peer_f4(g.grad[p] + e);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        *reinterpret_cast<float4 *>(out + e) = s;
+        acc += (double)(s.x * s.x + s.y * s.y) + (double)(s.z * s.z + s.w * s.w);
+    }
+    acc = warp_sum(acc);
+    if (lane_id() == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < RS_THREADS / 32; ++k) t += part[k];
+        partials[blockIdx.x] = (float)t;
+        if (blockIdx.x == 0 && step_count) *step_count += 1;
+    }
+}
+
 __global__ void __launch_bounds__(256) peer_adam_kernel(pb_peer_group g, long long n, long long slice,
                                                         float *__restrict__ param, float *__restrict__ exp_avg,
                                                         float *__restrict__ exp_avg_sq,
@@ -191,6 +223,7 @@ int pb_peer_preload(void)
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_state_allgather_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_reduce_scatter_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_adam_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_pull_sum_kernel);
     return e == cudaSuccess ? PB_OK : (int)e;
 }
 
@@ -252,6 +285,24 @@ int pb_peer_reduce_scatter(const pb_peer_group *g, long long n, float *partial_s
     if (nb < 1) nb = 1;
     unsigned int *ticket = reinterpret_cast<unsigned int *>(partial_scratch + 4092);
     PB_LAUNCH(peer_reduce_scatter_kernel, (unsigned)nb, RS_THREADS, 0, stream, *g, n, slice, partial_scratch, ticket, step_count);
+    return PB_OK;
+}
+
+int pb_peer_pull_sum(const pb_peer_group *g, long long n, float *partial_scratch, long long *step_count,
+                     int *n_partials_out_h, void *stream)
+{
+    int rc = check_group(g);
+    if (rc) return rc;
+    if (n <= 0 || (n % 4) != 0 || !partial_scratch) return PB_E_ARG;
+    for (int p = 0; p < g->world; ++p)
+        if (!g->grad[p]) return PB_E_ARG;
+    if (!g->reduced[g->rank]) return PB_E_ARG;
+    long long nb = ((n >> 2) + RS_THREADS - 1) / RS_THREADS;
+    const long long cap = (long long)pb_sm_count() * 4;
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+    PB_LAUNCH(peer_pull_sum_kernel, (unsigned)nb, RS_THREADS, 0, stream, *g, n, partial_scratch, step_count);
+    if (n_partials_out_h) *n_partials_out_h = (int)nb;
     return PB_OK;
 }
 

@@ -77,6 +77,7 @@ class LearnerStep:
                     from .peer import PeerGroup
                     self.peer = PeerGroup.create(self.pg, self.rank, self.world_size, opt.numel, d)
                     opt.attach_peer_group(self.peer)
+                    opt.peer_trailing_barrier = False        # the next step's state all-gather is the separating barrier
                     self.all_state = self.peer.all_state
                 except Exception as e:                                   # e.g. ranks on different boxes
                     sys.stderr.write("peer-memory exchange unavailable (%r): using the library collectives\n" % (e,))

@@ -15,6 +15,9 @@ import torch
 from . import _lib
 
 
+ONE_SHOT_MAX_BYTES = 32 * 1024 * 1024      # n * 4 * world up to which the one-shot (single barrier) all-reduce is used
+
+
 class _RawCuda:
     """Expose a raw device allocation to torch through __cuda_array_interface__."""
 
@@ -38,6 +41,7 @@ class PeerGroup:
         self._own_ptr, self._opened = own_ptr, list(opened)
         self.off = _layout(n)
         _lib.check(_lib.load().pb_peer_preload(), "pb_peer_preload")
+        _lib.check(_lib.load().pb_optimizer_preload(), "pb_optimizer_preload")
         g = _lib.pb_peer_group()
         g.world, g.rank = self.world, self.rank
         for p in range(self.world):
@@ -48,6 +52,7 @@ class PeerGroup:
         self.c = g
         self._block = torch.as_tensor(_RawCuda(own_ptr, self.off["total"]), device=self.device)
         self.grad = self._block[self.off["grad"]:self.off["grad"] + 4 * self.n].view(torch.float32)
+        self.reduced = self._block[self.off["reduced"]:self.off["reduced"] + 4 * self.n].view(torch.float32)
         self.all_state = self._block[self.off["state"]:self.off["state"] + 64 * self.world].view(self.world, 64)
 
     # ---- construction -------------------------------------------------------------------------------------
@@ -102,10 +107,26 @@ class PeerGroup:
                    "pb_peer_state_allgather")
         return self.all_state
 
-    def allreduce_adam(self, opt):
-        """Sum ``opt.grad`` (= self.grad) over the ranks and apply clip + Adam on every replica (csrc/peer.cu)."""
+    def allreduce_adam(self, opt, trailing_barrier=True):
+        """Sum ``opt.grad`` (= self.grad) over the ranks and apply clip + Adam on every replica (csrc/peer.cu).
+
+        ``trailing_barrier``: the one-shot schedule lets a fast rank leave while slower ranks still pull its gradient;
+        the next writer of ``grad`` must be separated from them by a barrier.  LearnerStep passes False because every
+        step starts with the state all-gather (a full handshake) before anything touches the arena again."""
         lib, st = _lib.load(), self._stream()
         _lib.check(lib.pb_peer_barrier(C.byref(self.c), st), "pb_peer_barrier")            # every rank packed its gradient
+        if self.n * 4 * self.world <= ONE_SHOT_MAX_BYTES:
+            # small arena: pulling every rank's gradient whole costs less than a second cross-GPU barrier
+            n_part = C.c_int(0)
+            _lib.check(lib.pb_peer_pull_sum(C.byref(self.c), self.n, opt.partials.data_ptr(), opt.step_count.data_ptr(),
+                                            C.byref(n_part), st), "pb_peer_pull_sum")
+            _lib.check(lib.pb_adam_clip_apply(self.n, opt.arena.data_ptr(), self.reduced.data_ptr(), opt.exp_avg.data_ptr(),
+                                              opt.exp_avg_sq.data_ptr(), opt.step_count.data_ptr(), opt.lr, opt.betas[0],
+                                              opt.betas[1], opt.eps, opt.max_grad_norm, opt.partials.data_ptr(), n_part.value,
+                                              opt.norm_out.data_ptr(), st), "pb_adam_clip_apply")
+            if trailing_barrier:
+                _lib.check(lib.pb_peer_barrier(C.byref(self.c), st), "pb_peer_barrier")
+            return
         _lib.check(lib.pb_peer_reduce_scatter(C.byref(self.c), self.n, opt.partials.data_ptr(), opt.step_count.data_ptr(), st),
                    "pb_peer_reduce_scatter")
         _lib.check(lib.pb_peer_barrier(C.byref(self.c), st), "pb_peer_barrier")            # every slice reduced + norms published

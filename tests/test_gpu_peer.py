@@ -27,10 +27,13 @@ class _Opt:
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("n", [4096, 1_000_004])
-def test_peer_allreduce_adam_matches_single_rank_step(world, n):
-    from prism_b200 import _lib
+@pytest.mark.parametrize("n,one_shot", [(4096, True), (1_000_004, True), (1_000_004, False)])
+def test_peer_allreduce_adam_matches_single_rank_step(world, n, one_shot, monkeypatch):
+    """Both exchange schedules: one-shot (every rank pulls everything, one barrier) and two-shot (reduce-scatter by
+    pull + the all-gather fused into the Adam sweep, two barriers)."""
+    from prism_b200 import _lib, peer as peer_mod
     from prism_b200.peer import PeerGroup
+    monkeypatch.setattr(peer_mod, "ONE_SHOT_MAX_BYTES", (1 << 40) if one_shot else 0)
     lib = _lib.load()
     groups = PeerGroup.loopback(world, n, DEV)
     g = torch.Generator(device=DEV).manual_seed(n + world)
