@@ -253,17 +253,81 @@ def kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src):
     opt.restore(snap)
     opt.allreduce = saved_allreduce
     opt.peer = saved_peer
+    # the dense layers of the Q head at the step's shapes (embedding 1024 -> hidden 256, fused bias + ReLU)
+    from prism_b200.agents import ops
+    F_, H_ = 1024, 256
+    xg = torch.randn(B, F_, device=buf.device)
+    wg = torch.randn(1, H_, F_, device=buf.device) / 32.0
+    bg = torch.zeros(1, H_, device=buf.device)
+    with torch.no_grad():
+        t_fc = time_kernel(lambda: ops.linear_heads(xg, wg, bg, relu=True), 50, torch)
+    fc_flops = 2.0 * B * H_ * F_
+    fc_bytes = 4 * (B * F_ + H_ * F_ + H_ + B * H_)
     out = {}
     for k, (sec, nbytes) in rows.items():
         gbs = nbytes / sec / 1e9
         out[k] = {"us": round(sec * 1e6, 2), "algorithmic_bytes": int(nbytes), "achieved_gbs": round(gbs, 2),
                   "frac": round(gbs / hbm_gbs, 5)}
+    bf16 = tensor_peak()
+    out["q_head_fc1_fwd (gemm_kernel, %dx%dx%d fp32 FFMA, cluster split-K)" % (B, H_, F_)] = {
+        "us": round(t_fc * 1e6, 2), "algorithmic_flops": int(fc_flops), "algorithmic_bytes": int(fc_bytes),
+        "achieved_tflops": round(fc_flops / t_fc / 1e12, 3), "achieved_gbs": round(fc_bytes / t_fc / 1e9, 2),
+        "frac_of_bf16_tensor_peak": round(fc_flops / t_fc / 1e12 / bf16, 5), "frac": round(fc_bytes / t_fc / 1e9 / hbm_gbs, 5)}
     dom = max(out, key=lambda k: out[k]["us"])
-    roof = {"bound": "hbm", "kernel": dom, "achieved": out[dom]["achieved_gbs"], "peak": hbm_gbs, "unit": "GB/s",
-            "frac": out[dom]["frac"], "traffic": None, "peak_source": peak_src,
-            "note": "batch-256 launches move KBs-MBs: latency-bound by construction; see extras.per_microbench "
-                    "for the saturated PER kernels"}
+    d = out[dom]
+    if "algorithmic_flops" in d:
+        # GEMM-shaped work: the tensor / FMA pipes bound it; 3 forward + 2x2 backward launches of this family are ~45 %
+        # of the step (profiles/launches_r01d_step.txt).  traffic: dram__bytes_read+write of one launch, ncu --set full
+        # (profiles/ncu_full_step_r01.txt, gemm_kernel<1,1,0> grid (4,4,8)).
+        roof = {"bound": "tensor", "kernel": dom, "achieved": d["achieved_tflops"], "peak": bf16, "unit": "TFLOP/s",
+                "frac": d["frac_of_bf16_tensor_peak"], "traffic": 2134784, "peak_source": peak_src,
+                "note": "batch-256 fp32 layer (134 MFLOP, 2.3 MB): latency-bound by construction -- 128 CTAs x 4 K "
+                        "iterations; the reference computes it in fp32, so the kernel runs on the FFMA pipe and the bf16 "
+                        "tensor peak is only the nominal denominator.  Layers from 2e8 FLOP up run on tcgen05 (3xTF32): "
+                        "see extras.tc_gemm for their tensor-pipe roofline and extras.per_microbench for the HBM-bound "
+                        "PER kernels"}
+    else:
+        roof = {"bound": "hbm", "kernel": dom, "achieved": d["achieved_gbs"], "peak": hbm_gbs, "unit": "GB/s",
+                "frac": d["frac"], "traffic": None, "peak_source": peak_src,
+                "note": "batch-256 launches move KBs-MBs: latency-bound by construction; see extras.per_microbench "
+                        "for the saturated PER kernels"}
     return roof, out
+
+
+def tensor_peak():
+    """Measured dense bf16 TFLOP/s (MEASURED_PEAKS.json, burst: kernels timed alone), else the nominal 2250."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["bf16_tflops"])
+    except Exception:
+        return 2250.0
+
+
+def tc_gemm_microbench(device, torch):
+    """The tcgen05 3xTF32 GEMMs of the configs[4] IQN hidden layer (32768 rows = 64 quantiles x 512, 3136 -> 512) and
+    K-head ensemble: forward, input gradient, weight gradient.  TF32 peak = half the measured bf16 peak; every
+    fp32-equivalent FLOP costs three TF32 FLOPs."""
+    from prism_b200.agents import ops
+    bf16 = tensor_peak()
+    out = {"tf32_peak_tflops": round(bf16 / 2, 1), "note": "achieved_tf32 = 3 x fp32-equivalent; frac = achieved_tf32 / (bf16 peak / 2); "
+           "ncu: sm__pipe_tensor_cycles_active 63-70 % (profiles/ncu_full_tc_gemm_r01.txt)"}
+    for name, (K, M, N, J) in {"iqn_hidden_32768x512x3136": (1, 32768, 512, 3136), "ensemble_10x512x512x3136": (10, 512, 512, 3136)}.items():
+        x = torch.randn(K, M, J, device=device)
+        w = torch.randn(K, N, J, device=device)
+        b = torch.randn(K, N, device=device)
+        dz = torch.randn(K, M, N, device=device)
+        y, dx, dw = torch.empty(K, M, N, device=device), torch.empty(K, M, J, device=device), torch.empty(K, N, J, device=device)
+        fl = 2.0 * K * M * N * J
+        for kind, fn in (("fwd", lambda: ops.tc_gemm(y, x, 0, J, M * J, w, 0, J, N * J, K, M, N, J, bias=b, bias_bs=N, act=1)),
+                         ("dgrad", lambda: ops.tc_gemm(dx, dz, 0, N, M * N, w, 1, J, N * J, K, M, J, N)),
+                         ("wgrad", lambda: ops.tc_gemm(dw, dz, 1, N, M * N, x, 1, J, M * J, K, N, J, M))):
+            t = time_kernel(fn, 10, torch)
+            eq = fl / t / 1e12
+            out["%s_%s" % (name, kind)] = {"us": round(t * 1e6, 1), "algorithmic_flops": int(fl), "fp32_equivalent_tflops": round(eq, 1),
+                                            "achieved_tf32_tflops": round(3 * eq, 1), "frac": round(3 * eq / (bf16 / 2), 3)}
+        del x, w, b, dz, y, dx, dw
+        torch.cuda.empty_cache()
+    return out
 
 
 def per_microbench(device, torch, hbm_gbs):
@@ -498,6 +562,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item())
     lp = step.launches_per_step if graph_ok else None
+    exchange = getattr(step, "exchange", None) if world > 1 else None
     gpu_launches = (lp * args.steps) if lp is not None else (_lib.launch_count() - launches0)
     value = BATCH * world * args.steps / sec
 
@@ -558,6 +623,10 @@ def run_ours(args):
     if world == 1 and not args.quick:
         del step
         extras["per_microbench"] = per_microbench(device, torch, hbm_gbs)
+        try:
+            extras["tc_gemm"] = tc_gemm_microbench(device, torch)
+        except Exception as e:
+            extras["tc_gemm"] = {"error": repr(e)[:300]}
         del agent, buf
         torch.cuda.empty_cache()
         try:
@@ -575,6 +644,8 @@ def run_ours(args):
                                "shard per GPU, batch 256 per GPU, 3-step returns, stratified sampling",
                    "capacity_per_gpu": CAPACITY, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                    "obs_shape": list(OBS_SHAPE), "n_step": 3, "parallelism": "dp%d (buffer sharded by collector)" % world,
+                   "exchange": ("NVLink peer-memory kernels (csrc/peer.cu): state all-gather + one-shot gradient all-reduce fused "
+                                "with clip+Adam" if exchange == "peer" else ("NCCL all-gather + all-reduce" if exchange else None)),
                    "l2": "inputs larger than L2: each step gathers random rows of a 2.4 GB ring; the 16 MB "
                          "sum/min trees are L2-resident by design"},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roof, "cpu_baseline": cpu,

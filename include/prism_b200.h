@@ -415,6 +415,18 @@ int pb_peer_adam(const pb_peer_group *g, long long n, float *param, float *exp_a
                  const long long *step_count, float lr, float beta1, float beta2, float adam_eps, float max_grad_norm,
                  float *norm_out, float *grad_out, void *stream);
 
+/* LayerNorm over the last dimension of a (rows x F) fp32 matrix, forward and backward (csrc/ln.cu), for the
+ * (T*B)-row IQN activations (nn.LayerNorm in ffnn_model.py:17-18, iqn_model.py:42-46).  F % 4 == 0, F <= 4096,
+ * 16-byte aligned pointers.  gamma / beta may be NULL (no affine); mean_out / rstd_out may be NULL (no backward).
+ * Backward makes ONE pass over (x, dy): dx plus per-CTA partial column sums, then a column reduction;
+ * partials = scratch of 2 * pb_layer_norm_bwd_blocks(rows, F) * F floats; dgamma / dbeta may be NULL. */
+int pb_layer_norm_supported(long long rows, int F);
+int pb_layer_norm_bwd_blocks(long long rows, int F);
+int pb_layer_norm_fwd(long long rows, int F, float eps, const float *x, const float *gamma, const float *beta, float *y,
+                      float *mean_out, float *rstd_out, void *stream);
+int pb_layer_norm_bwd(long long rows, int F, const float *x, const float *dy, const float *gamma, const float *mean,
+                      const float *rstd, float *dx, float *dgamma, float *dbeta, float *partials, void *stream);
+
 /* total_loss = mean_b(dist*w) + mean_b(q'*w);  td_b = 0.5*dist + 0.5*q' | dist | |q'|
  * (composite_model.py:135-142, agent.py:58-64) with q' = q_scale * (q - *q_offset)
  * (q_ensemble.py:92: q_loss_weight * (q_loss - theil * coef); q_offset NULL = 0).

@@ -381,6 +381,55 @@ def linear(x, weight, bias, relu=False):
     return _Linear.apply(x, weight.unsqueeze(0), b, 1 if relu else 0).squeeze(0)
 
 
+class _LayerNorm(torch.autograd.Function):
+    """nn.LayerNorm over the last dimension of a 2-D activation: one streaming pass forward, ONE pass backward
+    (csrc/ln.cu) instead of ATen's grad_input + GammaBeta kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        rows, F_ = x.shape
+        xc = _c(x)
+        need = any(ctx.needs_input_grad[:3])
+        y = torch.empty_like(xc)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
+        wc = None if weight is None else _c(weight)
+        bc = None if bias is None else _c(bias)
+        _lib.check(_lib.load().pb_layer_norm_fwd(rows, F_, float(eps), xc.data_ptr(), _lib.ptr(wc), _lib.ptr(bc), y.data_ptr(),
+                                                 _lib.ptr(mean), _lib.ptr(rstd), _stream(x)), "pb_layer_norm_fwd")
+        if need:
+            ctx.save_for_backward(xc, wc, mean, rstd)
+            ctx.has_affine = (weight is not None, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, wc, mean, rstd = ctx.saved_tensors
+        rows, F_ = xc.shape
+        dy = _c(dy)
+        lib = _lib.load()
+        nb = lib.pb_layer_norm_bwd_blocks(rows, F_)
+        partials = torch.empty(2 * nb * F_, dtype=torch.float32, device=dy.device)
+        dx = torch.empty_like(xc)
+        dg = torch.empty(F_, dtype=torch.float32, device=dy.device) if ctx.has_affine[0] else None
+        db = torch.empty(F_, dtype=torch.float32, device=dy.device) if ctx.has_affine[1] else None
+        _lib.check(lib.pb_layer_norm_bwd(rows, F_, xc.data_ptr(), dy.data_ptr(), _lib.ptr(wc), mean.data_ptr(), rstd.data_ptr(),
+                                         dx.data_ptr(), _lib.ptr(dg), _lib.ptr(db), partials.data_ptr(), _stream(dy)),
+                   "pb_layer_norm_bwd")
+        return dx, dg, db, None
+
+
+LN_MIN_ELEMENTS = 1 << 20      # below this ATen's kernels are launch-bound either way
+
+
+def layer_norm(x, module):
+    """nn.LayerNorm module applied through the fused kernels when the activation is large."""
+    if (x.is_cuda and x.dim() == 2 and len(module.normalized_shape) == 1 and x.dtype == torch.float32
+            and x.numel() >= LN_MIN_ELEMENTS and _lib.load().pb_layer_norm_supported(x.shape[0], x.shape[1])):
+        return _LayerNorm.apply(x, module.weight, module.bias, module.eps)
+    return module(x)
+
+
 def run_sequential(seq, x):
     """Evaluate an nn.Sequential of Linear / ReLU / LayerNorm / ... modules, routing every Linear (with a
     directly following ReLU fused in) through the fused kernel.  Other modules run as they are."""
@@ -393,6 +442,9 @@ def run_sequential(seq, x):
             fuse = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
             x = linear(x, m.weight, m.bias, relu=fuse)
             i += 2 if fuse else 1
+        elif isinstance(m, nn.LayerNorm):
+            x = layer_norm(x, m)
+            i += 1
         else:
             x = m(x)
             i += 1

@@ -1,0 +1,272 @@
+// ln.cu -- LayerNorm forward / backward for the (T*B)-row IQN activations (sm_100a), HBM-bound streaming kernels.
+//
+// The reference normalises before every Linear of its heads (nn.LayerNorm inside nn.Sequential,
+// prism/agents/models/ffnn_model.py:17-18, iqn_model.py:42-46, q_ensemble.py:26-40).  At configs[4] that is a
+// (32768 x 3136) fp32 tensor per pass: ATen's backward needs two kernels that each re-read x and dy
+// (layer_norm_grad_input 221 us + GammaBetaBackward 297 us on a B200, profiles/launches_atari_r01_step.txt).  Here
+//   forward : one pass, row kept in registers (two-pass mean / variance: no cancellation), saves mean and rstd;
+//   backward: ONE pass over (x, dy) producing dx and per-CTA partial sums of dgamma / dbeta held in registers by
+//             column-owning threads (persistent CTAs striding over rows), + a small column reduction.
+// Rows up to 1024 floats are handled by one warp (shuffle reductions only), up to 4096 by one 256-thread CTA.
+// Algorithmic traffic: forward 8 B / element, backward 12 B / element.
+#include "common.cuh"
+
+namespace {
+
+using namespace pb;
+
+constexpr int LN_THREADS = 256;
+
+template <int TPR>
+__device__ __forceinline__ float row_sum(float v, float *scratch)
+{
+    v = warp_sum(v);
+    if (TPR == 32) return v;
+    // whole CTA = one row
+    const int w = threadIdx.x >> 5;
+    __syncthreads();                                   // scratch reuse across successive reductions
+    if (lane_id() == 0) scratch[w] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_THREADS / 32; ++k) t += scratch[k];
+    return t;
+}
+
+// TPR threads per row (32: one warp, 8 rows per CTA; 256: one CTA), SLOTS float4 per thread
+template <int TPR, int SLOTS>
+__global__ void __launch_bounds__(LN_THREADS) ln_fwd_kernel(long long rows, int F4, float eps, const float4 *__restrict__ x,
+                                                            const float4 *__restrict__ gamma, const float4 *__restrict__ beta,
+                                                            float4 *__restrict__ y, float *__restrict__ mean_out,
+                                                            float *__restrict__ rstd_out)
+{
+    __shared__ float scratch[LN_THREADS / 32];
+    constexpr int RPC = LN_THREADS / TPR;
+    const int lr = threadIdx.x % TPR, grp = threadIdx.x / TPR;
+    const float inv_f = 1.0f / (float)(F4 * 4);
+    for (long long row = (long long)blockIdx.x * RPC + grp; row < rows; row += (long long)gridDim.x * RPC) {
+        const float4 *xr = x + row * F4;
+        float4 v[SLOTS];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) {
+            const int c = lr + k * TPR;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < F4) {
+                const uint4 u = ldg_stream(reinterpret_cast<const uint4 *>(xr + c));
+                v[k] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+            }
+            s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+        }
+        const float mean = row_sum<TPR>(s, scratch) * inv_f;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) {
+            if (lr + k * TPR < F4) {
+                const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+                q += (a * a + b * b) + (c * c + d * d);
+            }
+        }
+        const float var = row_sum<TPR>(q, scratch) * inv_f;
+        const float rstd = rsqrtf(var + eps);
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) {
+            const int c = lr + k * TPR;
+            if (c < F4) {
+                const float4 g = gamma ? __ldg(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+                const float4 b = beta ? __ldg(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 o;
+                o.x = (v[k].x - mean) * rstd * g.x + b.x;
+                o.y = (v[k].y - mean) * rstd * g.y + b.y;
+                o.z = (v[k].z - mean) * rstd * g.z + b.z;
+                o.w = (v[k].w - mean) * rstd * g.w + b.w;
+                stg_stream(reinterpret_cast<uint4 *>(y + row * F4 + c),
+                           make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
+            }
+        }
+        if (lr == 0) {
+            if (mean_out) mean_out[row] = mean;
+            if (rstd_out) rstd_out[row] = rstd;
+        }
+    }
+}
+
+// dx = rstd * (g - mean_j(g) - xhat * mean_j(g * xhat)),  g = dy * gamma,  xhat = (x - mean) * rstd
+// part_g[blockIdx][F], part_b[blockIdx][F]: this CTA's sums over its rows of dy * xhat and dy
+template <int TPR, int SLOTS>
+__global__ void __launch_bounds__(LN_THREADS) ln_bwd_kernel(long long rows, int F4, const float4 *__restrict__ x,
+                                                            const float4 *__restrict__ dy, const float4 *__restrict__ gamma,
+                                                            const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
+                                                            float4 *__restrict__ dx, float4 *__restrict__ part_g,
+                                                            float4 *__restrict__ part_b)
+{
+    __shared__ float scratch[LN_THREADS / 32];
+    extern __shared__ float4 colsum[];                       // TPR == 32: [2][F4] CTA-level combine of the 8 warps
+    constexpr int RPC = LN_THREADS / TPR;
+    const int lr = threadIdx.x % TPR, grp = threadIdx.x / TPR;
+    const float inv_f = 1.0f / (float)(F4 * 4);
+    float4 ag[SLOTS], ab[SLOTS], gm[SLOTS];
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) {
+        ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = lr + k * TPR;
+        gm[k] = (gamma && c < F4) ? __ldg(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+    // every thread of a CTA must take the same number of trips when the row reduction uses __syncthreads
+    const long long trips = (rows + (long long)gridDim.x * RPC - 1) / ((long long)gridDim.x * RPC);
+    for (long long it = 0; it < trips; ++it) {
+        const long long row = (it * gridDim.x + blockIdx.x) * RPC + grp;
+        const bool live = row < rows;
+        const float mean = live ? mean_in[row] : 0.f, rstd = live ? rstd_in[row] : 0.f;
+        float4 xh[SLOTS], g[SLOTS];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) {
+            const int c = lr + k * TPR;
+            xh[k] = g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && c < F4) {
+                const uint4 xu = ldg_stream(reinterpret_cast<const uint4 *>(x + row * F4 + c));
+                const uint4 du = ldg_stream(reinterpret_cast<const uint4 *>(dy + row * F4 + c));
+                const float4 d = make_float4(__uint_as_float(du.x), __uint_as_float(du.y), __uint_as_float(du.z), __uint_as_float(du.w));
+                xh[k].x = (__uint_as_float(xu.x) - mean) * rstd; xh[k].y = (__uint_as_float(xu.y) - mean) * rstd;
+                xh[k].z = (__uint_as_float(xu.z) - mean) * rstd; xh[k].w = (__uint_as_float(xu.w) - mean) * rstd;
+                ag[k].x += d.x * xh[k].x; ag[k].y += d.y * xh[k].y; ag[k].z += d.z * xh[k].z; ag[k].w += d.w * xh[k].w;
+                ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
+                g[k].x = d.x * gm[k].x; g[k].y = d.y * gm[k].y; g[k].z = d.z * gm[k].z; g[k].w = d.w * gm[k].w;
+                s1 += (g[k].x + g[k].y) + (g[k].z + g[k].w);
+                s2 += (g[k].x * xh[k].x + g[k].y * xh[k].y) + (g[k].z * xh[k].z + g[k].w * xh[k].w);
+            }
+        }
+        const float m1 = row_sum<TPR>(s1, scratch) * inv_f;
+        const float m2 = row_sum<TPR>(s2, scratch) * inv_f;
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) {
+            const int c = lr + k * TPR;
+            if (live && c < F4) {
+                float4 o;
+                o.x = rstd * (g[k].x - m1 - xh[k].x * m2);
+                o.y = rstd * (g[k].y - m1 - xh[k].y * m2);
+                o.z = rstd * (g[k].z - m1 - xh[k].z * m2);
+                o.w = rstd * (g[k].w - m1 - xh[k].w * m2);
+                stg_stream(reinterpret_cast<uint4 *>(dx + row * F4 + c),
+                           make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
+            }
+        }
+    }
+    if (TPR == 32) {
+        // the CTA's 8 warps own the same columns: add them in warp order through shared memory (deterministic)
+        for (int w = 0; w < RPC; ++w) {
+            __syncthreads();
+            if (grp == w) {
+#pragma unroll
+                for (int k = 0; k < SLOTS; ++k) {
+                    const int c = lr + k * TPR;
+                    if (c < F4) {
+                        if (w == 0) { colsum[c] = ag[k]; colsum[F4 + c] = ab[k]; }
+                        else {
+                            float4 a = colsum[c], b = colsum[F4 + c];
+                            a.x += ag[k].x; a.y += ag[k].y; a.z += ag[k].z; a.w += ag[k].w;
+                            b.x += ab[k].x; b.y += ab[k].y; b.z += ab[k].z; b.w += ab[k].w;
+                            colsum[c] = a; colsum[F4 + c] = b;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < F4; c += LN_THREADS) {
+            part_g[(size_t)blockIdx.x * F4 + c] = colsum[c];
+            part_b[(size_t)blockIdx.x * F4 + c] = colsum[F4 + c];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) {
+            const int c = lr + k * TPR;
+            if (c < F4) {
+                part_g[(size_t)blockIdx.x * F4 + c] = ag[k];
+                part_b[(size_t)blockIdx.x * F4 + c] = ab[k];
+            }
+        }
+    }
+}
+
+// dgamma[c] = sum_b part_g[b][c], dbeta likewise (fixed order)
+__global__ void __launch_bounds__(256) ln_colreduce_kernel(int nblocks, int F, const float *__restrict__ part_g,
+                                                           const float *__restrict__ part_b, float *__restrict__ dgamma,
+                                                           float *__restrict__ dbeta)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= F) return;
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < nblocks; ++k) {
+        a += part_g[(size_t)k * F + c];
+        b += part_b[(size_t)k * F + c];
+    }
+    if (dgamma) dgamma[c] = a;
+    if (dbeta) dbeta[c] = b;
+}
+
+int ln_grid(long long rows, int rpc)
+{
+    long long nb = (rows + rpc - 1) / rpc;
+    const long long cap = (long long)pb_sm_count() * 4;
+    if (nb > cap) nb = cap;
+    return (int)(nb < 1 ? 1 : nb);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pb_layer_norm_supported(long long rows, int F) { return (rows > 0 && F >= 4 && (F % 4) == 0 && F <= 4096) ? 1 : 0; }
+
+int pb_layer_norm_bwd_blocks(long long rows, int F) { return ln_grid(rows, F <= 1024 ? LN_THREADS / 32 : 1); }
+
+int pb_layer_norm_fwd(long long rows, int F, float eps, const float *x, const float *gamma, const float *beta, float *y,
+                      float *mean_out, float *rstd_out, void *stream)
+{
+    if (!pb_layer_norm_supported(rows, F) || !x || !y) return PB_E_ARG;
+    if ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)gamma) | ((uintptr_t)beta)) & 15) return PB_E_ARG;
+    const int F4 = F / 4;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x), *g4 = reinterpret_cast<const float4 *>(gamma),
+                 *b4 = reinterpret_cast<const float4 *>(beta);
+    float4 *y4 = reinterpret_cast<float4 *>(y);
+    if (F <= 512) {
+        const int nb = (int)((rows + 7) / 8);
+        PB_LAUNCH((ln_fwd_kernel<32, 4>), nb, LN_THREADS, 0, stream, rows, F4, eps, x4, g4, b4, y4, mean_out, rstd_out);
+    } else if (F <= 1024) {
+        const int nb = (int)((rows + 7) / 8);
+        PB_LAUNCH((ln_fwd_kernel<32, 8>), nb, LN_THREADS, 0, stream, rows, F4, eps, x4, g4, b4, y4, mean_out, rstd_out);
+    } else {
+        long long nb = rows;
+        if (nb > (1LL << 30)) return PB_E_ARG;
+        PB_LAUNCH((ln_fwd_kernel<256, 4>), (unsigned)nb, LN_THREADS, 0, stream, rows, F4, eps, x4, g4, b4, y4, mean_out, rstd_out);
+    }
+    return PB_OK;
+}
+
+// partials: 2 * pb_layer_norm_bwd_blocks(rows, F) * F floats of scratch
+int pb_layer_norm_bwd(long long rows, int F, const float *x, const float *dy, const float *gamma, const float *mean,
+                      const float *rstd, float *dx, float *dgamma, float *dbeta, float *partials, void *stream)
+{
+    if (!pb_layer_norm_supported(rows, F) || !x || !dy || !mean || !rstd || !dx || !partials) return PB_E_ARG;
+    if ((((uintptr_t)x) | ((uintptr_t)dy) | ((uintptr_t)dx) | ((uintptr_t)gamma) | ((uintptr_t)partials)) & 15) return PB_E_ARG;
+    const int F4 = F / 4;
+    const int nb = pb_layer_norm_bwd_blocks(rows, F);
+    const float4 *x4 = reinterpret_cast<const float4 *>(x), *d4 = reinterpret_cast<const float4 *>(dy),
+                 *g4 = reinterpret_cast<const float4 *>(gamma);
+    float4 *dx4 = reinterpret_cast<float4 *>(dx), *pg = reinterpret_cast<float4 *>(partials),
+           *pbeta = reinterpret_cast<float4 *>(partials + (size_t)nb * F);
+    if (F <= 512) {
+        PB_LAUNCH((ln_bwd_kernel<32, 4>), nb, LN_THREADS, 2 * F * sizeof(float), stream, rows, F4, x4, d4, g4, mean, rstd, dx4, pg, pbeta);
+    } else if (F <= 1024) {
+        PB_LAUNCH((ln_bwd_kernel<32, 8>), nb, LN_THREADS, 2 * F * sizeof(float), stream, rows, F4, x4, d4, g4, mean, rstd, dx4, pg, pbeta);
+    } else {
+        PB_LAUNCH((ln_bwd_kernel<256, 4>), nb, LN_THREADS, 0, stream, rows, F4, x4, d4, g4, mean, rstd, dx4, pg, pbeta);
+    }
+    if (dgamma || dbeta)
+        PB_LAUNCH(ln_colreduce_kernel, (F + 255) / 256, 256, 0, stream, nb, F, partials, partials + (size_t)nb * F, dgamma, dbeta);
+    return PB_OK;
+}
+
+}  // extern "C"

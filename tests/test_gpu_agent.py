@@ -431,3 +431,37 @@ def test_phi_times_x_matches_fp64(n, B, F_, J):
     assert rel_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 1e-4
     assert rel_err(seq[0].weight.grad.cpu().numpy(), wr.grad.numpy()) < 1e-4
     assert rel_err(seq[0].bias.grad.cpu().numpy(), br.grad.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("rows,F_", [(2048, 3136), (4100, 512), (1111, 1024), (513, 2052)])
+def test_fused_layer_norm_matches_fp64(rows, F_):
+    """csrc/ln.cu forward + single-pass backward against fp64 autograd of nn.LayerNorm (ffnn_model.py:17-18)."""
+    import torch.nn as nn
+    from prism_b200.agents import ops
+    g = torch.Generator().manual_seed(rows + F_)
+    x = torch.randn(rows, F_, generator=g) * 2.0 + 0.7
+    gy = torch.randn(rows, F_, generator=g)
+    ln = nn.LayerNorm(F_).to(DEV)
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(F_, generator=g))
+        ln.bias.copy_(torch.randn(F_, generator=g))
+    xd = x.to(DEV).requires_grad_(True)
+    old = ops.LN_MIN_ELEMENTS
+    ops.LN_MIN_ELEMENTS = 0
+    try:
+        y = ops.layer_norm(xd, ln)
+        assert "LayerNorm" in type(y.grad_fn).__name__ and "Native" not in type(y.grad_fn).__name__
+        y.backward(gy.to(DEV))
+    finally:
+        ops.LN_MIN_ELEMENTS = old
+    ref = nn.LayerNorm(F_).double()
+    with torch.no_grad():
+        ref.weight.copy_(ln.weight.cpu().double())
+        ref.bias.copy_(ln.bias.cpu().double())
+    xr = x.double().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(gy.double())
+    assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) < 1e-5
+    assert rel_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 1e-5
+    assert rel_err(ln.weight.grad.cpu().numpy(), ref.weight.grad.numpy()) < 1e-5
+    assert rel_err(ln.bias.grad.cpu().numpy(), ref.bias.grad.numpy()) < 1e-5
