@@ -576,18 +576,18 @@ def run_ours(args):
     pre_u = rng.random((n_pre, step.B_global))
     u_hosts = [torch.empty(step.B_global, dtype=torch.float64).pin_memory() for _ in range(2)]
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-    push = buf.ingest_graph(STEPS_PER_ITER)
     tick = [0]
 
     def e2e_one():
+        # one call of the public API per iteration: the new steps (host arrays) are staged in pinned memory, copied and
+        # scattered inside the step graph (FusedIngest); uniforms go up, the loss comes back
         i = tick[0]
         tick[0] += 1
         sl = slice(i * STEPS_PER_ITER, (i + 1) * STEPS_PER_ITER)
-        push(pre["stream"][sl], pre["obs"][sl], pre["action"][sl], pre["reward"][sl], pre["done"][sl],
-             pre["trunc"][sl], pre["next_obs"][sl])
         u_host = u_hosts[i & 1]             # double-buffered: the previous step's async H2D may still be queued
         u_host.numpy()[:] = pre_u[i]
-        total = step.step(u=u_host)
+        total = step.step(u=u_host, ingest=(pre["stream"][sl], pre["obs"][sl], pre["action"][sl], pre["reward"][sl],
+                                            pre["done"][sl], pre["trunc"][sl], pre["next_obs"][sl]))
         loss_host.copy_(total.detach(), non_blocking=True)
     for _ in range(max(3, args.warmup)):
         e2e_one()
@@ -607,7 +607,7 @@ def run_ours(args):
         t = torch.tensor([e2e_sec], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_sec = float(t.item())
-    h2d = push.h2d_bytes + step.B_global * 8
+    h2d = step.ingest.h2d_bytes + step.B_global * 8
     e2e = {"value": BATCH * world * e2e_steps / e2e_sec, "unit": "transitions/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": 4, "updates_per_s": e2e_steps / e2e_sec,
            "host_wall_s": round(wall, 4), "loss": float(loss_host)}

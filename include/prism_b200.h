@@ -209,6 +209,12 @@ int pb_store_extend_plan(long long size, long long aux_size, int n_streams, long
  * meta the device copy of the planned pb_step_meta array. */
 int pb_store_scatter(const pb_store *s, long long n, const void *obs, const void *next_obs,
                      const pb_step_meta *meta, void *stream);
+/* Same scatter for an ingest fused into a replayed CUDA graph: two staging blocks (A, B) with frozen addresses; the
+ * block of this replay is chosen on the device by the parity of *replay_counter (even: A), which the call then
+ * increments -- the host fills and copies the other block for the next replay meanwhile. */
+int pb_store_scatter_dbuf(const pb_store *st, long long n, const void *obs_a, const void *next_obs_a,
+                          const pb_step_meta *meta_a, const void *obs_b, const void *next_obs_b,
+                          const pb_step_meta *meta_b, long long *replay_counter, void *stream);
 
 /* TimestepBuffer._timesteps_to_batch + _compute_n_step + _stack_obs_into
  * (prism/experience/timestep_buffer.py:79-257) fused: for each sampled slot walk

@@ -111,10 +111,7 @@ class CompositeModel(nn.Module):
         return dist_loss, q_loss, td
 
     def _side_streams(self, device):
-        ss = getattr(self, "_streams", None)
-        if ss is None:
-            ss = self._streams = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
-        return ss
+        return ops.fork_stream(device, "boot1"), ops.fork_stream(device, "boot2")
 
     def losses_total(self, batch, target_model, per_weights=None):
         """get_losses + the PER-weighted total of Agent.update (agent.py:58-64) as one fused head:

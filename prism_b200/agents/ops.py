@@ -154,11 +154,22 @@ PARALLEL_BACKWARD = __import__('os').environ.get('PB_PARALLEL_BACKWARD', '1') !=
 _SIDE_STREAMS = {}
 
 
-def _side_stream(device):
-    s = _SIDE_STREAMS.get(device)
+SERIAL_GRAPH = __import__('os').environ.get('PB_SERIAL_GRAPH', '0') == '1'   # tuning switch: no parallel branches at all
+
+
+def fork_stream(device, key="bwd"):
+    """A cached side stream (a parallel branch under CUDA-graph capture); the current stream when PB_SERIAL_GRAPH=1."""
+    device = torch.device(device)
+    if SERIAL_GRAPH:
+        return torch.cuda.current_stream(device)
+    s = _SIDE_STREAMS.get((device, key))
     if s is None:
-        s = _SIDE_STREAMS[device] = torch.cuda.Stream(device=device)
+        s = _SIDE_STREAMS[(device, key)] = torch.cuda.Stream(device=device)
     return s
+
+
+def _side_stream(device):
+    return fork_stream(device, "bwd")
 
 
 class _Linear(torch.autograd.Function):

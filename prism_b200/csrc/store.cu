@@ -93,6 +93,41 @@ __global__ void __launch_bounds__(128) store_scatter_kernel(StoreView s, long lo
     }
 }
 
+// Double-buffered variant for an ingest that is fused into a replayed CUDA graph: the graph's kernel arguments are
+// frozen, so the staging block in use is picked on the device from the parity of a replay counter (block A on even
+// replays, B on odd ones) while the host fills / copies the other block for the next replay.
+__global__ void __launch_bounds__(128) store_scatter_dbuf_kernel(StoreView s, long long n, const uint8_t *obs_a,
+                                                                 const uint8_t *next_a, const pb_step_meta *meta_a,
+                                                                 const uint8_t *obs_b, const uint8_t *next_b,
+                                                                 const pb_step_meta *meta_b, const long long *counter)
+{
+    const bool odd = (*counter) & 1;
+    const uint8_t *obs = odd ? obs_b : obs_a, *next_obs = odd ? next_b : next_a;
+    const pb_step_meta *meta = odd ? meta_b : meta_a;
+    const long long j = blockIdx.x;
+    const pb_step_meta m = meta[j];
+    const long long slot = m.seq % s.size;
+    if (blockIdx.y == 0) {
+        copy_row_bytes(s.obs_w + slot * s.row_bytes, obs + j * s.row_bytes, s.row_bytes);
+        if (threadIdx.x == 0) {
+            s.action[slot] = m.action;
+            s.reward[slot] = m.reward;
+            s.done[slot] = m.done;
+            s.trunc[slot] = m.trunc;
+            s.slot_seq[slot] = m.seq;
+            s.prev_link[slot] = m.prev_link;
+            s.next_link[slot] = m.next_link;
+            if (m.patch_slot >= 0) s.next_link[m.patch_slot] = m.patch_val;
+        }
+    } else {
+        const long long row = m.aux_row;
+        if (row >= 0 && row < s.aux_size && next_obs)
+            copy_row_bytes(s.aux_w + row * s.row_bytes, next_obs + j * s.row_bytes, s.row_bytes);
+    }
+}
+
+__global__ void counter_inc_kernel(long long *counter) { *counter += 1; }
+
 // ---- n-step walk (uniform across the CTA: every thread reads the same addresses) ----
 struct Walk {
     float ret, gamma;
@@ -317,6 +352,21 @@ int pb_store_scatter(const pb_store *st, long long n, const void *obs, const voi
     if (!obs || !meta) return PB_E_ARG;
     dim3 grid((unsigned)n, 2);
     PB_LAUNCH(store_scatter_kernel, grid, 128, 0, stream, v, n, (const uint8_t *)obs, (const uint8_t *)next_obs, meta);
+    return PB_OK;
+}
+
+int pb_store_scatter_dbuf(const pb_store *st, long long n, const void *obs_a, const void *next_obs_a,
+                          const pb_step_meta *meta_a, const void *obs_b, const void *next_obs_b,
+                          const pb_step_meta *meta_b, long long *replay_counter, void *stream)
+{
+    StoreView v;
+    int rc = make_store(st, &v);
+    if (rc) return rc;
+    if (n <= 0 || n > v.size || !obs_a || !meta_a || !obs_b || !meta_b || !replay_counter) return PB_E_ARG;
+    dim3 grid((unsigned)n, 2);
+    PB_LAUNCH(store_scatter_dbuf_kernel, grid, 128, 0, stream, v, n, (const uint8_t *)obs_a, (const uint8_t *)next_obs_a,
+              meta_a, (const uint8_t *)obs_b, (const uint8_t *)next_obs_b, meta_b, (const long long *)replay_counter);
+    PB_LAUNCH(counter_inc_kernel, 1, 1, 0, stream, replay_counter);
     return PB_OK;
 }
 

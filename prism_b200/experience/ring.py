@@ -304,3 +304,59 @@ class IngestSlot:
         self.d_block.copy_(self.h_block, non_blocking=True)
         _lib.check(ring._lib.pb_store_scatter(ring._ref, self.n, self.d_rows[0].data_ptr(), self.d_rows[1].data_ptr(),
                                               self.d_meta.data_ptr(), ring._stream()), "pb_store_scatter")
+
+
+class FusedIngest:
+    """A fixed-size ingest (n steps per learner iteration) whose device half runs INSIDE the learner's step graph,
+    on the branch that follows the priority write-back, i.e. concurrently with backward / Adam -- the reference
+    interleaves `timesteps_per_iteration` new steps with every update (learner.py:95-125, collector drain) and pays
+    for them on the same thread.
+
+    Two staging blocks (pinned + device).  Host side, per iteration (``stage``): wait until the pinned block of this
+    parity is free, write it, run the link planner, and enqueue its H2D copy on a copy stream (ordered after the
+    graph replay that last read the device block).  Device side (``consume``, captured): the scatter kernel picks the
+    block by the parity of a device-resident replay counter, then the trees get the default priorities.
+    Steps staged before iteration k's launch become sampleable from iteration k+1 on."""
+
+    def __init__(self, ring, tree, n):
+        self.ring, self.tree, self.n = ring, tree, int(n)
+        self.slots = [IngestSlot(ring, n), IngestSlot(ring, n)]
+        dev = ring.device
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copied = [None, None]        # event: H2D of block p finished (pinned block reusable, device block valid)
+        self.consumed = [None, None]      # event: the replay that read device block p finished
+        self.calls = 0
+        self.h2d_bytes = self.slots[0].h2d_bytes
+
+    def stage(self, stream_ids, obs, action, reward, done, trunc, next_obs):
+        """Host half.  Returns the event the consuming replay must wait for."""
+        p = self.calls & 1
+        self.calls += 1
+        slot = self.slots[p]
+        if self.copied[p] is not None:
+            self.copied[p].synchronize()                      # pinned block free again (two iterations old)
+        slot.fill(stream_ids, obs, action, reward, done, trunc, next_obs)
+        if self.consumed[p] is not None:
+            self.copy_stream.wait_event(self.consumed[p])     # device block p was read by replay k-2
+        with torch.cuda.stream(self.copy_stream):
+            slot.d_block.copy_(slot.h_block, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.copied[p] = ev
+        return ev, p
+
+    def mark_consumed(self, p):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.ring.device))
+        self.consumed[p] = ev
+
+    def consume(self):
+        """Device half (capturable): scatter from the block of this replay's parity, then default priorities."""
+        ring, a, b = self.ring, self.slots[0], self.slots[1]
+        _lib.check(ring._lib.pb_store_scatter_dbuf(ring._ref, self.n, a.d_rows[0].data_ptr(), a.d_rows[1].data_ptr(),
+                                                   a.d_meta.data_ptr(), b.d_rows[0].data_ptr(), b.d_rows[1].data_ptr(),
+                                                   b.d_meta.data_ptr(), self.counter.data_ptr(), ring._stream()),
+                   "pb_store_scatter_dbuf")
+        if self.tree is not None:
+            self.tree.extend(self.n)

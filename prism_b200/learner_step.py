@@ -35,6 +35,8 @@ class LearnerStep:
         self.world_size, self.rank, self.pg = int(world_size), int(rank), process_group
         self.use_cuda_graph = use_cuda_graph
         self.graph = None
+        self._graph_key = None
+        self.ingest = None
         d = self.device
         if self.world_size > 1:
             if self.world_size & (self.world_size - 1):
@@ -86,12 +88,12 @@ class LearnerStep:
                 opt.allreduce = lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
             self.exchange = "peer" if self.peer is not None else "nccl"
         self.launches_per_step = None
-        self._side = torch.cuda.Stream(device=d)
+        self._side = None
         import os as _os
         self.overlap_write_back = _os.environ.get("PB_OVERLAP_WRITEBACK", "1") != "0"
 
     # ------------------------------------------------------------------------------------
-    def _body(self, refresh_table, draw):
+    def _body(self, refresh_table, draw, consume=False):
         tree, ring, agent, b = self.tree, self.ring, self.agent, self.buffer
         u = None if draw else self.u            # None: uniforms are drawn inside the sampling kernel
         if self.world_size > 1:
@@ -110,6 +112,8 @@ class LearnerStep:
         # The priority write-back (learner.py:120) needs the new TD errors only, not the optimizer step: it runs on
         # a second stream -- a parallel branch of the captured graph -- while backward / (exchange) / Adam proceed.
         cur = torch.cuda.current_stream(self.device)
+        from .agents import ops as _ops
+        self._side = _ops.fork_stream(self.device, "writeback")
 
         def write_back(td):
             self.td = td
@@ -118,6 +122,8 @@ class LearnerStep:
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
                 tree.update_priority(idx, td, sorted=self.sorted)      # |td| is taken inside the kernel
+                if consume:
+                    self.ingest.consume()      # next iteration's new steps: scatter + default priorities, same branch
 
         dl, ql, total, td = agent._loss_and_backward(self.batch, w, agent.target_model, after_loss=write_back)
         agent._static_distribution_loss, agent._static_q_loss, agent._static_total_loss = dl, ql, total
@@ -126,26 +132,41 @@ class LearnerStep:
             cur.wait_stream(self._side)
         else:
             tree.update_priority(idx, self.td, sorted=self.sorted)
+            if consume:
+                self.ingest.consume()
         return total
 
-    def step(self, u=None):
+    def step(self, u=None, ingest=None):
         """Run one iteration.  ``u`` (optional): fp64 uniforms (device or pinned-host tensor, B_global
-        values) used instead of the device Philox generator."""
+        values) used instead of the device Philox generator.  ``ingest`` (optional): a tuple
+        (stream_ids, obs, action, reward, done, trunc, next_obs) of a FIXED number of new steps per call; their
+        scatter into the ring and default priorities run inside the step graph, after the priority write-back and
+        concurrently with backward / Adam (FusedIngest); they are sampleable from the next iteration on."""
         self.buffer._flush()
         draw = u is None
         if not draw:
             self.u.copy_(u, non_blocking=True)
+        consume, parity = ingest is not None, None
+        if consume:
+            n = len(ingest[0])
+            if self.ingest is None or self.ingest.n != n:
+                from .experience.ring import FusedIngest
+                self.ingest = FusedIngest(self.ring, self.tree, n)
+            copied, parity = self.ingest.stage(*ingest)
+            torch.cuda.current_stream(self.device).wait_event(copied)
         if not self.use_cuda_graph:
-            total = self._body(refresh_table=True, draw=draw)
-            self.agent.n_updates += 1
-            return total
-        if self.graph is None or draw != self._graph_draws:
-            self._capture(draw)
-        self.graph.replay()
+            total = self._body(refresh_table=True, draw=draw, consume=consume)
+        else:
+            if self.graph is None or (draw, consume) != self._graph_key:
+                self._capture(draw, consume)
+            self.graph.replay()
+            total = self.agent._static_total_loss
+        if consume:
+            self.ingest.mark_consumed(parity)
         self.agent.n_updates += 1
-        return self.agent._static_total_loss
+        return total
 
-    def _capture(self, draw):
+    def _capture(self, draw, consume=False):
         opt = self.agent.optimizer
         flat = isinstance(opt, FlatAdam)
         # drop every reference to autograd graphs built on another stream (an eager update leaves its
@@ -170,12 +191,13 @@ class LearnerStep:
         self.tree.sum.copy_(tree_snap[0]); self.tree.min.copy_(tree_snap[1]); self.tree.state.copy_(tree_snap[2])
         self.u.copy_(u_snap)
         torch.cuda.set_rng_state(rng, self.device)
-        self._graph_draws = draw
+        self._graph_key = (draw, consume)
         opt.zero_grad(set_to_none=True)
+        self.graph = None                                   # release the previous graph's pool before capturing anew
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
         with torch.cuda.graph(self.graph):
-            self._body(refresh_table=False, draw=draw)
+            self._body(refresh_table=False, draw=draw, consume=consume)
         self.launches_per_step = _lib.launch_count() - before
         if flat:
             opt.refresh_grad_table()

@@ -1,0 +1,30 @@
+import sys, time, os
+sys.path.insert(0, "/root/repo")
+import numpy as np, torch
+import bench
+from prism_b200.learner_step import LearnerStep
+dev = "cuda:0"
+cfg, agent, buf, trace, _ = bench.build_ours(0, 1, dev, 1 << 18, 1 << 18, seed=4)
+step = LearnerStep(buf, agent, batch_size=256, use_cuda_graph=True)
+for _ in range(5): step.step()
+torch.cuda.synchronize()
+N = 3000
+pre = trace.chunk((N + 10) * 4)
+push = buf.ingest_graph(4)
+u_host = torch.empty(256, dtype=torch.float64).pin_memory()
+loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+def do_push(i):
+    sl = slice(i * 4, (i + 1) * 4)
+    push(pre["stream"][sl], pre["obs"][sl], pre["action"][sl], pre["reward"][sl], pre["done"][sl], pre["trunc"][sl], pre["next_obs"][sl])
+for name, fn in [("push only", lambda i: do_push(i)),
+                 ("step(u) only", lambda i: step.step(u=u_host)),
+                 ("step() only", lambda i: step.step()),
+                 ("push+step(u)+loss copy", lambda i: (do_push(i), loss_host.copy_(step.step(u=u_host).detach(), non_blocking=True)))]:
+    for i in range(5): fn(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(N): fn(i)
+    t_host = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    print("%-28s host issue %.1f us/iter   incl. GPU drain %.1f us/iter" % (name, t_host / N * 1e6, t_all / N * 1e6))

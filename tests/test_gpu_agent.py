@@ -465,3 +465,51 @@ def test_fused_layer_norm_matches_fp64(rows, F_):
     assert rel_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 1e-5
     assert rel_err(ln.weight.grad.cpu().numpy(), ref.weight.grad.numpy()) < 1e-5
     assert rel_err(ln.bias.grad.cpu().numpy(), ref.bias.grad.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_fused_ingest_step_equals_separate_push_then_step(use_graph):
+    """LearnerStep.step(ingest=...) scatters the new steps inside the step graph (after the priority write-back,
+    concurrently with backward) from double-buffered staging blocks.  Same uniforms, same data: it must produce the
+    same losses, parameters, ring and trees as `step(); push(new steps)` run one after the other."""
+    import prism_b200
+    from prism_b200.learner_step import LearnerStep
+    from oracle.gen_golden import make_script
+    cap, B, obs_shape, A, n_new, iters = 256, 16, (10, 10, 6), 4, 4, 9
+    S = make_script(5, n_streams=4, n_steps=200 + n_new * iters, obs_shape=obs_shape, p_done=0.05, p_trunc=0.03, n_actions=A)
+    succ = np.where(S["trunc"][:, None], S["final_obs"], S["next_obs"])
+    rng = np.random.default_rng(11)
+    us = rng.random((iters, B))
+
+    def run(fused):
+        cfg = prism_b200.minatar_dqn_per_config(device=DEV, experience_replay_capacity=cap, batch_size=B,
+                                                per_sampling="stratified", replay_max_streams=4, replay_staging_rows=64,
+                                                use_cuda_graph=False)
+        torch.manual_seed(0)
+        agent = prism_b200.build_agent(cfg, obs_shape, A)
+        buf = prism_b200.build_exp_buffer(cfg)
+        buf.extend_batch(S["stream"][:200], S["obs"][:200].reshape((-1,) + obs_shape), S["action"][:200], S["reward"][:200],
+                         S["done"][:200], S["trunc"][:200], succ[:200].reshape((-1,) + obs_shape))
+        step = LearnerStep(buf, agent, batch_size=B, use_cuda_graph=use_graph)
+        push = None if fused else buf.ingest_graph(n_new)
+        losses = []
+        for i in range(iters):
+            sl = slice(200 + i * n_new, 200 + (i + 1) * n_new)
+            new = (S["stream"][sl], S["obs"][sl], S["action"][sl], S["reward"][sl], S["done"][sl], S["trunc"][sl], succ[sl])
+            u = torch.from_numpy(us[i]).to(DEV)
+            if fused:
+                losses.append(float(step.step(u=u, ingest=new)))
+            else:
+                losses.append(float(step.step(u=u)))
+                push(*new)
+        torch.cuda.synchronize()
+        tree, ring = buf.buffer._sampler, buf.buffer._storage
+        return (losses, agent.optimizer.arena.clone(), tree.sum.clone(), tree.min.clone(), tree.state_host(),
+                ring.obs.clone(), ring.next_link.clone())
+
+    a, b = run(True), run(False)
+    assert a[0] == b[0]
+    assert torch.equal(a[1], b[1])
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert a[4] == b[4]
+    assert torch.equal(a[5], b[5]) and torch.equal(a[6], b[6])
