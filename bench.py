@@ -521,7 +521,9 @@ def run_ours(args):
         dist.broadcast(agent.optimizer.arena, src=0)
         if agent.target_model is not None:
             dist.broadcast(agent.target_model._flat_arena, src=0)
-    step = LearnerStep(buf, agent, batch_size=BATCH, use_cuda_graph=True, process_group=pg, rank=rank, world_size=world)
+    prefetch = os.environ.get("PB_PREFETCH", "1") != "0"
+    step = LearnerStep(buf, agent, batch_size=BATCH, use_cuda_graph=True, process_group=pg, rank=rank, world_size=world,
+                       prefetch=prefetch)
 
     def barrier():
         if world > 1:
@@ -543,7 +545,7 @@ def run_ours(args):
         graph_ok = False
         sys.stderr.write("graph capture failed (%r); running the step eagerly\n" % (e,))
         step = LearnerStep(buf, agent, batch_size=BATCH, use_cuda_graph=False, process_group=pg, rank=rank,
-                           world_size=world)
+                           world_size=world, prefetch=prefetch)
         for _ in range(max(3, args.warmup)):
             step.step()
     barrier()

@@ -168,6 +168,7 @@ class TimestepBuffer(object):
         n = ring.flush()
         if self.buffer._sampler is not None:
             self.buffer._sampler.extend(n)
+        self._mutations = getattr(self, "_mutations", 0) + 1      # LearnerStep(prefetch=True) re-samples after outside changes
         return n
 
     # ------------------------------------------------------------------ sampling
@@ -216,6 +217,7 @@ class TimestepBuffer(object):
         if self.buffer._sampler is None:
             return
         self._flush()
+        self._mutations = getattr(self, "_mutations", 0) + 1
         sorted_hint = self._last_sorted and isinstance(indices, torch.Tensor) and self._idx is not None \
             and indices.data_ptr() == self._idx.data_ptr()
         self.buffer._sampler.update_priority(indices, priorities, sorted=sorted_hint)
@@ -327,6 +329,7 @@ class _IngestGraph:
         if self.done is not None:
             self.done.synchronize()          # the previous replay has consumed the pinned block
         self.slot.fill(stream_ids, obs, action, reward, done, trunc, next_obs)
+        self.buffer._mutations = getattr(self.buffer, "_mutations", 0) + 1
         self.graph.replay()
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.ring.device))

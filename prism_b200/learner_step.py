@@ -24,7 +24,7 @@ from .experience.per import PrioritizedTree
 
 class LearnerStep:
     def __init__(self, buffer, agent, batch_size=None, use_cuda_graph=True, process_group=None,
-                 rank=0, world_size=1, pad_slack=None, exchange=None):
+                 rank=0, world_size=1, pad_slack=None, exchange=None, prefetch=False):
         self.buffer, self.agent = buffer, agent
         self.tree = buffer.buffer._sampler
         self.ring = buffer.buffer._storage
@@ -51,15 +51,34 @@ class LearnerStep:
             self.B_global = self.B_pad = self.B
             n_rows = self.B
         self.u = torch.empty(self.B_global, dtype=torch.float64, device=d)
-        self.idx = torch.zeros(n_rows, dtype=torch.int64, device=d)
-        self.weight = torch.zeros(n_rows, dtype=torch.float32, device=d)
         self.td = None
         self.sorted = self.world_size > 1 or self.tree.mode == PrioritizedTree.MODE_STRATIFIED
+        self.prefetch = bool(prefetch)
+        self._primed, self._seen_mutations = False, None
         # static batch, shared by the buffer (writes) and the agent (reads)
         buffer._flush()
-        if buffer._batch is None or buffer._obs.shape[0] != self.B_pad:
-            buffer._batch = None
-            buffer._alloc_static_batch(self.B_pad, self.ring)
+        if self.prefetch:
+            # Software pipelining: the NEXT iteration's batch is sampled and gathered on the tail branch of this
+            # iteration (after the priority write-back and the fused ingest, i.e. exactly where the reference order
+            # puts it) into a shadow copy of the static batch, while backward / exchange / Adam run; the next
+            # replay starts with one copy shadow -> live.  Live and shadow are two flat arenas of identical layout.
+            from .experience.batch import Batch
+            self._live, self._live_arena = self._carve(n_rows)
+            self._shadow, self._shadow_arena = self._carve(n_rows)
+            lv = self._live
+            batch = Batch({"observation": lv["obs"],
+                           "next": Batch({"observation": lv["next_obs"], "reward": lv["reward"]},
+                                         batch_size=self.B_pad, device=d),
+                           "nonterminal": lv["nonterminal"], "gamma": lv["gamma"], "action": lv["action"]},
+                          batch_size=self.B_pad, device=d)
+            buffer.set_static_batch(batch)
+            self.idx, self.weight = lv["idx"], lv["weight"]
+        else:
+            self.idx = torch.zeros(n_rows, dtype=torch.int64, device=d)
+            self.weight = torch.zeros(n_rows, dtype=torch.float32, device=d)
+            if buffer._batch is None or buffer._obs.shape[0] != self.B_pad:
+                buffer._batch = None
+                buffer._alloc_static_batch(self.B_pad, self.ring)
         self.batch = buffer.get_static_batch()
         agent.set_static_batch(self.batch)
         opt = agent.optimizer
@@ -93,9 +112,33 @@ class LearnerStep:
         self.overlap_write_back = _os.environ.get("PB_OVERLAP_WRITEBACK", "1") != "0"
 
     # ------------------------------------------------------------------------------------
-    def _body(self, refresh_table, draw, consume=False):
-        tree, ring, agent, b = self.tree, self.ring, self.agent, self.buffer
-        u = None if draw else self.u            # None: uniforms are drawn inside the sampling kernel
+    def _carve(self, n_rows):
+        """One flat arena holding a static batch + the sampled indices / weights; returns (views, arena)."""
+        import numpy as np
+        d, B = self.device, self.B_pad
+        E = self.buffer.frame_stack * int(np.prod(self.ring.obs_shape))
+        spec = [("obs", B * E, torch.float32), ("next_obs", B * E, torch.float32), ("reward", B, torch.float32),
+                ("gamma", B, torch.float32), ("nonterminal", B, torch.bool), ("action", B, torch.int64),
+                ("idx", n_rows, torch.int64), ("weight", n_rows, torch.float32)]
+        offs, off = {}, 0
+        for name, n, dt in spec:
+            offs[name] = off
+            off += (n * torch.empty(0, dtype=dt).element_size() + 255) // 256 * 256
+        arena = torch.zeros(off, dtype=torch.uint8, device=d)
+        v = {}
+        for name, n, dt in spec:
+            nbytes = n * torch.empty(0, dtype=dt).element_size()
+            v[name] = arena[offs[name]:offs[name] + nbytes].view(dt)
+        fs, shp = self.buffer.frame_stack, tuple(self.ring.obs_shape)
+        v["obs"], v["next_obs"] = v["obs"].view(B, fs, *shp), v["next_obs"].view(B, fs, *shp)
+        for k in ("reward", "gamma", "nonterminal", "action"):
+            v[k] = v[k].view(B, 1)
+        v["gamma"].fill_(1.0)
+        return v, arena
+
+    def _sample_gather(self, u, out):
+        """(all-gather of shard states +) sample + fused n-step gather into ``out`` (live or shadow views)."""
+        tree, ring = self.tree, self.ring
         if self.world_size > 1:
             if self.peer is not None:
                 self.peer.state_allgather(tree.state)
@@ -103,12 +146,30 @@ class LearnerStep:
                 import torch.distributed as dist
                 dist.all_gather_into_tensor(self.all_state.view(-1), tree.state, group=self.pg)
             tree.sample_global(self.world_size, self.rank, self.all_state, self.B_global, u,
-                               idx_out=self.idx, weight_out=self.weight, stratum_out=self.stratum)
+                               idx_out=out["idx"], weight_out=out["weight"], stratum_out=self.stratum)
         else:
-            tree.sample(self.B, u=u, idx_out=self.idx, weight_out=self.weight)
+            tree.sample(self.B, u=u, idx_out=out["idx"], weight_out=out["weight"])
         # rows past the strata this rank owns have idx -1 / weight 0: skipped by gather and update
+        ring.gather(out["idx"][:self.B_pad], out["obs"], out["next_obs"], out["reward"], out["gamma"],
+                    out["nonterminal"], out["action"])
+
+    def _prime(self):
+        """Fill the shadow batch eagerly (first iteration, or after anything outside this object touched the
+        buffer): uniforms from the in-kernel generator."""
+        self._sample_gather(None, self._shadow)
+        self._primed = True
+        self._seen_mutations = getattr(self.buffer, "_mutations", 0)
+
+    def _body(self, refresh_table, draw, consume=False):
+        tree, ring, agent, b = self.tree, self.ring, self.agent, self.buffer
+        u = None if draw else self.u            # None: uniforms are drawn inside the sampling kernel
+        if self.prefetch:
+            self._live_arena.copy_(self._shadow_arena)          # batch sampled on the previous iteration's tail
+        else:
+            self._sample_gather(u, {"idx": self.idx, "weight": self.weight, "obs": b._obs, "next_obs": b._next_obs,
+                                    "reward": b._reward, "gamma": b._gamma, "nonterminal": b._nonterminal,
+                                    "action": b._action})
         idx, w = self.idx[:self.B_pad], self.weight[:self.B_pad]
-        ring.gather(idx, b._obs, b._next_obs, b._reward, b._gamma, b._nonterminal, b._action)
         # The priority write-back (learner.py:120) needs the new TD errors only, not the optimizer step: it runs on
         # a second stream -- a parallel branch of the captured graph -- while backward / (exchange) / Adam proceed.
         cur = torch.cuda.current_stream(self.device)
@@ -124,6 +185,8 @@ class LearnerStep:
                 tree.update_priority(idx, td, sorted=self.sorted)      # |td| is taken inside the kernel
                 if consume:
                     self.ingest.consume()      # next iteration's new steps: scatter + default priorities, same branch
+                if self.prefetch:
+                    self._sample_gather(u, self._shadow)      # next iteration's batch
 
         dl, ql, total, td = agent._loss_and_backward(self.batch, w, agent.target_model, after_loss=write_back)
         agent._static_distribution_loss, agent._static_q_loss, agent._static_total_loss = dl, ql, total
@@ -134,11 +197,14 @@ class LearnerStep:
             tree.update_priority(idx, self.td, sorted=self.sorted)
             if consume:
                 self.ingest.consume()
+            if self.prefetch:
+                self._sample_gather(u, self._shadow)
         return total
 
     def step(self, u=None, ingest=None):
         """Run one iteration.  ``u`` (optional): fp64 uniforms (device or pinned-host tensor, B_global
-        values) used instead of the device Philox generator.  ``ingest`` (optional): a tuple
+        values) used instead of the device Philox generator (with ``prefetch`` they drive the sampling that happens
+        during this call, i.e. the NEXT iteration's batch).  ``ingest`` (optional): a tuple
         (stream_ids, obs, action, reward, done, trunc, next_obs) of a FIXED number of new steps per call; their
         scatter into the ring and default priorities run inside the step graph, after the priority write-back and
         concurrently with backward / Adam (FusedIngest); they are sampleable from the next iteration on."""
@@ -154,11 +220,14 @@ class LearnerStep:
                 self.ingest = FusedIngest(self.ring, self.tree, n)
             copied, parity = self.ingest.stage(*ingest)
             torch.cuda.current_stream(self.device).wait_event(copied)
+        if self.use_cuda_graph and (self.graph is None or (draw, consume) != self._graph_key):
+            self._capture(draw, consume)
+            self._primed = False                            # the warm-up iterations sampled into the shadow batch
+        if self.prefetch and (not self._primed or getattr(self.buffer, "_mutations", 0) != self._seen_mutations):
+            self._prime()
         if not self.use_cuda_graph:
             total = self._body(refresh_table=True, draw=draw, consume=consume)
         else:
-            if self.graph is None or (draw, consume) != self._graph_key:
-                self._capture(draw, consume)
             self.graph.replay()
             total = self.agent._static_total_loss
         if consume:

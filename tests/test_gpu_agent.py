@@ -513,3 +513,38 @@ def test_fused_ingest_step_equals_separate_push_then_step(use_graph):
     assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
     assert a[4] == b[4]
     assert torch.equal(a[5], b[5]) and torch.equal(a[6], b[6])
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_prefetched_batches_equal_in_order_sampling(use_graph):
+    """LearnerStep(prefetch=True) samples + gathers the next batch on the tail branch of the current iteration (after
+    the priority write-back, concurrently with backward / Adam).  The tree it sees and the order of the generator's
+    draws are the same as when the batch is sampled at the head of the next iteration: identical training."""
+    import prism_b200
+    from prism_b200.learner_step import LearnerStep
+    from oracle.gen_golden import make_script
+    cap, B, obs_shape, A, iters = 256, 16, (10, 10, 6), 4, 8
+    S = make_script(9, n_streams=4, n_steps=240, obs_shape=obs_shape, p_done=0.05, p_trunc=0.03, n_actions=A)
+    succ = np.where(S["trunc"][:, None], S["final_obs"], S["next_obs"])
+
+    def run(prefetch):
+        cfg = prism_b200.minatar_dqn_per_config(device=DEV, experience_replay_capacity=cap, batch_size=B,
+                                                per_sampling="stratified", replay_max_streams=4, replay_staging_rows=64,
+                                                use_cuda_graph=False)
+        torch.manual_seed(0)
+        agent = prism_b200.build_agent(cfg, obs_shape, A)
+        buf = prism_b200.build_exp_buffer(cfg)
+        buf.extend_batch(S["stream"], S["obs"].reshape((-1,) + obs_shape), S["action"], S["reward"], S["done"], S["trunc"],
+                         succ.reshape((-1,) + obs_shape))
+        buf._flush()
+        buf.buffer._sampler.seed(1234)
+        step = LearnerStep(buf, agent, batch_size=B, use_cuda_graph=use_graph, prefetch=prefetch)
+        losses = [float(step.step()) for _ in range(iters)]
+        torch.cuda.synchronize()
+        tree = buf.buffer._sampler
+        return losses, agent.optimizer.arena.clone(), tree.sum.clone(), tree.min.clone()
+
+    a, b = run(True), run(False)
+    assert a[0] == b[0]
+    assert torch.equal(a[1], b[1])
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
