@@ -389,10 +389,10 @@ typedef struct pb_peer_group {
     int world, rank;
     float *grad[PB_PEER_MAX];                 /* every rank's flat gradient arena (n floats)                         */
     float *reduced[PB_PEER_MAX];              /* every rank's reduced-gradient buffer (n floats; rank r fills slice r) */
-    unsigned long long *flags[PB_PEER_MAX];   /* every rank's signal pad: flags[dst][src] = last epoch src signalled  */
+    unsigned long long *flags[PB_PEER_MAX];   /* every rank's signal pad, 2 channels x PB_PEER_MAX: [dst][ch][src] = epoch */
     double *norm_parts[PB_PEER_MAX];          /* every rank's [PB_PEER_MAX] slice sums of squares                    */
-    unsigned char *state[PB_PEER_MAX];        /* every rank's gathered shard states [world][64]                      */
-    unsigned long long *epoch;                /* local barrier counter                                               */
+    unsigned char *state[PB_PEER_MAX];        /* every rank's gathered shard states, 2 parity slots x [PB_PEER_MAX][64] */
+    unsigned long long *epoch;                /* local barrier counters, one per channel (0 exchange, 1 state gather)  */
 } pb_peer_group;
 int pb_peer_alloc(long long bytes, void **ptr);            /* cudaMalloc + zero fill; blocking                      */
 int pb_peer_free(void *ptr);
@@ -402,9 +402,9 @@ int pb_peer_export(const void *ptr, void *handle64);
 int pb_peer_open(const void *handle64, void **ptr);        /* maps a peer block, enabling peer access               */
 int pb_peer_close(void *ptr);
 int pb_peer_barrier(const pb_peer_group *g, void *stream);
-/* state64: this rank's 64-byte tree state block (pb_tree state).  On return (stream order) state[rank] of this
- * rank holds every rank's block. */
-int pb_peer_state_allgather(const pb_peer_group *g, const void *state64, void *stream);
+/* state64: this rank's 64-byte tree state block (pb_tree state).  On return (stream order) all_state_out (local,
+ * world x 64 bytes) holds every rank's block. */
+int pb_peer_state_allgather(const pb_peer_group *g, const void *state64, void *all_state_out, void *stream);
 long long pb_peer_slice(long long n, int world);           /* floats per rank slice (multiple of 4)                 */
 /* reduced[rank][slice rank] = sum over ranks (rank order) of grad[p][slice]; publishes the slice's sum of squares
  * to every rank; increments *step_count (may be NULL).  Needs a pb_peer_barrier between the writers of grad and

@@ -108,7 +108,7 @@ SIGNATURES = {
     "pb_peer_open": [_P, C.POINTER(C.c_void_p)],
     "pb_peer_close": [_P],
     "pb_peer_barrier": [_PEER, _P],
-    "pb_peer_state_allgather": [_PEER, _P, _P],
+    "pb_peer_state_allgather": [_PEER, _P, _P, _P],
     "pb_peer_slice": [_LL, _I],
     "pb_peer_reduce_scatter": [_PEER, _LL, _P, _P, _P],
     "pb_peer_pull_sum": [_PEER, _LL, _P, _P, C.POINTER(C.c_int), _P],

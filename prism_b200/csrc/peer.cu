@@ -45,32 +45,43 @@ __device__ __forceinline__ double ld_peer_f64(const double *p)
     return v;
 }
 
-// one warp: lane i signals rank i and waits for rank i
-__device__ __forceinline__ void epoch_handshake(const pb_peer_group &g)
+// one warp: lane i signals rank i and waits for rank i.  Two independent CHANNELS (own flags, own epoch): calls on
+// one channel must be issued in the same order by every rank, but the gradient exchange (channel 0, main branch of
+// the step graph) and the shard-state all-gather (channel 1, tail branch) may interleave freely.
+__device__ __forceinline__ void epoch_handshake(const pb_peer_group &g, int ch)
 {
     const int lane = threadIdx.x & 31;
-    const unsigned long long e = *g.epoch + 1;
+    unsigned long long *epoch = g.epoch + ch;
+    const unsigned long long e = *epoch + 1;
     __threadfence_system();
     if (lane < g.world) {
-        st_release_sys(g.flags[lane] + g.rank, e);
-        while (ld_acquire_sys(g.flags[g.rank] + lane) < e) { }
+        st_release_sys(g.flags[lane] + ch * PB_PEER_MAX + g.rank, e);
+        while (ld_acquire_sys(g.flags[g.rank] + ch * PB_PEER_MAX + lane) < e) { }
     }
     __syncwarp();
-    if (lane == 0) *g.epoch = e;
+    if (lane == 0) *epoch = e;
 }
 
-__global__ void __launch_bounds__(32) peer_barrier_kernel(pb_peer_group g) { epoch_handshake(g); }
+__global__ void __launch_bounds__(32) peer_barrier_kernel(pb_peer_group g) { epoch_handshake(g, 0); }
 
-__global__ void __launch_bounds__(64) peer_state_allgather_kernel(pb_peer_group g, const unsigned int *__restrict__ state)
+// The gathered blocks land in one of two peer-visible slots (parity of the channel-1 epoch) and are copied to a
+// local buffer after the handshake: a fast rank's NEXT all-gather then never writes where a slower rank still reads.
+__global__ void __launch_bounds__(64) peer_state_allgather_kernel(pb_peer_group g, const unsigned int *__restrict__ state,
+                                                                  unsigned int *__restrict__ out_local)
 {
     const int t = threadIdx.x;
+    const unsigned long long slot = (g.epoch[1] + 1) & 1;
+    const size_t slot_words = (size_t)slot * PB_PEER_MAX * 16;
     if (t < 16) {
         const unsigned int v = state[t];
-        for (int p = 0; p < g.world; ++p) reinterpret_cast<unsigned int *>(g.state[p])[g.rank * 16 + t] = v;
+        for (int p = 0; p < g.world; ++p) reinterpret_cast<unsigned int *>(g.state[p])[slot_words + g.rank * 16 + t] = v;
         __threadfence_system();
     }
     __syncthreads();
-    if (t < 32) epoch_handshake(g);
+    if (t < 32) epoch_handshake(g, 1);
+    __syncthreads();
+    const volatile unsigned int *mine = reinterpret_cast<const volatile unsigned int *>(g.state[g.rank]) + slot_words;
+    for (int i = t; i < g.world * 16; i += blockDim.x) out_local[i] = mine[i];
 }
 
 constexpr int RS_THREADS = 256;
@@ -252,14 +263,15 @@ int pb_peer_barrier(const pb_peer_group *g, void *stream)
     return PB_OK;
 }
 
-int pb_peer_state_allgather(const pb_peer_group *g, const void *state64, void *stream)
+int pb_peer_state_allgather(const pb_peer_group *g, const void *state64, void *all_state_out, void *stream)
 {
     int rc = check_group(g);
     if (rc) return rc;
-    if (!state64) return PB_E_ARG;
+    if (!state64 || !all_state_out) return PB_E_ARG;
     for (int p = 0; p < g->world; ++p)
         if (!g->state[p]) return PB_E_ARG;
-    PB_LAUNCH(peer_state_allgather_kernel, 1, 64, 0, stream, *g, reinterpret_cast<const unsigned int *>(state64));
+    PB_LAUNCH(peer_state_allgather_kernel, 1, 64, 0, stream, *g, reinterpret_cast<const unsigned int *>(state64),
+              reinterpret_cast<unsigned int *>(all_state_out));
     return PB_OK;
 }
 

@@ -98,7 +98,9 @@ class LearnerStep:
                     from .peer import PeerGroup
                     self.peer = PeerGroup.create(self.pg, self.rank, self.world_size, opt.numel, d)
                     opt.attach_peer_group(self.peer)
-                    opt.peer_trailing_barrier = False        # the next step's state all-gather is the separating barrier
+                    # without prefetch the next step's state all-gather separates this step's pulls from the next pack;
+                    # with prefetch that all-gather runs on the tail branch, concurrently: keep the explicit barrier
+                    opt.peer_trailing_barrier = self.prefetch
                     self.all_state = self.peer.all_state
                 except Exception as e:                                   # e.g. ranks on different boxes
                     sys.stderr.write("peer-memory exchange unavailable (%r): using the library collectives\n" % (e,))

@@ -1,7 +1,7 @@
 """PeerGroup -- the host side of csrc/peer.cu: one peer-mapped block per rank (NVLink / NVSwitch, CUDA IPC).
 
 Layout of a rank's block (bytes):  grad [n floats] | reduced [n floats] | flags [64 u64] | norm_parts [8 f64] |
-state [8 x 64 B] | epoch [u64].  ``torch.distributed`` is only used once, to exchange the 64-byte IPC handles; no
+state [2 x 8 x 64 B] | epochs [2 x u64].  ``torch.distributed`` is only used once, to exchange the 64-byte IPC handles; no
 collective library call remains on the per-step path.
 
 ``PeerGroup.loopback(world, n, device)`` builds ``world`` groups inside ONE process on one GPU (plain pointers to
@@ -30,7 +30,7 @@ def _layout(n):
     off = {"grad": 0, "reduced": n_bytes, "flags": 2 * n_bytes}
     off["norm_parts"] = off["flags"] + 64 * 8
     off["state"] = off["norm_parts"] + 64
-    off["epoch"] = off["state"] + _lib.PB_PEER_MAX * 64
+    off["epoch"] = off["state"] + 2 * _lib.PB_PEER_MAX * 64
     off["total"] = off["epoch"] + 256
     return off
 
@@ -53,7 +53,7 @@ class PeerGroup:
         self._block = torch.as_tensor(_RawCuda(own_ptr, self.off["total"]), device=self.device)
         self.grad = self._block[self.off["grad"]:self.off["grad"] + 4 * self.n].view(torch.float32)
         self.reduced = self._block[self.off["reduced"]:self.off["reduced"] + 4 * self.n].view(torch.float32)
-        self.all_state = self._block[self.off["state"]:self.off["state"] + 64 * self.world].view(self.world, 64)
+        self.all_state = torch.zeros(self.world, 64, dtype=torch.uint8, device=self.device)     # local copy of the gather
 
     # ---- construction -------------------------------------------------------------------------------------
     @classmethod
@@ -103,7 +103,8 @@ class PeerGroup:
 
     def state_allgather(self, state):
         """state: this rank's 64-byte tree state block (uint8 tensor).  Returns the (world, 64) gathered view."""
-        _lib.check(_lib.load().pb_peer_state_allgather(C.byref(self.c), state.data_ptr(), self._stream()),
+        _lib.check(_lib.load().pb_peer_state_allgather(C.byref(self.c), state.data_ptr(), self.all_state.data_ptr(),
+                                                       self._stream()),
                    "pb_peer_state_allgather")
         return self.all_state
 
