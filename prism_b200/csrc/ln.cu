@@ -190,20 +190,31 @@ __global__ void __launch_bounds__(LN_THREADS) ln_bwd_kernel(long long rows, int 
     }
 }
 
-// dgamma[c] = sum_b part_g[b][c], dbeta likewise (fixed order)
-__global__ void __launch_bounds__(256) ln_colreduce_kernel(int nblocks, int F, const float *__restrict__ part_g,
-                                                           const float *__restrict__ part_b, float *__restrict__ dgamma,
-                                                           float *__restrict__ dbeta)
+// dgamma[c] = sum_b part_g[b][c], dbeta likewise.  Block = 32 columns x 32 row groups: group r adds partial rows
+// r, r+32, ... (coalesced 128-byte loads), then the 32 groups are combined in a fixed order through shared memory.
+__global__ void __launch_bounds__(1024) ln_colreduce_kernel(int nblocks, int F, const float *__restrict__ part_g,
+                                                            const float *__restrict__ part_b, float *__restrict__ dgamma,
+                                                            float *__restrict__ dbeta)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= F) return;
+    __shared__ float sg[32][33], sb[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x, r = threadIdx.y;
     float a = 0.f, b = 0.f;
-    for (int k = 0; k < nblocks; ++k) {
-        a += part_g[(size_t)k * F + c];
-        b += part_b[(size_t)k * F + c];
+    if (c < F) {
+        for (int k = r; k < nblocks; k += 32) {
+            a += part_g[(size_t)k * F + c];
+            b += part_b[(size_t)k * F + c];
+        }
     }
-    if (dgamma) dgamma[c] = a;
-    if (dbeta) dbeta[c] = b;
+    sg[r][threadIdx.x] = a;
+    sb[r][threadIdx.x] = b;
+    __syncthreads();
+    if (r == 0 && c < F) {
+        float ta = 0.f, tb = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { ta += sg[k][threadIdx.x]; tb += sb[k][threadIdx.x]; }
+        if (dgamma) dgamma[c] = ta;
+        if (dbeta) dbeta[c] = tb;
+    }
 }
 
 int ln_grid(long long rows, int rpc)
@@ -265,7 +276,7 @@ int pb_layer_norm_bwd(long long rows, int F, const float *x, const float *dy, co
         PB_LAUNCH((ln_bwd_kernel<256, 4>), nb, LN_THREADS, 0, stream, rows, F4, x4, d4, g4, mean, rstd, dx4, pg, pbeta);
     }
     if (dgamma || dbeta)
-        PB_LAUNCH(ln_colreduce_kernel, (F + 255) / 256, 256, 0, stream, nb, F, partials, partials + (size_t)nb * F, dgamma, dbeta);
+        PB_LAUNCH(ln_colreduce_kernel, (F + 31) / 32, dim3(32, 32), 0, stream, nb, F, partials, partials + (size_t)nb * F, dgamma, dbeta);
     return PB_OK;
 }
 

@@ -45,7 +45,7 @@ if mode == "atari":
                          (rng.random(n) < 0.05).astype(np.float32), rng.random(n) < (1 / 500), np.zeros(n, bool),
                          frames[32:32 + n].reshape(n, 84, 84))
     buf._flush()
-    step = LearnerStep(buf, agent, batch_size=cfg.batch_size, use_cuda_graph=True)
+    step = LearnerStep(buf, agent, batch_size=cfg.batch_size, use_cuda_graph=True, prefetch=True)
     for _ in range(4):
         step.step()
     torch.cuda.synchronize()
@@ -60,7 +60,7 @@ c = trace.chunk(n)
 buf.extend_batch(c["stream"], c["obs"].reshape((n,) + obs_shape), c["action"], c["reward"], c["done"], c["trunc"],
                  c["next_obs"].reshape((n,) + obs_shape))
 buf._flush()
-step = LearnerStep(buf, agent, batch_size=cfg.batch_size, use_cuda_graph=True)
+step = LearnerStep(buf, agent, batch_size=cfg.batch_size, use_cuda_graph=True, prefetch=True)
 for _ in range(6):
     step.step()
 torch.cuda.synchronize()
