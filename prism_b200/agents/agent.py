@@ -83,7 +83,14 @@ class Agent(object):
         if after_loss is not None:
             after_loss(td)
         self.optimizer.zero_grad(set_to_none=True)
-        total.backward()
+        if total.is_cuda and total.dim() == 0 and total.dtype == torch.float32:
+            ops.UNIT_TOTAL_GRAD = True          # the fused loss head then hands its saved gradients through unscaled
+            try:
+                total.backward(gradient=ops.unit_gradient(total.device))
+            finally:
+                ops.UNIT_TOTAL_GRAD = False
+        else:
+            total.backward()
         return dist_loss, q_loss, total, td
 
     def _optimizer_step(self, refresh_table=True):

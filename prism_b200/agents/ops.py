@@ -462,6 +462,18 @@ def run_sequential(seq, x):
     return x
 
 
+UNIT_TOTAL_GRAD = False        # set by Agent._loss_and_backward while it runs total.backward() with the implicit gradient 1
+_ONES = {}
+
+
+def unit_gradient(device):
+    """A cached scalar 1.0 on ``device`` (saves autograd's ones_like fill launch per backward)."""
+    t = _ONES.get(device)
+    if t is None:
+        t = _ONES[device] = torch.ones((), dtype=torch.float32, device=device)
+    return t
+
+
 class _FusedTotalLoss(torch.autograd.Function):
     """total = mean(dist*w) + mean(q'*w) straight from the quantile / ensemble tables: loss heads, PER
     weighting, TD mix and the gradients w.r.t. z_cur / q_cur (already scaled by w_b/B) in 3 launches;
@@ -511,6 +523,9 @@ class _FusedTotalLoss(torch.autograd.Function):
         gz, gq = ctx.saved_tensors
         if g_total is None:
             return (None,) * 18
+        if UNIT_TOTAL_GRAD:
+            # Agent._loss_and_backward differentiates the scalar total itself: d total / d total = 1 exactly
+            return (gz, gq) + (None,) * 16
         return (None if gz is None else gz * g_total, None if gq is None else gq * g_total) + (None,) * 16
 
 

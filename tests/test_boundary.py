@@ -48,9 +48,11 @@ def test_struct_layouts(tmp_path):
 #include <stddef.h>
 #include "prism_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(pb_per_state), sizeof(pb_tree), sizeof(pb_store),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pb_per_state), sizeof(pb_tree), sizeof(pb_store),
          offsetof(pb_tree, eps_f64), offsetof(pb_tree, default_priority_fp64),
-         offsetof(pb_store, size), offsetof(pb_store, gamma));
+         offsetof(pb_store, size), offsetof(pb_store, gamma),
+         sizeof(pb_peer_group), offsetof(pb_peer_group, reduced), offsetof(pb_peer_group, state),
+         offsetof(pb_peer_group, epoch));
   return 0; }
 """)
     exe = tmp_path / "sz"
@@ -58,8 +60,28 @@ int main(void) {
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(_lib.pb_per_state), C.sizeof(_lib.pb_tree), C.sizeof(_lib.pb_store),
             _lib.pb_tree.eps_f64.offset, _lib.pb_tree.default_priority_fp64.offset,
-            _lib.pb_store.size.offset, _lib.pb_store.gamma.offset]
+            _lib.pb_store.size.offset, _lib.pb_store.gamma.offset,
+            C.sizeof(_lib.pb_peer_group), _lib.pb_peer_group.reduced.offset, _lib.pb_peer_group.state.offset,
+            _lib.pb_peer_group.epoch.offset]
     assert got == want
+    assert _lib.PB_PEER_MAX == 8
+
+
+def test_peer_block_layout_and_slices():
+    """Host-side arithmetic of the peer exchange: block layout (prism_b200/peer.py) and the rank slices
+    (pb_peer_slice): 16-byte aligned, disjoint, covering."""
+    from prism_b200 import _lib, peer
+    lib = _lib.load()
+    for n in (4, 4096, 265_220, 18_167_208):
+        off = peer._layout(n)
+        assert off["grad"] == 0 and off["reduced"] >= 4 * n and off["reduced"] % 256 == 0
+        assert off["flags"] >= off["reduced"] + 4 * n and off["flags"] % 8 == 0
+        assert off["norm_parts"] - off["flags"] >= 2 * _lib.PB_PEER_MAX * 8          # two barrier channels
+        assert off["epoch"] - off["state"] >= 2 * _lib.PB_PEER_MAX * 64              # two parity slots
+        assert off["total"] > off["epoch"] + 16
+        for world in (1, 2, 4, 8):
+            sl = lib.pb_peer_slice(n, world)
+            assert sl % 4 == 0 and sl * world >= n and sl * (world - 1) < n + 4 * world
 
 
 def test_argument_errors_do_not_touch_the_gpu():
