@@ -590,9 +590,9 @@ def run_ours(args):
         sl = slice(i * STEPS_PER_ITER, (i + 1) * STEPS_PER_ITER)
         u_host = u_hosts[i & 1]             # double-buffered: the previous step's async H2D may still be queued
         u_host.numpy()[:] = pre_u[i]
-        total = step.step(u=u_host, ingest=(pre["stream"][sl], pre["obs"][sl], pre["action"][sl], pre["reward"][sl],
-                                            pre["done"][sl], pre["trunc"][sl], pre["next_obs"][sl]))
-        loss_host.copy_(total.detach(), non_blocking=True)
+        step.step(u=u_host, ingest=(pre["stream"][sl], pre["obs"][sl], pre["action"][sl], pre["reward"][sl],
+                                    pre["done"][sl], pre["trunc"][sl], pre["next_obs"][sl]))
+        step.copy_loss_to(loss_host)
     for _ in range(max(3, args.warmup)):
         e2e_one()
     barrier()

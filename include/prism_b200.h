@@ -44,6 +44,15 @@ enum {
 };
 
 int         pb_abi_version(void);
+/* Thin stream / event / copy wrappers (cudaEvent_t / cudaStream_t as void*): the per-iteration host path of the
+ * fused ingest orders its pinned->device staging copy against the step graph through these. */
+int pb_event_create(void **event);
+int pb_event_destroy(void *event);
+int pb_event_record(void *event, void *stream);
+int pb_event_synchronize(void *event);
+int pb_stream_wait_event(void *stream, void *event);
+int pb_copy_h2d_async(void *dst, const void *src, long long bytes, void *stream);
+int pb_copy_d2h_async(void *dst, const void *src, long long bytes, void *stream);
 const char *pb_error_string(int code);
 /* number of kernels this library has launched in this process (bench: gpu_launches) */
 long long   pb_launch_count(void);

@@ -72,6 +72,13 @@ SIGNATURES = {
     "pb_abi_version": [],
     "pb_error_string": [_I],
     "pb_launch_count": [],
+    "pb_event_create": [C.POINTER(C.c_void_p)],
+    "pb_event_destroy": [_P],
+    "pb_event_record": [_P, _P],
+    "pb_event_synchronize": [_P],
+    "pb_stream_wait_event": [_P, _P],
+    "pb_copy_h2d_async": [_P, _P, _LL, _P],
+    "pb_copy_d2h_async": [_P, _P, _LL, _P],
     "pb_tree_init": [_TREE, _P],
     "pb_tree_build": [_TREE, _P, _LL, _P],
     "pb_tree_stats": [_TREE, _P],

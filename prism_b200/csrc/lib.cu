@@ -22,6 +22,32 @@ int pb_abi_version(void) { return PB_ABI_VERSION; }
 
 long long pb_launch_count(void) { return g_pb_launches.load(std::memory_order_relaxed); }
 
+// ---- thin stream / event / copy wrappers: the per-iteration host path of the fused ingest issues its staging copy
+// and its cross-stream ordering through these (one ctypes call each) instead of framework context managers.
+int pb_event_create(void **event)
+{
+    if (!event) return PB_E_ARG;
+    cudaEvent_t e;
+    cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (rc != cudaSuccess) return (int)rc;
+    *event = (void *)e;
+    return PB_OK;
+}
+int pb_event_destroy(void *event) { return event ? (int)cudaEventDestroy((cudaEvent_t)event) : PB_OK; }
+int pb_event_record(void *event, void *stream) { return (int)cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream); }
+int pb_event_synchronize(void *event) { return (int)cudaEventSynchronize((cudaEvent_t)event); }
+int pb_stream_wait_event(void *stream, void *event) { return (int)cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0); }
+int pb_copy_h2d_async(void *dst, const void *src, long long bytes, void *stream)
+{
+    if (!dst || !src || bytes < 0) return PB_E_ARG;
+    return (int)cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+}
+int pb_copy_d2h_async(void *dst, const void *src, long long bytes, void *stream)
+{
+    if (!dst || !src || bytes < 0) return PB_E_ARG;
+    return (int)cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+}
+
 const char *pb_error_string(int code)
 {
     switch (code) {

@@ -319,37 +319,47 @@ class FusedIngest:
     Steps staged before iteration k's launch become sampleable from iteration k+1 on."""
 
     def __init__(self, ring, tree, n):
+        import ctypes as C
         self.ring, self.tree, self.n = ring, tree, int(n)
         self.slots = [IngestSlot(ring, n), IngestSlot(ring, n)]
         dev = ring.device
         self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.copy_stream = torch.cuda.Stream(device=dev)
-        self.copied = [None, None]        # event: H2D of block p finished (pinned block reusable, device block valid)
-        self.consumed = [None, None]      # event: the replay that read device block p finished
+        self._copy_handle = self.copy_stream.cuda_stream
+        lib = self._lib = ring._lib
+        # raw events (one ctypes call per operation on the per-iteration path)
+        self.copied, self.consumed = [], []     # H2D of block p finished / the replay that read device block p finished
+        for _ in range(2):
+            for lst in (self.copied, self.consumed):
+                ev = C.c_void_p()
+                _lib.check(lib.pb_event_create(C.byref(ev)), "pb_event_create")
+                lst.append(ev)
+        self._copied_valid, self._consumed_valid = [False, False], [False, False]
+        self._ptrs = [(s.d_block.data_ptr(), s.h_block.data_ptr(), s.h_block.numel()) for s in self.slots]
         self.calls = 0
         self.h2d_bytes = self.slots[0].h2d_bytes
 
-    def stage(self, stream_ids, obs, action, reward, done, trunc, next_obs):
-        """Host half.  Returns the event the consuming replay must wait for."""
+    def stage(self, stream_ids, obs, action, reward, done, trunc, next_obs, main_stream):
+        """Host half: fill the pinned block of this parity, copy it on the copy stream (after the replay that last
+        read the device block), make ``main_stream`` (raw handle) wait for the copy.  Returns the parity."""
+        lib = self._lib
         p = self.calls & 1
         self.calls += 1
-        slot = self.slots[p]
-        if self.copied[p] is not None:
-            self.copied[p].synchronize()                      # pinned block free again (two iterations old)
-        slot.fill(stream_ids, obs, action, reward, done, trunc, next_obs)
-        if self.consumed[p] is not None:
-            self.copy_stream.wait_event(self.consumed[p])     # device block p was read by replay k-2
-        with torch.cuda.stream(self.copy_stream):
-            slot.d_block.copy_(slot.h_block, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(self.copy_stream)
-        self.copied[p] = ev
-        return ev, p
+        if self._copied_valid[p]:
+            lib.pb_event_synchronize(self.copied[p])          # pinned block free again (two iterations old)
+        self.slots[p].fill(stream_ids, obs, action, reward, done, trunc, next_obs)
+        if self._consumed_valid[p]:
+            lib.pb_stream_wait_event(self._copy_handle, self.consumed[p])
+        dst, src, nbytes = self._ptrs[p]
+        _lib.check(lib.pb_copy_h2d_async(dst, src, nbytes, self._copy_handle), "pb_copy_h2d_async")
+        lib.pb_event_record(self.copied[p], self._copy_handle)
+        self._copied_valid[p] = True
+        lib.pb_stream_wait_event(main_stream, self.copied[p])
+        return p
 
-    def mark_consumed(self, p):
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.ring.device))
-        self.consumed[p] = ev
+    def mark_consumed(self, p, main_stream):
+        self._lib.pb_event_record(self.consumed[p], main_stream)
+        self._consumed_valid[p] = True
 
     def consume(self):
         """Device half (capturable): scatter from the block of this replay's parity, then default priorities."""

@@ -26,6 +26,7 @@ class LearnerStep:
     def __init__(self, buffer, agent, batch_size=None, use_cuda_graph=True, process_group=None,
                  rank=0, world_size=1, pad_slack=None, exchange=None, prefetch=False):
         self.buffer, self.agent = buffer, agent
+        self._lib = _lib.load()
         self.tree = buffer.buffer._sampler
         self.ring = buffer.buffer._storage
         if self.ring is None or self.tree is None:
@@ -213,15 +214,20 @@ class LearnerStep:
         self.buffer._flush()
         draw = u is None
         if not draw:
-            self.u.copy_(u, non_blocking=True)
+            if u.device.type == "cpu" and u.dtype == torch.float64 and u.is_contiguous() and u.numel() == self.u.numel():
+                # host uniforms (pinned): one raw async copy on the step's stream
+                _lib.check(self._lib.pb_copy_h2d_async(self.u.data_ptr(), u.data_ptr(), 8 * self.u.numel(),
+                                                       torch.cuda.current_stream(self.device).cuda_stream), "pb_copy_h2d_async")
+            else:
+                self.u.copy_(u, non_blocking=True)
         consume, parity = ingest is not None, None
         if consume:
             n = len(ingest[0])
             if self.ingest is None or self.ingest.n != n:
                 from .experience.ring import FusedIngest
                 self.ingest = FusedIngest(self.ring, self.tree, n)
-            copied, parity = self.ingest.stage(*ingest)
-            torch.cuda.current_stream(self.device).wait_event(copied)
+            main = torch.cuda.current_stream(self.device).cuda_stream
+            parity = self.ingest.stage(*ingest, main_stream=main)
         if self.use_cuda_graph and (self.graph is None or (draw, consume) != self._graph_key):
             self._capture(draw, consume)
             self._primed = False                            # the warm-up iterations sampled into the shadow batch
@@ -233,9 +239,15 @@ class LearnerStep:
             self.graph.replay()
             total = self.agent._static_total_loss
         if consume:
-            self.ingest.mark_consumed(parity)
+            self.ingest.mark_consumed(parity, main)
         self.agent.n_updates += 1
         return total
+
+    def copy_loss_to(self, host_scalar):
+        """Asynchronous device -> host read of the last step's total loss into a pinned fp32 scalar."""
+        t = self.agent._static_total_loss
+        _lib.check(self._lib.pb_copy_d2h_async(host_scalar.data_ptr(), t.data_ptr(), 4,
+                                               torch.cuda.current_stream(self.device).cuda_stream), "pb_copy_d2h_async")
 
     def _capture(self, draw, consume=False):
         opt = self.agent.optimizer
