@@ -224,6 +224,31 @@ def time_kernel(fn, reps, torch):
     return a.elapsed_time(b) * 1e-3 / reps
 
 
+def time_kernel_graph(fn, reps, torch):
+    """Average device time (s) of one call of fn: `reps` back-to-back calls captured in a CUDA graph (no host launch
+    overhead between them), replayed, CUDA events on the launching stream."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e-3 / (5 * reps)
+
+
 def kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src):
     """Per-C-ABI-op timing of our kernels at the step's shapes + algorithmic bytes."""
     tree, ring = buf.buffer._sampler, buf.buffer._storage
@@ -240,6 +265,7 @@ def kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src):
     saved_allreduce, opt.allreduce = opt.allreduce, None      # rank-0-only timing: no collective in here
     saved_peer, opt.peer = opt.peer, None
     rows = {}
+    time_kernel = time_kernel_graph          # device time per call, launch overhead excluded (shadows the eager timer)
     rows["per_sample (tree_sample_kernel)"] = (time_kernel(lambda: tree.sample(B, u=u, idx_out=idx, weight_out=w), 50, torch),
                                                B * (4 * L + 24))
     rows["per_gather (store_gather_kernel)"] = (time_kernel(lambda: ring.gather(idx, buf._obs, buf._next_obs, buf._reward,
@@ -292,6 +318,67 @@ def kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src):
                 "note": "batch-256 launches move KBs-MBs: latency-bound by construction; see extras.per_microbench "
                         "for the saturated PER kernels"}
     return roof, out
+
+
+def sharded_per_microbench(step, rank, world, device, torch, dist, hbm_gbs):
+    """BASELINE configs[3]: sharded PER, 8M (2^23) leaves per GPU, global batch 4096: exchange of the shard states +
+    global stratified sampling (owner-computes) + priority update of the owned strata, captured as one CUDA graph per
+    rank and replayed in lock-step; max over ranks.  Collective: the peer-memory all-gather of LearnerStep (or NCCL)."""
+    from prism_b200 import PrioritizedTree
+    N, Bg = 1 << 23, 4096
+    tree = PrioritizedTree(N, device=device, mode="stratified")
+    g = torch.Generator(device=device)
+    g.manual_seed(100 + rank)
+    tree.build(torch.empty(N, device=device).exponential_(1.0, generator=g))
+    tree.seed(7)                                       # same Philox key on every rank
+    idx = torch.zeros(Bg, dtype=torch.int64, device=device)
+    w = torch.zeros(Bg, dtype=torch.float32, device=device)
+    stratum = torch.zeros(Bg, dtype=torch.int64, device=device)
+    pad = Bg // world + int(4 * (Bg / world) ** 0.5)
+    prio = torch.rand(pad, device=device)
+    peer = step.peer
+    all_state = peer.all_state if peer is not None else torch.zeros(world, 64, dtype=torch.uint8, device=device)
+
+    def one():
+        if peer is not None:
+            peer.state_allgather(tree.state)
+        else:
+            dist.all_gather_into_tensor(all_state.view(-1), tree.state)
+        tree.sample_global(world, rank, all_state, Bg, None, idx_out=idx, weight_out=w, stratum_out=stratum)
+        tree.update_priority(idx[:pad], prio, sorted=True)
+    reps = 20
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            one()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    dist.barrier()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for _ in range(reps):
+            one()
+    gr.replay()
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        gr.replay()
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) * 1e-3 / (10 * reps)], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    L = 23
+    nbytes = Bg * (4 * L + 24) + Bg * (16 * L + 20)          # SURVEY 8d per-transition figures, whole job
+    del gr
+    return {"leaves_per_gpu": N, "global_batch": Bg, "us_per_iteration": round(sec * 1e6, 2),
+            "transitions_per_s": round(Bg / sec, 1), "algorithmic_bytes": int(nbytes),
+            "achieved_gbs": round(nbytes / sec / 1e9, 2), "frac_of_one_gpu_hbm": round(nbytes / sec / 1e9 / hbm_gbs, 5),
+            "exchange": "peer" if peer is not None else "nccl",
+            "note": "latency-bound: one cross-GPU handshake + 3 sampling launches + 3 update launches per iteration"}
 
 
 def tensor_peak():
@@ -616,6 +703,12 @@ def run_ours(args):
            "d2h_bytes_per_step": 4, "updates_per_s": e2e_steps / e2e_sec,
            "host_wall_s": round(wall, 4), "loss": float(loss_host)}
 
+    sharded = None
+    if world > 1 and not args.quick:
+        try:
+            sharded = sharded_per_microbench(step, rank, world, device, torch, dist, hbm_gbs)
+        except Exception as e:
+            sharded = {"error": repr(e)[:300]}
     if rank != 0:
         _finish(world, dist)
         return
@@ -623,6 +716,8 @@ def run_ours(args):
     roof, ktable = kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src)
     extras = {"kernels_at_step_shapes": ktable, "ingest_transitions_per_s": round(CAPACITY / ingest_s, 1),
               "launches_per_step_ours": lp, "graph": graph_ok}
+    if sharded is not None:
+        extras["sharded_per_configs3"] = sharded
     cpu = None
     if world == 1 and not args.quick:
         del step
