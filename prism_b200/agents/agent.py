@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .action_selectors import GreedyActionSelector, IDSActionSelector
 from .optim import FlatAdam
 
 
@@ -50,9 +51,52 @@ class Agent(object):
     # ---- acting -------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, obs):
-        q, z = self.model(obs, for_action=True)
         selector = self.eval_action_selector if self._is_eval else self.action_selector
+        if self.use_cuda_graph and type(selector) in (IDSActionSelector, GreedyActionSelector):
+            act = self._forward_acting_graph(obs, selector)
+            if act is not None:
+                return act
+        q, z = self.model(obs, for_action=True)
         return selector.select_action(selector.generate_action_probs(z, q))
+
+    @torch.no_grad()
+    def _forward_acting_graph(self, obs, selector):
+        """The whole acting path of prism/agents/agent.py:31-41 -- embedding, IQN with Nq quantile samples, K Q heads and
+        the IDS / greedy selection kernel -- as ONE CUDA graph per (selector, input shape): one staging copy in, one
+        replay, the action vector out.  Only selectors that live entirely on the device are captured (epsilon-greedy
+        flips a host coin per call and stays eager)."""
+        model = self.model
+        dev = torch.device(getattr(model, "device", "cpu"))
+        if dev.type != "cuda" or not hasattr(model, "_forward_without_cuda_graph"):
+            return None
+        if not isinstance(obs, torch.Tensor):
+            obs = torch.from_numpy(np.asarray(obs, dtype=np.float32))
+        key = (id(selector), tuple(obs.shape))
+        graphs = self.__dict__.setdefault("_acting_graphs", {})
+        entry = graphs.get(key)
+        if entry is None:
+            if len(graphs) >= 8:                       # a handful of inference batch shapes at most
+                return None
+            static_in = torch.zeros(obs.shape, dtype=torch.float32, device=dev)
+            static_in.copy_(obs)
+
+            def body():
+                q, z = model._forward_without_cuda_graph(static_in, for_action=True)
+                return selector.select_action(selector.generate_action_probs(z, q))
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = body()
+            entry = graphs[key] = (g, static_in, static_out)
+        g, static_in, static_out = entry
+        static_in.copy_(obs, non_blocking=True)
+        g.replay()
+        return static_out.clone()
 
     # ---- learning -----------------------------------------------------------------------
     def update(self, batch, per_weights=1):

@@ -548,3 +548,39 @@ def test_prefetched_batches_equal_in_order_sampling(use_graph):
     assert a[0] == b[0]
     assert torch.equal(a[1], b[1])
     assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+
+
+@pytest.mark.parametrize("kind", ["ids_iqn", "dqn_greedy"])
+def test_acting_graph_equals_eager_acting(kind, monkeypatch):
+    """Agent.forward as one CUDA graph (embedding -> IQN(Nq) -> K heads -> IDS / greedy kernel) picks the same actions
+    as the eager path (prism/agents/agent.py:31-41).  The quantile draw is pinned on both sides."""
+    import prism_b200
+    obs_shape, A, N = ((10, 10, 4), 3, 14) if kind == "ids_iqn" else ((10, 10, 6), 4, 9)
+    if kind == "ids_iqn":
+        cfg = prism_b200.minatar_ids_iqn_config(device=DEV, experience_replay_capacity=64, batch_size=8,
+                                                iqn_quantile_samples_per_action=16, iqn_quantile_model_feature_dim=32,
+                                                ids_q_head_feature_dim=16, ids_n_q_heads=3, use_cuda_graph=True,
+                                                replay_max_streams=2, replay_staging_rows=8)
+    else:
+        cfg = prism_b200.minatar_dqn_per_config(device=DEV, experience_replay_capacity=64, batch_size=8,
+                                                use_cuda_graph=True, replay_max_streams=2, replay_staging_rows=8)
+    torch.manual_seed(0)
+    agent = prism_b200.build_agent(cfg, obs_shape, A)
+    agent.eval() if kind == "dqn_greedy" else agent.train()
+    real_rand = torch.rand
+
+    def fixed_rand(size, *a, **kw):
+        n = int(np.prod(size))
+        return ((torch.arange(n, dtype=torch.float32, device=kw.get("device", "cpu")) * 0.6180339887) % 1.0).view(*size)
+    monkeypatch.setattr(torch, "rand", fixed_rand)
+    g = torch.Generator().manual_seed(3)
+    for trial in range(3):
+        obs = (real_rand((N,) + obs_shape, generator=g) < 0.15).float()
+        got = agent.forward(obs)                                   # graph (captured on the first trial)
+        agent.use_cuda_graph, saved = False, agent.use_cuda_graph
+        agent.model.use_cuda_graph, saved_m = False, getattr(agent.model, "use_cuda_graph", False)
+        want = agent.forward(obs)                                  # eager
+        agent.use_cuda_graph, agent.model.use_cuda_graph = saved, saved_m
+        assert got.dtype == torch.int64 and got.shape == (N,)
+        assert torch.equal(got.cpu(), want.cpu())
+    assert len(agent._acting_graphs) == 1
