@@ -427,7 +427,7 @@ def per_microbench(device, torch, hbm_gbs):
     g = torch.Generator(device=device)
     g.manual_seed(1)
     leaves = torch.empty(N, device=device).exponential_(1.0, generator=g).add_(1e-8).sqrt_()
-    sec = time_kernel(lambda: tree.build(leaves), 10, torch)
+    sec = time_kernel_graph(lambda: tree.build(leaves), 10, torch)
     nbytes = 2 * (4 * N + 4 * 2 * N)                     # read leaves once per tree, write 2N nodes per tree
     out["bulk_build_16M"] = {"ms": round(sec * 1e3, 4), "algorithmic_bytes": nbytes,
                              "achieved_gbs": round(nbytes / sec / 1e9, 1), "frac": round(nbytes / sec / 1e9 / hbm_gbs, 4)}
@@ -440,14 +440,10 @@ def per_microbench(device, torch, hbm_gbs):
         def both():
             tree.sample(B, u=u, idx_out=idx, weight_out=w)
             tree.update_priority(idx, prio, sorted=True)
-        gr = torch.cuda.CUDAGraph()
-        both(); torch.cuda.synchronize()
-        with torch.cuda.graph(gr):
-            both()
-        reps = 200 if B <= 65536 else 20
-        sec = time_kernel(gr.replay, reps, torch)
-        s_sec = time_kernel(lambda: tree.sample(B, u=u, idx_out=idx, weight_out=w), reps, torch)
-        u_sec = time_kernel(lambda: tree.update_priority(idx, prio, sorted=True), reps, torch)
+        reps = 40 if B <= 65536 else 10                      # back-to-back iterations inside one captured graph
+        sec = time_kernel_graph(both, reps, torch)
+        s_sec = time_kernel_graph(lambda: tree.sample(B, u=u, idx_out=idx, weight_out=w), reps, torch)
+        u_sec = time_kernel_graph(lambda: tree.update_priority(idx, prio, sorted=True), reps, torch)
         nbytes = B * (4 * L + 24 + 16 * L + 20)          # 524 B / transition
         out["sample+update_16M_B%d" % B] = {
             "us": round(sec * 1e6, 2), "transitions_per_s": round(B / sec, 1), "algorithmic_bytes": nbytes,
@@ -468,7 +464,7 @@ def per_microbench(device, torch, hbm_gbs):
     o = torch.empty(Bg, 4, 84, 84, device=device); no = torch.empty_like(o)
     r = torch.empty(Bg, 1, device=device); gm = torch.empty(Bg, 1, device=device)
     nt = torch.empty(Bg, 1, dtype=torch.bool, device=device); ac = torch.empty(Bg, 1, dtype=torch.int64, device=device)
-    sec = time_kernel(lambda: ring.gather(idx, o, no, r, gm, nt, ac), 100, torch)
+    sec = time_kernel_graph(lambda: ring.gather(idx, o, no, r, gm, nt, ac), 40, torch)
     nbytes = Bg * (2 * 4 * 7056 + 2 * 4 * 7056 * 4 + 43)
     out["gather_atari_u8_B512"] = {"us": round(sec * 1e6, 2), "algorithmic_bytes": nbytes,
                                    "achieved_gbs": round(nbytes / sec / 1e9, 1),
