@@ -33,6 +33,23 @@ __device__ __forceinline__ float row_sum(float v, float *scratch)
     return t;
 }
 
+// two sums in one pass (one pair of barriers instead of two)
+template <int TPR>
+__device__ __forceinline__ float2 row_sum2(float a, float b, float2 *scratch2)
+{
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (TPR == 32) return make_float2(a, b);
+    const int w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane_id() == 0) scratch2[w] = make_float2(a, b);
+    __syncthreads();
+    float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < LN_THREADS / 32; ++k) { t.x += scratch2[k].x; t.y += scratch2[k].y; }
+    return t;
+}
+
 // TPR threads per row (32: one warp, 8 rows per CTA; 256: one CTA), SLOTS float4 per thread
 template <int TPR, int SLOTS>
 __global__ void __launch_bounds__(LN_THREADS) ln_fwd_kernel(long long rows, int F4, float eps, const float4 *__restrict__ x,
@@ -94,24 +111,20 @@ __global__ void __launch_bounds__(LN_THREADS) ln_fwd_kernel(long long rows, int 
 // dx = rstd * (g - mean_j(g) - xhat * mean_j(g * xhat)),  g = dy * gamma,  xhat = (x - mean) * rstd
 // part_g[blockIdx][F], part_b[blockIdx][F]: this CTA's sums over its rows of dy * xhat and dy
 template <int TPR, int SLOTS>
-__global__ void __launch_bounds__(LN_THREADS) ln_bwd_kernel(long long rows, int F4, const float4 *__restrict__ x,
+__global__ void __launch_bounds__(LN_THREADS, (TPR == 256 ? 3 : 1)) ln_bwd_kernel(long long rows, int F4, const float4 *__restrict__ x,
                                                             const float4 *__restrict__ dy, const float4 *__restrict__ gamma,
                                                             const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
                                                             float4 *__restrict__ dx, float4 *__restrict__ part_g,
                                                             float4 *__restrict__ part_b)
 {
-    __shared__ float scratch[LN_THREADS / 32];
+    __shared__ float2 scratch2[LN_THREADS / 32];
     extern __shared__ float4 colsum[];                       // TPR == 32: [2][F4] CTA-level combine of the 8 warps
     constexpr int RPC = LN_THREADS / TPR;
     const int lr = threadIdx.x % TPR, grp = threadIdx.x / TPR;
     const float inv_f = 1.0f / (float)(F4 * 4);
-    float4 ag[SLOTS], ab[SLOTS], gm[SLOTS];
+    float4 ag[SLOTS], ab[SLOTS];
 #pragma unroll
-    for (int k = 0; k < SLOTS; ++k) {
-        ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int c = lr + k * TPR;
-        gm[k] = (gamma && c < F4) ? __ldg(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
-    }
+    for (int k = 0; k < SLOTS; ++k) ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     // every thread of a CTA must take the same number of trips when the row reduction uses __syncthreads
     const long long trips = (rows + (long long)gridDim.x * RPC - 1) / ((long long)gridDim.x * RPC);
     for (long long it = 0; it < trips; ++it) {
@@ -132,13 +145,14 @@ __global__ void __launch_bounds__(LN_THREADS) ln_bwd_kernel(long long rows, int 
                 xh[k].z = (__uint_as_float(xu.z) - mean) * rstd; xh[k].w = (__uint_as_float(xu.w) - mean) * rstd;
                 ag[k].x += d.x * xh[k].x; ag[k].y += d.y * xh[k].y; ag[k].z += d.z * xh[k].z; ag[k].w += d.w * xh[k].w;
                 ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
-                g[k].x = d.x * gm[k].x; g[k].y = d.y * gm[k].y; g[k].z = d.z * gm[k].z; g[k].w = d.w * gm[k].w;
+                const float4 gm = gamma ? __ldg(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);      // L1-resident
+                g[k].x = d.x * gm.x; g[k].y = d.y * gm.y; g[k].z = d.z * gm.z; g[k].w = d.w * gm.w;
                 s1 += (g[k].x + g[k].y) + (g[k].z + g[k].w);
                 s2 += (g[k].x * xh[k].x + g[k].y * xh[k].y) + (g[k].z * xh[k].z + g[k].w * xh[k].w);
             }
         }
-        const float m1 = row_sum<TPR>(s1, scratch) * inv_f;
-        const float m2 = row_sum<TPR>(s2, scratch) * inv_f;
+        const float2 ss = row_sum2<TPR>(s1, s2, scratch2);
+        const float m1 = ss.x * inv_f, m2 = ss.y * inv_f;
 #pragma unroll
         for (int k = 0; k < SLOTS; ++k) {
             const int c = lr + k * TPR;
