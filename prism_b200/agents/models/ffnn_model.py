@@ -2,8 +2,8 @@
 
 Constructor arguments and the ``model.<i>`` parameter names match the reference class
 (prism/agents/models/ffnn_model.py:46-97) so that state_dicts are interchangeable; the
-layer stack is: [LN(in)] Linear act ... [LN] Linear [output_act].  Dense layers are plain
-library GEMMs (cuBLAS through PyTorch).
+layer stack is: [LN(in)] Linear act ... [LN] Linear [output_act], evaluated by ops.run_sequential
+(fused Linear+ReLU launches, tcgen05 GEMMs and fused LayerNorm kernels for large activations).
 """
 import numpy as np
 import torch

@@ -8,7 +8,8 @@ and seeds carry over.  Differences underneath:
     embedding the reference materialises with torch.tile (:70) never exists;
   * target construction, the pairwise tau x tau' quantile-Huber loss and its gradient are one
     fused warp-per-row kernel (pb_iqn_qh_loss) instead of ~30 ATen kernels and 6 B*T'*T temporaries.
-Dense layers are cuBLAS GEMMs through PyTorch.
+Dense layers go through ops.linear / ops.phi_times_x: tcgen05 3xTF32 GEMMs for the (T*B)-row layers (the
+phi(tau) (.) x product fused into the GEMM epilogue), the fp32 FFMA cluster kernel for small ones.
 """
 import numpy as np
 import torch

@@ -227,10 +227,11 @@ class _Linear(torch.autograd.Function):
         return dx, dw, db, None
 
 
-# Above this many rows the fused split-K SIMT kernel loses to a plain library SGEMM (measured on B200,
-# profiles/microbench_r01.txt: 2048 x 256 x 1024 -> 46 us vs cuBLAS 34 us; 256 rows -> 14 us vs 22 us).
-# Learner-batch-sized layers (Q heads, ensemble) stay on the fused kernel; the (T*B)-row IQN layers are plain
-# library GEMMs until the tcgen05 3xTF32 kernel lands.
+# Dispatch of a dense layer (DESIGN.md sections 4 and 4.1):
+#   * >= TC_MIN_FLOPS and >= TC_MIN_ROWS rows: tcgen05 3xTF32 GEMM (csrc/tc_gemm.cu), forward and both gradients;
+#   * up to FUSED_LINEAR_MAX_ROWS rows: fp32 FFMA cluster split-K kernel (csrc/linear.cu) -- learner-batch-sized Q heads;
+#   * anything else (e.g. the 18-action output layer of the (T*B)-row IQN head, whose rows are not 16-byte
+#     aligned): library SGEMM.
 FUSED_LINEAR_MAX_ROWS = 512
 
 
@@ -302,7 +303,7 @@ class _LinearTC(torch.autograd.Function):
         return dx, dw, db, None
 
 
-TENSOR_CORE_LINEAR = True      # module switch for A/B timing; the tcgen05 path is the default for large layers
+TENSOR_CORE_LINEAR = True      # module switch for A/B timing
 TC_MIN_ROWS = 256              # an M = 128 tile needs rows to fill it
 TC_MIN_FLOPS = float(__import__('os').environ.get('PB_TC_MIN_FLOPS', 2.0e8))           # below this a layer is launch-bound and stays on the fused SIMT kernel / library
 
