@@ -442,6 +442,14 @@ int pb_layer_norm_fwd(long long rows, int F, float eps, const float *x, const fl
 int pb_layer_norm_bwd(long long rows, int F, const float *x, const float *dy, const float *gamma, const float *mean,
                       const float *rstd, float *dx, float *dgamma, float *dbeta, float *partials, void *stream);
 
+/* ReLU backward + bias gradient of a dense layer (heads stacked (heads, rows, N) matrices) in one pass:
+ * dz = dy * [y > 0] (y NULL: no activation, dz untouched) and dbias[h] = column sums of dz -- the autograd glue
+ * around the tensor-core GEMMs (nn.Linear + ReLU backward, ffnn_model.py:61-76).  N % 4 == 0; partials =
+ * heads * pb_relu_bwd_bias_strips(rows) * N floats of scratch. */
+int pb_relu_bwd_bias_strips(long long rows);
+int pb_relu_bwd_bias(int heads, long long rows, int N, const float *dy, const float *y, float *dz, float *dbias,
+                     float *partials, void *stream);
+
 /* total_loss = mean_b(dist*w) + mean_b(q'*w);  td_b = 0.5*dist + 0.5*q' | dist | |q'|
  * (composite_model.py:135-142, agent.py:58-64) with q' = q_scale * (q - *q_offset)
  * (q_ensemble.py:92: q_loss_weight * (q_loss - theil * coef); q_offset NULL = 0).

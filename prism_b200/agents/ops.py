@@ -284,8 +284,20 @@ class _LinearTC(torch.autograd.Function):
     def backward(ctx, dy):
         xc, wc, y = ctx.saved_tensors
         K, M, N, J = ctx.dims
-        dz = _c(dy * (y > 0) if ctx.act else dy)
-        dx = dw = db = None
+        dy = _c(dy)
+        lib = _lib.load()
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        dz, db = dy, None
+        if ctx.act or want_db:
+            # ReLU mask + bias gradient in one pass (pb_relu_bwd_bias) instead of compare + multiply + sum(dim)
+            strips = lib.pb_relu_bwd_bias_strips(M)
+            partials = torch.empty(K * strips * N, dtype=torch.float32, device=dy.device)
+            dz = torch.empty_like(dy) if ctx.act else dy
+            db = torch.empty(K, N, dtype=torch.float32, device=dy.device) if want_db else None
+            _lib.check(lib.pb_relu_bwd_bias(K, M, N, dy.data_ptr(), _lib.ptr(y) if ctx.act else None,
+                                            dz.data_ptr() if ctx.act else None, _lib.ptr(db), partials.data_ptr(),
+                                            _stream(dy)), "pb_relu_bwd_bias")
+        dx = dw = None
         if ctx.needs_input_grad[0]:
             # dX (M x J) = dZ (M x N) . W (N x J): B operand is W read as its transpose (b_major 1)
             if ctx.shared:
@@ -298,8 +310,6 @@ class _LinearTC(torch.autograd.Function):
             # dW (N x J) = dZ^T (N x M) . X (M x J): both operands read as transposes
             dw = torch.empty(K, N, J, dtype=torch.float32, device=dz.device)
             tc_gemm(dw, dz, 1, N, M * N, xc, 1, J, 0 if ctx.shared else M * J, K, N, J, M)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dz.sum(dim=1)
         return dx, dw, db, None
 
 

@@ -45,9 +45,76 @@ __global__ void __launch_bounds__(256) iqn_phi_bwd_kernel(int n, int B, int F4, 
     dbp[i] = ab;
 }
 
+// ReLU backward + bias gradient of a dense layer in one pass: dz = dy * [y > 0] (or dy itself), and per-strip column
+// sums of dz -- replaces ATen's compare + multiply + sum(dim) (three passes over an (M x N) tensor per layer).
+// Block = one strip of `strip` rows; thread t owns the 4-column groups t, t + 256, ...; coalesced 128-bit accesses.
+__global__ void __launch_bounds__(256) relu_bwd_colsum_kernel(long long rows, int N4, int strip, const float4 *__restrict__ dy,
+                                                              const float4 *__restrict__ y, float4 *__restrict__ dz,
+                                                              float4 *__restrict__ partial)
+{
+    const long long r0 = (long long)blockIdx.x * strip, r1 = min(rows, r0 + strip);
+    const size_t head = (size_t)blockIdx.y * rows * N4;                 // heads are stacked matrices
+    for (int c = threadIdx.x; c < N4; c += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (long long r = r0; r < r1; ++r) {
+            const size_t o = head + (size_t)r * N4 + c;
+            float4 d = dy[o];
+            if (y) {
+                const float4 m = y[o];
+                d.x = m.x > 0.f ? d.x : 0.f; d.y = m.y > 0.f ? d.y : 0.f;
+                d.z = m.z > 0.f ? d.z : 0.f; d.w = m.w > 0.f ? d.w : 0.f;
+                dz[o] = d;
+            }
+            acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+        }
+        partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * N4 + c] = acc;
+    }
+}
+
+// out[h][c] = sum over strips (fixed order); 32 columns x 32 strip groups per block
+__global__ void __launch_bounds__(1024) colsum_reduce_kernel(int nstrips, int N, const float *__restrict__ partial,
+                                                             float *__restrict__ out)
+{
+    __shared__ float sm[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x, r = threadIdx.y;
+    const float *p = partial + (size_t)blockIdx.y * nstrips * N;
+    float a = 0.f;
+    if (c < N)
+        for (int k = r; k < nstrips; k += 32) a += p[(size_t)k * N + c];
+    sm[r][threadIdx.x] = a;
+    __syncthreads();
+    if (r == 0 && c < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t += sm[k][threadIdx.x];
+        out[(size_t)blockIdx.y * N + c] = t;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int pb_relu_bwd_bias_strips(long long rows) { long long s = (rows + 63) / 64; return (int)(s < 1 ? 1 : s); }
+
+// heads stacked (heads, rows, N) matrices.  y NULL: no activation (dz is not written; dz may be NULL).
+// partials: heads * pb_relu_bwd_bias_strips(rows) * N floats.  dbias: (heads, N), may be NULL.
+int pb_relu_bwd_bias(int heads, long long rows, int N, const float *dy, const float *y, float *dz, float *dbias,
+                     float *partials, void *stream)
+{
+    if (heads <= 0 || rows <= 0 || N <= 0 || (N % 4) != 0 || !dy || !partials || (y && !dz)) return PB_E_ARG;
+    if ((((uintptr_t)dy) | ((uintptr_t)y) | ((uintptr_t)dz) | ((uintptr_t)partials)) & 15) return PB_E_ARG;
+    const int strips = pb_relu_bwd_bias_strips(rows);
+    dim3 grid((unsigned)strips, (unsigned)heads);
+    PB_LAUNCH(relu_bwd_colsum_kernel, grid, 256, 0, stream, rows, N / 4, 64, reinterpret_cast<const float4 *>(dy),
+              reinterpret_cast<const float4 *>(y), reinterpret_cast<float4 *>(dz), reinterpret_cast<float4 *>(partials));
+    if (dbias) {
+        dim3 rgrid((unsigned)((N + 31) / 32), (unsigned)heads);
+        PB_LAUNCH(colsum_reduce_kernel, rgrid, dim3(32, 32), 0, stream, strips, N, partials, dbias);
+    }
+    return PB_OK;
+}
 
 int pb_iqn_phi_bwd(int n, int B, int F, const float *dh, const float *phi, const float *x, float *dpre, float *dx,
                    float *dbias_partial, void *stream)
