@@ -363,10 +363,17 @@ class FusedIngest:
 
     def consume(self):
         """Device half (capturable): scatter from the block of this replay's parity, then default priorities."""
+        self.consume_ring()
+        self.consume_tree()
+
+    def consume_tree(self):
+        if self.tree is not None:
+            self.tree.extend(self.n)
+
+    def consume_ring(self):
+        """The ring half only (touches no tree array: may run beside the priority write-back)."""
         ring, a, b = self.ring, self.slots[0], self.slots[1]
         _lib.check(ring._lib.pb_store_scatter_dbuf(ring._ref, self.n, a.d_rows[0].data_ptr(), a.d_rows[1].data_ptr(),
                                                    a.d_meta.data_ptr(), b.d_rows[0].data_ptr(), b.d_rows[1].data_ptr(),
                                                    b.d_meta.data_ptr(), self.counter.data_ptr(), ring._stream()),
                    "pb_store_scatter_dbuf")
-        if self.tree is not None:
-            self.tree.extend(self.n)

@@ -184,10 +184,17 @@ class LearnerStep:
             if not self.overlap_write_back:
                 return
             self._side.wait_stream(cur)
+            side2 = _ops.fork_stream(self.device, "ingest") if consume else None
+            if consume:
+                # the ring scatter touches no tree array: a third branch, beside the priority write-back
+                side2.wait_stream(cur)
+                with torch.cuda.stream(side2):
+                    self.ingest.consume_ring()
             with torch.cuda.stream(self._side):
                 tree.update_priority(idx, td, sorted=self.sorted)      # |td| is taken inside the kernel
                 if consume:
-                    self.ingest.consume()      # next iteration's new steps: scatter + default priorities, same branch
+                    self.ingest.consume_tree()         # default priorities of the new steps, after the write-back
+                    self._side.wait_stream(side2)
                 if self.prefetch:
                     self._sample_gather(u, self._shadow)      # next iteration's batch
 
