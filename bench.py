@@ -675,7 +675,8 @@ def run_ours(args):
         u_host.numpy()[:] = pre_u[i]
         step.step(u=u_host, ingest=(pre["stream"][sl], pre["obs"][sl], pre["action"][sl], pre["reward"][sl],
                                     pre["done"][sl], pre["trunc"][sl], pre["next_obs"][sl]))
-        step.copy_loss_to(loss_host)
+        # the loss read-back (D2H, 4 bytes into a pinned scalar) is a node of the step graph: step.loss_host
+    loss_host = step.enable_loss_readback()
     for _ in range(max(3, args.warmup)):
         e2e_one()
     barrier()
@@ -694,7 +695,7 @@ def run_ours(args):
         t = torch.tensor([e2e_sec], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_sec = float(t.item())
-    h2d = step.ingest.h2d_bytes + step.B_global * 8
+    h2d = step.ingest.h2d_bytes                       # staged steps + the fp64 uniforms, one block per iteration
     e2e = {"value": BATCH * world * e2e_steps / e2e_sec, "unit": "transitions/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": 4, "updates_per_s": e2e_steps / e2e_sec,
            "host_wall_s": round(wall, 4), "loss": float(loss_host)}

@@ -224,6 +224,10 @@ int pb_store_scatter(const pb_store *s, long long n, const void *obs, const void
 int pb_store_scatter_dbuf(const pb_store *st, long long n, const void *obs_a, const void *next_obs_a,
                           const pb_step_meta *meta_a, const void *obs_b, const void *next_obs_b,
                           const pb_step_meta *meta_b, long long *replay_counter, void *stream);
+/* dst[0..n) = (parity of *replay_counter + bias) ? src_b : src_a -- the per-iteration fp64 uniforms ride in the same
+ * double-buffered staging block as the new steps and are picked by the same replay counter. */
+int pb_select_copy_f64(double *dst, const double *src_a, const double *src_b, const long long *replay_counter,
+                       long long bias, long long n, void *stream);
 
 /* TimestepBuffer._timesteps_to_batch + _compute_n_step + _stack_obs_into
  * (prism/experience/timestep_buffer.py:79-257) fused: for each sampled slot walk

@@ -90,6 +90,7 @@ SIGNATURES = {
     "pb_tree_sample_global": [_TREE, _I, _I, _P, _LL, _P, _F, _P, _P, _P, _P],
     "pb_store_extend_plan": [_LL, _LL, _I, _LL, _LL, _P, _P, _P, _P, _P, _P],
     "pb_store_scatter": [_STORE, _LL, _P, _P, _P, _P],
+    "pb_select_copy_f64": [_P, _P, _P, _P, _LL, _LL, _P],
     "pb_store_scatter_dbuf": [_STORE, _LL, _P, _P, _P, _P, _P, _P, _P, _P],
     "pb_store_gather": [_STORE, _LL, _P, _P, _P, _P, _P, _P, _P, _P],
     "pb_store_nstep": [_STORE, _LL, _P, _P, _P, _P, _P, _P, _P],

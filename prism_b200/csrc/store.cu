@@ -128,6 +128,17 @@ __global__ void __launch_bounds__(128) store_scatter_dbuf_kernel(StoreView s, lo
 
 __global__ void counter_inc_kernel(long long *counter) { *counter += 1; }
 
+// dst = (parity of (*counter + bias)) ? src_b : src_a  -- picks this replay's half of a double-buffered staging block
+// (the per-iteration uniforms ride in the same block as the new steps)
+__global__ void __launch_bounds__(256) select_copy_kernel(double *__restrict__ dst, const double *__restrict__ src_a,
+                                                          const double *__restrict__ src_b,
+                                                          const long long *__restrict__ counter, long long bias, long long n)
+{
+    const double *src = ((*counter + bias) & 1) ? src_b : src_a;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
 // ---- n-step walk (uniform across the CTA: every thread reads the same addresses) ----
 struct Walk {
     float ret, gamma;
@@ -367,6 +378,16 @@ int pb_store_scatter_dbuf(const pb_store *st, long long n, const void *obs_a, co
     PB_LAUNCH(store_scatter_dbuf_kernel, grid, 128, 0, stream, v, n, (const uint8_t *)obs_a, (const uint8_t *)next_obs_a,
               meta_a, (const uint8_t *)obs_b, (const uint8_t *)next_obs_b, meta_b, (const long long *)replay_counter);
     PB_LAUNCH(counter_inc_kernel, 1, 1, 0, stream, replay_counter);
+    return PB_OK;
+}
+
+int pb_select_copy_f64(double *dst, const double *src_a, const double *src_b, const long long *replay_counter,
+                       long long bias, long long n, void *stream)
+{
+    if (!dst || !src_a || !src_b || !replay_counter || n <= 0) return PB_E_ARG;
+    long long nb = (n + 255) / 256;
+    if (nb > 64) nb = 64;
+    PB_LAUNCH(select_copy_kernel, (unsigned)nb, 256, 0, stream, dst, src_a, src_b, replay_counter, bias, n);
     return PB_OK;
 }
 

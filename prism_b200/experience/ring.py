@@ -256,19 +256,25 @@ class IngestSlot:
     learner iteration (the reference collects `timesteps_per_iteration` = 4 steps per iteration).
     Host half: fill() writes the pinned block and runs the link planner."""
 
-    def __init__(self, ring, n):
+    def __init__(self, ring, n, n_uniforms=0):
         self.ring, self.n = ring, int(n)
         E, dt, dev = ring.obs_elems, ring.storage_dtype, ring.device
         esz = torch.empty(0, dtype=dt).element_size()
         rows_bytes = 2 * self.n * E * esz
         rows_bytes_al = (rows_bytes + 63) // 64 * 64
-        # ONE pinned block [obs rows | next_obs rows | pb_step_meta records] and its device mirror: one H2D copy
-        self.h_block = torch.zeros(rows_bytes_al + self.n * 64, dtype=torch.uint8).pin_memory()
+        # ONE pinned block [obs rows | next_obs rows | pb_step_meta records | fp64 uniforms] and its device mirror: one
+        # H2D copy per iteration
+        self.n_uniforms = int(n_uniforms)
+        u_off = rows_bytes_al + self.n * 64
+        self.h_block = torch.zeros(u_off + 8 * self.n_uniforms, dtype=torch.uint8).pin_memory()
         self.d_block = torch.zeros_like(self.h_block, device=dev)
         self.h_rows = self.h_block[:rows_bytes].view(dt).view(2, self.n, E)
         self.d_rows = self.d_block[:rows_bytes].view(dt).view(2, self.n, E)
-        self.h_meta = self.h_block[rows_bytes_al:]
-        self.d_meta = self.d_block[rows_bytes_al:]
+        self.h_meta = self.h_block[rows_bytes_al:u_off]
+        self.d_meta = self.d_block[rows_bytes_al:u_off]
+        self.h_u = self.h_block[u_off:].view(torch.float64) if self.n_uniforms else None
+        self.d_u = self.d_block[u_off:].view(torch.float64) if self.n_uniforms else None
+        self.h_u_np = self.h_u.numpy() if self.n_uniforms else None
         self.meta = self.h_meta.numpy().view(np.dtype(_lib.STEP_META_DTYPE))
         self.rows_np = self.h_rows.numpy()
         self.stream = np.zeros(self.n, dtype=np.int32)
@@ -318,10 +324,11 @@ class FusedIngest:
     block by the parity of a device-resident replay counter, then the trees get the default priorities.
     Steps staged before iteration k's launch become sampleable from iteration k+1 on."""
 
-    def __init__(self, ring, tree, n):
+    def __init__(self, ring, tree, n, n_uniforms=0):
         import ctypes as C
         self.ring, self.tree, self.n = ring, tree, int(n)
-        self.slots = [IngestSlot(ring, n), IngestSlot(ring, n)]
+        self.n_uniforms = int(n_uniforms)
+        self.slots = [IngestSlot(ring, n, n_uniforms), IngestSlot(ring, n, n_uniforms)]
         dev = ring.device
         self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.copy_stream = torch.cuda.Stream(device=dev)
@@ -339,7 +346,15 @@ class FusedIngest:
         self.calls = 0
         self.h2d_bytes = self.slots[0].h2d_bytes
 
-    def stage(self, stream_ids, obs, action, reward, done, trunc, next_obs, main_stream):
+    def select_uniforms(self, dst, after_counter_inc):
+        """Capturable: copy this replay's uniforms out of its staging block into ``dst`` (device fp64).
+        ``after_counter_inc``: whether the scatter (which bumps the replay counter) already ran in stream order."""
+        a, b = self.slots
+        _lib.check(self._lib.pb_select_copy_f64(dst.data_ptr(), a.d_u.data_ptr(), b.d_u.data_ptr(), self.counter.data_ptr(),
+                                                -1 if after_counter_inc else 0, self.n_uniforms, self.ring._stream()),
+                   "pb_select_copy_f64")
+
+    def stage(self, stream_ids, obs, action, reward, done, trunc, next_obs, main_stream, u=None):
         """Host half: fill the pinned block of this parity, copy it on the copy stream (after the replay that last
         read the device block), make ``main_stream`` (raw handle) wait for the copy.  Returns the parity."""
         lib = self._lib
@@ -348,6 +363,8 @@ class FusedIngest:
         if self._copied_valid[p]:
             lib.pb_event_synchronize(self.copied[p])          # pinned block free again (two iterations old)
         self.slots[p].fill(stream_ids, obs, action, reward, done, trunc, next_obs)
+        if u is not None:
+            self.slots[p].h_u_np[:] = u
         if self._consumed_valid[p]:
             lib.pb_stream_wait_event(self._copy_handle, self.consumed[p])
         dst, src, nbytes = self._ptrs[p]

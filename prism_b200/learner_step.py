@@ -56,6 +56,7 @@ class LearnerStep:
         self.sorted = self.world_size > 1 or self.tree.mode == PrioritizedTree.MODE_STRATIFIED
         self.prefetch = bool(prefetch)
         self._primed, self._seen_mutations = False, None
+        self.loss_host = None            # enable_loss_readback(): pinned fp32 scalar written by every step
         # static batch, shared by the buffer (writes) and the agent (reads)
         buffer._flush()
         if self.prefetch:
@@ -166,9 +167,12 @@ class LearnerStep:
     def _body(self, refresh_table, draw, consume=False):
         tree, ring, agent, b = self.tree, self.ring, self.agent, self.buffer
         u = None if draw else self.u            # None: uniforms are drawn inside the sampling kernel
+        u_sel = consume and getattr(self, "_u_in_block", False)
         if self.prefetch:
             self._live_arena.copy_(self._shadow_arena)          # batch sampled on the previous iteration's tail
         else:
+            if u_sel:
+                self.ingest.select_uniforms(self.u, after_counter_inc=False)
             self._sample_gather(u, {"idx": self.idx, "weight": self.weight, "obs": b._obs, "next_obs": b._next_obs,
                                     "reward": b._reward, "gamma": b._gamma, "nonterminal": b._nonterminal,
                                     "action": b._action})
@@ -195,12 +199,17 @@ class LearnerStep:
                 if consume:
                     self.ingest.consume_tree()         # default priorities of the new steps, after the write-back
                     self._side.wait_stream(side2)
+                if self.prefetch and u_sel:
+                    self.ingest.select_uniforms(self.u, after_counter_inc=True)
                 if self.prefetch:
                     self._sample_gather(u, self._shadow)      # next iteration's batch
 
         dl, ql, total, td = agent._loss_and_backward(self.batch, w, agent.target_model, after_loss=write_back)
         agent._static_distribution_loss, agent._static_q_loss, agent._static_total_loss = dl, ql, total
         agent._optimizer_step(refresh_table=refresh_table)
+        if self.loss_host is not None and total is not None:
+            # device -> host read of the step's result as a node of the same graph (pinned scalar)
+            self.loss_host.copy_(total.detach(), non_blocking=True)
         if self.overlap_write_back:
             cur.wait_stream(self._side)
         else:
@@ -208,6 +217,8 @@ class LearnerStep:
             if consume:
                 self.ingest.consume()
             if self.prefetch:
+                if u_sel:
+                    self.ingest.select_uniforms(self.u, after_counter_inc=True)
                 self._sample_gather(u, self._shadow)
         return total
 
@@ -220,7 +231,13 @@ class LearnerStep:
         concurrently with backward / Adam (FusedIngest); they are sampleable from the next iteration on."""
         self.buffer._flush()
         draw = u is None
-        if not draw:
+        # host uniforms + fused ingest: the uniforms ride in the ingest's staging block (one H2D copy per iteration) and
+        # are picked inside the graph by the replay counter
+        u_in_block = (not draw) and ingest is not None and isinstance(u, torch.Tensor) and u.device.type == "cpu" \
+            and u.dtype == torch.float64 and u.numel() == self.u.numel()
+        if u_in_block:
+            pass
+        elif not draw:
             if u.device.type == "cpu" and u.dtype == torch.float64 and u.is_contiguous() and u.numel() == self.u.numel():
                 # host uniforms (pinned): one raw async copy on the step's stream
                 _lib.check(self._lib.pb_copy_h2d_async(self.u.data_ptr(), u.data_ptr(), 8 * self.u.numel(),
@@ -232,10 +249,11 @@ class LearnerStep:
             n = len(ingest[0])
             if self.ingest is None or self.ingest.n != n:
                 from .experience.ring import FusedIngest
-                self.ingest = FusedIngest(self.ring, self.tree, n)
+                self.ingest = FusedIngest(self.ring, self.tree, n, n_uniforms=self.u.numel())
             main = torch.cuda.current_stream(self.device).cuda_stream
-            parity = self.ingest.stage(*ingest, main_stream=main)
-        if self.use_cuda_graph and (self.graph is None or (draw, consume) != self._graph_key):
+            parity = self.ingest.stage(*ingest, main_stream=main, u=u.numpy() if u_in_block else None)
+        self._u_in_block = u_in_block
+        if self.use_cuda_graph and (self.graph is None or (draw, consume, u_in_block) != self._graph_key):
             self._capture(draw, consume)
             self._primed = False                            # the warm-up iterations sampled into the shadow batch
         if self.prefetch and (not self._primed or getattr(self.buffer, "_mutations", 0) != self._seen_mutations):
@@ -249,6 +267,14 @@ class LearnerStep:
             self.ingest.mark_consumed(parity, main)
         self.agent.n_updates += 1
         return total
+
+    def enable_loss_readback(self):
+        """Every following step also copies its total loss into ``self.loss_host`` (pinned fp32 scalar): the
+        device -> host read is part of the step graph; synchronise before reading it on the host."""
+        if self.loss_host is None:
+            self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+            self.graph = None                      # recapture with the copy node
+        return self.loss_host
 
     def copy_loss_to(self, host_scalar):
         """Asynchronous device -> host read of the last step's total loss into a pinned fp32 scalar."""
@@ -281,7 +307,7 @@ class LearnerStep:
         self.tree.sum.copy_(tree_snap[0]); self.tree.min.copy_(tree_snap[1]); self.tree.state.copy_(tree_snap[2])
         self.u.copy_(u_snap)
         torch.cuda.set_rng_state(rng, self.device)
-        self._graph_key = (draw, consume)
+        self._graph_key = (draw, consume, getattr(self, "_u_in_block", False))
         opt.zero_grad(set_to_none=True)
         self.graph = None                                   # release the previous graph's pool before capturing anew
         self.graph = torch.cuda.CUDAGraph()

@@ -467,8 +467,9 @@ def test_fused_layer_norm_matches_fp64(rows, F_):
     assert rel_err(ln.bias.grad.cpu().numpy(), ref.bias.grad.numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("host_u", [False, True])
 @pytest.mark.parametrize("use_graph", [True, False])
-def test_fused_ingest_step_equals_separate_push_then_step(use_graph):
+def test_fused_ingest_step_equals_separate_push_then_step(use_graph, host_u):
     """LearnerStep.step(ingest=...) scatters the new steps inside the step graph (after the priority write-back,
     concurrently with backward) from double-buffered staging blocks.  Same uniforms, same data: it must produce the
     same losses, parameters, ring and trees as `step(); push(new steps)` run one after the other."""
@@ -498,6 +499,8 @@ def test_fused_ingest_step_equals_separate_push_then_step(use_graph):
             new = (S["stream"][sl], S["obs"][sl], S["action"][sl], S["reward"][sl], S["done"][sl], S["trunc"][sl], succ[sl])
             u = torch.from_numpy(us[i]).to(DEV)
             if fused:
+                if host_u:                       # host uniforms ride in the ingest's staging block
+                    u = torch.from_numpy(us[i].copy())
                 losses.append(float(step.step(u=u, ingest=new)))
             else:
                 losses.append(float(step.step(u=u)))
