@@ -659,7 +659,7 @@ def run_ours(args):
     e2e_steps = args.steps
     n_pre = max(3, args.warmup) + e2e_steps
     pre = trace.chunk(n_pre * STEPS_PER_ITER)
-    rng = np.random.default_rng(2 + rank)
+    rng = np.random.default_rng(2)                 # global stratified sampling: every rank must see the SAME uniforms
     pre_u = rng.random((n_pre, step.B_global))
     u_hosts = [torch.empty(step.B_global, dtype=torch.float64).pin_memory() for _ in range(2)]
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
