@@ -59,22 +59,10 @@ class LearnerStep:
         self.loss_host = None            # enable_loss_readback(): pinned fp32 scalar written by every step
         # static batch, shared by the buffer (writes) and the agent (reads)
         buffer._flush()
+        self._n_rows = n_rows
+        self._live = None
         if self.prefetch:
-            # Software pipelining: the NEXT iteration's batch is sampled and gathered on the tail branch of this
-            # iteration (after the priority write-back and the fused ingest, i.e. exactly where the reference order
-            # puts it) into a shadow copy of the static batch, while backward / exchange / Adam run; the next
-            # replay starts with one copy shadow -> live.  Live and shadow are two flat arenas of identical layout.
-            from .experience.batch import Batch
-            self._live, self._live_arena = self._carve(n_rows)
-            self._shadow, self._shadow_arena = self._carve(n_rows)
-            lv = self._live
-            batch = Batch({"observation": lv["obs"],
-                           "next": Batch({"observation": lv["next_obs"], "reward": lv["reward"]},
-                                         batch_size=self.B_pad, device=d),
-                           "nonterminal": lv["nonterminal"], "gamma": lv["gamma"], "action": lv["action"]},
-                          batch_size=self.B_pad, device=d)
-            buffer.set_static_batch(batch)
-            self.idx, self.weight = lv["idx"], lv["weight"]
+            self._setup_prefetch()
         else:
             self.idx = torch.zeros(n_rows, dtype=torch.int64, device=d)
             self.weight = torch.zeros(n_rows, dtype=torch.float32, device=d)
@@ -116,6 +104,38 @@ class LearnerStep:
         self.overlap_write_back = _os.environ.get("PB_OVERLAP_WRITEBACK", "1") != "0"
 
     # ------------------------------------------------------------------------------------
+    def _setup_prefetch(self):
+        """Software pipelining: the NEXT iteration's batch is sampled and gathered on the tail branch of this
+        iteration (after the priority write-back and the fused ingest, i.e. exactly where the reference order puts it)
+        into a shadow copy of the static batch, while backward / exchange / Adam run; the next replay starts with one
+        copy shadow -> live.  Live and shadow are two flat arenas of identical layout."""
+        from .experience.batch import Batch
+        d = self.device
+        self._live, self._live_arena = self._carve(self._n_rows)
+        self._shadow, self._shadow_arena = self._carve(self._n_rows)
+        lv = self._live
+        batch = Batch({"observation": lv["obs"],
+                       "next": Batch({"observation": lv["next_obs"], "reward": lv["reward"]},
+                                     batch_size=self.B_pad, device=d),
+                       "nonterminal": lv["nonterminal"], "gamma": lv["gamma"], "action": lv["action"]},
+                      batch_size=self.B_pad, device=d)
+        self.buffer.set_static_batch(batch)
+        self.idx, self.weight = lv["idx"], lv["weight"]
+
+    def set_prefetch(self, flag):
+        """Switch the tail-branch prefetch on or off (the step graph is re-captured on the next call)."""
+        flag = bool(flag)
+        if flag == self.prefetch:
+            return
+        self.prefetch = flag
+        if flag and self._live is None:
+            self._setup_prefetch()
+            self.batch = self.buffer.get_static_batch()
+            self.agent.set_static_batch(self.batch)
+        self.graph, self._primed = None, False
+        if self.peer is not None:
+            self.agent.optimizer.peer_trailing_barrier = flag
+
     def _carve(self, n_rows):
         """One flat arena holding a static batch + the sampled indices / weights; returns (views, arena)."""
         import numpy as np
