@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) conv3x3_relu_fwd_kernel(ConvDims d, const
 }
 
 // partial[g][e], e in [0, OC*C*9) = dW, e in [OC*C*9, OC*C*9+OC) = db, for the samples of CTA g
-__global__ void __launch_bounds__(256) conv3x3_relu_bwd_kernel(ConvDims d, const float *__restrict__ x,
+__global__ void __launch_bounds__(1024) conv3x3_relu_bwd_kernel(ConvDims d, const float *__restrict__ x,
                                                                const float *__restrict__ out,
                                                                const float *__restrict__ dout,
                                                                float *__restrict__ partial)
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) conv3x3_relu_bwd_kernel(ConvDims d, const
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const int e = threadIdx.x + q * 256;
+            const int e = threadIdx.x + q * blockDim.x;
             if (e >= ne) break;
             float a = 0.0f;
             if (e < nw) {
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) conv3x3_relu_bwd_kernel(ConvDims d, const
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const int e = threadIdx.x + q * 256;
+        const int e = threadIdx.x + q * blockDim.x;
         if (e < ne) partial[(size_t)blockIdx.x * ne + e] = acc[q];
     }
 }
@@ -169,7 +169,11 @@ int pb_conv3x3_relu_bwd(int B, int H, int W, int C, int OC, const float *x, cons
     const int groups = pb_conv3x3_relu_bwd_groups(B);
     const size_t smem = sizeof(float) * (size_t)(H * W * C + OC * d.OH * d.OW);
     if (smem > 48 * 1024) return PB_E_UNSUPPORTED;
-    PB_LAUNCH(conv3x3_relu_bwd_kernel, (unsigned)groups, 256, smem, stream, d, x, out, dout, partial_scratch);
+    // one gradient element per thread when they fit (880 for the MinAtar embedding): the 64-tap dependent FMA chain
+    // per element is the kernel's latency
+    const int ne_all = OC * C * 9 + OC;
+    const int bthreads = ne_all > 512 ? 1024 : (ne_all > 256 ? 512 : 256);
+    PB_LAUNCH(conv3x3_relu_bwd_kernel, (unsigned)groups, bthreads, smem, stream, d, x, out, dout, partial_scratch);
     const int ne = OC * C * 9 + OC;
     PB_LAUNCH(conv_bwd_reduce_kernel, (unsigned)((ne + 7) / 8), 256, 0, stream, groups, OC * C * 9, OC,
               partial_scratch, dw, db);
