@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g)
     }
     cluster.sync();
     const int S = g.splits, rank = (int)cluster.block_rank();
-    const int rows_per = TM / S;                           // S in {2,4,8}
+    const int rows_per = TM / S;                           // S in {2,4,8,16}
     for (int e = t; e < rows_per * TN; e += 256) {
         const int r = rank * rows_per + e / TN, c = e % TN;
         float v = 0.f;
@@ -236,10 +236,12 @@ int pick_splits(long long tiles, int total_chunks)
 {
     static int forced = -1;                         // PB_GEMM_SPLITS=n pins the split factor (tuning experiments)
     if (forced < 0) { const char *e = getenv("PB_GEMM_SPLITS"); forced = e ? atoi(e) : 0; }
-    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return total_chunks >= forced ? forced : 1;
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) return total_chunks >= forced ? forced : 1;
+    static int max_split = -1;                      // PB_GEMM_MAX_SPLIT=16 allows the non-portable 16-CTA cluster
+    if (max_split < 0) { const char *e = getenv("PB_GEMM_MAX_SPLIT"); max_split = e ? atoi(e) : 8; }
     const int sms = pb_sm_count();
     int s = 1;
-    while (s < 8 && tiles * (s * 2) <= 2LL * sms && total_chunks / (s * 2) >= 2) s *= 2;
+    while (s < max_split && tiles * (s * 2) <= 2LL * sms && total_chunks / (s * 2) >= 2) s *= 2;
     return s;
 }
 
@@ -250,6 +252,14 @@ int launch_gemm(GemmArgs g, int batch, void *stream)
     const int n_tiles = (g.N + TN - 1) / TN;
     const int total_chunks = g.n_seg * ((g.K + TK - 1) / TK);
     g.splits = pick_splits((long long)g.m_tiles * n_tiles * batch, total_chunks);
+    if (g.splits > 8) {
+        static bool allowed = false;                // one flag per template instantiation
+        if (!allowed) {
+            cudaError_t ea = cudaFuncSetAttribute(gemm_kernel<AK, BK, ROWSUM>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (ea != cudaSuccess) return (int)ea;
+            allowed = true;
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n_tiles, (unsigned)(g.m_tiles * batch), (unsigned)g.splits);
     cfg.blockDim = dim3(256);
