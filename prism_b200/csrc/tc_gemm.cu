@@ -129,6 +129,7 @@ struct TcParams {
     int a_batched, b_batched;
     int tiles_m, tiles_n;
     int bn;                        // tile width of this launch (fix-up kernel)
+    int fix_by_boundary;           // fix-up grid: 1 = one block column per CTA-range boundary, 0 = one per tile
     long long work, per_cta;       // stream-K: work = tiles * kb_total K blocks, dealt out in equal contiguous ranges
     int act;                       // 0 none, 1 ReLU
     int split_mode;                // 0: hi = raw word (hardware truncation); 1: hi rewritten as cvt.rna.tf32
@@ -500,14 +501,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-// Stream-K fix-up: block (tile, strip of FIX_ROWS rows) sums the partial tiles of a cut tile in CTA order (a
+// Stream-K fix-up: block (range boundary, strip of FIX_ROWS rows) sums the partial tiles of a cut tile in CTA order (a
 // fixed order: results do not depend on scheduling), applies bias / ReLU / multiplier and writes C.
 constexpr int FIX_ROWS = 4;
 
 __global__ void __launch_bounds__(256) tc_streamk_fixup_kernel(TcParams g)
 {
     const int kb_total = g.kblocks * g.kbatches;
-    const long long t = blockIdx.x;
+    // many tiles, few cuts: one block column per CTA-range boundary -- the tile it falls into is cut (unless the boundary
+    // sits on a tile edge); a tile holding several boundaries is summed at its first one.  Few tiles: one per tile.
+    long long t = blockIdx.x;                                         // fix_by_boundary == 0: one block column per tile
+    if (g.fix_by_boundary) {
+        const long long wb = (long long)(blockIdx.x + 1) * g.per_cta;
+        if (wb >= g.work || wb % kb_total == 0) return;
+        t = wb / kb_total;
+        if ((long long)blockIdx.x * g.per_cta > t * kb_total) return;
+    }
     const long long w0 = t * kb_total, w1 = w0 + kb_total;
     const int c_first = (int)(w0 / g.per_cta), c_last = (int)((w1 - 1) / g.per_cta);
     if (c_first == c_last) return;                                    // whole tile: written by the GEMM epilogue
@@ -754,8 +763,9 @@ int pb_tc_gemm(int batch, int kbatches, int M, int N, int K,
         else rc = launch_bn<64, 32>(a_major, b_major, ta, tb, tc, g, (int)grid, stream);
     }
     if (rc != PB_OK) return rc;
-    if ((g.per_cta % kb_total) != 0) {                                 // some tile is cut
-        dim3 fgrid((unsigned)tiles, BM / FIX_ROWS);
+    if ((g.per_cta % kb_total) != 0 && grid > 1) {                     // some tile is cut
+        g.fix_by_boundary = tiles > grid - 1 ? 1 : 0;
+        dim3 fgrid((unsigned)(g.fix_by_boundary ? grid - 1 : tiles), BM / FIX_ROWS);
         PB_LAUNCH(tc_streamk_fixup_kernel, fgrid, 256, 0, stream, g);
     }
     return PB_OK;
