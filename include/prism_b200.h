@@ -454,6 +454,14 @@ int pb_relu_bwd_bias_strips(long long rows);
 int pb_relu_bwd_bias(int heads, long long rows, int N, const float *dy, const float *y, float *dz, float *dbias,
                      float *partials, void *stream);
 
+/* Theil index of the K heads' parameter L2 norms (q_ensemble.py:86-92) over stacked parameter tensors (K, ...), and
+ * its gradient.  table (device): per tensor {address, elements per head, offset of its gradient in `out`} as int64
+ * triples.  forward: *theil_out = mean_k r_k log r_k, coef[k] = d T / d theta_k divided by theta_k; partial = scratch
+ * of n_tensors * K * 8 floats; K <= 64.  backward: out = *upstream * coef[k] * theta. */
+int pb_theil_fwd(int n_tensors, int K, const long long *table, float *partial, float *theil_out, float *coef, void *stream);
+int pb_theil_bwd(int n_tensors, int K, const long long *table, const float *coef, const float *upstream, float *out,
+                 void *stream);
+
 /* total_loss = mean_b(dist*w) + mean_b(q'*w);  td_b = 0.5*dist + 0.5*q' | dist | |q'|
  * (composite_model.py:135-142, agent.py:58-64) with q' = q_scale * (q - *q_offset)
  * (q_ensemble.py:92: q_loss_weight * (q_loss - theil * coef); q_offset NULL = 0).

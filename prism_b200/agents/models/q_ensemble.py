@@ -144,10 +144,14 @@ class QEnsemble(nn.Module):
         tensor.  Returns None when the regulariser is off."""
         if self.ensemble_variation_coef == 0:
             return None
-        sq = sum(p.square().flatten(1).sum(dim=1) for p in self.stacked)
-        l2_set = sq.sqrt()
-        ratio = l2_set / l2_set.mean()
-        theil = (ratio * torch.log(ratio)).mean()
+        params = list(self.stacked)
+        if params[0].is_cuda and all(p.is_contiguous() and p.dtype == torch.float32 for p in params) and self.n_heads <= 64:
+            theil = ops.theil_index(params, self.__dict__.setdefault("_theil_cache", {}))   # 3 launches incl. backward
+        else:
+            sq = sum(p.square().flatten(1).sum(dim=1) for p in params)
+            l2_set = sq.sqrt()
+            ratio = l2_set / l2_set.mean()
+            theil = (ratio * torch.log(ratio)).mean()
         self.theil = theil.detach()              # logged value only: never keep an autograd graph on the module
         return theil
 

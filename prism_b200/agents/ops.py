@@ -473,6 +473,57 @@ def run_sequential(seq, x):
     return x
 
 
+class _TheilIndex(torch.autograd.Function):
+    """Theil index of the heads' parameter norms over stacked (K, ...) tensors: 2 launches forward, 1 backward
+    (csrc/theil.cu) instead of ~100 ATen launches (q_ensemble.py:86-92)."""
+
+    @staticmethod
+    def forward(ctx, table, total_numel, *stacked):
+        K = stacked[0].shape[0]
+        dev = stacked[0].device
+        lib = _lib.load()
+        partial = torch.empty(len(stacked) * K * 8, dtype=torch.float32, device=dev)
+        theil = torch.empty((), dtype=torch.float32, device=dev)
+        coef = torch.empty(K, dtype=torch.float32, device=dev)
+        _lib.check(lib.pb_theil_fwd(len(stacked), K, table.data_ptr(), partial.data_ptr(), theil.data_ptr(), coef.data_ptr(),
+                                    _stream(stacked[0])), "pb_theil_fwd")
+        ctx.save_for_backward(table, coef)
+        ctx.meta = (len(stacked), K, int(total_numel), [tuple(p.shape) for p in stacked])
+        return theil
+
+    @staticmethod
+    def backward(ctx, g):
+        table, coef = ctx.saved_tensors
+        n, K, total, shapes = ctx.meta
+        g = _c(g)
+        out = torch.empty(total, dtype=torch.float32, device=g.device)
+        _lib.check(_lib.load().pb_theil_bwd(n, K, table.data_ptr(), coef.data_ptr(), g.data_ptr(), out.data_ptr(), _stream(g)),
+                   "pb_theil_bwd")
+        grads, off = [], 0
+        for shp in shapes:
+            cnt = 1
+            for d in shp:
+                cnt *= d
+            grads.append(out[off:off + cnt].view(shp))
+            off += cnt
+        return (None, None) + tuple(grads)
+
+
+def theil_index(stacked, cache):
+    """stacked: list of contiguous CUDA parameters of shape (K, ...).  ``cache``: dict owned by the module (the address
+    table is rebuilt when a parameter moves)."""
+    key = tuple(p.data_ptr() for p in stacked)
+    if cache.get("key") != key:
+        rows, off = [], 0
+        for p in stacked:
+            per = p[0].numel()
+            rows += [p.data_ptr(), per, off]
+            off += p.numel()
+        cache["key"], cache["total"] = key, off
+        cache["table"] = torch.tensor(rows, dtype=torch.int64, device=stacked[0].device)
+    return _TheilIndex.apply(cache["table"], cache["total"], *stacked)
+
+
 UNIT_TOTAL_GRAD = False        # set by Agent._loss_and_backward while it runs total.backward() with the implicit gradient 1
 _ONES = {}
 

@@ -587,3 +587,24 @@ def test_acting_graph_equals_eager_acting(kind, monkeypatch):
         assert got.dtype == torch.int64 and got.shape == (N,)
         assert torch.equal(got.cpu(), want.cpu())
     assert len(agent._acting_graphs) == 1
+
+
+def test_fused_theil_index_matches_autograd():
+    """csrc/theil.cu against the ATen formulation of q_ensemble.py:86-92 (value and gradient w.r.t. every stacked
+    parameter), K = 10 heads."""
+    from prism_b200.agents import ops
+    g = torch.Generator().manual_seed(4)
+    shapes = [(10, 256, 64), (10, 256), (10, 64), (10, 3, 256), (10, 3)]
+    base = [torch.randn(s, generator=g) * (0.5 + 0.1 * torch.arange(10.0).view(10, *([1] * (len(s) - 1)))) for s in shapes]
+    dev_p = [b.to(DEV).requires_grad_(True) for b in base]
+    T = ops.theil_index(dev_p, {})
+    (T * 3.0).backward()
+    ref_p = [b.double().requires_grad_(True) for b in base]
+    sq = sum(p.square().flatten(1).sum(dim=1) for p in ref_p)
+    l2 = sq.sqrt()
+    ratio = l2 / l2.mean()
+    Tr = (ratio * torch.log(ratio)).mean()
+    (Tr * 3.0).backward()
+    assert abs(float(T) - float(Tr)) < 1e-6 * max(1.0, abs(float(Tr)))
+    for d, r in zip(dev_p, ref_p):
+        assert rel_err(d.grad.cpu().numpy(), r.grad.numpy()) < 1e-4
