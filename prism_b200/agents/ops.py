@@ -233,6 +233,7 @@ class _Linear(torch.autograd.Function):
 #   * anything else (e.g. the 18-action output layer of the (T*B)-row IQN head, whose rows are not 16-byte
 #     aligned): library SGEMM.
 FUSED_LINEAR_MAX_ROWS = 512
+NARROW_OUT, NARROW_MAX_ROWS = 32, 4096
 
 
 _TC_WORKSPACE = {}
@@ -393,7 +394,10 @@ def linear_heads(x, w, b, relu=False):
 
 def linear(x, weight, bias, relu=False):
     """nn.Linear (+ optional fused ReLU) on a 2-D input through the fused kernel."""
-    if x.shape[0] > FUSED_LINEAR_MAX_ROWS:
+    # narrow output layers (a handful of actions) of a few thousand rows stay on the fused FFMA kernel: the library picks
+    # 64-wide tiles for them (25 us for the 3 x 256 weight gradient of configs[0])
+    narrow = weight.shape[0] <= NARROW_OUT and x.shape[0] <= NARROW_MAX_ROWS
+    if x.shape[0] > FUSED_LINEAR_MAX_ROWS and not narrow:
         if _tc_eligible(x, x.shape[0], 1, *weight.shape):
             b = None if bias is None else bias.unsqueeze(0)
             return _LinearTC.apply(x, weight.unsqueeze(0), b, 1 if relu else 0).squeeze(0)
