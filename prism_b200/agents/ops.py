@@ -237,14 +237,18 @@ NARROW_OUT, NARROW_MAX_ROWS = 32, 4096
 
 
 _TC_WORKSPACE = {}
-TC_WORKSPACE_FLOATS = 32 * 1024 * 1024      # split-K partials (128 MB), allocated on first use per device
+# stream-K partial tiles: at most 2 per CTA of 128 x 256 floats -> 2 * 148 * 128 * 256 floats (39 MB).  One workspace
+# PER STREAM: GEMMs on parallel graph branches (bootstrap passes, weight gradients) may overlap at their tails, and a
+# GEMM's fix-up must never read partial tiles of another one.
+TC_WORKSPACE_FLOATS = 10 * 1024 * 1024
 TC_SPLIT_MODE = 0                           # 0: hi = raw fp32 word (hardware reads its top 19 bits); 1: cvt.rna hi
 
 
-def _tc_workspace(device):
-    ws = _TC_WORKSPACE.get(device)
+def _tc_workspace(device, stream):
+    key = (device, stream)
+    ws = _TC_WORKSPACE.get(key)
     if ws is None:
-        ws = _TC_WORKSPACE[device] = torch.empty(TC_WORKSPACE_FLOATS, dtype=torch.float32, device=device)
+        ws = _TC_WORKSPACE[key] = torch.empty(TC_WORKSPACE_FLOATS, dtype=torch.float32, device=device)
     return ws
 
 
@@ -253,7 +257,8 @@ def tc_gemm(out, a, a_major, lda, a_bs, b, b_major, ldb, b_bs, batch, M, N, K, b
     """out[b] (M x N) = act(A[b] . B[b]^T + bias[b]) on the tensor cores (pb_tc_gemm, 3xTF32).  See
     include/prism_b200.h for the operand conventions (major 1 = the transposed view)."""
     _lib.require_cuda(out, "out")
-    ws = _tc_workspace(out.device)
+    stream = _stream(out)
+    ws = _tc_workspace(out.device, stream)
     _lib.check(_lib.load().pb_tc_gemm(int(batch), int(kbatches), int(M), int(N), int(K),
                                       a.data_ptr(), int(a_major), int(lda), int(a_bs),
                                       b.data_ptr(), int(b_major), int(ldb), int(b_bs),
@@ -261,7 +266,7 @@ def tc_gemm(out, a, a_major, lda, a_bs, b, b_major, ldb, b_bs, batch, M, N, K, b
                                       _lib.ptr(mul), 0 if mul is None else int(mul.shape[0]),
                                       0 if mul is None else int(mul.stride(0)),
                                       out.data_ptr(), int(N if ldc is None else ldc), int(M * N if c_bs is None else c_bs),
-                                      ws.data_ptr(), ws.numel(), int(TC_SPLIT_MODE), _stream(out)), "pb_tc_gemm")
+                                      ws.data_ptr(), ws.numel(), int(TC_SPLIT_MODE), stream), "pb_tc_gemm")
     return out
 
 
