@@ -456,11 +456,14 @@ int pb_relu_bwd_bias(int heads, long long rows, int N, const float *dy, const fl
 
 /* Theil index of the K heads' parameter L2 norms (q_ensemble.py:86-92) over stacked parameter tensors (K, ...), and
  * its gradient.  table (device): per tensor {address, elements per head, offset of its gradient in `out`} as int64
- * triples.  forward: *theil_out = mean_k r_k log r_k, coef[k] = d T / d theta_k divided by theta_k; partial = scratch
- * of n_tensors * K * 8 floats; K <= 64.  backward: out = *upstream * coef[k] * theta. */
-int pb_theil_fwd(int n_tensors, int K, const long long *table, float *partial, float *theil_out, float *coef, void *stream);
-int pb_theil_bwd(int n_tensors, int K, const long long *table, const float *coef, const float *upstream, float *out,
+ * triples.  forward: *theil_out = mean_k r_k log r_k, coef[k] = d T / d theta_k divided by theta_k; chunks = blocks per
+ * (tensor, head) from pb_theil_chunks(largest per-head size); partial = scratch of n_tensors * K * chunks floats;
+ * K <= 64.  backward: out = *upstream * coef[k] * theta. */
+int pb_theil_chunks(long long max_per_head);
+int pb_theil_fwd(int n_tensors, int K, int chunks, const long long *table, float *partial, float *theil_out, float *coef,
                  void *stream);
+int pb_theil_bwd(int n_tensors, int K, int chunks, const long long *table, const float *coef, const float *upstream,
+                 float *out, void *stream);
 
 /* total_loss = mean_b(dist*w) + mean_b(q'*w);  td_b = 0.5*dist + 0.5*q' | dist | |q'|
  * (composite_model.py:135-142, agent.py:58-64) with q' = q_scale * (q - *q_offset)

@@ -127,8 +127,9 @@ SIGNATURES = {
     "pb_layer_norm_bwd": [_LL, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "pb_relu_bwd_bias_strips": [_LL],
     "pb_relu_bwd_bias": [_I, _LL, _I, _P, _P, _P, _P, _P, _P],
-    "pb_theil_fwd": [_I, _I, _P, _P, _P, _P, _P],
-    "pb_theil_bwd": [_I, _I, _P, _P, _P, _P, _P],
+    "pb_theil_chunks": [_LL],
+    "pb_theil_fwd": [_I, _I, _I, _P, _P, _P, _P, _P],
+    "pb_theil_bwd": [_I, _I, _I, _P, _P, _P, _P, _P],
     "pb_iqn_phi_bwd": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "pb_tc_gemm_supported": [_I, _I, _I, _LL, _LL, _LL],
     "pb_tc_gemm": [_I, _I, _I, _I, _I, _P, _I, _LL, _LL, _P, _I, _LL, _LL, _P, _LL, _I, _P, _I, _LL, _P, _LL, _LL, _P, _LL, _I, _P],

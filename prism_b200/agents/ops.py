@@ -491,23 +491,24 @@ class _TheilIndex(torch.autograd.Function):
         K = stacked[0].shape[0]
         dev = stacked[0].device
         lib = _lib.load()
-        partial = torch.empty(len(stacked) * K * 8, dtype=torch.float32, device=dev)
+        chunks = lib.pb_theil_chunks(max(p[0].numel() for p in stacked))
+        partial = torch.empty(len(stacked) * K * chunks, dtype=torch.float32, device=dev)
         theil = torch.empty((), dtype=torch.float32, device=dev)
         coef = torch.empty(K, dtype=torch.float32, device=dev)
-        _lib.check(lib.pb_theil_fwd(len(stacked), K, table.data_ptr(), partial.data_ptr(), theil.data_ptr(), coef.data_ptr(),
-                                    _stream(stacked[0])), "pb_theil_fwd")
+        _lib.check(lib.pb_theil_fwd(len(stacked), K, chunks, table.data_ptr(), partial.data_ptr(), theil.data_ptr(),
+                                    coef.data_ptr(), _stream(stacked[0])), "pb_theil_fwd")
         ctx.save_for_backward(table, coef)
-        ctx.meta = (len(stacked), K, int(total_numel), [tuple(p.shape) for p in stacked])
+        ctx.meta = (len(stacked), K, int(total_numel), [tuple(p.shape) for p in stacked], chunks)
         return theil
 
     @staticmethod
     def backward(ctx, g):
         table, coef = ctx.saved_tensors
-        n, K, total, shapes = ctx.meta
+        n, K, total, shapes, chunks = ctx.meta
         g = _c(g)
         out = torch.empty(total, dtype=torch.float32, device=g.device)
-        _lib.check(_lib.load().pb_theil_bwd(n, K, table.data_ptr(), coef.data_ptr(), g.data_ptr(), out.data_ptr(), _stream(g)),
-                   "pb_theil_bwd")
+        _lib.check(_lib.load().pb_theil_bwd(n, K, chunks, table.data_ptr(), coef.data_ptr(), g.data_ptr(), out.data_ptr(),
+                                            _stream(g)), "pb_theil_bwd")
         grads, off = [], 0
         for shp in shapes:
             cnt = 1

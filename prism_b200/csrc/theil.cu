@@ -14,19 +14,27 @@ namespace {
 
 using namespace pb;
 
-constexpr int TH_CHUNKS = 8;
+constexpr int TH_MAX_CHUNKS = 128;   // blocks per (tensor, head): chosen by the caller from the largest per-head size
 
 // table[t] = {pointer to the stacked tensor (K, per_head), per_head element count, offset of its gradient in `out`}
 __global__ void __launch_bounds__(256) theil_sumsq_kernel(const long long *__restrict__ table, float *__restrict__ partial)
 {
     __shared__ float red[8];
-    const int t = blockIdx.z, k = blockIdx.y, c = blockIdx.x, K = gridDim.y;
+    const int t = blockIdx.z, k = blockIdx.y, c = blockIdx.x, K = gridDim.y, CH = gridDim.x;
     const long long per = table[3 * t + 1];
     const float *p = reinterpret_cast<const float *>(table[3 * t + 0]) + (long long)k * per;
     float acc = 0.f;
-    for (long long i = (long long)c * blockDim.x + threadIdx.x; i < per; i += (long long)TH_CHUNKS * blockDim.x) {
-        const float v = p[i];
-        acc = fmaf(v, v, acc);
+    if ((per & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const float4 *p4 = reinterpret_cast<const float4 *>(p);
+        for (long long i = (long long)c * blockDim.x + threadIdx.x; i < (per >> 2); i += (long long)CH * blockDim.x) {
+            const float4 v = p4[i];
+            acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        }
+    } else {
+        for (long long i = (long long)c * blockDim.x + threadIdx.x; i < per; i += (long long)CH * blockDim.x) {
+            const float v = p[i];
+            acc = fmaf(v, v, acc);
+        }
     }
     acc = warp_sum(acc);
     if (lane_id() == 0) red[threadIdx.x >> 5] = acc;
@@ -34,11 +42,11 @@ __global__ void __launch_bounds__(256) theil_sumsq_kernel(const long long *__res
     if (threadIdx.x == 0) {
         float s = 0.f;
         for (int w = 0; w < 8; ++w) s += red[w];
-        partial[((size_t)t * K + k) * TH_CHUNKS + c] = s;
+        partial[((size_t)t * K + k) * CH + c] = s;
     }
 }
 
-__global__ void __launch_bounds__(64) theil_finalize_kernel(int n_tensors, int K, const float *__restrict__ partial,
+__global__ void __launch_bounds__(64) theil_finalize_kernel(int n_tensors, int K, int CH, const float *__restrict__ partial,
                                                             float *__restrict__ theil_out, float *__restrict__ coef)
 {
     __shared__ float l[64];
@@ -46,7 +54,7 @@ __global__ void __launch_bounds__(64) theil_finalize_kernel(int n_tensors, int K
     float sq = 0.f;
     if (k < K)
         for (int t = 0; t < n_tensors; ++t)
-            for (int c = 0; c < TH_CHUNKS; ++c) sq += partial[((size_t)t * K + k) * TH_CHUNKS + c];
+            for (int c = 0; c < CH; ++c) sq += partial[((size_t)t * K + k) * CH + c];
     l[k] = k < K ? sqrtf(sq) : 0.f;
     __syncthreads();
     float m = 0.f;
@@ -62,34 +70,55 @@ __global__ void __launch_bounds__(64) theil_finalize_kernel(int n_tensors, int K
 __global__ void __launch_bounds__(256) theil_bwd_kernel(const long long *__restrict__ table, const float *__restrict__ coef,
                                                         const float *__restrict__ upstream, float *__restrict__ out)
 {
-    const int t = blockIdx.z, k = blockIdx.y, c = blockIdx.x;
+    const int t = blockIdx.z, k = blockIdx.y, c = blockIdx.x, CH = gridDim.x;
     const long long per = table[3 * t + 1];
     const float *p = reinterpret_cast<const float *>(table[3 * t + 0]) + (long long)k * per;
     float *o = out + table[3 * t + 2] + (long long)k * per;
     const float s = coef[k] * (*upstream);
-    for (long long i = (long long)c * blockDim.x + threadIdx.x; i < per; i += (long long)TH_CHUNKS * blockDim.x) o[i] = s * p[i];
+    if ((per & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(o)) & 15) == 0) {
+        const float4 *p4 = reinterpret_cast<const float4 *>(p);
+        float4 *o4 = reinterpret_cast<float4 *>(o);
+        for (long long i = (long long)c * blockDim.x + threadIdx.x; i < (per >> 2); i += (long long)CH * blockDim.x) {
+            const float4 v = p4[i];
+            o4[i] = make_float4(s * v.x, s * v.y, s * v.z, s * v.w);
+        }
+    } else {
+        for (long long i = (long long)c * blockDim.x + threadIdx.x; i < per; i += (long long)CH * blockDim.x) o[i] = s * p[i];
+    }
 }
 
 }  // namespace
 
 extern "C" {
 
-// partial: n_tensors * K * 8 floats of scratch; coef: K floats (kept for the backward call); K <= 64
-int pb_theil_fwd(int n_tensors, int K, const long long *table, float *partial, float *theil_out, float *coef, void *stream)
+// blocks per (tensor, head) for tensors of up to max_per_head elements per head
+int pb_theil_chunks(long long max_per_head)
 {
-    if (n_tensors <= 0 || K <= 0 || K > 64 || !table || !partial || !theil_out || !coef) return PB_E_ARG;
-    dim3 grid(TH_CHUNKS, (unsigned)K, (unsigned)n_tensors);
+    long long c = (max_per_head + 16383) / 16384;
+    if (c < 8) c = 8;
+    if (c > TH_MAX_CHUNKS) c = TH_MAX_CHUNKS;
+    return (int)c;
+}
+
+// partial: n_tensors * K * chunks floats of scratch; coef: K floats (kept for the backward call); K <= 64
+int pb_theil_fwd(int n_tensors, int K, int chunks, const long long *table, float *partial, float *theil_out, float *coef,
+                 void *stream)
+{
+    if (n_tensors <= 0 || K <= 0 || K > 64 || chunks <= 0 || chunks > TH_MAX_CHUNKS || !table || !partial || !theil_out || !coef)
+        return PB_E_ARG;
+    dim3 grid((unsigned)chunks, (unsigned)K, (unsigned)n_tensors);
     PB_LAUNCH(theil_sumsq_kernel, grid, 256, 0, stream, table, partial);
-    PB_LAUNCH(theil_finalize_kernel, 1, 64, 0, stream, n_tensors, K, partial, theil_out, coef);
+    PB_LAUNCH(theil_finalize_kernel, 1, 64, 0, stream, n_tensors, K, chunks, partial, theil_out, coef);
     return PB_OK;
 }
 
 // out[table[t].offset + k * per + i] = *upstream * coef[k] * theta_t[k][i]
-int pb_theil_bwd(int n_tensors, int K, const long long *table, const float *coef, const float *upstream, float *out,
-                 void *stream)
+int pb_theil_bwd(int n_tensors, int K, int chunks, const long long *table, const float *coef, const float *upstream,
+                 float *out, void *stream)
 {
-    if (n_tensors <= 0 || K <= 0 || K > 64 || !table || !coef || !upstream || !out) return PB_E_ARG;
-    dim3 grid(TH_CHUNKS, (unsigned)K, (unsigned)n_tensors);
+    if (n_tensors <= 0 || K <= 0 || K > 64 || chunks <= 0 || chunks > TH_MAX_CHUNKS || !table || !coef || !upstream || !out)
+        return PB_E_ARG;
+    dim3 grid((unsigned)chunks, (unsigned)K, (unsigned)n_tensors);
     PB_LAUNCH(theil_bwd_kernel, grid, 256, 0, stream, table, coef, upstream, out);
     return PB_OK;
 }
