@@ -93,6 +93,30 @@ def test_argument_errors_do_not_touch_the_gpu():
     t.capacity, t.size = 100, 100           # not a power of two
     assert lib.pb_tree_init(C.byref(t), None) == -2
     assert lib.pb_ids_select(4, 40, 10, 8, 1, 1, 0.1, 1e-10, 0.25, 1, None, None) == -3   # A > 32
+    # the round's newer entry points validate before they launch, too (PB_E_ARG = -1, PB_E_UNSUPPORTED = -3)
+    assert lib.pb_tc_gemm(1, 1, 128, 64, 32, None, 0, 32, 0, None, 0, 32, 0, None, 0, 0, None, 0, 0, None, 64, 0,
+                          None, 0, 0, None) == -1                                       # null operands
+    assert lib.pb_tc_gemm(1, 1, 128, 64, 30, 16, 0, 30, 0, 16, 0, 30, 0, None, 0, 0, None, 0, 0, 16, 64, 0,
+                          None, 0, 0, None) == -3                                       # row stride not 16-byte aligned
+    assert lib.pb_tc_gemm(2, 3, 128, 64, 32, 16, 0, 32, 0, 16, 0, 32, 0, None, 0, 0, None, 0, 0, 16, 64, 0,
+                          None, 0, 0, None) == -1                                       # kbatches > 1 needs batch == 1
+    assert lib.pb_tc_gemm_supported(128, 64, 32, 32, 32, 64) == 1 and lib.pb_tc_gemm_supported(128, 64, 32, 30, 32, 64) == 0
+    assert lib.pb_layer_norm_supported(10, 3136) == 1 and lib.pb_layer_norm_supported(10, 3138) == 0
+    assert lib.pb_layer_norm_supported(10, 8192) == 0
+    assert lib.pb_layer_norm_fwd(8, 6, 1e-5, 16, None, None, 16, None, None, None) == -1  # F % 4 != 0
+    assert lib.pb_relu_bwd_bias(1, 8, 6, 16, None, None, None, 16, None) == -1            # N % 4 != 0
+    assert lib.pb_iqn_phi_bwd(4, 8, 6, 16, 16, 16, 16, None, 16, None) == -1              # F % 4 != 0
+    assert lib.pb_theil_fwd(2, 65, 8, 16, 16, 16, 16, None) == -1                         # K > 64
+    assert lib.pb_theil_chunks(100) == 8 and lib.pb_theil_chunks(1 << 30) == 128
+    assert lib.pb_peer_barrier(None, None) == -1
+    g = _lib.pb_peer_group()
+    g.world, g.rank = 9, 0                                                                # more than PB_PEER_MAX ranks
+    assert lib.pb_peer_barrier(C.byref(g), None) == -1
+    g.world, g.rank = 2, 0                                                                # flags / epoch missing
+    assert lib.pb_peer_reduce_scatter(C.byref(g), 1024, 16, None, None) == -1
+    assert lib.pb_store_scatter_dbuf(None, 4, 16, 16, 16, 16, 16, 16, 16, None) != 0
+    assert lib.pb_select_copy_f64(None, 16, 16, 16, 0, 4, None) == -1
+    assert lib.pb_copy_h2d_async(None, 16, 4, None) == -1
 
 
 def test_product_never_imports_the_oracle():
