@@ -608,3 +608,45 @@ def test_fused_theil_index_matches_autograd():
     assert abs(float(T) - float(Tr)) < 1e-6 * max(1.0, abs(float(Tr)))
     for d, r in zip(dev_p, ref_p):
         assert rel_err(d.grad.cpu().numpy(), r.grad.numpy()) < 1e-4
+
+
+def test_prefetch_toggle_and_loss_readback_keep_training_identical():
+    """set_prefetch(True) in the middle of a run and the in-graph loss read-back change scheduling only: losses,
+    parameters and trees stay bit-identical to the plain in-order loop, and loss_host mirrors the returned loss."""
+    import prism_b200
+    from prism_b200.learner_step import LearnerStep
+    from oracle.gen_golden import make_script
+    cap, B, obs_shape, A = 256, 16, (10, 10, 6), 4
+    S = make_script(13, n_streams=4, n_steps=240, obs_shape=obs_shape, p_done=0.05, p_trunc=0.03, n_actions=A)
+    succ = np.where(S["trunc"][:, None], S["final_obs"], S["next_obs"])
+
+    def run(toggle):
+        cfg = prism_b200.minatar_dqn_per_config(device=DEV, experience_replay_capacity=cap, batch_size=B,
+                                                per_sampling="stratified", replay_max_streams=4, replay_staging_rows=64,
+                                                use_cuda_graph=False)
+        torch.manual_seed(0)
+        agent = prism_b200.build_agent(cfg, obs_shape, A)
+        buf = prism_b200.build_exp_buffer(cfg)
+        buf.extend_batch(S["stream"], S["obs"].reshape((-1,) + obs_shape), S["action"], S["reward"], S["done"], S["trunc"],
+                         succ.reshape((-1,) + obs_shape))
+        buf._flush()
+        buf.buffer._sampler.seed(77)
+        step = LearnerStep(buf, agent, batch_size=B, use_cuda_graph=True)
+        losses, mirrored = [], []
+        for i in range(7):
+            if toggle and i == 3:
+                step.set_prefetch(True)
+                host = step.enable_loss_readback()
+            total = step.step()
+            losses.append(float(total))
+            if toggle and i >= 3:
+                torch.cuda.synchronize()
+                mirrored.append(float(host))
+        torch.cuda.synchronize()
+        tree = buf.buffer._sampler
+        return losses, mirrored, agent.optimizer.arena.clone(), tree.sum.clone()
+
+    a, b = run(True), run(False)
+    assert a[0] == b[0]
+    assert a[1] == a[0][3:]
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
