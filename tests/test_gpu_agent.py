@@ -161,11 +161,19 @@ def test_ensemble_loss_kernel_vs_oracle_math(B, A, K):
 
 
 def test_cos_basis_kernel():
+    """cos(fl32(fl32(tau * i) * pi)) (iqn_model.py:89-92).  The argument is built exactly like torch builds it (checked
+    bit for bit); the cosine is judged against float64 math on that fp32 argument, so the host's libm plays no role.
+    Seeded: the draw used to come from the global generator, i.e. from whatever ran before."""
     from prism_b200.agents import ops
-    tau = torch.rand(4096, 1)
-    want = torch.cos(torch.tile(tau, [1, 64]) * torch.arange(1, 65) * np.pi)
-    got = ops.cos_basis(tau.to(DEV), 64).cpu()
-    assert float((got - want).abs().max()) < 2e-6
+    g = torch.Generator().manual_seed(0)
+    tau = torch.rand(4096, 1, generator=g)
+    arg = torch.tile(tau, [1, 64]) * torch.arange(1, 65) * np.pi               # fp32, as the reference computes it
+    arg_np = (tau.numpy() * np.arange(1, 65, dtype=np.float32)).astype(np.float32) * np.float32(np.pi)
+    assert np.array_equal(arg.numpy(), arg_np)
+    want = np.cos(arg_np.astype(np.float64))
+    got = ops.cos_basis(tau.to(DEV), 64).cpu().numpy().astype(np.float64)
+    assert float(np.abs(got - want).max()) < 2e-6
+    assert float(np.abs(torch.cos(arg).numpy() - want).max()) < 2e-6             # and so does torch on this host
 
 
 def test_flat_adam_matches_torch_adam_over_steps():
