@@ -21,8 +21,16 @@ extern std::atomic<long long> g_pb_launches;
 static inline int pb_ilog2(long long v) { int l = 0; while ((1LL << l) < v) ++l; return l; }
 static inline bool pb_is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
 
-// SM count of the current device (148 on B200); cached.
+// SM count of the current device (148 on B200); cached per device.
 int pb_sm_count();
+
+// One-time per-device setup (cudaFuncSetAttribute is a per-device property): a bitmask over device ordinals.
+struct PbPerDeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    static int device() { int d = 0; return cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64 ? d : 0; }
+    bool done() const { return (mask.load(std::memory_order_acquire) >> device()) & 1ull; }
+    void mark() { mask.fetch_or(1ull << device(), std::memory_order_release); }
+};
 
 namespace pb {
 

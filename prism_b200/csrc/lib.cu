@@ -5,14 +5,14 @@ std::atomic<long long> g_pb_launches{0};
 
 int pb_sm_count()
 {
-    static int cached = 0;
-    if (cached > 0) return cached;
+    static std::atomic<int> cached[64];
     int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) {
-        int v = 0;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
-    }
-    cached = n;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return n;
+    const int c = cached[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    cached[dev].store(n, std::memory_order_relaxed);
     return n;
 }
 

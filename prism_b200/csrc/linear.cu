@@ -253,11 +253,11 @@ int launch_gemm(GemmArgs g, int batch, void *stream)
     const int total_chunks = g.n_seg * ((g.K + TK - 1) / TK);
     g.splits = pick_splits((long long)g.m_tiles * n_tiles * batch, total_chunks);
     if (g.splits > 8) {
-        static bool allowed = false;                // one flag per template instantiation
-        if (!allowed) {
+        static PbPerDeviceOnce allowed;             // one flag per template instantiation
+        if (!allowed.done()) {
             cudaError_t ea = cudaFuncSetAttribute(gemm_kernel<AK, BK, ROWSUM>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             if (ea != cudaSuccess) return (int)ea;
-            allowed = true;
+            allowed.mark();
         }
     }
     cudaLaunchConfig_t cfg = {};

@@ -794,13 +794,13 @@ int sparse_phases(int L) { return L <= TOP_MAX ? 0 : (L - TOP_MAX + 4) / 5; }
 
 int launch_top(const TreeView &v, int T, int mode, long long n_new, long long set_len, void *stream)
 {
-    static bool attr_set = false;
+    static PbPerDeviceOnce attr_set;
     size_t smem = sizeof(float) * (2ull << T);
-    if (!attr_set) {
+    if (!attr_set.done()) {
         cudaError_t e = cudaFuncSetAttribute(tree_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(sizeof(float) * (2ull << TOP_MAX)));
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_set.mark();
     }
     PB_LAUNCH(tree_top_kernel, 2, 1024, smem, stream, v, T, mode, n_new, set_len);
     return PB_OK;
@@ -844,12 +844,12 @@ int launch_update(const pb_tree *t, long long n, const long long *idx, const flo
         const int Ps = v.L <= SMALL_TOP ? 0 : (v.L - SMALL_TOP + 4) / 5;
         const int Ts = v.L - 5 * Ps;
         if (!(sorted && Ps > 0) && !v.owner) return PB_E_ARG;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PbPerDeviceOnce attr_set;
+        if (!attr_set.done()) {
             cudaError_t e = cudaFuncSetAttribute(upd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)(sizeof(float) * 2 * (2ull << SMALL_TOP)));
             if (e != cudaSuccess) return (int)e;
-            attr_set = true;
+            attr_set.mark();
         }
         const size_t smem = sizeof(float) * 2 * (2ull << Ts);
         PB_LAUNCH(upd_small_kernel, 1, 1024, smem, stream, v, n, idx, val, mode, sorted, Ps, Ts, idx_out);

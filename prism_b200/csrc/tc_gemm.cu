@@ -621,12 +621,12 @@ int make_out_map(CUtensorMap *map, float *ptr, long long rows, long long cols, l
 template <int BN, int BK, int A_MN, int B_MN>
 int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, const TcParams &g, int grid, void *stream)
 {
-    static bool attr_set = false;
+    static PbPerDeviceOnce attr_set;
     const int smem = SMEM_BUDGET / (2 * (BM + BN) * BK * 4) * (2 * (BM + BN) * BK * 4) + 32768 + 1024;
-    if (!attr_set) {
+    if (!attr_set.done()) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, BK, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_set.mark();
     }
     PB_LAUNCH((tc_gemm_kernel<BN, BK, A_MN, B_MN>), grid, NUM_THREADS, smem, stream, ta, tb, tc, g);
     return PB_OK;
