@@ -10,10 +10,14 @@ n-step/gather into the agent's static batch), update (fused loss heads, clip+Ada
 priority write-back are captured into a single graph, replayed once per iteration.
 
 Data parallel: every rank owns a shard (ring + trees) fed by its own collectors.
-Per iteration: one NCCL all-gather of the 64-byte shard state blocks, global stratified sampling
-with owner-computes placement (no transition crosses NVLink), one all-reduce of the flat gradient
-arena fused with clip + Adam.  Both exchanges run as our own kernels over NVLink peer memory
+Per iteration: one all-gather of the 64-byte shard state blocks, global stratified sampling with
+owner-computes placement (no transition crosses NVLink), one all-reduce of the flat gradient arena
+fused with clip + Adam.  Both exchanges run as our own kernels over NVLink peer memory
 (csrc/peer.cu); PB_DP_EXCHANGE=nccl (or ranks that cannot map each other) falls back to NCCL.
+
+Software pipelining (``prefetch``, ``step(ingest=...)``): the priority write-back, the fused ingest
+of new collector steps and the NEXT iteration's sample + gather run on parallel branches of the
+same graph while backward / exchange / Adam proceed.
 """
 import torch
 

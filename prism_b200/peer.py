@@ -112,8 +112,9 @@ class PeerGroup:
         """Sum ``opt.grad`` (= self.grad) over the ranks and apply clip + Adam on every replica (csrc/peer.cu).
 
         ``trailing_barrier``: the one-shot schedule lets a fast rank leave while slower ranks still pull its gradient;
-        the next writer of ``grad`` must be separated from them by a barrier.  LearnerStep passes False because every
-        step starts with the state all-gather (a full handshake) before anything touches the arena again."""
+        the next writer of ``grad`` must be separated from them by a barrier.  Without prefetch LearnerStep passes False:
+        every step starts with the state all-gather (a full handshake on the same graph branch) before anything
+        touches the arena again.  With prefetch that handshake runs on the tail branch, so it passes True."""
         lib, st = _lib.load(), self._stream()
         _lib.check(lib.pb_peer_barrier(C.byref(self.c), st), "pb_peer_barrier")            # every rank packed its gradient
         if self.n * 4 * self.world <= ONE_SHOT_MAX_BYTES:
@@ -136,7 +137,14 @@ class PeerGroup:
                                     opt.eps, opt.max_grad_norm, opt.norm_out.data_ptr(), None, st), "pb_peer_adam")
 
     def close(self):
+        """Unmap the peers' blocks and free this rank's own.  Every rank must have finished its last exchange (the
+        caller synchronises and, across processes, barriers first); ``grad`` / ``reduced`` are dead afterwards."""
         lib = _lib.load()
         for p in self._opened:
             lib.pb_peer_close(C.c_void_p(p))
         self._opened = []
+        if self._own_ptr:
+            torch.cuda.synchronize(self.device)
+            self.grad = self.reduced = self._block = None
+            lib.pb_peer_free(C.c_void_p(self._own_ptr))
+            self._own_ptr = None
