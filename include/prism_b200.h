@@ -472,6 +472,25 @@ int pb_theil_bwd(int n_tensors, int K, int chunks, const long long *table, const
 int pb_loss_combine(int B, const float *dist, const float *q, const float *w, float q_scale,
                     const float *q_offset, float *total_out, float *td_out, void *stream);
 
+/* ---- wire codec of the remote-actor transport.  HOST functions: plain host pointers, no stream, no
+ * device work.  They replace the per-element Python walks of the reference's Redis path:
+ *   msgpack array of numbers -> float64   prism/async_components/compression_methods.py:72-80 (msgpack.unpackb)
+ *   Timestep records -> offsets           prism/experience/timestep.py:103-187 (Timestep.deserialize)
+ *   tensor memory -> msgpack numbers      prism/async_components/async_experience_buffer.py:90-96 (tensor.tolist())
+ * pb_wire_unpack_numbers: buf holds exactly ONE msgpack array of ints / floats / bools; *n_out = its length; out NULL
+ *   = validate and count only; PB_E_UNSUPPORTED for any other element type (nil, str, bin, containers).
+ * pb_wire_array_header: msgpack array header of n elements (out >= 5 bytes).
+ * pb_wire_pack_numbers: n elements (dtype 0 float32, 1 float64, 2 int64, 3 bool bytes) as msgpack encodes the
+ *   corresponding Python list (floats as float64, ints in their shortest form); cap >= 9 * n.
+ * pb_wire_index_timesteps: flat = the decoded numbers of a block of serialized Timesteps (timestep.py:30-101); per
+ *   record 12 int64 columns: id | obs offset (-1 none), values, shape offset, shape values | truncated successor id
+ *   (-1313 none) and the same four columns of its observation | offset of the 12 scalar fields (reward .. next id) |
+ *   offset one past the record.  rec NULL = count only.  PB_E_ARG on a malformed block. */
+int pb_wire_unpack_numbers(const unsigned char *buf, long long len, double *out, long long cap, long long *n_out);
+int pb_wire_array_header(long long n, unsigned char *out, long long *written);
+int pb_wire_pack_numbers(const void *src, int dtype, long long n, unsigned char *out, long long cap, long long *written);
+int pb_wire_index_timesteps(const double *flat, long long n, long long max_records, long long *rec, long long *n_rec);
+
 #ifdef __cplusplus
 }
 #endif

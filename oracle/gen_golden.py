@@ -9,6 +9,10 @@ What is frozen:
   nstep_gather_*.npz reference TimestepBuffer._timesteps_to_batch (prism/experience/timestep_buffer.py)
                      driven through a stub `tensordict` and a fake torchrl ring, on scripted
                      multi-stream trajectories (done / truncated / in-flight tail / ring wrap)
+  wire.npz           reference Timestep.serialize / deserialize_linked_list (prism/experience/timestep.py), the
+                     MessageSerializer envelope with the "NONE" compressor (async_components/compression_methods.py;
+                     lz4, msgpack_numpy and redis are absent here and stubbed at import) and the batch flat-list
+                     format (async_components/async_experience_buffer.py) on a scripted multi-stream trace
   per_tree.npz       ORACLE-generated (parity unpinned: torchrl is absent) -- freezes the restated
                      tree/sampler arithmetic so the C oracle and the CUDA path cannot drift apart
 """
@@ -302,6 +306,97 @@ def gen_nstep_gather(name, frame_stack, capacity, n_steps, checkpoints, seed):
 
 
 # --------------------------------------------------------------------------------------------
+# wire formats of the Redis transport, through the reference's own serializers
+# --------------------------------------------------------------------------------------------
+def _stub_wire_deps():
+    """Modules the reference's async components import at module level but that are absent here.  Only code paths
+    that never touch them are exercised (the "NONE" compressor; unbound tensor (de)serializers)."""
+    class _Anything(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return type(name, (), {})
+
+    for name in ("lz4", "lz4.frame", "redis", "torchrl", "torchrl.data", "torchrl.envs"):
+        mod = _Anything(name)
+        mod.__path__ = []
+        sys.modules.setdefault(name, mod)
+    mn = types.ModuleType("msgpack_numpy")
+    mn.patch = lambda: None
+    sys.modules.setdefault("msgpack_numpy", mn)
+
+
+def gen_wire():
+    import contextlib
+    import io
+    _stub_wire_deps()
+    from prism.async_components.compression_methods import MessageSerializer
+    from prism.async_components.async_experience_buffer import AsyncExperienceBuffer, AsyncExperienceBufferInterface
+    from prism.experience.timestep import Timestep
+    from oracle.buffer_oracle import StreamLinker
+    obs_shape = (3, 2)
+    n_steps, block = 90, 7
+    script = make_script(21, n_streams=3, n_steps=n_steps, obs_shape=obs_shape, p_done=0.08, p_trunc=0.06)
+    ser = MessageSerializer(compression_type="NONE")
+    ids = [0]
+
+    def make_step():
+        ids[0] += 1
+        return Timestep(ids[0])
+
+    out = {"obs_shape": np.array(obs_shape), "block": np.array(block)}
+    for k, v in script.items():
+        out["script." + k] = v
+    linkers, keep, pending, step_ids = {}, [], [], []
+    waiting, n_blocks = {}, 0
+    for t in range(n_steps):
+        s = int(script["stream"][t])
+        if s not in linkers:
+            linkers[s] = StreamLinker(torch.from_numpy(script["obs"][t].reshape(obs_shape).copy()), make_step)
+        step = linkers[s].step(int(script["action"][t]), float(script["reward"][t]), bool(script["done"][t]),
+                               bool(script["trunc"][t]),
+                               torch.from_numpy(script["next_obs"][t].reshape(obs_shape).copy()),
+                               torch.from_numpy(script["final_obs"][t].reshape(obs_shape).copy()))
+        keep.append(step)                      # the collector side keeps its steps alive (weak links)
+        step_ids.append(step.id)
+        pending.append(step)
+        if len(pending) == block or t == n_steps - 1:
+            serialized = []
+            for ts in pending:
+                serialized += ts.serialize()                               # redis_interface.py:113-116
+            packed = ser.pack(serialized)
+            tag = "block%d." % n_blocks
+            out[tag + "packed"] = np.frombuffer(packed, dtype=np.uint8).copy()
+            with contextlib.redirect_stdout(io.StringIO()):                # the reference prints per element
+                complete, waiting = Timestep.deserialize_linked_list(ser.unpack(packed), waiting)
+            out[tag + "released"] = np.array([ts.id for ts in complete], dtype=np.int64)
+            out[tag + "waiting"] = np.array(sorted(waiting.keys()), dtype=np.int64)
+            pending, n_blocks = [], n_blocks + 1
+    out["n_blocks"] = np.array(n_blocks)
+    out["step_ids"] = np.array(step_ids, dtype=np.int64)
+    # a training batch through the reference's tensor (de)serializers (async_experience_buffer.py:76-96, 148-184)
+    rng = np.random.default_rng(22)
+    B = 5
+    tensors = [torch.from_numpy(rng.standard_normal((B, 2, 3, 2)).astype(np.float32)),
+               torch.from_numpy(rng.standard_normal((B, 2, 3, 2)).astype(np.float32)),
+               torch.from_numpy(rng.standard_normal((B, 1)).astype(np.float32)),
+               torch.from_numpy(rng.random((B, 1)) < 0.7),
+               torch.from_numpy(np.full((B, 1), 0.99 ** 3, np.float32)),
+               torch.from_numpy(rng.integers(0, 5, (B, 1)).astype(np.int64))]
+    serialized = []
+    for x in tensors:
+        serialized += AsyncExperienceBuffer._serialize_tensor(None, x)
+    out["batch.packed"] = np.frombuffer(ser.pack(serialized), dtype=np.uint8).copy()
+    idx, flat = 0, ser.unpack(ser.pack(serialized))
+    for k, x in enumerate(tensors):
+        out["batch.in%d" % k] = x.numpy()
+        back, idx = AsyncExperienceBufferInterface._deserialize_tensor(None, flat, idx)
+        out["batch.out%d" % k] = back.numpy()
+    np.savez_compressed(os.path.join(GOLD, "wire.npz"), **out)
+    print("wrote wire")
+
+
+# --------------------------------------------------------------------------------------------
 # PER tree fixture (oracle-generated, parity unpinned)
 # --------------------------------------------------------------------------------------------
 def gen_per_tree():
@@ -337,6 +432,7 @@ def main():
     gen_nstep_gather("nstep_gather_fs1", 1, 64, 200, [10, 64, 130, 200], seed=11)
     gen_nstep_gather("nstep_gather_fs4", 4, 48, 160, [7, 48, 100, 160], seed=12)
     gen_per_tree()
+    gen_wire()
 
 
 if __name__ == "__main__":

@@ -137,6 +137,10 @@ SIGNATURES = {
     "pb_linear_fwd_tc": [_I, _I, _I, _I, _P, _LL, _P, _P, _I, _P, _P],
     "pb_linear_bwd_input": [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P],
     "pb_linear_bwd_weight": [_I, _I, _I, _I, _P, _P, _P, _LL, _P, _P, _P],
+    "pb_wire_unpack_numbers": [_P, _LL, _P, _LL, _P],
+    "pb_wire_array_header": [_LL, _P, _P],
+    "pb_wire_pack_numbers": [_P, _I, _LL, _P, _LL, _P],
+    "pb_wire_index_timesteps": [_P, _LL, _LL, _P, _P],
 }
 _RESTYPES = {"pb_error_string": C.c_char_p, "pb_launch_count": C.c_longlong, "pb_peer_slice": C.c_longlong}
 

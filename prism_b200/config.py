@@ -88,12 +88,37 @@ class Config:
     use_cuda_graph: bool = True
     frame_stack_size: int = 4
     run_through_redis: bool = False
+    redis_host: str = "localhost"
+    redis_port: int = 6379
+    redis_side: str = "server"
     # ---- device-buffer knobs (new; defaults reproduce reference behaviour) ----
     per_sampling: str = "iid"               # "iid" (torchrl) | "stratified" (north star)
     replay_storage_dtype: str = "float32"   # "float32" | "uint8"
     replay_obs_scale_255: bool = False      # uint8 storage: emit v/255 (gymnasium scale_obs)
     replay_max_streams: int = 256
     replay_staging_rows: int = 256
+    redis_local_buffer: bool = False        # learner drains the step blocks into its own device buffer (no batch hop)
+
+    # ---- wire form (prism/config/algorithm_configuration.py:117-123): JSON of the fields ----
+    def serialize(self):
+        import json
+        return json.dumps(self.__dict__)
+
+    @classmethod
+    def deserialize(cls, serialized_config):
+        """Accepts a config serialized by either implementation: fields this dataclass does not declare (the
+        reference has 91) are kept as plain attributes, since the factories read by attribute."""
+        import json
+        from dataclasses import fields
+        if isinstance(serialized_config, (bytes, bytearray)):
+            serialized_config = serialized_config.decode("utf-8")
+        cfg_json = dict(json.loads(serialized_config))
+        known = {f.name for f in fields(cls)}
+        cfg = cls(**{k: v for k, v in cfg_json.items() if k in known})
+        for k, v in cfg_json.items():
+            if k not in known:
+                setattr(cfg, k, v)
+        return cfg
 
 
 def minatar_ids_iqn_config(**kw):

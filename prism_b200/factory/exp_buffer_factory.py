@@ -7,7 +7,19 @@ from ..experience import DevicePrioritizedReplayBuffer, TimestepBuffer
 
 def build_exp_buffer(config):
     if getattr(config, "run_through_redis", False):
-        raise NotImplementedError("the Redis transport bypasses PER and is outside the hot-path scope")
+        # exp_buffer_factory.py:11-18: "server" = the learner / collector end, "client" = the buffer process
+        if config.redis_side == "server":
+            from ..async_components.async_experience_buffer import AsyncExperienceBufferInterface
+            local = None
+            if getattr(config, "redis_local_buffer", False):
+                import copy
+                local_config = copy.copy(config)
+                local_config.run_through_redis = False
+                local = build_exp_buffer(local_config)
+            return AsyncExperienceBufferInterface(config.redis_host, config.redis_port, config.device, local_buffer=local)
+        elif config.redis_side == "client":
+            from ..async_components.async_experience_buffer import AsyncExperienceBuffer
+            return AsyncExperienceBuffer(config.redis_host, config.redis_port)
     storage_dtype = torch.uint8 if getattr(config, "replay_storage_dtype", "float32") == "uint8" else torch.float32
     td_buffer = DevicePrioritizedReplayBuffer(
         capacity=config.experience_replay_capacity,

@@ -82,3 +82,52 @@ def replay_script_oracle(fx, upto=None, buf=None, linkers=None, start=0):
 def script_successor_obs(S, t):
     """Observation that follows step t of the trace: truncated -> final observation, else next/reset obs."""
     return S["final_obs"][t] if S["trunc"][t] else S["next_obs"][t]
+
+
+class FakeRedis(object):
+    """The redis-py calls RedisInterface uses, in memory."""
+
+    def __init__(self):
+        self.kv, self.lists = {}, {}
+
+    def get(self, k):
+        return self.kv.get(k)
+
+    def set(self, k, v):
+        self.kv[k] = v.encode() if isinstance(v, str) else (str(v).encode() if isinstance(v, (int, float)) else v)
+
+    def lpush(self, k, v):
+        self.lists.setdefault(k, []).insert(0, v)
+
+    def lrange(self, k, a, b):
+        lst = self.lists.get(k, [])
+        return lst[a:] if b == -1 else lst[a:b + 1]
+
+    def ltrim(self, k, a, b):
+        lst = self.lists.get(k, [])
+        self.lists[k] = lst[a:] if b == -1 else lst[a:b + 1]
+
+    def delete(self, k):
+        self.lists.pop(k, None)
+        self.kv.pop(k, None)
+
+    def incrby(self, k, n):
+        self.kv[k] = str(int(self.kv.get(k, b"0")) + n).encode()
+
+    def flushall(self):
+        self.kv, self.lists = {}, {}
+
+    def pipeline(self):
+        outer = self
+
+        class Pipe(object):
+            def __init__(self):
+                self.calls = []
+
+            def __getattr__(self, name):
+                return lambda *a: self.calls.append((name, a))
+
+            def execute(self):
+                return [getattr(outer, name)(*a) for name, a in self.calls]
+
+        return Pipe()

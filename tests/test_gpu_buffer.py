@@ -222,3 +222,35 @@ def test_graph_captured_ingest_matches_reference_golden(name, n):
                 _check_against_fixture(fx, cp, _gather_all(tb, fx["cp%d.index" % cp]))
     st = tb.buffer._sampler.state_host()
     assert st["seq"] == total - total % n and st["len"] == min(st["seq"], int(fx["capacity"]))
+
+
+def test_wire_blocks_fill_the_device_buffer():
+    """Remote-actor path: the reference's step blocks (tests/golden/wire.npz, bytes frozen from
+    Timestep.serialize) -> native decoder -> extend_batch, held by the learner-side interface in local-buffer mode,
+    give the same device buffer as handing the same steps to extend_batch with the collector's own stream ids."""
+    from helpers import FakeRedis
+    from prism_b200.async_components.async_experience_buffer import AsyncExperienceBufferInterface
+    from prism_b200.async_components.redis import RedisInterface
+    fx = load_golden("wire")
+    S = script_from_fixture(fx)
+    obs_shape = tuple(fx["obs_shape"].tolist())
+    n = len(S["stream"])
+    server = FakeRedis()
+    for k in range(int(fx["n_blocks"])):                               # what a reference collector would have pushed
+        server.lpush(RedisInterface.TIMESTEPS_KEY, fx["block%d.packed" % k].tobytes())
+    wired = _product_buffer(128, 2)
+    learner = AsyncExperienceBufferInterface("h", 0, DEV, redis_interface=RedisInterface(client=server), local_buffer=wired)
+    n_in = learner.drain()
+    assert n_in == n - learner._decoder.n_waiting and len(wired) == n_in and learner.drain() == 0
+    # the order the steps were released in, recovered from the stored observations
+    got = _gather_all(wired, np.arange(n_in))
+    key = {S["obs"][t].tobytes(): t for t in range(n)}
+    t_of = np.asarray([key[o[-1].reshape(-1).tobytes()] for o in got[0]])
+    assert len(set(t_of.tolist())) == n_in
+    direct = _product_buffer(128, 2)
+    succ = np.stack([script_successor_obs(S, t) for t in range(n)])
+    direct.extend_batch(S["stream"][t_of], S["obs"][t_of].reshape((-1,) + obs_shape), S["action"][t_of],
+                        S["reward"][t_of], S["done"][t_of], S["trunc"][t_of], succ[t_of].reshape((-1,) + obs_shape))
+    want = _gather_all(direct, np.arange(n_in))
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)

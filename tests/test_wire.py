@@ -1,0 +1,316 @@
+"""Remote-actor wire formats against the reference's own serializers (tests/golden/wire.npz, frozen by
+oracle/gen_golden.py from prism/experience/timestep.py and prism/async_components/*) -- CPU only: the codec is host
+code of libprism_b200.so; the device hand-off is ``TimestepBuffer.extend_batch`` (tests/test_gpu_buffer.py)."""
+import os
+
+import msgpack
+import numpy as np
+import pytest
+import torch
+
+from helpers import FakeRedis
+from oracle.buffer_oracle import StreamLinker
+from prism_b200 import _lib
+from prism_b200.async_components import compression_methods as cm
+from prism_b200.async_components import wire
+from prism_b200.async_components.async_experience_buffer import AsyncExperienceBuffer, AsyncExperienceBufferInterface
+from prism_b200.async_components.redis import RedisInterface
+from prism_b200.config import Config
+from prism_b200.experience.timestep import Timestep
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "wire.npz"))
+NONE = cm.MessageSerializer(compression_type="NONE")
+
+
+# ---------------------------------------------------------------------------------------------- native codec
+def test_pack_numbers_is_byte_identical_to_msgpack():
+    ints = [0, 1, 127, 128, 255, 256, 65535, 65536, 2 ** 32 - 1, 2 ** 32, 2 ** 53, 2 ** 62, -1, -32, -33, -128, -129,
+            -32768, -32769, -2 ** 31, -2 ** 31 - 1, -2 ** 53, -2 ** 63, -1313]
+    assert cm.pack_numbers([np.asarray(ints, dtype=np.int64)]) == msgpack.packb(ints)
+    rng = np.random.default_rng(0)
+    f32 = rng.standard_normal(3000).astype(np.float32)
+    f64 = rng.standard_normal(17)
+    flags = rng.random(40) < 0.5
+    mixed = [3, 2, 5, 10] + f32.tolist() + flags.tolist() + f64.tolist() + [7]
+    packed = cm.pack_numbers([np.asarray([3, 2, 5, 10]), f32, flags, f64, 7])
+    assert packed == msgpack.packb(mixed)
+    assert np.array_equal(cm.unpack_numbers(packed), np.asarray([float(v) for v in mixed]))
+
+
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 65535, 65536])
+def test_array_header_boundaries(n):
+    values = [float(i) for i in range(n)]
+    packed = cm.pack_numbers([np.asarray(values, dtype=np.float64)])
+    assert packed == msgpack.packb(values)
+    assert np.array_equal(cm.unpack_numbers(packed), np.asarray(values))
+
+
+def test_unpack_numbers_reads_every_numeric_encoding():
+    values = [5, -3, 200, -200, 70000, -70000, 2 ** 40, -2 ** 40, 1.5, True, False]
+    assert cm.unpack_numbers(msgpack.packb(values)).tolist() == [float(v) for v in values]
+    single = msgpack.packb([1.25, -2.5], use_single_float=True)
+    assert cm.unpack_numbers(single).tolist() == [1.25, -2.5]
+
+
+@pytest.mark.parametrize("payload", [msgpack.packb([1, None]), msgpack.packb([1, "a"]), msgpack.packb([[1]]),
+                                     msgpack.packb({"a": 1}), msgpack.packb([1, 2]) + b"\x00", msgpack.packb([1.0, 2.0])[:-1],
+                                     b"\xdd\xff\xff\xff\xff", b""])
+def test_unpack_numbers_rejects_anything_else(payload):
+    with pytest.raises(_lib.PbError):
+        cm.unpack_numbers(payload)
+
+
+def test_index_rejects_malformed_blocks():
+    good = np.asarray(wire.serialize_timestep(Timestep(4, obs=np.zeros((2, 2), np.float32), reward=1.0, done=True,
+                                                        truncated=False, action=1)), dtype=np.float64)
+    flat, rec = wire.index_timesteps(good)
+    assert rec.shape == (1, 12) and rec[0, 0] == 4 and rec[0, 2] == 4 and rec[0, 4] == 2 and rec[0, 11] == good.size
+    for bad in (good[:-1], good[:3], np.concatenate([good, good[:5]])):
+        with pytest.raises(_lib.PbError):
+            wire.index_timesteps(bad)
+    lying = good.copy()
+    lying[1] = 1e9                                   # observation longer than the block
+    with pytest.raises(_lib.PbError):
+        wire.index_timesteps(lying)
+    assert wire.index_timesteps(np.zeros(0))[1].shape == (0, 12)
+
+
+# ---------------------------------------------------------------------------------------------- envelope
+def test_envelope_tags_and_errors():
+    ser = cm.MessageSerializer()                                          # asks for LZ4 like the reference default
+    small = ser.pack([1, 2, 3])
+    assert msgpack.unpackb(small)[0] == "NONE" and ser.unpack(small) == [1, 2, 3]
+    big = ser.pack(list(range(2000)))
+    tag = msgpack.unpackb(big)[0]
+    assert tag == ("LZ4" if cm.LZ4MessageCompressor.available() else "NONE")
+    assert ser.unpack(big) == list(range(2000))
+    assert ser.pack(None) is None and ser.unpack(None) is None
+    with pytest.raises(ValueError):
+        ser.unpack(msgpack.packb(("ZSTD", b"x")))
+    if not cm.LZ4MessageCompressor.available():
+        with pytest.raises(_lib.PbError):                                 # never a silent skip
+            ser.unpack(msgpack.packb(("LZ4", b"\x04\x22\x4d\x18")))
+
+
+# ---------------------------------------------------------------------------------------------- golden: sender side
+def _replay_script():
+    """Rebuild the collector trace of the fixture with THIS package's Timestep; yields the blocks as the sender
+    would submit them."""
+    S = {k[len("script."):]: GOLD[k] for k in GOLD.files if k.startswith("script.")}
+    shape, block = tuple(GOLD["obs_shape"]), int(GOLD["block"])
+    ids = [0]
+
+    def make_step():
+        ids[0] += 1
+        return Timestep(ids[0])
+
+    linkers, keep, pending, blocks = {}, [], [], []
+    n = len(S["stream"])
+    for t in range(n):
+        s = int(S["stream"][t])
+        if s not in linkers:
+            linkers[s] = StreamLinker(torch.from_numpy(S["obs"][t].reshape(shape).copy()), make_step)
+        step = linkers[s].step(int(S["action"][t]), float(S["reward"][t]), bool(S["done"][t]), bool(S["trunc"][t]),
+                               torch.from_numpy(S["next_obs"][t].reshape(shape).copy()),
+                               torch.from_numpy(S["final_obs"][t].reshape(shape).copy()))
+        keep.append(step)
+        pending.append(step)
+        if len(pending) == block or t == n - 1:
+            blocks.append(pending)
+            pending = []
+    return S, blocks, keep + [lk.current for lk in linkers.values()]      # in-flight steps stay alive too
+
+
+def test_serialize_matches_reference_bytes():
+    S, blocks, keep = _replay_script()
+    assert len(blocks) == int(GOLD["n_blocks"])
+    assert [ts.id for b in blocks for ts in b] == GOLD["step_ids"].tolist()
+    for k, steps in enumerate(blocks):
+        serialized = []
+        for ts in steps:
+            serialized += ts.serialize()
+        assert NONE.pack(serialized) == GOLD["block%d.packed" % k].tobytes(), "block %d" % k
+        # the array-segment sender (what RedisInterface.submit_timesteps uses) emits the same bytes
+        assert NONE.pack_numbers(wire.timestep_segments(steps)) == GOLD["block%d.packed" % k].tobytes()
+
+
+def test_linked_list_matches_reference_release_order():
+    waiting = {}
+    for k in range(int(GOLD["n_blocks"])):
+        flat = NONE.unpack_numbers(GOLD["block%d.packed" % k].tobytes())
+        complete, waiting = Timestep.deserialize_linked_list(flat, waiting)
+        assert [ts.id for ts in complete] == GOLD["block%d.released" % k].tolist()
+        assert sorted(waiting) == GOLD["block%d.waiting" % k].tolist()
+        for ts in complete:                                   # released = every link it names is resolved
+            if not ts.done and not ts.truncated:
+                assert ts.next() is not None and ts.next().obs is not None
+
+
+# ---------------------------------------------------------------------------------------------- golden: columnar decoder
+def test_decoder_emits_the_script_in_stream_order():
+    S = {k[len("script."):]: GOLD[k] for k in GOLD.files if k.startswith("script.")}
+    dec = wire.TimestepWireDecoder(max_streams=8)
+    parts = []
+    for k in range(int(GOLD["n_blocks"])):
+        rows = dec.feed(NONE.unpack_numbers(GOLD["block%d.packed" % k].tobytes()))
+        if rows is not None:
+            parts.append(rows)
+    sid, obs, action, reward, done, trunc, next_obs = (np.concatenate([p[i] for p in parts]) for i in range(7))
+    assert obs.dtype == np.float32 and sid.dtype == np.int32 and action.dtype == np.int64
+    n = len(S["stream"])
+    assert len(sid) == n - dec.n_waiting and dec.n_decoded == n
+    key = {S["obs"][t].tobytes(): t for t in range(n)}
+    assert len(key) == n
+    t_of = np.asarray([key[o.reshape(-1).tobytes()] for o in obs])
+    assert len(set(t_of.tolist())) == len(t_of)
+    assert np.array_equal(action, S["action"][t_of]) and np.array_equal(reward, S["reward"][t_of])
+    assert np.array_equal(done, S["done"][t_of]) and np.array_equal(trunc, S["trunc"][t_of])
+    want_next = np.where(S["trunc"][t_of, None], S["final_obs"][t_of], S["next_obs"][t_of])
+    want_next[S["done"][t_of]] = 0.0
+    assert np.array_equal(next_obs.reshape(len(t_of), -1), want_next)
+    # every collector stream comes out in its own order, and one episode keeps one stream id
+    live = {}
+    for j, t in enumerate(t_of):
+        s = int(S["stream"][t])
+        if s in live:
+            last_t, last_sid = live[s]
+            assert t > last_t
+            if last_sid is not None:
+                assert sid[j] == last_sid
+        live[s] = (t, None if (S["done"][t] or S["trunc"][t]) else sid[j])
+    open_sids = [v[1] for v in live.values() if v[1] is not None]
+    assert len(open_sids) == len(set(open_sids))
+    # only the newest unfinished step of a stream may still be waiting for its successor
+    missing = sorted(set(range(n)) - set(t_of.tolist()))
+    assert len(missing) == dec.n_waiting
+    for t in missing:
+        assert not S["done"][t] and not S["trunc"][t]
+        assert not np.any(S["stream"][t + 1:] == S["stream"][t])
+
+
+def test_decoder_stream_budget():
+    dec = wire.TimestepWireDecoder(max_streams=1)
+    a = Timestep(1, obs=np.zeros(3, np.float32), reward=0.0, done=False, truncated=False, action=0)
+    a.next = Timestep(2, obs=np.ones(3, np.float32))
+    b = Timestep(10, obs=np.zeros(3, np.float32), reward=0.0, done=False, truncated=False, action=0)
+    b.next = Timestep(11, obs=np.ones(3, np.float32))
+    assert dec.feed(np.asarray(a.serialize(), dtype=np.float64)) is None and dec.n_waiting == 1
+    with pytest.raises(_lib.PbError):
+        dec.feed(np.asarray(b.serialize(), dtype=np.float64))
+
+
+# ---------------------------------------------------------------------------------------------- golden: batch format
+def test_batch_format_matches_reference():
+    tensors = [GOLD["batch.in%d" % k] for k in range(6)]
+    assert NONE.pack_numbers(wire.batch_segments(tensors)) == GOLD["batch.packed"].tobytes()
+    back = wire.split_batch(NONE.unpack_numbers(GOLD["batch.packed"].tobytes()))
+    for k in range(6):
+        assert back[k].dtype == np.float32 and np.array_equal(back[k], GOLD["batch.out%d" % k])
+    with pytest.raises(_lib.PbError):
+        wire.split_batch(NONE.unpack_numbers(GOLD["batch.packed"].tobytes())[:-3])
+
+
+# ---------------------------------------------------------------------------------------------- both ends over a fake Redis
+class RecordingBuffer(object):
+    """Stands where the device TimestepBuffer stands: records extend_batch, serves a fixed static batch."""
+
+    def __init__(self, B, shape):
+        self.rows, self.B, self.shape, self.n_sampled = [], B, shape, 0
+
+    def extend_batch(self, *rows):
+        self.rows.append(rows)
+        return len(rows[0])
+
+    def sample(self, batch_size=None, return_info=False):
+        g = torch.Generator().manual_seed(self.n_sampled)
+        self.n_sampled += 1
+        self._obs = torch.randn((self.B, 1) + self.shape, generator=g)
+        self._next_obs = torch.randn((self.B, 1) + self.shape, generator=g)
+        self._reward = torch.randn(self.B, 1, generator=g)
+        self._nonterminal = torch.rand(self.B, 1, generator=g) < 0.8
+        self._gamma = torch.full((self.B, 1), 0.99 ** 3)
+        self._action = torch.randint(0, 5, (self.B, 1), generator=g)
+
+
+def test_both_ends_over_fake_redis():
+    S, blocks, keep = _replay_script()
+    shape = tuple(int(s) for s in GOLD["obs_shape"])
+    server = FakeRedis()
+    cfg = Config(batch_size=4, device="cpu")
+    sender = AsyncExperienceBufferInterface("h", 0, "cpu", redis_interface=RedisInterface(client=server), block_size=7)
+    sender._redis_interface.set_config(cfg)
+    assert RedisInterface(client=server).get_config().batch_size == 4
+    steps = [ts for b in blocks for ts in b]
+    for ts in steps:
+        sender.extend(ts)
+    sender.flush()
+    assert int(server.get(RedisInterface.TOTAL_TIMESTEPS_COLLECTED_KEY)) == len(steps)
+    # the blocks on the wire are the reference's, byte for byte (NONE-tagged when lz4 is absent)
+    if not cm.LZ4MessageCompressor.available():
+        queued = list(reversed(server.lists[RedisInterface.TIMESTEPS_KEY]))
+        assert queued == [GOLD["block%d.packed" % k].tobytes() for k in range(int(GOLD["n_blocks"]))]
+
+    recorder = RecordingBuffer(4, shape)
+    middle = AsyncExperienceBuffer("h", 0, redis_interface=RedisInterface(client=server), experience_buffer=recorder)
+    middle._idle_sleep = 0.0
+    middle._time_between_collect_calls = 0.0
+    middle._time_between_command_pings = 0.0
+    middle._redis_interface.set_current_command(RedisInterface.START_COLLECTING_COMMAND)
+    middle.run(max_iterations=3)
+    n_rows = sum(len(r[0]) for r in recorder.rows)
+    assert n_rows == len(steps) - middle._decoder.n_waiting == middle._n_collected
+    assert recorder.n_sampled == 3 and len(server.lists[RedisInterface.TRAINING_BATCH_KEY]) == 3
+    sent = [recorder._obs.clone(), recorder._next_obs.clone(), recorder._reward.clone(),
+            recorder._nonterminal.float(), recorder._gamma.clone(), recorder._action.float()]
+
+    learner = AsyncExperienceBufferInterface("h", 0, "cpu", redis_interface=RedisInterface(client=server))
+    batch, info = learner.sample(return_info=True)
+    assert info == 1 and batch["action"].dtype == torch.int64
+    got = [batch["observation"], batch["next"]["observation"], batch["next"]["reward"], batch["nonterminal"],
+           batch["gamma"], batch["action"].float()]
+    for a, b in zip(got, sent):                       # lpush + lrange from the head: the newest batch comes first
+        assert torch.equal(a.float(), b)
+    assert learner.sample() is batch and learner.sample() is batch
+    with pytest.raises(_lib.PbError):
+        learner.update_priority(None, None)
+    middle._redis_interface.set_current_command(RedisInterface.SHUTDOWN_COMMAND)
+    middle.run(max_iterations=50)                     # returns on the command, not on the iteration cap
+    assert recorder.n_sampled == 4
+
+
+def test_local_buffer_mode_drains_into_the_learners_buffer():
+    S, blocks, keep = _replay_script()
+    server = FakeRedis()
+    sender = AsyncExperienceBufferInterface("h", 0, "cpu", redis_interface=RedisInterface(client=server), block_size=7)
+    steps = [ts for b in blocks for ts in b]
+    for ts in steps:
+        sender.extend(ts)
+    sender.flush()
+
+    class Local(RecordingBuffer):
+        buffer = type("TD", (), {"_storage_opts": {"max_streams": 16}})()
+
+        def sample(self, return_info=False):
+            return ("batch", {"index": 0}) if return_info else "batch"
+
+        def update_priority(self, idx, p):
+            self.updated = (idx, p)
+
+    local = Local(4, (3, 2))
+    learner = AsyncExperienceBufferInterface("h", 0, "cpu", redis_interface=RedisInterface(client=server), local_buffer=local)
+    assert learner.sample(return_info=True) == ("batch", {"index": 0})
+    assert sum(len(r[0]) for r in local.rows) == len(steps) - learner._decoder.n_waiting
+    assert learner._decoder.max_streams == 16
+    learner.update_priority(1, 2)
+    assert local.updated == (1, 2)
+
+
+def test_config_wire_form_keeps_foreign_fields():
+    cfg = Config(batch_size=64, per_alpha=0.7)
+    back = Config.deserialize(cfg.serialize().encode())
+    assert back == cfg
+    import json
+    foreign = json.loads(cfg.serialize())
+    foreign["env_name"] = "MinAtar/Breakout-v1"              # a field only the reference's 91-field Config has
+    back = Config.deserialize(json.dumps(foreign).encode())
+    assert back.env_name == "MinAtar/Breakout-v1" and back.batch_size == 64
