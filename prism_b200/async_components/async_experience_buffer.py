@@ -116,12 +116,9 @@ class AsyncExperienceBufferInterface(object):
         if self._local is not None:
             self._local.set_static_batch(batch)
         self._batch = batch
-        self._obs = batch["observation"]
-        self._next_obs = batch["next"]["observation"]
-        self._reward = batch["next"]["reward"]
-        self._nonterminal = batch["nonterminal"]
-        self._gamma = batch["gamma"]
-        self._action = batch["action"]
+        nxt = batch["next"]
+        self._obs, self._next_obs, self._reward = batch["observation"], nxt["observation"], nxt["reward"]
+        self._nonterminal, self._gamma, self._action = batch["nonterminal"], batch["gamma"], batch["action"]
 
     def get_static_batch(self):
         return self._local.get_static_batch() if self._local is not None else self._batch
@@ -161,16 +158,11 @@ class AsyncExperienceBufferInterface(object):
         if arrays is not None:
             for flat in arrays:
                 self._batch_buffer.append(self._deserialize_batch(flat))
-        batch = self._batch_buffer.pop(0)
-        self._obs.copy_(batch[0], non_blocking=True)
-        self._next_obs.copy_(batch[1], non_blocking=True)
-        self._reward.copy_(batch[2], non_blocking=True)
-        self._nonterminal.copy_(batch[3], non_blocking=True)
-        self._gamma.copy_(batch[4], non_blocking=True)
-        self._action.copy_(batch[5].long(), non_blocking=True)
-        if return_info:
-            return self._batch, 1
-        return self._batch
+        received = self._batch_buffer.pop(0)
+        received = received[:5] + (received[5].long(),)
+        for dst, src in zip((self._obs, self._next_obs, self._reward, self._nonterminal, self._gamma, self._action), received):
+            dst.copy_(src, non_blocking=True)
+        return (self._batch, 1) if return_info else self._batch
 
     def update_priority(self, indices, priorities):
         if self._local is None:
