@@ -26,25 +26,15 @@ from .optim import FlatAdam
 class Agent(object):
     def __init__(self, model, action_selector, eval_action_selector, optimizer, target_model,
                  use_cuda_graph, max_grad_norm):
-        super().__init__()
-        self.model = model
-        self.target_model = target_model
-        self.action_selector = action_selector
-        self.eval_action_selector = eval_action_selector
-        self.optimizer = optimizer
-        self.max_grad_norm = max_grad_norm
-        self.use_cuda_graph = use_cuda_graph
-        self.n_updates = 0
-        self._is_eval = False
+        self.model, self.target_model, self.optimizer = model, target_model, optimizer
+        self.action_selector, self.eval_action_selector = action_selector, eval_action_selector
+        self.max_grad_norm, self.use_cuda_graph = max_grad_norm, use_cuda_graph
+        self.n_updates, self._is_eval = 0, False
         if isinstance(optimizer, FlatAdam):
             optimizer.max_grad_norm = float(max_grad_norm) if max_grad_norm else 0.0
-
-        self._static_per_weights = None
-        self._static_distribution_loss = None
-        self._static_q_loss = None
-        self._static_total_loss = None
-        self._static_new_per_weights = None
-        self._static_batch = None
+        # static tensors of the captured update (names as upstream: learner.py and the logger read them)
+        for name in ("per_weights", "distribution_loss", "q_loss", "total_loss", "new_per_weights", "batch"):
+            setattr(self, "_static_" + name, None)
         self._learn_cuda_graph = None
         self.model.train()
 
@@ -101,12 +91,10 @@ class Agent(object):
     # ---- learning -----------------------------------------------------------------------
     def update(self, batch, per_weights=1):
         self.train()
-        if self.use_cuda_graph:
-            new_per_weights = self._update_with_cuda_graph(batch, per_weights)
-        else:
-            new_per_weights = self._update_without_cuda_graph(batch, per_weights)
+        step = self._update_with_cuda_graph if self.use_cuda_graph else self._update_without_cuda_graph
+        td = step(batch, per_weights)
         self.n_updates += 1
-        return new_per_weights
+        return td
 
     def _loss_and_backward(self, batch, per_weights, target_model, after_loss=None):
         """``after_loss(td)``: called once the losses / new priorities exist and before the backward pass starts

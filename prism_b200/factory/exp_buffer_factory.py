@@ -1,37 +1,41 @@
-"""build_exp_buffer(config) -> TimestepBuffer, the seam of prism/factory/exp_buffer_factory.py:10-37:
-the torchrl PrioritizedReplayBuffer(ListStorage) becomes a device-resident ring + sum/min trees."""
+"""build_exp_buffer(config): the seam of prism/factory/exp_buffer_factory.py:10-37.
+
+Local mode: the torchrl ``PrioritizedReplayBuffer(ListStorage)`` / ``ReplayBuffer`` becomes a device-resident ring with
+sum/min trees behind the same ``TimestepBuffer`` interface.  Redis mode (``run_through_redis``): the same two roles as
+upstream -- ``redis_side == "server"`` is the learner / collector end, ``"client"`` the process that owns the buffer --
+plus ``redis_local_buffer``: the learner keeps its own device buffer and only the collectors' steps cross the wire.
+"""
+import copy
+
 import torch
 
 from ..experience import DevicePrioritizedReplayBuffer, TimestepBuffer
 
 
+def _device_buffer(cfg):
+    opt = lambda name, default: getattr(cfg, name, default)            # fields the reference's Config does not have
+    ring_and_trees = DevicePrioritizedReplayBuffer(
+        cfg.experience_replay_capacity, alpha=cfg.per_alpha, beta=cfg.per_beta_start, batch_size=cfg.batch_size,
+        device=cfg.device, prioritized=bool(cfg.use_per), sampling=opt("per_sampling", "iid"),
+        storage_dtype=torch.uint8 if opt("replay_storage_dtype", "float32") == "uint8" else torch.float32,
+        obs_scale=opt("replay_obs_scale_255", False), max_streams=opt("replay_max_streams", 256),
+        staging_rows=opt("replay_staging_rows", 256))
+    return TimestepBuffer(ring_and_trees, frame_stack=cfg.frame_stack_size, device=cfg.device,
+                          n_step=cfg.n_step_returns_length, gamma=cfg.gamma)
+
+
 def build_exp_buffer(config):
-    if getattr(config, "run_through_redis", False):
-        # exp_buffer_factory.py:11-18: "server" = the learner / collector end, "client" = the buffer process
-        if config.redis_side == "server":
-            from ..async_components.async_experience_buffer import AsyncExperienceBufferInterface
-            local = None
-            if getattr(config, "redis_local_buffer", False):
-                import copy
-                local_config = copy.copy(config)
-                local_config.run_through_redis = False
-                local = build_exp_buffer(local_config)
-            return AsyncExperienceBufferInterface(config.redis_host, config.redis_port, config.device, local_buffer=local)
-        elif config.redis_side == "client":
-            from ..async_components.async_experience_buffer import AsyncExperienceBuffer
-            return AsyncExperienceBuffer(config.redis_host, config.redis_port)
-    storage_dtype = torch.uint8 if getattr(config, "replay_storage_dtype", "float32") == "uint8" else torch.float32
-    td_buffer = DevicePrioritizedReplayBuffer(
-        capacity=config.experience_replay_capacity,
-        alpha=config.per_alpha,
-        beta=config.per_beta_start,
-        batch_size=config.batch_size,
-        device=config.device,
-        prioritized=bool(config.use_per),
-        sampling=getattr(config, "per_sampling", "iid"),
-        storage_dtype=storage_dtype,
-        obs_scale=getattr(config, "replay_obs_scale_255", False),
-        max_streams=getattr(config, "replay_max_streams", 256),
-        staging_rows=getattr(config, "replay_staging_rows", 256))
-    return TimestepBuffer(td_buffer, frame_stack=config.frame_stack_size, device=config.device,
-                          n_step=config.n_step_returns_length, gamma=config.gamma)
+    if not getattr(config, "run_through_redis", False):
+        return _device_buffer(config)
+    from ..async_components import AsyncExperienceBuffer, AsyncExperienceBufferInterface
+    side = config.redis_side
+    if side == "client":
+        return AsyncExperienceBuffer(config.redis_host, config.redis_port)
+    if side != "server":
+        raise ValueError("redis_side must be 'server' or 'client', got %r" % (side,))
+    local = None
+    if getattr(config, "redis_local_buffer", False):
+        local_config = copy.copy(config)
+        local_config.run_through_redis = False
+        local = _device_buffer(local_config)
+    return AsyncExperienceBufferInterface(config.redis_host, config.redis_port, config.device, local_buffer=local)
