@@ -188,6 +188,49 @@ def test_decoder_emits_the_script_in_stream_order():
         assert not np.any(S["stream"][t + 1:] == S["stream"][t])
 
 
+def test_decoded_streams_rebuild_the_collectors_links():
+    """The CPU twin of tests/test_gpu_buffer.py::test_wire_blocks_fill_the_device_buffer: feeding the decoder's rows
+    (with the stream ids IT resolved from the prev / next ids) into the oracle buffer yields the same n-step / frame-
+    stacked batches as feeding the same steps with the collector's own stream ids."""
+    from oracle.buffer_oracle import OracleTimestepBuffer, Step
+    S = {k[len("script."):]: GOLD[k] for k in GOLD.files if k.startswith("script.")}
+    shape = tuple(int(d) for d in GOLD["obs_shape"])
+    dec = wire.TimestepWireDecoder(max_streams=8)
+    parts = [dec.feed(NONE.unpack_numbers(GOLD["block%d.packed" % k].tobytes())) for k in range(int(GOLD["n_blocks"]))]
+    sid, obs, action, reward, done, trunc, next_obs = (np.concatenate([p[i] for p in parts if p is not None]) for i in range(7))
+    key = {S["obs"][t].tobytes(): t for t in range(len(S["stream"]))}
+    t_of = [key[o.reshape(-1).tobytes()] for o in obs]
+
+    def fill(streams, rows):
+        buf = OracleTimestepBuffer(256, batch_size=4, frame_stack=2, n_step=3, gamma=0.99, prioritized=False)
+        ids, linkers, steps = [0], {}, []
+
+        def make_step():
+            ids[0] += 1
+            return Step(ids[0])
+
+        for s, (o, a, r, d, tr, nxt) in zip(streams, rows):
+            if s not in linkers:
+                linkers[s] = StreamLinker(o, make_step)
+            step = linkers[s].step(int(a), float(r), bool(d), bool(tr), nxt, nxt)
+            if d or tr:
+                del linkers[s]                       # the next step on this stream id opens a new episode
+            buf.extend(step)
+            steps.append(step)
+        return buf.batch_from(steps), list(linkers.values())
+
+    wired, keep_a = fill(sid.tolist(), zip(obs, action, reward, done, trunc, next_obs))
+    succ = [S["final_obs"][t] if S["trunc"][t] else S["next_obs"][t] for t in t_of]
+    direct, keep_b = fill([int(S["stream"][t]) for t in t_of],
+                          [(S["obs"][t].reshape(shape), S["action"][t], S["reward"][t], S["done"][t], S["trunc"][t],
+                            succ[j].reshape(shape)) for j, t in enumerate(t_of)])
+    for a, b in ((wired["observation"], direct["observation"]), (wired["next"]["observation"], direct["next"]["observation"]),
+                 (wired["next"]["reward"], direct["next"]["reward"]), (wired["nonterminal"], direct["nonterminal"]),
+                 (wired["gamma"], direct["gamma"]), (wired["action"], direct["action"])):
+        assert np.array_equal(a, b)
+    assert wired["gamma"].min() < 0.99 ** 2 and not wired["nonterminal"].all()       # the trace exercises 3-step windows and ends
+
+
 def test_decoder_stream_budget():
     dec = wire.TimestepWireDecoder(max_streams=1)
     a = Timestep(1, obs=np.zeros(3, np.float32), reward=0.0, done=False, truncated=False, action=0)
