@@ -15,7 +15,6 @@ import math
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 
 def _mlp(n_in, n_out, n_layers, width, use_ln, ln_first=True, out_act=False):

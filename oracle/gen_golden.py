@@ -19,7 +19,6 @@ What is frozen:
 import os
 import sys
 import types
-import weakref
 
 import numpy as np
 import torch

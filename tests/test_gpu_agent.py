@@ -1,7 +1,6 @@
 """GPU parity of the agent-side kernels and of the drop-in Agent update against the REFERENCE
 outputs frozen in tests/golden/agent_*.npz / ids.npz and against the CPU oracle.
 Bar (north star): loss and gradients within 1e-4 relative; IDS / greedy actions identical."""
-import copy
 
 import numpy as np
 import pytest

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import load_golden, replay_script_oracle, script_from_fixture, script_successor_obs
+from helpers import load_golden, script_from_fixture, script_successor_obs
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"

@@ -1,9 +1,7 @@
 """Peer-memory exchange kernels (csrc/peer.cu) driven in LOOPBACK: `world` ranks inside one process on one GPU,
 each on its own stream with plain pointers to the other ranks' blocks -- same kernels, same flag protocol as the
 multi-process CUDA-IPC set-up of LearnerStep."""
-import ctypes as C
 
-import numpy as np
 import pytest
 import torch
 

@@ -2,7 +2,6 @@
 oracle/per_oracle.c must reproduce the REFERENCE TimestepBuffer outputs frozen in
 tests/golden/nstep_gather_*.npz; the host link planner of the product library (pure host code,
 runs without a GPU) must produce links that lead to the same answers."""
-import ctypes as C
 
 import numpy as np
 import pytest
