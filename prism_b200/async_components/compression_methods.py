@@ -6,8 +6,9 @@ Two differences, both on the host side of the wire only:
 
 * numeric payloads (every payload this transport carries is one flat list of numbers) are encoded / decoded by the
   native codec in csrc/wire.cu (``pack_numbers`` / ``unpack_numbers``) instead of element by element in Python;
-* ``lz4`` is imported when first needed.  A sender without it falls back to the "NONE" tag (the envelope is
-  self-describing, so any receiver reads it); a receiver without it raises on an "LZ4" message -- never a silent skip.
+* the LZ4 frame codec is looked up when first needed: the ``lz4`` module, else pyarrow's bundled liblz4 (same frame
+  format).  A sender with neither falls back to the "NONE" tag (the envelope is self-describing, so any receiver
+  reads it); a receiver with neither raises on an "LZ4" message -- never a silent skip.
 """
 import ctypes as C
 
@@ -24,12 +25,39 @@ NONE = False
 _DTYPE_CODES = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.int64): 2, np.dtype(np.bool_): 3}
 
 
+class _ArrowLZ4Frame(object):
+    """LZ4 *frame* format through pyarrow's bundled liblz4 -- the same container ``lz4.frame`` reads and writes."""
+
+    def __init__(self, pa):
+        self._pa = pa
+
+    def compress(self, data):
+        return self._pa.Codec("lz4").compress(data, asbytes=True)
+
+    def decompress(self, data):
+        # streaming reader: python-lz4 frames carry linked blocks and an optional content size; both are handled
+        return self._pa.CompressedInputStream(self._pa.BufferReader(data), "lz4").read()
+
+
+_LZ4_PROVIDER = []
+
+
 def _lz4_frame():
-    try:
-        import lz4.frame
-        return lz4.frame
-    except ImportError:
-        return None
+    """The LZ4 frame codec: the ``lz4`` module when installed (what the reference uses), else pyarrow's."""
+    if not _LZ4_PROVIDER:
+        provider = None
+        try:
+            import lz4.frame
+            provider = lz4.frame
+        except ImportError:
+            try:
+                import pyarrow
+                if pyarrow.Codec.is_available("lz4"):
+                    provider = _ArrowLZ4Frame(pyarrow)
+            except ImportError:
+                pass
+        _LZ4_PROVIDER.append(provider)
+    return _LZ4_PROVIDER[0]
 
 
 class NullMessageCompressor(object):
@@ -59,7 +87,7 @@ class LZ4MessageCompressor(object):
     def decompress(data):
         frame = _lz4_frame()
         if frame is None:
-            raise _lib.PbError("received an LZ4-compressed message but the lz4 module is not installed")
+            raise _lib.PbError("received an LZ4-compressed message but neither lz4 nor pyarrow is installed")
         return frame.decompress(data)
 
 

@@ -76,20 +76,39 @@ def test_index_rejects_malformed_blocks():
 
 
 # ---------------------------------------------------------------------------------------------- envelope
-def test_envelope_tags_and_errors():
+def test_envelope_tags_and_errors(monkeypatch):
     ser = cm.MessageSerializer()                                          # asks for LZ4 like the reference default
     small = ser.pack([1, 2, 3])
     assert msgpack.unpackb(small)[0] == "NONE" and ser.unpack(small) == [1, 2, 3]
-    big = ser.pack(list(range(2000)))
-    tag = msgpack.unpackb(big)[0]
-    assert tag == ("LZ4" if cm.LZ4MessageCompressor.available() else "NONE")
-    assert ser.unpack(big) == list(range(2000))
+    zeros = [0.0] * 2000
+    big = ser.pack(zeros)
+    tag, body = msgpack.unpackb(big)
+    assert cm.LZ4MessageCompressor.available() and tag == "LZ4"          # lz4, or pyarrow's liblz4 (present here)
+    assert body[:4] == b"\x04\x22\x4d\x18" and len(body) < len(msgpack.packb(zeros)) // 10
+    assert ser.unpack(big) == zeros
     assert ser.pack(None) is None and ser.unpack(None) is None
     with pytest.raises(ValueError):
         ser.unpack(msgpack.packb(("ZSTD", b"x")))
-    if not cm.LZ4MessageCompressor.available():
-        with pytest.raises(_lib.PbError):                                 # never a silent skip
-            ser.unpack(msgpack.packb(("LZ4", b"\x04\x22\x4d\x18")))
+    # no LZ4 codec at all: the sender degrades to the NONE tag, the receiver refuses loudly
+    monkeypatch.setattr(cm, "_LZ4_PROVIDER", [None])
+    assert msgpack.unpackb(ser.pack(zeros))[0] == "NONE"
+    with pytest.raises(_lib.PbError):
+        ser.unpack(big)
+
+
+def test_lz4_frame_known_answer():
+    """A frame written by hand from the LZ4 frame specification (stored block, no checksums): magic, FLG 0x60
+    (version 01, independent blocks), BD 0x40 (64 KB), header checksum 0x82, block size with the 'uncompressed' bit,
+    end mark -- and the reverse direction: what we emit starts with the same descriptor."""
+    payload = msgpack.packb([1.5, 2, True])
+    stored = b"\x04\x22\x4d\x18\x60\x40\x82" + (len(payload) | 0x80000000).to_bytes(4, "little") + payload + b"\x00" * 4
+    assert cm.LZ4MessageCompressor.decompress(stored) == payload
+    ser = cm.MessageSerializer()
+    assert ser.unpack(msgpack.packb(("LZ4", stored))) == [1.5, 2, True]
+    assert np.array_equal(ser.unpack_numbers(msgpack.packb(("LZ4", stored))), [1.5, 2.0, 1.0])
+    ours = cm.LZ4MessageCompressor.compress(b"\x00" * 4096)
+    assert ours[:4] == b"\x04\x22\x4d\x18" and (ours[4] >> 6) == 1 and len(ours) < 100
+    assert cm.LZ4MessageCompressor.decompress(ours) == b"\x00" * 4096
 
 
 # ---------------------------------------------------------------------------------------------- golden: sender side
@@ -281,6 +300,7 @@ def test_both_ends_over_fake_redis():
     server = FakeRedis()
     cfg = Config(batch_size=4, device="cpu")
     sender = AsyncExperienceBufferInterface("h", 0, "cpu", redis_interface=RedisInterface(client=server), block_size=7)
+    sender._redis_interface.serializer = cm.MessageSerializer(min_size_to_compress=64)     # small blocks: force the LZ4 leg
     sender._redis_interface.set_config(cfg)
     assert RedisInterface(client=server).get_config().batch_size == 4
     steps = [ts for b in blocks for ts in b]
@@ -288,10 +308,11 @@ def test_both_ends_over_fake_redis():
         sender.extend(ts)
     sender.flush()
     assert int(server.get(RedisInterface.TOTAL_TIMESTEPS_COLLECTED_KEY)) == len(steps)
-    # the blocks on the wire are the reference's, byte for byte (NONE-tagged when lz4 is absent)
-    if not cm.LZ4MessageCompressor.available():
-        queued = list(reversed(server.lists[RedisInterface.TIMESTEPS_KEY]))
-        assert queued == [GOLD["block%d.packed" % k].tobytes() for k in range(int(GOLD["n_blocks"]))]
+    # the blocks on the wire are the reference's, byte for byte, inside the (LZ4-framed) envelope
+    queued = list(reversed(server.lists[RedisInterface.TIMESTEPS_KEY]))
+    assert [msgpack.unpackb(m)[0] for m in queued] == ["LZ4"] * len(queued)
+    assert [NONE._unwrap(m) for m in queued] == [NONE._unwrap(GOLD["block%d.packed" % k].tobytes())
+                                                 for k in range(int(GOLD["n_blocks"]))]
 
     recorder = RecordingBuffer(4, shape)
     middle = AsyncExperienceBuffer("h", 0, redis_interface=RedisInterface(client=server), experience_buffer=recorder)
