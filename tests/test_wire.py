@@ -378,3 +378,18 @@ def test_config_wire_form_keeps_foreign_fields():
     foreign["env_name"] = "MinAtar/Breakout-v1"              # a field only the reference's 91-field Config has
     back = Config.deserialize(json.dumps(foreign).encode())
     assert back.env_name == "MinAtar/Breakout-v1" and back.batch_size == 64
+
+
+def test_factory_routes_redis_mode_like_the_reference():
+    """exp_buffer_factory.py:11-18.  No Redis client library in this image: constructing either end without an
+    injected client must fail loudly at the import, not fall back to anything."""
+    import prism_b200
+    for side in ("server", "client"):
+        cfg = Config(run_through_redis=True, redis_side=side, device="cpu")
+        try:
+            import redis  # noqa: F401
+        except ImportError:
+            with pytest.raises(ImportError):
+                prism_b200.build_exp_buffer(cfg)
+    with pytest.raises(ValueError):
+        prism_b200.build_exp_buffer(Config(run_through_redis=True, redis_side="sideways", device="cpu"))
