@@ -12,6 +12,8 @@
 // any invalidation pass.  Each observation frame is stored once (fp32 or uint8); frame
 // stacks and n-step successors are resolved at gather time.  In-flight successors and
 // truncated final observations live in a small aux pool (never sampled).
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include <math.h>
 
@@ -349,6 +351,38 @@ int pb_store_extend_plan(long long size, long long aux_size, int n_streams, long
             meta_h[j].next_link = -((long long)sid + 2); meta_h[j].aux_row = sid; stream_last_h[sid] = s;
         }
     }
+    return PB_OK;
+}
+
+// Fill a staging block from the collector's arrays and plan it, in one host call (what IngestSlot.fill does with a
+// dozen small numpy assignments per learner iteration).
+int pb_store_stage_block(long long size, long long aux_size, int n_streams, long long n, long long seq0,
+                         long long row_bytes, const void *obs_h, const void *next_obs_h, const int *stream_id_h,
+                         const long long *action_h, const float *reward_h, const uint8_t *done_h, const uint8_t *trunc_h,
+                         void *rows_h, long long *stream_last_h, long long *trunc_cursor_h, long long *trunc_owner_h,
+                         pb_step_meta *meta_h)
+{
+    if (n < 0 || row_bytes <= 0) return PB_E_ARG;
+    if (n == 0) return PB_OK;
+    if (!obs_h || !next_obs_h || !stream_id_h || !action_h || !reward_h || !done_h || !trunc_h || !rows_h || !meta_h)
+        return PB_E_ARG;
+    uint8_t small[256];
+    uint8_t *flags = n <= 256 ? small : (uint8_t *)malloc((size_t)n);
+    if (!flags) return PB_E_ARG;
+    for (long long j = 0; j < n; ++j) {
+        const uint8_t d = done_h[j] ? 1 : 0, t = trunc_h[j] ? 1 : 0;
+        flags[j] = (uint8_t)(d * PB_STEP_DONE + t * PB_STEP_TRUNC);
+        meta_h[j].action = (int)action_h[j];
+        meta_h[j].reward = reward_h[j];
+        meta_h[j].done = d;
+        meta_h[j].trunc = t;
+    }
+    const int rc = pb_store_extend_plan(size, aux_size, n_streams, n, seq0, stream_id_h, flags, stream_last_h,
+                                        trunc_cursor_h, trunc_owner_h, meta_h);
+    if (flags != small) free(flags);
+    if (rc != PB_OK) return rc;                                     // nothing planned: leave the rows alone too
+    memcpy(rows_h, obs_h, (size_t)(n * row_bytes));
+    memcpy((char *)rows_h + n * row_bytes, next_obs_h, (size_t)(n * row_bytes));
     return PB_OK;
 }
 

@@ -6,6 +6,7 @@ multiprocessing_experience_collection/collector_process_interface.py:146-173) an
 Python batch loop of prism/experience/timestep_buffer.py:79-257.  Kernels: csrc/store.cu.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -13,6 +14,9 @@ import torch
 from .. import _lib
 
 STEP_DONE, STEP_TRUNC, STEP_NO_NEXT = 1, 2, 4
+# PB_NATIVE_STAGE=1: IngestSlot.fill stages a block with ONE host call instead of a dozen numpy assignments (opt-in
+# until it has run on the device path; the call itself is covered on CPU, tests/test_oracle_buffer.py)
+NATIVE_STAGE = os.environ.get("PB_NATIVE_STAGE", "0") == "1"
 
 
 class TransitionRing:
@@ -281,7 +285,34 @@ class IngestSlot:
         self.flags = np.zeros(self.n, dtype=np.uint8)
         self.h2d_bytes = self.h_block.numel()
 
+    def _fill_native(self, stream_ids, obs, action, reward, done, trunc, next_obs):
+        """One host call (pb_store_stage_block) when every array already has the staged layout and dtype; returns
+        False (nothing touched) otherwise."""
+        ring, n, rows = self.ring, self.n, self.rows_np
+
+        def ok(a, dtypes, size):
+            return isinstance(a, np.ndarray) and a.dtype in dtypes and a.size == size and a.flags.c_contiguous
+
+        one_byte = (np.dtype(np.bool_), np.dtype(np.uint8))
+        if not (ok(obs, (rows.dtype,), rows[0].size) and ok(next_obs, (rows.dtype,), rows[0].size)
+                and ok(stream_ids, (np.dtype(np.int32),), n) and ok(action, (np.dtype(np.int64),), n)
+                and ok(reward, (np.dtype(np.float32),), n) and ok(done, one_byte, n) and ok(trunc, one_byte, n)):
+            return False
+        rc = ring._lib.pb_store_stage_block(
+            ring.size, ring.aux_size, ring.max_streams, n, ring.seq, rows[0, 0].nbytes, obs.ctypes.data,
+            next_obs.ctypes.data, stream_ids.ctypes.data, action.ctypes.data, reward.ctypes.data, done.ctypes.data,
+            trunc.ctypes.data, rows.ctypes.data, ring.stream_last.ctypes.data, ring.trunc_cursor.ctypes.data,
+            ring.trunc_owner.ctypes.data, self.h_meta.data_ptr())
+        if rc == _lib.PB_E_POOL:
+            raise _lib.PbError("truncated-observation pool exhausted under a captured ingest graph: "
+                               "construct the ring with a larger trunc_pool")
+        _lib.check(rc, "pb_store_stage_block")
+        ring.seq += n
+        return True
+
     def fill(self, stream_ids, obs, action, reward, done, trunc, next_obs):
+        if NATIVE_STAGE and self._fill_native(stream_ids, obs, action, reward, done, trunc, next_obs):
+            return
         ring, n = self.ring, self.n
         self.rows_np[0] = np.asarray(obs).reshape(n, -1)
         self.rows_np[1] = np.asarray(next_obs).reshape(n, -1)

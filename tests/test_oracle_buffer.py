@@ -146,3 +146,68 @@ def test_planner_pool_exhaustion_is_side_effect_free():
                                   P(owner), P(meta))
     assert rc == _lib.PB_E_POOL
     assert (stream_last == -1).all() and cursor[0] == 0 and (owner == -1).all()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.uint8])
+def test_stage_block_equals_the_numpy_staging(dtype):
+    """pb_store_stage_block (one host call) == what IngestSlot.fill does with numpy assignments + the planner:
+    staged rows, the whole 64-byte metadata records and every piece of planner state, block after block."""
+    from prism_b200 import _lib
+    lib = _lib.load()
+    fx = load_golden("nstep_gather_fs4")
+    S = script_from_fixture(fx)
+    size, n_streams, pool, n = int(fx["capacity"]), 4, 16, 5
+    E = S["obs"].shape[1]
+    P = lambda a: a.ctypes.data
+    cast = (lambda a: np.ascontiguousarray(a, dtype)) if dtype is np.float32 else \
+        (lambda a: np.ascontiguousarray((np.abs(a) * 40).astype(np.uint8)))
+
+    def fresh():
+        return {"last": np.full(n_streams, -1, np.int64), "cursor": np.zeros(1, np.int64), "owner": np.full(pool, -1, np.int64),
+                "rows": np.zeros((2, n, E), dtype), "meta": np.zeros(n, dtype=np.dtype(_lib.STEP_META_DTYPE))}
+
+    a, b = fresh(), fresh()
+    for seq0 in range(0, (len(S["stream"]) // n) * n, n):
+        sl = slice(seq0, seq0 + n)
+        sid = np.ascontiguousarray(S["stream"][sl], np.int32)
+        obs = cast(S["obs"][sl])
+        nxt = cast(np.stack([script_successor_obs(S, t) for t in range(seq0, seq0 + n)]))
+        action = np.ascontiguousarray(S["action"][sl], np.int64)
+        reward = np.ascontiguousarray(S["reward"][sl], np.float32)
+        done, trunc = np.ascontiguousarray(S["done"][sl]), np.ascontiguousarray(S["trunc"][sl])
+        assert done.dtype == np.bool_
+        # numpy staging, as in IngestSlot.fill
+        a["rows"][0], a["rows"][1] = obs, nxt
+        d8, t8 = done.astype(np.uint8), trunc.astype(np.uint8)
+        flags = (d8 * 1 + t8 * 2).astype(np.uint8)
+        a["meta"]["action"], a["meta"]["reward"], a["meta"]["done"], a["meta"]["trunc"] = action, reward, d8, t8
+        assert lib.pb_store_extend_plan(size, n_streams + pool, n_streams, n, seq0, P(sid), P(flags), P(a["last"]),
+                                        P(a["cursor"]), P(a["owner"]), P(a["meta"])) == 0
+        # one call
+        assert lib.pb_store_stage_block(size, n_streams + pool, n_streams, n, seq0, obs[0].nbytes, P(obs), P(nxt), P(sid),
+                                        P(action), P(reward), P(done), P(trunc), P(b["rows"]), P(b["last"]),
+                                        P(b["cursor"]), P(b["owner"]), P(b["meta"])) == 0
+        assert a["rows"].tobytes() == b["rows"].tobytes() and a["meta"].tobytes() == b["meta"].tobytes()
+        for k in ("last", "cursor", "owner"):
+            assert np.array_equal(a[k], b[k])
+    assert S["trunc"].any() and S["done"].any() and (a["owner"] >= 0).any()
+
+
+def test_stage_block_failure_leaves_the_block_untouched():
+    from prism_b200 import _lib
+    lib = _lib.load()
+    size, n_streams, pool, n, E = 64, 2, 2, 3, 4
+    P = lambda a: a.ctypes.data
+    last, cursor, owner = np.full(n_streams, -1, np.int64), np.zeros(1, np.int64), np.full(pool, -1, np.int64)
+    rows = np.full((2, n, E), 7.0, np.float32)
+    meta = np.zeros(n, dtype=np.dtype(_lib.STEP_META_DTYPE))
+    obs = np.ones((n, E), np.float32)
+    keep = [np.zeros(n, np.int32), np.zeros(n, np.int64), np.zeros(n, np.float32), np.zeros(n, np.uint8),
+            np.ones(n, np.uint8)]                                        # three truncations, two pool rows
+    args = (P(obs), P(obs)) + tuple(P(a) for a in keep)
+    rc = lib.pb_store_stage_block(size, n_streams + pool, n_streams, n, 0, 4 * E, *args, P(rows), P(last), P(cursor),
+                                  P(owner), P(meta))
+    assert rc == _lib.PB_E_POOL
+    assert (rows == 7.0).all() and (last == -1).all() and cursor[0] == 0 and (owner == -1).all()
+    assert lib.pb_store_stage_block(size, n_streams + pool, n_streams, n, 0, 4 * E, None, *args[1:], P(rows), P(last),
+                                    P(cursor), P(owner), P(meta)) == -1      # PB_E_ARG
