@@ -214,13 +214,13 @@ int pb_store_extend_plan(long long size, long long aux_size, int n_streams, long
                          long long *trunc_owner_h, pb_step_meta *meta_h);
 
 /* HOST: fill a staging block and plan it in one call -- rows_h [2][n][row_bytes] <- obs_h, next_obs_h (n contiguous rows
- * of the store dtype each), the caller fields of meta_h <- action / reward / done / trunc, then pb_store_extend_plan
+ * of the store dtype each), the caller fields of meta_h <- action (int32 or int64: action_bytes 4 | 8) / reward / done / trunc, then pb_store_extend_plan
  * with flags = done * PB_STEP_DONE + trunc * PB_STEP_TRUNC.  On PB_E_POOL (or any error) the rows are left untouched. */
 int pb_store_stage_block(long long size, long long aux_size, int n_streams, long long n, long long seq0,
                          long long row_bytes, const void *obs_h, const void *next_obs_h, const int *stream_id_h,
-                         const long long *action_h, const float *reward_h, const uint8_t *done_h, const uint8_t *trunc_h,
-                         void *rows_h, long long *stream_last_h, long long *trunc_cursor_h, long long *trunc_owner_h,
-                         pb_step_meta *meta_h);
+                         const void *action_h, int action_bytes, const float *reward_h, const uint8_t *done_h,
+                         const uint8_t *trunc_h, void *rows_h, long long *stream_last_h, long long *trunc_cursor_h,
+                         long long *trunc_owner_h, pb_step_meta *meta_h);
 
 /* device scatter of n planned steps: obs rows -> ring, next_obs rows -> aux pool, metadata,
  * link patches.  obs/next_obs are device staging buffers [n][obs_elems] of the store dtype,

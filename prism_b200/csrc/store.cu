@@ -358,11 +358,11 @@ int pb_store_extend_plan(long long size, long long aux_size, int n_streams, long
 // dozen small numpy assignments per learner iteration).
 int pb_store_stage_block(long long size, long long aux_size, int n_streams, long long n, long long seq0,
                          long long row_bytes, const void *obs_h, const void *next_obs_h, const int *stream_id_h,
-                         const long long *action_h, const float *reward_h, const uint8_t *done_h, const uint8_t *trunc_h,
-                         void *rows_h, long long *stream_last_h, long long *trunc_cursor_h, long long *trunc_owner_h,
-                         pb_step_meta *meta_h)
+                         const void *action_h, int action_bytes, const float *reward_h, const uint8_t *done_h,
+                         const uint8_t *trunc_h, void *rows_h, long long *stream_last_h, long long *trunc_cursor_h,
+                         long long *trunc_owner_h, pb_step_meta *meta_h)
 {
-    if (n < 0 || row_bytes <= 0) return PB_E_ARG;
+    if (n < 0 || row_bytes <= 0 || (action_bytes != 4 && action_bytes != 8)) return PB_E_ARG;
     if (n == 0) return PB_OK;
     if (!obs_h || !next_obs_h || !stream_id_h || !action_h || !reward_h || !done_h || !trunc_h || !rows_h || !meta_h)
         return PB_E_ARG;
@@ -372,7 +372,7 @@ int pb_store_stage_block(long long size, long long aux_size, int n_streams, long
     for (long long j = 0; j < n; ++j) {
         const uint8_t d = done_h[j] ? 1 : 0, t = trunc_h[j] ? 1 : 0;
         flags[j] = (uint8_t)(d * PB_STEP_DONE + t * PB_STEP_TRUNC);
-        meta_h[j].action = (int)action_h[j];
+        meta_h[j].action = action_bytes == 8 ? (int)((const long long *)action_h)[j] : ((const int *)action_h)[j];
         meta_h[j].reward = reward_h[j];
         meta_h[j].done = d;
         meta_h[j].trunc = t;

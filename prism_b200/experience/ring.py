@@ -295,12 +295,12 @@ class IngestSlot:
 
         one_byte = (np.dtype(np.bool_), np.dtype(np.uint8))
         if not (ok(obs, (rows.dtype,), rows[0].size) and ok(next_obs, (rows.dtype,), rows[0].size)
-                and ok(stream_ids, (np.dtype(np.int32),), n) and ok(action, (np.dtype(np.int64),), n)
+                and ok(stream_ids, (np.dtype(np.int32),), n) and ok(action, (np.dtype(np.int64), np.dtype(np.int32)), n)
                 and ok(reward, (np.dtype(np.float32),), n) and ok(done, one_byte, n) and ok(trunc, one_byte, n)):
             return False
         rc = ring._lib.pb_store_stage_block(
             ring.size, ring.aux_size, ring.max_streams, n, ring.seq, rows[0, 0].nbytes, obs.ctypes.data,
-            next_obs.ctypes.data, stream_ids.ctypes.data, action.ctypes.data, reward.ctypes.data, done.ctypes.data,
+            next_obs.ctypes.data, stream_ids.ctypes.data, action.ctypes.data, action.itemsize, reward.ctypes.data, done.ctypes.data,
             trunc.ctypes.data, rows.ctypes.data, ring.stream_last.ctypes.data, ring.trunc_cursor.ctypes.data,
             ring.trunc_owner.ctypes.data, self.h_meta.data_ptr())
         if rc == _lib.PB_E_POOL:

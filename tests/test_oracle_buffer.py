@@ -148,8 +148,8 @@ def test_planner_pool_exhaustion_is_side_effect_free():
     assert (stream_last == -1).all() and cursor[0] == 0 and (owner == -1).all()
 
 
-@pytest.mark.parametrize("dtype", [np.float32, np.uint8])
-def test_stage_block_equals_the_numpy_staging(dtype):
+@pytest.mark.parametrize("dtype,action_dtype", [(np.float32, np.int64), (np.uint8, np.int32)])
+def test_stage_block_equals_the_numpy_staging(dtype, action_dtype):
     """pb_store_stage_block (one host call) == what IngestSlot.fill does with numpy assignments + the planner:
     staged rows, the whole 64-byte metadata records and every piece of planner state, block after block."""
     from prism_b200 import _lib
@@ -172,7 +172,7 @@ def test_stage_block_equals_the_numpy_staging(dtype):
         sid = np.ascontiguousarray(S["stream"][sl], np.int32)
         obs = cast(S["obs"][sl])
         nxt = cast(np.stack([script_successor_obs(S, t) for t in range(seq0, seq0 + n)]))
-        action = np.ascontiguousarray(S["action"][sl], np.int64)
+        action = np.ascontiguousarray(S["action"][sl], action_dtype)
         reward = np.ascontiguousarray(S["reward"][sl], np.float32)
         done, trunc = np.ascontiguousarray(S["done"][sl]), np.ascontiguousarray(S["trunc"][sl])
         assert done.dtype == np.bool_
@@ -185,7 +185,7 @@ def test_stage_block_equals_the_numpy_staging(dtype):
                                         P(a["cursor"]), P(a["owner"]), P(a["meta"])) == 0
         # one call
         assert lib.pb_store_stage_block(size, n_streams + pool, n_streams, n, seq0, obs[0].nbytes, P(obs), P(nxt), P(sid),
-                                        P(action), P(reward), P(done), P(trunc), P(b["rows"]), P(b["last"]),
+                                        P(action), action.itemsize, P(reward), P(done), P(trunc), P(b["rows"]), P(b["last"]),
                                         P(b["cursor"]), P(b["owner"]), P(b["meta"])) == 0
         assert a["rows"].tobytes() == b["rows"].tobytes() and a["meta"].tobytes() == b["meta"].tobytes()
         for k in ("last", "cursor", "owner"):
@@ -204,7 +204,7 @@ def test_stage_block_failure_leaves_the_block_untouched():
     obs = np.ones((n, E), np.float32)
     keep = [np.zeros(n, np.int32), np.zeros(n, np.int64), np.zeros(n, np.float32), np.zeros(n, np.uint8),
             np.ones(n, np.uint8)]                                        # three truncations, two pool rows
-    args = (P(obs), P(obs)) + tuple(P(a) for a in keep)
+    args = (P(obs), P(obs), P(keep[0]), P(keep[1]), 8) + tuple(P(a) for a in keep[2:])
     rc = lib.pb_store_stage_block(size, n_streams + pool, n_streams, n, 0, 4 * E, *args, P(rows), P(last), P(cursor),
                                   P(owner), P(meta))
     assert rc == _lib.PB_E_POOL
