@@ -111,6 +111,12 @@ class AsyncExperienceBufferInterface(object):
         if local_buffer is not None:
             self.buffer = local_buffer.buffer            # learner.py:104-107 reaches buffer.buffer._sampler._beta
 
+    @property
+    def local_buffer(self):
+        """The learner's own device buffer in local-buffer mode (hand THIS to ``LearnerStep`` and call ``drain()``
+        between iterations), else None."""
+        return self._local
+
     # ---- static batch ------------------------------------------------------------------------------------------------
     def set_static_batch(self, batch):
         if self._local is not None:
