@@ -1,0 +1,25 @@
+"""bench.py's reference arm runs on host cores only, so its JSON contract can be checked without a GPU."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1                                       # ONE JSON line
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 1
+    assert line["unit"] == "transitions/s" and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["value"] > 0 and abs(line["ms_per_step"] * 1e-3 * line["value"] - 256) < 1e-6 * 256
+    assert "workload" in line["config"] and "model" not in line["config"]
+    cpu = line["cpu_baseline"]
+    assert cpu["kind"] in ("port", "reference") and cpu["cores"] >= 1 and cpu["value"] == line["value"] and cpu["sample"]
+    e2e = line["e2e"]
+    assert e2e["value"] == line["value"] and e2e["unit"] == line["unit"]
+    assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
