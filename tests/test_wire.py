@@ -393,3 +393,27 @@ def test_factory_routes_redis_mode_like_the_reference():
                 prism_b200.build_exp_buffer(cfg)
     with pytest.raises(ValueError):
         prism_b200.build_exp_buffer(Config(run_through_redis=True, redis_side="sideways", device="cpu"))
+
+
+def test_codec_property_random_payloads():
+    """Random typed segments: the packer is byte-identical to msgpack on the concatenated Python list and the unpacker
+    inverts it (NaN and infinities included)."""
+    from hypothesis import given, settings, strategies as st
+
+    seg = st.one_of(
+        st.lists(st.integers(min_value=-2 ** 63, max_value=2 ** 63 - 1), max_size=40).map(lambda v: np.asarray(v, dtype=np.int64)),
+        st.lists(st.floats(width=32, allow_nan=True, allow_infinity=True), max_size=40).map(lambda v: np.asarray(v, dtype=np.float32)),
+        st.lists(st.floats(allow_nan=True, allow_infinity=True), max_size=40).map(lambda v: np.asarray(v, dtype=np.float64)),
+        st.lists(st.booleans(), max_size=40).map(lambda v: np.asarray(v, dtype=np.bool_)))
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(seg, max_size=6))
+    def check(segments):
+        as_list = [x for s in segments for x in s.tolist()]
+        packed = cm.pack_numbers(segments)
+        assert packed == msgpack.packb(as_list)
+        back = cm.unpack_numbers(packed)
+        want = np.asarray([float(x) for x in as_list], dtype=np.float64)
+        assert back.shape == want.shape and np.array_equal(back, want, equal_nan=True)
+
+    check()
