@@ -481,6 +481,11 @@ int pb_theil_bwd(int n_tensors, int K, int chunks, const long long *table, const
 int pb_loss_combine(int B, const float *dist, const float *q, const float *w, float q_scale,
                     const float *q_offset, float *total_out, float *td_out, void *stream);
 
+/* Timeline mark for measurement runs: *dst (device) = %globaltimer (ns) when the stream -- or the graph branch the call
+ * was captured on -- reaches this point.  One single-thread launch; the product path never calls it unless a trace was
+ * asked for (LearnerStep.enable_trace), since nsys is not available on the measurement boxes. */
+int pb_stamp_time(unsigned long long *dst, void *stream);
+
 /* ---- wire codec of the remote-actor transport.  HOST functions: plain host pointers, no stream, no
  * device work.  They replace the per-element Python walks of the reference's Redis path:
  *   msgpack array of numbers -> float64   prism/async_components/compression_methods.py:72-80 (msgpack.unpackb)

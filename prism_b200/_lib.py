@@ -137,6 +137,7 @@ SIGNATURES = {
     "pb_linear_fwd_tc": [_I, _I, _I, _I, _P, _LL, _P, _P, _I, _P, _P],
     "pb_linear_bwd_input": [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P],
     "pb_linear_bwd_weight": [_I, _I, _I, _I, _P, _P, _P, _LL, _P, _P, _P],
+    "pb_stamp_time": [_P, _P],
     "pb_store_stage_block": [_LL, _LL, _I, _LL, _LL, _LL, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "pb_wire_unpack_numbers": [_P, _LL, _P, _LL, _P],
     "pb_wire_array_header": [_LL, _P, _P],

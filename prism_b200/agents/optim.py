@@ -120,16 +120,19 @@ class FlatAdam(object):
         stream = torch.cuda.current_stream(self.device).cuda_stream
         import ctypes
         n_part = ctypes.c_int(0)
+        mark = getattr(self, "_mark", None) or (lambda name: None)      # LearnerStep.enable_trace()
         if self.peer is not None:
             _lib.check(self._lib.pb_pack_grads(len(self.params), self.table.data_ptr(), self.grad_scale,
                                                self.grad.data_ptr(), None, None, None, stream), "pb_pack_grads")
-            self.peer.allreduce_adam(self, trailing_barrier=self.peer_trailing_barrier)
+            mark("opt:packed")
+            self.peer.allreduce_adam(self, trailing_barrier=self.peer_trailing_barrier, mark=mark)
             return
         if self.allreduce is None:
             _lib.check(self._lib.pb_pack_grads(len(self.params), self.table.data_ptr(), self.grad_scale,
                                                self.grad.data_ptr(), self.partials.data_ptr(),
                                                self.step_count.data_ptr(), ctypes.byref(n_part), stream),
                        "pb_pack_grads")
+            mark("opt:packed")
         else:
             _lib.check(self._lib.pb_pack_grads(len(self.params), self.table.data_ptr(), self.grad_scale,
                                                self.grad.data_ptr(), None, None, None, stream), "pb_pack_grads")

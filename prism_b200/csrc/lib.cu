@@ -16,7 +16,24 @@ int pb_sm_count()
     return n;
 }
 
+namespace {
+// device timeline mark: the GPU's nanosecond clock at the point of the stream (or graph branch) it was enqueued on
+__global__ void stamp_kernel(unsigned long long *dst)
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *dst = t;
+}
+}  // namespace
+
 extern "C" {
+
+int pb_stamp_time(unsigned long long *dst, void *stream)
+{
+    if (!dst) return PB_E_ARG;
+    PB_LAUNCH(stamp_kernel, 1, 1, 0, stream, dst);
+    return PB_OK;
+}
 
 int pb_abi_version(void) { return PB_ABI_VERSION; }
 

@@ -104,6 +104,7 @@ class LearnerStep:
             self.exchange = "peer" if self.peer is not None else "nccl"
         self.launches_per_step = None
         self._side = None
+        self._trace = None               # enable_trace(): device buffer of timeline marks
         import os as _os
         self.overlap_write_back = _os.environ.get("PB_OVERLAP_WRITEBACK", "1") != "0"
 
@@ -164,7 +165,7 @@ class LearnerStep:
         v["gamma"].fill_(1.0)
         return v, arena
 
-    def _sample_gather(self, u, out):
+    def _sample_gather(self, u, out, tag=""):
         """(all-gather of shard states +) sample + fused n-step gather into ``out`` (live or shadow views)."""
         tree, ring = self.tree, self.ring
         if self.world_size > 1:
@@ -173,10 +174,12 @@ class LearnerStep:
             else:
                 import torch.distributed as dist
                 dist.all_gather_into_tensor(self.all_state.view(-1), tree.state, group=self.pg)
+            self._mark(tag + "shard_states_gathered")
             tree.sample_global(self.world_size, self.rank, self.all_state, self.B_global, u,
                                idx_out=out["idx"], weight_out=out["weight"], stratum_out=self.stratum)
         else:
             tree.sample(self.B, u=u, idx_out=out["idx"], weight_out=out["weight"])
+        self._mark(tag + "sampled")
         # rows past the strata this rank owns have idx -1 / weight 0: skipped by gather and update
         ring.gather(out["idx"][:self.B_pad], out["obs"], out["next_obs"], out["reward"], out["gamma"],
                     out["nonterminal"], out["action"])
@@ -184,7 +187,11 @@ class LearnerStep:
     def _prime(self):
         """Fill the shadow batch eagerly (first iteration, or after anything outside this object touched the
         buffer): uniforms from the in-kernel generator."""
-        self._sample_gather(None, self._shadow)
+        trace, self._trace = self._trace, None          # eager: not part of the replayed timeline
+        try:
+            self._sample_gather(None, self._shadow)
+        finally:
+            self._trace = trace
         self._primed = True
         self._seen_mutations = getattr(self.buffer, "_mutations", 0)
 
@@ -192,6 +199,8 @@ class LearnerStep:
         tree, ring, agent, b = self.tree, self.ring, self.agent, self.buffer
         u = None if draw else self.u            # None: uniforms are drawn inside the sampling kernel
         u_sel = consume and getattr(self, "_u_in_block", False)
+        mark = self._mark
+        mark("start")
         if self.prefetch:
             self._live_arena.copy_(self._shadow_arena)          # batch sampled on the previous iteration's tail
         else:
@@ -200,6 +209,7 @@ class LearnerStep:
             self._sample_gather(u, {"idx": self.idx, "weight": self.weight, "obs": b._obs, "next_obs": b._next_obs,
                                     "reward": b._reward, "gamma": b._gamma, "nonterminal": b._nonterminal,
                                     "action": b._action})
+        mark("batch_ready")
         idx, w = self.idx[:self.B_pad], self.weight[:self.B_pad]
         # The priority write-back (learner.py:120) needs the new TD errors only, not the optimizer step: it runs on
         # a second stream -- a parallel branch of the captured graph -- while backward / (exchange) / Adam proceed.
@@ -209,6 +219,7 @@ class LearnerStep:
 
         def write_back(td):
             self.td = td
+            mark("loss_ready")
             if not self.overlap_write_back:
                 return
             self._side.wait_stream(cur)
@@ -218,19 +229,24 @@ class LearnerStep:
                 side2.wait_stream(cur)
                 with torch.cuda.stream(side2):
                     self.ingest.consume_ring()
+                    mark("tail:ring_ingested")
             with torch.cuda.stream(self._side):
                 tree.update_priority(idx, td, sorted=self.sorted)      # |td| is taken inside the kernel
+                mark("tail:priorities_written")
                 if consume:
                     self.ingest.consume_tree()         # default priorities of the new steps, after the write-back
                     self._side.wait_stream(side2)
                 if self.prefetch and u_sel:
                     self.ingest.select_uniforms(self.u, after_counter_inc=True)
                 if self.prefetch:
-                    self._sample_gather(u, self._shadow)      # next iteration's batch
+                    self._sample_gather(u, self._shadow, tag="tail:")      # next iteration's batch
+                    mark("tail:next_batch_ready")
 
         dl, ql, total, td = agent._loss_and_backward(self.batch, w, agent.target_model, after_loss=write_back)
         agent._static_distribution_loss, agent._static_q_loss, agent._static_total_loss = dl, ql, total
+        mark("backward_done")
         agent._optimizer_step(refresh_table=refresh_table)
+        mark("optimizer_done")
         if self.loss_host is not None and total is not None:
             # device -> host read of the step's result as a node of the same graph (pinned scalar)
             self.loss_host.copy_(total.detach(), non_blocking=True)
@@ -243,8 +259,46 @@ class LearnerStep:
             if self.prefetch:
                 if u_sel:
                     self.ingest.select_uniforms(self.u, after_counter_inc=True)
-                self._sample_gather(u, self._shadow)
+                self._sample_gather(u, self._shadow, tag="tail:")
+        mark("end")
         return total
+
+    # ---- timeline marks (measurement only; nsys is not available on the boxes) ---------------------------------------
+    def enable_trace(self, max_marks=64):
+        """Insert device timestamps (pb_stamp_time: one single-thread launch each) at the phase boundaries of the
+        step, on whichever graph branch reaches them; the graph is re-captured.  ``trace_report()`` reads them."""
+        self._trace = {"buf": torch.zeros(max_marks, dtype=torch.int64, device=self.device), "names": {}}
+        opt = self.agent.optimizer
+        if isinstance(opt, FlatAdam):
+            opt._mark = self._mark
+        self.graph, self._primed = None, False
+
+    def disable_trace(self):
+        self._trace = None
+        if isinstance(self.agent.optimizer, FlatAdam):
+            self.agent.optimizer._mark = None
+        self.graph, self._primed = None, False
+
+    def _mark(self, name):
+        tr = self._trace
+        if tr is None:
+            return
+        names = tr["names"]
+        i = names.setdefault(name, len(names))
+        if i >= tr["buf"].numel():
+            raise _lib.PbError("more timeline marks than enable_trace(max_marks=%d)" % tr["buf"].numel())
+        _lib.check(self._lib.pb_stamp_time(tr["buf"].data_ptr() + 8 * i,
+                                           torch.cuda.current_stream(self.device).cuda_stream), "pb_stamp_time")
+
+    def trace_report(self):
+        """{mark: nanoseconds since "start"} of the LAST replay (synchronises)."""
+        tr = self._trace
+        if tr is None:
+            raise _lib.PbError("enable_trace() first")
+        torch.cuda.synchronize(self.device)
+        t = tr["buf"].cpu().tolist()
+        t0 = t[tr["names"]["start"]]
+        return {name: t[i] - t0 for name, i in sorted(tr["names"].items(), key=lambda kv: kv[1])}
 
     def step(self, u=None, ingest=None):
         """Run one iteration.  ``u`` (optional): fp64 uniforms (device or pinned-host tensor, B_global

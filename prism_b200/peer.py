@@ -108,7 +108,7 @@ class PeerGroup:
                    "pb_peer_state_allgather")
         return self.all_state
 
-    def allreduce_adam(self, opt, trailing_barrier=True):
+    def allreduce_adam(self, opt, trailing_barrier=True, mark=None):
         """Sum ``opt.grad`` (= self.grad) over the ranks and apply clip + Adam on every replica (csrc/peer.cu).
 
         ``trailing_barrier``: the one-shot schedule lets a fast rank leave while slower ranks still pull its gradient;
@@ -116,22 +116,28 @@ class PeerGroup:
         every step starts with the state all-gather (a full handshake on the same graph branch) before anything
         touches the arena again.  With prefetch that handshake runs on the tail branch, so it passes True."""
         lib, st = _lib.load(), self._stream()
+        mark = mark or (lambda name: None)                        # timeline marks of LearnerStep.enable_trace()
         _lib.check(lib.pb_peer_barrier(C.byref(self.c), st), "pb_peer_barrier")            # every rank packed its gradient
+        mark("opt:all_packed")
         if self.n * 4 * self.world <= ONE_SHOT_MAX_BYTES:
             # small arena: pulling every rank's gradient whole costs less than a second cross-GPU barrier
             n_part = C.c_int(0)
             _lib.check(lib.pb_peer_pull_sum(C.byref(self.c), self.n, opt.partials.data_ptr(), opt.step_count.data_ptr(),
                                             C.byref(n_part), st), "pb_peer_pull_sum")
+            mark("opt:summed")
             _lib.check(lib.pb_adam_clip_apply(self.n, opt.arena.data_ptr(), self.reduced.data_ptr(), opt.exp_avg.data_ptr(),
                                               opt.exp_avg_sq.data_ptr(), opt.step_count.data_ptr(), opt.lr, opt.betas[0],
                                               opt.betas[1], opt.eps, opt.max_grad_norm, opt.partials.data_ptr(), n_part.value,
                                               opt.norm_out.data_ptr(), st), "pb_adam_clip_apply")
+            mark("opt:applied")
             if trailing_barrier:
                 _lib.check(lib.pb_peer_barrier(C.byref(self.c), st), "pb_peer_barrier")
             return
         _lib.check(lib.pb_peer_reduce_scatter(C.byref(self.c), self.n, opt.partials.data_ptr(), opt.step_count.data_ptr(), st),
                    "pb_peer_reduce_scatter")
+        mark("opt:slice_reduced")
         _lib.check(lib.pb_peer_barrier(C.byref(self.c), st), "pb_peer_barrier")            # every slice reduced + norms published
+        mark("opt:all_reduced")
         _lib.check(lib.pb_peer_adam(C.byref(self.c), self.n, opt.arena.data_ptr(), opt.exp_avg.data_ptr(),
                                     opt.exp_avg_sq.data_ptr(), opt.step_count.data_ptr(), opt.lr, opt.betas[0], opt.betas[1],
                                     opt.eps, opt.max_grad_norm, opt.norm_out.data_ptr(), None, st), "pb_peer_adam")
