@@ -162,11 +162,14 @@ class CompositeModel(nn.Module):
                     z_tg = iqn_t.forward(emb_next, n_quantile_samples=Tp)[0]
                 if ens is not None:
                     q_tg = ens_t.forward_heads(emb_next)
+            ops.trace_mark("boot:target_next_done")
         emb = self.embedding_model(obs)
+        ops.trace_mark("fwd:embedded")
         if iqn is not None:
             z_cur, tau = iqn.forward(emb, n_quantile_samples=T)
         if ens is not None:
             q_cur = ens.forward_heads(emb)
+        ops.trace_mark("fwd:heads_done")
         if iqn_online_next or ens_online_next:
             s2.wait_event(emb_ready)
             with torch.cuda.stream(s2), torch.no_grad():
@@ -174,6 +177,7 @@ class CompositeModel(nn.Module):
                     z_on = iqn.forward(emb_next, n_quantile_samples=Tp)[0]
                 if ens_online_next:
                     q_on = ens.forward_heads(emb_next)
+                ops.trace_mark("boot:online_next_done")
             cur.wait_stream(s2)
         cur.wait_stream(s1)
         if iqn is not None:

@@ -151,6 +151,13 @@ def loss_combine(dist_loss, q_loss, per_weights):
 
 
 PARALLEL_BACKWARD = __import__('os').environ.get('PB_PARALLEL_BACKWARD', '1') != '0'
+# LearnerStep.enable_trace() points this at its timeline-mark function (measurement runs only); None otherwise
+TRACE_MARK = None
+
+
+def trace_mark(name):
+    if TRACE_MARK is not None:
+        TRACE_MARK(name)
 _SIDE_STREAMS = {}
 
 
@@ -224,6 +231,8 @@ class _Linear(torch.autograd.Function):
                                                dx.data_ptr(), stream), "pb_linear_bwd_input")
         if side is not None:
             torch.cuda.current_stream(dy.device).wait_stream(side)
+        if TRACE_MARK is not None:
+            TRACE_MARK("bwd:linear K%d M%d N%d J%d" % (K, M, N, J))
         return dx, dw, db, None
 
 
@@ -638,6 +647,8 @@ class _ConvEmbed(torch.autograd.Function):
         _lib.check(lib.pb_conv3x3_relu_bwd(B, H, W, C, OC, xc.data_ptr(), out.data_ptr(), dout.data_ptr(),
                                            scratch.data_ptr(), dw.data_ptr(), _lib.ptr(db), _stream(dout)),
                    "pb_conv3x3_relu_bwd")
+        if TRACE_MARK is not None:
+            TRACE_MARK("bwd:conv3x3")
         return None, dw, db
 
 

@@ -268,15 +268,19 @@ class LearnerStep:
         """Insert device timestamps (pb_stamp_time: one single-thread launch each) at the phase boundaries of the
         step, on whichever graph branch reaches them; the graph is re-captured.  ``trace_report()`` reads them."""
         self._trace = {"buf": torch.zeros(max_marks, dtype=torch.int64, device=self.device), "names": {}}
+        from .agents import ops as _ops
         opt = self.agent.optimizer
         if isinstance(opt, FlatAdam):
             opt._mark = self._mark
+        _ops.TRACE_MARK = self._mark                  # forward / backward phases inside the agent
         self.graph, self._primed = None, False
 
     def disable_trace(self):
+        from .agents import ops as _ops
         self._trace = None
         if isinstance(self.agent.optimizer, FlatAdam):
             self.agent.optimizer._mark = None
+        _ops.TRACE_MARK = None
         self.graph, self._primed = None, False
 
     def _mark(self, name):
