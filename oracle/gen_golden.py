@@ -13,6 +13,9 @@ What is frozen:
                      MessageSerializer envelope with the "NONE" compressor (async_components/compression_methods.py;
                      lz4, msgpack_numpy and redis are absent here and stubbed at import) and the batch flat-list
                      format (async_components/async_experience_buffer.py) on a scripted multi-stream trace
+  ref_checkpoint/    reference TimestepBuffer.save (prism/experience/timestep_buffer.py:259-302) of a wrapped 48-slot
+                     ring over the same kind of trace: experience_buffer/timesteps.pkl (+ ref_checkpoint.npz: the
+                     script and the stored ids) -- input of the checkpoint reader test
   per_tree.npz       ORACLE-generated (parity unpinned: torchrl is absent) -- freezes the restated
                      tree/sampler arithmetic so the C oracle and the CUDA path cannot drift apart
 """
@@ -395,6 +398,62 @@ def gen_wire():
     print("wrote wire")
 
 
+def gen_ref_checkpoint():
+    """The reference's own buffer checkpoint (timesteps.pkl) for the reader in prism_b200."""
+    from prism.experience.timestep import Timestep
+    from prism.experience.timestep_buffer import TimestepBuffer
+    from oracle.buffer_oracle import StreamLinker
+    obs_shape, capacity, n_steps = (3, 2), 48, 70
+    script = make_script(31, n_streams=3, n_steps=n_steps, obs_shape=obs_shape, p_done=0.08, p_trunc=0.06)
+
+    class Dumps:
+        def dumps(self, path):
+            pass
+
+    class FakeRing:
+        """torchrl stand-in: ListStorage semantics of `_storage[i]` (a one-element list per slot)."""
+
+        def __init__(self, cap):
+            self.cap, self._storage, self.cursor, self._batch_size = cap, [], 0, None
+            self._sampler, self._writer = Dumps(), Dumps()
+
+        def extend(self, lst):
+            for it in lst:
+                if self.cursor < len(self._storage):
+                    self._storage[self.cursor] = [it]
+                else:
+                    self._storage.append([it])
+                self.cursor = (self.cursor + 1) % self.cap
+
+    ring = FakeRing(capacity)
+    tb = TimestepBuffer(ring, frame_stack=1, device="cpu", n_step=3, gamma=0.99)
+    ids = [0]
+
+    def make_step():
+        ids[0] += 1
+        return Timestep(ids[0])
+
+    linkers, step_ids = {}, []
+    for t in range(n_steps):
+        s = int(script["stream"][t])
+        if s not in linkers:
+            linkers[s] = StreamLinker(torch.from_numpy(script["obs"][t].reshape(obs_shape).copy()), make_step)
+        step = linkers[s].step(int(script["action"][t]), float(script["reward"][t]), bool(script["done"][t]),
+                               bool(script["trunc"][t]),
+                               torch.from_numpy(script["next_obs"][t].reshape(obs_shape).copy()),
+                               torch.from_numpy(script["final_obs"][t].reshape(obs_shape).copy()))
+        step_ids.append(step.id)
+        tb.extend(step)
+    out_dir = os.path.join(GOLD, "ref_checkpoint")
+    tb.save(out_dir)
+    out = {"obs_shape": np.array(obs_shape), "capacity": np.array(capacity), "step_ids": np.array(step_ids, dtype=np.int64),
+           "stored_ids": np.array([slot[0].id for slot in ring._storage], dtype=np.int64)}
+    for k, v in script.items():
+        out["script." + k] = v
+    np.savez_compressed(os.path.join(GOLD, "ref_checkpoint.npz"), **out)
+    print("wrote ref_checkpoint")
+
+
 # --------------------------------------------------------------------------------------------
 # PER tree fixture (oracle-generated, parity unpinned)
 # --------------------------------------------------------------------------------------------
@@ -432,6 +491,7 @@ def main():
     gen_nstep_gather("nstep_gather_fs4", 4, 48, 160, [7, 48, 100, 160], seed=12)
     gen_per_tree()
     gen_wire()
+    gen_ref_checkpoint()
 
 
 if __name__ == "__main__":

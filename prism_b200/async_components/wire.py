@@ -138,13 +138,15 @@ class TimestepWireDecoder(object):
     def n_waiting(self):
         return len(self._waiting)
 
-    def feed(self, flat):
+    def feed(self, flat, by_id=False):
+        """``by_id``: take the records in increasing id order instead of block order (a checkpoint lists them in ring
+        slot order; ids are the collectors' creation counter, so within a stream they follow arrival order)."""
         flat, rec = index_timesteps(flat)
         if len(rec) == 0:
             return None
         tails = flat[rec[:, 10, None] + np.arange(12)[None, :]]                 # (records, 12) scalar fields
         rows = []                                                               # (stream, obs, action, reward, done, trunc, next_obs)
-        for r in range(len(rec)):
+        for r in (np.argsort(rec[:, 0], kind="stable") if by_id else range(len(rec))):
             c, t = rec[r], tails[r]
             ts_id = int(c[0])
             if c[1] < 0:

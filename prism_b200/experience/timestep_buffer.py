@@ -15,6 +15,7 @@ What changed underneath (B200-first):
     call forces a D2H copy of the TD errors every iteration).
 """
 import os
+import pickle
 
 import numpy as np
 import torch
@@ -281,6 +282,29 @@ class TimestepBuffer(object):
               "tree": None if self.buffer._sampler is None else self.buffer._sampler.state_dict()}
         torch.save(sd, os.path.join(buffer_path, "device_buffer.pt"))
 
+    def load_reference(self, path):
+        """Read a checkpoint written by the REFERENCE's ``TimestepBuffer.save`` (timestep_buffer.py:259-302):
+        ``experience_buffer/timesteps.pkl``, the stored steps as one flat ``Timestep.serialize`` list in ring-slot order,
+        unfinished trajectories artificially truncated by the writer.  The steps are re-ingested in id (creation)
+        order through the batched path.  torchrl's sampler / writer dumps next to it are not read: priorities restart
+        at the default (max) priority, as for freshly collected steps.  Returns the number of steps loaded."""
+        from ..async_components import wire
+        with open(os.path.join(path, "experience_buffer", "timesteps.pkl"), "rb") as f:
+            serialized = _NumbersOnlyUnpickler(f).load()
+        flat = np.asarray([wire.NULL_VALUE if v is None else v for v in serialized], dtype=np.float64)
+        decoder = wire.TimestepWireDecoder(max_streams=self.buffer._storage_opts.get("max_streams", 256))
+        rows = decoder.feed(flat, by_id=True)
+        if rows is None:
+            return 0
+        self.empty()
+        n = self.extend_batch(*rows)
+        self._flush()
+        # the decoder assigned the stream ids: hand back the ones of finished episodes, keep the live ones reserved
+        ring = self.buffer._storage
+        live = set(decoder._tail.values())
+        self._free_streams = [s for s in range(ring.max_streams - 1, -1, -1) if s not in live]
+        return n
+
     def load(self, path):
         buffer_path = os.path.join(path, "experience_buffer")
         sd = torch.load(os.path.join(buffer_path, "device_buffer.pt"), weights_only=False)
@@ -290,6 +314,13 @@ class TimestepBuffer(object):
             self._free_streams = list(range(ring.max_streams - 1, -1, -1))
         if sd["tree"] is not None and self.buffer._sampler is not None:
             self.buffer._sampler.load_state_dict(sd["tree"])
+
+
+class _NumbersOnlyUnpickler(pickle.Unpickler):
+    """timesteps.pkl is a flat list of Python numbers: refuse anything that would import a class."""
+
+    def find_class(self, module, name):
+        raise pickle.UnpicklingError("reference checkpoint may only hold numbers, found %s.%s" % (module, name))
 
 
 def _to_numpy(x):

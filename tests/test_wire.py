@@ -417,3 +417,67 @@ def test_codec_property_random_payloads():
         assert back.shape == want.shape and np.array_equal(back, want, equal_nan=True)
 
     check()
+
+
+def test_reference_checkpoint_reader():
+    """TimestepBuffer.load_reference on a checkpoint written by the REFERENCE's TimestepBuffer.save (frozen by
+    oracle/gen_golden.py: wrapped 48-slot ring, three streams): every stored step comes back, in creation order per
+    stream, unfinished trajectories truncated onto their in-flight observation."""
+    from prism_b200.experience.timestep_buffer import TimestepBuffer
+    gold_dir = os.path.join(os.path.dirname(__file__), "golden")
+    fx = np.load(os.path.join(gold_dir, "ref_checkpoint.npz"))
+    S = {k[len("script."):]: fx[k] for k in fx.files if k.startswith("script.")}
+
+    class Fake(object):
+        """The attributes load_reference touches, without a device."""
+
+        def __init__(self):
+            self.rows, self.emptied, self.flushed = None, 0, 0
+            ring = type("Ring", (), {"max_streams": 8})()
+            self.buffer = type("TD", (), {"_storage_opts": {"max_streams": 8}, "_storage": ring})()
+
+        def empty(self):
+            self.emptied += 1
+
+        def extend_batch(self, *rows):
+            self.rows = rows
+            return len(rows[0])
+
+        def _flush(self):
+            self.flushed += 1
+
+    fake = Fake()
+    n = TimestepBuffer.load_reference(fake, os.path.join(gold_dir, "ref_checkpoint"))
+    stored = fx["stored_ids"]
+    assert n == len(stored) == int(fx["capacity"]) and fake.emptied == 1 and fake.flushed == 1
+    assert fake._free_streams == list(range(7, -1, -1))            # every trajectory in the file is closed
+    sid, obs, action, reward, done, trunc, next_obs = fake.rows
+    t_of_id = {int(i): t for t, i in enumerate(fx["step_ids"])}
+    key = {S["obs"][t].tobytes(): t for t in range(len(S["stream"]))}
+    t_of = np.asarray([key[o.reshape(-1).tobytes()] for o in obs])
+    assert sorted(t_of.tolist()) == sorted(t_of_id[int(i)] for i in stored)
+    assert np.array_equal(action, S["action"][t_of]) and np.array_equal(reward, S["reward"][t_of])
+    assert np.array_equal(done, S["done"][t_of])
+    # per stream: creation order, one stream id per episode; the newest unfinished step of a stream was closed by the writer
+    last = {}
+    for j, t in enumerate(t_of):
+        s = int(S["stream"][t])
+        assert s not in last or t > last[s]
+        last[s] = t
+    tails = {t for t in last.values() if not S["done"][t] and not S["trunc"][t]}
+    assert tails, "the fixture must hold at least one unfinished trajectory"
+    for j, t in enumerate(t_of):
+        assert trunc[j] == (bool(S["trunc"][t]) or t in tails)
+        if S["done"][t]:
+            continue
+        want = S["final_obs"][t] if S["trunc"][t] else S["next_obs"][t]
+        assert np.array_equal(next_obs[j].reshape(-1), want)
+    # anything but numbers in the pickle is refused
+    import pickle
+    import tempfile
+    with tempfile.TemporaryDirectory(dir=gold_dir) as d:
+        os.makedirs(os.path.join(d, "experience_buffer"))
+        with open(os.path.join(d, "experience_buffer", "timesteps.pkl"), "wb") as f:
+            pickle.dump([1, 2.0, Config()], f)
+        with pytest.raises(pickle.UnpicklingError):
+            TimestepBuffer.load_reference(Fake(), d)
