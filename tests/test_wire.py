@@ -166,17 +166,14 @@ def test_linked_list_matches_reference_release_order():
 
 
 # ---------------------------------------------------------------------------------------------- golden: columnar decoder
-def test_decoder_emits_the_script_in_stream_order():
-    S = {k[len("script."):]: GOLD[k] for k in GOLD.files if k.startswith("script.")}
-    dec = wire.TimestepWireDecoder(max_streams=8)
-    parts = []
-    for k in range(int(GOLD["n_blocks"])):
-        rows = dec.feed(NONE.unpack_numbers(GOLD["block%d.packed" % k].tobytes()))
-        if rows is not None:
-            parts.append(rows)
+def _check_decoder_output(S, parts, dec):
+    """The decoder's rows against the collector trace ``S`` they were serialized from."""
+    n = len(S["stream"])
+    if not parts:
+        assert dec.n_waiting == n == dec.n_decoded
+        return
     sid, obs, action, reward, done, trunc, next_obs = (np.concatenate([p[i] for p in parts]) for i in range(7))
     assert obs.dtype == np.float32 and sid.dtype == np.int32 and action.dtype == np.int64
-    n = len(S["stream"])
     assert len(sid) == n - dec.n_waiting and dec.n_decoded == n
     key = {S["obs"][t].tobytes(): t for t in range(n)}
     assert len(key) == n
@@ -205,6 +202,56 @@ def test_decoder_emits_the_script_in_stream_order():
     for t in missing:
         assert not S["done"][t] and not S["trunc"][t]
         assert not np.any(S["stream"][t + 1:] == S["stream"][t])
+
+
+def test_decoder_emits_the_script_in_stream_order():
+    S = {k[len("script."):]: GOLD[k] for k in GOLD.files if k.startswith("script.")}
+    dec = wire.TimestepWireDecoder(max_streams=8)
+    parts = []
+    for k in range(int(GOLD["n_blocks"])):
+        rows = dec.feed(NONE.unpack_numbers(GOLD["block%d.packed" % k].tobytes()))
+        if rows is not None:
+            parts.append(rows)
+    _check_decoder_output(S, parts, dec)
+
+
+def test_decoder_property_random_traces_and_block_boundaries():
+    """Random collector traces (1-5 streams, ends and truncations at random rates) cut into blocks at random places:
+    same invariants as on the reference's fixture; the stream budget is exactly the number of collectors."""
+    from hypothesis import given, settings, strategies as st
+    from oracle.gen_golden import make_script
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.integers(1, 5), st.integers(1, 60), st.floats(0.0, 0.5), st.floats(0.0, 0.5),
+           st.integers(1, 9))
+    def check(seed, n_streams, n_steps, p_done, p_trunc, max_block):
+        S = make_script(seed, n_streams=n_streams, n_steps=n_steps, obs_shape=(2, 2), p_done=p_done, p_trunc=p_trunc)
+        rng = np.random.default_rng(seed)
+        ids = [0]
+
+        def make_step():
+            ids[0] += 1
+            return Timestep(ids[0])
+
+        linkers, steps = {}, []
+        for t in range(n_steps):
+            s = int(S["stream"][t])
+            if s not in linkers:
+                linkers[s] = StreamLinker(S["obs"][t].reshape(2, 2).copy(), make_step)
+            steps.append(linkers[s].step(int(S["action"][t]), float(S["reward"][t]), bool(S["done"][t]), bool(S["trunc"][t]),
+                                         S["next_obs"][t].reshape(2, 2).copy(), S["final_obs"][t].reshape(2, 2).copy()))
+        dec = wire.TimestepWireDecoder(max_streams=n_streams)
+        parts, at = [], 0
+        while at < n_steps:
+            size = int(rng.integers(1, max_block + 1))
+            block = steps[at:at + size]
+            at += size
+            rows = dec.feed(cm.unpack_numbers(cm.pack_numbers(wire.timestep_segments(block))))
+            if rows is not None:
+                parts.append(rows)
+        _check_decoder_output(S, parts, dec)
+
+    check()
 
 
 def test_decoded_streams_rebuild_the_collectors_links():
