@@ -211,3 +211,30 @@ def test_stage_block_failure_leaves_the_block_untouched():
     assert (rows == 7.0).all() and (last == -1).all() and cursor[0] == 0 and (owner == -1).all()
     assert lib.pb_store_stage_block(size, n_streams + pool, n_streams, n, 0, 4 * E, None, *args[1:], P(rows), P(last),
                                     P(cursor), P(owner), P(meta)) == -1      # PB_E_ARG
+
+
+def test_planner_property_random_traces_match_the_linked_object_oracle():
+    """Random 4-stream traces, ring sizes (wrapping several times), frame stacks and staging block sizes: the host
+    planner + the array model of the gather kernel give the same batches as the linked-object oracle buffer."""
+    from hypothesis import given, settings, strategies as st
+    from oracle.gen_golden import make_script
+
+    @settings(max_examples=80, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.integers(8, 64), st.integers(1, 150), st.integers(1, 4), st.integers(1, 11),
+           st.floats(0.0, 0.3), st.floats(0.0, 0.08))
+    def check(seed, capacity, n_steps, fs, staging, p_done, p_trunc):
+        obs_shape = (2, 2)
+        S = make_script(seed, n_streams=4, n_steps=n_steps, obs_shape=obs_shape, p_done=p_done, p_trunc=p_trunc)
+        fx = {"capacity": np.array(capacity), "frame_stack": np.array(fs), "n_step": np.array(3),
+              "gamma": np.array(0.99), "obs_shape": np.array(obs_shape)}
+        fx.update({"script." + k: v for k, v in S.items()})
+        ring, size = plan_script(fx, n_steps, staging=min(staging, capacity))
+        buf, linkers = replay_script_oracle(fx)
+        idx = np.arange(min(n_steps, capacity))
+        want = buf.batch_from([buf.storage[i] for i in idx])
+        obs, nobs, ret, gam, done, act = assemble_from_arrays(ring, size, idx, fs, 3, 0.99, obs_shape)
+        assert np.array_equal(obs, want["observation"]) and np.array_equal(nobs, want["next"]["observation"])
+        assert np.array_equal(ret, want["next"]["reward"].reshape(-1)) and np.array_equal(gam, want["gamma"].reshape(-1))
+        assert np.array_equal(done == 0, want["nonterminal"].reshape(-1)) and np.array_equal(act, want["action"].reshape(-1))
+
+    check()
