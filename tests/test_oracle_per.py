@@ -105,3 +105,106 @@ def test_scan_is_monotone_and_matches_cumsum_when_exact(n, seed):
     cs = np.cumsum(leaves.astype(np.float64))
     expect = np.searchsorted(cs, mass.astype(np.float64), side="left")
     assert np.array_equal(idx, np.minimum(expect, n))
+
+
+class _PyTree(object):
+    """Independent numpy restatement of the rules in SURVEY 8(c) (1)-(7), scalar by scalar in np.float32 -- a
+    second witness for oracle/per_oracle.c (alpha = 0.5 only)."""
+
+    def __init__(self, size, eps=1e-8):
+        self.size, self.cap = size, 1
+        while self.cap < size:
+            self.cap *= 2
+        self.sum = np.zeros(2 * self.cap, np.float32)
+        self.min = np.full(2 * self.cap, np.inf, np.float32)
+        self.len, self.cursor, self.max_priority, self.eps = 0, 0, 1.0, eps
+
+    def _set(self, i, v):
+        pos = i | self.cap
+        self.sum[pos] = self.min[pos] = np.float32(v)
+        while pos > 1:
+            left, right = pos & ~1, pos | 1
+            self.sum[pos >> 1] = np.float32(self.sum[left] + self.sum[right])
+            self.min[pos >> 1] = min(self.min[left], self.min[right])
+            pos >>= 1
+
+    def _query(self, arr, op, ident):
+        if self.len >= self.size:
+            return arr[1]
+        l, r, ret = self.cap, self.len + self.cap, ident
+        while l < r:
+            if l & 1:
+                ret = op(ret, arr[l]); l += 1
+            if r & 1:
+                r -= 1; ret = op(ret, arr[r])
+            l >>= 1; r >>= 1
+        return ret
+
+    def extend(self, n):
+        for _ in range(n):
+            self._set(self.cursor, np.float32((self.max_priority + self.eps) ** 0.5))
+            self.cursor = (self.cursor + 1) % self.size
+            self.len = min(self.len + 1, self.size)
+
+    def update_priority(self, idx, prio):
+        prio = np.asarray(prio, np.float32)
+        if len(prio):
+            self.max_priority = max(self.max_priority, float(prio.max()))
+        for i, p in zip(idx, prio):
+            self._set(int(i), np.sqrt(np.float32(p + np.float32(self.eps))))
+
+    def sample(self, u, beta, stratified):
+        p_sum = self._query(self.sum, lambda a, b: np.float32(a + b), np.float32(0))
+        p_min = self._query(self.min, min, np.float32(np.inf))
+        idx, w, n = [], [], len(u)
+        for k, uk in enumerate(u):
+            m = np.float32(((k + uk) / n) * float(p_sum)) if stratified else np.float32(float(p_sum) * uk)
+            if m > self.sum[1]:
+                i = self.size
+            else:
+                pos = 1
+                while pos < self.cap:
+                    pos <<= 1
+                    if m > self.sum[pos]:
+                        m = np.float32(m - self.sum[pos])
+                        pos |= 1
+                i = pos ^ self.cap
+            i = min(i, self.len - 1)
+            idx.append(i)
+            w.append(np.float32(self.sum[i | self.cap] / p_min) ** np.float32(-beta))
+        return np.asarray(idx), np.asarray(w, np.float32), p_sum, p_min
+
+
+def test_c_oracle_against_independent_numpy_model():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.integers(1, 70), st.integers(1, 12))
+    def check(seed, size, n_ops):
+        rng = np.random.default_rng(seed)
+        c, p = OracleTree(size), _PyTree(size)
+        for _ in range(n_ops):
+            op = rng.integers(0, 3)
+            if op == 0 or len(c) == 0:
+                n = int(rng.integers(1, size + 3))
+                c.extend(n); p.extend(n)
+            elif op == 1:
+                k = int(rng.integers(1, 2 * size))
+                idx = rng.integers(0, len(c), k)                          # duplicates: the last one wins
+                prio = rng.exponential(1.0, k).astype(np.float32) * (rng.random(k) > 0.1)     # some exact zeros
+                c.update_priority(idx, prio); p.update_priority(idx, prio)
+            else:
+                u = rng.random(int(rng.integers(1, 20)))
+                mode = int(rng.integers(0, 2))
+                if p._query(p.min, min, np.float32(np.inf)) <= 0:
+                    with pytest.raises(RuntimeError):
+                        c.sample(u, 0.5, mode)
+                    continue
+                ci, cw, _, cs, cm_ = c.sample(u, 0.5, mode)
+                pi, pw, ps, pm = p.sample(u, 0.5, bool(mode))
+                assert np.array_equal(ci, pi) and cs == ps and cm_ == pm
+                assert np.allclose(cw, pw, rtol=1e-6, atol=0)
+            assert np.array_equal(c.sum, p.sum) and np.array_equal(c.min, p.min)
+            assert len(c) == p.len and c.cursor == p.cursor and c.max_priority == p.max_priority
+
+    check()
