@@ -528,3 +528,49 @@ def test_reference_checkpoint_reader():
             pickle.dump([1, 2.0, Config()], f)
         with pytest.raises(pickle.UnpicklingError):
             TimestepBuffer.load_reference(Fake(), d)
+
+
+def test_reference_self_check_chain_through_the_object_path():
+    """The chain of the reference's own ``complex_save_load_test`` (timestep_buffer.py:397-475: 26 steps, an episode end
+    every 5 below 20, a truncation every 12 from 10 on, observations changing shape after the first step) serialized and
+    rebuilt: ids, observations, flags, prev / next identities and needs_n_step survive; the newest step waits for its
+    in-flight successor."""
+    import weakref
+    steps, t = [], Timestep(1, obs=torch.zeros(3, 4))
+    keep = [t]
+    for i in range(1, 27):
+        t.reward, t.action = i, torch.ones(1)
+        t.done = 20 > i > 0 and i % 5 == 0
+        t.truncated = i >= 10 and i % 12 == 0
+        nt = Timestep(i + 1, obs=torch.ones(2, 42, 42) * i)
+        if t.truncated:
+            t.next = Timestep(113 * (i + 1), obs=torch.ones(2, 42, 42) * -i)
+            t.next.prev = weakref.ref(t)
+        elif not t.done:
+            nt.prev, t.next = weakref.ref(t), weakref.ref(nt)
+        steps.append(t)
+        keep.append(nt)
+        t = nt
+    flat = []
+    for s in steps:
+        flat += s.serialize()
+    back, waiting = Timestep.deserialize_linked_list(NONE.unpack(NONE.pack(flat)))
+    assert sorted(waiting) == [26] and waiting[26][1] == [None, None, 27]
+    by_id = {s.id: s for s in back}
+    by_id[26] = waiting[26][0]
+    assert sorted(by_id) == list(range(1, 27))
+    for bef in steps:
+        aft = by_id[bef.id]
+        assert torch.equal(torch.as_tensor(bef.obs), aft.obs) and aft.reward == float(bef.reward) and aft.action == 1
+        assert (bef.done, bef.truncated, bef.needs_n_step) == (aft.done, aft.truncated, aft.needs_n_step)
+        if bef.truncated:
+            assert isinstance(aft.next, Timestep) and aft.next.id == bef.next.id
+            assert torch.equal(aft.next.obs, bef.next.obs) and aft.next.prev() is aft
+        elif bef.next is not None and bef.id != 26:
+            assert aft.next() is by_id[bef.next().id]
+        else:
+            assert aft.next is None
+        if bef.prev is not None:
+            assert aft.prev() is by_id[bef.prev().id]
+        else:
+            assert aft.prev is None
