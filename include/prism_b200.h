@@ -15,7 +15,10 @@
  *   - `stream` is a cudaStream_t passed as void*.
  *   - all entry points are CUDA-graph capturable (no host reads of device data).
  *   - pointers are DEVICE pointers unless the name ends in _h (host).
- *   - thread-compatible: no globals except a launch counter (atomic).
+ *   - a few entry points are HOST functions (no stream argument, no device work): the ingest planner
+ *     (pb_store_extend_plan, pb_store_stage_block), the wire codec (pb_wire_*), the peer-memory set-up
+ *     (pb_peer_alloc / export / open / close / free, which do allocate or map) and the event / copy wrappers.
+ *   - thread-compatible: no globals except a launch counter (atomic) and per-device one-time kernel attributes.
  */
 #ifndef PRISM_B200_H
 #define PRISM_B200_H
