@@ -657,3 +657,49 @@ def test_prefetch_toggle_and_loss_readback_keep_training_identical():
     assert a[0] == b[0]
     assert a[1] == a[0][3:]
     assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("PB_TEST_TRACE") != "1",
+                    reason="measurement tool added after the round's GPU budget was spent: PB_TEST_TRACE=1 to run")
+def test_step_trace_marks_are_ordered_and_do_not_change_training():
+    """LearnerStep.enable_trace(): the in-graph %globaltimer marks come out in phase order on the main branch, the tail
+    branches start after the loss exists, and a traced run trains bit-identically to an untraced one."""
+    import prism_b200
+    from prism_b200.learner_step import LearnerStep
+    from oracle.gen_golden import make_script
+    cap, B, obs_shape, A = 256, 16, (10, 10, 6), 4
+    S = make_script(13, n_streams=4, n_steps=240, obs_shape=obs_shape, p_done=0.05, p_trunc=0.03, n_actions=A)
+    succ = np.where(S["trunc"][:, None], S["final_obs"], S["next_obs"])
+
+    def run(traced):
+        cfg = prism_b200.minatar_dqn_per_config(device=DEV, experience_replay_capacity=cap, batch_size=B,
+                                                per_sampling="stratified", replay_max_streams=4, replay_staging_rows=64,
+                                                use_cuda_graph=False)
+        torch.manual_seed(0)
+        agent = prism_b200.build_agent(cfg, obs_shape, A)
+        buf = prism_b200.build_exp_buffer(cfg)
+        buf.extend_batch(S["stream"], S["obs"].reshape((-1,) + obs_shape), S["action"], S["reward"], S["done"], S["trunc"],
+                         succ.reshape((-1,) + obs_shape))
+        buf._flush()
+        buf.buffer._sampler.seed(77)
+        step = LearnerStep(buf, agent, batch_size=B, use_cuda_graph=True, prefetch=True)
+        report = None
+        if traced:
+            step.enable_trace()
+        losses = [float(step.step()) for _ in range(5)]
+        if traced:
+            report = step.trace_report()
+            step.disable_trace()
+        losses += [float(step.step()) for _ in range(2)]
+        torch.cuda.synchronize()
+        return losses, agent.optimizer.arena.clone(), report
+
+    (la, pa, rep), (lb, pb, _) = run(True), run(False)
+    assert la == lb and torch.equal(pa, pb)
+    main = ["start", "batch_ready", "fwd:embedded", "fwd:heads_done", "loss_ready", "backward_done", "opt:packed",
+            "optimizer_done", "end"]
+    assert all(m in rep for m in main), sorted(rep)
+    times = [rep[m] for m in main]
+    assert times[0] == 0 and times == sorted(times) and times[-1] < 5_000_000        # one small step: well under 5 ms
+    for tail in ("tail:priorities_written", "tail:sampled", "tail:next_batch_ready"):
+        assert rep["loss_ready"] <= rep[tail] <= rep["end"]
