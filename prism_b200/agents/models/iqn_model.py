@@ -58,6 +58,22 @@ class IQNModel(nn.Module):
         # injected quantile draws, consumed in call order (parity tests replay the reference's torch.rand
         # stream through this; production draws from the device Philox generator)
         self.tau_queue = []
+        # static quantile buffers (set_static_taus): device tensors every learning forward reads, in call order --
+        # how a CAPTURED update graph is fed chosen draws (a Python queue cannot be popped per replay)
+        self._static_taus = []
+        self._static_call = 0
+
+    def set_static_taus(self, taus):
+        """Pin the quantile draws of the learning forwards to these device tensors, consumed cyclically in call order
+        (current, next-online | next-target: iqn_model.py:104-126).  Calling it again with the same shapes copies IN
+        PLACE, so a captured graph sees the new values on its next replay.  ``None`` / [] returns to random draws."""
+        taus = [] if taus is None else [t.to(self.device).float().reshape(-1, 1) for t in taus]
+        if len(taus) == len(self._static_taus) and all(a.shape == b.shape for a, b in zip(taus, self._static_taus)):
+            for dst, src in zip(self._static_taus, taus):
+                dst.copy_(src)
+        else:
+            self._static_taus = [t.clone() for t in taus]
+        self._static_call = 0
 
     # ------------------------------------------------------------------
     def forward(self, x, n_quantile_samples=None, for_action=False, static_quantiles=None):
@@ -76,6 +92,11 @@ class IQNModel(nn.Module):
             quantiles = static_quantiles
         elif self.tau_queue:
             quantiles = self.tau_queue.pop(0).to(self.device).float().view(n * n_rows, 1)
+        elif self._static_taus and not for_action:
+            quantiles = self._static_taus[self._static_call % len(self._static_taus)]
+            self._static_call += 1
+            if quantiles.numel() != n * n_rows:
+                raise ValueError("static quantiles hold %d draws, this forward needs %d" % (quantiles.numel(), n * n_rows))
         else:
             # same shape and dtype as the reference draw (:64-66), from the device generator
             quantiles = torch.rand([n * n_rows, 1], device=self.device).float()

@@ -78,10 +78,13 @@ class QEnsemble(nn.Module):
 
     @staticmethod
     def _to_reference_keys(module, state_dict, prefix, local_metadata):
-        for (seq_idx, pname), pos in module._slot.items():
-            stacked = state_dict.pop("%sstacked.%d" % (prefix, pos))
-            for k in range(module.n_heads):
-                state_dict[prefix + module._ref_key(k, seq_idx, pname)] = stacked[k]
+        # head-major, each head's parameters in Sequential order: the order the reference's ModuleList of K heads
+        # yields (q_ensemble.py:26-42).  Agent.serialize_model / deserialize_model and the optimizer checkpoint walk
+        # state_dict order, so a reference process on the other end reads the heads in this order.
+        stacked = {key: state_dict.pop("%sstacked.%d" % (prefix, pos)) for key, pos in module._slot.items()}
+        for k in range(module.n_heads):
+            for (seq_idx, pname), t in stacked.items():
+                state_dict[prefix + module._ref_key(k, seq_idx, pname)] = t[k]
         return state_dict
 
     def _from_reference_keys(self, state_dict, prefix, *args):

@@ -4,9 +4,26 @@ Every function here launches hand-written sm_100a kernels through the C ABI on t
 torch stream; inputs must be CUDA tensors (no CPU path -- the CPU restatement lives in
 oracle/ and is only ever used by tests and the bench's cpu_baseline leg).
 """
+import collections
+
 import torch
 
 from .. import _lib
+
+# How every dense layer / LayerNorm call was executed, by route name.  "fallthrough:*" routes leave this library
+# (ATen / cuBLAS); the bench line prints the counter and the config-shape parity tests assert on it.
+ROUTES = collections.Counter()
+
+
+def route_counts(reset=False):
+    out = dict(ROUTES)
+    if reset:
+        ROUTES.clear()
+    return out
+
+
+def fallthrough_count():
+    return sum(v for k, v in ROUTES.items() if k.startswith("fallthrough"))
 
 
 def _c(t, dtype=torch.float32):
@@ -389,7 +406,9 @@ def phi_times_x(phi_seq, basis, x, n):
     F_ = lin.weight.shape[0]
     if (len(phi_seq) == 2 and isinstance(lin, nn.Linear) and isinstance(phi_seq[1], nn.ReLU) and lin.bias is not None
             and x.dim() == 2 and x.shape[1] == F_ and (F_ % 4) == 0 and _tc_eligible(x, M, 1, F_, J)):
+        ROUTES["phi_x:tc_gemm"] += 1
         return _PhiTimesX.apply(basis, lin.weight, lin.bias, x)
+    ROUTES["phi_x:unfused"] += 1
     phi = run_sequential(phi_seq, basis)
     return (phi.view(n, x.shape[0], -1) * x.unsqueeze(0)).view(n * x.shape[0], -1)
 
@@ -398,11 +417,14 @@ def linear_heads(x, w, b, relu=False):
     """Stacked-head dense layer: x (M, J) shared by all heads or (K, M, J); w (K, N, J); b (K, N) -> (K, M, N)."""
     M, (Kh, N, J) = x.shape[-2], w.shape
     if _tc_eligible(x, M, Kh, N, J):
+        ROUTES["linear:tc_gemm"] += 1
         return _LinearTC.apply(x, w, b, 1 if relu else 0)
     if x.shape[-2] > FUSED_LINEAR_MAX_ROWS:
+        ROUTES["fallthrough:baddbmm"] += 1
         xe = x.unsqueeze(0).expand(w.shape[0], -1, -1) if x.dim() == 2 else x
         y = torch.baddbmm(b.unsqueeze(1), xe, w.transpose(1, 2)) if b is not None else torch.bmm(xe, w.transpose(1, 2))
         return torch.relu(y) if relu else y
+    ROUTES["linear:ffma"] += 1
     return _Linear.apply(x, w, b, 1 if relu else 0)
 
 
@@ -413,10 +435,13 @@ def linear(x, weight, bias, relu=False):
     narrow = weight.shape[0] <= NARROW_OUT and x.shape[0] <= NARROW_MAX_ROWS
     if x.shape[0] > FUSED_LINEAR_MAX_ROWS and not narrow:
         if _tc_eligible(x, x.shape[0], 1, *weight.shape):
+            ROUTES["linear:tc_gemm"] += 1
             b = None if bias is None else bias.unsqueeze(0)
             return _LinearTC.apply(x, weight.unsqueeze(0), b, 1 if relu else 0).squeeze(0)
+        ROUTES["fallthrough:F.linear"] += 1
         y = torch.nn.functional.linear(x, weight, bias)
         return torch.relu(y) if relu else y
+    ROUTES["linear:ffma"] += 1
     b = None if bias is None else bias.unsqueeze(0)
     return _Linear.apply(x, weight.unsqueeze(0), b, 1 if relu else 0).squeeze(0)
 
@@ -466,7 +491,9 @@ def layer_norm(x, module):
     """nn.LayerNorm module applied through the fused kernels when the activation is large."""
     if (x.is_cuda and x.dim() == 2 and len(module.normalized_shape) == 1 and x.dtype == torch.float32
             and x.numel() >= LN_MIN_ELEMENTS and _lib.load().pb_layer_norm_supported(x.shape[0], x.shape[1])):
+        ROUTES["ln:fused"] += 1
         return _LayerNorm.apply(x, module.weight, module.bias, module.eps)
+    ROUTES["fallthrough:nn.LayerNorm"] += 1
     return module(x)
 
 
@@ -486,6 +513,8 @@ def run_sequential(seq, x):
             x = layer_norm(x, m)
             i += 1
         else:
+            if not isinstance(m, (nn.ReLU, nn.Flatten, nn.Identity)):
+                ROUTES["fallthrough:module:%s" % type(m).__name__] += 1
             x = m(x)
             i += 1
     return x

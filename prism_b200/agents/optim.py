@@ -146,13 +146,68 @@ class FlatAdam(object):
                                                 self.eps, self.max_grad_norm, self.partials.data_ptr(), n_part.value,
                                                 self.norm_out.data_ptr(), stream), "pb_adam_clip_apply")
 
+    # ---- checkpoint format: torch.optim.Adam's own (prism/agents/agent.py:231-252 saves optimizer.state_dict()) ------
+    def reference_layout(self):
+        """[(arena offset, shape)] in the order the REFERENCE's ``model.parameters()`` yields its tensors: the order of
+        ``model.state_dict()`` (reference key names; the stacked (K, ...) ensemble tensors un-stacked head by head).
+        Needs ``layout_model`` (set by build_agent); the entries are views of the parameter arena, so their addresses
+        give the offsets."""
+        model = getattr(self, "layout_model", None)
+        if model is None:
+            return [(o, tuple(p.shape)) for p, o in zip(self.params, self.offsets)]
+        base, out = self.arena.data_ptr(), []
+        for _, v in model.state_dict().items():
+            off = (v.data_ptr() - base) // 4
+            if not (0 <= off and off + v.numel() <= self.numel and v.is_contiguous()):
+                raise _lib.PbError("state_dict entry is not a contiguous view of the parameter arena")
+            out.append((off, tuple(v.shape)))
+        return out
+
     def state_dict(self):
-        return {"exp_avg": self.exp_avg.cpu(), "exp_avg_sq": self.exp_avg_sq.cpu(),
-                "step": self.step_count.cpu(), "lr": self.lr, "betas": self.betas, "eps": self.eps}
+        """A ``torch.optim.Adam.state_dict()``: per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq`` keyed by the
+        index of the parameter in the reference's ``model.parameters()``, plus ``param_groups`` -- what the reference
+        reads back with ``optimizer.load_state_dict`` (agent.py:244-252), and vice versa."""
+        layout = self.reference_layout()
+        template = torch.optim.Adam([torch.zeros(1)], lr=self.lr, betas=self.betas, eps=self.eps)
+        group = dict(template.state_dict()["param_groups"][0])
+        group["params"] = list(range(len(layout)))
+        state = {}
+        steps = int(self.step_count.item())
+        if steps > 0:
+            m, v = self.exp_avg.cpu(), self.exp_avg_sq.cpu()
+            for i, (off, shape) in enumerate(layout):
+                n = 1
+                for d in shape:
+                    n *= d
+                state[i] = {"step": torch.tensor(float(steps)), "exp_avg": m[off:off + n].view(shape).clone(),
+                            "exp_avg_sq": v[off:off + n].view(shape).clone()}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"]); self.step_count.copy_(sd["step"])
-        self.lr, self.betas, self.eps = sd["lr"], tuple(sd["betas"]), sd["eps"]
+        if "param_groups" not in sd:
+            # the flat layout written by earlier versions of this class
+            self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"]); self.step_count.copy_(sd["step"])
+            self.lr, self.betas, self.eps = sd["lr"], tuple(sd["betas"]), sd["eps"]
+            return
+        layout = self.reference_layout()
+        group = sd["param_groups"][0]
+        if len(group["params"]) != len(layout):
+            raise ValueError("optimizer checkpoint holds %d parameters, the model has %d" %
+                             (len(group["params"]), len(layout)))
+        self.lr, self.betas, self.eps = float(group["lr"]), tuple(float(b) for b in group["betas"]), float(group["eps"])
+        m, v = torch.zeros(self.numel), torch.zeros(self.numel)
+        steps = 0
+        for i, (off, shape) in enumerate(layout):
+            st = sd["state"].get(group["params"][i], sd["state"].get(i))
+            if st is None:
+                continue
+            n = st["exp_avg"].numel()
+            if tuple(st["exp_avg"].shape) != shape:
+                raise ValueError("optimizer state %d has shape %s, expected %s" % (i, tuple(st["exp_avg"].shape), shape))
+            m[off:off + n] = st["exp_avg"].detach().float().cpu().reshape(-1)
+            v[off:off + n] = st["exp_avg_sq"].detach().float().cpu().reshape(-1)
+            steps = max(steps, int(float(st["step"])))
+        self.exp_avg.copy_(m); self.exp_avg_sq.copy_(v); self.step_count.fill_(steps)
 
     # ---- helpers -------------------------------------------------------------------------
     def snapshot(self):

@@ -175,6 +175,10 @@ class PrioritizedTree:
         """{p_sum, p_min} as a 2-float device view of the state block (feeds the all-gather)."""
         return self.state.view(torch.float32)[5:7]
 
+    def leaves(self):
+        """The post-pow fp32 leaf values of slots [0, size): a device view, no copy."""
+        return self.sum[self.capacity:self.capacity + self.size]
+
     def len_tensor(self):
         return self.state.view(torch.int64)[0:1]
 

@@ -50,6 +50,9 @@ class TransitionRing:
         self.slot_seq = torch.full((self.size,), -1, dtype=torch.int64, device=d)
         self.next_link = torch.full((self.size,), -1, dtype=torch.int64, device=d)
         self.prev_link = torch.full((self.size,), -1, dtype=torch.int64, device=d)
+        # bumped whenever a device array is re-allocated (the descriptor changes): captured CUDA graphs hold the
+        # descriptor BY VALUE, so LearnerStep / ingest graphs compare generations and re-capture
+        self.generation = 0
         self._make_desc()
         # host-side planner state (mirrors what the collector knows about its streams)
         self.seq = 0
@@ -192,11 +195,16 @@ class TransitionRing:
         self.trunc_cursor[0] = old_pool
         self.aux_obs = aux
         self.aux_size = self.max_streams + new_pool
+        self.generation += 1
         self._make_desc()
 
     # ---------------------------------------------------------------------------
     def gather(self, idx, obs_out, next_obs_out, ret_out, gamma_out, nonterm_out, action_out):
         n = idx.numel()
+        row = self.frame_stack * self.obs_elems
+        if (obs_out.numel() < n * row or next_obs_out.numel() < n * row or ret_out.numel() < n or gamma_out.numel() < n
+                or nonterm_out.numel() < n or action_out.numel() < n):
+            raise ValueError("gather of %d rows into a batch with %d rows" % (n, obs_out.numel() // max(row, 1)))
         _lib.check(self._lib.pb_store_gather(
             self._ref, n, idx.data_ptr(), obs_out.data_ptr(), next_obs_out.data_ptr(), ret_out.data_ptr(),
             gamma_out.data_ptr(), nonterm_out.data_ptr(), action_out.data_ptr(), self._stream()),
@@ -252,6 +260,19 @@ class TransitionRing:
         self.stream_last[:] = -1
         self.trunc_cursor[0] = sd["trunc_cursor"]
         self.trunc_owner[:len(sd["trunc_owner"])] = sd["trunc_owner"]
+
+    def inflight_stream_rows(self):
+        """Stream ids whose aux row still backs the successor observation of a stored tail step (next_link = -(sid+2)
+        with sid < max_streams): after a reload these ids must not be handed to a new stream, or the first step of
+        that stream would overwrite the row (the reference truncates such trajectories at save,
+        prism/experience/timestep_buffer.py:274-297).  Synchronises; not on the hot path."""
+        n = len(self)
+        if n == 0:
+            return []
+        nl = self.next_link[:n]
+        rows = (-nl[nl <= -2] - 2)
+        rows = rows[rows < self.max_streams]
+        return sorted(set(int(r) for r in rows.cpu().tolist()))
 
 
 class IngestSlot:

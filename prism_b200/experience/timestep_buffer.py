@@ -189,6 +189,14 @@ class TimestepBuffer(object):
         B = int(batch_size)
         if self._batch is None:
             self._alloc_static_batch(B, ring)
+            self._own_batch = True
+        elif B > self._obs.shape[0]:
+            # more rows than the static batch holds: grow a batch this buffer allocated itself, refuse to write past one
+            # handed over by the agent (set_static_batch) -- the reference raises there as well (copy_ shape mismatch)
+            if not getattr(self, "_own_batch", False):
+                raise ValueError("sample(batch_size=%d) exceeds the static batch of %d rows" % (B, self._obs.shape[0]))
+            self._alloc_static_batch(B, ring)
+            self._own_batch = True
         if self._idx is None or self._idx.numel() != B:
             self._idx = torch.empty(B, dtype=torch.int64, device=self.device)
             self._weight = torch.ones(B, dtype=torch.float32, device=self.device)
@@ -240,6 +248,7 @@ class TimestepBuffer(object):
         self.set_static_batch(batch)
 
     def set_static_batch(self, batch):
+        self._own_batch = False
         self._batch = batch
         self._obs = batch["observation"]
         self._next_obs = batch["next"]["observation"]
@@ -307,11 +316,18 @@ class TimestepBuffer(object):
 
     def load(self, path):
         buffer_path = os.path.join(path, "experience_buffer")
-        sd = torch.load(os.path.join(buffer_path, "device_buffer.pt"), weights_only=False)
+        native = os.path.join(buffer_path, "device_buffer.pt")
+        if not os.path.exists(native) and os.path.exists(os.path.join(buffer_path, "timesteps.pkl")):
+            # a checkpoint directory written by the reference's own TimestepBuffer.save
+            return self.load_reference(path)
+        sd = torch.load(native, weights_only=False)
         if sd["ring"] is not None:
             ring = self._ring(tuple(sd["ring"]["obs_shape"]))
             ring.load_state_dict(sd["ring"])
-            self._free_streams = list(range(ring.max_streams - 1, -1, -1))
+            # tails of episodes that were in flight at save time keep their aux row: those stream ids stay reserved
+            reserved = set(ring.inflight_stream_rows())
+            self._free_streams = [s for s in range(ring.max_streams - 1, -1, -1) if s not in reserved]
+            self._stream_tail = {}
         if sd["tree"] is not None and self.buffer._sampler is not None:
             self.buffer._sampler.load_state_dict(sd["tree"])
 
@@ -348,17 +364,25 @@ class _IngestGraph:
             self.slot.d_block.copy_(self.slot.h_block, non_blocking=True)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        self._capture()
+        self.h2d_bytes = self.slot.h2d_bytes
+
+    def _capture(self):
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.slot.enqueue()
             if self.tree is not None:
                 self.tree.extend(self.n)
-        self.h2d_bytes = self.slot.h2d_bytes
+        self._generation = self.ring.generation
 
     def __call__(self, stream_ids, obs, action, reward, done, trunc, next_obs):
         self.buffer._flush()
         if self.done is not None:
             self.done.synchronize()          # the previous replay has consumed the pinned block
+        if self.ring.generation != self._generation:
+            # the flush above grew the aux pool: the captured scatter holds the old descriptor by value
+            torch.cuda.synchronize(self.ring.device)
+            self._capture()
         self.slot.fill(stream_ids, obs, action, reward, done, trunc, next_obs)
         self.buffer._mutations = getattr(self.buffer, "_mutations", 0) + 1
         self.graph.replay()

@@ -51,5 +51,8 @@ def build_agent(config, obs_shape, n_actions):
             for p in target.parameters():
                 p.requires_grad_(False)
 
-    return Agent(online, _acting_policy(config), action_selectors.GreedyActionSelector(),
-                 _optimizer(config, online, arena, graphed), target, graphed, config.max_grad_norm)
+    optimizer = _optimizer(config, online, arena, graphed)
+    if isinstance(optimizer, FlatAdam):
+        optimizer.layout_model = online        # checkpoints in torch.optim.Adam's format, reference parameter order
+    return Agent(online, _acting_policy(config), action_selectors.GreedyActionSelector(), optimizer, target, graphed,
+                 config.max_grad_norm)

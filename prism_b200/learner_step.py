@@ -335,7 +335,12 @@ class LearnerStep:
             main = torch.cuda.current_stream(self.device).cuda_stream
             parity = self.ingest.stage(*ingest, main_stream=main, u=u.numpy() if u_in_block else None)
         self._u_in_block = u_in_block
-        if self.use_cuda_graph and (self.graph is None or (draw, consume, u_in_block) != self._graph_key):
+        # the captured kernels hold the ring descriptor and beta BY VALUE: a grown aux pool (ring.generation) or a
+        # new beta (learner.py:105-107 writes _sampler._beta every iteration) re-captures
+        key = (draw, consume, u_in_block, self.ring.generation, float(self.tree._beta))
+        if self.use_cuda_graph and (self.graph is None or key != self._graph_key):
+            if self.graph is not None and key[3] != self._graph_key[3]:
+                torch.cuda.synchronize(self.device)
             self._capture(draw, consume)
             self._primed = False                            # the warm-up iterations sampled into the shadow batch
         if self.prefetch and (not self._primed or getattr(self.buffer, "_mutations", 0) != self._seen_mutations):
@@ -389,7 +394,8 @@ class LearnerStep:
         self.tree.sum.copy_(tree_snap[0]); self.tree.min.copy_(tree_snap[1]); self.tree.state.copy_(tree_snap[2])
         self.u.copy_(u_snap)
         torch.cuda.set_rng_state(rng, self.device)
-        self._graph_key = (draw, consume, getattr(self, "_u_in_block", False))
+        self._graph_key = (draw, consume, getattr(self, "_u_in_block", False), self.ring.generation,
+                           float(self.tree._beta))
         opt.zero_grad(set_to_none=True)
         self.graph = None                                   # release the previous graph's pool before capturing anew
         self.graph = torch.cuda.CUDAGraph()

@@ -703,3 +703,72 @@ def test_step_trace_marks_are_ordered_and_do_not_change_training():
     assert times[0] == 0 and times == sorted(times) and times[-1] < 5_000_000        # one small step: well under 5 ms
     for tail in ("tail:priorities_written", "tail:sampled", "tail:next_batch_ready"):
         assert rep["loss_ready"] <= rep[tail] <= rep["end"]
+
+
+def test_optimizer_checkpoint_is_a_torch_adam_state_dict():
+    """Agent.save writes ``optimizer.state_dict()`` (prism/agents/agent.py:231-236) and the reference reads it back into
+    torch.optim.Adam (:244-252).  After the same two updates, the product's checkpoint must load (strict) into a
+    torch.optim.Adam over the oracle model (reference parameter names / order) and equal the oracle's own Adam state;
+    and the oracle's checkpoint must load into the product."""
+    from oracle.agent_oracle import OracleAgent
+    fx = load_golden("agent_ids_iqn_ln_target")
+    cfg, agent = build_product_agent(fx)
+    import dataclasses
+    oracle = OracleAgent(dataclasses.replace(cfg, device="cpu"), tuple(fx["obs_shape"].tolist()), int(fx["n_actions"]))
+    sd = fixture_state_dict(fx)
+    oracle.model.load_state_dict(sd, strict=True)
+    oracle.target.load_state_dict({k: target_transform(v) for k, v in sd.items()})
+    w = torch.from_numpy(fx["per_weights"])
+    for _ in range(2):
+        taus = fixture_taus(fx)
+        oracle.inject_taus(taus)
+        oracle.update(fixture_batch(fx), w)
+        inject_taus(cfg, agent, taus)
+        agent.update(fixture_batch(fx, DEV), w.to(DEV))
+    torch.cuda.synchronize()
+    mine, ref = agent.optimizer.state_dict(), oracle.opt.state_dict()
+    assert set(mine["param_groups"][0].keys()) == set(ref["param_groups"][0].keys())
+    assert mine["param_groups"][0]["params"] == ref["param_groups"][0]["params"]
+    assert len(mine["state"]) == len(ref["state"])
+    for i, st in ref["state"].items():
+        assert float(mine["state"][i]["step"]) == float(st["step"]) == 2.0
+        assert mine["state"][i]["exp_avg"].shape == st["exp_avg"].shape
+        assert rel_err(mine["state"][i]["exp_avg"].numpy(), st["exp_avg"].numpy()) < 1e-4, i
+        assert rel_err(mine["state"][i]["exp_avg_sq"].numpy(), st["exp_avg_sq"].numpy()) < 2e-4, i
+    fresh = torch.optim.Adam(oracle.model.parameters(), lr=cfg.learning_rate)
+    fresh.load_state_dict(mine)                               # what the reference's Agent.load does
+    # and the other direction: a reference checkpoint into the product's arena
+    m_before = agent.optimizer.exp_avg.clone()
+    agent.optimizer.exp_avg.zero_(); agent.optimizer.step_count.zero_()
+    agent.optimizer.load_state_dict(ref)
+    assert int(agent.optimizer.step_count.item()) == 2
+    live = m_before != 0
+    assert rel_err(agent.optimizer.exp_avg[live].cpu().numpy(), m_before[live].cpu().numpy()) < 1e-4
+
+
+def test_static_batch_overflow_is_refused_and_ring_growth_recaptures():
+    """sample(batch_size > static batch rows) must not write out of bounds; a grown aux pool must not leave a
+    captured graph holding the freed descriptor."""
+    import prism_b200
+    cfg = prism_b200.minatar_dqn_per_config(device=DEV, experience_replay_capacity=4096, batch_size=16,
+                                            replay_max_streams=4, replay_staging_rows=64, use_cuda_graph=False)
+    buf = prism_b200.build_exp_buffer(cfg)
+    rng = np.random.default_rng(0)
+    n = 512
+    obs = (rng.random((n + 4, 10, 10, 6)) < 0.1).astype(np.float32)
+    sid = (np.arange(n) % 4).astype(np.int32)
+    buf.extend_batch(sid, obs[:n], rng.integers(0, 4, n).astype(np.int32), np.zeros(n, np.float32), np.zeros(n, bool),
+                     np.zeros(n, bool), obs[4:n + 4])
+    buf.sample(batch_size=16)
+    buf.sample(batch_size=32)                                  # own static batch: grows
+    assert buf._obs.shape[0] == 32
+    buf.set_static_batch(buf.get_static_batch())               # now "owned by the agent" (learner.py:96-97)
+    with pytest.raises(ValueError):
+        buf.sample(batch_size=64)
+    ring = buf.buffer._storage
+    gen = ring.generation
+    ring._grow_trunc_pool()
+    assert ring.generation == gen + 1
+    with pytest.raises(ValueError):
+        ring.gather(torch.zeros(64, dtype=torch.int64, device=DEV), buf._obs, buf._next_obs, buf._reward, buf._gamma,
+                    buf._nonterminal, buf._action)
