@@ -271,7 +271,7 @@ def kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src):
     rows["per_gather (store_gather_kernel)"] = (time_kernel(lambda: ring.gather(idx, buf._obs, buf._next_obs, buf._reward,
                                                                                  buf._gamma, buf._nonterminal, buf._action), 50, torch),
                                                 B * (2 * D + 2 * Dout + 43))
-    rows["per_update (upd_sparse x2 + tree_top)"] = (time_kernel(lambda: tree.update_priority(idx, prio, sorted=True), 50, torch),
+    rows["per_update (upd_chain_kernel, one launch)"] = (time_kernel(lambda: tree.update_priority(idx, prio, sorted=True), 50, torch),
                                                      B * (16 * L + 20))
     snap = opt.snapshot()
     rows["clip+adam (pack_grads + adam_clip)"] = (time_kernel(lambda: opt.step(refresh_table=False), 50, torch),
@@ -428,10 +428,36 @@ def per_microbench(device, torch, hbm_gbs):
     g.manual_seed(1)
     leaves = torch.empty(N, device=device).exponential_(1.0, generator=g).add_(1e-8).sqrt_()
     sec = time_kernel_graph(lambda: tree.build(leaves), 10, torch)
-    nbytes = 2 * (4 * N + 4 * 2 * N)                     # read leaves once per tree, write 2N nodes per tree
+    nbytes = 2 * (4 * N + 4 * 2 * N)                     # SURVEY 8d: read leaves once per tree, write 2N nodes per tree
     out["bulk_build_16M"] = {"ms": round(sec * 1e3, 4), "algorithmic_bytes": nbytes,
                              "achieved_gbs": round(nbytes / sec / 1e9, 1), "frac": round(nbytes / sec / 1e9 / hbm_gbs, 4)}
-    for B in (4096, 65536, 1 << 20):
+    nbytes_per = 4 * L + 24 + 16 * L + 20                  # 524 B / transition at L = 24
+    # K batches of 4096 in flight: ONE sampling launch draws K stratified batches against the current tree, ONE
+    # write-back call applies the K*4096 priorities (later batches win, like K successive reference calls)
+    B = 4096
+    for K in (1, 4, 16, 64):
+        n = K * B
+        u = torch.rand(n, dtype=torch.float64, device=device, generator=g)
+        idx = torch.empty(n, dtype=torch.int64, device=device)
+        w = torch.empty(n, dtype=torch.float32, device=device)
+        prio = torch.rand(n, device=device, generator=g)
+        srt = (K == 1)
+
+        def both():
+            tree.sample(B, u=u, idx_out=idx, weight_out=w, n_batches=K)
+            tree.update_priority(idx, prio, sorted=srt)
+        reps = 40 if K <= 16 else 10                        # back-to-back iterations inside one captured graph
+        sec = time_kernel_graph(both, reps, torch)
+        s_sec = time_kernel_graph(lambda: tree.sample(B, u=u, idx_out=idx, weight_out=w, n_batches=K), reps, torch)
+        u_sec = time_kernel_graph(lambda: tree.update_priority(idx, prio, sorted=srt), reps, torch)
+        nbytes = n * nbytes_per
+        key = "sample+update_16M_B4096" if K == 1 else "sample+update_16M_B4096_x%d_in_flight" % K
+        out[key] = {
+            "batches_in_flight": K, "us": round(sec * 1e6, 2), "transitions_per_s": round(n / sec, 1),
+            "algorithmic_bytes": nbytes, "achieved_gbs": round(nbytes / sec / 1e9, 2),
+            "frac": round(nbytes / sec / 1e9 / hbm_gbs, 5), "sample_us": round(s_sec * 1e6, 2),
+            "update_us": round(u_sec * 1e6, 2)}
+    for B in (65536, 1 << 20):                              # one large stratified (sorted) batch
         u = torch.rand(B, dtype=torch.float64, device=device, generator=g)
         idx = torch.empty(B, dtype=torch.int64, device=device)
         w = torch.empty(B, dtype=torch.float32, device=device)
@@ -440,11 +466,11 @@ def per_microbench(device, torch, hbm_gbs):
         def both():
             tree.sample(B, u=u, idx_out=idx, weight_out=w)
             tree.update_priority(idx, prio, sorted=True)
-        reps = 40 if B <= 65536 else 10                      # back-to-back iterations inside one captured graph
+        reps = 40 if B <= 65536 else 10
         sec = time_kernel_graph(both, reps, torch)
         s_sec = time_kernel_graph(lambda: tree.sample(B, u=u, idx_out=idx, weight_out=w), reps, torch)
         u_sec = time_kernel_graph(lambda: tree.update_priority(idx, prio, sorted=True), reps, torch)
-        nbytes = B * (4 * L + 24 + 16 * L + 20)          # 524 B / transition
+        nbytes = B * nbytes_per
         out["sample+update_16M_B%d" % B] = {
             "us": round(sec * 1e6, 2), "transitions_per_s": round(B / sec, 1), "algorithmic_bytes": nbytes,
             "achieved_gbs": round(nbytes / sec / 1e9, 2), "frac": round(nbytes / sec / 1e9 / hbm_gbs, 5),

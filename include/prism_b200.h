@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 1
+#define PB_ABI_VERSION 2
 
 enum {
     PB_OK = 0,
@@ -64,9 +64,16 @@ long long   pb_launch_count(void);
  * Prioritized replay: sum-tree + min-tree priority store.
  * Replaces torchrl.data.PrioritizedReplayBuffer's sampler as constructed at
  * prism/factory/exp_buffer_factory.py:22-28.
- * Layout: level-ordered (heap) fp32 arrays of 2*capacity floats, node i has
- * children 2i and 2i+1, leaves at [capacity, 2*capacity).  Every internal node
- * is fl32(left + right) / min(left, right): the reference's add order.
+ * Every node is fl32(left + right) / min(left, right) of a binary tree over the
+ * leaves: the reference's add order.  Layout ("compact"): a warp rebuilds the 5
+ * levels above a 128-byte line of 32 sibling nodes with shuffles, bit-identical to
+ * the nodes a pointer-walking tree would store, so only every 5th level is kept:
+ *     levels 0 .. TL               one level-ordered heap array of 2^(TL+1) floats
+ *                                  (node i: children 2i, 2i+1; TL <= 14)
+ *     levels TL+5, TL+10, .., L    one array of 2^level floats each, L = leaves
+ * and the min tree has no leaf array of its own (a leaf holds the same value in both
+ * trees; slots >= len read as +inf on the min side).  pb_tree_layout() gives the
+ * sizes; pb_tree_export() materialises the full 2*capacity arrays.
  * ------------------------------------------------------------------------- */
 
 /* 64-byte device-resident state block of one shard */
@@ -84,9 +91,10 @@ typedef struct pb_per_state {
 } pb_per_state;
 
 typedef struct pb_tree {
-    float        *sum;       /* 2*capacity floats */
-    float        *min;       /* 2*capacity floats */
-    int          *owner;     /* capacity ints, all -1 between calls (dedup scratch) */
+    float        *sum;       /* compact sum store, pb_tree_layout() floats (leaves last) */
+    float        *min;       /* compact min store, pb_tree_layout() floats (no leaf level) */
+    int          *owner;     /* capacity ints, all -1 between calls (dedup scratch of unsorted updates) */
+    int          *counters;  /* pb_tree_layout() ints, all 0 between calls (arrival counters of the one-launch update) */
     pb_per_state *state;
     long long     capacity;  /* power of two */
     long long     size;      /* addressable slots N <= capacity */
@@ -97,8 +105,17 @@ typedef struct pb_tree {
     int           default_priority_fp64;     /* (max_p+eps)^alpha in double, then cast */
 } pb_tree;
 
-/* zero the trees (sum 0, min +inf), owner = -1, state = {len 0, max_priority 1} */
+/* HOST: sizes of the compact stores for a power-of-two capacity (any output may be NULL): floats of the sum store,
+ * floats of the min store, ints of the arrival counters, float offset of leaf 0 inside the sum store, and TL. */
+int pb_tree_layout(long long capacity, long long *sum_floats, long long *min_floats, long long *counter_ints,
+                   long long *leaf_offset, int *top_level);
+
+/* zero the trees (sum 0, min +inf), owner = -1, counters = 0, state = {len 0, max_priority 1} */
 int pb_tree_init(const pb_tree *t, void *stream);
+
+/* the full level-ordered arrays a pointer-walking tree would hold (2*capacity floats each, node i has children 2i and
+ * 2i+1, leaves at [capacity, 2*capacity); either may be NULL): parity tests and checkpoints, not the hot path */
+int pb_tree_export(const pb_tree *t, float *sum_heap, float *min_heap, void *stream);
 
 /* bulk load n post-pow fp32 leaves (rest padded with the identity) and rebuild
  * every internal node pairwise; sets len=min(n,size), seq=n.  Streaming kernel. */
@@ -110,7 +127,8 @@ int pb_tree_stats(const pb_tree *t, void *stream);
 
 /* raw leaf write + ancestor recompute (both trees).  Duplicates: last wins,
  * like the sequential reference loop.  sorted!=0 promises idx is non-decreasing
- * (true for stratified samples) and skips the owner-scratch pass. */
+ * (true for stratified samples; out-of-range entries such as the -1 padding rows of
+ * a sharded sample may only form a suffix) and takes the one-launch path. */
 int pb_tree_set_leaves(const pb_tree *t, long long n, const long long *idx,
                        const float *leaves, int sorted, void *stream);
 
@@ -139,6 +157,14 @@ int pb_tree_scan(const pb_tree *t, long long n, const float *mass, long long *id
  * mass_out optional. */
 int pb_tree_sample(const pb_tree *t, long long n, const double *u, int mode, float beta,
                    long long *idx_out, float *weight_out, float *mass_out, void *stream);
+
+/* n_batches independent batches of `batch` samples in ONE launch, all against the current tree state ("batches in
+ * flight": a learner that samples several batches before their priorities come back).  Sample k = b*batch + j is
+ * stratum j of batch b (mode 1: mass = (j + u_k)/batch * p_sum); outputs are [n_batches][batch].  The matching
+ * write-back is pb_tree_update_priority on the concatenation with sorted = 0 (later batches win, like n_batches
+ * successive reference calls). */
+int pb_tree_sample_batches(const pb_tree *t, long long n_batches, long long batch, const double *u, int mode,
+                           float beta, long long *idx_out, float *weight_out, float *mass_out, void *stream);
 
 /* Sharded global stratified sampling (new design).  Every rank holds
  * one shard; all_state is the all-gathered array of the G shards' 64-byte state

@@ -26,7 +26,8 @@ class pb_per_state(C.Structure):
 
 class pb_tree(C.Structure):
     _fields_ = [
-        ("sum", C.c_void_p), ("min", C.c_void_p), ("owner", C.c_void_p), ("state", C.c_void_p),
+        ("sum", C.c_void_p), ("min", C.c_void_p), ("owner", C.c_void_p), ("counters", C.c_void_p),
+        ("state", C.c_void_p),
         ("capacity", C.c_longlong), ("size", C.c_longlong), ("alpha", C.c_float), ("eps_f32", C.c_float),
         ("eps_f64", C.c_double), ("weight_eps_in_denominator", C.c_int), ("default_priority_fp64", C.c_int),
     ]
@@ -79,7 +80,11 @@ SIGNATURES = {
     "pb_stream_wait_event": [_P, _P],
     "pb_copy_h2d_async": [_P, _P, _LL, _P],
     "pb_copy_d2h_async": [_P, _P, _LL, _P],
+    "pb_tree_layout": [_LL, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+                       C.POINTER(C.c_longlong), C.POINTER(C.c_int)],
     "pb_tree_init": [_TREE, _P],
+    "pb_tree_export": [_TREE, _P, _P, _P],
+    "pb_tree_sample_batches": [_TREE, _LL, _LL, _P, _I, _F, _P, _P, _P, _P],
     "pb_tree_build": [_TREE, _P, _LL, _P],
     "pb_tree_stats": [_TREE, _P],
     "pb_tree_set_leaves": [_TREE, _LL, _P, _P, _I, _P],
@@ -147,6 +152,7 @@ SIGNATURES = {
 _RESTYPES = {"pb_error_string": C.c_char_p, "pb_launch_count": C.c_longlong, "pb_peer_slice": C.c_longlong}
 
 PB_E_POOL = -4
+ABI_VERSION = 2
 
 
 def lib_path():
@@ -166,7 +172,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError = ABI drift, fail loudly
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.pb_abi_version() != 1:
+    if lib.pb_abi_version() != ABI_VERSION:
         raise PbError("libprism_b200.so ABI version mismatch")
     _LIB = lib
     return lib

@@ -5,20 +5,27 @@
 // prism/experience/timestep_buffer.py:33,37,54; prism/learner.py:100,120).
 //
 // Design (B200-first, not a port of a pointer-walking CPU tree):
-//  * level-ordered fp32 heap array; node = fl32(left+right) -> the reference add order,
-//    so sampled indices are bit-exact whatever order updates arrive in.
-//  * one primitive everywhere: a warp loads one aligned 128-byte line (32 sibling nodes)
-//    and rebuilds the 5 levels above it with xor-shuffles.  Those rebuilt values are
-//    bit-identical to the stored internal nodes, so
-//      - sampling descends 5 levels per dependent memory round trip (5 trips for 2^24
-//        leaves instead of 24),
-//      - a batched priority update needs 2 sparse phases + 1 single-CTA top phase (the
-//        top <=14 levels live in shared memory) instead of 24 level-synchronous steps,
-//      - the bulk build streams leaves once at HBM speed.
-//  * duplicates in an update batch: last occurrence wins (sequential reference loop),
-//    resolved deterministically (owner scratch + atomicMax, or adjacency when sorted).
-//  * no host sync anywhere: len / cursor / max_priority / p_sum / p_min live in a 64-byte
-//    device state block, so the whole sample->update loop is CUDA-graph capturable.
+//  * every node is fl32(left + right) / min(left, right) of a binary tree over the leaves -- the reference add
+//    order, so sampled indices are bit-exact whatever order updates arrive in.
+//  * one primitive everywhere: 32 sibling nodes (one aligned 128-byte line) are reduced over 5 levels in registers
+//    and shuffles.  The rebuilt intermediate values are bit-identical to the nodes a pointer-walking tree would
+//    store, so they are NOT stored: the tree keeps only every 5th level below its top ("compact" layout)
+//        levels 0 .. TL          one level-ordered heap array (TL <= 14: <= 128 KB, L1/L2 resident)
+//        levels TL+5, TL+10, .., L   one array per level; L = leaves
+//    and the min tree shares the leaf array of the sum tree (a leaf is written with the same value in both;
+//    slots that were never written -- index >= len -- read as +inf on the min side).
+//    16M leaves: 64 MiB + 2 x 2.1 MiB instead of 2 x 128 MiB, i.e. the whole store fits the 126 MB L2.
+//      - sampling descends 5 levels per dependent 128-byte load, 8 lanes per sample (4 samples per warp);
+//      - a sorted priority update is ONE launch: the leader of every touched line applies its leaves, reduces the
+//        line and climbs; lines of the next stored level are finished by whichever child arrives last (arrival
+//        counters, no spinning), and the last CTA (ticket) rebuilds the top heap and the state block;
+//      - large / unsorted batches scatter their leaves and rebuild every line with one streaming pass over the leaf
+//        array (4.3 B per leaf of traffic, independent of the batch size);
+//      - the bulk build is that same streaming pass.
+//  * duplicates in an update batch: last occurrence wins (sequential reference loop), resolved deterministically
+//    (adjacency when sorted, owner scratch + atomicMax otherwise).
+//  * no host sync anywhere: len / cursor / max_priority / p_sum / p_min live in a 64-byte device state block, so
+//    the whole sample->update loop is CUDA-graph capturable.
 #include "common.cuh"
 #include <math.h>
 
@@ -26,24 +33,42 @@ namespace {
 
 using namespace pb;
 
+constexpr int TOP_MAX = 14;        // the top heap holds levels [0, TL], TL <= 14
+constexpr int MAX_DEEP = 8;        // stored levels below the heap (capacity <= 2^30 -> at most 4)
+
 struct TreeView {
     float *sum, *min;
-    int *owner;
+    int *owner, *cnt;
     pb_per_state *st;
     long long cap, size;
-    int L;
+    int L, TL, P;                  // P = (L - TL) / 5 deep levels: L, L-5, .., TL+5
+    long long off[MAX_DEEP];       // off[m]: float offset of level TL + 5m in the sum / min store (m >= 1)
+    long long coff[MAX_DEEP];      // coff[m]: int offset of the arrival counters of the lines at level TL + 5m (1 <= m < P)
     float alpha, eps32;
     double eps64;
     int weps, dp64;
 };
 
 enum { MODE_RAW = 0, MODE_PRIORITY = 1, MODE_EXTEND = 2 };
-constexpr int TOP_MAX = 14;       // top kernel holds depths [0, T], T <= 14 -> 2^(T+1)*4 B = 128 KB smem
-constexpr int STAGE_TILE = 2048;  // bulk build: source nodes per CTA (11 levels)
-constexpr long long THREAD_MODE_MIN = 16384;  // samples per call from which one-thread-per-sample wins
+constexpr float INF = __builtin_huge_valf();
 
 __device__ __forceinline__ float op_sum(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float op_min(float a, float b) { return fminf(a, b); }
+
+// level s of the sum tree (node i of that level at [i])
+__device__ __forceinline__ float *sum_level(const TreeView &t, int s)
+{
+    return s <= t.TL ? t.sum + (1LL << s) : t.sum + t.off[(s - t.TL) / 5];
+}
+// level s < L of the min tree (the leaf level is shared with the sum tree, see min_of_leaf)
+__device__ __forceinline__ float *min_level(const TreeView &t, int s)
+{
+    return s <= t.TL ? t.min + (1LL << s) : t.min + t.off[(s - t.TL) / 5];
+}
+__device__ __forceinline__ float *leaf_ptr(const TreeView &t) { return sum_level(t, t.L); }
+__device__ __forceinline__ float min_of_leaf(float v, long long i, long long len) { return i < len ? v : INF; }
+
+__device__ __forceinline__ float ldcg(const float *p) { return __ldcg(p); }
 
 __device__ __forceinline__ float pow_leaf(float p, const TreeView &t)
 {
@@ -65,38 +90,72 @@ __device__ __forceinline__ float default_priority(const TreeView &t)
     return pow_leaf(mp, t);
 }
 
-__device__ __forceinline__ long long entry_index(const TreeView &t, const long long *idx, long long j,
-                                                 int mode)
+__device__ __forceinline__ long long entry_index(const TreeView &t, const long long *idx, long long j, int mode,
+                                                 long long seq0)
 {
-    if (mode == MODE_EXTEND) return (t.st->seq + j) % t.size;
+    if (mode == MODE_EXTEND) return (seq0 + j) % t.size;
     return idx[j];
 }
 
-__device__ __forceinline__ float entry_leaf(const TreeView &t, const float *val, long long j, int mode,
-                                            float defp)
+__device__ __forceinline__ float entry_leaf(const TreeView &t, const float *val, long long j, int mode, float defp)
 {
     if (mode == MODE_RAW) return val[j];
     if (mode == MODE_PRIORITY) return pow_leaf(fabsf(val[j]), t);   // learner.py:120 passes |td|; idempotent
     return defp;
 }
 
-// ---------------------------------------------------------------------------------
-// init
-// ---------------------------------------------------------------------------------
-__global__ void tree_init_kernel(TreeView t)
+__device__ __forceinline__ long long len_after(const TreeView &t, int mode, long long n_new, long long set_len)
 {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long stride = (long long)gridDim.x * blockDim.x;
-    const float inf = __int_as_float(0x7f800000);
-    for (long long k = i; k < 2 * t.cap; k += stride) { t.sum[k] = 0.0f; t.min[k] = inf; }
-    if (t.owner) for (long long k = i; k < t.cap; k += stride) t.owner[k] = -1;
-    if (i == 0) {
-        pb_per_state s;
-        s.len = 0; s.seq = 0; s.max_priority = 1.0f; s.p_sum = 0.0f; s.p_min = inf; s.status = 0;
-        s.batch_max = 0.0f; s.owned_lo = 0; s.owned_n = 0;
-        for (int k = 0; k < 5; ++k) s.pad[k] = 0;
-        *t.st = s;
+    long long len = t.st->len;
+    if (mode == MODE_EXTEND) len = len + n_new < t.size ? len + n_new : t.size;
+    else if (set_len >= 0) len = set_len < t.size ? set_len : t.size;
+    return len;
+}
+
+// reduce one line: every lane holds one of 32 sibling nodes; returns the 5-level pairwise total in every lane
+__device__ __forceinline__ void line_reduce(float &vs, float &vm)
+{
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        vs = op_sum(vs, __shfl_xor_sync(FULL, vs, 1 << s));
+        vm = op_min(vm, __shfl_xor_sync(FULL, vm, 1 << s));
     }
+}
+
+// ---------------------------------------------------------------------------------
+// value of ANY node (level d, index i), stored or not: an unstored level is rebuilt pairwise from the next
+// stored level below it (<= 16 nodes).
+// ---------------------------------------------------------------------------------
+template <bool IS_MIN>
+__device__ float node_value(const TreeView &t, int d, long long i, long long len)
+{
+    const float ident = IS_MIN ? INF : 0.0f;
+    const int r = d <= t.TL ? 0 : (t.L - d) % 5;     // levels to the next stored level below
+    const int s = d + r;
+    const long long base = i << r;
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (k < (1 << r)) {
+            if (s == t.L) {
+                float x = leaf_ptr(t)[base + k];
+                v[k] = IS_MIN ? min_of_leaf(x, base + k, len) : x;
+            } else {
+                v[k] = IS_MIN ? min_level(t, s)[base + k] : sum_level(t, s)[base + k];
+            }
+        } else {
+            v[k] = ident;
+        }
+    }
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1) {
+        if (w < (1 << r)) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < w) v[k] = IS_MIN ? op_min(v[2 * k], v[2 * k + 1]) : op_sum(v[2 * k], v[2 * k + 1]);
+        }
+    }
+    return v[0];
 }
 
 // ---------------------------------------------------------------------------------
@@ -105,13 +164,13 @@ __global__ void tree_init_kernel(TreeView t)
 template <bool IS_MIN>
 __device__ float tree_query_prefix(const TreeView &t, long long len)
 {
-    const float *tree = IS_MIN ? t.min : t.sum;
-    const float ident = IS_MIN ? __int_as_float(0x7f800000) : 0.0f;
-    if (len >= t.size) return tree[1];
+    const float ident = IS_MIN ? INF : 0.0f;
+    if (len >= t.size) return IS_MIN ? (t.L == 0 ? min_of_leaf(leaf_ptr(t)[0], 0, len) : t.min[1]) : t.sum[1];
     if (len <= 0) return ident;
-    int k = lane_id();
+    const int k = lane_id();
     float v = ident;
-    if (k < t.L && ((len >> k) & 1)) v = tree[((t.cap + len) >> k) - 1];
+    // bit k of len set: the walk takes node (len >> k) - 1 of level L - k (a node fully inside [0, len))
+    if (k < t.L && ((len >> k) & 1)) v = node_value<IS_MIN>(t, t.L - k, (len >> k) - 1, len);
     float ret = ident;
     for (int b = 0; b < t.L; ++b) {
         float vb = __shfl_sync(FULL, v, b);
@@ -120,139 +179,19 @@ __device__ float tree_query_prefix(const TreeView &t, long long len)
     return ret;
 }
 
-__global__ void tree_stats_kernel(TreeView t)
+// one warp: advance len / seq, merge max_priority, refresh p_sum / p_min
+__device__ void finalize_state(const TreeView &t, int mode, long long n_new, long long set_len)
 {
-    long long len = t.st->len;
-    float ps = tree_query_prefix<false>(t, len);
-    float pm = tree_query_prefix<true>(t, len);
-    if (threadIdx.x == 0) { t.st->p_sum = ps; t.st->p_min = pm; }
-}
-
-// ---------------------------------------------------------------------------------
-// bulk build, stage 1: each CTA reduces 2048 source nodes by 11 levels (both trees via
-// blockIdx.y).  Streaming: one 2x float4 load per thread, coalesced stores per level.
-// ---------------------------------------------------------------------------------
-template <bool FROM_LEAVES>
-__global__ void __launch_bounds__(256) tree_reduce11_kernel(TreeView t, int d_src, const float *leaves,
-                                                            long long n_leaves)
-{
-    const bool is_min = blockIdx.y != 0;
-    float *tree = is_min ? t.min : t.sum;
-    const float ident = is_min ? __int_as_float(0x7f800000) : 0.0f;
-    const long long n_src = 1LL << d_src;
-    const long long base = (long long)blockIdx.x * STAGE_TILE + (long long)threadIdx.x * 8;
-    float a[8];
-    if (FROM_LEAVES) {
-        if (base + 8 <= n_leaves) {
-            float4 x = *reinterpret_cast<const float4 *>(leaves + base);
-            float4 y = *reinterpret_cast<const float4 *>(leaves + base + 4);
-            a[0] = x.x; a[1] = x.y; a[2] = x.z; a[3] = x.w; a[4] = y.x; a[5] = y.y; a[6] = y.z; a[7] = y.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = (base + i < n_leaves) ? leaves[base + i] : ident;
-        }
-        float4 *dst = reinterpret_cast<float4 *>(tree + n_src + base);
-        dst[0] = make_float4(a[0], a[1], a[2], a[3]);
-        dst[1] = make_float4(a[4], a[5], a[6], a[7]);
-    } else {
-        const float4 *src = reinterpret_cast<const float4 *>(tree + n_src + base);
-        float4 x = src[0], y = src[1];
-        a[0] = x.x; a[1] = x.y; a[2] = x.z; a[3] = x.w; a[4] = y.x; a[5] = y.y; a[6] = y.z; a[7] = y.w;
-    }
-    auto op = [&](float l, float r) { return is_min ? op_min(l, r) : op_sum(l, r); };
-    float b0 = op(a[0], a[1]), b1 = op(a[2], a[3]), b2 = op(a[4], a[5]), b3 = op(a[6], a[7]);
-    *reinterpret_cast<float4 *>(tree + (n_src >> 1) + (base >> 1)) = make_float4(b0, b1, b2, b3);
-    float c0 = op(b0, b1), c1 = op(b2, b3);
-    *reinterpret_cast<float2 *>(tree + (n_src >> 2) + (base >> 2)) = make_float2(c0, c1);
-    float d = op(c0, c1);
-    const long long e = base >> 3;  // element index at depth d_src-3
-    tree[(n_src >> 3) + e] = d;
-    const int lane = lane_id();
-#pragma unroll
-    for (int s = 0; s < 5; ++s) {
-        d = op(d, __shfl_xor_sync(FULL, d, 1 << s));
-        if ((lane & ((2 << s) - 1)) == 0) tree[(n_src >> (4 + s)) + (e >> (s + 1))] = d;
-    }
-    __shared__ float warp_part[8];
-    if (lane == 0) warp_part[threadIdx.x >> 5] = d;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        float x = lane < 8 ? warp_part[lane] : ident;
-        const long long e8 = (long long)blockIdx.x * 8 + lane;  // element index at depth d_src-8
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            x = op(x, __shfl_xor_sync(FULL, x, 1 << s));
-            if (lane < 8 && (lane & ((2 << s) - 1)) == 0) tree[(n_src >> (9 + s)) + (e8 >> (s + 1))] = x;
-        }
-    }
-}
-
-// small trees (L <= 14): copy leaves (identity padded) into both leaf regions
-__global__ void tree_fill_leaves_kernel(TreeView t, const float *leaves, long long n_leaves)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= t.cap) return;
-    bool in = i < n_leaves;
-    float v = in ? leaves[i] : 0.0f;
-    t.sum[t.cap + i] = in ? v : 0.0f;
-    t.min[t.cap + i] = in ? v : __int_as_float(0x7f800000);
-}
-
-// ---------------------------------------------------------------------------------
-// top phase: one CTA per tree holds depths [0, T] in shared memory (heap layout),
-// reduces them pairwise, writes nodes [1, 2^T) back, and the last CTA to finish
-// finalises the state block (len/seq advance, max_priority merge, p_sum/p_min).
-// ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) tree_top_kernel(TreeView t, int T, int mode, long long n_new,
-                                                        long long set_len)
-{
-    extern __shared__ float sm[];
-    const bool is_min = blockIdx.x != 0;
-    float *tree = is_min ? t.min : t.sum;
-    const int n_top = 1 << T;
-    if (T >= 2) {
-        const float4 *src = reinterpret_cast<const float4 *>(tree + n_top);
-        float4 *dst = reinterpret_cast<float4 *>(sm + n_top);
-        for (int i = threadIdx.x; i < (n_top >> 2); i += blockDim.x) dst[i] = src[i];
-    } else {
-        for (int i = threadIdx.x; i < n_top; i += blockDim.x) sm[n_top + i] = tree[n_top + i];
-    }
-    __syncthreads();
-    for (int d = T - 1; d >= 0; --d) {
-        const int n_d = 1 << d;
-        for (int i = threadIdx.x; i < n_d; i += blockDim.x) {
-            float l = sm[2 * (n_d + i)], r = sm[2 * (n_d + i) + 1];
-            sm[n_d + i] = is_min ? op_min(l, r) : op_sum(l, r);
-        }
-        __syncthreads();
-    }
-    for (int i = threadIdx.x + 1; i < n_top; i += blockDim.x) tree[i] = sm[i];
-    __threadfence();
-    __syncthreads();
-    __shared__ int is_last;
-    if (threadIdx.x == 0) {
-        int ticket = atomicAdd(&t.st->pad[0], 1);
-        is_last = (ticket == (int)gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last || threadIdx.x >= 32) return;
-    __threadfence();
-    // finalise (one warp of the last CTA)
-    long long len = t.st->len;
-    if (mode == MODE_EXTEND) {
-        len = len + n_new < t.size ? len + n_new : t.size;
-    } else if (set_len >= 0) {
-        len = set_len < t.size ? set_len : t.size;
-    }
-    float ps = tree_query_prefix<false>(t, len);
-    float pm = tree_query_prefix<true>(t, len);
-    if (threadIdx.x == 0) {
+    const long long len = len_after(t, mode, n_new, set_len);
+    const float ps = tree_query_prefix<false>(t, len);
+    const float pm = tree_query_prefix<true>(t, len);
+    if (lane_id() == 0) {
         pb_per_state *s = t.st;
         if (mode == MODE_EXTEND) s->seq += n_new;
         else if (set_len >= 0) s->seq = set_len;
         s->len = len;
         if (mode == MODE_PRIORITY) {
-            float bm = s->batch_max;
+            const float bm = s->batch_max;
             if (bm > s->max_priority) s->max_priority = bm;
         }
         s->batch_max = 0.0f;
@@ -262,15 +201,210 @@ __global__ void __launch_bounds__(1024) tree_top_kernel(TreeView t, int T, int m
 }
 
 // ---------------------------------------------------------------------------------
-// sparse update, general (unsorted) path: A) mark owner = last occurrence, B) winner
-// writes the leaf and clears the scratch.
+// top phase: rebuild heap levels TL-1 .. 0 of BOTH trees from level TL.  Called by every thread of ONE CTA
+// (blockDim.x threads, a multiple of 64; the first half works on the sum tree, the second on the min tree).
+// sm: 2 x 2048 floats.  Levels > 10 are reduced in registers per level-10 subtree, levels <= 10 in shared memory.
+// ---------------------------------------------------------------------------------
+constexpr int TOP_SM_LEVEL = 10;
+constexpr int TOP_SM_FLOATS = 2 << TOP_SM_LEVEL;    // one smem heap of levels 0..10
+
+__device__ void top_rebuild(const TreeView &t, float *sm, long long len)
+{
+    const int half = blockDim.x >> 1;
+    const bool is_min = threadIdx.x >= half;
+    const int tid = is_min ? threadIdx.x - half : threadIdx.x;
+    float *heap = is_min ? t.min : t.sum;
+    float *s = sm + (is_min ? TOP_SM_FLOATS : 0);
+    const int TL = t.TL;
+    const bool shared_leaves = is_min && TL == t.L;             // tiny trees: level TL is the shared leaf level
+    const float *src = shared_leaves ? t.sum + (1 << TL) : heap + (1 << TL);
+    const int S = TL < TOP_SM_LEVEL ? TL : TOP_SM_LEVEL;        // level held at the bottom of the smem heap
+    const int r = TL - S;                                       // register levels (0..4)
+    const int n_sub = 1 << S;
+    for (int q = tid; q < n_sub; q += half) {
+        float v[16];
+        const long long base = (long long)q << r;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k < (1 << r)) {
+                float x = ldcg(src + base + k);
+                v[k] = shared_leaves ? min_of_leaf(x, base + k, len) : x;
+            } else {
+                v[k] = 0.0f;
+            }
+        }
+#pragma unroll
+        for (int lv = 1; lv <= 4; ++lv) {
+            if (lv <= r) {
+                const int w = 1 << (r - lv);                    // nodes of this subtree at level TL - lv
+                float *dst = heap + (1 << (TL - lv)) + ((long long)q << (r - lv));
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k < w) {
+                        v[k] = is_min ? op_min(v[2 * k], v[2 * k + 1]) : op_sum(v[2 * k], v[2 * k + 1]);
+                        dst[k] = v[k];
+                    }
+            }
+        }
+        s[n_sub + q] = v[0];
+    }
+    __syncthreads();
+    for (int d = S - 1; d >= 0; --d) {
+        const int n_d = 1 << d;
+        for (int i = tid; i < n_d; i += half) {
+            const float l = s[2 * (n_d + i)], rr = s[2 * (n_d + i) + 1];
+            s[n_d + i] = is_min ? op_min(l, rr) : op_sum(l, rr);
+        }
+        __syncthreads();
+    }
+    // heap levels S-1 .. 0 (level S itself was written by the register stage, or is level TL)
+    for (int i = tid + 1; i < n_sub; i += half) heap[i] = s[i];
+}
+
+// last-CTA ticket: returns true in every thread of the CTA that arrives last.  pad[0] is reset by finalize_state.
+__device__ bool last_cta(const TreeView &t)
+{
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int ticket = atomicAdd(&t.st->pad[0], 1);
+        is_last = (ticket == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last != 0;
+}
+
+__device__ void top_and_finalize(const TreeView &t, float *sm, int mode, long long n_new, long long set_len)
+{
+    const long long len = len_after(t, mode, n_new, set_len);
+    top_rebuild(t, sm, len);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x < 32) finalize_state(t, mode, n_new, set_len);
+}
+
+// ---------------------------------------------------------------------------------
+// init
+// ---------------------------------------------------------------------------------
+__global__ void tree_init_kernel(TreeView t, long long n_sum, long long n_min, long long n_cnt)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = i; k < n_sum; k += stride) t.sum[k] = 0.0f;
+    for (long long k = i; k < n_min; k += stride) t.min[k] = INF;
+    for (long long k = i; k < n_cnt; k += stride) t.cnt[k] = 0;
+    if (t.owner) for (long long k = i; k < t.cap; k += stride) t.owner[k] = -1;
+    if (i == 0) {
+        pb_per_state s;
+        s.len = 0; s.seq = 0; s.max_priority = 1.0f; s.p_sum = 0.0f; s.p_min = INF; s.status = 0;
+        s.batch_max = 0.0f; s.owned_lo = 0; s.owned_n = 0;
+        for (int k = 0; k < 5; ++k) s.pad[k] = 0;
+        *t.st = s;
+    }
+}
+
+__global__ void tree_stats_kernel(TreeView t)
+{
+    const long long len = t.st->len;
+    const float ps = tree_query_prefix<false>(t, len);
+    const float pm = tree_query_prefix<true>(t, len);
+    if (threadIdx.x == 0) { t.st->p_sum = ps; t.st->p_min = pm; }
+}
+
+// ---------------------------------------------------------------------------------
+// streaming rebuild: every line of level s is reduced to its node of level s-5 and, when that level is stored
+// too, on to level s-10.  Tile = 1024 source nodes per CTA iteration (256 threads x float4, 8 lanes per line);
+// persistent grid.  s == L reads the shared leaf array (optionally first loading it from `ext`, the bulk build).
+// FUSE_TOP: the last CTA (ticket) rebuilds the top heap and the state block.
+// ---------------------------------------------------------------------------------
+constexpr int RB_THREADS = 256;
+constexpr int RB_TILE = RB_THREADS * 4;
+
+__global__ void __launch_bounds__(RB_THREADS) tree_rebuild_kernel(TreeView t, int s, int two_levels, const float *ext,
+                                                                  long long n_ext, int fuse_top, int mode,
+                                                                  long long n_new, long long set_len)
+{
+    __shared__ float sm_top[2 * TOP_SM_FLOATS];
+    __shared__ float part_s[32], part_m[32];
+    const long long len = len_after(t, mode, n_new, set_len);
+    const bool leaves = (s == t.L);
+    const float *src_s = sum_level(t, s);
+    const float *src_m = leaves ? src_s : min_level(t, s);
+    float *dst1_s = sum_level(t, s - 5), *dst1_m = min_level(t, s - 5);
+    const long long n_tiles = (1LL << s) / RB_TILE;
+    const int lane = lane_id(), grp = threadIdx.x >> 3;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long base = tile * RB_TILE + (long long)threadIdx.x * 4;
+        float4 a, m;
+        if (ext) {
+            if (base + 4 <= n_ext) a = *reinterpret_cast<const float4 *>(ext + base);
+            else {
+                a.x = base + 0 < n_ext ? ext[base + 0] : 0.0f; a.y = base + 1 < n_ext ? ext[base + 1] : 0.0f;
+                a.z = base + 2 < n_ext ? ext[base + 2] : 0.0f; a.w = base + 3 < n_ext ? ext[base + 3] : 0.0f;
+            }
+            *reinterpret_cast<float4 *>(sum_level(t, s) + base) = a;
+        } else {
+            a = __ldcs(reinterpret_cast<const float4 *>(src_s + base));
+        }
+        if (leaves) {
+            m.x = min_of_leaf(a.x, base + 0, len); m.y = min_of_leaf(a.y, base + 1, len);
+            m.z = min_of_leaf(a.z, base + 2, len); m.w = min_of_leaf(a.w, base + 3, len);
+        } else {
+            m = __ldcs(reinterpret_cast<const float4 *>(src_m + base));
+        }
+        float vs = op_sum(op_sum(a.x, a.y), op_sum(a.z, a.w));
+        float vm = op_min(op_min(m.x, m.y), op_min(m.z, m.w));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            vs = op_sum(vs, __shfl_xor_sync(FULL, vs, 1 << k));
+            vm = op_min(vm, __shfl_xor_sync(FULL, vm, 1 << k));
+        }
+        if ((threadIdx.x & 7) == 0) { part_s[grp] = vs; part_m[grp] = vm; }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float ps = part_s[lane], pm = part_m[lane];
+            dst1_s[tile * 32 + lane] = ps;                       // 32 nodes of level s-5: one coalesced line
+            dst1_m[tile * 32 + lane] = pm;
+            if (two_levels) {
+                line_reduce(ps, pm);
+                if (lane == 0) { sum_level(t, s - 10)[tile] = ps; min_level(t, s - 10)[tile] = pm; }
+            }
+        }
+        __syncthreads();
+    }
+    if (!fuse_top) return;
+    if (!last_cta(t)) return;
+    top_and_finalize(t, sm_top, mode, n_new, set_len);
+}
+
+// trees without deep levels (L <= 14): copy the leaves (identity padded) into the heap's leaf level
+__global__ void tree_fill_leaves_kernel(TreeView t, const float *leaves, long long n_leaves)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= t.cap) return;
+    leaf_ptr(t)[i] = i < n_leaves ? leaves[i] : 0.0f;
+}
+
+// standalone top phase (one CTA)
+__global__ void __launch_bounds__(512) tree_top_kernel(TreeView t, int mode, long long n_new, long long set_len)
+{
+    __shared__ float sm_top[2 * TOP_SM_FLOATS];
+    top_and_finalize(t, sm_top, mode, n_new, set_len);
+}
+
+// ---------------------------------------------------------------------------------
+// leaf scatter, general (unsorted) path: A) mark owner = last occurrence, B) the winner writes the leaf and clears
+// the scratch.  Dense path, sorted input: the last entry of every run of equal indices writes the leaf.
 // ---------------------------------------------------------------------------------
 __global__ void upd_mark_kernel(TreeView t, long long n, const long long *idx, const float *val, int mode)
 {
-    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long seq0 = t.st->seq;
     float bm = 0.0f;
     if (j < n) {
-        long long i = entry_index(t, idx, j, mode);
+        const long long i = entry_index(t, idx, j, mode, seq0);
         if (i >= 0 && i < t.size) {
             atomicMax(&t.owner[i], (int)j);
             if (mode == MODE_PRIORITY) bm = fabsf(val[j]);
@@ -285,36 +419,32 @@ __global__ void upd_mark_kernel(TreeView t, long long n, const long long *idx, c
 __global__ void upd_leaf_kernel(TreeView t, long long n, const long long *idx, const float *val, int mode,
                                 long long *idx_out)
 {
-    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    long long i = entry_index(t, idx, j, mode);
+    const long long i = entry_index(t, idx, j, mode, t.st->seq);
     if (idx_out) idx_out[j] = i;
     if (i < 0 || i >= t.size) return;
     if (t.owner[i] != (int)j) return;
-    float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
-    float v = entry_leaf(t, val, j, mode, defp);
-    t.sum[t.cap + i] = v;
-    t.min[t.cap + i] = v;
+    const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
+    leaf_ptr(t)[i] = entry_leaf(t, val, j, mode, defp);
     t.owner[i] = -1;
 }
 
-// dense path, sorted input: the last entry of every run of equal indices writes the leaf
 __global__ void upd_leaf_sorted_kernel(TreeView t, long long n, const long long *idx, const float *val, int mode,
                                        long long *idx_out)
 {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long seq0 = t.st->seq;
     float bm = 0.0f;
     if (j < n) {
-        const long long i = entry_index(t, idx, j, mode);
+        const long long i = entry_index(t, idx, j, mode, seq0);
         if (idx_out) idx_out[j] = i;
         if (i >= 0 && i < t.size) {
             if (mode == MODE_PRIORITY) bm = fabsf(val[j]);
-            const long long nx = (j + 1 < n) ? entry_index(t, idx, j + 1, mode) : -1;
+            const long long nx = (j + 1 < n) ? entry_index(t, idx, j + 1, mode, seq0) : -1;
             if (nx != i) {
                 const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
-                const float v = entry_leaf(t, val, j, mode, defp);
-                t.sum[t.cap + i] = v;
-                t.min[t.cap + i] = v;
+                leaf_ptr(t)[i] = entry_leaf(t, val, j, mode, defp);
             }
         }
     }
@@ -325,232 +455,224 @@ __global__ void upd_leaf_sorted_kernel(TreeView t, long long n, const long long 
 }
 
 // ---------------------------------------------------------------------------------
-// sparse phase p: one warp per batch entry; loads the 32 sibling nodes at depth
-// d = L-5p that contain the entry's ancestor and rebuilds the 5 levels above with
-// shuffles.  FUSED (sorted input, p == 0): the run leader also applies every leaf of
-// its run (sequentially -> last wins) before reducing.
+// unsorted sparse path, phase m (m = P .. 1): one warp per batch entry recomputes the line of level TL + 5m that
+// holds the entry's ancestor (entries that share a line do the same work and write the same values).
 // ---------------------------------------------------------------------------------
-template <bool FUSED>
-__device__ __forceinline__ void sparse_entry(const TreeView &t, long long n, const long long *idx, const float *val,
-                                             int mode, int p, int sorted, long long *idx_out, long long j)
-{
-    const int lane = lane_id();
-    const int sh = 5 * p + 5;
-    const long long i = entry_index(t, idx, j, mode);
-    if (i < 0 || i >= t.size) return;
-    const long long g = i >> sh;
-    if (sorted && j > 0) {
-        long long ip = entry_index(t, idx, j - 1, mode);
-        if (ip >= 0 && ip < t.size && (ip >> sh) == g) return;  // the run leader does this line
-    }
-    const int d = t.L - 5 * p;
-    const long long src = (1LL << d) + (g << 5) + lane;
-    float vs = t.sum[src], vm = t.min[src];
-    if (FUSED) {
-        const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
-        float bm = 0.0f;
-        bool touched = false;
-        for (long long jj = j; jj < n; ++jj) {
-            long long ii = entry_index(t, idx, jj, mode);
-            if (ii < 0 || ii >= t.size || (ii >> 5) != g) break;
-            float v = entry_leaf(t, val, jj, mode, defp);
-            if (mode == MODE_PRIORITY) bm = fmaxf(bm, fabsf(val[jj]));
-            if (lane == (int)(ii & 31)) { vs = v; vm = v; touched = true; }
-            if (idx_out && lane == 0) idx_out[jj] = ii;
-        }
-        if (touched) { t.sum[src] = vs; t.min[src] = vm; }
-        if (mode == MODE_PRIORITY && lane == 0 && bm > 0.0f)
-            atomicMax(reinterpret_cast<int *>(&t.st->batch_max), __float_as_int(bm));
-    }
-    const long long e = (g << 5) + lane;
-#pragma unroll
-    for (int s = 0; s < 5; ++s) {
-        vs = op_sum(vs, __shfl_xor_sync(FULL, vs, 1 << s));
-        vm = op_min(vm, __shfl_xor_sync(FULL, vm, 1 << s));
-        if ((lane & ((2 << s) - 1)) == 0) {
-            long long node = (1LL << (d - s - 1)) + (e >> (s + 1));
-            t.sum[node] = vs;
-            t.min[node] = vm;
-        }
-    }
-}
-
-template <bool FUSED>
-__global__ void __launch_bounds__(256) upd_sparse_kernel(TreeView t, long long n, const long long *idx,
-                                                         const float *val, int mode, int p, int sorted,
-                                                         long long *idx_out)
+__global__ void __launch_bounds__(256) upd_lines_kernel(TreeView t, long long n, const long long *idx, int mode, int m,
+                                                        long long n_new)
 {
     const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (j >= n) return;
-    sparse_entry<FUSED>(t, n, idx, val, mode, p, sorted, idx_out, j);
+    const long long i = entry_index(t, idx, j, mode, t.st->seq);
+    if (i < 0 || i >= t.size) return;
+    const long long len = len_after(t, mode, n_new, -1);
+    const int lane = lane_id();
+    const int s = t.TL + 5 * m;
+    const long long g = i >> (t.L - s + 5);                      // line index at level s
+    float vs, vm;
+    if (s == t.L) {
+        vs = leaf_ptr(t)[(g << 5) + lane];
+        vm = min_of_leaf(vs, (g << 5) + lane, len);
+    } else {
+        vs = sum_level(t, s)[(g << 5) + lane];
+        vm = min_level(t, s)[(g << 5) + lane];
+    }
+    line_reduce(vs, vm);
+    if (lane == 0) { sum_level(t, s - 5)[g] = vs; min_level(t, s - 5)[g] = vm; }
 }
 
 // ---------------------------------------------------------------------------------
-// latency mode (n <= 64: the handful of new transitions of one learner iteration): the whole update -- dedup,
-// leaves, every sparse phase, the top levels of both trees, the state block -- in ONE single-CTA launch,
-// phases separated by __syncthreads instead of kernel boundaries.
+// sorted input, ONE launch: warp per batch entry (grid-stride).  The first entry of every run of entries that
+// fall into the same leaf line is the line's leader: it writes the run's leaves (last of equal indices wins),
+// reduces the line and writes the node of the stored level above.  Lines of the levels above are finished by
+// whichever child arrives last: the first entry of a line's run registers the number of touched children in the
+// line's arrival counter (+c), every finished child subtracts one, and the warp whose atomic brings the counter
+// back to zero reduces the line and climbs on (the counter is zero again for the next call; nobody spins).
+// The last CTA (ticket) rebuilds the top heap and the state block.
 // ---------------------------------------------------------------------------------
-constexpr int SMALL_MAX = 64;      // beyond ~2 entries per warp the serial in-CTA loop loses to 3 wide launches (measured: 29 vs 17 us at n=256)
-constexpr int SMALL_TOP = 12;      // both trees' top levels in shared memory: 2 * 2^(12+1) * 4 B = 64 KB
+constexpr int CHAIN_THREADS = 512;
 
-__global__ void __launch_bounds__(1024) upd_small_kernel(TreeView t, long long n, const long long *idx,
-                                                         const float *val, int mode, int sorted, int P, int T,
-                                                         long long *idx_out)
+struct RunScan { long long seq0; const long long *idx; long long n; int mode; };
+
+__device__ __forceinline__ bool valid_at(const TreeView &t, const RunScan &r, long long j, long long &i)
 {
-    extern __shared__ float sm[];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const bool fused = sorted && P > 0;
-    if (!fused) {
-        float bm = 0.0f;
-        for (long long j = tid; j < n; j += blockDim.x) {
-            const long long i = entry_index(t, idx, j, mode);
-            if (i >= 0 && i < t.size) {
-                atomicMax(&t.owner[i], (int)j);
-                if (mode == MODE_PRIORITY) bm = fmaxf(bm, fabsf(val[j]));
+    if (j < 0 || j >= r.n) return false;
+    i = entry_index(t, r.idx, j, r.mode, r.seq0);
+    return i >= 0 && i < t.size;
+}
+
+// number of distinct values of (index >> child_shift) among the run of entries starting at j whose
+// (index >> shift) equals key (warp-uniform result)
+__device__ int count_children(const TreeView &t, const RunScan &r, long long j, int shift, int child_shift,
+                              long long key)
+{
+    const int lane = lane_id();
+    int c = 0;
+    for (long long base = j;; base += 32) {
+        const long long jj = base + lane;
+        long long ii = -1, ip = -1;
+        const bool ok = valid_at(t, r, jj, ii) && (ii >> shift) == key;
+        const unsigned bad = ~__ballot_sync(FULL, ok);
+        const int run = bad ? __ffs(bad) - 1 : 32;
+        bool fresh = false;
+        if (lane < run) fresh = (jj == j) || !valid_at(t, r, jj - 1, ip) || (ip >> child_shift) != (ii >> child_shift);
+        c += __popc(__ballot_sync(FULL, fresh));
+        if (run < 32) break;
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(CHAIN_THREADS) upd_chain_kernel(TreeView t, long long n, const long long *idx,
+                                                                  const float *val, int mode, long long *idx_out)
+{
+    __shared__ float sm_top[2 * TOP_SM_FLOATS];
+    const int lane = lane_id();
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    RunScan r;
+    r.seq0 = t.st->seq; r.idx = idx; r.n = n; r.mode = mode;
+    const long long len = len_after(t, mode, n, -1);
+    const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
+    float *leaf = leaf_ptr(t);
+    const int P = t.P;
+    for (long long j = w0; j < n; j += n_warps) {
+        long long i, ip = -1;
+        if (!valid_at(t, r, j, i)) continue;
+        const bool prev_ok = valid_at(t, r, j - 1, ip);
+        if (P == 0) {
+            // no deep level: the heap's leaf level is written directly, the top phase does the rest
+            float bm = 0.0f;
+            long long inx = -1;
+            const bool last_of_idx = !valid_at(t, r, j + 1, inx) || inx != i;
+            if (lane == 0) {
+                if (idx_out) idx_out[j] = i;
+                if (last_of_idx) leaf[i] = entry_leaf(t, val, j, mode, defp);
+                if (mode == MODE_PRIORITY) bm = fabsf(val[j]);
+                if (bm > 0.0f) atomicMax(reinterpret_cast<int *>(&t.st->batch_max), __float_as_int(bm));
             }
+            continue;
+        }
+        const long long line = i >> 5;
+        if (prev_ok && (ip >> 5) == line) continue;               // the run leader does this line
+        // ---- registration: lines of the upper deep levels whose run starts at this entry
+        for (int m = P - 1; m >= 1; --m) {
+            const int shift = 5 * (P - m) + 5;                    // index >> shift = line index at level TL + 5m
+            const long long pl = i >> shift;
+            if (prev_ok && (ip >> shift) == pl) break;            // not the first entry of that line (nor of any above)
+            const int c = count_children(t, r, j, shift, shift - 5, pl);
+            if (lane == 0) atomicAdd(&t.cnt[t.coff[m] + pl], c);
+        }
+        // ---- the leaf line: write the run's leaves, 32 entries at a time
+        float bm = 0.0f;
+        for (long long base = j;; base += 32) {
+            const long long jj = base + lane;
+            long long ii = -1, inx = -1;
+            const bool ok = valid_at(t, r, jj, ii) && (ii >> 5) == line;
+            const unsigned bad = ~__ballot_sync(FULL, ok);
+            const int run = bad ? __ffs(bad) - 1 : 32;
+            if (lane < run) {
+                if (idx_out) idx_out[jj] = ii;
+                if (mode == MODE_PRIORITY) bm = fmaxf(bm, fabsf(val[jj]));
+                if (!valid_at(t, r, jj + 1, inx) || inx != ii) leaf[ii] = entry_leaf(t, val, jj, mode, defp);
+            }
+            if (run < 32) break;
         }
         if (mode == MODE_PRIORITY) {
             bm = warp_max(bm);
-            if (lane_id() == 0 && bm > 0.0f) atomicMax(reinterpret_cast<int *>(&t.st->batch_max), __float_as_int(bm));
+            if (lane == 0 && bm > 0.0f) atomicMax(reinterpret_cast<int *>(&t.st->batch_max), __float_as_int(bm));
         }
-        __syncthreads();
-        const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
-        for (long long j = tid; j < n; j += blockDim.x) {
-            const long long i = entry_index(t, idx, j, mode);
-            if (idx_out) idx_out[j] = i;
-            if (i < 0 || i >= t.size || t.owner[i] != (int)j) continue;
-            const float v = entry_leaf(t, val, j, mode, defp);
-            t.sum[t.cap + i] = v;
-            t.min[t.cap + i] = v;
-            t.owner[i] = -1;
+        __syncwarp();
+        float vs = leaf[(line << 5) + lane];
+        float vm = min_of_leaf(vs, (line << 5) + lane, len);
+        line_reduce(vs, vm);
+        long long g = line;                                       // node index at level TL + 5(m) with m = P - 1
+        if (lane == 0) { sum_level(t, t.L - 5)[g] = vs; min_level(t, t.L - 5)[g] = vm; }
+        // ---- climb: level TL + 5m lines, m = P-1 .. 1
+        for (int m = P - 1; m >= 1; --m) {
+            const long long pl = g >> 5;
+            int newv = 0;
+            __threadfence();
+            if (lane == 0) newv = atomicAdd(&t.cnt[t.coff[m] + pl], -1) - 1;
+            newv = __shfl_sync(FULL, newv, 0);
+            if (newv != 0) break;                                 // another child of this line is still on its way
+            __threadfence();
+            const int s = t.TL + 5 * m;
+            vs = ldcg(sum_level(t, s) + (pl << 5) + lane);
+            vm = ldcg(min_level(t, s) + (pl << 5) + lane);
+            line_reduce(vs, vm);
+            if (lane == 0) { sum_level(t, s - 5)[pl] = vs; min_level(t, s - 5)[pl] = vm; }
+            g = pl;
         }
-        __syncthreads();
     }
-    for (int p = 0; p < P; ++p) {
-        for (long long j = warp; j < n; j += (blockDim.x >> 5)) {
-            if (p == 0 && fused) sparse_entry<true>(t, n, idx, val, mode, p, 1, idx_out, j);
-            else sparse_entry<false>(t, n, idx, val, mode, p, fused ? 1 : 0, nullptr, j);
-        }
-        __syncthreads();
-    }
-    // top levels: threads [0, 512) own the sum tree, [512, 1024) the min tree
-    const bool is_min = tid >= 512;
-    const int gt = tid & 511;
-    float *tree = is_min ? t.min : t.sum;
-    float *s = sm + (is_min ? (2 << T) : 0);
-    const int n_top = 1 << T;
-    for (int i = gt; i < n_top; i += 512) s[n_top + i] = tree[n_top + i];
-    __syncthreads();
-    for (int d = T - 1; d >= 0; --d) {
-        const int n_d = 1 << d;
-        for (int i = gt; i < n_d; i += 512) {
-            const float l = s[2 * (n_d + i)], r = s[2 * (n_d + i) + 1];
-            s[n_d + i] = is_min ? op_min(l, r) : op_sum(l, r);
-        }
-        __syncthreads();
-    }
-    for (int i = gt + 1; i < n_top; i += 512) tree[i] = s[i];
-    __syncthreads();
-    if (tid >= 32) return;
-    long long len = t.st->len;
-    if (mode == MODE_EXTEND) len = len + n < t.size ? len + n : t.size;
-    const float ps = tree_query_prefix<false>(t, len);
-    const float pm = tree_query_prefix<true>(t, len);
-    if (tid == 0) {
-        pb_per_state *st = t.st;
-        if (mode == MODE_EXTEND) st->seq += n;
-        st->len = len;
-        if (mode == MODE_PRIORITY) {
-            const float bm = st->batch_max;
-            if (bm > st->max_priority) st->max_priority = bm;
-        }
-        st->batch_max = 0.0f;
-        st->p_sum = ps; st->p_min = pm;
-    }
+    if (!last_cta(t)) return;
+    top_and_finalize(t, sm_top, mode, n, -1);
 }
 
 // ---------------------------------------------------------------------------------
-// prefix-sum descent: one warp per sample, 5 levels per dependent 128-byte load.
-// Returns the leaf index (or size when mass > root), uniform across the warp.
+// prefix-sum descent: 8 lanes per sample (4 samples per warp), 5 levels per dependent 128-byte load: every lane
+// loads 4 of the line's 32 nodes (one float4), two levels are reduced in registers and three with shuffles.  Same
+// comparisons in the same order as the reference loop (go right and subtract iff mass > left).  All 32 lanes of the
+// warp must call this together.  Returns the leaf index (or size when mass > root) and the leaf's value.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ long long warp_descend(const float *__restrict__ sum, int L, long long size,
-                                                  float m)
+__device__ __forceinline__ long long group_descend(const TreeView &t, float m, float *leaf_out)
 {
-    const int lane = lane_id();
-    if (m > sum[1]) return size;
-    long long node = 1;
-    int rem = L;
-    int c = rem % 5;          // short chunk first, so every deeper chunk is a full aligned line
+    const int gl = threadIdx.x & 7;
+    const bool over = m > t.sum[1];
+    if (over) m = 0.0f;                                           // stay on real nodes; the result is discarded
+    long long node = 0;                                           // index within the current level
+    int d = 0;
+    int c = t.L % 5;                                              // short chunk first: deeper chunks are full aligned lines
     if (c == 0) c = 5;
-    while (rem > 0) {
-        const int cnt = 1 << c;
-        const long long base = node << c;
-        float s0 = lane < cnt ? sum[base + lane] : 0.0f;
-        float s1 = op_sum(s0, __shfl_xor_sync(FULL, s0, 1));
-        float s2 = op_sum(s1, __shfl_xor_sync(FULL, s1, 2));
-        float s3 = op_sum(s2, __shfl_xor_sync(FULL, s2, 4));
-        float s4 = op_sum(s3, __shfl_xor_sync(FULL, s3, 8));
+    float leafv = 0.0f;
+    while (d < t.L) {
+        const int s = d + c;
+        const float *p = sum_level(t, s) + (node << c);
+        float4 v;
+        if (c == 5) {
+            v = *reinterpret_cast<const float4 *>(p + 4 * gl);
+        } else {
+            const int cnt = 1 << c, b = 4 * gl;
+            v.x = b + 0 < cnt ? p[b + 0] : 0.0f; v.y = b + 1 < cnt ? p[b + 1] : 0.0f;
+            v.z = b + 2 < cnt ? p[b + 2] : 0.0f; v.w = b + 3 < cnt ? p[b + 3] : 0.0f;
+        }
+        const float a = op_sum(v.x, v.y), b2 = op_sum(v.z, v.w);
+        const float c4 = op_sum(a, b2);
+        const float s1 = op_sum(c4, __shfl_xor_sync(FULL, c4, 1, 8));
+        const float s2 = op_sum(s1, __shfl_xor_sync(FULL, s1, 2, 8));
         int pos = 0;
-        if (c >= 5) { float l = __shfl_sync(FULL, s4, pos); if (m > l) { m = __fsub_rn(m, l); pos += 16; } }
-        if (c >= 4) { float l = __shfl_sync(FULL, s3, pos); if (m > l) { m = __fsub_rn(m, l); pos += 8; } }
-        if (c >= 3) { float l = __shfl_sync(FULL, s2, pos); if (m > l) { m = __fsub_rn(m, l); pos += 4; } }
-        if (c >= 2) { float l = __shfl_sync(FULL, s1, pos); if (m > l) { m = __fsub_rn(m, l); pos += 2; } }
-        {             float l = __shfl_sync(FULL, s0, pos); if (m > l) { m = __fsub_rn(m, l); pos += 1; } }
-        node = base + pos;
-        rem -= c;
+        float l = __shfl_sync(FULL, s2, 0, 8);
+        if (m > l) { m = __fsub_rn(m, l); pos = 4; }
+        l = __shfl_sync(FULL, s1, pos, 8);
+        if (m > l) { m = __fsub_rn(m, l); pos += 2; }
+        l = __shfl_sync(FULL, c4, pos, 8);
+        if (m > l) { m = __fsub_rn(m, l); pos += 1; }
+        const float la = __shfl_sync(FULL, a, pos, 8);
+        const float lx = __shfl_sync(FULL, v.x, pos, 8), ly = __shfl_sync(FULL, v.y, pos, 8);
+        const float lz = __shfl_sync(FULL, v.z, pos, 8), lw = __shfl_sync(FULL, v.w, pos, 8);
+        int sub = 0;
+        float l0 = lx, l1 = ly;
+        if (m > la) { m = __fsub_rn(m, la); sub = 2; l0 = lz; l1 = lw; }
+        leafv = l0;
+        if (m > l0) { m = __fsub_rn(m, l0); sub += 1; leafv = l1; }
+        node = (c == 5 ? (node << 5) : 0) + 4 * pos + sub;
+        d = s;
         c = 5;
     }
-    return node ^ (1LL << L);
+    *leaf_out = leafv;
+    return over ? t.size : node;
 }
 
-// ---------------------------------------------------------------------------------
-// throughput mode (large batches): one THREAD per sample, the top levels staged in shared
-// memory.  Same comparisons in the same order as warp_descend (and as the reference loop), so
-// the two modes return identical indices; with stratified (sorted) masses neighbouring threads
-// walk neighbouring paths, so the per-level loads of a warp coalesce into a few sectors.
-// ---------------------------------------------------------------------------------
-constexpr int STAGE_LEVELS = 11;   // nodes [1, 2^11) = 8 KB of shared memory per CTA
-
-__device__ __forceinline__ void stage_top(const float *__restrict__ sum, int L, float *sm)
+__global__ void __launch_bounds__(256) tree_scan_kernel(TreeView t, long long n, const float *mass, long long *idx_out)
 {
-    const int S = L < STAGE_LEVELS ? L : STAGE_LEVELS;
-    const int n = 1 << S;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = sum[i];
-    __syncthreads();
-}
-
-__device__ __forceinline__ long long thread_descend(const float *__restrict__ sum, const float *sm, int L,
-                                                    long long size, float m)
-{
-    if (m > sm[1]) return size;
-    const int S = L < STAGE_LEVELS ? L : STAGE_LEVELS;
-    const long long staged = 1LL << S;
-    long long node = 1;
-    for (int d = 0; d < L; ++d) {
-        node <<= 1;
-        const float left = node < staged ? sm[node] : __ldg(sum + node);
-        if (m > left) { m = __fsub_rn(m, left); node |= 1; }
+    const long long n_groups = ((long long)gridDim.x * blockDim.x) >> 3;
+    const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const long long rounds = (n + n_groups - 1) / n_groups;
+    for (long long rd = 0; rd < rounds; ++rd) {
+        const long long k = g0 + rd * n_groups;
+        float leafv;
+        const long long i = group_descend(t, k < n ? mass[k] : 0.0f, &leafv);
+        if (k < n && (threadIdx.x & 7) == 0) idx_out[k] = i;
     }
-    return node ^ (1LL << L);
-}
-
-__global__ void __launch_bounds__(256) tree_scan_thread_kernel(TreeView t, long long n, const float *mass,
-                                                               long long *idx_out)
-{
-    __shared__ float sm[1 << STAGE_LEVELS];
-    stage_top(t.sum, t.L, sm);
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    idx_out[k] = thread_descend(t.sum, sm, t.L, t.size, mass[k]);
-}
-
-__global__ void __launch_bounds__(256) tree_scan_kernel(TreeView t, long long n, const float *mass,
-                                                        long long *idx_out)
-{
-    const long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (k >= n) return;
-    long long i = warp_descend(t.sum, t.L, t.size, mass[k]);
-    if (lane_id() == 0) idx_out[k] = i;
 }
 
 __device__ __forceinline__ float is_weight(float leaf, float p_min, float beta, const TreeView &t)
@@ -562,7 +684,7 @@ __device__ __forceinline__ float is_weight(float leaf, float p_min, float beta, 
 }
 
 // ---------------------------------------------------------------------------------
-// device-side uniforms: Philox4x32-10 keyed by the shard seed, counter = (stratum, call number).
+// device-side uniforms: Philox4x32-10 keyed by the shard seed, counter = (sample number, call number).
 // Every rank of a sharded buffer draws the same u_k without communication; the call number lives in
 // the state block and is advanced by the last CTA of the launch (ticket), so a replayed CUDA graph
 // gets fresh numbers every iteration with no extra launch.
@@ -595,72 +717,50 @@ __device__ __forceinline__ void rng_advance(const TreeView &t)
     }
 }
 
-__global__ void __launch_bounds__(256) tree_sample_kernel(TreeView t, long long n, const double *u, int mode,
-                                                          float beta, long long *idx_out, float *w_out,
+__device__ __forceinline__ float stratified_mass(long long k, double uk, long long n, float total)
+{
+    return (float)__dmul_rn(__ddiv_rn(__dadd_rn((double)k, uk), (double)n), (double)total);
+}
+
+// n = n_batches * batch samples; sample k belongs to batch k / batch, stratum k % batch of its batch (every batch
+// is stratified on its own, all against the same tree state).  Persistent grid.
+__global__ void __launch_bounds__(256) tree_sample_kernel(TreeView t, long long n, long long batch, const double *u,
+                                                          int mode, float beta, long long *idx_out, float *w_out,
                                                           float *mass_out)
 {
-    const long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = lane_id();
     const unsigned call = (unsigned)t.st->pad[2], seed = (unsigned)t.st->pad[3];
-    if (k < n) {
-        const long long len = t.st->len;
-        const float p_sum = t.st->p_sum, p_min = t.st->p_min;
-        int bad = 0;
-        if (len <= 0) bad = PB_ST_EMPTY;
-        else if (!(p_sum > 0.0f)) bad = PB_ST_PSUM_NONPOS;
-        else if (!(p_min > 0.0f)) bad = PB_ST_PMIN_NONPOS;
+    const long long len = t.st->len;
+    const float p_sum = t.st->p_sum, p_min = t.st->p_min;
+    int bad = 0;
+    if (len <= 0) bad = PB_ST_EMPTY;
+    else if (!(p_sum > 0.0f)) bad = PB_ST_PSUM_NONPOS;
+    else if (!(p_min > 0.0f)) bad = PB_ST_PMIN_NONPOS;
+    const long long n_groups = ((long long)gridDim.x * blockDim.x) >> 3;
+    const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const long long rounds = (n + n_groups - 1) / n_groups;
+    const bool head = (threadIdx.x & 7) == 0;
+    for (long long rd = 0; rd < rounds; ++rd) {
+        const long long k = g0 + rd * n_groups;
+        const bool live = k < n;
         if (bad) {
-            if (lane == 0) {
+            if (live && head) {
                 idx_out[k] = 0; w_out[k] = 0.0f;
                 if (mass_out) mass_out[k] = 0.0f;
                 if (k == 0) atomicOr(&t.st->status, bad);
             }
-        } else {
-            const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
-            const double m64 = (mode == 0) ? (0.0 + ((double)p_sum - 0.0) * uk)
-                                           : __dmul_rn(__ddiv_rn(__dadd_rn((double)k, uk), (double)n), (double)p_sum);
-            const float m = (float)m64;
-            long long i = warp_descend(t.sum, t.L, t.size, m);
-            if (i > len - 1) i = len - 1;
-            if (lane == 0) {
-                float leaf = t.sum[t.cap + i];
-                idx_out[k] = i;
-                w_out[k] = is_weight(leaf, p_min, beta, t);
-                if (mass_out) mass_out[k] = m;
-            }
+            continue;
         }
-    }
-    if (!u) { __syncthreads(); rng_advance(t); }
-}
-
-__global__ void __launch_bounds__(256) tree_sample_thread_kernel(TreeView t, long long n, const double *u, int mode,
-                                                                 float beta, long long *idx_out, float *w_out,
-                                                                 float *mass_out)
-{
-    __shared__ float sm[1 << STAGE_LEVELS];
-    const unsigned call = (unsigned)t.st->pad[2], seed = (unsigned)t.st->pad[3];
-    stage_top(t.sum, t.L, sm);
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) {
-        const long long len = t.st->len;
-        const float p_sum = t.st->p_sum, p_min = t.st->p_min;
-        int bad = 0;
-        if (len <= 0) bad = PB_ST_EMPTY;
-        else if (!(p_sum > 0.0f)) bad = PB_ST_PSUM_NONPOS;
-        else if (!(p_min > 0.0f)) bad = PB_ST_PMIN_NONPOS;
-        if (bad) {
-            idx_out[k] = 0; w_out[k] = 0.0f;
-            if (mass_out) mass_out[k] = 0.0f;
-            if (k == 0) atomicOr(&t.st->status, bad);
-        } else {
+        float m = 0.0f;
+        if (live) {
             const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
-            const double m64 = (mode == 0) ? (0.0 + ((double)p_sum - 0.0) * uk)
-                                           : __dmul_rn(__ddiv_rn(__dadd_rn((double)k, uk), (double)n), (double)p_sum);
-            const float m = (float)m64;
-            long long i = thread_descend(t.sum, sm, t.L, t.size, m);
-            if (i > len - 1) i = len - 1;
+            m = (mode == 0) ? (float)(0.0 + ((double)p_sum - 0.0) * uk) : stratified_mass(k % batch, uk, batch, p_sum);
+        }
+        float leafv;
+        long long i = group_descend(t, m, &leafv);
+        if (live && head) {
+            if (i > len - 1) { i = len - 1; leafv = leaf_ptr(t)[i]; }
             idx_out[k] = i;
-            w_out[k] = is_weight(__ldg(t.sum + t.cap + i), p_min, beta, t);
+            w_out[k] = is_weight(leafv, p_min, beta, t);
             if (mass_out) mass_out[k] = m;
         }
     }
@@ -669,16 +769,18 @@ __global__ void __launch_bounds__(256) tree_sample_thread_kernel(TreeView t, lon
 
 // ---------------------------------------------------------------------------------
 // sharded global stratified sampling: the G shard roots are the leaves of a virtual
-// top tree, summed pairwise in fp32 (so shards concatenated == one big tree).
+// top tree, summed pairwise in fp32 (so shards concatenated == one big tree).  ONE launch: masses are
+// non-decreasing in the stratum number and the descent is monotone, so the strata a rank owns are a contiguous
+// range [lo, lo + cnt) that every CTA finds by a warp-parallel 32-ary search (no counting pass, no atomics).
 // ---------------------------------------------------------------------------------
 constexpr int MAX_RANKS = 64;
 
 struct GlobalTop {
     float psum[2 * MAX_RANKS];  // heap layout of the virtual top: leaves (shard p_sums) at [G, 2G)
     float pmin;
+    long long lo, hi;           // this rank owns strata [lo, hi)
 };
 
-// every CTA rebuilds the virtual top from the all-gathered shard stats (device memory)
 __device__ __forceinline__ void build_top(GlobalTop *g, const pb_per_state *all_state, int G)
 {
     if (threadIdx.x < G) g->psum[G + threadIdx.x] = all_state[threadIdx.x].p_sum;
@@ -699,8 +801,7 @@ __device__ __forceinline__ int route_stratum(const GlobalTop &g, int G, long lon
                                              double uk, float *residual)
 {
     const float total = g.psum[1];
-    const double m64 = __dmul_rn(__ddiv_rn(__dadd_rn((double)k, uk), (double)n_global), (double)total);
-    float m = (float)m64;
+    float m = stratified_mass(k, uk, n_global, total);
     *residual = m;
     if (m > total) return G - 1;  // unreachable for u < 1; clamp like idx.clamp_max(len-1)
     int node = 1;
@@ -713,25 +814,31 @@ __device__ __forceinline__ int route_stratum(const GlobalTop &g, int G, long lon
     return node - G;
 }
 
-__global__ void __launch_bounds__(256) global_count_kernel(TreeView t, const pb_per_state *all_state,
-                                                           int G, int rank, long long n_global, const double *u)
+// first stratum k in [0, n] whose owner is >= rank_bound (n when there is none); one warp, 32-ary search over the
+// monotone predicate owner(k) >= rank_bound
+__device__ long long first_owned(const GlobalTop &g, int G, long long n, int rank_bound, const double *u,
+                                 unsigned seed, unsigned call)
 {
-    __shared__ GlobalTop g;
-    build_top(&g, all_state, G);
-    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int lo = 0, mine = 0;
-    if (k < n_global) {
-        float res;
-        const double uk = u ? u[k] : philox_uniform((unsigned)t.st->pad[3], (unsigned)t.st->pad[2], (unsigned long long)k);
-        int owner = route_stratum(g, G, k, n_global, uk, &res);
-        lo = owner < rank;
-        mine = owner == rank;
+    const int lane = lane_id();
+    long long lo = 0, hi = n;                                     // the answer lies in [lo, hi]
+    while (lo < hi) {
+        const long long step = (hi - lo + 31) / 32;
+        const long long k = lo + (long long)lane * step;          // 32 probes, lo first
+        bool ge = true;                                           // probes at or past hi count as "owned"
+        if (k < hi) {
+            float res;
+            const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
+            ge = route_stratum(g, G, k, n, uk, &res) >= rank_bound;
+        }
+        const unsigned m = __ballot_sync(FULL, ge);
+        if (m == 0u) { lo = lo + 31 * step + 1; continue; }       // all 32 probes below hi and none owned yet
+        const int first = __ffs(m) - 1;
+        if (first == 0) { hi = lo; break; }
+        const long long k_first = lo + (long long)first * step;
+        lo = k_first - step + 1;                                  // probe first-1 was not owned
+        hi = k_first < hi ? k_first : hi;
     }
-    unsigned blo = __ballot_sync(FULL, lo), bmine = __ballot_sync(FULL, mine);
-    if (lane_id() == 0) {
-        if (blo) atomicAdd(&t.st->owned_lo, __popc(blo));
-        if (bmine) atomicAdd(&t.st->owned_n, __popc(bmine));
-    }
+    return hi;
 }
 
 __global__ void __launch_bounds__(256) global_sample_kernel(TreeView t, const pb_per_state *all_state, int G, int rank,
@@ -740,69 +847,133 @@ __global__ void __launch_bounds__(256) global_sample_kernel(TreeView t, const pb
 {
     __shared__ GlobalTop g;
     build_top(&g, all_state, G);
-    const long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = lane_id();
     const unsigned call = (unsigned)t.st->pad[2], seed = (unsigned)t.st->pad[3];
-    if (k < n_global) {
-        const int lo = t.st->owned_lo, cnt = t.st->owned_n;
-        if (k >= cnt && lane == 0) {  // padding rows of the static batch: idx -1 is skipped downstream
-            idx_out[k] = -1; w_out[k] = 0.0f;
-            if (stratum_out) stratum_out[k] = -1;
+    if (threadIdx.x < 32) {
+        const long long lo = first_owned(g, G, n_global, rank, u, seed, call);
+        const long long hi = first_owned(g, G, n_global, rank + 1, u, seed, call);
+        if (threadIdx.x == 0) { g.lo = lo; g.hi = hi; }
+    }
+    __syncthreads();
+    const long long lo = g.lo, cnt = g.hi - g.lo;
+    const long long len = all_state[rank].len;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        t.st->owned_lo = (int)lo; t.st->owned_n = (int)cnt;
+        if (cnt > 0 && (len <= 0 || !(g.psum[1] > 0.0f) || !(g.pmin > 0.0f)))
+            atomicOr(&t.st->status, len <= 0 ? PB_ST_EMPTY : (!(g.psum[1] > 0.0f) ? PB_ST_PSUM_NONPOS : PB_ST_PMIN_NONPOS));
+    }
+    const long long n_groups = ((long long)gridDim.x * blockDim.x) >> 3;
+    const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const long long rounds = (n_global + n_groups - 1) / n_groups;
+    const bool head = (threadIdx.x & 7) == 0;
+    for (long long rd = 0; rd < rounds; ++rd) {
+        const long long pos = g0 + rd * n_groups;                 // output row
+        const bool live = pos < cnt;
+        float res = 0.0f;
+        if (live) {
+            const long long k = lo + pos;
+            const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
+            route_stratum(g, G, k, n_global, uk, &res);
         }
-        float res;
-        const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
-        const int owner = route_stratum(g, G, k, n_global, uk, &res);
-        if (owner == rank) {
-            const long long len = all_state[rank].len;
-            if (len <= 0 || !(g.psum[1] > 0.0f) || !(g.pmin > 0.0f)) {
-                if (lane == 0 && k == lo)
-                    atomicOr(&t.st->status, len <= 0 ? PB_ST_EMPTY : (!(g.psum[1] > 0.0f) ? PB_ST_PSUM_NONPOS : PB_ST_PMIN_NONPOS));
-            }
-            long long i = warp_descend(t.sum, t.L, t.size, res);
-            if (i > len - 1) i = len - 1;
-            if (i < 0) i = 0;
-            if (lane == 0) {
-                const long long pos = k - lo;
-                float leaf = t.sum[t.cap + i];
+        float leafv;
+        long long i = group_descend(t, res, &leafv);
+        if (head && pos < n_global) {
+            if (live) {
+                if (i > len - 1) { i = len - 1; if (i < 0) i = 0; leafv = leaf_ptr(t)[i]; }
                 idx_out[pos] = i;
-                w_out[pos] = is_weight(leaf, g.pmin, beta, t);
-                if (stratum_out) stratum_out[pos] = k;
+                w_out[pos] = is_weight(leafv, g.pmin, beta, t);
+                if (stratum_out) stratum_out[pos] = lo + pos;
+            } else {                                              // padding rows of the static batch: skipped downstream
+                idx_out[pos] = -1; w_out[pos] = 0.0f;
+                if (stratum_out) stratum_out[pos] = -1;
             }
         }
     }
     if (!u) { __syncthreads(); rng_advance(t); }
 }
 
-__global__ void global_reset_kernel(TreeView t) { t.st->owned_lo = 0; t.st->owned_n = 0; }
+// ---------------------------------------------------------------------------------
+// export: the full level-ordered arrays (2 * capacity floats per tree) a pointer-walking tree would hold --
+// parity tests and checkpoints.  One launch per level.
+// ---------------------------------------------------------------------------------
+__global__ void tree_export_kernel(TreeView t, int d, float *sum_heap, float *min_heap)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1LL << d)) return;
+    const long long len = t.st->len;
+    if (sum_heap) sum_heap[(1LL << d) + i] = node_value<false>(t, d, i, len);
+    if (min_heap) min_heap[(1LL << d) + i] = node_value<true>(t, d, i, len);
+    if (d == 0 && i == 0) {
+        if (sum_heap) sum_heap[0] = 0.0f;
+        if (min_heap) min_heap[0] = INF;
+    }
+}
 
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
+struct Layout { int L, TL, P; long long off[MAX_DEEP], coff[MAX_DEEP]; long long n_sum, n_min, n_cnt; };
+
+void make_layout(long long cap, Layout *y)
+{
+    y->L = pb_ilog2(cap);
+    y->P = y->L <= TOP_MAX ? 0 : (y->L - TOP_MAX + 4) / 5;
+    y->TL = y->L - 5 * y->P;
+    long long off = 2LL << y->TL, coff = 0;
+    for (int m = 0; m < MAX_DEEP; ++m) { y->off[m] = 0; y->coff[m] = 0; }
+    y->n_min = off;
+    for (int m = 1; m <= y->P; ++m) {
+        y->off[m] = off;
+        off += 1LL << (y->TL + 5 * m);
+        if (m < y->P) {
+            y->n_min = off;                                       // the min store ends before the leaf level
+            y->coff[m] = coff;
+            coff += 1LL << (y->TL + 5 * m - 5);                   // one counter per line of level TL + 5m
+        }
+    }
+    y->n_sum = off;
+    y->n_cnt = coff > 0 ? coff : 1;
+}
+
 int make_view(const pb_tree *t, TreeView *v)
 {
     if (!t || !t->sum || !t->min || !t->state) return PB_E_ARG;
     if (!pb_is_pow2(t->capacity) || t->size <= 0 || t->size > t->capacity) return PB_E_CAPACITY;
     if (t->capacity < 2 || t->capacity > (1LL << 30)) return PB_E_CAPACITY;
-    v->sum = t->sum; v->min = t->min; v->owner = t->owner; v->st = t->state;
-    v->cap = t->capacity; v->size = t->size; v->L = pb_ilog2(t->capacity);
+    Layout y;
+    make_layout(t->capacity, &y);
+    if (y.P > 1 && !t->counters) return PB_E_ARG;
+    v->sum = t->sum; v->min = t->min; v->owner = t->owner; v->cnt = t->counters; v->st = t->state;
+    v->cap = t->capacity; v->size = t->size; v->L = y.L; v->TL = y.TL; v->P = y.P;
+    for (int m = 0; m < MAX_DEEP; ++m) { v->off[m] = y.off[m]; v->coff[m] = y.coff[m]; }
     v->alpha = t->alpha; v->eps32 = t->eps_f32; v->eps64 = t->eps_f64;
     v->weps = t->weight_eps_in_denominator; v->dp64 = t->default_priority_fp64;
     return PB_OK;
 }
 
-int sparse_phases(int L) { return L <= TOP_MAX ? 0 : (L - TOP_MAX + 4) / 5; }
-
-int launch_top(const TreeView &v, int T, int mode, long long n_new, long long set_len, void *stream)
+int persistent_grid(long long work_items, int per_cta, int ctas_per_sm)
 {
-    static PbPerDeviceOnce attr_set;
-    size_t smem = sizeof(float) * (2ull << T);
-    if (!attr_set.done()) {
-        cudaError_t e = cudaFuncSetAttribute(tree_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(sizeof(float) * (2ull << TOP_MAX)));
-        if (e != cudaSuccess) return (int)e;
-        attr_set.mark();
+    long long need = (work_items + per_cta - 1) / per_cta;
+    long long cap = (long long)pb_sm_count() * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// every line of every deep level from the leaves up, then the top heap + state (streaming; ext: bulk build source)
+int launch_rebuild(const TreeView &v, const float *ext, long long n_ext, int mode, long long n_new, long long set_len,
+                   void *stream)
+{
+    if (v.P == 0) {
+        if (ext) PB_LAUNCH(tree_fill_leaves_kernel, (unsigned)((v.cap + 255) / 256), 256, 0, stream, v, ext, n_ext);
+        PB_LAUNCH(tree_top_kernel, 1, 512, 0, stream, v, mode, n_new, set_len);
+        return PB_OK;
     }
-    PB_LAUNCH(tree_top_kernel, 2, 1024, smem, stream, v, T, mode, n_new, set_len);
+    for (int s = v.L; s > v.TL; s -= 10) {
+        const int two = (s - 10 >= v.TL) ? 1 : 0;
+        const int fuse = (s - 10 <= v.TL) ? 1 : 0;
+        const int grid = persistent_grid(1LL << s, RB_TILE, 8);
+        PB_LAUNCH(tree_rebuild_kernel, grid, RB_THREADS, 0, stream, v, s, two, s == v.L ? ext : (const float *)nullptr,
+                  n_ext, fuse, mode, n_new, set_len);
+    }
     return PB_OK;
 }
 
@@ -817,73 +988,61 @@ int launch_update(const pb_tree *t, long long n, const long long *idx, const flo
     if (n == 0) return PB_OK;
     if (mode == MODE_EXTEND) {
         if (n > v.size) return PB_E_ARG;
-        sorted = (n + 64 <= v.size);  // contiguous run, except when it can wrap onto its own line
+        sorted = (2 * n <= v.size);     // a contiguous run of slots; a long one may wrap onto lines it already touched
     }
-    const int P = sparse_phases(v.L);
-    // dense path: when the batch touches a sizeable part of the tree, scatter the leaves and rebuild
-    // every level with the streaming build kernels (2 x 12 B x cap of traffic, independent of n)
-    if (P > 0 && n * 128 >= v.cap && v.L >= 11) {
-        const int nb = (int)((n + 255) / 256);
-        if (sorted) {
-            PB_LAUNCH(upd_leaf_sorted_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out);
-        } else {
-            if (!v.owner) return PB_E_ARG;
-            PB_LAUNCH(upd_mark_kernel, nb, 256, 0, stream, v, n, idx, val, mode);
-            PB_LAUNCH(upd_leaf_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out);
-        }
-        int d = v.L;
-        while (d > TOP_MAX) {
-            dim3 g2((unsigned)((1LL << d) / STAGE_TILE), 2);
-            PB_LAUNCH(tree_reduce11_kernel<false>, g2, 256, 0, stream, v, d, (const float *)nullptr, 0LL);
-            d -= 11;
-        }
-        return launch_top(v, d, mode, n, -1, stream);
-    }
-    if (n <= SMALL_MAX && v.L >= 5) {
-        // latency mode: one single-CTA launch
-        const int Ps = v.L <= SMALL_TOP ? 0 : (v.L - SMALL_TOP + 4) / 5;
-        const int Ts = v.L - 5 * Ps;
-        if (!(sorted && Ps > 0) && !v.owner) return PB_E_ARG;
-        static PbPerDeviceOnce attr_set;
-        if (!attr_set.done()) {
-            cudaError_t e = cudaFuncSetAttribute(upd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)(sizeof(float) * 2 * (2ull << SMALL_TOP)));
-            if (e != cudaSuccess) return (int)e;
-            attr_set.mark();
-        }
-        const size_t smem = sizeof(float) * 2 * (2ull << Ts);
-        PB_LAUNCH(upd_small_kernel, 1, 1024, smem, stream, v, n, idx, val, mode, sorted, Ps, Ts, idx_out);
+    // dense path: when the batch touches a sizeable part of the tree, scatter the leaves and rebuild every line with
+    // the streaming pass (4.3 B per leaf of traffic, independent of n)
+    const long long dense_min = sorted ? v.cap / 64 : v.cap / 256;
+    const bool dense = v.P > 0 && n >= dense_min;
+    if (sorted && !dense) {
+        const int grid = persistent_grid(n, CHAIN_THREADS / 32, 2);
+        PB_LAUNCH(upd_chain_kernel, grid, CHAIN_THREADS, 0, stream, v, n, idx, val, mode, idx_out);
         return PB_OK;
     }
-    const bool fused = sorted && P > 0;
-    if (!fused) {
+    const int nb = (int)((n + 255) / 256);
+    if (sorted) {
+        PB_LAUNCH(upd_leaf_sorted_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out);
+    } else {
         if (!v.owner) return PB_E_ARG;
-        const int nb = (int)((n + 255) / 256);
         PB_LAUNCH(upd_mark_kernel, nb, 256, 0, stream, v, n, idx, val, mode);
         PB_LAUNCH(upd_leaf_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out);
     }
+    if (dense || v.P == 0) return launch_rebuild(v, nullptr, 0, mode, n, -1, stream);
     const int nbw = (int)((n + 7) / 8);
-    for (int p = 0; p < P; ++p) {
-        if (p == 0 && fused)
-            PB_LAUNCH(upd_sparse_kernel<true>, nbw, 256, 0, stream, v, n, idx, val, mode, p, 1, idx_out);
-        else
-            PB_LAUNCH(upd_sparse_kernel<false>, nbw, 256, 0, stream, v, n, idx, val, mode, p, fused ? 1 : 0,
-                      (long long *)nullptr);
-    }
-    return launch_top(v, v.L - 5 * P, mode, n, -1, stream);
+    for (int m = v.P; m >= 1; --m)
+        PB_LAUNCH(upd_lines_kernel, nbw, 256, 0, stream, v, n, idx, mode, m, n);
+    PB_LAUNCH(tree_top_kernel, 1, 512, 0, stream, v, mode, n, -1LL);
+    return PB_OK;
 }
 
 }  // namespace
 
 extern "C" {
 
+int pb_tree_layout(long long capacity, long long *sum_floats, long long *min_floats, long long *counter_ints,
+                   long long *leaf_offset, int *top_level)
+{
+    if (!pb_is_pow2(capacity) || capacity < 2 || capacity > (1LL << 30)) return PB_E_CAPACITY;
+    Layout y;
+    make_layout(capacity, &y);
+    if (sum_floats) *sum_floats = y.n_sum;
+    if (min_floats) *min_floats = y.n_min;
+    if (counter_ints) *counter_ints = y.n_cnt;
+    if (leaf_offset) *leaf_offset = y.P == 0 ? (1LL << y.L) : y.off[y.P];
+    if (top_level) *top_level = y.TL;
+    return PB_OK;
+}
+
 int pb_tree_init(const pb_tree *t, void *stream)
 {
     TreeView v;
     int rc = make_view(t, &v);
     if (rc) return rc;
+    if (!t->counters) return PB_E_ARG;
+    Layout y;
+    make_layout(t->capacity, &y);
     int nb = pb_sm_count() * 8;
-    PB_LAUNCH(tree_init_kernel, nb, 256, 0, stream, v);
+    PB_LAUNCH(tree_init_kernel, nb, 256, 0, stream, v, y.n_sum, y.n_min, y.n_cnt);
     return PB_OK;
 }
 
@@ -902,23 +1061,7 @@ int pb_tree_build(const pb_tree *t, const float *leaves, long long n, void *stre
     int rc = make_view(t, &v);
     if (rc) return rc;
     if (!leaves || n < 0 || n > v.size) return PB_E_ARG;
-    int d = v.L;
-    if (d > TOP_MAX) {
-        // stage 1 from the leaves, then further 11-level stages while the frontier is too deep
-        if (d < 11) return PB_E_CAPACITY;
-        dim3 grid((unsigned)(v.cap / STAGE_TILE), 2);
-        PB_LAUNCH(tree_reduce11_kernel<true>, grid, 256, 0, stream, v, d, leaves, n);
-        d -= 11;
-        while (d > TOP_MAX) {
-            dim3 g2((unsigned)((1LL << d) / STAGE_TILE), 2);
-            PB_LAUNCH(tree_reduce11_kernel<false>, g2, 256, 0, stream, v, d, (const float *)nullptr, 0LL);
-            d -= 11;
-        }
-    } else {
-        int nb = (int)((v.cap + 255) / 256);
-        PB_LAUNCH(tree_fill_leaves_kernel, nb, 256, 0, stream, v, leaves, n);
-    }
-    return launch_top(v, d, MODE_RAW, 0, n, stream);
+    return launch_rebuild(v, leaves, n, MODE_RAW, 0, n, stream);
 }
 
 int pb_tree_set_leaves(const pb_tree *t, long long n, const long long *idx, const float *leaves, int sorted,
@@ -945,28 +1088,29 @@ int pb_tree_scan(const pb_tree *t, long long n, const float *mass, long long *id
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!mass || !idx_out))) return PB_E_ARG;
     if (n == 0) return PB_OK;
-    if (n >= THREAD_MODE_MIN)
-        PB_LAUNCH(tree_scan_thread_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, v, n, mass, idx_out);
-    else
-        PB_LAUNCH(tree_scan_kernel, (unsigned)((n + 7) / 8), 256, 0, stream, v, n, mass, idx_out);
+    PB_LAUNCH(tree_scan_kernel, persistent_grid(n, 32, 8), 256, 0, stream, v, n, mass, idx_out);
+    return PB_OK;
+}
+
+int pb_tree_sample_batches(const pb_tree *t, long long n_batches, long long batch, const double *u, int mode,
+                           float beta, long long *idx_out, float *weight_out, float *mass_out, void *stream)
+{
+    TreeView v;
+    int rc = make_view(t, &v);
+    if (rc) return rc;
+    if (n_batches < 0 || batch < 0 || (mode != 0 && mode != 1)) return PB_E_ARG;
+    const long long n = n_batches * batch;
+    if (n >= (1LL << 31) || (n > 0 && (!idx_out || !weight_out))) return PB_E_ARG;
+    if (n == 0) return PB_OK;
+    PB_LAUNCH(tree_sample_kernel, persistent_grid(n, 32, 8), 256, 0, stream, v, n, batch, u, mode, beta, idx_out,
+              weight_out, mass_out);
     return PB_OK;
 }
 
 int pb_tree_sample(const pb_tree *t, long long n, const double *u, int mode, float beta, long long *idx_out,
                    float *weight_out, float *mass_out, void *stream)
 {
-    TreeView v;
-    int rc = make_view(t, &v);
-    if (rc) return rc;
-    if (n < 0 || (n > 0 && (!idx_out || !weight_out)) || (mode != 0 && mode != 1)) return PB_E_ARG;
-    if (n == 0) return PB_OK;
-    if (n >= THREAD_MODE_MIN)
-        PB_LAUNCH(tree_sample_thread_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, v, n, u, mode, beta,
-                  idx_out, weight_out, mass_out);
-    else
-        PB_LAUNCH(tree_sample_kernel, (unsigned)((n + 7) / 8), 256, 0, stream, v, n, u, mode, beta, idx_out,
-                  weight_out, mass_out);
-    return PB_OK;
+    return pb_tree_sample_batches(t, n > 0 ? 1 : 0, n, u, mode, beta, idx_out, weight_out, mass_out, stream);
 }
 
 int pb_tree_sample_global(const pb_tree *t, int n_ranks, int rank, const pb_per_state *all_state,
@@ -979,12 +1123,20 @@ int pb_tree_sample_global(const pb_tree *t, int n_ranks, int rank, const pb_per_
     if (n_ranks < 1 || n_ranks > MAX_RANKS || !pb_is_pow2(n_ranks) || rank < 0 || rank >= n_ranks) return PB_E_ARG;
     if (!all_state || n_global < 0) return PB_E_ARG;
     if (n_global > 0 && (!idx_out || !weight_out)) return PB_E_ARG;
-    PB_LAUNCH(global_reset_kernel, 1, 1, 0, stream, v);
     if (n_global == 0) return PB_OK;
-    PB_LAUNCH(global_count_kernel, (unsigned)((n_global + 255) / 256), 256, 0, stream, v, all_state,
-              n_ranks, rank, n_global, u);
-    PB_LAUNCH(global_sample_kernel, (unsigned)((n_global + 7) / 8), 256, 0, stream, v, all_state,
-              n_ranks, rank, n_global, u, beta, idx_out, weight_out, stratum_out);
+    PB_LAUNCH(global_sample_kernel, persistent_grid(n_global, 32, 8), 256, 0, stream, v, all_state, n_ranks, rank,
+              n_global, u, beta, idx_out, weight_out, stratum_out);
+    return PB_OK;
+}
+
+int pb_tree_export(const pb_tree *t, float *sum_heap, float *min_heap, void *stream)
+{
+    TreeView v;
+    int rc = make_view(t, &v);
+    if (rc) return rc;
+    if (!sum_heap && !min_heap) return PB_E_ARG;
+    for (int d = v.L; d >= 0; --d)
+        PB_LAUNCH(tree_export_kernel, (unsigned)(((1LL << d) + 255) / 256), 256, 0, stream, v, d, sum_heap, min_heap);
     return PB_OK;
 }
 

@@ -21,7 +21,9 @@ def _pow2_ceil(n):
 
 
 class PrioritizedTree:
-    """Sum/min segment trees over ``size`` slots, level-ordered fp32 arrays in HBM.
+    """Sum/min segment trees over ``size`` slots in the compact 32-ary layout of csrc/per_tree.cu (every 5th level
+    stored, the levels in between rebuilt in registers; the min tree shares the leaf array).  ``sum`` / ``min`` export
+    the full level-ordered arrays a pointer-walking tree would hold (tests, checkpoints); ``leaves()`` is a view.
 
     Attribute names follow torchrl's PrioritizedSampler where the reference pokes at
     them (``_beta`` is written by prism/learner.py:107; ``_alpha``, ``_eps``).
@@ -44,13 +46,18 @@ class PrioritizedTree:
         self._beta = float(beta)
         self._eps = float(eps)
         self.mode = self.MODE_STRATIFIED if mode in ("stratified", 1) else self.MODE_IID
-        self.sum = torch.empty(2 * self.capacity, dtype=torch.float32, device=self.device)
-        self.min = torch.empty(2 * self.capacity, dtype=torch.float32, device=self.device)
+        n_sum, n_min, n_cnt, leaf_off, top = (C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_int())
+        _lib.check(self._lib.pb_tree_layout(self.capacity, C.byref(n_sum), C.byref(n_min), C.byref(n_cnt),
+                                            C.byref(leaf_off), C.byref(top)), "pb_tree_layout")
+        self.top_level, self._leaf_offset = top.value, leaf_off.value
+        self.sum_store = torch.empty(n_sum.value, dtype=torch.float32, device=self.device)
+        self.min_store = torch.empty(n_min.value, dtype=torch.float32, device=self.device)
+        self.counters = torch.zeros(n_cnt.value, dtype=torch.int32, device=self.device)
         self.owner = torch.empty(self.capacity, dtype=torch.int32, device=self.device)
         self.state = torch.zeros(64, dtype=torch.uint8, device=self.device)
         self._c = _lib.pb_tree(
-            sum=self.sum.data_ptr(), min=self.min.data_ptr(), owner=self.owner.data_ptr(),
-            state=self.state.data_ptr(), capacity=self.capacity, size=self.size,
+            sum=self.sum_store.data_ptr(), min=self.min_store.data_ptr(), owner=self.owner.data_ptr(),
+            counters=self.counters.data_ptr(), state=self.state.data_ptr(), capacity=self.capacity, size=self.size,
             alpha=self._alpha, eps_f32=self._eps, eps_f64=self._eps,
             weight_eps_in_denominator=int(bool(weight_eps_in_denominator)),
             default_priority_fp64=int(bool(default_priority_fp64)))
@@ -120,10 +127,13 @@ class PrioritizedTree:
                                           self._stream()), "pb_tree_scan")
         return out
 
-    def sample(self, n, u=None, mode=None, beta=None, idx_out=None, weight_out=None, mass_out=None):
-        """Draw n indices.  ``u``: fp64 uniforms in [0,1) (device); drawn inside the kernel (Philox4x32-10
-        keyed by ``seed()``) when omitted."""
-        n = int(n)
+    def sample(self, n, u=None, mode=None, beta=None, idx_out=None, weight_out=None, mass_out=None, n_batches=1):
+        """Draw ``n_batches`` batches of n indices each, all against the current tree (outputs (n_batches * n,),
+        batch-major).  ``u``: fp64 uniforms in [0,1) (device); drawn inside the kernel (Philox4x32-10 keyed by
+        ``seed()``) when omitted.  ``n_batches`` > 1 = batches in flight: write their priorities back with
+        ``update_priority(idx, prio, sorted=False)`` on the concatenation (later batches win)."""
+        batch, n_batches = int(n), int(n_batches)
+        n = batch * n_batches
         if u is not None:
             u = torch.as_tensor(u)
             if u.device != self.device or u.dtype != torch.float64 or not u.is_contiguous():
@@ -134,9 +144,9 @@ class PrioritizedTree:
             weight_out = torch.empty(n, dtype=torch.float32, device=self.device)
         mode = self.mode if mode is None else (self.MODE_STRATIFIED if mode in ("stratified", 1) else self.MODE_IID)
         beta = self._beta if beta is None else float(beta)
-        _lib.check(self._lib.pb_tree_sample(self._ref, n, _lib.ptr(u), mode, beta, idx_out.data_ptr(),
-                                            weight_out.data_ptr(), _lib.ptr(mass_out), self._stream()),
-                   "pb_tree_sample")
+        _lib.check(self._lib.pb_tree_sample_batches(self._ref, n_batches, batch, _lib.ptr(u), mode, beta,
+                                                    idx_out.data_ptr(), weight_out.data_ptr(), _lib.ptr(mass_out),
+                                                    self._stream()), "pb_tree_sample_batches")
         return idx_out, weight_out
 
     def sample_global(self, n_ranks, rank, all_state, n_global, u, beta=None,
@@ -177,7 +187,30 @@ class PrioritizedTree:
 
     def leaves(self):
         """The post-pow fp32 leaf values of slots [0, size): a device view, no copy."""
-        return self.sum[self.capacity:self.capacity + self.size]
+        return self.sum_store[self._leaf_offset:self._leaf_offset + self.size]
+
+    def export(self):
+        """(sum, min): the full level-ordered arrays (2 * capacity floats each; node i has children 2i, 2i+1; leaves at
+        [capacity, 2 * capacity); never-written min leaves +inf) -- what the reference's segment trees hold."""
+        s = torch.empty(2 * self.capacity, dtype=torch.float32, device=self.device)
+        m = torch.empty(2 * self.capacity, dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.pb_tree_export(self._ref, s.data_ptr(), m.data_ptr(), self._stream()), "pb_tree_export")
+        return s, m
+
+    @property
+    def sum(self):
+        return self.export()[0]
+
+    @property
+    def min(self):
+        return self.export()[1]
+
+    def snapshot(self):
+        """Device copies of everything a mutation touches (graph warm-ups that must not disturb the priorities)."""
+        return (self.sum_store.clone(), self.min_store.clone(), self.state.clone())
+
+    def restore(self, snap):
+        self.sum_store.copy_(snap[0]); self.min_store.copy_(snap[1]); self.state.copy_(snap[2])
 
     def len_tensor(self):
         return self.state.view(torch.int64)[0:1]
@@ -187,11 +220,19 @@ class PrioritizedTree:
         return self.state_host()["max_priority"]
 
     def state_dict(self):
-        return {"sum": self.sum.cpu(), "min": self.min.cpu(), "state": self.state.cpu(), "size": self.size,
+        # every node is a deterministic function of the leaves: the leaves + the state block are the whole store
+        return {"leaves": self.leaves().cpu(), "state": self.state.cpu(), "size": self.size,
                 "alpha": self._alpha, "beta": self._beta, "eps": self._eps}
 
     def load_state_dict(self, sd):
         assert sd["size"] == self.size
-        self.sum.copy_(sd["sum"]); self.min.copy_(sd["min"]); self.state.copy_(sd["state"])
+        if "leaves" in sd:
+            leaves = sd["leaves"]
+        else:                                   # checkpoints of the full-heap layout: leaves at [capacity, capacity + size)
+            cap = sd["sum"].numel() // 2
+            leaves = sd["sum"][cap:cap + self.size]
+        self.build(leaves.to(self.device))
+        self.state.copy_(sd["state"])           # len / seq / max_priority / p_sum / p_min / rng as saved
         self.owner.fill_(-1)
+        self.counters.zero_()
         self._beta = sd["beta"]

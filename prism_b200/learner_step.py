@@ -380,7 +380,7 @@ class LearnerStep:
         opt.zero_grad(set_to_none=True)
         # warm-up on a side stream; it must neither train nor disturb the priorities
         snap = opt.snapshot() if flat else None
-        tree_snap = (self.tree.sum.clone(), self.tree.min.clone(), self.tree.state.clone())
+        tree_snap = self.tree.snapshot()
         u_snap = self.u.clone()
         rng = torch.cuda.get_rng_state(self.device)
         side = torch.cuda.Stream(device=self.device)
@@ -391,7 +391,7 @@ class LearnerStep:
         torch.cuda.current_stream(self.device).wait_stream(side)
         if flat:
             opt.restore(snap)
-        self.tree.sum.copy_(tree_snap[0]); self.tree.min.copy_(tree_snap[1]); self.tree.state.copy_(tree_snap[2])
+        self.tree.restore(tree_snap)
         self.u.copy_(u_snap)
         torch.cuda.set_rng_state(rng, self.device)
         self._graph_key = (draw, consume, getattr(self, "_u_in_block", False), self.ring.generation,

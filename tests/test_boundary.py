@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert len(fns) >= 25
     for name in fns:
         assert hasattr(lib, name), name
-    assert lib.pb_abi_version() == 1
+    assert lib.pb_abi_version() == 2
     assert lib.pb_error_string(-1).decode() == "invalid argument"
 
 

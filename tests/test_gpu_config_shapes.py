@@ -91,25 +91,27 @@ def _named_grads(agent):
     return reference_named_grads(agent)
 
 
-def _compare(agent, oracle, out, td, name):
+def _compare(agent, oracle, out, td, name, tol=TOL):
+    errs = {}
     if out["dist"] is not None:
-        assert rel_err(agent._static_distribution_loss.detach().cpu().numpy(), out["dist"].detach().numpy()) < TOL
+        errs["loss.dist"] = rel_err(agent._static_distribution_loss.detach().cpu().numpy(), out["dist"].detach().numpy())
     if out["q"] is not None:
-        assert rel_err(agent._static_q_loss.detach().cpu().numpy(), out["q"].detach().numpy()) < TOL
-    assert rel_err(td.cpu().numpy(), out["td"].numpy()) < TOL
-    assert rel_err(agent._static_total_loss.detach().cpu().numpy(), out["total"].numpy()) < TOL
+        errs["loss.q"] = rel_err(agent._static_q_loss.detach().cpu().numpy(), out["q"].detach().numpy())
+    errs["td"] = rel_err(td.cpu().numpy(), out["td"].numpy())
+    errs["loss.total"] = rel_err(agent._static_total_loss.detach().cpu().numpy(), out["total"].numpy())
     # clip coefficient applied by the fused clip+Adam kernel vs clip_grad_norm_ (the oracle's .grad are already clipped)
     ograds = {k: p.grad for k, p in oracle.model.named_parameters()}
     coef = float(agent.optimizer.norm_out[1])
-    worst = 0.0
     for k, g in _named_grads(agent).items():
-        e = rel_err(g.cpu().numpy() * coef, ograds[k].numpy())
-        worst = max(worst, e)
-        assert e < TOL, "%s: gradient of %s off by %.2e" % (name, k, e)
+        errs["grad." + k] = rel_err(g.cpu().numpy() * coef, ograds[k].numpy())
     osd = oracle.model.state_dict()
     for k, v in agent.model.state_dict().items():
-        assert rel_err(v.cpu().numpy(), osd[k].numpy()) < TOL, "%s: parameter %s after the step" % (name, k)
-    return worst
+        errs["param." + k] = rel_err(v.cpu().numpy(), osd[k].numpy())
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    print("%s: worst errors %s" % (name, ", ".join("%s %.2e" % kv for kv in worst)))
+    bad = [(k, e) for k, e in errs.items() if not e < tol]
+    assert not bad, "%s: %d quantities beyond %.0e, worst %s" % (name, len(bad), tol, worst[:3])
+    return max(e for k, e in errs.items() if k.startswith("grad."))
 
 
 @pytest.mark.parametrize("name", ["configs0", "configs1", "configs4"])
@@ -168,10 +170,13 @@ def _set_static_taus(cfg, agent, taus):
         agent.target_model.distribution_model.set_static_taus(dev[1:])
 
 
-def test_learner_step_graph_at_configs0_shapes_keeps_parity_over_steps():
-    """Three consecutive eager product updates vs three oracle updates at configs[0] shapes: Adam state carries over, so
-    drift between the two implementations would compound here."""
+def test_configs0_parity_holds_over_consecutive_steps():
+    """Three consecutive eager product updates vs three oracle updates at configs[0] shapes: the Adam state carries
+    over, so a systematic difference between the two implementations would compound here.  Parameters are compared by
+    their UPDATE (value - initial value): Adam's step is ~lr per element whatever the gradient's size, so the change of
+    a parameter, not its magnitude, is the scale on which an fp32 rounding difference of a near-zero gradient shows."""
     cfg, agent, oracle, obs_shape, A, B, fs = _build_pair("configs0")
+    init = {k: v.detach().cpu().clone() for k, v in agent.model.state_dict().items()}
     for it in range(3):
         cpu_batch, dev_batch, w = _make_batch(obs_shape, A, B, fs, seed=40 + it)
         taus = _taus(cfg, B, seed=50 + it)
@@ -179,11 +184,15 @@ def test_learner_step_graph_at_configs0_shapes_keeps_parity_over_steps():
         out = oracle.update(cpu_batch, w)
         _inject(cfg, agent, taus)
         td = agent.update(dev_batch, w.to(DEV))
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        _compare(agent, oracle, out, td, "configs0 step %d" % it, tol=3e-4)
     osd = oracle.model.state_dict()
+    frac_off = []
     for k, v in agent.model.state_dict().items():
-        assert rel_err(v.cpu().numpy(), osd[k].numpy()) < 3e-4, k
-    assert rel_err(td.cpu().numpy(), out["td"].numpy()) < 3e-4
+        du, do = (v.cpu() - init[k]).numpy(), (osd[k] - init[k]).numpy()
+        # elements whose 3-step update differs by more than 2 % of the largest update of the tensor
+        frac_off.append(float((np.abs(du - do) > 0.02 * np.abs(do).max()).mean()))
+    assert max(frac_off) < 1e-3, max(frac_off)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -224,6 +233,40 @@ def test_tree_2_24_batch_4096_is_bit_exact_vs_oracle():
     assert np.array_equal(g.min.cpu().numpy()[1:], o.min[1:]), "min tree differs"
     st = g.state_host()
     assert st["max_priority"] == np.float32(o.max_priority) and st["p_sum"] == o.sum[1] and st["p_min"] == o.min[1]
+
+
+@pytest.mark.parametrize("K", [4, 16, 64])
+def test_tree_2_24_batches_in_flight_are_bit_exact_vs_oracle(K):
+    """configs[2] with K batches of 4096 in flight (one sampling launch, one write-back call) against K sequential
+    oracle samples + K sequential oracle updates: indices, whole trees, state."""
+    from oracle.per_oracle import OracleTree
+    from prism_b200 import PrioritizedTree
+    N, B = 1 << 24, 4096
+    rng = np.random.default_rng(240 + K)
+    leaves = np.sqrt(rng.exponential(1.0, N).astype(np.float32) + np.float32(1e-8))
+    g, o = PrioritizedTree(N, device=DEV, mode="stratified"), OracleTree(N)
+    g.build(torch.from_numpy(leaves).to(DEV))
+    o.build(leaves)
+    for rnd in range(2):
+        u = rng.random((K, B))
+        idx, w = g.sample(B, u=torch.from_numpy(u.reshape(-1)).to(DEV), n_batches=K)
+        gi = idx.cpu().numpy().reshape(K, B)
+        newp = rng.exponential(2.0, (K, B)).astype(np.float32)
+        ois = []
+        for b in range(K):
+            oi, ow, _, _, _ = o.sample(u[b], 0.5, mode=1)
+            assert np.array_equal(gi[b], oi), (rnd, b)
+            ois.append(oi)
+        g.update_priority(idx, torch.from_numpy(newp.reshape(-1)).to(DEV), sorted=False)
+        for b in range(K):
+            o.update_priority(ois[b], newp[b])
+    torch.cuda.synchronize()
+    gs, gm = g.export()
+    assert np.array_equal(gs.cpu().numpy()[1:], o.sum[1:]), "sum tree differs"
+    assert np.array_equal(gm.cpu().numpy()[1:], o.min[1:]), "min tree differs"
+    st = g.state_host()
+    assert st["max_priority"] == np.float32(o.max_priority) and st["p_sum"] == o.sum[1] and st["p_min"] == o.min[1]
+    assert int((g.owner != -1).sum()) == 0 and int(g.counters.abs().sum()) == 0
 
 
 @pytest.mark.parametrize("G", [2, 4, 8])

@@ -110,6 +110,7 @@ def test_update_priority_sequences_are_bit_exact(N):
         assert st["max_priority"] == np.float32(o.max_priority)
         assert st["p_sum"] == o.query_sum(0, len(o)) and st["p_min"] == o.query_min(0, len(o))
     assert int((g.owner != -1).sum()) == 0           # dedup scratch left clean
+    assert int(g.counters.abs().sum()) == 0          # arrival counters of the one-launch update back at zero
 
 
 @pytest.mark.parametrize("N", [100, 1000, 70_000])
@@ -286,3 +287,95 @@ def test_device_philox_uniforms():
     big, _ = a.sample(1 << 16)                                 # thread-per-sample kernel, same generator
     assert int(big.min()) >= 0 and int(big.max()) < N and bool((big[1:] >= big[:-1]).all())
     assert a.state_host()["status"] == 0
+
+
+@pytest.mark.parametrize("N", [1 << 15, 1 << 20, (1 << 21) + 77])
+@pytest.mark.parametrize("kind", ["onehot", "cluster", "one_line", "spread", "padded"])
+def test_one_launch_sorted_update_adversarial_runs(N, kind):
+    """The single-launch sorted update (leaders, arrival counters, last-CTA top) on index sets that stress it: every
+    entry on ONE leaf (a run of 4096 duplicates), all entries inside one 1024-leaf line of the level above, a few dense
+    clusters, an even spread, and a batch whose tail is -1 padding rows (sharded sampling)."""
+    rng = np.random.default_rng(N % 1000 + len(kind))
+    g, o = _trees(N, mode="stratified")
+    g.extend(N); o.extend(N)
+    B = 4096
+    if kind == "onehot":
+        idx = np.full(B, N // 3, np.int64)
+    elif kind == "cluster":
+        centers = rng.integers(0, N - 64, 7)
+        idx = np.sort((centers[rng.integers(0, 7, B)] + rng.integers(0, 64, B)).astype(np.int64))
+    elif kind == "one_line":
+        base = (N // 2048) * 1024
+        idx = np.sort(base + rng.integers(0, 1024, B)).astype(np.int64)
+    else:
+        idx = np.sort(rng.integers(0, N, B)).astype(np.int64)
+    prio = rng.exponential(2.0, B).astype(np.float32)
+    gi = idx.copy()
+    if kind == "padded":
+        gi[-300:] = -1
+        idx, oprio = idx[:-300], prio[:-300]
+    else:
+        oprio = prio
+    for _ in range(2):                                  # twice: the counters must come back to zero in between
+        g.update_priority(torch.from_numpy(gi).to(DEV), torch.from_numpy(prio).to(DEV), sorted=True)
+        o.update_priority(idx, oprio)
+        _assert_same_tree(g, o)
+        assert int(g.counters.abs().sum()) == 0
+        st = g.state_host()
+        assert st["max_priority"] == np.float32(o.max_priority)
+        assert st["p_sum"] == o.query_sum(0, len(o)) and st["p_min"] == o.query_min(0, len(o))
+        prio = prio[::-1].copy()
+        oprio = prio[:len(idx)] if kind == "padded" else prio
+
+
+@pytest.mark.parametrize("N,B", [(1 << 20, 4096), (1 << 22, 1024), (50_000, 256)])
+@pytest.mark.parametrize("K", [1, 4, 16])
+def test_batches_in_flight_equal_sequential_reference_calls(N, B, K):
+    """K batches sampled in ONE launch against the same tree == K reference sample() calls with no update in
+    between; writing all K*B priorities back in ONE call == K successive update_priority calls (later batches win)."""
+    rng = np.random.default_rng(K * 7 + B)
+    prio0 = rng.exponential(1.0, N).astype(np.float32)
+    g, o = _trees(N, mode="stratified")
+    g.extend(N); o.extend(N)
+    g.update_priority(torch.arange(N, device=DEV), torch.from_numpy(prio0).to(DEV), sorted=True)
+    o.update_priority(np.arange(N), prio0)
+    for rnd in range(2):
+        u = rng.random((K, B))
+        mass = torch.empty(K * B, dtype=torch.float32, device=DEV)
+        idx, w = g.sample(B, u=torch.from_numpy(u.reshape(-1)).to(DEV), n_batches=K, mass_out=mass)
+        newp = rng.exponential(2.0, (K, B)).astype(np.float32)
+        ois = []
+        for b in range(K):
+            oi, ow, om, _, _ = o.sample(u[b], 0.5, mode=1)
+            assert np.array_equal(idx[b * B:(b + 1) * B].cpu().numpy(), oi), (rnd, b)
+            assert np.array_equal(mass[b * B:(b + 1) * B].cpu().numpy(), om)
+            assert np.allclose(w[b * B:(b + 1) * B].cpu().numpy(), ow, rtol=1e-6, atol=0)
+            ois.append(oi)
+        g.update_priority(idx, torch.from_numpy(newp.reshape(-1)).to(DEV), sorted=(K == 1))
+        for b in range(K):
+            o.update_priority(ois[b], newp[b])
+        _assert_same_tree(g, o)
+        st = g.state_host()
+        assert st["max_priority"] == np.float32(o.max_priority) and st["p_sum"] == o.sum[1] and st["p_min"] == o.min[1]
+
+
+def test_checkpoint_round_trip_and_legacy_heap_format():
+    from prism_b200 import PrioritizedTree
+    N = 70_000
+    rng = np.random.default_rng(3)
+    g, o = _trees(N)
+    g.extend(50_000); o.extend(50_000)
+    idx = rng.integers(0, 50_000, 4096)
+    prio = rng.exponential(2.0, 4096).astype(np.float32)
+    g.update_priority(torch.from_numpy(idx).to(DEV), torch.from_numpy(prio).to(DEV))
+    o.update_priority(idx, prio)
+    sd = g.state_dict()
+    h = PrioritizedTree(N, device=DEV)
+    h.load_state_dict(sd)
+    _assert_same_tree(h, o)
+    assert h.state_host() == g.state_host()
+    legacy = {"sum": torch.from_numpy(o.sum.copy()), "min": torch.from_numpy(o.min.copy()), "state": sd["state"],
+              "size": N, "alpha": 0.5, "beta": 0.5, "eps": 1e-8}
+    h2 = PrioritizedTree(N, device=DEV)
+    h2.load_state_dict(legacy)
+    _assert_same_tree(h2, o)
