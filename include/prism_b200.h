@@ -534,6 +534,43 @@ int pb_wire_array_header(long long n, unsigned char *out, long long *written);
 int pb_wire_pack_numbers(const void *src, int dtype, long long n, unsigned char *out, long long cap, long long *written);
 int pb_wire_index_timesteps(const double *flat, long long n, long long max_records, long long *rec, long long *n_rec);
 
+/* ------------------------------------------------------------------------- *
+ * Grouped LayerNorm (csrc/ln.cu): `groups` affine pairs, gamma / beta (groups, F).  Output row r of
+ * groups * rows_per_group rows normalises input row r % x_rows with the pair r / rows_per_group.  K ensemble heads on
+ * one shared embedding (prism/agents/models/q_ensemble.py:26-48: every head starts with its own LayerNorm):
+ * groups = K, x_rows = rows_per_group = B.  Backward: dx per OUTPUT row (sum it over the heads with pb_sum_heads
+ * when the input is shared); partials = 2 * groups * pb_layer_norm_grouped_bwd_blocks() * F floats of scratch.
+ * ------------------------------------------------------------------------- */
+int pb_layer_norm_grouped_fwd(int groups, long long rows_per_group, long long x_rows, int F, float eps, const float *x,
+                              const float *gamma, const float *beta, float *y, float *mean_out, float *rstd_out,
+                              void *stream);
+int pb_layer_norm_grouped_bwd_blocks(int groups, long long rows_per_group, int F);
+int pb_layer_norm_grouped_bwd(int groups, long long rows_per_group, long long x_rows, int F, const float *x,
+                              const float *dy, const float *gamma, const float *mean, const float *rstd, float *dx,
+                              float *dgamma, float *dbeta, float *partials, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Narrow dense layer (csrc/narrow.cu): y (M x N) = x (M x J) . W^T (N x J) + bias with N <= 32 outputs -- the
+ * n_actions-wide output layer of the IQN head on (T*B) rows (prism/agents/models/iqn_model.py:42-46, autograd of
+ * nn.Linear).  One streaming pass over x forward; backward reads x once, writes dx once, and combines per-CTA
+ * partials of dW / db in a fixed order.  partials: pb_narrow_linear_bwd_blocks(M) * (N * J + N) floats.
+ * ------------------------------------------------------------------------- */
+int pb_narrow_linear_supported(long long M, int N, int J);
+int pb_narrow_linear_bwd_blocks(long long M);
+int pb_narrow_linear_fwd(long long M, int N, int J, const float *x, const float *w, const float *bias, float *y,
+                         void *stream);
+int pb_narrow_linear_bwd(long long M, int N, int J, const float *x, const float *w, const float *dy, float *dx,
+                         float *dW, float *db, float *partials, void *stream);
+
+/* out[i] = sum_k in[k][i], i < n (n % 4 == 0): gradients of an input shared by K heads (q_ensemble.py:44-48) */
+int pb_sum_heads(int K, long long n, const float *in, float *out, void *stream);
+
+/* IQN quantile draw + cosine basis in one launch (prism/agents/models/iqn_model.py:64-66, 89-92): tau_out (n_rows)
+ * ~ U[0,1) from Philox4x32-10 keyed by rng[0] with counter (row, rng[1]); out (n_rows, n_basis) = cos(pi i tau).
+ * rng: device long long[4] = {seed, call number, ticket, unused}; the call number advances once per launch, so a
+ * replayed CUDA graph draws fresh quantiles. */
+int pb_iqn_draw_cos_basis(long long n_rows, int n_basis, long long *rng, float *tau_out, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,21 @@ class Agent(object):
         g.replay()
         return static_out.clone()
 
+    # ---- device generators of the IQN heads (quantile draws): graph warm-ups must not advance them --------------
+    def quantile_rng_snapshot(self):
+        out = []
+        for m in (self.model, self.target_model):
+            d = getattr(m, "distribution_model", None) if m is not None else None
+            rng = getattr(d, "_rng", None) if d is not None else None
+            if rng is not None:
+                out.append((rng, rng.clone()))
+        return out
+
+    @staticmethod
+    def quantile_rng_restore(snap):
+        for rng, saved in snap:
+            rng.copy_(saved)
+
     # ---- learning -----------------------------------------------------------------------
     def update(self, batch, per_weights=1):
         self.train()
@@ -171,6 +186,11 @@ class Agent(object):
         self._static_total_loss = self._static_distribution_loss = self._static_q_loss = None
         self.optimizer.zero_grad(set_to_none=True)
         rng_state = torch.cuda.get_rng_state(dev)
+        for m in (self.model, self.target_model):              # make the IQN generators exist before they are snapshotted
+            d = getattr(m, "distribution_model", None) if m is not None else None
+            if d is not None and hasattr(d, "_rng_state"):
+                d._rng_state()
+        q_rng = self.quantile_rng_snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -181,6 +201,7 @@ class Agent(object):
         if flat:
             self.optimizer.restore(snap)                         # warm-up must not train
         torch.cuda.set_rng_state(rng_state, dev)
+        self.quantile_rng_restore(q_rng)
 
         self._learn_cuda_graph = torch.cuda.CUDAGraph()
         self.optimizer.zero_grad(set_to_none=True)

@@ -98,10 +98,14 @@ class IQNModel(nn.Module):
             if quantiles.numel() != n * n_rows:
                 raise ValueError("static quantiles hold %d draws, this forward needs %d" % (quantiles.numel(), n * n_rows))
         else:
-            # same shape and dtype as the reference draw (:64-66), from the device generator
-            quantiles = torch.rand([n * n_rows, 1], device=self.device).float()
+            quantiles = None
 
-        basis = ops.cos_basis(quantiles, self.n_basis_elements)            # (n*rows, n_basis)
+        if quantiles is None:
+            # same shape and dtype as the reference draw (:64-66), drawn by this library's Philox generator in the
+            # same launch that builds the cosine basis (seeded from torch's seed at first use)
+            quantiles, basis = ops.draw_cos_basis(n * n_rows, self.n_basis_elements, self._rng_state())
+        else:
+            basis = ops.cos_basis(quantiles, self.n_basis_elements)        # (n*rows, n_basis)
         # phi(tau) (.) x with quantile-major rows (r = q*rows + b): the state embedding is broadcast over q inside
         # the phi GEMM's epilogue (large layers) or by a broadcasting multiply (small ones)
         h = ops.phi_times_x(self.phi, basis, x, n)
@@ -112,6 +116,14 @@ class IQNModel(nn.Module):
         if for_action:
             return z.view(n, -1, self.n_actions)
         return z, quantiles
+
+    def _rng_state(self):
+        rng = getattr(self, "_rng", None)
+        if rng is None or rng.device != torch.device(self.device):
+            IQNModel._n_generators = getattr(IQNModel, "_n_generators", 0) + 1
+            seed = (torch.initial_seed() * 2654435761 + IQNModel._n_generators * 40503) & 0x7FFFFFFF
+            rng = self._rng = torch.tensor([seed, 0, 0, 0], dtype=torch.int64, device=self.device)
+        return rng
 
     def _embed_quantiles(self, quantiles):
         return ops.run_sequential(self.phi, ops.cos_basis(quantiles, self.n_basis_elements))

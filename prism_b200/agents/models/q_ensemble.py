@@ -109,9 +109,7 @@ class QEnsemble(nn.Module):
             kind, si = plan[i]
             if kind == "ln":
                 w, b = self._p(si, "weight"), self._p(si, "bias")
-                src = x if h is None else h
-                normed = F.layer_norm(src, (src.shape[-1],))            # statistics are head-independent for x
-                h = torch.addcmul(b.unsqueeze(1), normed if h is not None else normed.unsqueeze(0), w.unsqueeze(1))
+                h = ops.layer_norm_heads(x if h is None else h, w, b)   # K heads, one launch (shared x: stats per row)
             elif kind == "linear":
                 w, b = self._p(si, "weight"), self._p(si, "bias")        # (K, out, in), (K, out)
                 fuse = i + 1 < n and plan[i + 1][0] == "act" and isinstance(self.act, nn.ReLU)

@@ -47,6 +47,31 @@ def cos_basis(tau, n_basis):
     return out
 
 
+def draw_cos_basis(n_rows, n_basis, rng):
+    """tau ~ U[0,1) drawn on the device + its cosine basis, one launch (pb_iqn_draw_cos_basis).  ``rng``: int64[4]
+    device tensor {seed, call number, ticket, -}.  Returns (tau (n_rows, 1), basis (n_rows, n_basis))."""
+    _lib.require_cuda(rng, "rng")
+    tau = torch.empty(n_rows, 1, dtype=torch.float32, device=rng.device)
+    out = torch.empty(n_rows, n_basis, dtype=torch.float32, device=rng.device)
+    _lib.check(_lib.load().pb_iqn_draw_cos_basis(int(n_rows), int(n_basis), rng.data_ptr(), tau.data_ptr(), out.data_ptr(),
+                                                 _stream(rng)), "pb_iqn_draw_cos_basis")
+    return tau, out
+
+
+def sum_leading(x):
+    """x (K, ...) -> sum over the leading axis, fixed order (pb_sum_heads)."""
+    K = x.shape[0]
+    n = x[0].numel()
+    if K == 1:
+        return x[0]
+    if n % 4 != 0 or not x.is_contiguous():
+        ROUTES["fallthrough:sum"] += 1
+        return x.sum(dim=0)
+    out = torch.empty(x.shape[1:], dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().pb_sum_heads(int(K), int(n), x.data_ptr(), out.data_ptr(), _stream(x)), "pb_sum_heads")
+    return out
+
+
 class _QuantileHuberLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z_cur, tau, z_next_online, z_next_target, action, ret, gdn, B, T, Tp, kappa, loss_weight):
@@ -345,6 +370,47 @@ class _LinearTC(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class _NarrowLinear(torch.autograd.Function):
+    """y = x W^T + b for a handful of outputs (the n_actions-wide layer of the IQN head on (T*B) rows): one streaming
+    pass forward, one backward (csrc/narrow.cu) instead of library SGEMMs with 64-wide tiles."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        M, J = x.shape
+        N = w.shape[0]
+        xc, wc, bc = _c(x), _c(w), (None if b is None else _c(b))
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().pb_narrow_linear_fwd(M, N, J, xc.data_ptr(), wc.data_ptr(), _lib.ptr(bc), y.data_ptr(),
+                                                    _stream(x)), "pb_narrow_linear_fwd")
+        ctx.save_for_backward(xc, wc)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, wc = ctx.saved_tensors
+        M, J = xc.shape
+        N = wc.shape[0]
+        dy = _c(dy)
+        lib = _lib.load()
+        want_dx, want_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        dx = torch.empty_like(xc) if want_dx else None
+        dw = torch.empty_like(wc) if want_dw else None
+        db = torch.empty(N, dtype=torch.float32, device=dy.device) if want_db else None
+        partials = None
+        if want_dw or want_db:
+            partials = torch.empty(lib.pb_narrow_linear_bwd_blocks(M) * (N * J + N), dtype=torch.float32, device=dy.device)
+        _lib.check(lib.pb_narrow_linear_bwd(M, N, J, xc.data_ptr(), wc.data_ptr(), dy.data_ptr(), _lib.ptr(dx), _lib.ptr(dw),
+                                            _lib.ptr(db), _lib.ptr(partials), _stream(dy)), "pb_narrow_linear_bwd")
+        return dx, dw, db
+
+
+def _narrow_eligible(x, weight):
+    return (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.shape[0] > FUSED_LINEAR_MAX_ROWS
+            and _lib.load().pb_narrow_linear_supported(x.shape[0], weight.shape[0], weight.shape[1]) == 1)
+
+
 TENSOR_CORE_LINEAR = True      # module switch for A/B timing
 TC_MIN_ROWS = 256              # an M = 128 tile needs rows to fill it
 TC_MIN_FLOPS = float(__import__('os').environ.get('PB_TC_MIN_FLOPS', 2.0e8))           # below this a layer is launch-bound and stays on the fused SIMT kernel / library
@@ -394,7 +460,7 @@ class _PhiTimesX(torch.autograd.Function):
             dw = torch.empty(F_, J, dtype=torch.float32, device=dh.device)
             # dW (F x J) = dpre^T (F x M) . basis (M x J): both operands read as transposes
             tc_gemm(dw, dpre, 1, F_, 0, basis_c, 1, J, 0, 1, F_, J, M)
-        db = dbp.sum(dim=0) if ctx.needs_input_grad[2] else None
+        db = sum_leading(dbp) if ctx.needs_input_grad[2] else None
         return None, dw, db, dx
 
 
@@ -408,7 +474,7 @@ def phi_times_x(phi_seq, basis, x, n):
             and x.dim() == 2 and x.shape[1] == F_ and (F_ % 4) == 0 and _tc_eligible(x, M, 1, F_, J)):
         ROUTES["phi_x:tc_gemm"] += 1
         return _PhiTimesX.apply(basis, lin.weight, lin.bias, x)
-    ROUTES["phi_x:unfused"] += 1
+    ROUTES["fallthrough:phi_x_mul"] += 1                      # small layers (the reference-golden shapes): ATen broadcast multiply
     phi = run_sequential(phi_seq, basis)
     return (phi.view(n, x.shape[0], -1) * x.unsqueeze(0)).view(n * x.shape[0], -1)
 
@@ -432,6 +498,9 @@ def linear(x, weight, bias, relu=False):
     """nn.Linear (+ optional fused ReLU) on a 2-D input through the fused kernel."""
     # narrow output layers (a handful of actions) of a few thousand rows stay on the fused FFMA kernel: the library picks
     # 64-wide tiles for them (25 us for the 3 x 256 weight gradient of configs[0])
+    if not relu and _narrow_eligible(x, weight):
+        ROUTES["linear:narrow"] += 1
+        return _NarrowLinear.apply(x, weight, bias)
     narrow = weight.shape[0] <= NARROW_OUT and x.shape[0] <= NARROW_MAX_ROWS
     if x.shape[0] > FUSED_LINEAR_MAX_ROWS and not narrow:
         if _tc_eligible(x, x.shape[0], 1, *weight.shape):
@@ -447,54 +516,80 @@ def linear(x, weight, bias, relu=False):
 
 
 class _LayerNorm(torch.autograd.Function):
-    """nn.LayerNorm over the last dimension of a 2-D activation: one streaming pass forward, ONE pass backward
-    (csrc/ln.cu) instead of ATen's grad_input + GammaBeta kernels."""
+    """nn.LayerNorm over the last dimension: one streaming pass forward, ONE pass backward (csrc/ln.cu) instead of
+    ATen's grad_input + GammaBeta kernels.  Grouped form: ``groups`` affine pairs (weight / bias (groups, F)); output row
+    r of groups * rows_per_group rows normalises input row r % x_rows -- the K ensemble heads, each starting with its own
+    LayerNorm on the SHARED embedding (q_ensemble.py:26-48), are one launch instead of F.layer_norm + addcmul."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps):
-        rows, F_ = x.shape
+    def forward(ctx, x, weight, bias, eps, groups):
         xc = _c(x)
+        F_ = xc.shape[-1]
+        x_rows = xc.numel() // F_
+        shared = groups > 1 and xc.dim() == 2                    # (B, F) shared by the heads -> (K, B, F)
+        rpg = x_rows if (groups == 1 or shared) else x_rows // groups
+        rows = groups * rpg
         need = any(ctx.needs_input_grad[:3])
-        y = torch.empty_like(xc)
+        y = torch.empty((groups, rpg, F_) if groups > 1 else xc.shape, dtype=torch.float32, device=x.device)
         mean = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
         wc = None if weight is None else _c(weight)
         bc = None if bias is None else _c(bias)
-        _lib.check(_lib.load().pb_layer_norm_fwd(rows, F_, float(eps), xc.data_ptr(), _lib.ptr(wc), _lib.ptr(bc), y.data_ptr(),
-                                                 _lib.ptr(mean), _lib.ptr(rstd), _stream(x)), "pb_layer_norm_fwd")
+        _lib.check(_lib.load().pb_layer_norm_grouped_fwd(int(groups), int(rpg), int(x_rows), F_, float(eps), xc.data_ptr(),
+                                                         _lib.ptr(wc), _lib.ptr(bc), y.data_ptr(), _lib.ptr(mean),
+                                                         _lib.ptr(rstd), _stream(x)), "pb_layer_norm_grouped_fwd")
         if need:
             ctx.save_for_backward(xc, wc, mean, rstd)
             ctx.has_affine = (weight is not None, bias is not None)
+            ctx.meta = (int(groups), int(rpg), int(x_rows), F_, shared)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         xc, wc, mean, rstd = ctx.saved_tensors
-        rows, F_ = xc.shape
+        groups, rpg, x_rows, F_, shared = ctx.meta
         dy = _c(dy)
         lib = _lib.load()
-        nb = lib.pb_layer_norm_bwd_blocks(rows, F_)
-        partials = torch.empty(2 * nb * F_, dtype=torch.float32, device=dy.device)
-        dx = torch.empty_like(xc)
-        dg = torch.empty(F_, dtype=torch.float32, device=dy.device) if ctx.has_affine[0] else None
-        db = torch.empty(F_, dtype=torch.float32, device=dy.device) if ctx.has_affine[1] else None
-        _lib.check(lib.pb_layer_norm_bwd(rows, F_, xc.data_ptr(), dy.data_ptr(), _lib.ptr(wc), mean.data_ptr(), rstd.data_ptr(),
-                                         dx.data_ptr(), _lib.ptr(dg), _lib.ptr(db), partials.data_ptr(), _stream(dy)),
-                   "pb_layer_norm_bwd")
-        return dx, dg, db, None
+        nb = lib.pb_layer_norm_grouped_bwd_blocks(groups, rpg, F_)
+        partials = torch.empty(2 * groups * nb * F_, dtype=torch.float32, device=dy.device)
+        dx = torch.empty((groups, rpg, F_) if groups > 1 else xc.shape, dtype=torch.float32, device=dy.device)
+        shape_p = (groups, F_) if groups > 1 else (F_,)
+        dg = torch.empty(shape_p, dtype=torch.float32, device=dy.device) if ctx.has_affine[0] else None
+        db = torch.empty(shape_p, dtype=torch.float32, device=dy.device) if ctx.has_affine[1] else None
+        _lib.check(lib.pb_layer_norm_grouped_bwd(groups, rpg, x_rows, F_, xc.data_ptr(), dy.data_ptr(), _lib.ptr(wc),
+                                                 mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), _lib.ptr(dg), _lib.ptr(db),
+                                                 partials.data_ptr(), _stream(dy)), "pb_layer_norm_grouped_bwd")
+        if not ctx.needs_input_grad[0]:
+            dx = None
+        elif shared:
+            dx = sum_leading(dx)                                  # the heads share their input
+        return dx, dg, db, None, None
 
 
-LN_MIN_ELEMENTS = 1 << 20      # below this ATen's kernels are launch-bound either way
+def _ln_supported(x, F_):
+    return (x.is_cuda and x.dtype == torch.float32 and x.numel() > 0
+            and _lib.load().pb_layer_norm_supported(x.numel() // F_, F_) == 1)
 
 
 def layer_norm(x, module):
-    """nn.LayerNorm module applied through the fused kernels when the activation is large."""
-    if (x.is_cuda and x.dim() == 2 and len(module.normalized_shape) == 1 and x.dtype == torch.float32
-            and x.numel() >= LN_MIN_ELEMENTS and _lib.load().pb_layer_norm_supported(x.shape[0], x.shape[1])):
+    """nn.LayerNorm module applied through the fused kernels (any number of rows)."""
+    if x.dim() == 2 and len(module.normalized_shape) == 1 and _ln_supported(x, x.shape[1]):
         ROUTES["ln:fused"] += 1
-        return _LayerNorm.apply(x, module.weight, module.bias, module.eps)
+        return _LayerNorm.apply(x, module.weight, module.bias, module.eps, 1)
     ROUTES["fallthrough:nn.LayerNorm"] += 1
     return module(x)
+
+
+def layer_norm_heads(x, weight, bias, eps=1e-5):
+    """LayerNorm with per-head affine parameters weight / bias (K, F): x (B, F) shared by the heads or (K, B, F)
+    -> (K, B, F)."""
+    K, F_ = weight.shape
+    if _ln_supported(x, F_) and (x.dim() == 2 or (x.dim() == 3 and x.shape[0] == K)):
+        ROUTES["ln:fused_heads"] += 1
+        return _LayerNorm.apply(x, weight, bias, eps, K)
+    ROUTES["fallthrough:F.layer_norm+addcmul"] += 1
+    normed = torch.nn.functional.layer_norm(x, (F_,), eps=eps)
+    return torch.addcmul(bias.unsqueeze(1), normed if x.dim() == 3 else normed.unsqueeze(0), weight.unsqueeze(1))
 
 
 def run_sequential(seq, x):

@@ -53,16 +53,20 @@ __device__ __forceinline__ float2 row_sum2(float a, float b, float2 *scratch2)
 // TPR threads per row (32: one warp, 8 rows per CTA; 256: one CTA), SLOTS float4 per thread
 template <int TPR, int SLOTS>
 __global__ void __launch_bounds__(LN_THREADS) ln_fwd_kernel(long long rows, int F4, float eps, const float4 *__restrict__ x,
-                                                            const float4 *__restrict__ gamma, const float4 *__restrict__ beta,
+                                                            long long x_rows, const float4 *__restrict__ gamma,
+                                                            const float4 *__restrict__ beta, long long group_rows,
                                                             float4 *__restrict__ y, float *__restrict__ mean_out,
                                                             float *__restrict__ rstd_out)
 {
+    // output row r normalises input row r % x_rows (K heads sharing one input) with the affine pair of group
+    // r / group_rows (stacked (K, F) parameters of the ensemble heads); plain LayerNorm: x_rows = group_rows = rows
     __shared__ float scratch[LN_THREADS / 32];
     constexpr int RPC = LN_THREADS / TPR;
     const int lr = threadIdx.x % TPR, grp = threadIdx.x / TPR;
     const float inv_f = 1.0f / (float)(F4 * 4);
     for (long long row = (long long)blockIdx.x * RPC + grp; row < rows; row += (long long)gridDim.x * RPC) {
-        const float4 *xr = x + row * F4;
+        const float4 *xr = x + (row % x_rows) * F4;
+        const long long gofs = (row / group_rows) * F4;
         float4 v[SLOTS];
         float s = 0.f;
 #pragma unroll
@@ -90,8 +94,8 @@ __global__ void __launch_bounds__(LN_THREADS) ln_fwd_kernel(long long rows, int 
         for (int k = 0; k < SLOTS; ++k) {
             const int c = lr + k * TPR;
             if (c < F4) {
-                const float4 g = gamma ? __ldg(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
-                const float4 b = beta ? __ldg(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 g = gamma ? __ldg(gamma + gofs + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+                const float4 b = beta ? __ldg(beta + gofs + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                 float4 o;
                 o.x = (v[k].x - mean) * rstd * g.x + b.x;
                 o.y = (v[k].y - mean) * rstd * g.y + b.y;
@@ -112,6 +116,7 @@ __global__ void __launch_bounds__(LN_THREADS) ln_fwd_kernel(long long rows, int 
 // part_g[blockIdx][F], part_b[blockIdx][F]: this CTA's sums over its rows of dy * xhat and dy
 template <int TPR, int SLOTS>
 __global__ void __launch_bounds__(LN_THREADS, (TPR == 256 ? 3 : 1)) ln_bwd_kernel(long long rows, int F4, const float4 *__restrict__ x,
+                                                            long long x_rows,
                                                             const float4 *__restrict__ dy, const float4 *__restrict__ gamma,
                                                             const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
                                                             float4 *__restrict__ dx, float4 *__restrict__ part_g,
@@ -125,11 +130,18 @@ __global__ void __launch_bounds__(LN_THREADS, (TPR == 256 ? 3 : 1)) ln_bwd_kerne
     float4 ag[SLOTS], ab[SLOTS];
 #pragma unroll
     for (int k = 0; k < SLOTS; ++k) ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // grid.y = affine groups (rows = rows PER GROUP; group g covers output rows [g * rows, (g + 1) * rows)); the
+    // partial sums of a CTA belong to one group.  Output row r reads input row r % x_rows.
+    const long long row0 = (long long)blockIdx.y * rows;
+    const size_t pblock = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    if (gamma) gamma += (size_t)blockIdx.y * F4;
     // every thread of a CTA must take the same number of trips when the row reduction uses __syncthreads
     const long long trips = (rows + (long long)gridDim.x * RPC - 1) / ((long long)gridDim.x * RPC);
     for (long long it = 0; it < trips; ++it) {
-        const long long row = (it * gridDim.x + blockIdx.x) * RPC + grp;
-        const bool live = row < rows;
+        const long long lrow = (it * gridDim.x + blockIdx.x) * RPC + grp;
+        const bool live = lrow < rows;
+        const long long row = row0 + lrow;
+        const long long xrow = row % x_rows;
         const float mean = live ? mean_in[row] : 0.f, rstd = live ? rstd_in[row] : 0.f;
         float4 xh[SLOTS], g[SLOTS];
         float s1 = 0.f, s2 = 0.f;
@@ -138,7 +150,7 @@ __global__ void __launch_bounds__(LN_THREADS, (TPR == 256 ? 3 : 1)) ln_bwd_kerne
             const int c = lr + k * TPR;
             xh[k] = g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (live && c < F4) {
-                const uint4 xu = ldg_stream(reinterpret_cast<const uint4 *>(x + row * F4 + c));
+                const uint4 xu = ldg_stream(reinterpret_cast<const uint4 *>(x + xrow * F4 + c));
                 const uint4 du = ldg_stream(reinterpret_cast<const uint4 *>(dy + row * F4 + c));
                 const float4 d = make_float4(__uint_as_float(du.x), __uint_as_float(du.y), __uint_as_float(du.z), __uint_as_float(du.w));
                 xh[k].x = (__uint_as_float(xu.x) - mean) * rstd; xh[k].y = (__uint_as_float(xu.y) - mean) * rstd;
@@ -189,16 +201,16 @@ __global__ void __launch_bounds__(LN_THREADS, (TPR == 256 ? 3 : 1)) ln_bwd_kerne
         }
         __syncthreads();
         for (int c = threadIdx.x; c < F4; c += LN_THREADS) {
-            part_g[(size_t)blockIdx.x * F4 + c] = colsum[c];
-            part_b[(size_t)blockIdx.x * F4 + c] = colsum[F4 + c];
+            part_g[pblock * F4 + c] = colsum[c];
+            part_b[pblock * F4 + c] = colsum[F4 + c];
         }
     } else {
 #pragma unroll
         for (int k = 0; k < SLOTS; ++k) {
             const int c = lr + k * TPR;
             if (c < F4) {
-                part_g[(size_t)blockIdx.x * F4 + c] = ag[k];
-                part_b[(size_t)blockIdx.x * F4 + c] = ab[k];
+                part_g[pblock * F4 + c] = ag[k];
+                part_b[pblock * F4 + c] = ab[k];
             }
         }
     }
@@ -211,6 +223,10 @@ __global__ void __launch_bounds__(1024) ln_colreduce_kernel(int nblocks, int F, 
                                                             float *__restrict__ dbeta)
 {
     __shared__ float sg[32][33], sb[32][33];
+    part_g += (size_t)blockIdx.y * nblocks * F;                 // grid.y = affine groups
+    part_b += (size_t)blockIdx.y * nblocks * F;
+    if (dgamma) dgamma += (size_t)blockIdx.y * F;
+    if (dbeta) dbeta += (size_t)blockIdx.y * F;
     const int c = blockIdx.x * 32 + threadIdx.x, r = threadIdx.y;
     float a = 0.f, b = 0.f;
     if (c < F) {
@@ -245,12 +261,15 @@ extern "C" {
 
 int pb_layer_norm_supported(long long rows, int F) { return (rows > 0 && F >= 4 && (F % 4) == 0 && F <= 4096) ? 1 : 0; }
 
-int pb_layer_norm_bwd_blocks(long long rows, int F) { return ln_grid(rows, F <= 1024 ? LN_THREADS / 32 : 1); }
-
-int pb_layer_norm_fwd(long long rows, int F, float eps, const float *x, const float *gamma, const float *beta, float *y,
-                      float *mean_out, float *rstd_out, void *stream)
+// Grouped form: `groups` affine pairs (gamma / beta are (groups, F)); output row r of `groups * rows_per_group` rows
+// normalises input row r % x_rows and uses the affine pair r / rows_per_group.  Plain LayerNorm: groups = 1,
+// x_rows = rows.  K ensemble heads on one shared input: groups = K, x_rows = rows_per_group = B.
+int pb_layer_norm_grouped_fwd(int groups, long long rows_per_group, long long x_rows, int F, float eps, const float *x,
+                              const float *gamma, const float *beta, float *y, float *mean_out, float *rstd_out,
+                              void *stream)
 {
-    if (!pb_layer_norm_supported(rows, F) || !x || !y) return PB_E_ARG;
+    const long long rows = (long long)groups * rows_per_group;
+    if (groups < 1 || rows_per_group < 1 || x_rows < 1 || !pb_layer_norm_supported(rows, F) || !x || !y) return PB_E_ARG;
     if ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)gamma) | ((uintptr_t)beta)) & 15) return PB_E_ARG;
     const int F4 = F / 4;
     const float4 *x4 = reinterpret_cast<const float4 *>(x), *g4 = reinterpret_cast<const float4 *>(gamma),
@@ -258,40 +277,70 @@ int pb_layer_norm_fwd(long long rows, int F, float eps, const float *x, const fl
     float4 *y4 = reinterpret_cast<float4 *>(y);
     if (F <= 512) {
         const int nb = (int)((rows + 7) / 8);
-        PB_LAUNCH((ln_fwd_kernel<32, 4>), nb, LN_THREADS, 0, stream, rows, F4, eps, x4, g4, b4, y4, mean_out, rstd_out);
+        PB_LAUNCH((ln_fwd_kernel<32, 4>), nb, LN_THREADS, 0, stream, rows, F4, eps, x4, x_rows, g4, b4, rows_per_group, y4, mean_out, rstd_out);
     } else if (F <= 1024) {
         const int nb = (int)((rows + 7) / 8);
-        PB_LAUNCH((ln_fwd_kernel<32, 8>), nb, LN_THREADS, 0, stream, rows, F4, eps, x4, g4, b4, y4, mean_out, rstd_out);
+        PB_LAUNCH((ln_fwd_kernel<32, 8>), nb, LN_THREADS, 0, stream, rows, F4, eps, x4, x_rows, g4, b4, rows_per_group, y4, mean_out, rstd_out);
     } else {
         long long nb = rows;
         if (nb > (1LL << 30)) return PB_E_ARG;
-        PB_LAUNCH((ln_fwd_kernel<256, 4>), (unsigned)nb, LN_THREADS, 0, stream, rows, F4, eps, x4, g4, b4, y4, mean_out, rstd_out);
+        PB_LAUNCH((ln_fwd_kernel<256, 4>), (unsigned)nb, LN_THREADS, 0, stream, rows, F4, eps, x4, x_rows, g4, b4, rows_per_group, y4, mean_out, rstd_out);
     }
     return PB_OK;
 }
+
+int pb_layer_norm_fwd(long long rows, int F, float eps, const float *x, const float *gamma, const float *beta, float *y,
+                      float *mean_out, float *rstd_out, void *stream)
+{
+    return pb_layer_norm_grouped_fwd(1, rows, rows, F, eps, x, gamma, beta, y, mean_out, rstd_out, stream);
+}
+
+// CTAs per group of the grouped backward (partials: 2 * groups * blocks * F floats)
+int pb_layer_norm_grouped_bwd_blocks(int groups, long long rows_per_group, int F)
+{
+    int nb = ln_grid(rows_per_group, F <= 1024 ? LN_THREADS / 32 : 1);
+    const int cap = (pb_sm_count() * 4 + groups - 1) / (groups > 0 ? groups : 1);
+    if (groups > 1 && nb > cap) nb = cap < 1 ? 1 : cap;
+    return nb;
+}
+
+// dx is per OUTPUT row (groups * rows_per_group, F): for heads that share their input the caller sums it over the
+// groups (pb_sum_heads).  dgamma / dbeta: (groups, F).
+int pb_layer_norm_grouped_bwd(int groups, long long rows_per_group, long long x_rows, int F, const float *x,
+                              const float *dy, const float *gamma, const float *mean, const float *rstd, float *dx,
+                              float *dgamma, float *dbeta, float *partials, void *stream)
+{
+    const long long rows = (long long)groups * rows_per_group;
+    if (groups < 1 || rows_per_group < 1 || x_rows < 1 || !pb_layer_norm_supported(rows, F) || !x || !dy || !mean || !rstd || !dx || !partials)
+        return PB_E_ARG;
+    if ((((uintptr_t)x) | ((uintptr_t)dy) | ((uintptr_t)dx) | ((uintptr_t)gamma) | ((uintptr_t)partials)) & 15) return PB_E_ARG;
+    const int F4 = F / 4;
+    const int nb = pb_layer_norm_grouped_bwd_blocks(groups, rows_per_group, F);
+    const float4 *x4 = reinterpret_cast<const float4 *>(x), *d4 = reinterpret_cast<const float4 *>(dy),
+                 *g4 = reinterpret_cast<const float4 *>(gamma);
+    float4 *dx4 = reinterpret_cast<float4 *>(dx), *pg = reinterpret_cast<float4 *>(partials),
+           *pbeta = reinterpret_cast<float4 *>(partials + (size_t)groups * nb * F);
+    const dim3 grid(nb, groups);
+    if (F <= 512) {
+        PB_LAUNCH((ln_bwd_kernel<32, 4>), grid, LN_THREADS, 2 * F * sizeof(float), stream, rows_per_group, F4, x4, x_rows, d4, g4, mean, rstd, dx4, pg, pbeta);
+    } else if (F <= 1024) {
+        PB_LAUNCH((ln_bwd_kernel<32, 8>), grid, LN_THREADS, 2 * F * sizeof(float), stream, rows_per_group, F4, x4, x_rows, d4, g4, mean, rstd, dx4, pg, pbeta);
+    } else {
+        PB_LAUNCH((ln_bwd_kernel<256, 4>), grid, LN_THREADS, 0, stream, rows_per_group, F4, x4, x_rows, d4, g4, mean, rstd, dx4, pg, pbeta);
+    }
+    if (dgamma || dbeta)
+        PB_LAUNCH(ln_colreduce_kernel, dim3((F + 31) / 32, groups), dim3(32, 32), 0, stream, nb, F, partials,
+                  partials + (size_t)groups * nb * F, dgamma, dbeta);
+    return PB_OK;
+}
+
+int pb_layer_norm_bwd_blocks(long long rows, int F) { return pb_layer_norm_grouped_bwd_blocks(1, rows, F); }
 
 // partials: 2 * pb_layer_norm_bwd_blocks(rows, F) * F floats of scratch
 int pb_layer_norm_bwd(long long rows, int F, const float *x, const float *dy, const float *gamma, const float *mean,
                       const float *rstd, float *dx, float *dgamma, float *dbeta, float *partials, void *stream)
 {
-    if (!pb_layer_norm_supported(rows, F) || !x || !dy || !mean || !rstd || !dx || !partials) return PB_E_ARG;
-    if ((((uintptr_t)x) | ((uintptr_t)dy) | ((uintptr_t)dx) | ((uintptr_t)gamma) | ((uintptr_t)partials)) & 15) return PB_E_ARG;
-    const int F4 = F / 4;
-    const int nb = pb_layer_norm_bwd_blocks(rows, F);
-    const float4 *x4 = reinterpret_cast<const float4 *>(x), *d4 = reinterpret_cast<const float4 *>(dy),
-                 *g4 = reinterpret_cast<const float4 *>(gamma);
-    float4 *dx4 = reinterpret_cast<float4 *>(dx), *pg = reinterpret_cast<float4 *>(partials),
-           *pbeta = reinterpret_cast<float4 *>(partials + (size_t)nb * F);
-    if (F <= 512) {
-        PB_LAUNCH((ln_bwd_kernel<32, 4>), nb, LN_THREADS, 2 * F * sizeof(float), stream, rows, F4, x4, d4, g4, mean, rstd, dx4, pg, pbeta);
-    } else if (F <= 1024) {
-        PB_LAUNCH((ln_bwd_kernel<32, 8>), nb, LN_THREADS, 2 * F * sizeof(float), stream, rows, F4, x4, d4, g4, mean, rstd, dx4, pg, pbeta);
-    } else {
-        PB_LAUNCH((ln_bwd_kernel<256, 4>), nb, LN_THREADS, 0, stream, rows, F4, x4, d4, g4, mean, rstd, dx4, pg, pbeta);
-    }
-    if (dgamma || dbeta)
-        PB_LAUNCH(ln_colreduce_kernel, (F + 31) / 32, dim3(32, 32), 0, stream, nb, F, partials, partials + (size_t)nb * F, dgamma, dbeta);
-    return PB_OK;
+    return pb_layer_norm_grouped_bwd(1, rows, rows, F, x, dy, gamma, mean, rstd, dx, dgamma, dbeta, partials, stream);
 }
 
 }  // extern "C"

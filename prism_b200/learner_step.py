@@ -383,6 +383,11 @@ class LearnerStep:
         tree_snap = self.tree.snapshot()
         u_snap = self.u.clone()
         rng = torch.cuda.get_rng_state(self.device)
+        for m in (ag.model, ag.target_model):                   # the IQN heads' own generators (quantile draws)
+            d = getattr(m, "distribution_model", None) if m is not None else None
+            if d is not None and hasattr(d, "_rng_state"):
+                d._rng_state()
+        q_rng = ag.quantile_rng_snapshot()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -394,6 +399,7 @@ class LearnerStep:
         self.tree.restore(tree_snap)
         self.u.copy_(u_snap)
         torch.cuda.set_rng_state(rng, self.device)
+        ag.quantile_rng_restore(q_rng)
         self._graph_key = (draw, consume, getattr(self, "_u_in_block", False), self.ring.generation,
                            float(self.tree._beta))
         opt.zero_grad(set_to_none=True)

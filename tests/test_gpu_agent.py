@@ -453,14 +453,9 @@ def test_fused_layer_norm_matches_fp64(rows, F_):
         ln.weight.copy_(torch.randn(F_, generator=g))
         ln.bias.copy_(torch.randn(F_, generator=g))
     xd = x.to(DEV).requires_grad_(True)
-    old = ops.LN_MIN_ELEMENTS
-    ops.LN_MIN_ELEMENTS = 0
-    try:
-        y = ops.layer_norm(xd, ln)
-        assert "LayerNorm" in type(y.grad_fn).__name__ and "Native" not in type(y.grad_fn).__name__
-        y.backward(gy.to(DEV))
-    finally:
-        ops.LN_MIN_ELEMENTS = old
+    y = ops.layer_norm(xd, ln)
+    assert "LayerNorm" in type(y.grad_fn).__name__ and "Native" not in type(y.grad_fn).__name__
+    y.backward(gy.to(DEV))
     ref = nn.LayerNorm(F_).double()
     with torch.no_grad():
         ref.weight.copy_(ln.weight.cpu().double())
@@ -772,3 +767,103 @@ def test_static_batch_overflow_is_refused_and_ring_growth_recaptures():
     with pytest.raises(ValueError):
         ring.gather(torch.zeros(64, dtype=torch.int64, device=DEV), buf._obs, buf._next_obs, buf._reward, buf._gamma,
                     buf._nonterminal, buf._action)
+
+
+@pytest.mark.parametrize("M,N,J", [(32768, 18, 512), (2048, 3, 256), (1000, 6, 64), (777, 32, 1024), (4100, 4, 320)])
+def test_narrow_linear_matches_fp64(M, N, J):
+    """pb_narrow_linear_fwd / _bwd (the n_actions-wide output layer of the IQN head) against fp64 math + autograd."""
+    from prism_b200.agents import ops
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, J, generator=g)
+    w = torch.randn(N, J, generator=g) / J ** 0.5
+    b = torch.randn(N, generator=g)
+    dy = torch.randn(M, N, generator=g)
+    xd, wd, bd = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    ops.route_counts(reset=True)
+    y = ops.linear(xd, wd, bd)
+    assert ops.route_counts().get("linear:narrow", 0) == 1, ops.route_counts()
+    y.backward(dy.to(DEV))
+    torch.cuda.synchronize()
+    x64, w64, b64 = (t.double().requires_grad_(True) for t in (x, w, b))
+    y64 = x64 @ w64.t() + b64
+    y64.backward(dy.double())
+    assert rel_err(y.detach().cpu().numpy(), y64.detach().numpy()) < 2e-6
+    assert rel_err(xd.grad.cpu().numpy(), x64.grad.numpy()) < 2e-6
+    assert rel_err(wd.grad.cpu().numpy(), w64.grad.numpy()) < 2e-5
+    assert rel_err(bd.grad.cpu().numpy(), b64.grad.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("K,B,F_,shared", [(10, 512, 3136, True), (10, 64, 1024, True), (10, 64, 256, False),
+                                           (4, 33, 512, False), (3, 7, 64, True), (1, 256, 256, True)])
+def test_grouped_layer_norm_matches_fp64(K, B, F_, shared):
+    """LayerNorm with per-head affine parameters (K ensemble heads; shared or per-head input) against fp64 autograd."""
+    from prism_b200.agents import ops
+    g = torch.Generator().manual_seed(K * 100 + B)
+    x = torch.randn((B, F_) if shared else (K, B, F_), generator=g) * 2 + 0.5
+    w = torch.rand(K, F_, generator=g) + 0.5
+    b = torch.randn(K, F_, generator=g)
+    dy = torch.randn(K, B, F_, generator=g)
+    xd, wd, bd = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    ops.route_counts(reset=True)
+    y = ops.layer_norm_heads(xd, wd, bd)
+    assert ops.route_counts().get("ln:fused_heads", 0) == 1
+    y.backward(dy.to(DEV))
+    torch.cuda.synchronize()
+    x64, w64, b64 = (t.double().requires_grad_(True) for t in (x, w, b))
+    n64 = torch.nn.functional.layer_norm(x64, (F_,))
+    y64 = (n64 if not shared else n64.unsqueeze(0)) * w64.unsqueeze(1) + b64.unsqueeze(1)
+    y64.backward(dy.double())
+    assert rel_err(y.detach().cpu().numpy(), y64.detach().numpy()) < 1e-5
+    assert rel_err(xd.grad.cpu().numpy(), x64.grad.numpy()) < 2e-5
+    assert rel_err(wd.grad.cpu().numpy(), w64.grad.numpy()) < 2e-5
+    assert rel_err(bd.grad.cpu().numpy(), b64.grad.numpy()) < 2e-5
+
+
+def test_small_layer_norm_goes_through_the_fused_kernel():
+    from prism_b200.agents import ops
+    ln = torch.nn.LayerNorm(256).to(DEV)
+    x = torch.randn(64, 256, device=DEV, requires_grad=True)
+    ops.route_counts(reset=True)
+    y = ops.layer_norm(x, ln)
+    assert ops.route_counts() == {"ln:fused": 1}
+    y.square().sum().backward()
+    xr = x.detach().clone().requires_grad_(True)
+    yr = ln(xr)
+    yr.square().sum().backward()
+    assert rel_err(y.detach().cpu().numpy(), yr.detach().cpu().numpy()) < 1e-5
+    assert rel_err(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 1e-4
+
+
+def test_device_quantile_draws():
+    """pb_iqn_draw_cos_basis: uniforms in [0, 1) from the library's Philox generator, fresh per launch (also under graph
+    replay), equal for equal seeds, and the basis is cos(pi i tau) of exactly those draws."""
+    from prism_b200.agents import ops
+    rng_a = torch.tensor([1234, 0, 0, 0], dtype=torch.int64, device=DEV)
+    rng_b = rng_a.clone()
+    t1, b1 = ops.draw_cos_basis(4096, 64, rng_a)
+    t2, _ = ops.draw_cos_basis(4096, 64, rng_a)
+    t3, _ = ops.draw_cos_basis(4096, 64, rng_b)
+    torch.cuda.synchronize()
+    assert torch.equal(t1, t3) and not torch.equal(t1, t2)
+    assert float(t1.min()) >= 0.0 and float(t1.max()) < 1.0
+    assert 0.47 < float(t1.mean()) < 0.53 and 0.27 < float(t1.std()) < 0.31
+    assert rng_a.cpu().tolist()[:3] == [1234, 2, 0]
+    assert torch.equal(b1, ops.cos_basis(t1, 64))
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        ops.draw_cos_basis(512, 64, rng_a)
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(graph):
+        tg, _ = ops.draw_cos_basis(512, 64, rng_a)
+    graph.replay()
+    first = tg.clone()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert not torch.equal(first, tg)
+
+
+def test_sum_leading_matches_torch():
+    from prism_b200.agents import ops
+    x = torch.randn(10, 512, 3136, device=DEV)
+    assert rel_err(ops.sum_leading(x).cpu().numpy(), x.double().sum(0).cpu().numpy()) < 1e-6
