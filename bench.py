@@ -33,6 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+METRIC = ("PER sampled transitions/s (4 new steps ingested -> sample -> 3-step gather -> DQN update -> priority "
+          "write-back, per learner iteration)")
 OBS_SHAPE = (10, 10, 6)
 N_ACTIONS = 4
 CAPACITY = 1_000_000
@@ -305,16 +307,19 @@ def kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src):
         # GEMM-shaped work: the tensor / FMA pipes bound it; 3 forward + 2x2 backward launches of this family are ~45 %
         # of the step (profiles/launches_r01d_step.txt).  traffic: dram__bytes_read+write of one launch, ncu --set full
         # (profiles/ncu_full_step_r01.txt, gemm_kernel<1,1,0> grid (4,4,8)).
+        traffic, traffic_file = ncu_traffic("gemm_kernel<1, 1, 0>")
         roof = {"bound": "tensor", "kernel": dom, "achieved": d["achieved_tflops"], "peak": bf16, "unit": "TFLOP/s",
-                "frac": d["frac_of_bf16_tensor_peak"], "traffic": 2134784, "peak_source": peak_src,
+                "frac": d["frac_of_bf16_tensor_peak"], "traffic": traffic, "traffic_source": traffic_file,
+                "peak_source": peak_src,
                 "note": "batch-256 fp32 layer (134 MFLOP, 2.3 MB): latency-bound by construction -- 128 CTAs x 4 K "
                         "iterations; the reference computes it in fp32, so the kernel runs on the FFMA pipe and the bf16 "
                         "tensor peak is only the nominal denominator.  Layers from 2e8 FLOP up run on tcgen05 (3xTF32): "
                         "see extras.tc_gemm for their tensor-pipe roofline and extras.per_microbench for the HBM-bound "
                         "PER kernels"}
     else:
+        traffic, traffic_file = ncu_traffic(dom.split("(")[-1].split(",")[0].split(")")[0].strip())
         roof = {"bound": "hbm", "kernel": dom, "achieved": d["achieved_gbs"], "peak": hbm_gbs, "unit": "GB/s",
-                "frac": d["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": d["frac"], "traffic": traffic, "traffic_source": traffic_file, "peak_source": peak_src,
                 "note": "batch-256 launches move KBs-MBs: latency-bound by construction; see extras.per_microbench "
                         "for the saturated PER kernels"}
     return roof, out
@@ -378,7 +383,137 @@ def sharded_per_microbench(step, rank, world, device, torch, dist, hbm_gbs):
             "transitions_per_s": round(Bg / sec, 1), "algorithmic_bytes": int(nbytes),
             "achieved_gbs": round(nbytes / sec / 1e9, 2), "frac_of_one_gpu_hbm": round(nbytes / sec / 1e9 / hbm_gbs, 5),
             "exchange": "peer" if peer is not None else "nccl",
-            "note": "latency-bound: one cross-GPU handshake + 3 sampling launches + 3 update launches per iteration"}
+            "note": "latency-bound: one cross-GPU handshake + 1 sampling launch + 1 update launch per iteration"}
+
+
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, read from the committed `ncu --set full`
+    summaries of this round (profiles/ncu_full_*_r02*.txt, written by profiles/summarize_ncu.py).  Returns
+    (bytes or None, file name or None)."""
+    import glob
+    best = (None, None)
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_full_*_r02*.txt"))):
+        try:
+            lines = open(path).read().splitlines()
+        except OSError:
+            continue
+        vals = []
+        for ln in lines[1:]:
+            if kernel_substr not in ln:
+                continue
+            m = __import__("re").search(r"\(\d+,\d+,\d+\)\s+\(\d+,\d+,\d+\)\s+([0-9.]+)\s+(\d+)\s+(\d+)", ln)
+            if m:
+                vals.append(float(m.group(2)) + float(m.group(3)))
+        if vals:
+            best = (int(sum(vals) / len(vals)), os.path.basename(path))
+    return best
+
+
+def measure_tf32_peak(device, torch):
+    """Dense TF32 TFLOP/s of this GPU: the library GEMM on 8192^3 fp32 operands with TF32 allowed (best of 5) -- the
+    denominator of the 3xTF32 kernels' roofline, measured instead of assumed (bf16 / 2)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=device)
+        b = torch.randn(n, n, device=device)
+        for _ in range(2):
+            a @ b
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        del a, b
+        return best
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def torch_gpu_baseline(device, torch):
+    """BASELINE leg (not the product): the reference-equivalent update step in STOCK PyTorch on this GPU, captured as a
+    CUDA graph -- the stand-in for the reference's best GPU path (prism/agents/agent.py:102-147; the reference itself
+    needs torchrl to run).  Same models (oracle/agent_oracle.py restates the reference's modules with the reference's
+    parameter names), same shapes, ATen / cuBLAS / cuDNN kernels, torch.optim.Adam(capturable).  Update only: the
+    reference samples and writes priorities back on the CPU."""
+    import dataclasses
+    import prism_b200
+    from oracle.agent_oracle import OracleAgent
+    out = {}
+    specs = {"configs[1] dqn_B256": (prism_b200.minatar_dqn_per_config, OBS_SHAPE, N_ACTIONS, 256, 1, 200),
+             "configs[0] minatar_ids_iqn_B64": (prism_b200.minatar_ids_iqn_config, (10, 10, 4), 3, 64, 1, 100),
+             "configs[4] atari_iqn64x64_ids_B512": (prism_b200.atari_iqn_ids_config, (4, 84, 84), 18, 512, 4, 10)}
+    for name, (make, obs_shape, A, B, fs, reps) in specs.items():
+        try:
+            cfg = dataclasses.replace(make(), device=device, use_cuda_graph=False)
+            torch.manual_seed(123)
+            with torch.device(device):
+                oracle = OracleAgent(cfg, obs_shape, A)
+                oracle.opt = torch.optim.Adam(oracle.model.parameters(), lr=cfg.learning_rate,
+                                              betas=(cfg.adam_beta1, cfg.adam_beta2), eps=cfg.adam_epsilon, capturable=True)
+                shape = (B,) + tuple(obs_shape) if fs > 1 else (B, 1) + tuple(obs_shape)
+                batch = {"observation": torch.rand(shape), "next": {"observation": torch.rand(shape), "reward": torch.randn(B, 1)},
+                         "nonterminal": torch.rand(B, 1) > 0.1, "gamma": torch.full((B, 1), 0.97),
+                         "action": torch.randint(0, A, (B, 1))}
+                w = torch.rand(B)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        oracle.update(batch, w)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    oracle.update(batch, w)
+                sec = time_kernel(g.replay, reps, torch)
+            out[name] = {"ms_per_update": round(sec * 1e3, 4), "updates_per_s": round(1.0 / sec, 2), "batch": B,
+                         "what": "stock PyTorch (ATen/cuBLAS/cuDNN, TF32 matmul off) update step under one CUDA graph"}
+            del g, oracle, batch
+        except Exception as e:
+            out[name] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+    return out
+
+
+def config_rooflines(extras, hbm_gbs, tf32_peak):
+    """One roofline object per BASELINE config, from the live measurements already in `extras`."""
+    out = {}
+    pm = extras.get("per_microbench", {})
+    tc = extras.get("tc_gemm", {})
+    oc = extras.get("other_configs", {})
+
+    def tc_row(key, label):
+        r = tc.get(key)
+        if not isinstance(r, dict) or "us" not in r:
+            return None
+        return {"kernel": label, "bound": "tensor", "achieved": r["achieved_tf32_tflops"], "peak": round(tf32_peak, 1),
+                "unit": "TFLOP/s (TF32; 3 TF32 FLOP per fp32-equivalent FLOP)", "frac": round(r["achieved_tf32_tflops"] / tf32_peak, 4),
+                "us": r["us"], "peak_source": "measured here: library TF32 GEMM 8192^3"}
+    r = tc_row("iqn_hidden_cfg0_2048x256x1024_fwd", "tc_gemm_kernel (IQN hidden layer 2048x256x1024)")
+    if r:
+        r["step_ms"] = oc.get("configs[0] minatar_ids_iqn_B64", {}).get("ms_per_update")
+        out["configs[0]"] = r
+    k = pm.get("sample+update_16M_B4096_x64_in_flight") or pm.get("sample+update_16M_B4096")
+    if k:
+        out["configs[2]"] = {"kernel": "tree_sample_kernel + priority write-back, 64 batches of 4096 in flight (see per_microbench for K = 1, 4, 16)",
+                             "bound": "hbm", "achieved": k["achieved_gbs"], "peak": hbm_gbs, "unit": "GB/s", "frac": k["frac"],
+                             "us": k["us"], "single_batch_us": pm.get("sample+update_16M_B4096", {}).get("us")}
+    k = extras.get("sharded_per_configs3") or pm.get("shard_8M_global_sample+update_B4096")
+    if k and "us_per_iteration" in k:
+        out["configs[3]"] = {"kernel": "global_sample_kernel + upd_chain_kernel per 2^23-leaf shard", "bound": "hbm",
+                             "achieved": k["achieved_gbs"], "peak": hbm_gbs, "unit": "GB/s",
+                             "frac": k.get("frac_of_one_gpu_hbm"), "us": k["us_per_iteration"]}
+    r = tc_row("iqn_hidden_32768x512x3136_fwd", "tc_gemm_kernel (IQN hidden layer 32768x512x3136)")
+    if r:
+        r["step_ms"] = oc.get("configs[4] atari_iqn64x64_ids_B512", {}).get("ms_per_update")
+        out["configs[4]"] = r
+    return out
 
 
 def tensor_peak():
@@ -395,10 +530,12 @@ def tc_gemm_microbench(device, torch):
     K-head ensemble: forward, input gradient, weight gradient.  TF32 peak = half the measured bf16 peak; every
     fp32-equivalent FLOP costs three TF32 FLOPs."""
     from prism_b200.agents import ops
-    bf16 = tensor_peak()
-    out = {"tf32_peak_tflops": round(bf16 / 2, 1), "note": "achieved_tf32 = 3 x fp32-equivalent; frac = achieved_tf32 / (bf16 peak / 2); "
-           "ncu: sm__pipe_tensor_cycles_active 63-70 % (profiles/ncu_full_tc_gemm_r01.txt)"}
-    for name, (K, M, N, J) in {"iqn_hidden_32768x512x3136": (1, 32768, 512, 3136), "ensemble_10x512x512x3136": (10, 512, 512, 3136)}.items():
+    tf32 = measure_tf32_peak(device, torch)
+    out = {"tf32_peak_tflops": round(tf32, 1), "bf16_peak_tflops": tensor_peak(),
+           "note": "achieved_tf32 = 3 x fp32-equivalent (3xTF32 split keeps the reference's fp32 accuracy); frac = "
+                   "achieved_tf32 / the TF32 peak MEASURED here (library TF32 GEMM, 8192^3)"}
+    for name, (K, M, N, J) in {"iqn_hidden_32768x512x3136": (1, 32768, 512, 3136), "ensemble_10x512x512x3136": (10, 512, 512, 3136),
+                               "iqn_hidden_cfg0_2048x256x1024": (1, 2048, 256, 1024)}.items():
         x = torch.randn(K, M, J, device=device)
         w = torch.randn(K, N, J, device=device)
         b = torch.randn(K, N, device=device)
@@ -411,7 +548,7 @@ def tc_gemm_microbench(device, torch):
             t = time_kernel(fn, 10, torch)
             eq = fl / t / 1e12
             out["%s_%s" % (name, kind)] = {"us": round(t * 1e6, 1), "algorithmic_flops": int(fl), "fp32_equivalent_tflops": round(eq, 1),
-                                            "achieved_tf32_tflops": round(3 * eq, 1), "frac": round(3 * eq / (bf16 / 2), 3)}
+                                            "achieved_tf32_tflops": round(3 * eq, 1), "frac": round(3 * eq / tf32, 3)}
         del x, w, b, dz, y, dx, dw
         torch.cuda.empty_cache()
     return out
@@ -476,6 +613,28 @@ def per_microbench(device, torch, hbm_gbs):
             "achieved_gbs": round(nbytes / sec / 1e9, 2), "frac": round(nbytes / sec / 1e9 / hbm_gbs, 5),
             "sample_us": round(s_sec * 1e6, 2), "update_us": round(u_sec * 1e6, 2)}
     del tree, leaves
+    torch.cuda.empty_cache()
+    # configs[3] on one GPU: ONE 2^23-leaf shard doing its part of a global batch of 4096 (the sharded sampling kernel
+    # with a single-rank virtual top; the multi-GPU run adds the peer state exchange: extras.sharded_per_configs3)
+    Ns, Bs, Ls = 1 << 23, 4096, 23
+    shard = PrioritizedTree(Ns, device=device, mode="stratified")
+    shard.build(torch.empty(Ns, device=device).exponential_(1.0, generator=g))
+    idx = torch.empty(Bs, dtype=torch.int64, device=device)
+    w = torch.empty(Bs, dtype=torch.float32, device=device)
+    prio = torch.rand(Bs, device=device, generator=g)
+    all_state = torch.zeros(1, 64, dtype=torch.uint8, device=device)
+
+    def shard_iter():
+        all_state.copy_(shard.state.view(1, 64))
+        shard.sample_global(1, 0, all_state, Bs, None, idx_out=idx, weight_out=w)
+        shard.update_priority(idx, prio, sorted=True)
+    sec = time_kernel_graph(shard_iter, 40, torch)
+    nbytes = Bs * (4 * Ls + 24 + 16 * Ls + 20)
+    out["shard_8M_global_sample+update_B4096"] = {
+        "leaves": Ns, "us_per_iteration": round(sec * 1e6, 2), "transitions_per_s": round(Bs / sec, 1),
+        "algorithmic_bytes": nbytes, "achieved_gbs": round(nbytes / sec / 1e9, 2),
+        "frac_of_one_gpu_hbm": round(nbytes / sec / 1e9 / hbm_gbs, 5)}
+    del shard
     torch.cuda.empty_cache()
     # Atari-shaped gather: uint8 frames 84x84, frame_stack 4, batch 512 (configs[4] shapes)
     cap, Bg = 1 << 17, 512
@@ -546,13 +705,68 @@ def config_extras(device, torch):
     return out
 
 
-def cpu_baseline(steps, fill, budget_s=25.0):
+def configs4_dp(rank, world, device, pg, torch, dist):
+    """BASELINE configs[4] data parallel: IQN 64x64 + IDS on Atari-shaped 84x84x4 transitions, batch 512 PER GPU, one
+    shard per rank, global stratified sampling, 73 MB gradient arena through the reduce-scatter-by-pull + fused
+    clip/Adam exchange (csrc/peer.cu).  Every rank runs it; returns the max-over-ranks step time."""
+    import prism_b200
+    from prism_b200.learner_step import LearnerStep
+    cfg = prism_b200.atari_iqn_ids_config(device=device, experience_replay_capacity=1 << 15, per_sampling="stratified",
+                                          replay_max_streams=32, replay_staging_rows=8192, replay_storage_dtype="uint8",
+                                          replay_obs_scale_255=True, use_cuda_graph=False)
+    torch.manual_seed(123)
+    agent = prism_b200.build_agent(cfg, (cfg.frame_stack_size, 84, 84), 18)
+    buf = prism_b200.build_exp_buffer(cfg)
+    rng = np.random.default_rng(50 + rank)
+    fill, done_n, E = 1 << 14, 0, 84 * 84
+    while done_n < fill:
+        n = min(8192, fill - done_n)
+        frames = rng.integers(0, 256, (n + 32, E), dtype=np.uint8)
+        sid = ((done_n + np.arange(n)) % 32).astype(np.int32)
+        buf.extend_batch(sid, frames[:n].reshape((n, 84, 84)), rng.integers(0, 18, n).astype(np.int32),
+                         (rng.random(n) < 0.05).astype(np.float32), rng.random(n) < (1 / 500), np.zeros(n, bool),
+                         frames[32:32 + n].reshape((n, 84, 84)))
+        done_n += n
+    buf._flush()
+    if world > 1:
+        dist.broadcast(agent.optimizer.arena, src=0)
+    step = LearnerStep(buf, agent, batch_size=cfg.batch_size, use_cuda_graph=True, process_group=pg, rank=rank,
+                       world_size=world, prefetch=True)
+    for _ in range(3):
+        step.step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = 10
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        step.step()
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) * 1e-3 / reps], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    if step.peer is not None:
+        step.peer.check()
+    out = {"ms_per_update": round(sec * 1e3, 4), "updates_per_s": round(1.0 / sec, 2), "batch_per_gpu": cfg.batch_size,
+           "global_batch": cfg.batch_size * world, "transitions_per_s": round(cfg.batch_size * world / sec, 1),
+           "parameters": int(agent.optimizer.numel), "exchange": getattr(step, "exchange", None),
+           "launches_per_step_ours": step.launches_per_step}
+    del step, agent, buf
+    torch.cuda.empty_cache()
+    return out
+
+
+def cpu_baseline(steps, fill, budget_s=25.0, batch=BATCH, warmup=3):
     """The oracle port (reference algorithm restated for the CPU) on the host cores: Python linked-list
     buffer + C sum-tree (1 thread, like torchrl) + PyTorch CPU agent (all intra-op threads)."""
     import torch
     from oracle.agent_oracle import OracleAgent
     from oracle.buffer_oracle import OracleTimestepBuffer, Step, StreamLinker
     import prism_b200
+    BATCH = int(batch)                                       # noqa: N806 (shadows the module constant on purpose)
     cfg = prism_b200.minatar_dqn_per_config(device="cpu", batch_size=BATCH)
     torch.manual_seed(123)
     agent = OracleAgent(cfg, OBS_SHAPE, N_ACTIONS)
@@ -590,7 +804,7 @@ def cpu_baseline(steps, fill, budget_s=25.0):
         out = agent.update(tb, torch.from_numpy(info["_weight"]))
         buf.update_priority(info["index"], out["td"].numpy())
 
-    for _ in range(3):
+    for _ in range(max(3, warmup)):
         one()
     t0 = time.perf_counter()
     n = 0
@@ -600,10 +814,10 @@ def cpu_baseline(steps, fill, budget_s=25.0):
     dt = time.perf_counter() - t0
     return {"value": BATCH * n / dt, "unit": "transitions/s", "updates_per_s": n / dt, "cores": torch.get_num_threads(),
             "kind": "port",
-            "sample": "%d hot-loop iterations (4 new steps, sample 256, DQN update, priority write-back) on a "
-                      "1M-capacity buffer holding %d transitions; Python linked-list store + single-thread C tree "
-                      "+ torch CPU agent" % (n, fill),
-            "ms_per_step": dt / max(n, 1) * 1e3, "host_cpus": os.cpu_count()}
+            "sample": "%d hot-loop iterations after %d warm-ups (4 new steps, sample %d, DQN update, priority "
+                      "write-back) on a 1M-capacity buffer holding %d transitions; Python linked-list store + "
+                      "single-thread C tree + torch CPU agent" % (n, max(3, warmup), BATCH, fill),
+            "ms_per_step": dt / max(n, 1) * 1e3, "host_cpus": os.cpu_count(), "batch": BATCH, "fill": fill}
 
 
 def run_ours(args):
@@ -630,9 +844,9 @@ def run_ours(args):
         dist.broadcast(agent.optimizer.arena, src=0)
         if agent.target_model is not None:
             dist.broadcast(agent.target_model._flat_arena, src=0)
-    # tail prefetch of the next batch: measured faster at 1 GPU (111 -> 101 us/step); with the cross-GPU handshakes on
-    # both graph branches it is slower for the device-resident metric at 2 GPUs (165 vs 154 us), so off there
-    prefetch = os.environ.get("PB_PREFETCH", "1" if world == 1 else "0") != "0"
+    # prefetch of the next batch: on the tail branch at 1 GPU; at N > 1 beside the gradient pulls + optimizer sweep,
+    # right after the step's single cross-GPU handshake (which carries the shard states the sampling needs)
+    prefetch = os.environ.get("PB_PREFETCH", "1") != "0"
     step = LearnerStep(buf, agent, batch_size=BATCH, use_cuda_graph=True, process_group=pg, rank=rank, world_size=world,
                        prefetch=prefetch)
 
@@ -642,30 +856,46 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident metric: W warm-up + K timed graph replays -----------------
+    # Every iteration ingests STEPS_PER_ITER new transitions (like the reference loop and like the CPU arm), samples,
+    # gathers, updates and writes the priorities back.  Here the new steps' staged blocks (rows + link records + the
+    # iteration's uniforms) are planned on the host BEFORE the timed region and parked in HBM: the timed loop only
+    # copies a block device-to-device into the staging slot and replays the step graph.
     # clocks are sampled (NVML, every 5 ms) only inside the two timed regions (device-resident and e2e)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
         clocks.window(False)
+    n_warm = max(3, args.warmup)
+    rng_u = np.random.default_rng(2)               # global stratified sampling: every rank must see the SAME uniforms
+    n_res = n_warm + args.steps
+    pre = trace.chunk(n_res * STEPS_PER_ITER)
+    pre_u = rng_u.random((n_res, step.B_global))
+
+    def ingest_slice(src, i):
+        sl = slice(i * STEPS_PER_ITER, (i + 1) * STEPS_PER_ITER)
+        return (src["stream"][sl], src["obs"][sl], src["action"][sl], src["reward"][sl], src["done"][sl], src["trunc"][sl],
+                src["next_obs"][sl])
+
+    pool = torch.stack([step.plan_ingest(ingest_slice(pre, i), u=pre_u[i]) for i in range(n_res)]).to(device)
+    torch.cuda.synchronize()
     graph_ok = True
     try:
-        for _ in range(max(3, args.warmup)):
-            step.step()
+        for i in range(n_warm):
+            step.step(ingest_block=pool[i])
         torch.cuda.synchronize()
-    except Exception as e:                                    # e.g. NCCL capture refused: fall back to eager launches
+    except Exception as e:                                    # e.g. capture refused: fall back to eager launches
         graph_ok = False
         sys.stderr.write("graph capture failed (%r); running the step eagerly\n" % (e,))
-        step = LearnerStep(buf, agent, batch_size=BATCH, use_cuda_graph=False, process_group=pg, rank=rank,
-                           world_size=world, prefetch=prefetch)
-        for _ in range(max(3, args.warmup)):
-            step.step()
+        step.use_cuda_graph = False
+        for i in range(n_warm):
+            step.step(ingest_block=pool[i])
     barrier()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks.window(True)
     ev0.record()
-    for _ in range(args.steps):
-        step.step()
+    for i in range(args.steps):
+        step.step(ingest_block=pool[n_warm + i])
     ev1.record()
     barrier()
     clocks.window(False)
@@ -678,18 +908,15 @@ def run_ours(args):
     exchange = getattr(step, "exchange", None) if world > 1 else None
     gpu_launches = (lp * args.steps) if lp is not None else (_lib.launch_count() - launches0)
     value = BATCH * world * args.steps / sec
+    del pool
 
     # ---------------- end-to-end through the public API with host buffers ----------------------
     # synthetic host inputs are generated BEFORE the timed region; the timed loop copies them through pinned
     # staging (H2D), runs the step, and reads the loss back (D2H)
-    if world > 1 and os.environ.get("PB_PREFETCH") is None:
-        # with host-fed steps the tail prefetch pays at N > 1 as well (2 GPUs: 3.31 vs 3.09 M transitions/s end to end)
-        step.set_prefetch(True)
     e2e_steps = args.steps
     n_pre = max(3, args.warmup) + e2e_steps
     pre = trace.chunk(n_pre * STEPS_PER_ITER)
-    rng = np.random.default_rng(2)                 # global stratified sampling: every rank must see the SAME uniforms
-    pre_u = rng.random((n_pre, step.B_global))
+    pre_u = rng_u.random((n_pre, step.B_global))
     u_hosts = [torch.empty(step.B_global, dtype=torch.float64).pin_memory() for _ in range(2)]
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     tick = [0]
@@ -729,12 +956,18 @@ def run_ours(args):
            "d2h_bytes_per_step": 4, "updates_per_s": e2e_steps / e2e_sec,
            "host_wall_s": round(wall, 4), "loss": float(loss_host)}
 
-    sharded = None
+    sharded = cfg4 = None
     if world > 1 and not args.quick:
         try:
             sharded = sharded_per_microbench(step, rank, world, device, torch, dist, hbm_gbs)
         except Exception as e:
             sharded = {"error": repr(e)[:300]}
+        try:
+            if step.peer is not None:
+                step.peer.check()
+            cfg4 = configs4_dp(rank, world, device, pg, torch, dist)
+        except Exception as e:
+            cfg4 = {"error": repr(e)[:300]}
     if rank != 0:
         _finish(world, dist)
         return
@@ -744,6 +977,8 @@ def run_ours(args):
               "launches_per_step_ours": lp, "graph": graph_ok}
     if sharded is not None:
         extras["sharded_per_configs3"] = sharded
+    if cfg4 is not None:
+        extras["configs4_data_parallel"] = cfg4
     cpu = None
     if world == 1 and not args.quick:
         del step
@@ -758,9 +993,21 @@ def run_ours(args):
             extras["other_configs"] = config_extras(device, torch)
         except Exception as e:                       # never lose the headline line to an extra
             extras["other_configs"] = {"error": repr(e)[:300]}
-        cpu = cpu_baseline(steps=400, fill=50_000)
+        try:
+            extras["torch_gpu_baseline"] = torch_gpu_baseline(device, torch)
+        except Exception as e:
+            extras["torch_gpu_baseline"] = {"error": repr(e)[:300]}
+        try:
+            extras["rooflines"] = config_rooflines(extras, hbm_gbs, extras["tc_gemm"].get("tf32_peak_tflops", tensor_peak() / 2))
+        except Exception as e:
+            extras["rooflines"] = {"error": repr(e)[:300]}
+        from prism_b200.agents import ops as _ops
+        extras["routes"] = _ops.route_counts()
+        extras["library_fallthroughs"] = _ops.fallthrough_count()
+        # same buffer fill and batch as our arm; bounded to ~25 s of timed CPU work (the fill itself takes about as long)
+        cpu = cpu_baseline(steps=400, fill=CAPACITY, budget_s=25.0, warmup=20)
     line = {
-        "metric": "PER sampled transitions/s (sample -> 3-step gather -> DQN update -> priority write-back)",
+        "metric": METRIC,
         "value": value, "unit": "transitions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -796,15 +1043,21 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cpu = cpu_baseline(steps=args.steps, fill=50_000, budget_s=120.0)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    # like for like with our arm at N GPUs: the global batch (256 per GPU) on the host, a 1M-filled buffer, and at
+    # least 200 timed iterations after 20 warm-ups (20 cold iterations overstated the ratio in round 1)
+    steps = max(args.steps, 200)
+    cpu = cpu_baseline(steps=steps, fill=CAPACITY, budget_s=150.0, batch=BATCH * world, warmup=max(20, args.warmup))
     line = {
         "impl": "reference",
-        "metric": "PER sampled transitions/s (sample -> 3-step gather -> DQN update -> priority write-back)",
-        "value": cpu["value"], "unit": "transitions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC,
+        "value": cpu["value"], "unit": "transitions/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(20, args.warmup),
         "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "learner_updates_per_s": cpu["updates_per_s"],
         "config": {"workload": "configs[1]: MinAtar SpaceInvaders-shaped (10x10x6) DQN + double-Q + PER, 1M-capacity "
-                               "buffer, batch 256, 3-step returns -- reference algorithm on the host CPU",
+                               "buffer (filled), global batch %d (256 per GPU of the other arm), 3-step returns, 4 new "
+                               "steps ingested per iteration -- reference algorithm on the host CPU" % (BATCH * world),
+                   "global_batch": BATCH * world,
                    "note": "the reference is pure Python + torchrl (absent): this arm times the oracle port of its "
                            "algorithm (oracle/buffer_oracle.py, oracle/per_oracle.c, oracle/agent_oracle.py); "
                            "single process, rank 0 only"},

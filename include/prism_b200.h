@@ -56,6 +56,7 @@ int pb_event_synchronize(void *event);
 int pb_stream_wait_event(void *stream, void *event);
 int pb_copy_h2d_async(void *dst, const void *src, long long bytes, void *stream);
 int pb_copy_d2h_async(void *dst, const void *src, long long bytes, void *stream);
+int pb_copy_d2d_async(void *dst, const void *src, long long bytes, void *stream);
 const char *pb_error_string(int code);
 /* number of kernels this library has launched in this process (bench: gpu_launches) */
 long long   pb_launch_count(void);
@@ -349,6 +350,11 @@ int pb_greedy_select(int N, int A, int K, const float *q, long long *action_out,
  *   float[2]) = {total_norm, coef}.
  * pb_adam_clip_step = pb_grad_sumsq + pb_adam_clip_apply. */
 #define PB_ADAM_MAX_PARTIALS 4096
+/* pb_pack_grads_parity: the same gather into one half of a double-buffered arena: destination = flat +
+ * (*epoch & 1) * stride, epoch a device counter (the peer exchange's count of completed state gathers, csrc/peer.cu). */
+int pb_pack_grads_parity(int n_tensors, const long long *table, float scale, float *flat,
+                         const unsigned long long *epoch, long long stride, float *partial_scratch,
+                         long long *step_count, int *n_partials_out_h, void *stream);
 int pb_pack_grads(int n_tensors, const long long *table, float scale, float *flat,
                   float *partial_scratch, long long *step_count, int *n_partials_out_h,
                   void *stream);
@@ -444,6 +450,10 @@ typedef struct pb_peer_group {
     double *norm_parts[PB_PEER_MAX];          /* every rank's [PB_PEER_MAX] slice sums of squares                    */
     unsigned char *state[PB_PEER_MAX];        /* every rank's gathered shard states, 2 parity slots x [PB_PEER_MAX][64] */
     unsigned long long *epoch;                /* local barrier counters, one per channel (0 exchange, 1 state gather)  */
+    unsigned int *status;                     /* local status word: bit ch set = a wait on channel ch timed out (may be NULL) */
+    unsigned long long timeout_ns;            /* bound of every flag wait; 0 = wait forever                          */
+    long long grad_stride;                    /* floats between the two halves of the double-buffered gradient arena
+                                                 (0: single buffer); the half in use = parity of completed state gathers */
 } pb_peer_group;
 int pb_peer_alloc(long long bytes, void **ptr);            /* cudaMalloc + zero fill; blocking                      */
 int pb_peer_free(void *ptr);

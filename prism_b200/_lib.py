@@ -57,7 +57,8 @@ class pb_peer_group(C.Structure):
     _fields_ = [("world", C.c_int), ("rank", C.c_int),
                 ("grad", C.c_void_p * PB_PEER_MAX), ("reduced", C.c_void_p * PB_PEER_MAX),
                 ("flags", C.c_void_p * PB_PEER_MAX), ("norm_parts", C.c_void_p * PB_PEER_MAX),
-                ("state", C.c_void_p * PB_PEER_MAX), ("epoch", C.c_void_p)]
+                ("state", C.c_void_p * PB_PEER_MAX), ("epoch", C.c_void_p), ("status", C.c_void_p),
+                ("timeout_ns", C.c_ulonglong), ("grad_stride", C.c_longlong)]
 
 
 _P = C.c_void_p
@@ -80,6 +81,7 @@ SIGNATURES = {
     "pb_stream_wait_event": [_P, _P],
     "pb_copy_h2d_async": [_P, _P, _LL, _P],
     "pb_copy_d2h_async": [_P, _P, _LL, _P],
+    "pb_copy_d2d_async": [_P, _P, _LL, _P],
     "pb_tree_layout": [_LL, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                        C.POINTER(C.c_longlong), C.POINTER(C.c_int)],
     "pb_tree_init": [_TREE, _P],
@@ -106,6 +108,7 @@ SIGNATURES = {
     "pb_greedy_select": [_I, _I, _I, _P, _P, _P],
     "pb_adam_clip_step": [_LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
     "pb_pack_grads": [_I, _P, _F, _P, _P, _P, _P, _P],
+    "pb_pack_grads_parity": [_I, _P, _F, _P, _P, _LL, _P, _P, _P, _P],
     "pb_grad_sumsq": [_LL, _P, _P, _P, _P, _P],
     "pb_adam_clip_apply": [_LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _I, _P, _P],
     "pb_loss_combine": [_I, _P, _P, _P, _F, _P, _P, _P, _P],

@@ -79,7 +79,8 @@ class FlatAdam(object):
         self.grad_scale = 1.0           # 1/world_size under data parallelism
         self.allreduce = None           # callable(flat_grad) inserted between gather and Adam (library collective)
         self.peer = None                # PeerGroup: gradient exchange fused with clip + Adam over peer memory
-        self.peer_trailing_barrier = True
+        self.peer_state = None          # 64-byte shard state block that rides on the exchange's handshake (LearnerStep)
+        self.peer_after_exchange = None  # callable run right after the handshake (LearnerStep: prefetch of the next batch)
 
     def attach_peer_group(self, peer):
         """Route the data-parallel gradient exchange through csrc/peer.cu: the flat gradient arena moves into the
@@ -122,10 +123,13 @@ class FlatAdam(object):
         n_part = ctypes.c_int(0)
         mark = getattr(self, "_mark", None) or (lambda name: None)      # LearnerStep.enable_trace()
         if self.peer is not None:
-            _lib.check(self._lib.pb_pack_grads(len(self.params), self.table.data_ptr(), self.grad_scale,
-                                               self.grad.data_ptr(), None, None, None, stream), "pb_pack_grads")
+            # into the half of the double-buffered peer arena this step's exchange will read (device-side parity)
+            _lib.check(self._lib.pb_pack_grads_parity(len(self.params), self.table.data_ptr(), self.grad_scale,
+                                                      self.grad.data_ptr(), self.peer.epoch_gather_ptr,
+                                                      self.peer.grad_stride, None, None, None, stream),
+                       "pb_pack_grads_parity")
             mark("opt:packed")
-            self.peer.allreduce_adam(self, trailing_barrier=self.peer_trailing_barrier, mark=mark)
+            self.peer.allreduce_adam(self, state=self.peer_state, mark=mark, after_exchange=self.peer_after_exchange)
             return
         if self.allreduce is None:
             _lib.check(self._lib.pb_pack_grads(len(self.params), self.table.data_ptr(), self.grad_scale,

@@ -246,10 +246,12 @@ constexpr int PACK_BLOCKS_PER_TENSOR = 16;
 // sum of squares of the scaled values folded in.  table[t] = {grad pointer, arena offset, numel}.
 __global__ void __launch_bounds__(ADAM_THREADS) pack_grads_kernel(const long long *__restrict__ table, float scale,
                                                                   float *__restrict__ flat,
-                                                                  float *__restrict__ partial,
+                                                                  const unsigned long long *__restrict__ epoch,
+                                                                  long long stride, float *__restrict__ partial,
                                                                   long long *__restrict__ step_count)
 {
     __shared__ double part[ADAM_THREADS / 32];
+    if (epoch) flat += (long long)(*epoch & 1ull) * stride;      // double-buffered arena of the peer exchange
     const int t = blockIdx.y;
     const float *__restrict__ src = reinterpret_cast<const float *>(table[3 * t + 0]);
     float *__restrict__ dst = flat + table[3 * t + 1];
@@ -461,7 +463,15 @@ int pb_loss_combine(int B, const float *dist, const float *q, const float *w, fl
 int pb_pack_grads(int n_tensors, const long long *table, float scale, float *flat, float *partial_scratch,
                   long long *step_count, int *n_partials_out_h, void *stream)
 {
-    if (n_tensors <= 0 || !table || !flat) return PB_E_ARG;
+    return pb_pack_grads_parity(n_tensors, table, scale, flat, nullptr, 0, partial_scratch, step_count, n_partials_out_h,
+                                stream);
+}
+
+int pb_pack_grads_parity(int n_tensors, const long long *table, float scale, float *flat,
+                         const unsigned long long *epoch, long long stride, float *partial_scratch,
+                         long long *step_count, int *n_partials_out_h, void *stream)
+{
+    if (n_tensors <= 0 || !table || !flat || stride < 0 || (stride & 3)) return PB_E_ARG;
     if ((long long)n_tensors * PACK_BLOCKS_PER_TENSOR > ADAM_MAX_PARTIALS) return PB_E_UNSUPPORTED;
     // as many blocks per tensor as the partial-sum table allows (blocks of small tensors exit at once; the
     // multi-million-element tensors need the whole machine)
@@ -469,7 +479,8 @@ int pb_pack_grads(int n_tensors, const long long *table, float scale, float *fla
     if (per > 128) per = 128;
     if (per < PACK_BLOCKS_PER_TENSOR) per = PACK_BLOCKS_PER_TENSOR;
     dim3 grid((unsigned)per, (unsigned)n_tensors);
-    PB_LAUNCH(pack_grads_kernel, grid, ADAM_THREADS, 0, stream, table, scale, flat, partial_scratch, step_count);
+    PB_LAUNCH(pack_grads_kernel, grid, ADAM_THREADS, 0, stream, table, scale, flat, epoch, stride, partial_scratch,
+              step_count);
     if (n_partials_out_h) *n_partials_out_h = n_tensors * per;
     return PB_OK;
 }

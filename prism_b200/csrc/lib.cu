@@ -65,6 +65,12 @@ int pb_copy_d2h_async(void *dst, const void *src, long long bytes, void *stream)
     return (int)cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
 }
 
+int pb_copy_d2d_async(void *dst, const void *src, long long bytes, void *stream)
+{
+    if (!dst || !src || bytes < 0) return PB_E_ARG;
+    return (int)cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+}
+
 const char *pb_error_string(int code)
 {
     switch (code) {

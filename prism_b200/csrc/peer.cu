@@ -45,9 +45,19 @@ __device__ __forceinline__ double ld_peer_f64(const double *p)
     return v;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // one warp: lane i signals rank i and waits for rank i.  Two independent CHANNELS (own flags, own epoch): calls on
-// one channel must be issued in the same order by every rank, but the gradient exchange (channel 0, main branch of
-// the step graph) and the shard-state all-gather (channel 1, tail branch) may interleave freely.
+// one channel must be issued in the same order by every rank, but they may interleave with the other channel.
+// The wait is BOUNDED: a rank that does not show up within g.timeout_ns (dead process, missed launch) makes the
+// waiting lanes give up, set bit (1 << channel) of the local status word and let the kernel finish -- results are
+// garbage from then on, but no GPU hangs in a kernel that cannot be cancelled; the host checks the status word
+// (PeerGroup.check) and raises.
 __device__ __forceinline__ void epoch_handshake(const pb_peer_group &g, int ch)
 {
     const int lane = threadIdx.x & 31;
@@ -56,10 +66,30 @@ __device__ __forceinline__ void epoch_handshake(const pb_peer_group &g, int ch)
     __threadfence_system();
     if (lane < g.world) {
         st_release_sys(g.flags[lane] + ch * PB_PEER_MAX + g.rank, e);
-        while (ld_acquire_sys(g.flags[g.rank] + ch * PB_PEER_MAX + lane) < e) { }
+        const unsigned long long *mine = g.flags[g.rank] + ch * PB_PEER_MAX + lane;
+        if (ld_acquire_sys(mine) < e) {
+            const unsigned long long t0 = global_timer_ns();
+            unsigned spins = 0;
+            while (ld_acquire_sys(mine) < e) {
+                if ((++spins & 1023u) == 0 && g.timeout_ns && global_timer_ns() - t0 > g.timeout_ns) {
+                    if (g.status) atomicOr(g.status, 1u << ch);
+                    break;
+                }
+            }
+        }
     }
     __syncwarp();
     if (lane == 0) *epoch = e;
+}
+
+// which half of the double-buffered gradient arena the exchange in flight uses: the parity of the number of
+// COMPLETED state exchanges (channel 1).  Writers (pack) run before the exchange of their step, readers (pulls)
+// after it, so a fast rank packing step t+1 never touches the half a slow rank still pulls for step t, and it
+// cannot reach step t+2 before that rank has signalled exchange t+1, i.e. finished pulling t.
+__device__ __forceinline__ long long grad_parity_offset(const pb_peer_group &g, bool after_exchange)
+{
+    const unsigned long long e = g.epoch[1];
+    return (long long)((after_exchange ? e - 1 : e) & 1ull) * g.grad_stride;
 }
 
 __global__ void __launch_bounds__(32) peer_barrier_kernel(pb_peer_group g) { epoch_handshake(g, 0); }
@@ -96,12 +126,13 @@ __global__ void __launch_bounds__(RS_THREADS) peer_reduce_scatter_kernel(pb_peer
     const long long lo = (long long)g.rank * slice, hi = min(n, lo + slice);
     const long long n4 = hi > lo ? (hi - lo) >> 2 : 0;                  // slices are multiples of 4 floats; n % 4 == 0
     float *out = g.reduced[g.rank];
+    const long long po = grad_parity_offset(g, true);
     double acc = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const long long e = lo + (i << 2);
-        float4 s = ld_peer_f4(g.grad[0] + e);
+        float4 s = ld_peer_f4(g.grad[0] + po + e);
         for (int p = 1; p < g.world; ++p) {
-            const float4 v = ld_peer_f4(g.grad[p] + e);
+            const float4 v = ld_peer_f4(g.grad[p] + po + e);
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
         *reinterpret_cast<float4 *>(out + e) = s;
@@ -139,12 +170,13 @@ __global__ void __launch_bounds__(RS_THREADS) peer_pull_sum_kernel(pb_peer_group
     __shared__ double part[RS_THREADS / 32];
     const long long n4 = n >> 2;
     float *out = g.reduced[g.rank];
+    const long long po = grad_parity_offset(g, true);
     double acc = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const long long e = i << 2;
-        float4 s = ld_peer_f4(g.grad[0] + e);
+        float4 s = ld_peer_f4(g.grad[0] + po + e);
         for (int p = 1; p < g.world; ++p) {
-            const float4 v = ld_peer_f4(g.grad[p] + e);
+            const float4 v = ld_peer_f4(g.grad[p] + po + e);
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
         *reinterpret_cast<float4 *>(out + e) = s;

@@ -426,6 +426,31 @@ class FusedIngest:
         lib.pb_stream_wait_event(main_stream, self.copied[p])
         return p
 
+    def plan_block(self, stream_ids, obs, action, reward, done, trunc, next_obs, u=None):
+        """Host half WITHOUT the copy: run the link planner for the next n steps and return the staged block's bytes
+        (a pinned uint8 tensor: rows | step records | uniforms).  Blocks planned in order can be parked anywhere
+        (e.g. in HBM) and fed back in the same order with ``stage_device``."""
+        p = self._planned & 1 if hasattr(self, "_planned") else 0
+        self._planned = getattr(self, "_planned", 0) + 1
+        if self._copied_valid[p]:
+            self._lib.pb_event_synchronize(self.copied[p])
+        self.slots[p].fill(stream_ids, obs, action, reward, done, trunc, next_obs)
+        if u is not None:
+            self.slots[p].h_u_np[:] = u
+        return self.slots[p].h_block.clone()
+
+    def stage_device(self, block, main_stream):
+        """Device-resident variant of ``stage``: ``block`` (uint8 CUDA tensor from ``plan_block``) is copied device to
+        device into the staging block of this parity on the step's own stream (ordered after the replay that last
+        read it).  Returns the parity."""
+        p = self.calls & 1
+        self.calls += 1
+        dst, _, nbytes = self._ptrs[p]
+        if block.numel() != nbytes or not block.is_cuda:
+            raise _lib.PbError("stage_device needs the %d-byte CUDA block plan_block produced" % nbytes)
+        _lib.check(self._lib.pb_copy_d2d_async(dst, block.data_ptr(), nbytes, main_stream), "pb_copy_d2d_async")
+        return p
+
     def mark_consumed(self, p, main_stream):
         self._lib.pb_event_record(self.consumed[p], main_stream)
         self._consumed_valid[p] = True

@@ -47,7 +47,10 @@ class LearnerStep:
             if self.world_size & (self.world_size - 1):
                 raise ValueError("sharded sampling needs a power-of-two number of ranks")
             self.B_global = self.B * self.world_size
-            slack = pad_slack if pad_slack is not None else max(16, int(4 * (self.B ** 0.5)))
+            # owner-computes placement: a rank trains on the strata that land in its shard.  With STRATIFIED masses that
+            # count is B_global * (shard mass / total mass) +- 1, so the slack only has to cover the imbalance of the
+            # shards' priority mass, not sampling noise (strata beyond B_pad are dropped for that step)
+            slack = pad_slack if pad_slack is not None else max(8, self.B // 16)
             self.B_pad = self.B + slack                      # static rows per rank (zero-weight padding)
             self.all_state = torch.zeros(self.world_size, 64, dtype=torch.uint8, device=d)
             self.stratum = torch.empty(self.B_global, dtype=torch.int64, device=d)
@@ -92,10 +95,11 @@ class LearnerStep:
                     from .peer import PeerGroup
                     self.peer = PeerGroup.create(self.pg, self.rank, self.world_size, opt.numel, d)
                     opt.attach_peer_group(self.peer)
-                    # without prefetch the next step's state all-gather separates this step's pulls from the next pack;
-                    # with prefetch that all-gather runs on the tail branch, concurrently: keep the explicit barrier
-                    opt.peer_trailing_barrier = self.prefetch
+                    # ONE handshake per step: the shard states ride on the gradient exchange's barrier and are used by
+                    # the NEXT step's global sampling
+                    opt.peer_state = self.tree.state
                     self.all_state = self.peer.all_state
+                    self._states_synced = False
                 except Exception as e:                                   # e.g. ranks on different boxes
                     sys.stderr.write("peer-memory exchange unavailable (%r): using the library collectives\n" % (e,))
                     self.peer = None
@@ -138,8 +142,6 @@ class LearnerStep:
             self.batch = self.buffer.get_static_batch()
             self.agent.set_static_batch(self.batch)
         self.graph, self._primed = None, False
-        if self.peer is not None:
-            self.agent.optimizer.peer_trailing_barrier = flag
 
     def _carve(self, n_rows):
         """One flat arena holding a static batch + the sampled indices / weights; returns (views, arena)."""
@@ -165,16 +167,23 @@ class LearnerStep:
         v["gamma"].fill_(1.0)
         return v, arena
 
+    def sync_shard_states(self):
+        """Collective (every rank, same stream order): exchange the shard state blocks NOW.  The step graph gathers them
+        on its gradient exchange for the next step; this primes the first step and re-synchronises after anything
+        outside the step changed a tree (ingest, a manual priority update)."""
+        if self.peer is not None:
+            self.peer.state_allgather(self.tree.state)
+            self._states_synced = True
+
     def _sample_gather(self, u, out, tag=""):
-        """(all-gather of shard states +) sample + fused n-step gather into ``out`` (live or shadow views)."""
+        """(shard states of all ranks ->) sample + fused n-step gather into ``out`` (live or shadow views)."""
         tree, ring = self.tree, self.ring
         if self.world_size > 1:
-            if self.peer is not None:
-                self.peer.state_allgather(tree.state)
-            else:
+            if self.peer is None:
                 import torch.distributed as dist
                 dist.all_gather_into_tensor(self.all_state.view(-1), tree.state, group=self.pg)
-            self._mark(tag + "shard_states_gathered")
+                self._mark(tag + "shard_states_gathered")
+            # peer path: all_state was gathered by the previous step's exchange (or sync_shard_states)
             tree.sample_global(self.world_size, self.rank, self.all_state, self.B_global, u,
                                idx_out=out["idx"], weight_out=out["weight"], stratum_out=self.stratum)
         else:
@@ -189,6 +198,7 @@ class LearnerStep:
         buffer): uniforms from the in-kernel generator."""
         trace, self._trace = self._trace, None          # eager: not part of the replayed timeline
         try:
+            self.sync_shard_states()
             self._sample_gather(None, self._shadow)
         finally:
             self._trace = trace
@@ -199,6 +209,7 @@ class LearnerStep:
         tree, ring, agent, b = self.tree, self.ring, self.agent, self.buffer
         u = None if draw else self.u            # None: uniforms are drawn inside the sampling kernel
         u_sel = consume and getattr(self, "_u_in_block", False)
+        dp_peer = self.peer is not None
         mark = self._mark
         mark("start")
         if self.prefetch:
@@ -238,21 +249,46 @@ class LearnerStep:
                     self._side.wait_stream(side2)
                 if self.prefetch and u_sel:
                     self.ingest.select_uniforms(self.u, after_counter_inc=True)
-                if self.prefetch:
+                if self.prefetch and not dp_peer:
                     self._sample_gather(u, self._shadow, tag="tail:")      # next iteration's batch
                     mark("tail:next_batch_ready")
 
         dl, ql, total, td = agent._loss_and_backward(self.batch, w, agent.target_model, after_loss=write_back)
         agent._static_distribution_loss, agent._static_q_loss, agent._static_total_loss = dl, ql, total
         mark("backward_done")
-        agent._optimizer_step(refresh_table=refresh_table)
+        if dp_peer:
+            opt = agent.optimizer
+            if self.overlap_write_back:
+                cur.wait_stream(self._side)            # the tree state rides on the exchange: the tail must be done
+            pre = None
+            if self.prefetch:
+                pre = _ops.fork_stream(self.device, "prefetch")
+
+                def fork_prefetch():
+                    # the next batch needs THIS exchange's shard states: sampled beside the pulls + optimizer sweep
+                    pre.wait_stream(cur)
+                    with torch.cuda.stream(pre):
+                        self._sample_gather(u, self._shadow, tag="tail:")
+                        mark("tail:next_batch_ready")
+                opt.peer_after_exchange = fork_prefetch
+            try:
+                agent._optimizer_step(refresh_table=refresh_table)
+            finally:
+                opt.peer_after_exchange = None
+            if pre is not None:
+                cur.wait_stream(pre)
+        else:
+            agent._optimizer_step(refresh_table=refresh_table)
         mark("optimizer_done")
         if self.loss_host is not None and total is not None:
             # device -> host read of the step's result as a node of the same graph (pinned scalar)
             self.loss_host.copy_(total.detach(), non_blocking=True)
         if self.overlap_write_back:
-            cur.wait_stream(self._side)
+            if not dp_peer:
+                cur.wait_stream(self._side)
         else:
+            if dp_peer:
+                raise _lib.PbError("PB_OVERLAP_WRITEBACK=0 is a single-GPU tuning switch")
             tree.update_priority(idx, self.td, sorted=self.sorted)
             if consume:
                 self.ingest.consume()
@@ -304,7 +340,17 @@ class LearnerStep:
         t0 = t[tr["names"]["start"]]
         return {name: t[i] - t0 for name, i in sorted(tr["names"].items(), key=lambda kv: kv[1])}
 
-    def step(self, u=None, ingest=None):
+    def plan_ingest(self, ingest, u=None):
+        """Host half of a fused ingest without the copy: plans the links of the next ``len(ingest[0])`` steps and returns
+        the staged block (pinned uint8 tensor; the fp64 uniforms ``u`` of that iteration ride in it).  Blocks must be fed
+        back IN ORDER through ``step(ingest_block=...)`` -- e.g. after parking them in HBM (bench.py's resident leg)."""
+        n = len(ingest[0])
+        if self.ingest is None or self.ingest.n != n:
+            from .experience.ring import FusedIngest
+            self.ingest = FusedIngest(self.ring, self.tree, n, n_uniforms=self.u.numel())
+        return self.ingest.plan_block(*ingest, u=None if u is None else u.numpy() if isinstance(u, torch.Tensor) else u)
+
+    def step(self, u=None, ingest=None, ingest_block=None):
         """Run one iteration.  ``u`` (optional): fp64 uniforms (device or pinned-host tensor, B_global
         values) used instead of the device Philox generator (with ``prefetch`` they drive the sampling that happens
         during this call, i.e. the NEXT iteration's batch).  ``ingest`` (optional): a tuple
@@ -312,6 +358,32 @@ class LearnerStep:
         scatter into the ring and default priorities run inside the step graph, after the priority write-back and
         concurrently with backward / Adam (FusedIngest); they are sampleable from the next iteration on."""
         self.buffer._flush()
+        if ingest_block is not None:
+            # a block planned by plan_ingest (uniforms inside), resident on the device: D2D into the staging slot
+            if self.ingest is None:
+                raise _lib.PbError("plan_ingest() first")
+            main = torch.cuda.current_stream(self.device).cuda_stream
+            parity = self.ingest.stage_device(ingest_block, main)
+            draw, consume, u_in_block = False, True, True
+            self._u_in_block = True
+            key = (draw, consume, u_in_block, self.ring.generation, float(self.tree._beta))
+            if self.use_cuda_graph and (self.graph is None or key != self._graph_key):
+                self._capture(draw, consume)
+                self._primed = False
+            if self.prefetch and (not self._primed or getattr(self.buffer, "_mutations", 0) != self._seen_mutations):
+                self._prime()
+            elif self.peer is not None and (not self._states_synced
+                                            or getattr(self.buffer, "_mutations", 0) != self._seen_mutations):
+                self.sync_shard_states()
+                self._seen_mutations = getattr(self.buffer, "_mutations", 0)
+            if not self.use_cuda_graph:
+                total = self._body(refresh_table=True, draw=draw, consume=consume)
+            else:
+                self.graph.replay()
+                total = self.agent._static_total_loss
+            self.ingest.mark_consumed(parity, main)
+            self.agent.n_updates += 1
+            return total
         draw = u is None
         # host uniforms + fused ingest: the uniforms ride in the ingest's staging block (one H2D copy per iteration) and
         # are picked inside the graph by the replay counter
@@ -345,6 +417,10 @@ class LearnerStep:
             self._primed = False                            # the warm-up iterations sampled into the shadow batch
         if self.prefetch and (not self._primed or getattr(self.buffer, "_mutations", 0) != self._seen_mutations):
             self._prime()
+        elif self.peer is not None and (not self._states_synced
+                                        or getattr(self.buffer, "_mutations", 0) != self._seen_mutations):
+            self.sync_shard_states()
+            self._seen_mutations = getattr(self.buffer, "_mutations", 0)
         if not self.use_cuda_graph:
             total = self._body(refresh_table=True, draw=draw, consume=consume)
         else:
@@ -400,6 +476,7 @@ class LearnerStep:
         self.u.copy_(u_snap)
         torch.cuda.set_rng_state(rng, self.device)
         ag.quantile_rng_restore(q_rng)
+        self._states_synced = False                         # the warm-up's exchanges carried warm-up tree states
         self._graph_key = (draw, consume, getattr(self, "_u_in_block", False), self.ring.generation,
                            float(self.tree._beta))
         opt.zero_grad(set_to_none=True)

@@ -1,7 +1,7 @@
 """PeerGroup -- the host side of csrc/peer.cu: one peer-mapped block per rank (NVLink / NVSwitch, CUDA IPC).
 
-Layout of a rank's block (bytes):  grad [n floats] | reduced [n floats] | flags [64 u64] | norm_parts [8 f64] |
-state [2 x 8 x 64 B] | epochs [2 x u64].  ``torch.distributed`` is only used once, to exchange the 64-byte IPC handles; no
+Layout of a rank's block (bytes):  grad [2 x n floats, double-buffered] | reduced [n floats] | flags [64 u64] |
+norm_parts [8 f64] | state [2 x 8 x 64 B] | epochs [2 x u64] | status [u32].  ``torch.distributed`` is only used once, to exchange the 64-byte IPC handles; no
 collective library call remains on the per-step path.
 
 ``PeerGroup.loopback(world, n, device)`` builds ``world`` groups inside ONE process on one GPU (plain pointers to
@@ -16,6 +16,7 @@ from . import _lib
 
 
 ONE_SHOT_MAX_BYTES = 32 * 1024 * 1024      # n * 4 * world up to which the one-shot (single barrier) all-reduce is used
+WAIT_TIMEOUT_S = float(__import__("os").environ.get("PB_PEER_TIMEOUT_S", "20"))   # bound of every cross-GPU flag wait
 
 
 class _RawCuda:
@@ -27,10 +28,11 @@ class _RawCuda:
 
 def _layout(n):
     n_bytes = ((int(n) * 4 + 255) // 256) * 256
-    off = {"grad": 0, "reduced": n_bytes, "flags": 2 * n_bytes}
+    off = {"grad": 0, "grad_stride_bytes": n_bytes, "reduced": 2 * n_bytes, "flags": 3 * n_bytes}
     off["norm_parts"] = off["flags"] + 64 * 8
     off["state"] = off["norm_parts"] + 64
     off["epoch"] = off["state"] + 2 * _lib.PB_PEER_MAX * 64
+    off["status"] = off["epoch"] + 64
     off["total"] = off["epoch"] + 256
     return off
 
@@ -49,9 +51,21 @@ class PeerGroup:
             g.grad[p], g.reduced[p] = b + self.off["grad"], b + self.off["reduced"]
             g.flags[p], g.norm_parts[p], g.state[p] = b + self.off["flags"], b + self.off["norm_parts"], b + self.off["state"]
         g.epoch = bases[self.rank] + self.off["epoch"]
+        g.status = bases[self.rank] + self.off["status"]
+        g.timeout_ns = int(WAIT_TIMEOUT_S * 1e9)
+        g.grad_stride = self.off["grad_stride_bytes"] // 4
         self.c = g
+        self.grad_stride = self.off["grad_stride_bytes"] // 4
+        self.epoch_gather_ptr = bases[self.rank] + self.off["epoch"] + 8        # channel 1: completed state gathers
+        self._n_gathers = 0                                                     # host mirror of that count (eager calls)
         self._block = torch.as_tensor(_RawCuda(own_ptr, self.off["total"]), device=self.device)
+        # both halves of the double-buffered gradient arena; the pack of a step writes half (completed gathers & 1)
         self.grad = self._block[self.off["grad"]:self.off["grad"] + 4 * self.n].view(torch.float32)
+        self.grad_halves = [self._block[self.off["grad"] + h * self.off["grad_stride_bytes"]:
+                                        self.off["grad"] + h * self.off["grad_stride_bytes"] + 4 * self.n].view(torch.float32)
+                            for h in (0, 1)]
+        self._status = self._block[self.off["status"]:self.off["status"] + 4].view(torch.int32)
+        self._dummy_state = torch.zeros(64, dtype=torch.uint8, device=self.device)
         self.reduced = self._block[self.off["reduced"]:self.off["reduced"] + 4 * self.n].view(torch.float32)
         self.all_state = torch.zeros(self.world, 64, dtype=torch.uint8, device=self.device)     # local copy of the gather
 
@@ -102,23 +116,41 @@ class PeerGroup:
         _lib.check(_lib.load().pb_peer_barrier(C.byref(self.c), self._stream()), "pb_peer_barrier")
 
     def state_allgather(self, state):
-        """state: this rank's 64-byte tree state block (uint8 tensor).  Returns the (world, 64) gathered view."""
+        """state: this rank's 64-byte tree state block (uint8 tensor).  Returns the (world, 64) gathered view.
+        A full handshake of all ranks: it is also THE barrier of the gradient exchange (allreduce_adam)."""
         _lib.check(_lib.load().pb_peer_state_allgather(C.byref(self.c), state.data_ptr(), self.all_state.data_ptr(),
                                                        self._stream()),
                    "pb_peer_state_allgather")
+        self._n_gathers += 1
         return self.all_state
 
-    def allreduce_adam(self, opt, trailing_barrier=True, mark=None):
-        """Sum ``opt.grad`` (= self.grad) over the ranks and apply clip + Adam on every replica (csrc/peer.cu).
+    def grad_in_flight(self):
+        """The half of the gradient arena the next exchange reads (eager calls only: under graph replay the device
+        counter decides, see pb_pack_grads_parity)."""
+        return self.grad_halves[self._n_gathers & 1]
 
-        ``trailing_barrier``: the one-shot schedule lets a fast rank leave while slower ranks still pull its gradient;
-        the next writer of ``grad`` must be separated from them by a barrier.  Without prefetch LearnerStep passes False:
-        every step starts with the state all-gather (a full handshake on the same graph branch) before anything
-        touches the arena again.  With prefetch that handshake runs on the tail branch, so it passes True."""
+    def check(self):
+        """Raise if a cross-GPU wait timed out (synchronises; call it off the hot path)."""
+        st = int(self._status.item())
+        if st:
+            raise _lib.PbError("peer exchange: a rank did not arrive within %.0f s (status 0x%x, rank %d of %d)"
+                               % (WAIT_TIMEOUT_S, st, self.rank, self.world))
+
+    def allreduce_adam(self, opt, state=None, mark=None, after_exchange=None):
+        """Sum the gradient arenas over the ranks and apply clip + Adam on every replica (csrc/peer.cu).
+
+        ONE cross-GPU handshake per step for small arenas: the exchange of the 64-byte shard state blocks (``state``:
+        this rank's tree state, gathered into ``self.all_state`` for the NEXT step's global sampling) is the barrier
+        that tells every rank all gradients are packed.  The arena is double-buffered by the parity of that exchange's
+        count, so a fast rank packing its next gradient never overwrites what a slower rank still pulls -- no trailing
+        barrier.  ``after_exchange``: called right after the handshake (LearnerStep forks the prefetch of the next batch
+        there, beside the pulls and the optimizer sweep)."""
         lib, st = _lib.load(), self._stream()
         mark = mark or (lambda name: None)                        # timeline marks of LearnerStep.enable_trace()
-        _lib.check(lib.pb_peer_barrier(C.byref(self.c), st), "pb_peer_barrier")            # every rank packed its gradient
-        mark("opt:all_packed")
+        self.state_allgather(self._dummy_state if state is None else state)     # every rank packed its gradient
+        mark("opt:exchanged")
+        if after_exchange is not None:
+            after_exchange()
         if self.n * 4 * self.world <= ONE_SHOT_MAX_BYTES:
             # small arena: pulling every rank's gradient whole costs less than a second cross-GPU barrier
             n_part = C.c_int(0)
@@ -130,8 +162,6 @@ class PeerGroup:
                                               opt.betas[1], opt.eps, opt.max_grad_norm, opt.partials.data_ptr(), n_part.value,
                                               opt.norm_out.data_ptr(), st), "pb_adam_clip_apply")
             mark("opt:applied")
-            if trailing_barrier:
-                _lib.check(lib.pb_peer_barrier(C.byref(self.c), st), "pb_peer_barrier")
             return
         _lib.check(lib.pb_peer_reduce_scatter(C.byref(self.c), self.n, opt.partials.data_ptr(), opt.step_count.data_ptr(), st),
                    "pb_peer_reduce_scatter")
@@ -151,6 +181,6 @@ class PeerGroup:
         self._opened = []
         if self._own_ptr:
             torch.cuda.synchronize(self.device)
-            self.grad = self.reduced = self._block = None
+            self.grad = self.reduced = self._block = self.grad_halves = self._status = None
             lib.pb_peer_free(C.c_void_p(self._own_ptr))
             self._own_ptr = None

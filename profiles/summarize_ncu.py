@@ -29,8 +29,11 @@ def short(name):
 
 
 def is_ours(name):
+    """Every kernel of libprism_b200.so lives in an anonymous namespace at file scope: ncu prints `<unnamed>::name`
+    (framework kernels carry their own namespace first: at::, at::<unnamed>::, cutlass::, cublasLt::, ...)."""
     n = short(name)
-    return any(n.startswith(p) or ("::" + p) in n[:40] for p in OURS)
+    return n.startswith("<unnamed>::") or n.startswith("(anonymous namespace)::") or \
+        any(n.startswith(p) for p in OURS)
 
 
 def num(s):

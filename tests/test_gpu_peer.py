@@ -46,7 +46,7 @@ def test_peer_allreduce_adam_matches_single_rank_step(world, n, one_shot, monkey
     for it in range(3):                                       # three steps: epochs, ticket and step counter carry over
         for r in range(world):
             with torch.cuda.stream(streams[r]):
-                groups[r].grad.copy_(staged[it][r])
+                groups[r].grad_in_flight().copy_(staged[it][r])     # the half this step's exchange reads
                 groups[r].allreduce_adam(opts[r])
     torch.cuda.synchronize()
     # reference: the single-rank fused step on the rank-order fp32 sum
@@ -85,3 +85,17 @@ def test_peer_state_allgather_and_barrier():
         want = torch.stack(states)
         for r in range(world):
             assert torch.equal(groups[r].all_state, want)
+
+
+def test_a_missing_rank_times_out_instead_of_hanging(monkeypatch):
+    """Verdict r1 #8: the flag wait is bounded.  Rank 1 of a 2-rank loopback group never launches; rank 0's barrier
+    gives up after the timeout, sets its status word, and PeerGroup.check() raises."""
+    from prism_b200 import _lib, peer as peer_mod
+    from prism_b200.peer import PeerGroup
+    monkeypatch.setattr(peer_mod, "WAIT_TIMEOUT_S", 0.2)
+    groups = PeerGroup.loopback(2, 1024, DEV)
+    groups[0].check()
+    groups[0].barrier()
+    torch.cuda.synchronize()                                  # returns: the kernel gave up after ~0.2 s
+    with pytest.raises(_lib.PbError):
+        groups[0].check()
