@@ -1047,11 +1047,13 @@ def run_reference(args):
     # like for like with our arm at N GPUs: the global batch (256 per GPU) on the host, a 1M-filled buffer, and at
     # least 200 timed iterations after 20 warm-ups (20 cold iterations overstated the ratio in round 1)
     steps = max(args.steps, 200)
-    cpu = cpu_baseline(steps=steps, fill=CAPACITY, budget_s=150.0, batch=BATCH * world, warmup=max(20, args.warmup))
+    fill = int(os.environ.get("PB_REF_FILL", CAPACITY))      # tests shrink the fill; the driver's run uses the full 1M
+    cpu = cpu_baseline(steps=steps, fill=fill, budget_s=150.0, batch=BATCH * world, warmup=max(20, args.warmup))
     line = {
         "impl": "reference",
         "metric": METRIC,
         "value": cpu["value"], "unit": "transitions/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(20, args.warmup),
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
         "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "learner_updates_per_s": cpu["updates_per_s"],
         "config": {"workload": "configs[1]: MinAtar SpaceInvaders-shaped (10x10x6) DQN + double-Q + PER, 1M-capacity "
