@@ -73,6 +73,10 @@ class Agent(object):
             def body():
                 q, z = model._forward_without_cuda_graph(static_in, for_action=True)
                 return selector.select_action(selector.generate_action_probs(z, q))
+            d = getattr(model, "distribution_model", None)
+            if d is not None and hasattr(d, "_rng_state"):
+                d._rng_state()
+            q_rng = self.quantile_rng_snapshot()               # warm-up and capture must not consume quantile draws
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
@@ -82,6 +86,7 @@ class Agent(object):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 static_out = body()
+            self.quantile_rng_restore(q_rng)
             entry = graphs[key] = (g, static_in, static_out)
         g, static_in, static_out = entry
         static_in.copy_(obs, non_blocking=True)

@@ -522,15 +522,15 @@ class _LayerNorm(torch.autograd.Function):
     LayerNorm on the SHARED embedding (q_ensemble.py:26-48), are one launch instead of F.layer_norm + addcmul."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, groups):
+    def forward(ctx, x, weight, bias, eps, groups, heads=False):
         xc = _c(x)
         F_ = xc.shape[-1]
         x_rows = xc.numel() // F_
-        shared = groups > 1 and xc.dim() == 2                    # (B, F) shared by the heads -> (K, B, F)
-        rpg = x_rows if (groups == 1 or shared) else x_rows // groups
+        shared = heads and xc.dim() == 2                         # (B, F) shared by the heads -> (K, B, F)
+        rpg = x_rows if (not heads or shared) else x_rows // groups
         rows = groups * rpg
         need = any(ctx.needs_input_grad[:3])
-        y = torch.empty((groups, rpg, F_) if groups > 1 else xc.shape, dtype=torch.float32, device=x.device)
+        y = torch.empty((groups, rpg, F_) if heads else xc.shape, dtype=torch.float32, device=x.device)
         mean = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
         wc = None if weight is None else _c(weight)
@@ -541,19 +541,19 @@ class _LayerNorm(torch.autograd.Function):
         if need:
             ctx.save_for_backward(xc, wc, mean, rstd)
             ctx.has_affine = (weight is not None, bias is not None)
-            ctx.meta = (int(groups), int(rpg), int(x_rows), F_, shared)
+            ctx.meta = (int(groups), int(rpg), int(x_rows), F_, shared, bool(heads))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         xc, wc, mean, rstd = ctx.saved_tensors
-        groups, rpg, x_rows, F_, shared = ctx.meta
+        groups, rpg, x_rows, F_, shared, heads = ctx.meta
         dy = _c(dy)
         lib = _lib.load()
         nb = lib.pb_layer_norm_grouped_bwd_blocks(groups, rpg, F_)
         partials = torch.empty(2 * groups * nb * F_, dtype=torch.float32, device=dy.device)
-        dx = torch.empty((groups, rpg, F_) if groups > 1 else xc.shape, dtype=torch.float32, device=dy.device)
-        shape_p = (groups, F_) if groups > 1 else (F_,)
+        dx = torch.empty((groups, rpg, F_) if heads else xc.shape, dtype=torch.float32, device=dy.device)
+        shape_p = (groups, F_) if heads else (F_,)
         dg = torch.empty(shape_p, dtype=torch.float32, device=dy.device) if ctx.has_affine[0] else None
         db = torch.empty(shape_p, dtype=torch.float32, device=dy.device) if ctx.has_affine[1] else None
         _lib.check(lib.pb_layer_norm_grouped_bwd(groups, rpg, x_rows, F_, xc.data_ptr(), dy.data_ptr(), _lib.ptr(wc),
@@ -563,7 +563,7 @@ class _LayerNorm(torch.autograd.Function):
             dx = None
         elif shared:
             dx = sum_leading(dx)                                  # the heads share their input
-        return dx, dg, db, None, None
+        return dx, dg, db, None, None, None
 
 
 def _ln_supported(x, F_):
@@ -575,7 +575,7 @@ def layer_norm(x, module):
     """nn.LayerNorm module applied through the fused kernels (any number of rows)."""
     if x.dim() == 2 and len(module.normalized_shape) == 1 and _ln_supported(x, x.shape[1]):
         ROUTES["ln:fused"] += 1
-        return _LayerNorm.apply(x, module.weight, module.bias, module.eps, 1)
+        return _LayerNorm.apply(x, module.weight, module.bias, module.eps, 1, False)
     ROUTES["fallthrough:nn.LayerNorm"] += 1
     return module(x)
 
@@ -586,7 +586,7 @@ def layer_norm_heads(x, weight, bias, eps=1e-5):
     K, F_ = weight.shape
     if _ln_supported(x, F_) and (x.dim() == 2 or (x.dim() == 3 and x.shape[0] == K)):
         ROUTES["ln:fused_heads"] += 1
-        return _LayerNorm.apply(x, weight, bias, eps, K)
+        return _LayerNorm.apply(x, weight, bias, eps, K, True)
     ROUTES["fallthrough:F.layer_norm+addcmul"] += 1
     normed = torch.nn.functional.layer_norm(x, (F_,), eps=eps)
     return torch.addcmul(bias.unsqueeze(1), normed if x.dim() == 3 else normed.unsqueeze(0), weight.unsqueeze(1))

@@ -10,7 +10,7 @@
 //  * one primitive everywhere: 32 sibling nodes (one aligned 128-byte line) are reduced over 5 levels in registers
 //    and shuffles.  The rebuilt intermediate values are bit-identical to the nodes a pointer-walking tree would
 //    store, so they are NOT stored: the tree keeps only every 5th level below its top ("compact" layout)
-//        levels 0 .. TL          one level-ordered heap array (TL <= 14: <= 128 KB, L1/L2 resident)
+//        levels 0 .. TL          one level-ordered heap array (TL <= 9: <= 4 KB)
 //        levels TL+5, TL+10, .., L   one array per level; L = leaves
 //    and the min tree shares the leaf array of the sum tree (a leaf is written with the same value in both;
 //    slots that were never written -- index >= len -- read as +inf on the min side).
@@ -33,7 +33,7 @@ namespace {
 
 using namespace pb;
 
-constexpr int TOP_MAX = 14;        // the top heap holds levels [0, TL], TL <= 14
+constexpr int TOP_MAX = 9;         // the top heap holds levels [0, TL], TL <= 9: rebuilt whole by ONE CTA after every update
 constexpr int MAX_DEEP = 8;        // stored levels below the heap (capacity <= 2^30 -> at most 4)
 
 struct TreeView {
@@ -69,6 +69,15 @@ __device__ __forceinline__ float *leaf_ptr(const TreeView &t) { return sum_level
 __device__ __forceinline__ float min_of_leaf(float v, long long i, long long len) { return i < len ? v : INF; }
 
 __device__ __forceinline__ float ldcg(const float *p) { return __ldcg(p); }
+
+// arrival-counter update with release (my node store is visible to whoever reads the counter after me) and acquire
+// (I see the node stores of everyone who updated it before me) semantics in ONE instruction -- no MEMBAR.SC
+__device__ __forceinline__ int atom_add_acq_rel(int *p, int v)
+{
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
 
 __device__ __forceinline__ float pow_leaf(float p, const TreeView &t)
 {
@@ -137,11 +146,12 @@ __device__ float node_value(const TreeView &t, int d, long long i, long long len
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         if (k < (1 << r)) {
+            // L2 loads: the state block is finalised by the last CTA of a launch whose other CTAs wrote these nodes
             if (s == t.L) {
-                float x = leaf_ptr(t)[base + k];
+                float x = ldcg(leaf_ptr(t) + base + k);
                 v[k] = IS_MIN ? min_of_leaf(x, base + k, len) : x;
             } else {
-                v[k] = IS_MIN ? min_level(t, s)[base + k] : sum_level(t, s)[base + k];
+                v[k] = IS_MIN ? ldcg(min_level(t, s) + base + k) : ldcg(sum_level(t, s) + base + k);
             }
         } else {
             v[k] = ident;
@@ -165,7 +175,7 @@ template <bool IS_MIN>
 __device__ float tree_query_prefix(const TreeView &t, long long len)
 {
     const float ident = IS_MIN ? INF : 0.0f;
-    if (len >= t.size) return IS_MIN ? (t.L == 0 ? min_of_leaf(leaf_ptr(t)[0], 0, len) : t.min[1]) : t.sum[1];
+    if (len >= t.size) return IS_MIN ? ldcg(t.min + 1) : ldcg(t.sum + 1);
     if (len <= 0) return ident;
     const int k = lane_id();
     float v = ident;
@@ -265,14 +275,12 @@ __device__ void top_rebuild(const TreeView &t, float *sm, long long len)
 __device__ bool last_cta(const TreeView &t)
 {
     __shared__ int is_last;
-    __threadfence();
-    __syncthreads();
+    __syncthreads();                                  // the CTA's stores happen-before thread 0's release below
     if (threadIdx.x == 0) {
-        const int ticket = atomicAdd(&t.st->pad[0], 1);
+        const int ticket = atom_add_acq_rel(&t.st->pad[0], 1);
         is_last = (ticket == (int)gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last) __threadfence();
     return is_last != 0;
 }
 
@@ -315,64 +323,109 @@ __global__ void tree_stats_kernel(TreeView t)
 
 // ---------------------------------------------------------------------------------
 // streaming rebuild: every line of level s is reduced to its node of level s-5 and, when that level is stored
-// too, on to level s-10.  Tile = 1024 source nodes per CTA iteration (256 threads x float4, 8 lanes per line);
-// persistent grid.  s == L reads the shared leaf array (optionally first loading it from `ext`, the bulk build).
+// too, on to level s-10.  Warp-autonomous, no shared memory: per iteration a warp streams 1024 consecutive source
+// nodes with 8 coalesced float4 loads per lane in flight (8 lanes per 128-byte line), reduces every line in
+// registers + 3 shuffle levels, transposes the 32 line totals into one lane each with shuffles (= one coalesced
+// 128-byte store of level s-5) and reduces those 5 more levels for the node of level s-10.  Persistent grid.
+// s == L reads the shared leaf array (optionally first loading it from `ext`, the bulk build).
 // FUSE_TOP: the last CTA (ticket) rebuilds the top heap and the state block.
 // ---------------------------------------------------------------------------------
 constexpr int RB_THREADS = 256;
-constexpr int RB_TILE = RB_THREADS * 4;
+constexpr int RB_TILE = 1024;                                    // source nodes per warp iteration
 
-__global__ void __launch_bounds__(RB_THREADS) tree_rebuild_kernel(TreeView t, int s, int two_levels, const float *ext,
+// n_lv = 1, 2 or 3 levels per pass (s-5, s-10, s-15).  The third level needs 32 warp tiles in one CTA: a CTA then takes
+// 32768 consecutive source nodes per iteration (4 warp tiles per warp) and combines their level s-10 nodes through
+// shared memory.
+__global__ void __launch_bounds__(RB_THREADS) tree_rebuild_kernel(TreeView t, int s, int n_lv, const float *ext,
                                                                   long long n_ext, int fuse_top, int mode,
                                                                   long long n_new, long long set_len)
 {
     __shared__ float sm_top[2 * TOP_SM_FLOATS];
-    __shared__ float part_s[32], part_m[32];
+    __shared__ float l2s[32], l2m[32];
+    const int two_levels = n_lv >= 2;
     const long long len = len_after(t, mode, n_new, set_len);
     const bool leaves = (s == t.L);
-    const float *src_s = sum_level(t, s);
+    float *src_s = sum_level(t, s);
     const float *src_m = leaves ? src_s : min_level(t, s);
     float *dst1_s = sum_level(t, s - 5), *dst1_m = min_level(t, s - 5);
     const long long n_tiles = (1LL << s) / RB_TILE;
-    const int lane = lane_id(), grp = threadIdx.x >> 3;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long base = tile * RB_TILE + (long long)threadIdx.x * 4;
-        float4 a, m;
+    const int lane = lane_id();
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    // n_lv < 3: warps stride over the warp tiles on their own.  n_lv == 3: CTAs stride over groups of 32 warp tiles.
+    const int wic = threadIdx.x >> 5;                            // warp in CTA (RB_THREADS / 32 = 8 of them)
+    const long long n_outer = n_lv == 3 ? n_tiles / 32 : 1;
+    for (long long outer = n_lv == 3 ? blockIdx.x : 0; outer < n_outer; outer += n_lv == 3 ? gridDim.x : 1) {
+    const long long t_first = n_lv == 3 ? outer * 32 + wic : (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const long long t_step = n_lv == 3 ? RB_THREADS / 32 : n_warps;
+    const long long t_end = n_lv == 3 ? outer * 32 + 32 : n_tiles;
+    for (long long tile = t_first; tile < t_end; tile += t_step) {
+        const long long base = tile * RB_TILE + lane * 4;        // load q covers nodes base + 128 q .. + 3
+        float4 a[8], m[8];
         if (ext) {
-            if (base + 4 <= n_ext) a = *reinterpret_cast<const float4 *>(ext + base);
-            else {
-                a.x = base + 0 < n_ext ? ext[base + 0] : 0.0f; a.y = base + 1 < n_ext ? ext[base + 1] : 0.0f;
-                a.z = base + 2 < n_ext ? ext[base + 2] : 0.0f; a.w = base + 3 < n_ext ? ext[base + 3] : 0.0f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const long long e = base + 128 * q;
+                if (e + 4 <= n_ext) a[q] = __ldcs(reinterpret_cast<const float4 *>(ext + e));
+                else {
+                    a[q].x = e + 0 < n_ext ? ext[e + 0] : 0.0f; a[q].y = e + 1 < n_ext ? ext[e + 1] : 0.0f;
+                    a[q].z = e + 2 < n_ext ? ext[e + 2] : 0.0f; a[q].w = e + 3 < n_ext ? ext[e + 3] : 0.0f;
+                }
             }
-            *reinterpret_cast<float4 *>(sum_level(t, s) + base) = a;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) *reinterpret_cast<float4 *>(src_s + base + 128 * q) = a[q];
         } else {
-            a = __ldcs(reinterpret_cast<const float4 *>(src_s + base));
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a[q] = __ldcg(reinterpret_cast<const float4 *>(src_s + base + 128 * q));
         }
         if (leaves) {
-            m.x = min_of_leaf(a.x, base + 0, len); m.y = min_of_leaf(a.y, base + 1, len);
-            m.z = min_of_leaf(a.z, base + 2, len); m.w = min_of_leaf(a.w, base + 3, len);
-        } else {
-            m = __ldcs(reinterpret_cast<const float4 *>(src_m + base));
-        }
-        float vs = op_sum(op_sum(a.x, a.y), op_sum(a.z, a.w));
-        float vm = op_min(op_min(m.x, m.y), op_min(m.z, m.w));
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            vs = op_sum(vs, __shfl_xor_sync(FULL, vs, 1 << k));
-            vm = op_min(vm, __shfl_xor_sync(FULL, vm, 1 << k));
+            for (int q = 0; q < 8; ++q) {
+                const long long e = base + 128 * q;
+                m[q] = a[q];
+                if (e + 4 > len) {
+                    m[q].x = min_of_leaf(a[q].x, e + 0, len); m[q].y = min_of_leaf(a[q].y, e + 1, len);
+                    m[q].z = min_of_leaf(a[q].z, e + 2, len); m[q].w = min_of_leaf(a[q].w, e + 3, len);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) m[q] = __ldcg(reinterpret_cast<const float4 *>(src_m + base + 128 * q));
         }
-        if ((threadIdx.x & 7) == 0) { part_s[grp] = vs; part_m[grp] = vm; }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            float ps = part_s[lane], pm = part_m[lane];
-            dst1_s[tile * 32 + lane] = ps;                       // 32 nodes of level s-5: one coalesced line
-            dst1_m[tile * 32 + lane] = pm;
-            if (two_levels) {
-                line_reduce(ps, pm);
-                if (lane == 0) { sum_level(t, s - 10)[tile] = ps; min_level(t, s - 10)[tile] = pm; }
+        // line totals: load q holds 4 lines (8 lanes each); afterwards lane l owns line l of the tile
+        float ps = 0.0f, pm = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float vs = op_sum(op_sum(a[q].x, a[q].y), op_sum(a[q].z, a[q].w));
+            float vm = op_min(op_min(m[q].x, m[q].y), op_min(m[q].z, m[q].w));
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                vs = op_sum(vs, __shfl_xor_sync(FULL, vs, 1 << k));
+                vm = op_min(vm, __shfl_xor_sync(FULL, vm, 1 << k));
+            }
+            // line 4q + g sits in the lanes of group g: hand it to lane 4q + g
+            const float gs = __shfl_sync(FULL, vs, (lane & 3) << 3);
+            const float gm = __shfl_sync(FULL, vm, (lane & 3) << 3);
+            if ((lane >> 2) == q) { ps = gs; pm = gm; }
+        }
+        dst1_s[tile * 32 + lane] = ps;                           // 32 nodes of level s-5: one coalesced line
+        dst1_m[tile * 32 + lane] = pm;
+        if (two_levels) {
+            line_reduce(ps, pm);
+            if (lane == 0) {
+                sum_level(t, s - 10)[tile] = ps; min_level(t, s - 10)[tile] = pm;
+                if (n_lv == 3) { l2s[tile & 31] = ps; l2m[tile & 31] = pm; }
             }
         }
+    }
+    if (n_lv == 3) {
         __syncthreads();
+        if (wic == 0) {
+            float ps = l2s[lane], pm = l2m[lane];
+            line_reduce(ps, pm);
+            if (lane == 0) { sum_level(t, s - 15)[outer] = ps; min_level(t, s - 15)[outer] = pm; }
+        }
+        __syncthreads();
+    }
     }
     if (!fuse_top) return;
     if (!last_cta(t)) return;
@@ -591,11 +644,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS) upd_chain_kernel(TreeView t, lo
         for (int m = P - 1; m >= 1; --m) {
             const long long pl = g >> 5;
             int newv = 0;
-            __threadfence();
-            if (lane == 0) newv = atomicAdd(&t.cnt[t.coff[m] + pl], -1) - 1;
+            if (lane == 0) newv = atom_add_acq_rel(&t.cnt[t.coff[m] + pl], -1) - 1;     // releases lane 0's node store
             newv = __shfl_sync(FULL, newv, 0);
             if (newv != 0) break;                                 // another child of this line is still on its way
-            __threadfence();
+            __syncwarp();                                         // lane 0's acquire orders the whole warp's loads below
             const int s = t.TL + 5 * m;
             vs = ldcg(sum_level(t, s) + (pl << 5) + lane);
             vm = ldcg(min_level(t, s) + (pl << 5) + lane);
@@ -664,14 +716,23 @@ __device__ __forceinline__ long long group_descend(const TreeView &t, float m, f
 
 __global__ void __launch_bounds__(256) tree_scan_kernel(TreeView t, long long n, const float *mass, long long *idx_out)
 {
-    const long long n_groups = ((long long)gridDim.x * blockDim.x) >> 3;
-    const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const long long rounds = (n + n_groups - 1) / n_groups;
+    const int lane = lane_id();
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long rounds = (n + 32 * n_warps - 1) / (32 * n_warps);
     for (long long rd = 0; rd < rounds; ++rd) {
-        const long long k = g0 + rd * n_groups;
-        float leafv;
-        const long long i = group_descend(t, k < n ? mass[k] : 0.0f, &leafv);
-        if (k < n && (threadIdx.x & 7) == 0) idx_out[k] = i;
+        const long long k = (w0 + rd * n_warps) * 32 + lane;
+        const float m = k < n ? mass[k] : 0.0f;
+        long long mine = 0;
+#pragma unroll 1
+        for (int sub = 0; sub < 8; ++sub) {
+            const float mg = __shfl_sync(FULL, m, 4 * sub + (lane >> 3));
+            float leafv;
+            const long long i = group_descend(t, mg, &leafv);
+            const long long gi = __shfl_sync(FULL, i, (lane & 3) << 3);
+            if ((lane >> 2) == sub) mine = gi;
+        }
+        if (k < n) idx_out[k] = mine;
     }
 }
 
@@ -723,10 +784,15 @@ __device__ __forceinline__ float stratified_mass(long long k, double uk, long lo
 }
 
 // n = n_batches * batch samples; sample k belongs to batch k / batch, stratum k % batch of its batch (every batch
-// is stratified on its own, all against the same tree state).  Persistent grid.
+// is stratified on its own, all against the same tree state).  Persistent grid.  A warp takes 32 consecutive samples
+// per round: every lane prepares ONE sample (uniform, fp64 mass), the descents run 4 at a time (8 lanes each, 8
+// sub-rounds, masses and results handed over by shuffles), then every lane finishes its own sample (clamp, fp64
+// importance weight) and the 32 results leave as coalesced stores.
+// R sub-rounds per warp round (4 R samples per warp): 8 for large n (throughput), 1 for small batches (a warp then
+// runs ONE descent chain, the latency of a single learner batch).
 __global__ void __launch_bounds__(256) tree_sample_kernel(TreeView t, long long n, long long batch, const double *u,
                                                           int mode, float beta, long long *idx_out, float *w_out,
-                                                          float *mass_out)
+                                                          float *mass_out, int R)
 {
     const unsigned call = (unsigned)t.st->pad[2], seed = (unsigned)t.st->pad[3];
     const long long len = t.st->len;
@@ -735,15 +801,16 @@ __global__ void __launch_bounds__(256) tree_sample_kernel(TreeView t, long long 
     if (len <= 0) bad = PB_ST_EMPTY;
     else if (!(p_sum > 0.0f)) bad = PB_ST_PSUM_NONPOS;
     else if (!(p_min > 0.0f)) bad = PB_ST_PMIN_NONPOS;
-    const long long n_groups = ((long long)gridDim.x * blockDim.x) >> 3;
-    const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const long long rounds = (n + n_groups - 1) / n_groups;
-    const bool head = (threadIdx.x & 7) == 0;
+    const int lane = lane_id();
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int per_warp = 4 * R;
+    const long long rounds = (n + per_warp * n_warps - 1) / (per_warp * n_warps);
     for (long long rd = 0; rd < rounds; ++rd) {
-        const long long k = g0 + rd * n_groups;
-        const bool live = k < n;
+        const long long k = (w0 + rd * n_warps) * per_warp + lane;
+        const bool live = lane < per_warp && k < n;
         if (bad) {
-            if (live && head) {
+            if (live) {
                 idx_out[k] = 0; w_out[k] = 0.0f;
                 if (mass_out) mass_out[k] = 0.0f;
                 if (k == 0) atomicOr(&t.st->status, bad);
@@ -755,12 +822,23 @@ __global__ void __launch_bounds__(256) tree_sample_kernel(TreeView t, long long 
             const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
             m = (mode == 0) ? (float)(0.0 + ((double)p_sum - 0.0) * uk) : stratified_mass(k % batch, uk, batch, p_sum);
         }
-        float leafv;
-        long long i = group_descend(t, m, &leafv);
-        if (live && head) {
-            if (i > len - 1) { i = len - 1; leafv = leaf_ptr(t)[i]; }
-            idx_out[k] = i;
-            w_out[k] = is_weight(leafv, p_min, beta, t);
+        long long mine = 0;
+        float my_leaf = 0.0f;
+#pragma unroll 1
+        for (int sub = 0; sub < R; ++sub) {
+            // group g (lanes 8g .. 8g+7) descends for the sample of lane 4 sub + g
+            const float mg = __shfl_sync(FULL, m, 4 * sub + (lane >> 3));
+            float leafv;
+            const long long i = group_descend(t, mg, &leafv);
+            // lane l = 4 sub + g collects from the head of group g
+            const long long gi = __shfl_sync(FULL, i, (lane & 3) << 3);
+            const float gl = __shfl_sync(FULL, leafv, (lane & 3) << 3);
+            if ((lane >> 2) == sub) { mine = gi; my_leaf = gl; }
+        }
+        if (live) {
+            if (mine > len - 1) { mine = len - 1; my_leaf = leaf_ptr(t)[mine]; }
+            idx_out[k] = mine;
+            w_out[k] = is_weight(my_leaf, p_min, beta, t);
             if (mass_out) mass_out[k] = m;
         }
     }
@@ -843,7 +921,8 @@ __device__ long long first_owned(const GlobalTop &g, int G, long long n, int ran
 
 __global__ void __launch_bounds__(256) global_sample_kernel(TreeView t, const pb_per_state *all_state, int G, int rank,
                                                             long long n_global, const double *u, float beta,
-                                                            long long *idx_out, float *w_out, long long *stratum_out)
+                                                            long long *idx_out, float *w_out, long long *stratum_out,
+                                                            int R)
 {
     __shared__ GlobalTop g;
     build_top(&g, all_state, G);
@@ -861,26 +940,37 @@ __global__ void __launch_bounds__(256) global_sample_kernel(TreeView t, const pb
         if (cnt > 0 && (len <= 0 || !(g.psum[1] > 0.0f) || !(g.pmin > 0.0f)))
             atomicOr(&t.st->status, len <= 0 ? PB_ST_EMPTY : (!(g.psum[1] > 0.0f) ? PB_ST_PSUM_NONPOS : PB_ST_PMIN_NONPOS));
     }
-    const long long n_groups = ((long long)gridDim.x * blockDim.x) >> 3;
-    const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const long long rounds = (n_global + n_groups - 1) / n_groups;
-    const bool head = (threadIdx.x & 7) == 0;
+    const int lane = lane_id();
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int per_warp = 4 * R;
+    const long long rounds = (n_global + per_warp * n_warps - 1) / (per_warp * n_warps);
     for (long long rd = 0; rd < rounds; ++rd) {
-        const long long pos = g0 + rd * n_groups;                 // output row
-        const bool live = pos < cnt;
+        const long long pos = (w0 + rd * n_warps) * per_warp + lane;    // output row
+        const bool mine_row = lane < per_warp;
+        const bool live = mine_row && pos < cnt;
         float res = 0.0f;
         if (live) {
             const long long k = lo + pos;
             const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
             route_stratum(g, G, k, n_global, uk, &res);
         }
-        float leafv;
-        long long i = group_descend(t, res, &leafv);
-        if (head && pos < n_global) {
+        long long mine = 0;
+        float my_leaf = 0.0f;
+#pragma unroll 1
+        for (int sub = 0; sub < R; ++sub) {
+            const float mg = __shfl_sync(FULL, res, 4 * sub + (lane >> 3));
+            float leafv;
+            const long long i = group_descend(t, mg, &leafv);
+            const long long gi = __shfl_sync(FULL, i, (lane & 3) << 3);
+            const float gl = __shfl_sync(FULL, leafv, (lane & 3) << 3);
+            if ((lane >> 2) == sub) { mine = gi; my_leaf = gl; }
+        }
+        if (mine_row && pos < n_global) {
             if (live) {
-                if (i > len - 1) { i = len - 1; if (i < 0) i = 0; leafv = leaf_ptr(t)[i]; }
-                idx_out[pos] = i;
-                w_out[pos] = is_weight(leafv, g.pmin, beta, t);
+                if (mine > len - 1) { mine = len - 1; if (mine < 0) mine = 0; my_leaf = leaf_ptr(t)[mine]; }
+                idx_out[pos] = mine;
+                w_out[pos] = is_weight(my_leaf, g.pmin, beta, t);
                 if (stratum_out) stratum_out[pos] = lo + pos;
             } else {                                              // padding rows of the static batch: skipped downstream
                 idx_out[pos] = -1; w_out[pos] = 0.0f;
@@ -967,12 +1057,15 @@ int launch_rebuild(const TreeView &v, const float *ext, long long n_ext, int mod
         PB_LAUNCH(tree_top_kernel, 1, 512, 0, stream, v, mode, n_new, set_len);
         return PB_OK;
     }
-    for (int s = v.L; s > v.TL; s -= 10) {
-        const int two = (s - 10 >= v.TL) ? 1 : 0;
-        const int fuse = (s - 10 <= v.TL) ? 1 : 0;
-        const int grid = persistent_grid(1LL << s, RB_TILE, 8);
-        PB_LAUNCH(tree_rebuild_kernel, grid, RB_THREADS, 0, stream, v, s, two, s == v.L ? ext : (const float *)nullptr,
+    for (int s = v.L; s > v.TL;) {
+        int n_lv = (s - v.TL) / 5;
+        if (n_lv > 3) n_lv = 3;
+        const int fuse = (s - 5 * n_lv <= v.TL) ? 1 : 0;
+        const int grid = n_lv == 3 ? persistent_grid(1LL << s, 32 * RB_TILE, 4)
+                                   : persistent_grid(1LL << s, RB_TILE * (RB_THREADS / 32), 8);
+        PB_LAUNCH(tree_rebuild_kernel, grid, RB_THREADS, 0, stream, v, s, n_lv, s == v.L ? ext : (const float *)nullptr,
                   n_ext, fuse, mode, n_new, set_len);
+        s -= 5 * n_lv;
     }
     return PB_OK;
 }
@@ -1088,7 +1181,7 @@ int pb_tree_scan(const pb_tree *t, long long n, const float *mass, long long *id
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!mass || !idx_out))) return PB_E_ARG;
     if (n == 0) return PB_OK;
-    PB_LAUNCH(tree_scan_kernel, persistent_grid(n, 32, 8), 256, 0, stream, v, n, mass, idx_out);
+    PB_LAUNCH(tree_scan_kernel, persistent_grid(n, 256, 6), 256, 0, stream, v, n, mass, idx_out);
     return PB_OK;
 }
 
@@ -1102,8 +1195,10 @@ int pb_tree_sample_batches(const pb_tree *t, long long n_batches, long long batc
     const long long n = n_batches * batch;
     if (n >= (1LL << 31) || (n > 0 && (!idx_out || !weight_out))) return PB_E_ARG;
     if (n == 0) return PB_OK;
-    PB_LAUNCH(tree_sample_kernel, persistent_grid(n, 32, 8), 256, 0, stream, v, n, batch, u, mode, beta, idx_out,
-              weight_out, mass_out);
+    // small batches: one descent chain per warp (latency); large ones: 32 samples per warp round (throughput)
+    const int R = n <= 16384 ? 1 : 8;
+    const int sgrid = persistent_grid(n, 8 * 4 * R, 6);
+    PB_LAUNCH(tree_sample_kernel, sgrid, 256, 0, stream, v, n, batch, u, mode, beta, idx_out, weight_out, mass_out, R);
     return PB_OK;
 }
 
@@ -1124,8 +1219,9 @@ int pb_tree_sample_global(const pb_tree *t, int n_ranks, int rank, const pb_per_
     if (!all_state || n_global < 0) return PB_E_ARG;
     if (n_global > 0 && (!idx_out || !weight_out)) return PB_E_ARG;
     if (n_global == 0) return PB_OK;
-    PB_LAUNCH(global_sample_kernel, persistent_grid(n_global, 32, 8), 256, 0, stream, v, all_state, n_ranks, rank,
-              n_global, u, beta, idx_out, weight_out, stratum_out);
+    const int R = n_global <= 16384 ? 1 : 8;
+    PB_LAUNCH(global_sample_kernel, persistent_grid(n_global, 8 * 4 * R, 6), 256, 0, stream, v, all_state, n_ranks, rank,
+              n_global, u, beta, idx_out, weight_out, stratum_out, R);
     return PB_OK;
 }
 

@@ -231,7 +231,9 @@ class PrioritizedTree:
         else:                                   # checkpoints of the full-heap layout: leaves at [capacity, capacity + size)
             cap = sd["sum"].numel() // 2
             leaves = sd["sum"][cap:cap + self.size]
-        self.build(leaves.to(self.device))
+        # slots at or past `len` were never written (they read as +inf on the min side): build from the filled prefix
+        n_filled = int(sd["state"].view(torch.int64)[0])
+        self.build(leaves[:n_filled].to(self.device))
         self.state.copy_(sd["state"])           # len / seq / max_priority / p_sum / p_min / rng as saved
         self.owner.fill_(-1)
         self.counters.zero_()
