@@ -94,7 +94,7 @@ typedef struct pb_per_state {
 typedef struct pb_tree {
     float        *sum;       /* compact sum store, pb_tree_layout() floats (leaves last) */
     float        *min;       /* compact min store, pb_tree_layout() floats (no leaf level) */
-    int          *owner;     /* capacity ints, all -1 between calls (dedup scratch of unsorted updates) */
+    int          *owner;     /* reserved, may be NULL (unsorted updates dedup on the leaf slots themselves) */
     int          *counters;  /* pb_tree_layout() ints, all 0 between calls (arrival counters of the one-launch update) */
     pb_per_state *state;
     long long     capacity;  /* power of two */
@@ -111,7 +111,7 @@ typedef struct pb_tree {
 int pb_tree_layout(long long capacity, long long *sum_floats, long long *min_floats, long long *counter_ints,
                    long long *leaf_offset, int *top_level);
 
-/* zero the trees (sum 0, min +inf), owner = -1, counters = 0, state = {len 0, max_priority 1} */
+/* zero the trees (sum 0, min +inf), counters = 0, state = {len 0, max_priority 1} */
 int pb_tree_init(const pb_tree *t, void *stream);
 
 /* the full level-ordered arrays a pointer-walking tree would hold (2*capacity floats each, node i has children 2i and
@@ -562,15 +562,17 @@ int pb_layer_norm_grouped_bwd(int groups, long long rows_per_group, long long x_
 /* ------------------------------------------------------------------------- *
  * Narrow dense layer (csrc/narrow.cu): y (M x N) = x (M x J) . W^T (N x J) + bias with N <= 32 outputs -- the
  * n_actions-wide output layer of the IQN head on (T*B) rows (prism/agents/models/iqn_model.py:42-46, autograd of
- * nn.Linear).  One streaming pass over x forward; backward reads x once, writes dx once, and combines per-CTA
- * partials of dW / db in a fixed order.  partials: pb_narrow_linear_bwd_blocks(M) * (N * J + N) floats.
+ * nn.Linear) and of the K ensemble heads (q_ensemble.py:26-48), batched over K heads: x (K, M, J) with head stride
+ * x_head_stride floats (0 = the heads share one (M, J) input), W (K, N, J), bias (K, N), y / dy (K, M, N), dx (K, M, J).
+ * One streaming pass over x forward; backward reads x once, writes dx once, and combines per-CTA partials of dW / db in a
+ * fixed order.  partials: K * pb_narrow_linear_bwd_blocks(M) * (N * J + N) floats.
  * ------------------------------------------------------------------------- */
 int pb_narrow_linear_supported(long long M, int N, int J);
 int pb_narrow_linear_bwd_blocks(long long M);
-int pb_narrow_linear_fwd(long long M, int N, int J, const float *x, const float *w, const float *bias, float *y,
-                         void *stream);
-int pb_narrow_linear_bwd(long long M, int N, int J, const float *x, const float *w, const float *dy, float *dx,
-                         float *dW, float *db, float *partials, void *stream);
+int pb_narrow_linear_fwd(int K, long long M, int N, int J, const float *x, long long x_head_stride, const float *w,
+                         const float *bias, float *y, void *stream);
+int pb_narrow_linear_bwd(int K, long long M, int N, int J, const float *x, long long x_head_stride, const float *w,
+                         const float *dy, float *dx, float *dW, float *db, float *partials, void *stream);
 
 /* out[i] = sum_k in[k][i], i < n (n % 4 == 0): gradients of an input shared by K heads (q_ensemble.py:44-48) */
 int pb_sum_heads(int K, long long n, const float *in, float *out, void *stream);

@@ -138,8 +138,8 @@ SIGNATURES = {
     "pb_layer_norm_grouped_bwd": [_I, _LL, _LL, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "pb_narrow_linear_supported": [_LL, _I, _I],
     "pb_narrow_linear_bwd_blocks": [_LL],
-    "pb_narrow_linear_fwd": [_LL, _I, _I, _P, _P, _P, _P, _P],
-    "pb_narrow_linear_bwd": [_LL, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
+    "pb_narrow_linear_fwd": [_I, _LL, _I, _I, _P, _LL, _P, _P, _P, _P],
+    "pb_narrow_linear_bwd": [_I, _LL, _I, _I, _P, _LL, _P, _P, _P, _P, _P, _P, _P],
     "pb_sum_heads": [_I, _LL, _P, _P, _P],
     "pb_iqn_draw_cos_basis": [_LL, _I, _P, _P, _P, _P],
     "pb_relu_bwd_bias_strips": [_LL],

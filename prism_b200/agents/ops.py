@@ -371,44 +371,54 @@ class _LinearTC(torch.autograd.Function):
 
 
 class _NarrowLinear(torch.autograd.Function):
-    """y = x W^T + b for a handful of outputs (the n_actions-wide layer of the IQN head on (T*B) rows): one streaming
-    pass forward, one backward (csrc/narrow.cu) instead of library SGEMMs with 64-wide tiles."""
+    """y = x W^T + b for a handful of outputs (the n_actions-wide layers of the IQN head and of the K ensemble heads):
+    one streaming pass forward, one backward (csrc/narrow.cu) instead of library SGEMMs with 64-wide tiles.
+    x: (M, J) shared by the heads or (K, M, J); W: (K, N, J); b: (K, N) or None -> (K, M, N)."""
 
     @staticmethod
     def forward(ctx, x, w, b):
-        M, J = x.shape
-        N = w.shape[0]
+        K, N, J = w.shape
+        shared = x.dim() == 2
+        M = x.shape[-2]
         xc, wc, bc = _c(x), _c(w), (None if b is None else _c(b))
-        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
-        _lib.check(_lib.load().pb_narrow_linear_fwd(M, N, J, xc.data_ptr(), wc.data_ptr(), _lib.ptr(bc), y.data_ptr(),
-                                                    _stream(x)), "pb_narrow_linear_fwd")
+        y = torch.empty(K, M, N, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().pb_narrow_linear_fwd(K, M, N, J, xc.data_ptr(), 0 if shared else M * J, wc.data_ptr(),
+                                                    _lib.ptr(bc), y.data_ptr(), _stream(x)), "pb_narrow_linear_fwd")
         ctx.save_for_backward(xc, wc)
-        ctx.has_bias = b is not None
+        ctx.has_bias, ctx.shared = b is not None, shared
         return y
 
     @staticmethod
     def backward(ctx, dy):
         xc, wc = ctx.saved_tensors
-        M, J = xc.shape
-        N = wc.shape[0]
+        K, N, J = wc.shape
+        M = xc.shape[-2]
         dy = _c(dy)
         lib = _lib.load()
         want_dx, want_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
-        dx = torch.empty_like(xc) if want_dx else None
+        dx = torch.empty(K, M, J, dtype=torch.float32, device=dy.device) if want_dx else None
         dw = torch.empty_like(wc) if want_dw else None
-        db = torch.empty(N, dtype=torch.float32, device=dy.device) if want_db else None
+        db = torch.empty(K, N, dtype=torch.float32, device=dy.device) if want_db else None
         partials = None
         if want_dw or want_db:
-            partials = torch.empty(lib.pb_narrow_linear_bwd_blocks(M) * (N * J + N), dtype=torch.float32, device=dy.device)
-        _lib.check(lib.pb_narrow_linear_bwd(M, N, J, xc.data_ptr(), wc.data_ptr(), dy.data_ptr(), _lib.ptr(dx), _lib.ptr(dw),
-                                            _lib.ptr(db), _lib.ptr(partials), _stream(dy)), "pb_narrow_linear_bwd")
+            partials = torch.empty(K * lib.pb_narrow_linear_bwd_blocks(M) * (N * J + N), dtype=torch.float32, device=dy.device)
+        _lib.check(lib.pb_narrow_linear_bwd(K, M, N, J, xc.data_ptr(), 0 if ctx.shared else M * J, wc.data_ptr(), dy.data_ptr(),
+                                            _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(partials), _stream(dy)),
+                   "pb_narrow_linear_bwd")
+        if want_dx and ctx.shared:
+            dx = sum_leading(dx)                                   # the heads share their input
         return dx, dw, db
 
 
+NARROW_MIN_ROWS = 32
+
+
 def _narrow_eligible(x, weight):
-    return (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.shape[0] > FUSED_LINEAR_MAX_ROWS
-            and _lib.load().pb_narrow_linear_supported(x.shape[0], weight.shape[0], weight.shape[1]) == 1)
+    """weight: (N, J) or (K, N, J)."""
+    N, J = weight.shape[-2], weight.shape[-1]
+    return (x.is_cuda and x.dtype == torch.float32 and x.shape[-2] >= NARROW_MIN_ROWS
+            and _lib.load().pb_narrow_linear_supported(x.shape[-2], N, J) == 1)
 
 
 TENSOR_CORE_LINEAR = True      # module switch for A/B timing
@@ -485,6 +495,9 @@ def linear_heads(x, w, b, relu=False):
     if _tc_eligible(x, M, Kh, N, J):
         ROUTES["linear:tc_gemm"] += 1
         return _LinearTC.apply(x, w, b, 1 if relu else 0)
+    if not relu and N <= NARROW_OUT and _narrow_eligible(x, w):
+        ROUTES["linear:narrow"] += 1
+        return _NarrowLinear.apply(x, w, b)
     if x.shape[-2] > FUSED_LINEAR_MAX_ROWS:
         ROUTES["fallthrough:baddbmm"] += 1
         xe = x.unsqueeze(0).expand(w.shape[0], -1, -1) if x.dim() == 2 else x
@@ -498,9 +511,9 @@ def linear(x, weight, bias, relu=False):
     """nn.Linear (+ optional fused ReLU) on a 2-D input through the fused kernel."""
     # narrow output layers (a handful of actions) of a few thousand rows stay on the fused FFMA kernel: the library picks
     # 64-wide tiles for them (25 us for the 3 x 256 weight gradient of configs[0])
-    if not relu and _narrow_eligible(x, weight):
+    if not relu and x.dim() == 2 and weight.shape[0] <= NARROW_OUT and _narrow_eligible(x, weight):
         ROUTES["linear:narrow"] += 1
-        return _NarrowLinear.apply(x, weight, bias)
+        return _NarrowLinear.apply(x, weight.unsqueeze(0), None if bias is None else bias.unsqueeze(0)).squeeze(0)
     narrow = weight.shape[0] <= NARROW_OUT and x.shape[0] <= NARROW_MAX_ROWS
     if x.shape[0] > FUSED_LINEAR_MAX_ROWS and not narrow:
         if _tc_eligible(x, x.shape[0], 1, *weight.shape):

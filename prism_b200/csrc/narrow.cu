@@ -45,10 +45,15 @@ __device__ __forceinline__ float warp_reduce_multi(float (&p)[NP])
 // forward: one warp per row; W staged in shared memory as float4 [N][J/4]
 template <int NP>
 __global__ void __launch_bounds__(256) narrow_fwd_kernel(long long M, int N, int J4, const float4 *__restrict__ x,
-                                                         const float4 *__restrict__ w, const float *__restrict__ bias,
-                                                         float *__restrict__ y)
+                                                         long long x_hs4, const float4 *__restrict__ w,
+                                                         const float *__restrict__ bias, float *__restrict__ y)
 {
     extern __shared__ float4 ws[];
+    // grid.y = heads: head k works on x + k * x_hs (x_hs = 0: the heads share x), W + k * N * J, bias + k * N, y + k * M * N
+    x += (size_t)blockIdx.y * x_hs4;
+    w += (size_t)blockIdx.y * N * J4;
+    if (bias) bias += (size_t)blockIdx.y * N;
+    y += (size_t)blockIdx.y * M * N;
     for (int e = threadIdx.x; e < N * J4; e += blockDim.x) ws[e] = w[e];
     __syncthreads();
     const int lane = lane_id();
@@ -80,11 +85,18 @@ __global__ void __launch_bounds__(256) narrow_fwd_kernel(long long M, int N, int
 //   dWp[cta][n][j] = sum_{m in cta} dy[m][n] x[m][j],  dbp[cta][n] = sum_{m in cta} dy[m][n]
 template <int NP>
 __global__ void __launch_bounds__(512) narrow_bwd_kernel(long long M, int N, int J, const float *__restrict__ x,
-                                                         const float *__restrict__ w, const float *__restrict__ dy,
-                                                         float *__restrict__ dx, float *__restrict__ dWp,
-                                                         float *__restrict__ dbp)
+                                                         long long x_hs, const float *__restrict__ w,
+                                                         const float *__restrict__ dy, float *__restrict__ dx,
+                                                         float *__restrict__ dWp, float *__restrict__ dbp)
 {
     __shared__ float sdy[32 * NP];
+    // grid.y = heads (dx is per head: (K, M, J); the caller sums it over the heads when they share x)
+    x += (size_t)blockIdx.y * x_hs;
+    w += (size_t)blockIdx.y * N * J;
+    dy += (size_t)blockIdx.y * M * N;
+    if (dx) dx += (size_t)blockIdx.y * M * J;
+    if (dWp) dWp += (size_t)blockIdx.y * gridDim.x * N * J;
+    if (dbp) dbp += (size_t)blockIdx.y * gridDim.x * N;
     const int t = threadIdx.x, j = 2 * t;
     float2 wr[NP], acc[NP];
 #pragma unroll
@@ -130,6 +142,8 @@ __global__ void __launch_bounds__(512) narrow_bwd_kernel(long long M, int N, int
 // out[e] = sum_b part[b][e], fixed order
 __global__ void partial_reduce_kernel(int nblocks, long long n, const float *__restrict__ part, float *__restrict__ out)
 {
+    part += (size_t)blockIdx.y * nblocks * n;                      // grid.y = heads
+    out += (size_t)blockIdx.y * n;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     float a = 0.0f;
@@ -206,22 +220,26 @@ int pb_narrow_linear_supported(long long M, int N, int J)
 
 int pb_narrow_linear_bwd_blocks(long long M)
 {
-    long long nb = (M + 63) / 64;
+    long long nb = (M + 31) / 32;
     const long long cap = (long long)pb_sm_count() * 2;
     if (nb > cap) nb = cap;
     return (int)(nb < 1 ? 1 : nb);
 }
 
-// y (M x N) = x (M x J) . W^T (N x J) + bias
-int pb_narrow_linear_fwd(long long M, int N, int J, const float *x, const float *w, const float *bias, float *y,
-                         void *stream)
+// y (K, M, N) = x . W^T + bias per head: x (K, M, J) with head stride x_head_stride floats (0: one (M, J) input shared by
+// the heads), W (K, N, J), bias (K, N) or NULL
+int pb_narrow_linear_fwd(int K, long long M, int N, int J, const float *x, long long x_head_stride, const float *w,
+                         const float *bias, float *y, void *stream)
 {
-    if (!pb_narrow_linear_supported(M, N, J) || !x || !w || !y) return PB_E_ARG;
+    if (K < 1 || K > 65535 || !pb_narrow_linear_supported(M, N, J) || !x || !w || !y || x_head_stride < 0 || (x_head_stride & 3))
+        return PB_E_ARG;
     if ((((uintptr_t)x) | ((uintptr_t)w)) & 15) return PB_E_ARG;
     const size_t smem = (size_t)N * J * sizeof(float);
     long long nb = (M + 7) / 8;
-    const long long cap = (long long)pb_sm_count() * 4;
+    long long cap = ((long long)pb_sm_count() * 4 + K - 1) / K;
+    if (cap < 1) cap = 1;
     if (nb > cap) nb = cap;
+    const dim3 grid((unsigned)nb, (unsigned)K);
     const float4 *x4 = reinterpret_cast<const float4 *>(x), *w4 = reinterpret_cast<const float4 *>(w);
 #define PB_NARROW_FWD(NP)                                                                                          \
     do {                                                                                                           \
@@ -232,7 +250,7 @@ int pb_narrow_linear_fwd(long long M, int N, int J, const float *x, const float 
             if (e != cudaSuccess) return (int)e;                                                                   \
             once.mark();                                                                                           \
         }                                                                                                          \
-        PB_LAUNCH(narrow_fwd_kernel<NP>, (unsigned)nb, 256, smem, stream, M, N, J / 4, x4, w4, bias, y);           \
+        PB_LAUNCH(narrow_fwd_kernel<NP>, grid, 256, smem, stream, M, N, J / 4, x4, x_head_stride / 4, w4, bias, y); \
     } while (0)
     switch (narrow_np(N)) {
         case 4: PB_NARROW_FWD(4); break;
@@ -244,28 +262,29 @@ int pb_narrow_linear_fwd(long long M, int N, int J, const float *x, const float 
     return PB_OK;
 }
 
-// dx (M x J, optional) = dy . W ; dW (N x J, optional) = dy^T . x ; db (N, optional) = column sums of dy.
-// partials: pb_narrow_linear_bwd_blocks(M) * (N * J + N) floats of scratch.
-int pb_narrow_linear_bwd(long long M, int N, int J, const float *x, const float *w, const float *dy, float *dx,
-                         float *dW, float *db, float *partials, void *stream)
+// per head: dx (K, M, J; optional) = dy . W ; dW (K, N, J; optional) = dy^T . x ; db (K, N; optional) = column sums of dy.
+// partials: K * pb_narrow_linear_bwd_blocks(M) * (N * J + N) floats of scratch.
+int pb_narrow_linear_bwd(int K, long long M, int N, int J, const float *x, long long x_head_stride, const float *w,
+                         const float *dy, float *dx, float *dW, float *db, float *partials, void *stream)
 {
-    if (!pb_narrow_linear_supported(M, N, J) || !x || !w || !dy) return PB_E_ARG;
+    if (K < 1 || K > 65535 || !pb_narrow_linear_supported(M, N, J) || !x || !w || !dy || x_head_stride < 0) return PB_E_ARG;
     if ((dW || db) && !partials) return PB_E_ARG;
     if ((((uintptr_t)x) | ((uintptr_t)w) | ((uintptr_t)dx) | ((uintptr_t)partials)) & 7) return PB_E_ARG;
     const int nb = pb_narrow_linear_bwd_blocks(M);
     float *dWp = (dW || db) ? partials : nullptr;
-    float *dbp = (dW || db) ? partials + (size_t)nb * N * J : nullptr;
+    float *dbp = (dW || db) ? partials + (size_t)K * nb * N * J : nullptr;
+    const dim3 grid((unsigned)nb, (unsigned)K);
     switch (narrow_np(N)) {
-        case 4: PB_LAUNCH(narrow_bwd_kernel<4>, nb, J / 2, 0, stream, M, N, J, x, w, dy, dx, dWp, dbp); break;
-        case 8: PB_LAUNCH(narrow_bwd_kernel<8>, nb, J / 2, 0, stream, M, N, J, x, w, dy, dx, dWp, dbp); break;
-        case 16: PB_LAUNCH(narrow_bwd_kernel<16>, nb, J / 2, 0, stream, M, N, J, x, w, dy, dx, dWp, dbp); break;
-        default: PB_LAUNCH(narrow_bwd_kernel<32>, nb, J / 2, 0, stream, M, N, J, x, w, dy, dx, dWp, dbp); break;
+        case 4: PB_LAUNCH(narrow_bwd_kernel<4>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp); break;
+        case 8: PB_LAUNCH(narrow_bwd_kernel<8>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp); break;
+        case 16: PB_LAUNCH(narrow_bwd_kernel<16>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp); break;
+        default: PB_LAUNCH(narrow_bwd_kernel<32>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp); break;
     }
     if (dW) {
         const long long n = (long long)N * J;
-        PB_LAUNCH(partial_reduce_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, nb, n, dWp, dW);
+        PB_LAUNCH(partial_reduce_kernel, dim3((unsigned)((n + 255) / 256), (unsigned)K), 256, 0, stream, nb, n, dWp, dW);
     }
-    if (db) PB_LAUNCH(partial_reduce_kernel, 1, 256, 0, stream, nb, (long long)N, dbp, db);
+    if (db) PB_LAUNCH(partial_reduce_kernel, dim3(1, (unsigned)K), 256, 0, stream, nb, (long long)N, dbp, db);
     return PB_OK;
 }
 

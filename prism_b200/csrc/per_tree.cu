@@ -19,11 +19,14 @@
 //      - a sorted priority update is ONE launch: the leader of every touched line applies its leaves, reduces the
 //        line and climbs; lines of the next stored level are finished by whichever child arrives last (arrival
 //        counters, no spinning), and the last CTA (ticket) rebuilds the top heap and the state block;
-//      - large / unsorted batches scatter their leaves and rebuild every line with one streaming pass over the leaf
-//        array (4.3 B per leaf of traffic, independent of the batch size);
+//      - any other batch (unsorted, duplicates, K batches in flight) is TWO launches: a mark pass (dedup tag on the
+//        leaf slot + one bit per touched leaf line) and a sparse rebuild whose CTAs own 32768-leaf spans and climb three
+//        stored levels without any cross-CTA dependency -- cost proportional to the touched lines;
+//      - batches beyond cap/16 entries scatter their leaves and rebuild every line with one streaming pass over the
+//        leaf array (4.3 B per leaf of traffic, independent of the batch size);
 //      - the bulk build is that same streaming pass.
 //  * duplicates in an update batch: last occurrence wins (sequential reference loop), resolved deterministically
-//    (adjacency when sorted, owner scratch + atomicMax otherwise).
+//    (adjacency when sorted; otherwise atomicMax of a NaN-tagged entry number on the leaf slot itself -- no side array).
 //  * no host sync anywhere: len / cursor / max_priority / p_sum / p_min live in a 64-byte device state block, so
 //    the whole sample->update loop is CUDA-graph capturable.
 #include "common.cuh"
@@ -44,6 +47,7 @@ struct TreeView {
     int L, TL, P;                  // P = (L - TL) / 5 deep levels: L, L-5, .., TL+5
     long long off[MAX_DEEP];       // off[m]: float offset of level TL + 5m in the sum / min store (m >= 1)
     long long coff[MAX_DEEP];      // coff[m]: int offset of the arrival counters of the lines at level TL + 5m (1 <= m < P)
+    unsigned *bitmap;              // one bit per leaf line (cap / 32 bits), all zero between calls: lines an update touched
     float alpha, eps32;
     double eps64;
     int weps, dp64;
@@ -303,7 +307,6 @@ __global__ void tree_init_kernel(TreeView t, long long n_sum, long long n_min, l
     for (long long k = i; k < n_sum; k += stride) t.sum[k] = 0.0f;
     for (long long k = i; k < n_min; k += stride) t.min[k] = INF;
     for (long long k = i; k < n_cnt; k += stride) t.cnt[k] = 0;
-    if (t.owner) for (long long k = i; k < t.cap; k += stride) t.owner[k] = -1;
     if (i == 0) {
         pb_per_state s;
         s.len = 0; s.seq = 0; s.max_priority = 1.0f; s.p_sum = 0.0f; s.p_min = INF; s.status = 0;
@@ -448,18 +451,27 @@ __global__ void __launch_bounds__(512) tree_top_kernel(TreeView t, int mode, lon
 }
 
 // ---------------------------------------------------------------------------------
-// leaf scatter, general (unsorted) path: A) mark owner = last occurrence, B) the winner writes the leaf and clears
-// the scratch.  Dense path, sorted input: the last entry of every run of equal indices writes the leaf.
+// leaf scatter, general (unsorted) path.  Duplicates: the LAST occurrence wins (sequential reference loop).  No side
+// array: the leaf slot itself is the scratch.  A) every entry j does atomicMax(int view of leaf[i], TAG + j): TAG + j
+// is a NaN bit pattern, as a signed int larger than every non-NaN float's, so the slot ends up holding the tag of the
+// highest j that targets it.  B) the entry whose tag it finds there writes the value.  Dense path, sorted input: the
+// last entry of every run of equal indices writes the leaf.
 // ---------------------------------------------------------------------------------
-__global__ void upd_mark_kernel(TreeView t, long long n, const long long *idx, const float *val, int mode)
+constexpr int LEAF_TAG = 0x7F800001;                 // first NaN pattern; TAG + j stays a positive int for j < 2^23 - 1
+constexpr long long LEAF_TAG_MAX_N = (1LL << 23) - 2;
+
+__global__ void upd_mark_kernel(TreeView t, long long n, const long long *idx, const float *val, int mode,
+                                long long *idx_out, int set_bits)
 {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long seq0 = t.st->seq;
     float bm = 0.0f;
     if (j < n) {
         const long long i = entry_index(t, idx, j, mode, seq0);
+        if (idx_out) idx_out[j] = i;
         if (i >= 0 && i < t.size) {
-            atomicMax(&t.owner[i], (int)j);
+            atomicMax(reinterpret_cast<int *>(leaf_ptr(t) + i), LEAF_TAG + (int)j);
+            if (set_bits) atomicOr(t.bitmap + (i >> 10), 1u << ((i >> 5) & 31));      // leaf line i >> 5 is touched
             if (mode == MODE_PRIORITY) bm = fabsf(val[j]);
         }
     }
@@ -477,10 +489,9 @@ __global__ void upd_leaf_kernel(TreeView t, long long n, const long long *idx, c
     const long long i = entry_index(t, idx, j, mode, t.st->seq);
     if (idx_out) idx_out[j] = i;
     if (i < 0 || i >= t.size) return;
-    if (t.owner[i] != (int)j) return;
+    if (__ldcg(reinterpret_cast<const int *>(leaf_ptr(t) + i)) != LEAF_TAG + (int)j) return;
     const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
     leaf_ptr(t)[i] = entry_leaf(t, val, j, mode, defp);
-    t.owner[i] = -1;
 }
 
 __global__ void upd_leaf_sorted_kernel(TreeView t, long long n, const long long *idx, const float *val, int mode,
@@ -508,30 +519,86 @@ __global__ void upd_leaf_sorted_kernel(TreeView t, long long n, const long long 
 }
 
 // ---------------------------------------------------------------------------------
-// unsorted sparse path, phase m (m = P .. 1): one warp per batch entry recomputes the line of level TL + 5m that
-// holds the entry's ancestor (entries that share a line do the same work and write the same values).
+// sparse rebuild (the second launch of a general update; the first is upd_mark_kernel).  A CTA owns a span of 32768
+// leaves = 32 words of the touched-line bitmap = one line of level L-10.  Warp v takes 4 of those words: for every set
+// bit it loads the leaf line, RESOLVES the dedup tags it finds there (a NaN-tagged slot names the winning entry: its
+// value is computed and stored now), reduces the line to its node of level L-5; for every word with a bit set it then
+// reduces that line of level L-5 (which it has just completed) to the node of level L-10; finally warp 0 reduces the
+// CTA's line of level L-10 to the node of level L-15.  No cross-CTA dependency below the top heap; cost is
+// proportional to the number of touched lines.  The bitmap words are cleared on the way.  The last CTA (ticket)
+// rebuilds the top heap and the state block when level L-15 is (or lies above) the heap's bottom level.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) upd_lines_kernel(TreeView t, long long n, const long long *idx, int mode, int m,
-                                                        long long n_new)
+constexpr int SPR_THREADS = 256;
+
+__global__ void __launch_bounds__(SPR_THREADS) tree_rebuild_sparse_kernel(TreeView t, const float *val, int mode,
+                                                                          long long n_new, int fuse_top)
 {
-    const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j >= n) return;
-    const long long i = entry_index(t, idx, j, mode, t.st->seq);
-    if (i < 0 || i >= t.size) return;
+    __shared__ float sm_top[2 * TOP_SM_FLOATS];
+    const int lane = lane_id(), wic = threadIdx.x >> 5;
     const long long len = len_after(t, mode, n_new, -1);
-    const int lane = lane_id();
-    const int s = t.TL + 5 * m;
-    const long long g = i >> (t.L - s + 5);                      // line index at level s
-    float vs, vm;
-    if (s == t.L) {
-        vs = leaf_ptr(t)[(g << 5) + lane];
-        vm = min_of_leaf(vs, (g << 5) + lane, len);
-    } else {
-        vs = sum_level(t, s)[(g << 5) + lane];
-        vm = min_level(t, s)[(g << 5) + lane];
+    const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
+    float *leaf = leaf_ptr(t);
+    const long long n_words = t.cap >= 1024 ? t.cap >> 10 : 1;
+    const int P = t.P;
+    for (long long span = blockIdx.x; span * 32 < n_words; span += gridDim.x) {
+        int touched_any = 0;
+        for (int q = 0; q < 4; ++q) {
+            const long long w = span * 32 + wic * 4 + q;
+            if (w >= n_words) break;
+            unsigned bits = 0;
+            if (lane == 0) { bits = t.bitmap[w]; if (bits) t.bitmap[w] = 0u; }
+            bits = __shfl_sync(FULL, bits, 0);
+            if (!bits) continue;
+            touched_any = 1;
+            // two touched lines per round: two independent 128-byte loads in flight
+            while (bits) {
+                const int b0 = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int b1 = bits ? __ffs(bits) - 1 : -1;
+                if (b1 >= 0) bits &= bits - 1;
+                const long long l0 = (w << 5) + b0, l1 = (w << 5) + (b1 >= 0 ? b1 : b0);
+                int x0 = __ldcg(reinterpret_cast<const int *>(leaf + (l0 << 5) + lane));
+                int x1 = __ldcg(reinterpret_cast<const int *>(leaf + (l1 << 5) + lane));
+                if (x0 >= LEAF_TAG) {
+                    const float v = entry_leaf(t, val, (long long)(x0 - LEAF_TAG), mode, defp);
+                    leaf[(l0 << 5) + lane] = v;
+                    x0 = __float_as_int(v);
+                }
+                if (b1 >= 0 && x1 >= LEAF_TAG) {
+                    const float v = entry_leaf(t, val, (long long)(x1 - LEAF_TAG), mode, defp);
+                    leaf[(l1 << 5) + lane] = v;
+                    x1 = __float_as_int(v);
+                }
+                float vs = __int_as_float(x0), vm = min_of_leaf(vs, (l0 << 5) + lane, len);
+                line_reduce(vs, vm);
+                if (lane == 0) { sum_level(t, t.L - 5)[l0] = vs; min_level(t, t.L - 5)[l0] = vm; }
+                if (b1 >= 0) {
+                    vs = __int_as_float(x1); vm = min_of_leaf(vs, (l1 << 5) + lane, len);
+                    line_reduce(vs, vm);
+                    if (lane == 0) { sum_level(t, t.L - 5)[l1] = vs; min_level(t, t.L - 5)[l1] = vm; }
+                }
+            }
+            if (P >= 2) {
+                __syncwarp();                                     // lane 0's node stores -> the whole warp's loads
+                float vs = ldcg(sum_level(t, t.L - 5) + (w << 5) + lane);
+                float vm = ldcg(min_level(t, t.L - 5) + (w << 5) + lane);
+                line_reduce(vs, vm);
+                if (lane == 0) { sum_level(t, t.L - 10)[w] = vs; min_level(t, t.L - 10)[w] = vm; }
+            }
+        }
+        if (P >= 3) {
+            const int any = __syncthreads_or(touched_any);        // also orders the warps' level L-10 stores
+            if (any && wic == 0) {
+                float vs = ldcg(sum_level(t, t.L - 10) + (span << 5) + lane);
+                float vm = ldcg(min_level(t, t.L - 10) + (span << 5) + lane);
+                line_reduce(vs, vm);
+                if (lane == 0) { sum_level(t, t.L - 15)[span] = vs; min_level(t, t.L - 15)[span] = vm; }
+            }
+        }
     }
-    line_reduce(vs, vm);
-    if (lane == 0) { sum_level(t, s - 5)[g] = vs; min_level(t, s - 5)[g] = vm; }
+    if (!fuse_top) return;
+    if (!last_cta(t)) return;
+    top_and_finalize(t, sm_top, mode, n_new, -1);
 }
 
 // ---------------------------------------------------------------------------------
@@ -544,6 +611,7 @@ __global__ void __launch_bounds__(256) upd_lines_kernel(TreeView t, long long n,
 // The last CTA (ticket) rebuilds the top heap and the state block.
 // ---------------------------------------------------------------------------------
 constexpr int CHAIN_THREADS = 512;
+constexpr long long CHAIN_MAX_N = 8192;      // beyond this the per-warp serial chain loses to mark + sparse rebuild
 
 struct RunScan { long long seq0; const long long *idx; long long n; int mode; };
 
@@ -1001,7 +1069,7 @@ __global__ void tree_export_kernel(TreeView t, int d, float *sum_heap, float *mi
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
-struct Layout { int L, TL, P; long long off[MAX_DEEP], coff[MAX_DEEP]; long long n_sum, n_min, n_cnt; };
+struct Layout { int L, TL, P; long long off[MAX_DEEP], coff[MAX_DEEP]; long long n_sum, n_min, n_cnt, bitmap_off; };
 
 void make_layout(long long cap, Layout *y)
 {
@@ -1021,7 +1089,8 @@ void make_layout(long long cap, Layout *y)
         }
     }
     y->n_sum = off;
-    y->n_cnt = coff > 0 ? coff : 1;
+    y->bitmap_off = coff;                                         // touched-line bitmap behind the arrival counters
+    y->n_cnt = coff + (cap >= 1024 ? cap / 1024 : 1);
 }
 
 int make_view(const pb_tree *t, TreeView *v)
@@ -1031,8 +1100,9 @@ int make_view(const pb_tree *t, TreeView *v)
     if (t->capacity < 2 || t->capacity > (1LL << 30)) return PB_E_CAPACITY;
     Layout y;
     make_layout(t->capacity, &y);
-    if (y.P > 1 && !t->counters) return PB_E_ARG;
+    if (!t->counters) return PB_E_ARG;
     v->sum = t->sum; v->min = t->min; v->owner = t->owner; v->cnt = t->counters; v->st = t->state;
+    v->bitmap = reinterpret_cast<unsigned *>(t->counters + y.bitmap_off);
     v->cap = t->capacity; v->size = t->size; v->L = y.L; v->TL = y.TL; v->P = y.P;
     for (int m = 0; m < MAX_DEEP; ++m) { v->off[m] = y.off[m]; v->coff[m] = y.coff[m]; }
     v->alpha = t->alpha; v->eps32 = t->eps_f32; v->eps64 = t->eps_f64;
@@ -1083,29 +1153,57 @@ int launch_update(const pb_tree *t, long long n, const long long *idx, const flo
         if (n > v.size) return PB_E_ARG;
         sorted = (2 * n <= v.size);     // a contiguous run of slots; a long one may wrap onto lines it already touched
     }
-    // dense path: when the batch touches a sizeable part of the tree, scatter the leaves and rebuild every line with
-    // the streaming pass (4.3 B per leaf of traffic, independent of n)
-    const long long dense_min = sorted ? v.cap / 64 : v.cap / 256;
-    const bool dense = v.P > 0 && n >= dense_min;
-    if (sorted && !dense) {
+    // Three regimes.  (1) small sorted batches (one learner batch, the ring's extends): ONE launch, leaders + arrival
+    // counters.  (2) anything else up to cap/16 entries: mark (dedup tags + touched-line bitmap) + sparse rebuild, cost
+    // proportional to the touched lines.  (3) beyond that: scatter the leaves and stream the whole leaf array once.
+    if (v.P == 0) {
+        if (sorted) {
+            const int grid = persistent_grid(n, CHAIN_THREADS / 32, 2);
+            PB_LAUNCH(upd_chain_kernel, grid, CHAIN_THREADS, 0, stream, v, n, idx, val, mode, idx_out);
+            return PB_OK;
+        }
+        if (n > LEAF_TAG_MAX_N) return PB_E_UNSUPPORTED;
+        const int nb0 = (int)((n + 255) / 256);
+        PB_LAUNCH(upd_mark_kernel, nb0, 256, 0, stream, v, n, idx, val, mode, idx_out, 0);
+        PB_LAUNCH(upd_leaf_kernel, nb0, 256, 0, stream, v, n, idx, val, mode, (long long *)nullptr);
+        PB_LAUNCH(tree_top_kernel, 1, 512, 0, stream, v, mode, n, -1LL);
+        return PB_OK;
+    }
+    if (sorted && n <= CHAIN_MAX_N) {
         const int grid = persistent_grid(n, CHAIN_THREADS / 32, 2);
         PB_LAUNCH(upd_chain_kernel, grid, CHAIN_THREADS, 0, stream, v, n, idx, val, mode, idx_out);
         return PB_OK;
     }
     const int nb = (int)((n + 255) / 256);
+    if (n < v.cap / 16 && n <= LEAF_TAG_MAX_N) {
+        PB_LAUNCH(upd_mark_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out, 1);
+        const long long spans = v.cap >= 32768 ? v.cap >> 15 : 1;
+        const int fuse = v.P <= 3 ? 1 : 0;
+        PB_LAUNCH(tree_rebuild_sparse_kernel, (int)(spans < 2048 ? spans : 2048), SPR_THREADS, 0, stream, v, val, mode, n, fuse);
+        if (!fuse) {
+            // deeper trees: levels L-15 .. TL by the streaming pass over the (small) array of level L-15
+            TreeView u2 = v;
+            for (int s2 = v.L - 15; s2 > v.TL;) {
+                int n_lv = (s2 - v.TL) / 5;
+                if (n_lv > 3) n_lv = 3;
+                const int f2 = (s2 - 5 * n_lv <= v.TL) ? 1 : 0;
+                const int grid = n_lv == 3 ? persistent_grid(1LL << s2, 32 * RB_TILE, 4)
+                                           : persistent_grid(1LL << s2, RB_TILE * (RB_THREADS / 32), 8);
+                PB_LAUNCH(tree_rebuild_kernel, grid, RB_THREADS, 0, stream, u2, s2, n_lv, (const float *)nullptr, 0LL, f2,
+                          mode, n, -1LL);
+                s2 -= 5 * n_lv;
+            }
+        }
+        return PB_OK;
+    }
     if (sorted) {
         PB_LAUNCH(upd_leaf_sorted_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out);
     } else {
-        if (!v.owner) return PB_E_ARG;
-        PB_LAUNCH(upd_mark_kernel, nb, 256, 0, stream, v, n, idx, val, mode);
-        PB_LAUNCH(upd_leaf_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out);
+        if (n > LEAF_TAG_MAX_N) return PB_E_UNSUPPORTED;        // the dedup tags are NaN payloads: 2^23 - 2 of them
+        PB_LAUNCH(upd_mark_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out, 0);
+        PB_LAUNCH(upd_leaf_kernel, nb, 256, 0, stream, v, n, idx, val, mode, (long long *)nullptr);
     }
-    if (dense || v.P == 0) return launch_rebuild(v, nullptr, 0, mode, n, -1, stream);
-    const int nbw = (int)((n + 7) / 8);
-    for (int m = v.P; m >= 1; --m)
-        PB_LAUNCH(upd_lines_kernel, nbw, 256, 0, stream, v, n, idx, mode, m, n);
-    PB_LAUNCH(tree_top_kernel, 1, 512, 0, stream, v, mode, n, -1LL);
-    return PB_OK;
+    return launch_rebuild(v, nullptr, 0, mode, n, -1, stream);
 }
 
 }  // namespace

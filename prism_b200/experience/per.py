@@ -53,10 +53,9 @@ class PrioritizedTree:
         self.sum_store = torch.empty(n_sum.value, dtype=torch.float32, device=self.device)
         self.min_store = torch.empty(n_min.value, dtype=torch.float32, device=self.device)
         self.counters = torch.zeros(n_cnt.value, dtype=torch.int32, device=self.device)
-        self.owner = torch.empty(self.capacity, dtype=torch.int32, device=self.device)
         self.state = torch.zeros(64, dtype=torch.uint8, device=self.device)
         self._c = _lib.pb_tree(
-            sum=self.sum_store.data_ptr(), min=self.min_store.data_ptr(), owner=self.owner.data_ptr(),
+            sum=self.sum_store.data_ptr(), min=self.min_store.data_ptr(), owner=None,
             counters=self.counters.data_ptr(), state=self.state.data_ptr(), capacity=self.capacity, size=self.size,
             alpha=self._alpha, eps_f32=self._eps, eps_f64=self._eps,
             weight_eps_in_denominator=int(bool(weight_eps_in_denominator)),
@@ -235,6 +234,5 @@ class PrioritizedTree:
         n_filled = int(sd["state"].view(torch.int64)[0])
         self.build(leaves[:n_filled].to(self.device))
         self.state.copy_(sd["state"])           # len / seq / max_priority / p_sum / p_min / rng as saved
-        self.owner.fill_(-1)
         self.counters.zero_()
         self._beta = sd["beta"]

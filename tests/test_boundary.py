@@ -107,7 +107,7 @@ def test_argument_errors_do_not_touch_the_gpu():
     assert lib.pb_relu_bwd_bias(1, 8, 6, 16, None, None, None, 16, None) == -1            # N % 4 != 0
     assert lib.pb_iqn_phi_bwd(4, 8, 6, 16, 16, 16, 16, None, 16, None) == -1              # F % 4 != 0
     assert lib.pb_theil_fwd(2, 65, 8, 16, 16, 16, 16, None) == -1                         # K > 64
-    assert lib.pb_theil_chunks(100) == 8 and lib.pb_theil_chunks(1 << 30) == 128
+    assert lib.pb_theil_chunks(100) == 8 and lib.pb_theil_chunks(262144) == 64 and lib.pb_theil_chunks(1 << 30) == 128
     assert lib.pb_peer_barrier(None, None) == -1
     g = _lib.pb_peer_group()
     g.world, g.rank = 9, 0                                                                # more than PB_PEER_MAX ranks

@@ -871,3 +871,29 @@ def test_sum_leading_matches_torch():
     from prism_b200.agents import ops
     x = torch.randn(10, 512, 3136, device=DEV)
     assert rel_err(ops.sum_leading(x).cpu().numpy(), x.double().sum(0).cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("K,M,N,J,shared", [(10, 64, 3, 256, False), (10, 512, 18, 512, False), (1, 256, 4, 256, False),
+                                            (4, 100, 6, 128, True)])
+def test_narrow_linear_heads_matches_fp64(K, M, N, J, shared):
+    """The n_actions-wide last layer of the K ensemble heads through the narrow kernels (batched over heads)."""
+    from prism_b200.agents import ops
+    g = torch.Generator().manual_seed(K * 7 + M)
+    x = torch.randn((M, J) if shared else (K, M, J), generator=g)
+    w = torch.randn(K, N, J, generator=g) / J ** 0.5
+    b = torch.randn(K, N, generator=g)
+    dy = torch.randn(K, M, N, generator=g)
+    xd, wd, bd = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    ops.route_counts(reset=True)
+    y = ops.linear_heads(xd, wd, bd)
+    assert ops.route_counts().get("linear:narrow", 0) == 1, ops.route_counts()
+    y.backward(dy.to(DEV))
+    torch.cuda.synchronize()
+    x64, w64, b64 = (t.double().requires_grad_(True) for t in (x, w, b))
+    xe = x64.unsqueeze(0).expand(K, -1, -1) if shared else x64
+    y64 = torch.baddbmm(b64.unsqueeze(1), xe, w64.transpose(1, 2))
+    y64.backward(dy.double())
+    assert rel_err(y.detach().cpu().numpy(), y64.detach().numpy()) < 2e-6
+    assert rel_err(xd.grad.cpu().numpy(), x64.grad.numpy()) < 2e-6
+    assert rel_err(wd.grad.cpu().numpy(), w64.grad.numpy()) < 2e-5
+    assert rel_err(bd.grad.cpu().numpy(), b64.grad.numpy()) < 2e-5
