@@ -528,62 +528,82 @@ __global__ void upd_leaf_sorted_kernel(TreeView t, long long n, const long long 
 // proportional to the number of touched lines.  The bitmap words are cleared on the way.  The last CTA (ticket)
 // rebuilds the top heap and the state block when level L-15 is (or lies above) the heap's bottom level.
 // ---------------------------------------------------------------------------------
-constexpr int SPR_THREADS = 256;
+constexpr int SPR_THREADS = 512;                 // 16 warps, 2 bitmap words (64 leaf lines) each
+constexpr int SPR_U = 8;                         // touched lines per round: that many 128-byte loads in flight per warp
 
 __global__ void __launch_bounds__(SPR_THREADS) tree_rebuild_sparse_kernel(TreeView t, const float *val, int mode,
                                                                           long long n_new, int fuse_top)
 {
     __shared__ float sm_top[2 * TOP_SM_FLOATS];
     const int lane = lane_id(), wic = threadIdx.x >> 5;
+    constexpr int WPW = 32 / (SPR_THREADS / 32);                 // bitmap words per warp
     const long long len = len_after(t, mode, n_new, -1);
     const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
     float *leaf = leaf_ptr(t);
+    float *n1s = sum_level(t, t.L - 5), *n1m = min_level(t, t.L - 5);
     const long long n_words = t.cap >= 1024 ? t.cap >> 10 : 1;
     const int P = t.P;
     for (long long span = blockIdx.x; span * 32 < n_words; span += gridDim.x) {
+        unsigned word_bits[WPW];
         int touched_any = 0;
-        for (int q = 0; q < 4; ++q) {
-            const long long w = span * 32 + wic * 4 + q;
-            if (w >= n_words) break;
+#pragma unroll
+        for (int q = 0; q < WPW; ++q) {
+            const long long w = span * 32 + wic * WPW + q;
             unsigned bits = 0;
-            if (lane == 0) { bits = t.bitmap[w]; if (bits) t.bitmap[w] = 0u; }
-            bits = __shfl_sync(FULL, bits, 0);
-            if (!bits) continue;
-            touched_any = 1;
-            // two touched lines per round: two independent 128-byte loads in flight
+            if (w < n_words && lane == 0) { bits = t.bitmap[w]; if (bits) t.bitmap[w] = 0u; }
+            word_bits[q] = __shfl_sync(FULL, bits, 0);
+            touched_any |= word_bits[q] != 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < WPW; ++q) {
+            const long long w = span * 32 + wic * WPW + q;
+            unsigned bits = word_bits[q];
             while (bits) {
-                const int b0 = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int b1 = bits ? __ffs(bits) - 1 : -1;
-                if (b1 >= 0) bits &= bits - 1;
-                const long long l0 = (w << 5) + b0, l1 = (w << 5) + (b1 >= 0 ? b1 : b0);
-                int x0 = __ldcg(reinterpret_cast<const int *>(leaf + (l0 << 5) + lane));
-                int x1 = __ldcg(reinterpret_cast<const int *>(leaf + (l1 << 5) + lane));
-                if (x0 >= LEAF_TAG) {
-                    const float v = entry_leaf(t, val, (long long)(x0 - LEAF_TAG), mode, defp);
-                    leaf[(l0 << 5) + lane] = v;
-                    x0 = __float_as_int(v);
+                long long line[SPR_U];
+                int x[SPR_U];
+#pragma unroll
+                for (int u = 0; u < SPR_U; ++u) {
+                    line[u] = -1;
+                    if (bits) { line[u] = (w << 5) + (__ffs(bits) - 1); bits &= bits - 1; }
                 }
-                if (b1 >= 0 && x1 >= LEAF_TAG) {
-                    const float v = entry_leaf(t, val, (long long)(x1 - LEAF_TAG), mode, defp);
-                    leaf[(l1 << 5) + lane] = v;
-                    x1 = __float_as_int(v);
+#pragma unroll
+                for (int u = 0; u < SPR_U; ++u)
+                    x[u] = line[u] >= 0 ? __ldcg(reinterpret_cast<const int *>(leaf + (line[u] << 5) + lane)) : 0;
+                // resolve dedup tags: the winning entry's value (gathers first, stores after: independent loads)
+                float nv[SPR_U];
+#pragma unroll
+                for (int u = 0; u < SPR_U; ++u)
+                    nv[u] = (line[u] >= 0 && x[u] >= LEAF_TAG) ? entry_leaf(t, val, (long long)(x[u] - LEAF_TAG), mode, defp) : 0.0f;
+#pragma unroll
+                for (int u = 0; u < SPR_U; ++u) {
+                    if (line[u] >= 0 && x[u] >= LEAF_TAG) {
+                        leaf[(line[u] << 5) + lane] = nv[u];
+                        x[u] = __float_as_int(nv[u]);
+                    }
                 }
-                float vs = __int_as_float(x0), vm = min_of_leaf(vs, (l0 << 5) + lane, len);
-                line_reduce(vs, vm);
-                if (lane == 0) { sum_level(t, t.L - 5)[l0] = vs; min_level(t, t.L - 5)[l0] = vm; }
-                if (b1 >= 0) {
-                    vs = __int_as_float(x1); vm = min_of_leaf(vs, (l1 << 5) + lane, len);
+#pragma unroll
+                for (int u = 0; u < SPR_U; ++u) {
+                    if (line[u] < 0) continue;                    // warp-uniform
+                    float vs = __int_as_float(x[u]), vm = min_of_leaf(vs, (line[u] << 5) + lane, len);
                     line_reduce(vs, vm);
-                    if (lane == 0) { sum_level(t, t.L - 5)[l1] = vs; min_level(t, t.L - 5)[l1] = vm; }
+                    if (lane == 0) { n1s[line[u]] = vs; n1m[line[u]] = vm; }
                 }
             }
-            if (P >= 2) {
-                __syncwarp();                                     // lane 0's node stores -> the whole warp's loads
-                float vs = ldcg(sum_level(t, t.L - 5) + (w << 5) + lane);
-                float vm = ldcg(min_level(t, t.L - 5) + (w << 5) + lane);
-                line_reduce(vs, vm);
-                if (lane == 0) { sum_level(t, t.L - 10)[w] = vs; min_level(t, t.L - 10)[w] = vm; }
+        }
+        if (P >= 2) {
+            __syncwarp();                                         // lane 0's node stores -> the whole warp's loads
+            float vs[WPW], vm[WPW];
+#pragma unroll
+            for (int q = 0; q < WPW; ++q) {
+                const long long w = span * 32 + wic * WPW + q;
+                if (word_bits[q]) { vs[q] = ldcg(n1s + (w << 5) + lane); vm[q] = ldcg(n1m + (w << 5) + lane); }
+            }
+#pragma unroll
+            for (int q = 0; q < WPW; ++q) {
+                const long long w = span * 32 + wic * WPW + q;
+                if (!word_bits[q]) continue;
+                line_reduce(vs[q], vm[q]);
+                if (lane == 0) { sum_level(t, t.L - 10)[w] = vs[q]; min_level(t, t.L - 10)[w] = vm[q]; }
             }
         }
         if (P >= 3) {
@@ -734,52 +754,113 @@ __global__ void __launch_bounds__(CHAIN_THREADS) upd_chain_kernel(TreeView t, lo
 // comparisons in the same order as the reference loop (go right and subtract iff mass > left).  All 32 lanes of the
 // warp must call this together.  Returns the leaf index (or size when mass > root) and the leaf's value.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ long long group_descend(const TreeView &t, float m, float *leaf_out)
+template <int U>
+__device__ __forceinline__ void group_descend_multi(const TreeView &t, float (&m)[U], long long (&node)[U],
+                                                    float (&leafv)[U])
 {
+    // U independent descents per 8-lane group, interleaved level by level: U 128-byte loads in flight per group
     const int gl = threadIdx.x & 7;
-    const bool over = m > t.sum[1];
-    if (over) m = 0.0f;                                           // stay on real nodes; the result is discarded
-    long long node = 0;                                           // index within the current level
+    const float root = t.sum[1];
+    bool over[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        over[u] = m[u] > root;
+        if (over[u]) m[u] = 0.0f;                                 // stay on real nodes; the result is discarded
+        node[u] = 0;                                              // index within the current level
+        leafv[u] = 0.0f;
+    }
     int d = 0;
     int c = t.L % 5;                                              // short chunk first: deeper chunks are full aligned lines
     if (c == 0) c = 5;
-    float leafv = 0.0f;
     while (d < t.L) {
         const int s = d + c;
-        const float *p = sum_level(t, s) + (node << c);
-        float4 v;
-        if (c == 5) {
-            v = *reinterpret_cast<const float4 *>(p + 4 * gl);
-        } else {
-            const int cnt = 1 << c, b = 4 * gl;
-            v.x = b + 0 < cnt ? p[b + 0] : 0.0f; v.y = b + 1 < cnt ? p[b + 1] : 0.0f;
-            v.z = b + 2 < cnt ? p[b + 2] : 0.0f; v.w = b + 3 < cnt ? p[b + 3] : 0.0f;
+        const float *lvl = sum_level(t, s);
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float *p = lvl + (node[u] << c);
+            if (c == 5) {
+                v[u] = *reinterpret_cast<const float4 *>(p + 4 * gl);
+            } else {
+                const int cnt = 1 << c, b = 4 * gl;
+                v[u].x = b + 0 < cnt ? p[b + 0] : 0.0f; v[u].y = b + 1 < cnt ? p[b + 1] : 0.0f;
+                v[u].z = b + 2 < cnt ? p[b + 2] : 0.0f; v[u].w = b + 3 < cnt ? p[b + 3] : 0.0f;
+            }
         }
-        const float a = op_sum(v.x, v.y), b2 = op_sum(v.z, v.w);
-        const float c4 = op_sum(a, b2);
-        const float s1 = op_sum(c4, __shfl_xor_sync(FULL, c4, 1, 8));
-        const float s2 = op_sum(s1, __shfl_xor_sync(FULL, s1, 2, 8));
-        int pos = 0;
-        float l = __shfl_sync(FULL, s2, 0, 8);
-        if (m > l) { m = __fsub_rn(m, l); pos = 4; }
-        l = __shfl_sync(FULL, s1, pos, 8);
-        if (m > l) { m = __fsub_rn(m, l); pos += 2; }
-        l = __shfl_sync(FULL, c4, pos, 8);
-        if (m > l) { m = __fsub_rn(m, l); pos += 1; }
-        const float la = __shfl_sync(FULL, a, pos, 8);
-        const float lx = __shfl_sync(FULL, v.x, pos, 8), ly = __shfl_sync(FULL, v.y, pos, 8);
-        const float lz = __shfl_sync(FULL, v.z, pos, 8), lw = __shfl_sync(FULL, v.w, pos, 8);
-        int sub = 0;
-        float l0 = lx, l1 = ly;
-        if (m > la) { m = __fsub_rn(m, la); sub = 2; l0 = lz; l1 = lw; }
-        leafv = l0;
-        if (m > l0) { m = __fsub_rn(m, l0); sub += 1; leafv = l1; }
-        node = (c == 5 ? (node << 5) : 0) + 4 * pos + sub;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float a = op_sum(v[u].x, v[u].y), b2 = op_sum(v[u].z, v[u].w);
+            const float c4 = op_sum(a, b2);
+            const float s1 = op_sum(c4, __shfl_xor_sync(FULL, c4, 1, 8));
+            const float s2 = op_sum(s1, __shfl_xor_sync(FULL, s1, 2, 8));
+            float mm = m[u];
+            int pos = 0;
+            float l = __shfl_sync(FULL, s2, 0, 8);
+            if (mm > l) { mm = __fsub_rn(mm, l); pos = 4; }
+            l = __shfl_sync(FULL, s1, pos, 8);
+            if (mm > l) { mm = __fsub_rn(mm, l); pos += 2; }
+            l = __shfl_sync(FULL, c4, pos, 8);
+            if (mm > l) { mm = __fsub_rn(mm, l); pos += 1; }
+            const float la = __shfl_sync(FULL, a, pos, 8);
+            const float lx = __shfl_sync(FULL, v[u].x, pos, 8), ly = __shfl_sync(FULL, v[u].y, pos, 8);
+            const float lz = __shfl_sync(FULL, v[u].z, pos, 8), lw = __shfl_sync(FULL, v[u].w, pos, 8);
+            int sub = 0;
+            float l0 = lx, l1 = ly;
+            if (mm > la) { mm = __fsub_rn(mm, la); sub = 2; l0 = lz; l1 = lw; }
+            float lf = l0;
+            if (mm > l0) { mm = __fsub_rn(mm, l0); sub += 1; lf = l1; }
+            m[u] = mm;
+            leafv[u] = lf;
+            node[u] = (c == 5 ? (node[u] << 5) : 0) + 4 * pos + sub;
+        }
         d = s;
         c = 5;
     }
-    *leaf_out = leafv;
-    return over ? t.size : node;
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (over[u]) node[u] = t.size;
+}
+
+__device__ __forceinline__ long long group_descend(const TreeView &t, float m, float *leaf_out)
+{
+    float mm[1] = {m}, lf[1];
+    long long nd[1];
+    group_descend_multi<1>(t, mm, nd, lf);
+    *leaf_out = lf[0];
+    return nd[0];
+}
+
+// R sub-rounds of 4 descents each (one per 8-lane group): lane l = 4 sub + g hands its mass to group g in sub-round
+// `sub` and collects the result.  R = 8 runs the sub-rounds four at a time (interleaved descents).
+__device__ __forceinline__ void warp_descend_rounds(const TreeView &t, float m, int R, long long &mine, float &my_leaf)
+{
+    const int lane = lane_id();
+    mine = 0; my_leaf = 0.0f;
+    if (R == 8) {
+#pragma unroll 1
+        for (int sub = 0; sub < 8; sub += 4) {
+            float mg[4], lf[4];
+            long long nd[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mg[u] = __shfl_sync(FULL, m, 4 * (sub + u) + (lane >> 3));
+            group_descend_multi<4>(t, mg, nd, lf);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long gi = __shfl_sync(FULL, nd[u], (lane & 3) << 3);
+                const float gf = __shfl_sync(FULL, lf[u], (lane & 3) << 3);
+                if ((lane >> 2) == sub + u) { mine = gi; my_leaf = gf; }
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int sub = 0; sub < R; ++sub) {
+            const float mg = __shfl_sync(FULL, m, 4 * sub + (lane >> 3));
+            float leafv;
+            const long long i = group_descend(t, mg, &leafv);
+            const long long gi = __shfl_sync(FULL, i, (lane & 3) << 3);
+            const float gf = __shfl_sync(FULL, leafv, (lane & 3) << 3);
+            if ((lane >> 2) == sub) { mine = gi; my_leaf = gf; }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) tree_scan_kernel(TreeView t, long long n, const float *mass, long long *idx_out)
@@ -791,15 +872,9 @@ __global__ void __launch_bounds__(256) tree_scan_kernel(TreeView t, long long n,
     for (long long rd = 0; rd < rounds; ++rd) {
         const long long k = (w0 + rd * n_warps) * 32 + lane;
         const float m = k < n ? mass[k] : 0.0f;
-        long long mine = 0;
-#pragma unroll 1
-        for (int sub = 0; sub < 8; ++sub) {
-            const float mg = __shfl_sync(FULL, m, 4 * sub + (lane >> 3));
-            float leafv;
-            const long long i = group_descend(t, mg, &leafv);
-            const long long gi = __shfl_sync(FULL, i, (lane & 3) << 3);
-            if ((lane >> 2) == sub) mine = gi;
-        }
+        long long mine;
+        float my_leaf;
+        warp_descend_rounds(t, m, 8, mine, my_leaf);
         if (k < n) idx_out[k] = mine;
     }
 }
@@ -890,19 +965,9 @@ __global__ void __launch_bounds__(256) tree_sample_kernel(TreeView t, long long 
             const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
             m = (mode == 0) ? (float)(0.0 + ((double)p_sum - 0.0) * uk) : stratified_mass(k % batch, uk, batch, p_sum);
         }
-        long long mine = 0;
-        float my_leaf = 0.0f;
-#pragma unroll 1
-        for (int sub = 0; sub < R; ++sub) {
-            // group g (lanes 8g .. 8g+7) descends for the sample of lane 4 sub + g
-            const float mg = __shfl_sync(FULL, m, 4 * sub + (lane >> 3));
-            float leafv;
-            const long long i = group_descend(t, mg, &leafv);
-            // lane l = 4 sub + g collects from the head of group g
-            const long long gi = __shfl_sync(FULL, i, (lane & 3) << 3);
-            const float gl = __shfl_sync(FULL, leafv, (lane & 3) << 3);
-            if ((lane >> 2) == sub) { mine = gi; my_leaf = gl; }
-        }
+        long long mine;
+        float my_leaf;
+        warp_descend_rounds(t, m, R, mine, my_leaf);
         if (live) {
             if (mine > len - 1) { mine = len - 1; my_leaf = leaf_ptr(t)[mine]; }
             idx_out[k] = mine;
@@ -1023,17 +1088,9 @@ __global__ void __launch_bounds__(256) global_sample_kernel(TreeView t, const pb
             const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
             route_stratum(g, G, k, n_global, uk, &res);
         }
-        long long mine = 0;
-        float my_leaf = 0.0f;
-#pragma unroll 1
-        for (int sub = 0; sub < R; ++sub) {
-            const float mg = __shfl_sync(FULL, res, 4 * sub + (lane >> 3));
-            float leafv;
-            const long long i = group_descend(t, mg, &leafv);
-            const long long gi = __shfl_sync(FULL, i, (lane & 3) << 3);
-            const float gl = __shfl_sync(FULL, leafv, (lane & 3) << 3);
-            if ((lane >> 2) == sub) { mine = gi; my_leaf = gl; }
-        }
+        long long mine;
+        float my_leaf;
+        warp_descend_rounds(t, res, R, mine, my_leaf);
         if (mine_row && pos < n_global) {
             if (live) {
                 if (mine > len - 1) { mine = len - 1; if (mine < 0) mine = 0; my_leaf = leaf_ptr(t)[mine]; }

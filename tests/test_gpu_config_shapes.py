@@ -53,8 +53,61 @@ def _make_batch(obs_shape, A, B, fs, seed):
     return batch, to(batch), w
 
 
-def _build_pair(name, use_cuda_graph=False):
-    """Product agent on the GPU, oracle agent on the CPU, identical weights (target = a transformed copy)."""
+def _relu_inputs(model, run):
+    """{ReLU module: (preceding Linear / Conv2d, max |z - bias|, min |z|)} over one oracle forward pass ``run()``."""
+    import torch.nn as nn
+    prev_of, stats, hooks = {}, {}, []
+    for seq in (m for m in model.modules() if isinstance(m, nn.Sequential)):
+        mods = list(seq)
+        for i, m in enumerate(mods):
+            if isinstance(m, nn.ReLU) and i > 0 and isinstance(mods[i - 1], (nn.Linear, nn.Conv2d)):
+                prev_of[m] = mods[i - 1]
+    for relu, lin in prev_of.items():
+        def hook(mod, inp, _lin=lin, _relu=relu):
+            z = inp[0].detach()
+            b = _lin.bias.detach().view(1, -1, *([1] * (z.dim() - 2)))
+            hi, lo = float((z - b).abs().max()), float(z.abs().min())
+            old = stats.get(_relu)
+            stats[_relu] = (_lin, max(hi, old[1]) if old else hi, min(lo, old[2]) if old else lo)
+        hooks.append(relu.register_forward_pre_hook(hook))
+    try:
+        with torch.no_grad():
+            run()
+    finally:
+        for h in hooks:
+            h.remove()
+    return stats
+
+
+def _move_off_the_kinks(oracle, cpu_batch, taus, margin=3.0):
+    """A ReLU mask is a step function of its pre-activation: where z is within an fp32 rounding of 0, the CPU and the
+    GPU may legitimately disagree about the mask, and ONE such element moves a whole row of a weight gradient (measured
+    with default initialisation: 1-3 flips per update at configs[0] shapes, rows off by up to 6e-3 -- profiles/
+    diag_parity.py; the loss and the TD errors are continuous and stay exact).  Parity of GRADIENTS is therefore
+    judged away from the kinks: every layer that feeds a ReLU gets biases +-margin * max|z - bias| (alternating by
+    unit), so each unit is firmly on or firmly off for every row, and both mask states are exercised.  Layers are
+    settled front to back (a layer's inputs change when the layer before it is moved): a few passes.  Returns the
+    smallest min|z| / max|z - bias| ratio over the layers."""
+    def run():
+        oracle.inject_taus([t.clone() for t in taus])
+        oracle.model.get_losses(cpu_batch, oracle.target)
+    ratio = 0.0
+    for _ in range(6):
+        stats = _relu_inputs(oracle.model, run)
+        ratio = min(lo / max(hi, 1e-30) for _, hi, lo in stats.values())
+        if ratio > 1.0:
+            break
+        with torch.no_grad():
+            for relu, (lin, hi, lo) in stats.items():
+                sign = torch.ones_like(lin.bias)
+                sign[1::2] = -1.0
+                lin.bias.copy_(sign * (margin * hi))
+    return ratio
+
+
+def _build_pair(name, use_cuda_graph=False, dekink_with=None):
+    """Product agent on the GPU, oracle agent on the CPU, identical weights (target = a transformed copy).
+    ``dekink_with`` = (cpu_batch, taus): see _move_off_the_kinks."""
     import prism_b200
     from oracle.agent_oracle import OracleAgent
     make, obs_shape, A, B, fs = _spec(name)
@@ -70,14 +123,20 @@ def _build_pair(name, use_cuda_graph=False):
         if k.endswith(".bias") and v.dim() == 1 and v.numel() == A and ("embedding_to_quantile_layer" in k or "q_heads" in k):
             head = int(k.split("q_heads.")[1].split(".")[0]) if "q_heads." in k else 0
             v += torch.linspace(-0.6, 0.6, A).roll(head) * (1.0 + 0.05 * head)
-    agent.model.load_state_dict(sd, strict=True)
     ocfg = dataclasses.replace(cfg, device="cpu", use_cuda_graph=False)
     oracle = OracleAgent(ocfg, obs_shape, A)
     oracle.model.load_state_dict(sd, strict=True)
+    if oracle.target is not None:
+        oracle.target.load_state_dict({k: target_transform(v) for k, v in sd.items()}, strict=True)
+    if dekink_with is not None:
+        ratio = _move_off_the_kinks(oracle, *dekink_with)
+        assert ratio > 1.0, "pre-activations still near a ReLU kink: min |z| / max |z - bias| = %.3g" % ratio
+        sd = {k: v.detach().clone() for k, v in oracle.model.state_dict().items()}
+        if oracle.target is not None:
+            oracle.target.load_state_dict({k: target_transform(v) for k, v in sd.items()}, strict=True)
+    agent.model.load_state_dict(sd, strict=True)
     if agent.target_model is not None:
-        tsd = {k: target_transform(v) for k, v in sd.items()}
-        agent.target_model.load_state_dict(tsd, strict=True)
-        oracle.target.load_state_dict(tsd, strict=True)
+        agent.target_model.load_state_dict({k: target_transform(v) for k, v in sd.items()}, strict=True)
     return cfg, agent, oracle, obs_shape, A, B, fs
 
 
@@ -127,9 +186,10 @@ def _compare(agent, oracle, out, td, name, tol=TOL):
 @pytest.mark.parametrize("name", ["configs0", "configs1", "configs4"])
 def test_update_at_baseline_shapes_matches_oracle(name):
     from prism_b200.agents import ops
-    cfg, agent, oracle, obs_shape, A, B, fs = _build_pair(name)
+    make, obs_shape, A, B, fs = _spec(name)
     cpu_batch, dev_batch, w = _make_batch(obs_shape, A, B, fs, seed=7)
-    taus = _taus(cfg, B, seed=11)
+    taus = _taus(make(), B, seed=11)
+    cfg, agent, oracle, obs_shape, A, B, fs = _build_pair(name, dekink_with=(cpu_batch, taus))
     oracle.inject_taus([t.clone() for t in taus])
     out = oracle.update(cpu_batch, w)
     _inject(cfg, agent, taus)
@@ -147,11 +207,38 @@ def test_update_at_baseline_shapes_matches_oracle(name):
         assert routes.get("ln:fused", 0) >= 2, routes                # LayerNorm kernels of this library
 
 
+@pytest.mark.parametrize("name", ["configs0", "configs4"])
+def test_default_initialisation_values_exact_gradients_up_to_relu_flips(name):
+    """The same comparison WITHOUT moving the weights off the ReLU kinks (the reference's own initialisation): losses and
+    TD errors -- continuous in every pre-activation -- must still agree to 1e-4; a gradient tensor may differ only
+    through a handful of flipped masks, i.e. in a small part of its energy (relative L2 error below 2 %)."""
+    cfg, agent, oracle, obs_shape, A, B, fs = _build_pair(name)
+    cpu_batch, dev_batch, w = _make_batch(obs_shape, A, B, fs, seed=40)
+    taus = _taus(cfg, B, seed=50)
+    oracle.inject_taus([t.clone() for t in taus])
+    out = oracle.update(cpu_batch, w)
+    _inject(cfg, agent, taus)
+    td = agent.update(dev_batch, w.to(DEV))
+    torch.cuda.synchronize()
+    assert rel_err(td.cpu().numpy(), out["td"].numpy()) < TOL
+    assert rel_err(agent._static_total_loss.detach().cpu().numpy(), out["total"].numpy()) < TOL
+    ograds = {k: p.grad for k, p in oracle.model.named_parameters()}
+    coef = float(agent.optimizer.norm_out[1])
+    worst = 0.0
+    for k, g in _named_grads(agent).items():
+        a, b = g.cpu().double().numpy() * coef, ograds[k].double().numpy()
+        worst = max(worst, float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)))
+    print("%s default init: worst relative L2 gradient error %.2e" % (name, worst))
+    assert worst < 2e-2
+
+
 @pytest.mark.parametrize("name", ["configs0", "configs1"])
 def test_graph_update_at_baseline_shapes_matches_oracle(name):
     """Same comparison with the update captured as a CUDA graph (Agent._update_with_cuda_graph): two steps, so the
     replayed graph -- not the capture's warm-up -- is what is checked."""
-    cfg, agent, oracle, obs_shape, A, B, fs = _build_pair(name, use_cuda_graph=True)
+    make, obs_shape, A, B, fs = _spec(name)
+    probe = (_make_batch(obs_shape, A, B, fs, seed=20)[0], _taus(make(), B, seed=30))
+    cfg, agent, oracle, obs_shape, A, B, fs = _build_pair(name, use_cuda_graph=True, dekink_with=probe)
     for it in range(2):
         cpu_batch, dev_batch, w = _make_batch(obs_shape, A, B, fs, seed=20 + it)
         taus = _taus(cfg, B, seed=30 + it)
@@ -185,7 +272,9 @@ def test_configs0_parity_holds_over_consecutive_steps():
     over, so a systematic difference between the two implementations would compound here.  Parameters are compared by
     their UPDATE (value - initial value): Adam's step is ~lr per element whatever the gradient's size, so the change of
     a parameter, not its magnitude, is the scale on which an fp32 rounding difference of a near-zero gradient shows."""
-    cfg, agent, oracle, obs_shape, A, B, fs = _build_pair("configs0")
+    make, obs_shape, A, B, fs = _spec("configs0")
+    probe = (_make_batch(obs_shape, A, B, fs, seed=40)[0], _taus(make(), B, seed=50))
+    cfg, agent, oracle, obs_shape, A, B, fs = _build_pair("configs0", dekink_with=probe)
     init = {k: v.detach().cpu().clone() for k, v in agent.model.state_dict().items()}
     for it in range(3):
         cpu_batch, dev_batch, w = _make_batch(obs_shape, A, B, fs, seed=40 + it)
@@ -195,7 +284,7 @@ def test_configs0_parity_holds_over_consecutive_steps():
         _inject(cfg, agent, taus)
         td = agent.update(dev_batch, w.to(DEV))
         torch.cuda.synchronize()
-        _compare(agent, oracle, out, td, "configs0 step %d" % it, tol=3e-4)
+        _compare(agent, oracle, out, td, "configs0 step %d" % it, tol=2e-4)
     osd = oracle.model.state_dict()
     frac_off = []
     for k, v in agent.model.state_dict().items():
