@@ -288,10 +288,11 @@ NARROW_OUT, NARROW_MAX_ROWS = 32, 4096
 
 
 _TC_WORKSPACE = {}
-# stream-K partial tiles: at most 2 per CTA of 128 x 256 floats -> 2 * 148 * 128 * 256 floats (39 MB).  One workspace
+# partial tiles: at most 3 per CTA of 128 x 256 floats (two stream-K cut tiles + the running sum of a tile accumulated
+# in chunks) -> 3 * 148 * 128 * 256 floats (58 MB).  One workspace
 # PER STREAM: GEMMs on parallel graph branches (bootstrap passes, weight gradients) may overlap at their tails, and a
 # GEMM's fix-up must never read partial tiles of another one.
-TC_WORKSPACE_FLOATS = 10 * 1024 * 1024
+TC_WORKSPACE_FLOATS = 15 * 1024 * 1024
 TC_SPLIT_MODE = 0                           # 0: hi = raw fp32 word (hardware reads its top 19 bits); 1: cvt.rna hi
 
 

@@ -76,7 +76,7 @@ const char *pb_error_string(int code)
     switch (code) {
         case PB_OK: return "ok";
         case PB_E_ARG: return "invalid argument";
-        case PB_E_CAPACITY: return "capacity must be a power of two in [2, 2^30] with size <= capacity";
+        case PB_E_CAPACITY: return "capacity must be a power of two in [32, 2^30] with size <= capacity";
         case PB_E_UNSUPPORTED: return "unsupported option";
         case PB_E_POOL: return "aux observation pool exhausted";
         default: break;

@@ -15,13 +15,14 @@
 //    and the min tree shares the leaf array of the sum tree (a leaf is written with the same value in both;
 //    slots that were never written -- index >= len -- read as +inf on the min side).
 //    16M leaves: 64 MiB + 2 x 2.1 MiB instead of 2 x 128 MiB, i.e. the whole store fits the 126 MB L2.
-//      - sampling descends 5 levels per dependent 128-byte load, 8 lanes per sample (4 samples per warp);
+//      - sampling descends 5 levels per dependent 128-byte load: 8 lanes per sample for one learner batch (latency),
+//        a thread per sample over a shared-memory copy of the top 14 levels for many batches in flight (throughput);
 //      - a sorted priority update is ONE launch: the leader of every touched line applies its leaves, reduces the
 //        line and climbs; lines of the next stored level are finished by whichever child arrives last (arrival
 //        counters, no spinning), and the last CTA (ticket) rebuilds the top heap and the state block;
-//      - any other batch (unsorted, duplicates, K batches in flight) is TWO launches: a mark pass (dedup tag on the
-//        leaf slot + one bit per touched leaf line) and a sparse rebuild whose CTAs own 32768-leaf spans and climb three
-//        stored levels without any cross-CTA dependency -- cost proportional to the touched lines;
+//      - any other batch (unsorted, duplicates, K batches in flight) is three launches: a mark pass (dedup tag on the
+//        leaf slot + one bit per touched leaf line), the leaf scatter, and a sparse rebuild whose CTAs own 32768-leaf
+//        spans (lane per touched leaf line) and climb three stored levels without any cross-CTA dependency;
 //      - batches beyond cap/16 entries scatter their leaves and rebuild every line with one streaming pass over the
 //        leaf array (4.3 B per leaf of traffic, independent of the batch size);
 //      - the bulk build is that same streaming pass.
@@ -215,64 +216,46 @@ __device__ void finalize_state(const TreeView &t, int mode, long long n_new, lon
 }
 
 // ---------------------------------------------------------------------------------
-// top phase: rebuild heap levels TL-1 .. 0 of BOTH trees from level TL.  Called by every thread of ONE CTA
-// (blockDim.x threads, a multiple of 64; the first half works on the sum tree, the second on the min tree).
-// sm: 2 x 2048 floats.  Levels > 10 are reduced in registers per level-10 subtree, levels <= 10 in shared memory.
+// top phase: rebuild heap levels TL-1 .. 0 of BOTH trees from level TL (32 .. 512 nodes).  Called by every thread of ONE
+// CTA (blockDim.x threads, a multiple of 64; the first half works on the sum tree, the second on the min tree).
+// Every warp reduces lines of 32 level-TL nodes with shuffles, storing the intermediate levels as it goes; the
+// <= 16 line totals (level TL-5) meet in shared memory and one warp per tree finishes the last levels.
 // ---------------------------------------------------------------------------------
-constexpr int TOP_SM_LEVEL = 10;
-constexpr int TOP_SM_FLOATS = 2 << TOP_SM_LEVEL;    // one smem heap of levels 0..10
+constexpr int TOP_SM_FLOATS = 32;                   // per tree: the line totals
 
 __device__ void top_rebuild(const TreeView &t, float *sm, long long len)
 {
     const int half = blockDim.x >> 1;
     const bool is_min = threadIdx.x >= half;
     const int tid = is_min ? threadIdx.x - half : threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5, n_warps = half >> 5;
     float *heap = is_min ? t.min : t.sum;
     float *s = sm + (is_min ? TOP_SM_FLOATS : 0);
-    const int TL = t.TL;
+    const int TL = t.TL;                                        // 5 .. 9
     const bool shared_leaves = is_min && TL == t.L;             // tiny trees: level TL is the shared leaf level
     const float *src = shared_leaves ? t.sum + (1 << TL) : heap + (1 << TL);
-    const int S = TL < TOP_SM_LEVEL ? TL : TOP_SM_LEVEL;        // level held at the bottom of the smem heap
-    const int r = TL - S;                                       // register levels (0..4)
-    const int n_sub = 1 << S;
-    for (int q = tid; q < n_sub; q += half) {
-        float v[16];
-        const long long base = (long long)q << r;
+    const int n_lines = 1 << (TL - 5);
+    for (int line = warp; line < n_lines; line += n_warps) {
+        const int e = (line << 5) + lane;
+        float v = ldcg(src + e);
+        if (shared_leaves) v = min_of_leaf(v, e, len);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            if (k < (1 << r)) {
-                float x = ldcg(src + base + k);
-                v[k] = shared_leaves ? min_of_leaf(x, base + k, len) : x;
-            } else {
-                v[k] = 0.0f;
-            }
+        for (int k = 0; k < 5; ++k) {
+            const float o = __shfl_xor_sync(FULL, v, 1 << k);
+            v = is_min ? op_min(v, o) : op_sum(v, o);
+            if ((lane & ((2 << k) - 1)) == 0) heap[(1 << (TL - 1 - k)) + (e >> (k + 1))] = v;
         }
-#pragma unroll
-        for (int lv = 1; lv <= 4; ++lv) {
-            if (lv <= r) {
-                const int w = 1 << (r - lv);                    // nodes of this subtree at level TL - lv
-                float *dst = heap + (1 << (TL - lv)) + ((long long)q << (r - lv));
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (k < w) {
-                        v[k] = is_min ? op_min(v[2 * k], v[2 * k + 1]) : op_sum(v[2 * k], v[2 * k + 1]);
-                        dst[k] = v[k];
-                    }
-            }
-        }
-        s[n_sub + q] = v[0];
+        if (lane == 0) s[line] = v;                              // node `line` of level TL - 5 (already stored above)
     }
     __syncthreads();
-    for (int d = S - 1; d >= 0; --d) {
-        const int n_d = 1 << d;
-        for (int i = tid; i < n_d; i += half) {
-            const float l = s[2 * (n_d + i)], rr = s[2 * (n_d + i) + 1];
-            s[n_d + i] = is_min ? op_min(l, rr) : op_sum(l, rr);
+    if (warp == 0 && TL > 5) {
+        float v = lane < n_lines ? s[lane] : (is_min ? INF : 0.0f);
+        for (int k = 0; k < TL - 5; ++k) {
+            const float o = __shfl_xor_sync(FULL, v, 1 << k);
+            v = is_min ? op_min(v, o) : op_sum(v, o);
+            if (lane < n_lines && (lane & ((2 << k) - 1)) == 0) heap[(1 << (TL - 6 - k)) + (lane >> (k + 1))] = v;
         }
-        __syncthreads();
     }
-    // heap levels S-1 .. 0 (level S itself was written by the register stage, or is level TL)
-    for (int i = tid + 1; i < n_sub; i += half) heap[i] = s[i];
 }
 
 // last-CTA ticket: returns true in every thread of the CTA that arrives last.  pad[0] is reset by finalize_state.
@@ -519,91 +502,68 @@ __global__ void upd_leaf_sorted_kernel(TreeView t, long long n, const long long 
 }
 
 // ---------------------------------------------------------------------------------
-// sparse rebuild (the second launch of a general update; the first is upd_mark_kernel).  A CTA owns a span of 32768
-// leaves = 32 words of the touched-line bitmap = one line of level L-10.  Warp v takes 4 of those words: for every set
-// bit it loads the leaf line, RESOLVES the dedup tags it finds there (a NaN-tagged slot names the winning entry: its
-// value is computed and stored now), reduces the line to its node of level L-5; for every word with a bit set it then
-// reduces that line of level L-5 (which it has just completed) to the node of level L-10; finally warp 0 reduces the
-// CTA's line of level L-10 to the node of level L-15.  No cross-CTA dependency below the top heap; cost is
-// proportional to the number of touched lines.  The bitmap words are cleared on the way.  The last CTA (ticket)
-// rebuilds the top heap and the state block when level L-15 is (or lies above) the heap's bottom level.
+// sparse rebuild (the last launch of a general update, after upd_mark_kernel + upd_leaf_kernel).  A CTA owns a span of
+// 32768 leaves = 32 words of the touched-line bitmap = one line of level L-10; a warp takes 2 of those words.  For a
+// word, LANE l owns leaf line 32 w + l: if its bit is set it streams the line (8 x 128-bit loads, all in flight),
+// reduces it in registers in tree order and stores the node of level L-5; otherwise it just loads the node that is
+// there.  The warp then holds the whole line of level L-5 in its lanes: 5 shuffle levels give the node of level L-10.
+// Finally warp 0 reduces the CTA's line of level L-10 to the node of level L-15.  No cross-CTA dependency below the
+// top heap; ~130 warp instructions per bitmap word whatever its population.  The bitmap words are cleared on the
+// way.  The last CTA (ticket) rebuilds the top heap and the state block when level L-15 is (or lies above) the
+// heap's bottom level.
 // ---------------------------------------------------------------------------------
 constexpr int SPR_THREADS = 512;                 // 16 warps, 2 bitmap words (64 leaf lines) each
-constexpr int SPR_U = 8;                         // touched lines per round: that many 128-byte loads in flight per warp
 
-__global__ void __launch_bounds__(SPR_THREADS) tree_rebuild_sparse_kernel(TreeView t, const float *val, int mode,
-                                                                          long long n_new, int fuse_top)
+__global__ void __launch_bounds__(SPR_THREADS) tree_rebuild_sparse_kernel(TreeView t, int mode, long long n_new,
+                                                                          int fuse_top)
 {
     __shared__ float sm_top[2 * TOP_SM_FLOATS];
     const int lane = lane_id(), wic = threadIdx.x >> 5;
     constexpr int WPW = 32 / (SPR_THREADS / 32);                 // bitmap words per warp
     const long long len = len_after(t, mode, n_new, -1);
-    const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
-    float *leaf = leaf_ptr(t);
+    const float *leaf = leaf_ptr(t);
     float *n1s = sum_level(t, t.L - 5), *n1m = min_level(t, t.L - 5);
     const long long n_words = t.cap >= 1024 ? t.cap >> 10 : 1;
     const int P = t.P;
     for (long long span = blockIdx.x; span * 32 < n_words; span += gridDim.x) {
-        unsigned word_bits[WPW];
         int touched_any = 0;
 #pragma unroll
         for (int q = 0; q < WPW; ++q) {
             const long long w = span * 32 + wic * WPW + q;
             unsigned bits = 0;
             if (w < n_words && lane == 0) { bits = t.bitmap[w]; if (bits) t.bitmap[w] = 0u; }
-            word_bits[q] = __shfl_sync(FULL, bits, 0);
-            touched_any |= word_bits[q] != 0u;
-        }
+            bits = __shfl_sync(FULL, bits, 0);
+            if (!bits) continue;                                  // warp-uniform
+            touched_any = 1;
+            const long long line = (w << 5) + lane;
+            float vs, vm;
+            if ((bits >> lane) & 1u) {
+                const float4 *src = reinterpret_cast<const float4 *>(leaf + (line << 5));
+                float4 v[8];
 #pragma unroll
-        for (int q = 0; q < WPW; ++q) {
-            const long long w = span * 32 + wic * WPW + q;
-            unsigned bits = word_bits[q];
-            while (bits) {
-                long long line[SPR_U];
-                int x[SPR_U];
+                for (int k = 0; k < 8; ++k) v[k] = __ldcg(src + k);
+                float ps[8], pm[8];
+                const bool whole = (line << 5) + 32 <= len;       // every leaf of the line is a filled slot
 #pragma unroll
-                for (int u = 0; u < SPR_U; ++u) {
-                    line[u] = -1;
-                    if (bits) { line[u] = (w << 5) + (__ffs(bits) - 1); bits &= bits - 1; }
-                }
-#pragma unroll
-                for (int u = 0; u < SPR_U; ++u)
-                    x[u] = line[u] >= 0 ? __ldcg(reinterpret_cast<const int *>(leaf + (line[u] << 5) + lane)) : 0;
-                // resolve dedup tags: the winning entry's value (gathers first, stores after: independent loads)
-                float nv[SPR_U];
-#pragma unroll
-                for (int u = 0; u < SPR_U; ++u)
-                    nv[u] = (line[u] >= 0 && x[u] >= LEAF_TAG) ? entry_leaf(t, val, (long long)(x[u] - LEAF_TAG), mode, defp) : 0.0f;
-#pragma unroll
-                for (int u = 0; u < SPR_U; ++u) {
-                    if (line[u] >= 0 && x[u] >= LEAF_TAG) {
-                        leaf[(line[u] << 5) + lane] = nv[u];
-                        x[u] = __float_as_int(nv[u]);
+                for (int k = 0; k < 8; ++k) {
+                    float4 m = v[k];
+                    if (!whole) {
+                        const long long e = (line << 5) + 4 * k;
+                        m.x = min_of_leaf(m.x, e + 0, len); m.y = min_of_leaf(m.y, e + 1, len);
+                        m.z = min_of_leaf(m.z, e + 2, len); m.w = min_of_leaf(m.w, e + 3, len);
                     }
+                    ps[k] = op_sum(op_sum(v[k].x, v[k].y), op_sum(v[k].z, v[k].w));
+                    pm[k] = op_min(op_min(m.x, m.y), op_min(m.z, m.w));
                 }
-#pragma unroll
-                for (int u = 0; u < SPR_U; ++u) {
-                    if (line[u] < 0) continue;                    // warp-uniform
-                    float vs = __int_as_float(x[u]), vm = min_of_leaf(vs, (line[u] << 5) + lane, len);
-                    line_reduce(vs, vm);
-                    if (lane == 0) { n1s[line[u]] = vs; n1m[line[u]] = vm; }
-                }
+                vs = op_sum(op_sum(op_sum(ps[0], ps[1]), op_sum(ps[2], ps[3])), op_sum(op_sum(ps[4], ps[5]), op_sum(ps[6], ps[7])));
+                vm = op_min(op_min(op_min(pm[0], pm[1]), op_min(pm[2], pm[3])), op_min(op_min(pm[4], pm[5]), op_min(pm[6], pm[7])));
+                n1s[line] = vs; n1m[line] = vm;
+            } else {
+                vs = ldcg(n1s + line); vm = ldcg(n1m + line);
             }
-        }
-        if (P >= 2) {
-            __syncwarp();                                         // lane 0's node stores -> the whole warp's loads
-            float vs[WPW], vm[WPW];
-#pragma unroll
-            for (int q = 0; q < WPW; ++q) {
-                const long long w = span * 32 + wic * WPW + q;
-                if (word_bits[q]) { vs[q] = ldcg(n1s + (w << 5) + lane); vm[q] = ldcg(n1m + (w << 5) + lane); }
-            }
-#pragma unroll
-            for (int q = 0; q < WPW; ++q) {
-                const long long w = span * 32 + wic * WPW + q;
-                if (!word_bits[q]) continue;
-                line_reduce(vs[q], vm[q]);
-                if (lane == 0) { sum_level(t, t.L - 10)[w] = vs[q]; min_level(t, t.L - 10)[w] = vm[q]; }
+            if (P >= 2) {
+                line_reduce(vs, vm);                              // the lanes hold the word's line of level L-5
+                if (lane == 0) { sum_level(t, t.L - 10)[w] = vs; min_level(t, t.L - 10)[w] = vm; }
             }
         }
         if (P >= 3) {
@@ -622,16 +582,19 @@ __global__ void __launch_bounds__(SPR_THREADS) tree_rebuild_sparse_kernel(TreeVi
 }
 
 // ---------------------------------------------------------------------------------
-// sorted input, ONE launch: warp per batch entry (grid-stride).  The first entry of every run of entries that
-// fall into the same leaf line is the line's leader: it writes the run's leaves (last of equal indices wins),
-// reduces the line and writes the node of the stored level above.  Lines of the levels above are finished by
-// whichever child arrives last: the first entry of a line's run registers the number of touched children in the
-// line's arrival counter (+c), every finished child subtracts one, and the warp whose atomic brings the counter
-// back to zero reduces the line and climbs on (the counter is zero again for the next call; nobody spins).
-// The last CTA (ticket) rebuilds the top heap and the state block.
+// sorted input, ONE launch: warp per batch entry (grid-stride).  Entries are grouped by the 1024-leaf SPAN they fall
+// into (one line of level L-5; 32 leaf lines).  The first entry of a span's run is its leader: it writes the run's
+// leaves (last of equal indices wins), reduces the touched leaf lines (several loads in flight) to their nodes of
+// level L-5, then -- being the only writer of that line -- reduces the span's line of level L-5 to the node of
+// level L-10.  Lines of the levels above are finished by whichever child arrives last: the first entry of a line's
+// run registers the number of touched children in the line's arrival counter (+c), every finished child subtracts
+// one (acq_rel), and the warp whose atomic brings the counter back to zero reduces the line and climbs on (the
+// counter is zero again for the next call; nobody spins).  The last CTA (ticket) rebuilds the top heap and the
+// state block.  Trees with a single deep level (P == 1) use the leaf line itself as the group.
 // ---------------------------------------------------------------------------------
 constexpr int CHAIN_THREADS = 512;
 constexpr long long CHAIN_MAX_N = 8192;      // beyond this the per-warp serial chain loses to mark + sparse rebuild
+constexpr int CHAIN_U = 4;                   // touched leaf lines in flight per leader
 
 struct RunScan { long long seq0; const long long *idx; long long n; int mode; };
 
@@ -676,6 +639,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) upd_chain_kernel(TreeView t, lo
     const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
     float *leaf = leaf_ptr(t);
     const int P = t.P;
+    const int gs = P >= 2 ? 10 : 5;                               // group = span of 2^gs leaves
     for (long long j = w0; j < n; j += n_warps) {
         long long i, ip = -1;
         if (!valid_at(t, r, j, i)) continue;
@@ -693,29 +657,35 @@ __global__ void __launch_bounds__(CHAIN_THREADS) upd_chain_kernel(TreeView t, lo
             }
             continue;
         }
-        const long long line = i >> 5;
-        if (prev_ok && (ip >> 5) == line) continue;               // the run leader does this line
-        // ---- registration: lines of the upper deep levels whose run starts at this entry
-        for (int m = P - 1; m >= 1; --m) {
+        const long long grp = i >> gs;
+        if (prev_ok && (ip >> gs) == grp) continue;               // the group's leader does this span
+        // ---- registration: lines of the levels above the group whose run starts at this entry.  The group's node
+        // lives at level L - gs = TL + 5 mg; the lines above are those of levels TL + 5m, m = mg .. 1.
+        const int mg = P - gs / 5;
+        for (int m = mg; m >= 1; --m) {
             const int shift = 5 * (P - m) + 5;                    // index >> shift = line index at level TL + 5m
             const long long pl = i >> shift;
             if (prev_ok && (ip >> shift) == pl) break;            // not the first entry of that line (nor of any above)
             const int c = count_children(t, r, j, shift, shift - 5, pl);
             if (lane == 0) atomicAdd(&t.cnt[t.coff[m] + pl], c);
         }
-        // ---- the leaf line: write the run's leaves, 32 entries at a time
+        // ---- the group's run: write its leaves, 32 entries at a time; collect the touched leaf lines
         float bm = 0.0f;
+        unsigned linebits = 0;
         for (long long base = j;; base += 32) {
             const long long jj = base + lane;
             long long ii = -1, inx = -1;
-            const bool ok = valid_at(t, r, jj, ii) && (ii >> 5) == line;
+            const bool ok = valid_at(t, r, jj, ii) && (ii >> gs) == grp;
             const unsigned bad = ~__ballot_sync(FULL, ok);
             const int run = bad ? __ffs(bad) - 1 : 32;
+            unsigned mine = 0;
             if (lane < run) {
                 if (idx_out) idx_out[jj] = ii;
                 if (mode == MODE_PRIORITY) bm = fmaxf(bm, fabsf(val[jj]));
                 if (!valid_at(t, r, jj + 1, inx) || inx != ii) leaf[ii] = entry_leaf(t, val, jj, mode, defp);
+                mine = 1u << ((ii >> 5) & (gs == 10 ? 31 : 0));
             }
+            linebits |= __reduce_or_sync(FULL, mine);
             if (run < 32) break;
         }
         if (mode == MODE_PRIORITY) {
@@ -723,13 +693,39 @@ __global__ void __launch_bounds__(CHAIN_THREADS) upd_chain_kernel(TreeView t, lo
             if (lane == 0 && bm > 0.0f) atomicMax(reinterpret_cast<int *>(&t.st->batch_max), __float_as_int(bm));
         }
         __syncwarp();
-        float vs = leaf[(line << 5) + lane];
-        float vm = min_of_leaf(vs, (line << 5) + lane, len);
-        line_reduce(vs, vm);
-        long long g = line;                                       // node index at level TL + 5(m) with m = P - 1
-        if (lane == 0) { sum_level(t, t.L - 5)[g] = vs; min_level(t, t.L - 5)[g] = vm; }
-        // ---- climb: level TL + 5m lines, m = P-1 .. 1
-        for (int m = P - 1; m >= 1; --m) {
+        // ---- touched leaf lines -> nodes of level L-5, CHAIN_U lines per round
+        float *n1s = sum_level(t, t.L - 5), *n1m = min_level(t, t.L - 5);
+        const long long line0 = gs == 10 ? grp << 5 : grp;        // first leaf line of the group
+        float vs = 0.0f, vm = 0.0f;
+        while (linebits) {
+            long long line[CHAIN_U];
+            float x[CHAIN_U];
+#pragma unroll
+            for (int u = 0; u < CHAIN_U; ++u) {
+                line[u] = -1;
+                if (linebits) { line[u] = line0 + (__ffs(linebits) - 1); linebits &= linebits - 1; }
+            }
+#pragma unroll
+            for (int u = 0; u < CHAIN_U; ++u) x[u] = line[u] >= 0 ? ldcg(leaf + (line[u] << 5) + lane) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < CHAIN_U; ++u) {
+                if (line[u] < 0) continue;                        // warp-uniform
+                vs = x[u]; vm = min_of_leaf(vs, (line[u] << 5) + lane, len);
+                line_reduce(vs, vm);
+                if (lane == 0) { n1s[line[u]] = vs; n1m[line[u]] = vm; }
+            }
+        }
+        long long g = grp;                                        // node index at the group's level
+        if (gs == 10) {
+            // the span's line of level L-5: this warp is its only writer in this launch
+            __syncwarp();
+            vs = ldcg(n1s + (grp << 5) + lane);
+            vm = ldcg(n1m + (grp << 5) + lane);
+            line_reduce(vs, vm);
+            if (lane == 0) { sum_level(t, t.L - 10)[grp] = vs; min_level(t, t.L - 10)[grp] = vm; }
+        }
+        // ---- climb: lines of level TL + 5m, m = mg .. 1
+        for (int m = mg; m >= 1; --m) {
             const long long pl = g >> 5;
             int newv = 0;
             if (lane == 0) newv = atom_add_acq_rel(&t.cnt[t.coff[m] + pl], -1) - 1;     // releases lane 0's node store
@@ -979,6 +975,131 @@ __global__ void __launch_bounds__(256) tree_sample_kernel(TreeView t, long long 
 }
 
 // ---------------------------------------------------------------------------------
+// throughput mode (many batches in flight): one THREAD per sample.  The CTA stages the top of the tree as a full
+// level-ordered heap in shared memory -- heap levels 0..TL copied, the stored level S <= 14 copied and the levels in
+// between rebuilt pairwise (bit-identical to a stored tree) -- so the first S levels cost one shared-memory load
+// each; every deeper stored level costs the thread one 128-byte line (8 x 128-bit loads in flight) whose 5 levels
+// it resolves in registers.  Same comparisons in the same order as the reference loop and as group_descend, so
+// both modes return identical indices.  ~10x fewer warp instructions per sample than the 8-lane descent.
+// ---------------------------------------------------------------------------------
+constexpr int ST_THREADS = 512;
+
+// one line (32 nodes of a stored level, children of `node`): go right and subtract iff mass > left, 5 times
+__device__ __forceinline__ void thread_line_descend(const float *__restrict__ lvl, long long &node, float &m, float &leaf)
+{
+    const float4 *p = reinterpret_cast<const float4 *>(lvl + (node << 5));
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 q = __ldg(p + k);
+        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+    float t16[16], t8[8], t4[4], t2[2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t16[i] = op_sum(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t8[i] = op_sum(t16[2 * i], t16[2 * i + 1]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t4[i] = op_sum(t8[2 * i], t8[2 * i + 1]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) t2[i] = op_sum(t4[2 * i], t4[2 * i + 1]);
+    int pos = 0;
+    float l = t2[0];
+    if (m > l) { m = __fsub_rn(m, l); pos = 1; }
+    l = pos ? t4[2] : t4[0];
+    pos <<= 1;
+    if (m > l) { m = __fsub_rn(m, l); pos |= 1; }
+    {   // left child of node `pos` at the 4-node level: t8[2 pos]
+        const float a = (pos & 1) ? t8[2] : t8[0], b = (pos & 1) ? t8[6] : t8[4];
+        l = (pos & 2) ? b : a;
+    }
+    pos <<= 1;
+    if (m > l) { m = __fsub_rn(m, l); pos |= 1; }
+    {   // t16[2 pos], pos in 0..7
+        const float a0 = (pos & 1) ? t16[2] : t16[0], a1 = (pos & 1) ? t16[6] : t16[4];
+        const float a2 = (pos & 1) ? t16[10] : t16[8], a3 = (pos & 1) ? t16[14] : t16[12];
+        const float b0 = (pos & 2) ? a1 : a0, b1 = (pos & 2) ? a3 : a2;
+        l = (pos & 4) ? b1 : b0;
+    }
+    pos <<= 1;
+    if (m > l) { m = __fsub_rn(m, l); pos |= 1; }
+    float lo, hi;                                                 // v[2 pos], v[2 pos + 1], pos in 0..15
+    {
+        float e[8], o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { e[i] = (pos & 1) ? v[4 * i + 2] : v[4 * i]; o[i] = (pos & 1) ? v[4 * i + 3] : v[4 * i + 1]; }
+        float e2[4], o2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { e2[i] = (pos & 2) ? e[2 * i + 1] : e[2 * i]; o2[i] = (pos & 2) ? o[2 * i + 1] : o[2 * i]; }
+        const float e3a = (pos & 4) ? e2[1] : e2[0], e3b = (pos & 4) ? e2[3] : e2[2];
+        const float o3a = (pos & 4) ? o2[1] : o2[0], o3b = (pos & 4) ? o2[3] : o2[2];
+        lo = (pos & 8) ? e3b : e3a;
+        hi = (pos & 8) ? o3b : o3a;
+    }
+    pos <<= 1;
+    leaf = lo;
+    if (m > lo) { m = __fsub_rn(m, lo); pos |= 1; leaf = hi; }
+    node = (node << 5) + pos;
+}
+
+__global__ void __launch_bounds__(ST_THREADS) tree_sample_thread_kernel(TreeView t, long long n, long long batch,
+                                                                        const double *u, int mode, float beta,
+                                                                        long long *idx_out, float *w_out,
+                                                                        float *mass_out, int S)
+{
+    extern __shared__ float sh[];                                 // heap of levels 0..S: node i of level d at [2^d + i]
+    const unsigned call = (unsigned)t.st->pad[2], seed = (unsigned)t.st->pad[3];
+    const int TL = t.TL;
+    for (int i = threadIdx.x; i < (2 << TL); i += blockDim.x) sh[i] = i ? t.sum[i] : 0.0f;
+    if (S > TL) {
+        const float4 *lv = reinterpret_cast<const float4 *>(sum_level(t, S));
+        float4 *dst = reinterpret_cast<float4 *>(sh + (1 << S));
+        for (int i = threadIdx.x; i < (1 << (S - 2)); i += blockDim.x) dst[i] = lv[i];
+        for (int d = S - 1; d > TL; --d) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < (1 << d); i += blockDim.x)
+                sh[(1 << d) + i] = op_sum(sh[2 * ((1 << d) + i)], sh[2 * ((1 << d) + i) + 1]);
+        }
+    }
+    __syncthreads();
+    const long long len = t.st->len;
+    const float p_sum = t.st->p_sum, p_min = t.st->p_min;
+    int bad = 0;
+    if (len <= 0) bad = PB_ST_EMPTY;
+    else if (!(p_sum > 0.0f)) bad = PB_ST_PSUM_NONPOS;
+    else if (!(p_min > 0.0f)) bad = PB_ST_PMIN_NONPOS;
+    const float root = sh[1];
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        if (bad) {
+            idx_out[k] = 0; w_out[k] = 0.0f;
+            if (mass_out) mass_out[k] = 0.0f;
+            if (k == 0) atomicOr(&t.st->status, bad);
+            continue;
+        }
+        const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
+        const float m0 = (mode == 0) ? (float)(0.0 + ((double)p_sum - 0.0) * uk) : stratified_mass(k % batch, uk, batch, p_sum);
+        float m = m0;
+        const bool over = m > root;
+        if (over) m = 0.0f;
+        int hn = 1;                                               // heap index in shared memory
+        for (int d = 0; d < S; ++d) {
+            hn <<= 1;
+            const float left = sh[hn];
+            if (m > left) { m = __fsub_rn(m, left); hn |= 1; }
+        }
+        long long node = hn - (1 << S);                           // index within level S
+        float leafv = sh[hn];
+        for (int s = S + 5; s <= t.L; s += 5) thread_line_descend(sum_level(t, s), node, m, leafv);
+        long long i = over ? t.size : node;
+        if (i > len - 1) { i = len - 1; leafv = leaf_ptr(t)[i]; }
+        idx_out[k] = i;
+        w_out[k] = is_weight(leafv, p_min, beta, t);
+        if (mass_out) mass_out[k] = m0;
+    }
+    if (!u) { __syncthreads(); rng_advance(t); }
+}
+
+// ---------------------------------------------------------------------------------
 // sharded global stratified sampling: the G shard roots are the leaves of a virtual
 // top tree, summed pairwise in fp32 (so shards concatenated == one big tree).  ONE launch: masses are
 // non-decreasing in the stratum number and the descent is monotone, so the strata a rank owns are a contiguous
@@ -1154,7 +1275,7 @@ int make_view(const pb_tree *t, TreeView *v)
 {
     if (!t || !t->sum || !t->min || !t->state) return PB_E_ARG;
     if (!pb_is_pow2(t->capacity) || t->size <= 0 || t->size > t->capacity) return PB_E_CAPACITY;
-    if (t->capacity < 2 || t->capacity > (1LL << 30)) return PB_E_CAPACITY;
+    if (t->capacity < 32 || t->capacity > (1LL << 30)) return PB_E_CAPACITY;     // at least one 32-leaf line
     Layout y;
     make_layout(t->capacity, &y);
     if (!t->counters) return PB_E_ARG;
@@ -1211,8 +1332,8 @@ int launch_update(const pb_tree *t, long long n, const long long *idx, const flo
         sorted = (2 * n <= v.size);     // a contiguous run of slots; a long one may wrap onto lines it already touched
     }
     // Three regimes.  (1) small sorted batches (one learner batch, the ring's extends): ONE launch, leaders + arrival
-    // counters.  (2) anything else up to cap/16 entries: mark (dedup tags + touched-line bitmap) + sparse rebuild, cost
-    // proportional to the touched lines.  (3) beyond that: scatter the leaves and stream the whole leaf array once.
+    // counters.  (2) anything else up to cap/16 entries: mark (dedup tags + touched-line bitmap), leaf scatter, sparse
+    // rebuild -- cost proportional to the batch.  (3) beyond that: scatter the leaves and stream the whole leaf array.
     if (v.P == 0) {
         if (sorted) {
             const int grid = persistent_grid(n, CHAIN_THREADS / 32, 2);
@@ -1234,9 +1355,10 @@ int launch_update(const pb_tree *t, long long n, const long long *idx, const flo
     const int nb = (int)((n + 255) / 256);
     if (n < v.cap / 16 && n <= LEAF_TAG_MAX_N) {
         PB_LAUNCH(upd_mark_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out, 1);
+        PB_LAUNCH(upd_leaf_kernel, nb, 256, 0, stream, v, n, idx, val, mode, (long long *)nullptr);
         const long long spans = v.cap >= 32768 ? v.cap >> 15 : 1;
         const int fuse = v.P <= 3 ? 1 : 0;
-        PB_LAUNCH(tree_rebuild_sparse_kernel, (int)(spans < 2048 ? spans : 2048), SPR_THREADS, 0, stream, v, val, mode, n, fuse);
+        PB_LAUNCH(tree_rebuild_sparse_kernel, (int)(spans < 2048 ? spans : 2048), SPR_THREADS, 0, stream, v, mode, n, fuse);
         if (!fuse) {
             // deeper trees: levels L-15 .. TL by the streaming pass over the (small) array of level L-15
             TreeView u2 = v;
@@ -1270,7 +1392,7 @@ extern "C" {
 int pb_tree_layout(long long capacity, long long *sum_floats, long long *min_floats, long long *counter_ints,
                    long long *leaf_offset, int *top_level)
 {
-    if (!pb_is_pow2(capacity) || capacity < 2 || capacity > (1LL << 30)) return PB_E_CAPACITY;
+    if (!pb_is_pow2(capacity) || capacity < 32 || capacity > (1LL << 30)) return PB_E_CAPACITY;
     Layout y;
     make_layout(capacity, &y);
     if (sum_floats) *sum_floats = y.n_sum;
@@ -1350,8 +1472,26 @@ int pb_tree_sample_batches(const pb_tree *t, long long n_batches, long long batc
     const long long n = n_batches * batch;
     if (n >= (1LL << 31) || (n > 0 && (!idx_out || !weight_out))) return PB_E_ARG;
     if (n == 0) return PB_OK;
-    // small batches: one descent chain per warp (latency); large ones: 32 samples per warp round (throughput)
-    const int R = n <= 16384 ? 1 : 8;
+    if (n > 16384 && v.L >= 10) {
+        // throughput mode: a thread per sample over a shared-memory heap of the top S levels (S = the deepest stored
+        // level <= 14)
+        int S = v.TL;
+        while (S + 5 <= v.L && S + 5 <= 14) S += 5;
+        const size_t smem = sizeof(float) * (2ull << S);
+        static PbPerDeviceOnce attr_set;
+        if (!attr_set.done()) {
+            cudaError_t e = cudaFuncSetAttribute(tree_sample_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(sizeof(float) * (2ull << 14)));
+            if (e != cudaSuccess) return (int)e;
+            attr_set.mark();
+        }
+        const int per_sm = smem > 100 * 1024 ? 1 : 2;
+        PB_LAUNCH(tree_sample_thread_kernel, persistent_grid(n, ST_THREADS, per_sm), ST_THREADS, smem, stream, v, n, batch, u,
+                  mode, beta, idx_out, weight_out, mass_out, S);
+        return PB_OK;
+    }
+    // one learner batch: one 8-lane descent chain per group, 4 samples per warp (latency)
+    const int R = 1;
     const int sgrid = persistent_grid(n, 8 * 4 * R, 6);
     PB_LAUNCH(tree_sample_kernel, sgrid, 256, 0, stream, v, n, batch, u, mode, beta, idx_out, weight_out, mass_out, R);
     return PB_OK;

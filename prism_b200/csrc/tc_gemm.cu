@@ -119,7 +119,9 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint
 struct TcParams {
     float *C;
     const float *bias;
-    float *ws;                     // stream-K partial tiles [2 * grid][128][BN] (two per CTA at most)
+    float *ws;                     // partial tiles [3 * grid][128][BN]: per CTA its first cut tile, its last cut tile, and
+                                   // the running sum of a whole tile accumulated in chunks (kc)
+    int kc;                        // longest accumulation chain in TMEM, in K blocks (0 = unlimited), see SegIter
     long long c_bs, bias_bs;
     int ldc;
     int M, N;
@@ -145,7 +147,17 @@ struct TcParams {
 // boundaries; a segment covering all of a tile's K blocks is finished by the epilogue directly, any other
 // segment leaves a raw partial tile in the workspace (slot 2c for the CTA's first segment, 2c + 1 for its
 // last -- the segments in between are whole tiles) and tc_streamk_fixup_kernel sums the cut tiles.
-struct Seg { int b, tm, tn, kb0, kb1, slot; bool whole; };
+//
+// Accumulation chains.  The tensor core adds into its fp32 accumulator with truncation, not round-to-nearest: every
+// MMA loses ~half an ulp of the accumulator in the same direction, so a chain of n MMAs drifts by ~n * 3e-8
+// relative (measured: -4.2e-5 of the result per 2048 floats of K on same-signed products) -- 1.4e-4 for the K = 32768
+// weight gradients of configs[4] against the fp32 CPU oracle (tests/test_gpu_config_shapes.py).  g.kc > 0 caps a chain at kc K blocks: a segment is
+// issued as CHUNKS of <= kc blocks, each into a fresh TMEM accumulator (the two accumulators alternate, so the tensor
+// pipe never waits), and the epilogue warps add the chunks in round-to-nearest fp32 -- the running sum lives in the
+// CTA's own workspace slot (L2-resident, read and written by the same thread, fixed order: deterministic).
+constexpr int SLOTS_PER_CTA = 3;
+
+struct Seg { int b, tm, tn, kb0, kb1, slot; bool whole, first, last; };
 
 struct SegIter {
     long long pos, end, start;
@@ -156,18 +168,28 @@ struct SegIter {
         end = min(g.work, pos + g.per_cta);
         kb_total = g.kblocks * g.kbatches;
     }
+    // one CHUNK per call: [kb0, kb1) of tile (b, tm, tn); first / last chunk of its segment
     __device__ __forceinline__ bool next(const TcParams &g, Seg &w)
     {
         if (pos >= end) return false;
         const long long t = pos / kb_total;
-        w.kb0 = (int)(pos - t * kb_total);
-        w.kb1 = (int)min((long long)kb_total, w.kb0 + (end - pos));
-        w.whole = (w.kb0 == 0 && w.kb1 == kb_total);
-        w.slot = 2 * (int)blockIdx.x + (pos == start ? 0 : 1);
+        const long long t0 = t * kb_total;
+        const long long s0 = max(start, t0), s1 = min(end, t0 + kb_total);      // the segment of this tile
+        w.whole = (s0 == t0 && s1 == t0 + kb_total);
+        long long c1 = s1;
+        if (g.kc > 0 && s1 - s0 > g.kc) {
+            const long long n_chunks = (s1 - s0 + g.kc - 1) / g.kc, len = (s1 - s0 + n_chunks - 1) / n_chunks;
+            c1 = min(s1, s0 + ((pos - s0) / len + 1) * len);
+        }
+        w.first = (pos == s0);
+        w.last = (c1 == s1);
+        w.kb0 = (int)(pos - t0);
+        w.kb1 = (int)(c1 - t0);
+        w.slot = SLOTS_PER_CTA * (int)blockIdx.x + (w.whole ? 2 : (s0 == start ? 0 : 1));
         int u = (int)t;
         w.tn = u % g.tiles_n; u /= g.tiles_n;
         w.tm = u % g.tiles_m; w.b = u / g.tiles_m;
-        pos += w.kb1 - w.kb0;
+        pos = c1;
         return true;
     }
 };
@@ -358,12 +380,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         Seg w;
         for (; segs.next(g, w); ++ui) {
             const int acc = ui % ACC;
-            const bool partial = !w.whole;
+            const bool partial = !w.whole;                            // the segment's result goes to the workspace
+            const bool fin = w.last;                                  // this chunk completes its segment
             const int row0 = w.tm * BM + q * 32, row = row0 + lane, n0 = w.tn * BN;
             // the tile's bias row goes to shared memory while the MMAs are still running (named barriers among the
             // four epilogue warps: everyone is done with the previous tile's row / the new row is published)
             float *bias_t = bias_s;
-            const bool has_bias = g.bias && !partial;
+            const bool has_bias = g.bias && !partial && fin;
             if (g.bias) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (has_bias) {
@@ -374,8 +397,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             mbar_wait(&bar_acc_full[acc], (ui / ACC) & 1);
             tc_fence_after();
-            const bool relu = g.act == 1 && !partial;
-            const bool use_mul = g.mul && !partial;
+            const bool relu = g.act == 1 && !partial && fin;
+            const bool use_mul = g.mul && !partial && fin;
             float *crow = g.C + (size_t)w.b * g.c_bs + (size_t)row * g.ldc;
             float4 *prow = reinterpret_cast<float4 *>(g.ws + ((size_t)w.slot * BM + q * 32 + lane) * BN);
             // multiplier tile of one chunk, COALESCED (lane l: 16-byte chunk (l & 7) of rows 4i + (l >> 3)); requested one
@@ -417,7 +440,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                              : "r"(taddr) : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (partial) {
+                if (!w.first) {
+                    // running sum of the segment's earlier chunks (this thread's own stores), round-to-nearest adds
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 sacc = prow[(cc * 32 + j) >> 2];
+                        r[j] = __float_as_uint(__uint_as_float(r[j]) + sacc.x);
+                        r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + sacc.y);
+                        r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + sacc.z);
+                        r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + sacc.w);
+                    }
+                }
+                if (partial || !fin) {
                     // raw partial tile, dense [128][BN] in the workspace: every lane writes 128 contiguous bytes
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
@@ -526,7 +560,7 @@ __global__ void __launch_bounds__(256) tc_streamk_fixup_kernel(TcParams g)
     const int bn4 = g.bn >> 2;
     const float *bias = g.bias ? g.bias + (size_t)b * g.bias_bs : nullptr;
     const bool cvec = (g.ldc % 4 == 0) && (g.c_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
-    const int first_slot = 2 * c_first + ((long long)c_first * g.per_cta < w0 ? 1 : 0);
+    const int first_slot = SLOTS_PER_CTA * c_first + ((long long)c_first * g.per_cta < w0 ? 1 : 0);
     for (int i = threadIdx.x; i < FIX_ROWS * bn4; i += blockDim.x) {
         const int r = blockIdx.y * FIX_ROWS + i / bn4, c = (i % bn4) << 2;
         const int row = tm * BM + r, col = tn * g.bn + c;
@@ -535,7 +569,7 @@ __global__ void __launch_bounds__(256) tc_streamk_fixup_kernel(TcParams g)
         float4 a = *reinterpret_cast<const float4 *>(g.ws + first_slot * slot_stride + off);
 #pragma unroll 4
         for (int cta = c_first + 1; cta <= c_last; ++cta) {          // every later CTA reaches this tile as its first segment
-            const float4 v = *reinterpret_cast<const float4 *>(g.ws + (size_t)(2 * cta) * slot_stride + off);
+            const float4 v = *reinterpret_cast<const float4 *>(g.ws + (size_t)(SLOTS_PER_CTA * cta) * slot_stride + off);
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
         float o[4] = {a.x, a.y, a.z, a.w};
@@ -654,6 +688,8 @@ int pick_bk(int bn, int K)
     return (bn == 256 && K >= 256) ? 16 : 32;    // 4 x 48 KB stages instead of 2 x 96 KB once the K loop is long
 }
 
+constexpr int TC_CHAIN_FLOATS = 1024;
+
 // modelled cost (SM clocks) of one K block and one epilogue at tile width bn: the MMA time and the shared-memory
 // traffic (12 operand reads + the split pass) whichever is larger -- see DESIGN.md section 4
 double kb_clocks(int bn)                       // per 32 floats of K
@@ -717,7 +753,7 @@ int pb_tc_gemm(int batch, int kbatches, int M, int N, int K,
         if (dp < best) { best = dp; best_bn = bn; best_sk = false; }
         const double work = (double)tiles * kb32;
         const double ctas = work / 4 < sms ? (work + 3) / 4 : sms;
-        const bool ws_ok = workspace && 2 * (long long)ctas * BM * bn <= workspace_floats;
+        const bool ws_ok = workspace && SLOTS_PER_CTA * (long long)ctas * BM * bn <= workspace_floats;
         const double sk = work / ctas * kb_clocks(bn) + (tiles / ctas + 1.0) * t_epi + 2.0 * bn * BM * 4 / 48.0 + 14000.0;
         if (ws_ok && sk < best) { best = sk; best_bn = bn; best_sk = true; }
     }
@@ -739,6 +775,10 @@ int pb_tc_gemm(int batch, int kbatches, int M, int N, int K,
         g.per_cta = ((tiles + grid - 1) / grid) * kb_total;
     }
     grid = (g.work + g.per_cta - 1) / g.per_cta;
+    // accumulation chains of at most ~1024 floats of K once a tile's K loop is twice that (see SegIter)
+    if ((long long)kb_total * bk >= 2 * TC_CHAIN_FLOATS && workspace &&
+        SLOTS_PER_CTA * grid * BM * best_bn <= workspace_floats)
+        g.kc = TC_CHAIN_FLOATS / bk;
 
     CUtensorMap ta, tb;
     const long long nb = kbatches > 1 ? kbatches : batch;

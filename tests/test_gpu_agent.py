@@ -353,6 +353,32 @@ def test_tc_gemm_matches_fp64(batch, kbatches, M, N, K, a_major, b_major, act, s
     assert rel_err(got.numpy(), ref.numpy()) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K,a_major,b_major", [
+    (512, 3136, 32768, 1, 1),                # configs[4] weight gradient: stream-K segments, each several chunks
+    (256, 256, 16384, 1, 1),                 # 4 tiles on 148 SMs: stream-K ranges shorter than a chunk and longer
+    (4736, 256, 8192, 0, 0),                 # 74 whole tiles per CTA-wave: whole tiles accumulated in chunks (slot 2)
+])
+def test_tc_gemm_long_k_chains_do_not_drift(M, N, K, a_major, b_major):
+    """The tensor core accumulates with truncation: one chain of K / 8 * 3 MMAs over same-signed products drifts by
+    ~7e-4 at K = 32768 (the configs[4] weight gradient: dW = dZ^T X over 32768 rows) -- measured -4.2e-5 per 2048 floats
+    of K.  pb_tc_gemm caps a chain at 1024 floats of K and adds the chunks in round-to-nearest fp32 (csrc/tc_gemm.cu,
+    SegIter): 3e-5 on operands whose products all have the same sign, the worst case for a truncating adder (mixed
+    signs, as in the layers' real operands, sit below the 2e-5 of the short-K tests)."""
+    from prism_b200.agents import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn((1, K, M) if a_major else (1, M, K), generator=g).abs_()
+    b = torch.randn((1, K, N) if b_major else (1, N, K), generator=g).abs_() / K
+    out = torch.full((1, M, N), float("nan"), device=DEV)
+    ops.tc_gemm(out, a.to(DEV), a_major, M if a_major else K, M * K, b.to(DEV), b_major, N if b_major else K, N * K, 1, M, N, K)
+    torch.cuda.synchronize()
+    al = (a.transpose(1, 2) if a_major else a).double()
+    bl = (b.transpose(1, 2) if b_major else b).double()
+    ref = torch.bmm(al, bl.transpose(1, 2))
+    err = (out.cpu().double() - ref) / ref.abs().max()
+    print("long-K chain: max |err| %.2e, mean signed err %.2e" % (float(err.abs().max()), float(err.mean())))
+    assert float(err.abs().max()) < 3e-5
+
+
 @pytest.mark.parametrize("M,N,K,rows", [(2048, 1024, 64, 64), (640, 328, 64, 10), (384, 18, 512, 384)])
 def test_tc_gemm_fused_multiplier_and_unaligned_output(M, N, K, rows):
     """Epilogue fusion of iqn_model.py:70-71: out = relu(A B^T + bias) * x[row % rows] (x broadcast over the
@@ -826,16 +852,26 @@ def test_grouped_layer_norm_matches_fp64(K, B, F_, shared):
 def test_small_layer_norm_goes_through_the_fused_kernel():
     from prism_b200.agents import ops
     ln = torch.nn.LayerNorm(256).to(DEV)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.5, 0.5)
     x = torch.randn(64, 256, device=DEV, requires_grad=True)
+    # a generic upstream gradient: sum(y^2) would make dx the O(eps) residual of an exact cancellation (dy = 2 y is
+    # collinear with xhat), which no two fp32 implementations agree on
+    gy = torch.randn(64, 256, device=DEV)
     ops.route_counts(reset=True)
     y = ops.layer_norm(x, ln)
     assert ops.route_counts() == {"ln:fused": 1}
-    y.square().sum().backward()
+    y.backward(gy)
+    got_w, got_b = ln.weight.grad.clone(), ln.bias.grad.clone()
+    ln.weight.grad = ln.bias.grad = None
     xr = x.detach().clone().requires_grad_(True)
     yr = ln(xr)
-    yr.square().sum().backward()
+    yr.backward(gy)
     assert rel_err(y.detach().cpu().numpy(), yr.detach().cpu().numpy()) < 1e-5
     assert rel_err(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 1e-4
+    assert rel_err(got_w.cpu().numpy(), ln.weight.grad.cpu().numpy()) < 1e-4
+    assert rel_err(got_b.cpu().numpy(), ln.bias.grad.cpu().numpy()) < 1e-4
 
 
 def test_device_quantile_draws():
