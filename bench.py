@@ -346,10 +346,12 @@ def sharded_per_microbench(step, rank, world, device, torch, dist, hbm_gbs):
 
     def one():
         if peer is not None:
-            peer.state_allgather(tree.state)
+            # every rank puts its 64-byte state to every rank; the sampling kernel itself waits for the puts
+            peer.state_put(tree.state)
+            tree.sample_global_peer(peer, Bg, None, idx_out=idx, weight_out=w, stratum_out=stratum)
         else:
             dist.all_gather_into_tensor(all_state.view(-1), tree.state)
-        tree.sample_global(world, rank, all_state, Bg, None, idx_out=idx, weight_out=w, stratum_out=stratum)
+            tree.sample_global(world, rank, all_state, Bg, None, idx_out=idx, weight_out=w, stratum_out=stratum)
         tree.update_priority(idx[:pad], prio, sorted=True)
     reps = 20
     side = torch.cuda.Stream()
@@ -383,7 +385,8 @@ def sharded_per_microbench(step, rank, world, device, torch, dist, hbm_gbs):
             "transitions_per_s": round(Bg / sec, 1), "algorithmic_bytes": int(nbytes),
             "achieved_gbs": round(nbytes / sec / 1e9, 2), "frac_of_one_gpu_hbm": round(nbytes / sec / 1e9 / hbm_gbs, 5),
             "exchange": "peer" if peer is not None else "nccl",
-            "note": "latency-bound: one cross-GPU handshake + 1 sampling launch + 1 update launch per iteration"}
+            "note": "latency-bound: one cross-GPU state exchange (put + in-kernel wait) + 1 sampling launch + 2 update "
+                    "launches per iteration"}
 
 
 def ncu_traffic(kernel_substr):

@@ -95,7 +95,7 @@ typedef struct pb_tree {
     float        *sum;       /* compact sum store, pb_tree_layout() floats (leaves last) */
     float        *min;       /* compact min store, pb_tree_layout() floats (no leaf level) */
     int          *owner;     /* reserved, may be NULL (unsorted updates dedup on the leaf slots themselves) */
-    int          *counters;  /* pb_tree_layout() ints, all 0 between calls (arrival counters of the one-launch update) */
+    int          *counters;  /* pb_tree_layout() ints of reserved scratch, all 0 (no kernel uses a side array any more) */
     pb_per_state *state;
     long long     capacity;  /* power of two */
     long long     size;      /* addressable slots N <= capacity */
@@ -107,12 +107,17 @@ typedef struct pb_tree {
 } pb_tree;
 
 /* HOST: sizes of the compact stores for a power-of-two capacity (any output may be NULL): floats of the sum store,
- * floats of the min store, ints of the arrival counters, float offset of leaf 0 inside the sum store, and TL. */
+ * floats of the min store, ints of the reserved scratch, float offset of leaf 0 inside the sum store, and TL. */
 int pb_tree_layout(long long capacity, long long *sum_floats, long long *min_floats, long long *counter_ints,
                    long long *leaf_offset, int *top_level);
 
 /* zero the trees (sum 0, min +inf), counters = 0, state = {len 0, max_priority 1} */
 int pb_tree_init(const pb_tree *t, void *stream);
+
+/* HOST, synchronous, measurement runs only (profiles/per_phases.py): copies the phase marks of the priority-store kernels
+ * (%globaltimer ns per slot, 0 = not reached; slot numbering in csrc/per_tree.cu) into out[0 .. n_out), clears them and
+ * switches marking on (enable != 0) or off.  Marking is off by default and costs one cached load per mark when off. */
+int pb_tree_trace(int enable, unsigned long long *out, int n_out);
 
 /* the full level-ordered arrays a pointer-walking tree would hold (2*capacity floats each, node i has children 2i and
  * 2i+1, leaves at [capacity, 2*capacity); either may be NULL): parity tests and checkpoints, not the hot path */
@@ -446,10 +451,12 @@ typedef struct pb_peer_group {
     int world, rank;
     float *grad[PB_PEER_MAX];                 /* every rank's flat gradient arena (n floats)                         */
     float *reduced[PB_PEER_MAX];              /* every rank's reduced-gradient buffer (n floats; rank r fills slice r) */
-    unsigned long long *flags[PB_PEER_MAX];   /* every rank's signal pad, 2 channels x PB_PEER_MAX: [dst][ch][src] = epoch */
+    unsigned long long *flags[PB_PEER_MAX];   /* every rank's signal pad, 3 channels x PB_PEER_MAX: [dst][ch][src] = epoch */
     double *norm_parts[PB_PEER_MAX];          /* every rank's [PB_PEER_MAX] slice sums of squares                    */
-    unsigned char *state[PB_PEER_MAX];        /* every rank's gathered shard states, 2 parity slots x [PB_PEER_MAX][64] */
-    unsigned long long *epoch;                /* local barrier counters, one per channel (0 exchange, 1 state gather)  */
+    unsigned char *state[PB_PEER_MAX];        /* every rank's gathered shard states, 4 slots x [PB_PEER_MAX][64]: 0-1 the
+                                                 parity slots of pb_peer_state_allgather, 2-3 those of pb_peer_state_put */
+    unsigned long long *epoch;                /* local counters, one per channel (0 barrier, 1 gradient exchange /
+                                                 state gather, 2 state puts)                                          */
     unsigned int *status;                     /* local status word: bit ch set = a wait on channel ch timed out (may be NULL) */
     unsigned long long timeout_ns;            /* bound of every flag wait; 0 = wait forever                          */
     long long grad_stride;                    /* floats between the two halves of the double-buffered gradient arena
@@ -481,6 +488,23 @@ int pb_peer_pull_sum(const pb_peer_group *g, long long n, float *partial_scratch
 int pb_peer_adam(const pb_peer_group *g, long long n, float *param, float *exp_avg, float *exp_avg_sq,
                  const long long *step_count, float lr, float beta1, float beta2, float adam_eps, float max_grad_norm,
                  float *norm_out, float *grad_out, void *stream);
+/* Small arenas (n <= pb_peer_allreduce_adam_max_n()), ONE launch for everything after the pack: handshake on channel 1
+ * (every CTA waits on the local pad), pull + sum of every rank's gradient in rank order into registers, global norm
+ * (the CTAs of the grid meet at a counter), clip + Adam -- agent.py:73-74 on W replicas.  Advances *step_count and
+ * the channel-1 epoch (the parity of the double-buffered gradient arena); reduced[rank] receives the summed gradient.
+ * partial_scratch: 4096 floats, the last 4 zero between calls. */
+long long pb_peer_allreduce_adam_max_n(void);
+int pb_peer_allreduce_adam(const pb_peer_group *g, long long n, float *param, float *exp_avg, float *exp_avg_sq,
+                           long long *step_count, float lr, float beta1, float beta2, float adam_eps, float max_grad_norm,
+                           float *partial_scratch, float *norm_out, void *stream);
+/* Non-blocking half of the shard-state exchange (channel 2): this rank's 64-byte state block goes into slot
+ * 2 + (count & 1) of every rank's state area and this rank's flag is raised there.  The matching wait is inside
+ * pb_tree_sample_global_peer.  The state area holds 4 slots of PB_PEER_MAX x 64 bytes (0-1: pb_peer_state_allgather). */
+int pb_peer_state_put(const pb_peer_group *g, const void *state64, void *stream);
+/* pb_tree_sample_global on the states of the latest pb_peer_state_put exchange: every CTA first waits (bounded by
+ * g->timeout_ns; bit 2 of *g->status on a timeout) until every rank's put has landed in the local slot. */
+int pb_tree_sample_global_peer(const pb_tree *t, const pb_peer_group *g, long long n_global, const double *u, float beta,
+                               long long *idx_out, float *weight_out, long long *stratum_out, void *stream);
 
 /* LayerNorm over the last dimension of a (rows x F) fp32 matrix, forward and backward (csrc/ln.cu), for the
  * (T*B)-row IQN activations (nn.LayerNorm in ffnn_model.py:17-18, iqn_model.py:42-46).  F % 4 == 0, F <= 4096,

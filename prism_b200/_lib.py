@@ -86,6 +86,7 @@ SIGNATURES = {
                        C.POINTER(C.c_longlong), C.POINTER(C.c_int)],
     "pb_tree_init": [_TREE, _P],
     "pb_tree_export": [_TREE, _P, _P, _P],
+    "pb_tree_trace": [_I, _P, _I],
     "pb_tree_sample_batches": [_TREE, _LL, _LL, _P, _I, _F, _P, _P, _P, _P],
     "pb_tree_build": [_TREE, _P, _LL, _P],
     "pb_tree_stats": [_TREE, _P],
@@ -129,6 +130,10 @@ SIGNATURES = {
     "pb_peer_reduce_scatter": [_PEER, _LL, _P, _P, _P],
     "pb_peer_pull_sum": [_PEER, _LL, _P, _P, C.POINTER(C.c_int), _P],
     "pb_peer_adam": [_PEER, _LL, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
+    "pb_peer_allreduce_adam_max_n": [],
+    "pb_peer_allreduce_adam": [_PEER, _LL, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
+    "pb_peer_state_put": [_PEER, _P, _P],
+    "pb_tree_sample_global_peer": [_TREE, _PEER, _LL, _P, _F, _P, _P, _P, _P],
     "pb_layer_norm_supported": [_LL, _I],
     "pb_layer_norm_bwd_blocks": [_LL, _I],
     "pb_layer_norm_fwd": [_LL, _I, _F, _P, _P, _P, _P, _P, _P, _P],
@@ -161,7 +166,8 @@ SIGNATURES = {
     "pb_wire_pack_numbers": [_P, _I, _LL, _P, _LL, _P],
     "pb_wire_index_timesteps": [_P, _LL, _LL, _P, _P],
 }
-_RESTYPES = {"pb_error_string": C.c_char_p, "pb_launch_count": C.c_longlong, "pb_peer_slice": C.c_longlong}
+_RESTYPES = {"pb_error_string": C.c_char_p, "pb_launch_count": C.c_longlong, "pb_peer_slice": C.c_longlong,
+             "pb_peer_allreduce_adam_max_n": C.c_longlong}
 
 PB_E_POOL = -4
 ABI_VERSION = 2

@@ -18,6 +18,25 @@ extern std::atomic<long long> g_pb_launches;
         if (pb_e_ != cudaSuccess) return (int)pb_e_;                                        \
     } while (0)
 
+// Same, as a PROGRAMMATIC DEPENDENT LAUNCH: the kernel may be scheduled while its predecessor on the stream (or the
+// graph branch it is captured on) is still running; it must call pb::pdl_wait() before touching anything the
+// predecessor wrote.  Chains of short dependent kernels (the priority store's sample -> mark -> lines -> rebuild) save
+// the launch latency at every boundary.  PB_NO_PDL=1 launches them the ordinary way.
+bool pb_pdl_enabled();
+#define PB_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                               \
+    do {                                                                                    \
+        cudaLaunchConfig_t pb_cfg_ = {};                                                    \
+        pb_cfg_.gridDim = dim3(grid); pb_cfg_.blockDim = dim3(block);                       \
+        pb_cfg_.dynamicSmemBytes = (smem); pb_cfg_.stream = (cudaStream_t)(stream);         \
+        cudaLaunchAttribute pb_at_[1];                                                      \
+        pb_at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                  \
+        pb_at_[0].val.programmaticStreamSerializationAllowed = 1;                           \
+        pb_cfg_.attrs = pb_at_; pb_cfg_.numAttrs = pb_pdl_enabled() ? 1 : 0;                \
+        cudaError_t pb_e_ = cudaLaunchKernelEx(&pb_cfg_, kernel, __VA_ARGS__);              \
+        g_pb_launches.fetch_add(1, std::memory_order_relaxed);                              \
+        if (pb_e_ != cudaSuccess) return (int)pb_e_;                                        \
+    } while (0)
+
 static inline int pb_ilog2(long long v) { int l = 0; while ((1LL << l) < v) ++l; return l; }
 static inline bool pb_is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
 
@@ -37,6 +56,11 @@ namespace pb {
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// programmatic dependent launch (PB_LAUNCH_PDL): wait until the preceding grid has completed and its writes are
+// visible / allow the next grid to be scheduled.  Both are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // streaming 128-bit accesses that do not pollute L1
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)

@@ -1,5 +1,6 @@
 // lib.cu -- library-level entry points of libprism_b200.so
 #include "common.cuh"
+#include <stdlib.h>
 
 std::atomic<long long> g_pb_launches{0};
 
@@ -14,6 +15,12 @@ int pb_sm_count()
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
     cached[dev].store(n, std::memory_order_relaxed);
     return n;
+}
+
+bool pb_pdl_enabled()
+{
+    static const bool on = [] { const char *e = getenv("PB_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
 }
 
 namespace {

@@ -52,6 +52,24 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return t;
 }
 
+// Poll a flag in (local) peer-mapped memory until it reaches e: relaxed volatile loads (L2 round trips) in the loop,
+// ONE acquire fence at system scope when the value is there -- an acquire load per iteration costs a system-scope
+// fence each time and delays the detection by as much.  Bounded by timeout_ns (0 = forever); false on a timeout.
+__device__ __forceinline__ bool wait_flag_sys(const unsigned long long *p, unsigned long long e, unsigned long long timeout_ns)
+{
+    const volatile unsigned long long *vp = p;
+    bool ok = true;
+    if (*vp < e) {
+        const unsigned long long t0 = global_timer_ns();
+        unsigned spins = 0;
+        while (*vp < e) {
+            if ((++spins & 1023u) == 0 && timeout_ns && global_timer_ns() - t0 > timeout_ns) { ok = false; break; }
+        }
+    }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    return ok;
+}
+
 // one warp: lane i signals rank i and waits for rank i.  Two independent CHANNELS (own flags, own epoch): calls on
 // one channel must be issued in the same order by every rank, but they may interleave with the other channel.
 // The wait is BOUNDED: a rank that does not show up within g.timeout_ns (dead process, missed launch) makes the
@@ -67,16 +85,7 @@ __device__ __forceinline__ void epoch_handshake(const pb_peer_group &g, int ch)
     if (lane < g.world) {
         st_release_sys(g.flags[lane] + ch * PB_PEER_MAX + g.rank, e);
         const unsigned long long *mine = g.flags[g.rank] + ch * PB_PEER_MAX + lane;
-        if (ld_acquire_sys(mine) < e) {
-            const unsigned long long t0 = global_timer_ns();
-            unsigned spins = 0;
-            while (ld_acquire_sys(mine) < e) {
-                if ((++spins & 1023u) == 0 && g.timeout_ns && global_timer_ns() - t0 > g.timeout_ns) {
-                    if (g.status) atomicOr(g.status, 1u << ch);
-                    break;
-                }
-            }
-        }
+        if (!wait_flag_sys(mine, e, g.timeout_ns) && g.status) atomicOr(g.status, 1u << ch);
     }
     __syncwarp();
     if (lane == 0) *epoch = e;
@@ -232,6 +241,163 @@ __global__ void __launch_bounds__(256) peer_adam_kernel(pb_peer_group g, long lo
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small arenas, ONE kernel for the whole data-parallel optimizer step (after pack): handshake -> pull + sum ->
+// global norm -> clip + Adam.  Every CTA waits on the local signal pad itself (no separate barrier launch), pulls its
+// elements of every rank's gradient with 128-bit loads and adds them in rank order INTO REGISTERS, publishes its
+// sum of squares, meets the other CTAs of this grid at a counter (all CTAs are co-resident: grid <= 4 per SM), and
+// applies clip + Adam to the elements it still holds -- the summed gradient is never re-read.  Same grid and the
+// same order of additions on every rank: the replicas stay bit-identical.
+// Channel 1 carries the handshake (its completed count is the parity of the double-buffered gradient arena).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FA_THREADS = 256;
+constexpr int FA_U = 8;                                               // 128-bit elements per thread held in registers
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(FA_THREADS) peer_allreduce_adam_kernel(pb_peer_group g, long long n,
+                                                                         float *__restrict__ param,
+                                                                         float *__restrict__ exp_avg,
+                                                                         float *__restrict__ exp_avg_sq,
+                                                                         long long *__restrict__ step_count, float lr,
+                                                                         float beta1, float beta2, float adam_eps,
+                                                                         float max_grad_norm, float *__restrict__ partials,
+                                                                         unsigned int *__restrict__ counters,
+                                                                         float *__restrict__ norm_out)
+{
+    __shared__ double red[FA_THREADS / 32];
+    __shared__ float s_coef;
+    __shared__ unsigned s_last;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long e = g.epoch[1] + 1;                      // this exchange (epoch[1] advances at the very end)
+    const long long step_now = *step_count + 1;                       // likewise
+    // ---- handshake: CTA 0 tells every rank "my gradient is packed"; every CTA waits for all ranks on the local pad
+    if (threadIdx.x < 32) {
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            if (lane < g.world) st_release_sys(g.flags[lane] + 1 * PB_PEER_MAX + g.rank, e);
+        }
+        if (lane < g.world) {
+            const unsigned long long *mine = g.flags[g.rank] + 1 * PB_PEER_MAX + lane;
+            if (!wait_flag_sys(mine, e, g.timeout_ns) && g.status) atomicOr(g.status, 1u << 1);
+        }
+    }
+    __syncthreads();
+    // ---- pull + sum in rank order, kept in registers
+    const long long n4 = n >> 2;
+    const long long po = (long long)((e - 1) & 1ull) * g.grad_stride;  // the half packed for this exchange
+    const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 sum[FA_U];
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < FA_U; ++k) {
+        const long long i = i0 + k * stride;
+        sum[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n4) {
+            float4 s4 = ld_peer_f4(g.grad[0] + po + (i << 2));
+            for (int p = 1; p < g.world; ++p) {
+                const float4 v = ld_peer_f4(g.grad[p] + po + (i << 2));
+                s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+            }
+            sum[k] = s4;
+            acc += (double)(s4.x * s4.x + s4.y * s4.y) + (double)(s4.z * s4.z + s4.w * s4.w);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < FA_THREADS / 32; ++k) t += red[k];
+        partials[blockIdx.x] = (float)t;
+        __threadfence();
+        atomicAdd(&counters[0], 1u);
+        // ---- meet the other CTAs of this grid (all resident)
+        while (ld_acquire_gpu_u32(&counters[0]) < gridDim.x) { }
+    }
+    __syncthreads();
+    // ---- global norm: every CTA adds the partials in the same order
+    double a2 = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) a2 += (double)__ldcg(partials + k);
+    a2 = warp_sum(a2);
+    __syncthreads();                                                  // red[] is reused
+    if (lane == 0) red[threadIdx.x >> 5] = a2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < FA_THREADS / 32; ++k) t += red[k];
+        const float total_norm = (float)sqrt(t);
+        float coef = max_grad_norm / (total_norm + 1e-6f);            // clip_grad_norm_
+        coef = coef > 1.0f ? 1.0f : coef;
+        if (!(max_grad_norm > 0.0f)) coef = 1.0f;
+        s_coef = coef;
+        if (blockIdx.x == 0 && norm_out) { norm_out[0] = total_norm; norm_out[1] = coef; }
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    const double step = (double)step_now;
+    const float bc1 = (float)(1.0 - pow((double)beta1, step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
+    const float step_size = lr / bc1;
+    auto upd = [&](float &p, float gg, float &m, float &v) {          // same arithmetic as adam_clip_kernel
+        gg *= coef;
+        m = m + (gg - m) * (1.0f - beta1);
+        v = v * beta2 + (1.0f - beta2) * gg * gg;
+        const float denom = sqrtf(v) / bc2_sqrt + adam_eps;
+        p = p - step_size * (m / denom);
+    };
+    float4 *p4 = reinterpret_cast<float4 *>(param), *m4 = reinterpret_cast<float4 *>(exp_avg),
+           *v4 = reinterpret_cast<float4 *>(exp_avg_sq), *r4 = reinterpret_cast<float4 *>(g.reduced[g.rank]);
+#pragma unroll
+    for (int k = 0; k < FA_U; ++k) {
+        const long long i = i0 + k * stride;
+        if (i < n4) {
+            float4 p = p4[i], m = m4[i], v = v4[i];
+            const float4 gr = sum[k];
+            upd(p.x, gr.x, m.x, v.x); upd(p.y, gr.y, m.y, v.y); upd(p.z, gr.z, m.z, v.z); upd(p.w, gr.w, m.w, v.w);
+            p4[i] = p; m4[i] = m; v4[i] = v;
+            r4[i] = gr;                                               // the summed gradient (diagnostics, tests)
+        }
+    }
+    // ---- the last CTA out closes the exchange: counters back to zero, epoch and step count advanced
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&counters[1], 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        counters[0] = 0u; counters[1] = 0u;
+        g.epoch[1] = e;
+        *step_count = step_now;
+    }
+}
+
+// Non-blocking half of the shard-state exchange (channel 2): store this rank's 64-byte state block into every rank's
+// slot (parity of the put count) and raise this rank's flag there.  Nobody waits here: the consumer -- the global
+// sampling kernel (pb_tree_sample_global_peer) -- waits on its local pad, so the exchange hides behind whatever runs
+// between the priority write-back and the next batch's sampling (the backward pass).
+__global__ void __launch_bounds__(32) peer_state_put_kernel(pb_peer_group g, const unsigned int *__restrict__ state)
+{
+    const int lane = threadIdx.x;
+    const unsigned long long e = g.epoch[2] + 1;
+    const size_t slot_words = (size_t)(2 + (e & 1)) * PB_PEER_MAX * 16;
+    if (lane < 16) {
+        const unsigned int v = state[lane];
+        for (int p = 0; p < g.world; ++p) reinterpret_cast<unsigned int *>(g.state[p])[slot_words + g.rank * 16 + lane] = v;
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane < g.world) st_release_sys(g.flags[lane] + 2 * PB_PEER_MAX + g.rank, e);
+    __syncwarp();
+    if (lane == 0) g.epoch[2] = e;
+}
+
 int check_group(const pb_peer_group *g)
 {
     if (!g || g->world < 1 || g->world > PB_PEER_MAX || g->rank < 0 || g->rank >= g->world || !g->epoch) return PB_E_ARG;
@@ -267,6 +433,8 @@ int pb_peer_preload(void)
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_reduce_scatter_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_adam_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_pull_sum_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_allreduce_adam_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_state_put_kernel);
     return e == cudaSuccess ? PB_OK : (int)e;
 }
 
@@ -347,6 +515,59 @@ int pb_peer_pull_sum(const pb_peer_group *g, long long n, float *partial_scratch
     if (nb < 1) nb = 1;
     PB_LAUNCH(peer_pull_sum_kernel, (unsigned)nb, RS_THREADS, 0, stream, *g, n, partial_scratch, step_count);
     if (n_partials_out_h) *n_partials_out_h = (int)nb;
+    return PB_OK;
+}
+
+// CTAs of the fused kernel that are resident at once (its grid never exceeds this: the CTAs meet at a counter)
+static int fa_max_blocks()
+{
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    int c = cached[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer_allreduce_adam_kernel, FA_THREADS, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    c = pb_sm_count() * per_sm;
+    cached[dev].store(c, std::memory_order_relaxed);
+    return c;
+}
+
+long long pb_peer_allreduce_adam_max_n(void) { return (long long)fa_max_blocks() * FA_THREADS * FA_U * 4; }
+
+int pb_peer_allreduce_adam(const pb_peer_group *g, long long n, float *param, float *exp_avg, float *exp_avg_sq,
+                           long long *step_count, float lr, float beta1, float beta2, float adam_eps, float max_grad_norm,
+                           float *partial_scratch, float *norm_out, void *stream)
+{
+    int rc = check_group(g);
+    if (rc) return rc;
+    if (n <= 0 || (n % 4) != 0 || n > pb_peer_allreduce_adam_max_n()) return PB_E_ARG;
+    if (!param || !exp_avg || !exp_avg_sq || !step_count || !partial_scratch) return PB_E_ARG;
+    if ((((uintptr_t)param) | ((uintptr_t)exp_avg) | ((uintptr_t)exp_avg_sq)) & 15) return PB_E_ARG;
+    for (int p = 0; p < g->world; ++p)
+        if (!g->grad[p]) return PB_E_ARG;
+    if (!g->reduced[g->rank]) return PB_E_ARG;
+    // one 128-bit element per thread while that fits the resident grid, then up to FA_U
+    long long nb = ((n >> 2) + FA_THREADS - 1) / FA_THREADS;
+    const long long cap = fa_max_blocks();
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+    unsigned int *counters = reinterpret_cast<unsigned int *>(partial_scratch + 4092);    // zero between calls
+    PB_LAUNCH(peer_allreduce_adam_kernel, (unsigned)nb, FA_THREADS, 0, stream, *g, n, param, exp_avg, exp_avg_sq, step_count,
+              lr, beta1, beta2, adam_eps, max_grad_norm, partial_scratch, counters, norm_out);
+    return PB_OK;
+}
+
+int pb_peer_state_put(const pb_peer_group *g, const void *state64, void *stream)
+{
+    int rc = check_group(g);
+    if (rc) return rc;
+    if (!state64) return PB_E_ARG;
+    for (int p = 0; p < g->world; ++p)
+        if (!g->state[p]) return PB_E_ARG;
+    PB_LAUNCH(peer_state_put_kernel, 1, 32, 0, stream, *g, reinterpret_cast<const unsigned int *>(state64));
     return PB_OK;
 }
 

@@ -16,16 +16,18 @@
 //    slots that were never written -- index >= len -- read as +inf on the min side).
 //    16M leaves: 64 MiB + 2 x 2.1 MiB instead of 2 x 128 MiB, i.e. the whole store fits the 126 MB L2.
 //      - sampling descends 5 levels per dependent 128-byte load: 8 lanes per sample for one learner batch (latency),
-//        a thread per sample over a shared-memory copy of the top 14 levels for many batches in flight (throughput);
-//      - a sorted priority update is ONE launch: the leader of every touched line applies its leaves, reduces the
-//        line and climbs; lines of the next stored level are finished by whichever child arrives last (arrival
-//        counters, no spinning), and the last CTA (ticket) rebuilds the top heap and the state block;
-//      - any other batch (unsorted, duplicates, K batches in flight) is three launches: a mark pass (dedup tag on the
-//        leaf slot + one bit per touched leaf line), the leaf scatter, and a sparse rebuild whose CTAs own 32768-leaf
-//        spans (lane per touched leaf line) and climb three stored levels without any cross-CTA dependency;
+//        a thread per sample over a shared-memory copy of the top 14 levels for many batches in flight (throughput:
+//        the warp fetches its 32 lines together and transposes them through shared memory);
+//      - an update is a LINE phase -- every touched 32-leaf line is patched and reduced to its node of level L-5 by one
+//        thread holding the line in registers -- followed by a streaming rebuild of the (32 x smaller) tree above
+//        level L-5, whose last CTA (ticket) rebuilds the top heap and the state block.  Sorted batches (one
+//        stratified learner batch, the ring's extends): the first entry of every line's run is its leader, 2 launches.
+//        Any other batch (unsorted, duplicates, K batches in flight): a mark pass leaves a dedup tag on every touched
+//        leaf slot, then the entry whose tag sits in a line's lowest tagged slot leads that line, 3 launches;
 //      - batches beyond cap/16 entries scatter their leaves and rebuild every line with one streaming pass over the
 //        leaf array (4.3 B per leaf of traffic, independent of the batch size);
-//      - the bulk build is that same streaming pass.
+//      - the bulk build is that same streaming pass;
+//      - the launches of one call (and the sampling launch that follows) are programmatic dependent launches.
 //  * duplicates in an update batch: last occurrence wins (sequential reference loop), resolved deterministically
 //    (adjacency when sorted; otherwise atomicMax of a NaN-tagged entry number on the leaf slot itself -- no side array).
 //  * no host sync anywhere: len / cursor / max_priority / p_sum / p_min live in a 64-byte device state block, so
@@ -47,8 +49,6 @@ struct TreeView {
     long long cap, size;
     int L, TL, P;                  // P = (L - TL) / 5 deep levels: L, L-5, .., TL+5
     long long off[MAX_DEEP];       // off[m]: float offset of level TL + 5m in the sum / min store (m >= 1)
-    long long coff[MAX_DEEP];      // coff[m]: int offset of the arrival counters of the lines at level TL + 5m (1 <= m < P)
-    unsigned *bitmap;              // one bit per leaf line (cap / 32 bits), all zero between calls: lines an update touched
     float alpha, eps32;
     double eps64;
     int weps, dp64;
@@ -84,13 +84,52 @@ __device__ __forceinline__ int atom_add_acq_rel(int *p, int v)
     return old;
 }
 
+// ---------------------------------------------------------------------------------
+// phase marks for measurement runs (pb_tree_trace; profiles/per_phases.py): slot <- the LATEST %globaltimer at which
+// any CTA passed the mark (start marks: slot <- CTA 0's own time).  Off by default: one cached load per mark.
+// ---------------------------------------------------------------------------------
+constexpr int TRACE_SLOTS = 48;
+__device__ unsigned long long g_trace[TRACE_SLOTS];
+__device__ int g_trace_on;
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+// `on` = g_trace_on read ONCE at kernel entry (TRACE_ON).  Call from one thread per CTA (or per warp).
+#define TRACE_ON() (__ldg(&g_trace_on))
+__device__ __forceinline__ void trace_max(int on, int slot)
+{
+    if (on) atomicMax(&g_trace[slot], global_ns());
+}
+__device__ __forceinline__ void trace_cta0(int on, int slot)
+{
+    if (on && blockIdx.x == 0 && threadIdx.x == 0) g_trace[slot] = global_ns();
+}
+enum {
+    TR_SAMPLE_START = 0, TR_SAMPLE_STAGED, TR_SAMPLE_END,
+    TR_CHAIN_START = 4, TR_CHAIN_REGISTERED, TR_CHAIN_LEAVES, TR_CHAIN_GROUP, TR_CHAIN_CLIMBED, TR_CHAIN_TICKET, TR_CHAIN_TOP,
+    TR_CHAIN_END,
+    TR_MARK_START = 16, TR_MARK_END, TR_LEAF_START, TR_LEAF_END, TR_SPARSE_START, TR_SPARSE_SPANS, TR_SPARSE_TICKET,
+    TR_SPARSE_TOP, TR_SPARSE_END,
+    TR_REBUILD_START = 28, TR_REBUILD_END, TR_REBUILD_TICKET, TR_REBUILD_TOP, TR_REBUILD_STATE,
+    TR_LINES_START = 36, TR_LINES_END
+};
+
+// cold paths (every reference configuration has alpha = 0.5): kept out of line so that the latency-bound update
+// kernels stay small in the instruction cache
+__device__ __noinline__ float powf_cold(float x, float a) { return powf(x, a); }
+__device__ __noinline__ double pow_cold(double x, double a) { return pow(x, a); }
+
 __device__ __forceinline__ float pow_leaf(float p, const TreeView &t)
 {
     // torch.pow(priority + eps, alpha) on an fp32 tensor; alpha == 0.5 is torch's sqrt path
     float x = __fadd_rn(p, t.eps32);
     if (t.alpha == 0.5f) return __fsqrt_rn(x);
     if (t.alpha == 1.0f) return x;
-    return powf(x, t.alpha);
+    return powf_cold(x, t.alpha);
 }
 
 __device__ __forceinline__ float default_priority(const TreeView &t)
@@ -98,7 +137,7 @@ __device__ __forceinline__ float default_priority(const TreeView &t)
     float mp = t.st->max_priority;
     if (t.dp64) {
         double x = (double)mp + t.eps64;
-        double r = (t.alpha == 0.5f) ? sqrt(x) : ((t.alpha == 1.0f) ? x : pow(x, (double)t.alpha));
+        double r = (t.alpha == 0.5f) ? __dsqrt_rn(x) : ((t.alpha == 1.0f) ? x : pow_cold(x, (double)t.alpha));
         return (float)r;
     }
     return pow_leaf(mp, t);
@@ -194,12 +233,19 @@ __device__ float tree_query_prefix(const TreeView &t, long long len)
     return ret;
 }
 
-// one warp: advance len / seq, merge max_priority, refresh p_sum / p_min
-__device__ void finalize_state(const TreeView &t, int mode, long long n_new, long long set_len)
+// one warp: advance len / seq, merge max_priority, refresh p_sum / p_min.  have_roots: the caller rebuilt the top heap and
+// hands over the roots (a full tree's query(0, len) IS the root: no load, no fence)
+__device__ void finalize_state(const TreeView &t, int mode, long long n_new, long long set_len, bool have_roots = false,
+                               float root_s = 0.0f, float root_m = 0.0f)
 {
     const long long len = len_after(t, mode, n_new, set_len);
-    const float ps = tree_query_prefix<false>(t, len);
-    const float pm = tree_query_prefix<true>(t, len);
+    float ps, pm;
+    if (have_roots && len >= t.size) { ps = root_s; pm = root_m; }
+    else {
+        if (have_roots) __threadfence();          // partial fill: the walk reads heap nodes other warps of this CTA just stored
+        ps = tree_query_prefix<false>(t, len);
+        pm = tree_query_prefix<true>(t, len);
+    }
     if (lane_id() == 0) {
         pb_per_state *s = t.st;
         if (mode == MODE_EXTEND) s->seq += n_new;
@@ -235,17 +281,27 @@ __device__ void top_rebuild(const TreeView &t, float *sm, long long len)
     const bool shared_leaves = is_min && TL == t.L;             // tiny trees: level TL is the shared leaf level
     const float *src = shared_leaves ? t.sum + (1 << TL) : heap + (1 << TL);
     const int n_lines = 1 << (TL - 5);
-    for (int line = warp; line < n_lines; line += n_warps) {
-        const int e = (line << 5) + lane;
-        float v = ldcg(src + e);
-        if (shared_leaves) v = min_of_leaf(v, e, len);
+    for (int base = warp; base < n_lines; base += 4 * n_warps) {
+        float v4[4];                                            // up to 4 lines per warp with their loads in flight
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const float o = __shfl_xor_sync(FULL, v, 1 << k);
-            v = is_min ? op_min(v, o) : op_sum(v, o);
-            if ((lane & ((2 << k) - 1)) == 0) heap[(1 << (TL - 1 - k)) + (e >> (k + 1))] = v;
+        for (int u = 0; u < 4; ++u) {
+            const int line = base + u * n_warps, e = (line << 5) + lane;
+            v4[u] = line < n_lines ? ldcg(src + e) : 0.0f;
+            if (shared_leaves && line < n_lines) v4[u] = min_of_leaf(v4[u], e, len);
         }
-        if (lane == 0) s[line] = v;                              // node `line` of level TL - 5 (already stored above)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int line = base + u * n_warps, e = (line << 5) + lane;
+            if (line >= n_lines) break;                         // warp-uniform
+            float v = v4[u];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const float o = __shfl_xor_sync(FULL, v, 1 << k);
+                v = is_min ? op_min(v, o) : op_sum(v, o);
+                if ((lane & ((2 << k) - 1)) == 0) heap[(1 << (TL - 1 - k)) + (e >> (k + 1))] = v;
+            }
+            if (lane == 0) s[line] = v;                          // node `line` of level TL - 5 (already stored above)
+        }
     }
     __syncthreads();
     if (warp == 0 && TL > 5) {
@@ -255,6 +311,7 @@ __device__ void top_rebuild(const TreeView &t, float *sm, long long len)
             v = is_min ? op_min(v, o) : op_sum(v, o);
             if (lane < n_lines && (lane & ((2 << k) - 1)) == 0) heap[(1 << (TL - 6 - k)) + (lane >> (k + 1))] = v;
         }
+        if (lane == 0) s[0] = v;                                  // the root (TL == 5: s[0] already is)
     }
 }
 
@@ -271,13 +328,15 @@ __device__ bool last_cta(const TreeView &t)
     return is_last != 0;
 }
 
-__device__ void top_and_finalize(const TreeView &t, float *sm, int mode, long long n_new, long long set_len)
+__device__ void top_and_finalize(const TreeView &t, float *sm, int mode, long long n_new, long long set_len,
+                                 int tr_top = -1, int tr_end = -1)
 {
     const long long len = len_after(t, mode, n_new, set_len);
     top_rebuild(t, sm, len);
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x < 32) finalize_state(t, mode, n_new, set_len);
+    if (tr_top >= 0 && threadIdx.x == 0) trace_max(1, tr_top);
+    if (threadIdx.x < 32) finalize_state(t, mode, n_new, set_len, true, sm[0], sm[TOP_SM_FLOATS]);
+    if (tr_end >= 0 && threadIdx.x == 0) trace_max(1, tr_end);
 }
 
 // ---------------------------------------------------------------------------------
@@ -326,11 +385,15 @@ __global__ void __launch_bounds__(RB_THREADS) tree_rebuild_kernel(TreeView t, in
                                                                   long long n_ext, int fuse_top, int mode,
                                                                   long long n_new, long long set_len)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     __shared__ float sm_top[2 * TOP_SM_FLOATS];
     __shared__ float l2s[32], l2m[32];
     const int two_levels = n_lv >= 2;
     const long long len = len_after(t, mode, n_new, set_len);
     const bool leaves = (s == t.L);
+    const int tr_on = TRACE_ON();
+    trace_cta0(tr_on, TR_REBUILD_START);
     float *src_s = sum_level(t, s);
     const float *src_m = leaves ? src_s : min_level(t, s);
     float *dst1_s = sum_level(t, s - 5), *dst1_m = min_level(t, s - 5);
@@ -413,14 +476,18 @@ __global__ void __launch_bounds__(RB_THREADS) tree_rebuild_kernel(TreeView t, in
         __syncthreads();
     }
     }
+    if (threadIdx.x == 0) trace_max(tr_on, TR_REBUILD_END);
     if (!fuse_top) return;
     if (!last_cta(t)) return;
-    top_and_finalize(t, sm_top, mode, n_new, set_len);
+    if (threadIdx.x == 0) trace_max(tr_on, TR_REBUILD_TICKET);
+    top_and_finalize(t, sm_top, mode, n_new, set_len, tr_on ? TR_REBUILD_TOP : -1, tr_on ? TR_REBUILD_STATE : -1);
 }
 
 // trees without deep levels (L <= 14): copy the leaves (identity padded) into the heap's leaf level
 __global__ void tree_fill_leaves_kernel(TreeView t, const float *leaves, long long n_leaves)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= t.cap) return;
     leaf_ptr(t)[i] = i < n_leaves ? leaves[i] : 0.0f;
@@ -429,6 +496,8 @@ __global__ void tree_fill_leaves_kernel(TreeView t, const float *leaves, long lo
 // standalone top phase (one CTA)
 __global__ void __launch_bounds__(512) tree_top_kernel(TreeView t, int mode, long long n_new, long long set_len)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     __shared__ float sm_top[2 * TOP_SM_FLOATS];
     top_and_finalize(t, sm_top, mode, n_new, set_len);
 }
@@ -443,43 +512,68 @@ __global__ void __launch_bounds__(512) tree_top_kernel(TreeView t, int mode, lon
 constexpr int LEAF_TAG = 0x7F800001;                 // first NaN pattern; TAG + j stays a positive int for j < 2^23 - 1
 constexpr long long LEAF_TAG_MAX_N = (1LL << 23) - 2;
 
-__global__ void upd_mark_kernel(TreeView t, long long n, const long long *idx, const float *val, int mode,
-                                long long *idx_out, int set_bits)
+// the batch's largest |priority| (max_priority is merged by the finalising CTA): one conditional atomic per CTA -- an
+// atomic per warp on this ONE address serialises in L2 (measured: 73 us of a 1M-entry mark pass).  Every thread calls.
+__device__ __forceinline__ void cta_batch_max(const TreeView &t, float bm)
 {
+    __shared__ float s_bm[32];
+    bm = warp_max(bm);
+    if (lane_id() == 0) s_bm[threadIdx.x >> 5] = bm;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) >> 5;
+        bm = warp_max(threadIdx.x < nw ? s_bm[threadIdx.x] : 0.0f);
+        if (threadIdx.x == 0 && bm > 0.0f && bm > __ldcg(&t.st->batch_max))
+            atomicMax(reinterpret_cast<int *>(&t.st->batch_max), __float_as_int(bm));
+    }
+}
+
+__global__ void upd_mark_kernel(TreeView t, long long n, const long long *idx, const float *val, int mode,
+                                long long *idx_out)
+{
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long seq0 = t.st->seq;
+    const int tr_on = TRACE_ON();
+    trace_cta0(tr_on, TR_MARK_START);
     float bm = 0.0f;
     if (j < n) {
         const long long i = entry_index(t, idx, j, mode, seq0);
         if (idx_out) idx_out[j] = i;
         if (i >= 0 && i < t.size) {
             atomicMax(reinterpret_cast<int *>(leaf_ptr(t) + i), LEAF_TAG + (int)j);
-            if (set_bits) atomicOr(t.bitmap + (i >> 10), 1u << ((i >> 5) & 31));      // leaf line i >> 5 is touched
             if (mode == MODE_PRIORITY) bm = fabsf(val[j]);
         }
     }
-    if (mode == MODE_PRIORITY) {
-        bm = warp_max(bm);
-        if (lane_id() == 0 && bm > 0.0f) atomicMax(reinterpret_cast<int *>(&t.st->batch_max), __float_as_int(bm));
-    }
+    if (mode == MODE_PRIORITY) cta_batch_max(t, bm);
+    if (threadIdx.x == 0) trace_max(tr_on, TR_MARK_END);
 }
 
 __global__ void upd_leaf_kernel(TreeView t, long long n, const long long *idx, const float *val, int mode,
                                 long long *idx_out)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const long long i = entry_index(t, idx, j, mode, t.st->seq);
-    if (idx_out) idx_out[j] = i;
-    if (i < 0 || i >= t.size) return;
-    if (__ldcg(reinterpret_cast<const int *>(leaf_ptr(t) + i)) != LEAF_TAG + (int)j) return;
-    const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
-    leaf_ptr(t)[i] = entry_leaf(t, val, j, mode, defp);
+    const int tr_on = TRACE_ON();
+    trace_cta0(tr_on, TR_LEAF_START);
+    if (j < n) {
+        const long long i = entry_index(t, idx, j, mode, t.st->seq);
+        if (idx_out) idx_out[j] = i;
+        if (i >= 0 && i < t.size && __ldcg(reinterpret_cast<const int *>(leaf_ptr(t) + i)) == LEAF_TAG + (int)j) {
+            const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
+            leaf_ptr(t)[i] = entry_leaf(t, val, j, mode, defp);
+        }
+    }
+    if (threadIdx.x == 0) trace_max(tr_on, TR_LEAF_END);
 }
 
 __global__ void upd_leaf_sorted_kernel(TreeView t, long long n, const long long *idx, const float *val, int mode,
                                        long long *idx_out)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long seq0 = t.st->seq;
     float bm = 0.0f;
@@ -495,106 +589,35 @@ __global__ void upd_leaf_sorted_kernel(TreeView t, long long n, const long long 
             }
         }
     }
-    if (mode == MODE_PRIORITY) {
-        bm = warp_max(bm);
-        if (lane_id() == 0 && bm > 0.0f) atomicMax(reinterpret_cast<int *>(&t.st->batch_max), __float_as_int(bm));
-    }
+    if (mode == MODE_PRIORITY) cta_batch_max(t, bm);
 }
 
 // ---------------------------------------------------------------------------------
-// sparse rebuild (the last launch of a general update, after upd_mark_kernel + upd_leaf_kernel).  A CTA owns a span of
-// 32768 leaves = 32 words of the touched-line bitmap = one line of level L-10; a warp takes 2 of those words.  For a
-// word, LANE l owns leaf line 32 w + l: if its bit is set it streams the line (8 x 128-bit loads, all in flight),
-// reduces it in registers in tree order and stores the node of level L-5; otherwise it just loads the node that is
-// there.  The warp then holds the whole line of level L-5 in its lanes: 5 shuffle levels give the node of level L-10.
-// Finally warp 0 reduces the CTA's line of level L-10 to the node of level L-15.  No cross-CTA dependency below the
-// top heap; ~130 warp instructions per bitmap word whatever its population.  The bitmap words are cleared on the
-// way.  The last CTA (ticket) rebuilds the top heap and the state block when level L-15 is (or lies above) the
-// heap's bottom level.
+// LINE PHASE of an update: every touched leaf line (32 leaves, 128 bytes) is reduced to its node of level L-5 by ONE
+// thread that holds the whole line in registers (8 x 128-bit loads in flight, tree-order sums in registers).  Nothing
+// above level L-5 is touched here: from there the tree is small (2^-5 of the leaves) and a streaming pass rebuilds it
+// whole (tree_rebuild_kernel from level L-5, top heap and state block by its last CTA) -- two short launches with no
+// dependency between CTAs instead of a climb through arrival counters (measured at 2^24 leaves, batch 4096: 15 us for
+// the one-launch climb, of which 5 us waiting on store -> load round trips, profiles/per_phases_r02.txt).
 // ---------------------------------------------------------------------------------
-constexpr int SPR_THREADS = 512;                 // 16 warps, 2 bitmap words (64 leaf lines) each
-
-__global__ void __launch_bounds__(SPR_THREADS) tree_rebuild_sparse_kernel(TreeView t, int mode, long long n_new,
-                                                                          int fuse_top)
+__device__ __forceinline__ void line_total(const float4 (&v)[8], long long base, long long len, float &vs, float &vm)
 {
-    __shared__ float sm_top[2 * TOP_SM_FLOATS];
-    const int lane = lane_id(), wic = threadIdx.x >> 5;
-    constexpr int WPW = 32 / (SPR_THREADS / 32);                 // bitmap words per warp
-    const long long len = len_after(t, mode, n_new, -1);
-    const float *leaf = leaf_ptr(t);
-    float *n1s = sum_level(t, t.L - 5), *n1m = min_level(t, t.L - 5);
-    const long long n_words = t.cap >= 1024 ? t.cap >> 10 : 1;
-    const int P = t.P;
-    for (long long span = blockIdx.x; span * 32 < n_words; span += gridDim.x) {
-        int touched_any = 0;
+    float ps[8], pm[8];
+    const bool whole = base + 32 <= len;                          // every leaf of the line is a filled slot
 #pragma unroll
-        for (int q = 0; q < WPW; ++q) {
-            const long long w = span * 32 + wic * WPW + q;
-            unsigned bits = 0;
-            if (w < n_words && lane == 0) { bits = t.bitmap[w]; if (bits) t.bitmap[w] = 0u; }
-            bits = __shfl_sync(FULL, bits, 0);
-            if (!bits) continue;                                  // warp-uniform
-            touched_any = 1;
-            const long long line = (w << 5) + lane;
-            float vs, vm;
-            if ((bits >> lane) & 1u) {
-                const float4 *src = reinterpret_cast<const float4 *>(leaf + (line << 5));
-                float4 v[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = __ldcg(src + k);
-                float ps[8], pm[8];
-                const bool whole = (line << 5) + 32 <= len;       // every leaf of the line is a filled slot
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float4 m = v[k];
-                    if (!whole) {
-                        const long long e = (line << 5) + 4 * k;
-                        m.x = min_of_leaf(m.x, e + 0, len); m.y = min_of_leaf(m.y, e + 1, len);
-                        m.z = min_of_leaf(m.z, e + 2, len); m.w = min_of_leaf(m.w, e + 3, len);
-                    }
-                    ps[k] = op_sum(op_sum(v[k].x, v[k].y), op_sum(v[k].z, v[k].w));
-                    pm[k] = op_min(op_min(m.x, m.y), op_min(m.z, m.w));
-                }
-                vs = op_sum(op_sum(op_sum(ps[0], ps[1]), op_sum(ps[2], ps[3])), op_sum(op_sum(ps[4], ps[5]), op_sum(ps[6], ps[7])));
-                vm = op_min(op_min(op_min(pm[0], pm[1]), op_min(pm[2], pm[3])), op_min(op_min(pm[4], pm[5]), op_min(pm[6], pm[7])));
-                n1s[line] = vs; n1m[line] = vm;
-            } else {
-                vs = ldcg(n1s + line); vm = ldcg(n1m + line);
-            }
-            if (P >= 2) {
-                line_reduce(vs, vm);                              // the lanes hold the word's line of level L-5
-                if (lane == 0) { sum_level(t, t.L - 10)[w] = vs; min_level(t, t.L - 10)[w] = vm; }
-            }
+    for (int k = 0; k < 8; ++k) {
+        float4 m = v[k];
+        if (!whole) {
+            const long long e = base + 4 * k;
+            m.x = min_of_leaf(m.x, e + 0, len); m.y = min_of_leaf(m.y, e + 1, len);
+            m.z = min_of_leaf(m.z, e + 2, len); m.w = min_of_leaf(m.w, e + 3, len);
         }
-        if (P >= 3) {
-            const int any = __syncthreads_or(touched_any);        // also orders the warps' level L-10 stores
-            if (any && wic == 0) {
-                float vs = ldcg(sum_level(t, t.L - 10) + (span << 5) + lane);
-                float vm = ldcg(min_level(t, t.L - 10) + (span << 5) + lane);
-                line_reduce(vs, vm);
-                if (lane == 0) { sum_level(t, t.L - 15)[span] = vs; min_level(t, t.L - 15)[span] = vm; }
-            }
-        }
+        ps[k] = op_sum(op_sum(v[k].x, v[k].y), op_sum(v[k].z, v[k].w));
+        pm[k] = op_min(op_min(m.x, m.y), op_min(m.z, m.w));
     }
-    if (!fuse_top) return;
-    if (!last_cta(t)) return;
-    top_and_finalize(t, sm_top, mode, n_new, -1);
+    vs = op_sum(op_sum(op_sum(ps[0], ps[1]), op_sum(ps[2], ps[3])), op_sum(op_sum(ps[4], ps[5]), op_sum(ps[6], ps[7])));
+    vm = op_min(op_min(op_min(pm[0], pm[1]), op_min(pm[2], pm[3])), op_min(op_min(pm[4], pm[5]), op_min(pm[6], pm[7])));
 }
-
-// ---------------------------------------------------------------------------------
-// sorted input, ONE launch: warp per batch entry (grid-stride).  Entries are grouped by the 1024-leaf SPAN they fall
-// into (one line of level L-5; 32 leaf lines).  The first entry of a span's run is its leader: it writes the run's
-// leaves (last of equal indices wins), reduces the touched leaf lines (several loads in flight) to their nodes of
-// level L-5, then -- being the only writer of that line -- reduces the span's line of level L-5 to the node of
-// level L-10.  Lines of the levels above are finished by whichever child arrives last: the first entry of a line's
-// run registers the number of touched children in the line's arrival counter (+c), every finished child subtracts
-// one (acq_rel), and the warp whose atomic brings the counter back to zero reduces the line and climbs on (the
-// counter is zero again for the next call; nobody spins).  The last CTA (ticket) rebuilds the top heap and the
-// state block.  Trees with a single deep level (P == 1) use the leaf line itself as the group.
-// ---------------------------------------------------------------------------------
-constexpr int CHAIN_THREADS = 512;
-constexpr long long CHAIN_MAX_N = 8192;      // beyond this the per-warp serial chain loses to mark + sparse rebuild
-constexpr int CHAIN_U = 4;                   // touched leaf lines in flight per leader
 
 struct RunScan { long long seq0; const long long *idx; long long n; int mode; };
 
@@ -605,143 +628,179 @@ __device__ __forceinline__ bool valid_at(const TreeView &t, const RunScan &r, lo
     return i >= 0 && i < t.size;
 }
 
-// number of distinct values of (index >> child_shift) among the run of entries starting at j whose
-// (index >> shift) equals key (warp-uniform result)
-__device__ int count_children(const TreeView &t, const RunScan &r, long long j, int shift, int child_shift,
-                              long long key)
+// Every lane of a warp wants one 128-byte line (line index `node` of the array `lvl`).  Fetched TOGETHER: 4 lines per
+// load instruction (8 lanes x 16 bytes per line -- one L1 wavefront per line instead of eight when every lane
+// streams its own line, which is what bounded the first thread-per-sample / thread-per-entry kernels), transposed
+// through 4 KB of shared memory per warp (XOR-swizzled 16-byte chunks, conflict-free both ways).  All 32 lanes call.
+__device__ __forceinline__ void warp_fetch_lines_raw(const float *__restrict__ lvl, long long node, float4 *wbuf, float4 (&q)[8])
 {
     const int lane = lane_id();
-    int c = 0;
-    for (long long base = j;; base += 32) {
-        const long long jj = base + lane;
-        long long ii = -1, ip = -1;
-        const bool ok = valid_at(t, r, jj, ii) && (ii >> shift) == key;
-        const unsigned bad = ~__ballot_sync(FULL, ok);
-        const int run = bad ? __ffs(bad) - 1 : 32;
-        bool fresh = false;
-        if (lane < run) fresh = (jj == j) || !valid_at(t, r, jj - 1, ip) || (ip >> child_shift) != (ii >> child_shift);
-        c += __popc(__ballot_sync(FULL, fresh));
-        if (run < 32) break;
+    const int g = lane >> 3, c = lane & 7;
+    float4 r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const long long ln = __shfl_sync(FULL, node, 4 * k + g);
+        r[k] = __ldcg(reinterpret_cast<const float4 *>(lvl + (ln << 5)) + c);
     }
-    return c;
+    __syncwarp();                                                 // everyone is done reading the previous fetch
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int slot = 4 * k + g;
+        wbuf[slot * 8 + (c ^ (slot & 7))] = r[k];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[k] = wbuf[lane * 8 + (k ^ (lane & 7))];
 }
 
-__global__ void __launch_bounds__(CHAIN_THREADS) upd_chain_kernel(TreeView t, long long n, const long long *idx,
-                                                                  const float *val, int mode, long long *idx_out)
+// Sorted input (one stratified learner batch, the ring's extends), thread per entry.  The first entry of every run of
+// entries that fall into the same leaf line is the line's leader: it loads the line, applies the run in entry order
+// (last of equal indices wins, like the sequential reference loop) to its registers AND to the leaf array, and stores
+// the line's node of level L-5.  No thread reads what another one wrote in this launch.  Needs P >= 1.
+constexpr int LS_THREADS = 128;
+constexpr long long SORTED_LINES_MAX_N = 1 << 20;   // thread per entry; beyond this the streaming pass over all leaves wins
+
+__global__ void __launch_bounds__(LS_THREADS) upd_lines_sorted_kernel(TreeView t, long long n, const long long *idx,
+                                                                      const float *val, int mode, long long *idx_out)
 {
-    __shared__ float sm_top[2 * TOP_SM_FLOATS];
-    const int lane = lane_id();
-    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
+    const int tr_on = TRACE_ON();
+    trace_cta0(tr_on, TR_LINES_START);
     RunScan r;
-    r.seq0 = t.st->seq; r.idx = idx; r.n = n; r.mode = mode;
+    r.seq0 = mode == MODE_EXTEND ? t.st->seq : 0; r.idx = idx; r.n = n; r.mode = mode;     // the cursor only names slots of an extend
     const long long len = len_after(t, mode, n, -1);
     const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
     float *leaf = leaf_ptr(t);
-    const int P = t.P;
-    const int gs = P >= 2 ? 10 : 5;                               // group = span of 2^gs leaves
-    for (long long j = w0; j < n; j += n_warps) {
-        long long i, ip = -1;
-        if (!valid_at(t, r, j, i)) continue;
-        const bool prev_ok = valid_at(t, r, j - 1, ip);
-        if (P == 0) {
-            // no deep level: the heap's leaf level is written directly, the top phase does the rest
-            float bm = 0.0f;
-            long long inx = -1;
-            const bool last_of_idx = !valid_at(t, r, j + 1, inx) || inx != i;
-            if (lane == 0) {
-                if (idx_out) idx_out[j] = i;
-                if (last_of_idx) leaf[i] = entry_leaf(t, val, j, mode, defp);
-                if (mode == MODE_PRIORITY) bm = fabsf(val[j]);
-                if (bm > 0.0f) atomicMax(reinterpret_cast<int *>(&t.st->batch_max), __float_as_int(bm));
-            }
-            continue;
-        }
-        const long long grp = i >> gs;
-        if (prev_ok && (ip >> gs) == grp) continue;               // the group's leader does this span
-        // ---- registration: lines of the levels above the group whose run starts at this entry.  The group's node
-        // lives at level L - gs = TL + 5 mg; the lines above are those of levels TL + 5m, m = mg .. 1.
-        const int mg = P - gs / 5;
-        for (int m = mg; m >= 1; --m) {
-            const int shift = 5 * (P - m) + 5;                    // index >> shift = line index at level TL + 5m
-            const long long pl = i >> shift;
-            if (prev_ok && (ip >> shift) == pl) break;            // not the first entry of that line (nor of any above)
-            const int c = count_children(t, r, j, shift, shift - 5, pl);
-            if (lane == 0) atomicAdd(&t.cnt[t.coff[m] + pl], c);
-        }
-        // ---- the group's run: write its leaves, 32 entries at a time; collect the touched leaf lines
-        float bm = 0.0f;
-        unsigned linebits = 0;
-        for (long long base = j;; base += 32) {
-            const long long jj = base + lane;
-            long long ii = -1, inx = -1;
-            const bool ok = valid_at(t, r, jj, ii) && (ii >> gs) == grp;
-            const unsigned bad = ~__ballot_sync(FULL, ok);
-            const int run = bad ? __ffs(bad) - 1 : 32;
-            unsigned mine = 0;
-            if (lane < run) {
-                if (idx_out) idx_out[jj] = ii;
-                if (mode == MODE_PRIORITY) bm = fmaxf(bm, fabsf(val[jj]));
-                if (!valid_at(t, r, jj + 1, inx) || inx != ii) leaf[ii] = entry_leaf(t, val, jj, mode, defp);
-                mine = 1u << ((ii >> 5) & (gs == 10 ? 31 : 0));
-            }
-            linebits |= __reduce_or_sync(FULL, mine);
-            if (run < 32) break;
-        }
-        if (mode == MODE_PRIORITY) {
-            bm = warp_max(bm);
-            if (lane == 0 && bm > 0.0f) atomicMax(reinterpret_cast<int *>(&t.st->batch_max), __float_as_int(bm));
-        }
-        __syncwarp();
-        // ---- touched leaf lines -> nodes of level L-5, CHAIN_U lines per round
-        float *n1s = sum_level(t, t.L - 5), *n1m = min_level(t, t.L - 5);
-        const long long line0 = gs == 10 ? grp << 5 : grp;        // first leaf line of the group
-        float vs = 0.0f, vm = 0.0f;
-        while (linebits) {
-            long long line[CHAIN_U];
-            float x[CHAIN_U];
+    float *n1s = sum_level(t, t.L - 5), *n1m = min_level(t, t.L - 5);
+    float bm = 0.0f;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+        // everything the common case needs is requested up front: own index, both neighbours, own value
+        long long i = -1, ip = -1, inx = -1;
+        const bool ok = valid_at(t, r, j, i);
+        const bool ok_prev = valid_at(t, r, j - 1, ip), ok_next = valid_at(t, r, j + 1, inx);
+        const float vj = (ok && mode != MODE_EXTEND) ? val[j] : 0.0f;
+        if (!ok) continue;
+        if (idx_out) idx_out[j] = i;
+        if (mode == MODE_PRIORITY) bm = fmaxf(bm, fabsf(vj));
+        const long long line = i >> 5;
+        if (ok_prev && (ip >> 5) == line) continue;               // the line's leader does this entry
+        float4 v[8];
+        const float4 *src = reinterpret_cast<const float4 *>(leaf + (line << 5));
 #pragma unroll
-            for (int u = 0; u < CHAIN_U; ++u) {
-                line[u] = -1;
-                if (linebits) { line[u] = line0 + (__ffs(linebits) - 1); linebits &= linebits - 1; }
-            }
+        for (int k = 0; k < 8; ++k) v[k] = __ldcg(src + k);
+        long long ii = i;
+        float x = mode == MODE_RAW ? vj : (mode == MODE_PRIORITY ? pow_leaf(fabsf(vj), t) : defp);
+        bool more = ok_next && (inx >> 5) == line;
+        for (long long jj = j;;) {
+            leaf[ii] = x;                                         // equal indices: the later entry overwrites (last wins)
+            const int pos = (int)(ii & 31);
 #pragma unroll
-            for (int u = 0; u < CHAIN_U; ++u) x[u] = line[u] >= 0 ? ldcg(leaf + (line[u] << 5) + lane) : 0.0f;
-#pragma unroll
-            for (int u = 0; u < CHAIN_U; ++u) {
-                if (line[u] < 0) continue;                        // warp-uniform
-                vs = x[u]; vm = min_of_leaf(vs, (line[u] << 5) + lane, len);
-                line_reduce(vs, vm);
-                if (lane == 0) { n1s[line[u]] = vs; n1m[line[u]] = vm; }
+            for (int k = 0; k < 8; ++k) {                         // 32 selects: the line stays in registers
+                v[k].x = pos == 4 * k ? x : v[k].x;
+                v[k].y = pos == 4 * k + 1 ? x : v[k].y;
+                v[k].z = pos == 4 * k + 2 ? x : v[k].z;
+                v[k].w = pos == 4 * k + 3 ? x : v[k].w;
             }
+            if (!more) break;
+            ++jj;
+            ii = jj == j + 1 ? inx : entry_index(t, idx, jj, mode, r.seq0);
+            x = entry_leaf(t, val, jj, mode, defp);
+            long long nx;
+            more = valid_at(t, r, jj + 1, nx) && (nx >> 5) == line;
         }
-        long long g = grp;                                        // node index at the group's level
-        if (gs == 10) {
-            // the span's line of level L-5: this warp is its only writer in this launch
-            __syncwarp();
-            vs = ldcg(n1s + (grp << 5) + lane);
-            vm = ldcg(n1m + (grp << 5) + lane);
-            line_reduce(vs, vm);
-            if (lane == 0) { sum_level(t, t.L - 10)[grp] = vs; min_level(t, t.L - 10)[grp] = vm; }
+        float vs, vm;
+        line_total(v, line << 5, len, vs, vm);
+        n1s[line] = vs; n1m[line] = vm;
+    }
+    if (mode == MODE_PRIORITY) cta_batch_max(t, bm);
+    if (threadIdx.x == 0) trace_max(tr_on, TR_LINES_END);
+}
+
+// Any other batch (unsorted, duplicates, K batches in flight), after upd_mark_kernel: thread per ENTRY.  Every entry
+// loads its leaf line (8 x 128-bit) and looks at the dedup tags in it: the entry whose tag sits in the LOWEST tagged
+// slot of the line is the line's leader -- it resolves every tagged slot (a NaN-tagged slot names its winning entry:
+// that entry's value is computed and stored), reduces the line and stores its node of level L-5; everybody else is
+// done.  No side structure, no barrier, every lane of every warp works on a touched line (a pass over a touched-line
+// bitmap spends its instructions on empty lines: 9 us at 64K entries against 4 us here, profiles/per_phases_r02.txt).
+// Entries of one line may run at different times: a late one finds slots already resolved by the leader.  It is then
+// either no leader (nothing to do) or the leader of what is left, and rebuilds the same node from the same final
+// values -- stores of equal values, a benign race.
+constexpr int LT_THREADS = 128;
+
+__global__ void __launch_bounds__(LT_THREADS) upd_lines_tagged_kernel(TreeView t, long long n, const long long *idx,
+                                                                      const float *val, int mode)
+{
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
+    const int tr_on = TRACE_ON();
+    trace_cta0(tr_on, TR_LINES_START);
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long len = len_after(t, mode, n, -1);
+    const float defp = (mode == MODE_EXTEND) ? default_priority(t) : 0.0f;
+    float *leaf = leaf_ptr(t);
+    __shared__ float4 wbuf_all[(LT_THREADS / 32) * 256];
+    long long i = -1;
+    if (j < n) i = entry_index(t, idx, j, mode, mode == MODE_EXTEND ? t.st->seq : 0);
+    const bool live = i >= 0 && i < t.size;
+    const long long line = live ? i >> 5 : 0;
+    float4 xf[8];
+    warp_fetch_lines_raw(leaf, line, wbuf_all + (threadIdx.x >> 5) * 256, xf);     // the warp's 32 lines, fetched together
+    if (live) {
+        int4 x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            x[k] = make_int4(__float_as_int(xf[k].x), __float_as_int(xf[k].y), __float_as_int(xf[k].z), __float_as_int(xf[k].w));
+        unsigned tagged = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            tagged |= (x[k].x >= LEAF_TAG ? 1u : 0u) << (4 * k);
+            tagged |= (x[k].y >= LEAF_TAG ? 1u : 0u) << (4 * k + 1);
+            tagged |= (x[k].z >= LEAF_TAG ? 1u : 0u) << (4 * k + 2);
+            tagged |= (x[k].w >= LEAF_TAG ? 1u : 0u) << (4 * k + 3);
         }
-        // ---- climb: lines of level TL + 5m, m = mg .. 1
-        for (int m = mg; m >= 1; --m) {
-            const long long pl = g >> 5;
-            int newv = 0;
-            if (lane == 0) newv = atom_add_acq_rel(&t.cnt[t.coff[m] + pl], -1) - 1;     // releases lane 0's node store
-            newv = __shfl_sync(FULL, newv, 0);
-            if (newv != 0) break;                                 // another child of this line is still on its way
-            __syncwarp();                                         // lane 0's acquire orders the whole warp's loads below
-            const int s = t.TL + 5 * m;
-            vs = ldcg(sum_level(t, s) + (pl << 5) + lane);
-            vm = ldcg(min_level(t, s) + (pl << 5) + lane);
-            line_reduce(vs, vm);
-            if (lane == 0) { sum_level(t, s - 5)[pl] = vs; min_level(t, s - 5)[pl] = vm; }
-            g = pl;
+        const int p0 = __ffs(tagged) - 1;                         // -1: everything resolved already
+        int first = 0;                                            // the tag in the lowest tagged slot
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            first = p0 == 4 * k ? x[k].x : first;
+            first = p0 == 4 * k + 1 ? x[k].y : first;
+            first = p0 == 4 * k + 2 ? x[k].z : first;
+            first = p0 == 4 * k + 3 ? x[k].w : first;
+        }
+        if (p0 >= 0 && first == LEAF_TAG + (int)j) {
+            float4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                v[k] = make_float4(__int_as_float(x[k].x), __int_as_float(x[k].y), __int_as_float(x[k].z), __int_as_float(x[k].w));
+            while (tagged) {                                      // one or two per line; ONE copy of the entry code
+                const int pos = __ffs(tagged) - 1;
+                tagged &= tagged - 1;
+                int tag = first;                                  // the tag this thread SAW in slot pos (its snapshot)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    tag = pos == 4 * k ? x[k].x : tag;
+                    tag = pos == 4 * k + 1 ? x[k].y : tag;
+                    tag = pos == 4 * k + 2 ? x[k].z : tag;
+                    tag = pos == 4 * k + 3 ? x[k].w : tag;
+                }
+                const float nv = entry_leaf(t, val, (long long)(tag - LEAF_TAG), mode, defp);
+                leaf[(line << 5) + pos] = nv;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    v[k].x = pos == 4 * k ? nv : v[k].x;
+                    v[k].y = pos == 4 * k + 1 ? nv : v[k].y;
+                    v[k].z = pos == 4 * k + 2 ? nv : v[k].z;
+                    v[k].w = pos == 4 * k + 3 ? nv : v[k].w;
+                }
+            }
+            float vs, vm;
+            line_total(v, line << 5, len, vs, vm);
+            sum_level(t, t.L - 5)[line] = vs;
+            min_level(t, t.L - 5)[line] = vm;
         }
     }
-    if (!last_cta(t)) return;
-    top_and_finalize(t, sm_top, mode, n, -1);
+    if (threadIdx.x == 0) trace_max(tr_on, TR_LINES_END);
 }
 
 // ---------------------------------------------------------------------------------
@@ -879,8 +938,10 @@ __device__ __forceinline__ float is_weight(float leaf, float p_min, float beta, 
 {
     float denom = t.weps ? __fadd_rn(p_min, t.eps32) : p_min;
     float ratio = __fdiv_rn(leaf, denom);
-    // np.power(fp32, -beta) -> libm powf (< 1 ulp); evaluate in double and round once
-    return (float)pow((double)ratio, -(double)beta);
+    // np.power(fp32, -beta) -> libm powf (< 1 ulp); evaluate in double and round once (beta = 0.5, the value the learner
+    // forces, learner.py:105-107: 1 / sqrt in double, same rounding, a fifth of the instructions)
+    if (beta == 0.5f) return (float)__ddiv_rn(1.0, __dsqrt_rn((double)ratio));
+    return (float)pow_cold((double)ratio, -(double)beta);
 }
 
 // ---------------------------------------------------------------------------------
@@ -933,6 +994,8 @@ __global__ void __launch_bounds__(256) tree_sample_kernel(TreeView t, long long 
                                                           int mode, float beta, long long *idx_out, float *w_out,
                                                           float *mass_out, int R)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     const unsigned call = (unsigned)t.st->pad[2], seed = (unsigned)t.st->pad[3];
     const long long len = t.st->len;
     const float p_sum = t.st->p_sum, p_min = t.st->p_min;
@@ -945,6 +1008,8 @@ __global__ void __launch_bounds__(256) tree_sample_kernel(TreeView t, long long 
     const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int per_warp = 4 * R;
     const long long rounds = (n + per_warp * n_warps - 1) / (per_warp * n_warps);
+    const int tr_on = TRACE_ON();
+    trace_cta0(tr_on, TR_SAMPLE_START);
     for (long long rd = 0; rd < rounds; ++rd) {
         const long long k = (w0 + rd * n_warps) * per_warp + lane;
         const bool live = lane < per_warp && k < n;
@@ -971,29 +1036,51 @@ __global__ void __launch_bounds__(256) tree_sample_kernel(TreeView t, long long 
             if (mass_out) mass_out[k] = m;
         }
     }
+    if (threadIdx.x == 0) trace_max(tr_on, TR_SAMPLE_END);
     if (!u) { __syncthreads(); rng_advance(t); }
 }
 
 // ---------------------------------------------------------------------------------
-// throughput mode (many batches in flight): one THREAD per sample.  The CTA stages the top of the tree as a full
-// level-ordered heap in shared memory -- heap levels 0..TL copied, the stored level S <= 14 copied and the levels in
-// between rebuilt pairwise (bit-identical to a stored tree) -- so the first S levels cost one shared-memory load
-// each; every deeper stored level costs the thread one 128-byte line (8 x 128-bit loads in flight) whose 5 levels
-// it resolves in registers.  Same comparisons in the same order as the reference loop and as group_descend, so
-// both modes return identical indices.  ~10x fewer warp instructions per sample than the 8-lane descent.
+// throughput mode (many batches in flight): one THREAD per sample.
+//  * The CTA stages the top of the tree as a full level-ordered heap in shared memory: heap levels 0..TL copied, and
+//    every thread streams one line of the stored level S = TL + 5 (<= 14) and rebuilds the four levels in between in
+//    registers (bit-identical to a stored tree) -- one round trip, one barrier.  The first S levels of a descent then
+//    cost one shared-memory load each.
+//  * Every deeper stored level costs the thread one 128-byte line whose 5 levels it resolves in registers.  The warp
+//    fetches its 32 lines TOGETHER: 4 lines per load instruction (8 lanes x 16 bytes each, one L1 wavefront per line
+//    instead of eight when every lane streams its own line -- the unit that bounded the first version of this
+//    kernel), transposed through 4 KB of shared memory per warp (XOR-swizzled 16-byte chunks, conflict-free both ways).
+// Same comparisons in the same order as the reference loop and as group_descend: both modes return identical indices.
 // ---------------------------------------------------------------------------------
 constexpr int ST_THREADS = 512;
 
-// one line (32 nodes of a stored level, children of `node`): go right and subtract iff mass > left, 5 times
-__device__ __forceinline__ void thread_line_descend(const float *__restrict__ lvl, long long &node, float &m, float &leaf)
+__device__ __forceinline__ void warp_fetch_lines(const float *__restrict__ lvl, long long node, float4 *wbuf, float (&v)[32])
 {
-    const float4 *p = reinterpret_cast<const float4 *>(lvl + (node << 5));
-    float v[32];
+    const int lane = lane_id();
+    const int g = lane >> 3, c = lane & 7;
+    float4 q[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const long long ln = __shfl_sync(FULL, node, 4 * r + g);
+        q[r] = __ldg(reinterpret_cast<const float4 *>(lvl + (ln << 5)) + c);
+    }
+    __syncwarp();                                                 // everyone is done reading the previous level's lines
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int slot = 4 * r + g;
+        wbuf[slot * 8 + (c ^ (slot & 7))] = q[r];
+    }
+    __syncwarp();
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float4 q = __ldg(p + k);
-        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+        const float4 x = wbuf[lane * 8 + (k ^ (lane & 7))];
+        v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
     }
+}
+
+// one line (32 nodes of a stored level, children of `node`) in registers: go right and subtract iff mass > left, 5 times
+__device__ __forceinline__ void thread_line_descend(const float (&v)[32], long long &node, float &m, float &leaf)
+{
     float t16[16], t8[8], t4[4], t2[2];
 #pragma unroll
     for (int i = 0; i < 16; ++i) t16[i] = op_sum(v[2 * i], v[2 * i + 1]);
@@ -1047,21 +1134,51 @@ __global__ void __launch_bounds__(ST_THREADS) tree_sample_thread_kernel(TreeView
                                                                         long long *idx_out, float *w_out,
                                                                         float *mass_out, int S)
 {
-    extern __shared__ float sh[];                                 // heap of levels 0..S: node i of level d at [2^d + i]
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
+    extern __shared__ float4 sh4[];
+    float *sh = reinterpret_cast<float *>(sh4);                   // heap of levels 0..S: node i of level d at [2^d + i]
+    float4 *wbuf = sh4 + ((2u << S) >> 2) + (threadIdx.x >> 5) * 256;     // this warp's 32 lines x 8 chunks
     const unsigned call = (unsigned)t.st->pad[2], seed = (unsigned)t.st->pad[3];
-    const int TL = t.TL;
-    for (int i = threadIdx.x; i < (2 << TL); i += blockDim.x) sh[i] = i ? t.sum[i] : 0.0f;
-    if (S > TL) {
+    const int TL = t.TL;                                          // S == TL + 5
+    const int tr_on = TRACE_ON();
+    trace_cta0(tr_on, TR_SAMPLE_START);
+    for (int i = threadIdx.x; i < (2 << TL); i += blockDim.x) sh[i] = i ? __ldg(t.sum + i) : 0.0f;
+    {
+        // level S, coalesced: 128-bit word i holds nodes 4i .. 4i+3 of level S = 2 nodes of level S-1 = 1 node of level
+        // S-2; neighbouring lanes hold neighbouring words, so levels S-3 and S-4 come from two shuffles.  Conflict-free
+        // shared-memory stores; no barrier until everything is in place.
         const float4 *lv = reinterpret_cast<const float4 *>(sum_level(t, S));
-        float4 *dst = reinterpret_cast<float4 *>(sh + (1 << S));
-        for (int i = threadIdx.x; i < (1 << (S - 2)); i += blockDim.x) dst[i] = lv[i];
-        for (int d = S - 1; d > TL; --d) {
-            __syncthreads();
-            for (int i = threadIdx.x; i < (1 << d); i += blockDim.x)
-                sh[(1 << d) + i] = op_sum(sh[2 * ((1 << d) + i)], sh[2 * ((1 << d) + i) + 1]);
+        const int n4 = 1 << (S - 2);                              // 128-bit words of level S (a multiple of 32)
+        float4 *d0 = reinterpret_cast<float4 *>(sh + (1 << S));
+        float2 *d1 = reinterpret_cast<float2 *>(sh + (1 << (S - 1)));
+        float *d2 = sh + (1 << (S - 2)), *d3 = sh + (1 << (S - 3)), *d4 = sh + (1 << (S - 4));
+        const int lane = threadIdx.x & 31;
+        for (int i0 = threadIdx.x; i0 < n4; i0 += 8 * blockDim.x) {
+            float4 q[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = i0 + k * blockDim.x;
+                q[k] = i < n4 ? __ldg(lv + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = i0 + k * blockDim.x;
+                if (i - lane >= n4) break;                        // warp-uniform: whole warps are in or out (n4 % 32 == 0)
+                const float a = op_sum(q[k].x, q[k].y), b = op_sum(q[k].z, q[k].w);
+                const float c = op_sum(a, b);
+                const float c2 = op_sum(c, __shfl_xor_sync(FULL, c, 1));
+                const float c3 = op_sum(c2, __shfl_xor_sync(FULL, c2, 2));
+                d0[i] = q[k];
+                d1[i] = make_float2(a, b);
+                d2[i] = c;
+                if ((lane & 1) == 0) d3[i >> 1] = c2;
+                if ((lane & 3) == 0) d4[i >> 2] = c3;
+            }
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) trace_max(tr_on, TR_SAMPLE_STAGED);
     const long long len = t.st->len;
     const float p_sum = t.st->p_sum, p_min = t.st->p_min;
     int bad = 0;
@@ -1069,15 +1186,28 @@ __global__ void __launch_bounds__(ST_THREADS) tree_sample_thread_kernel(TreeView
     else if (!(p_sum > 0.0f)) bad = PB_ST_PSUM_NONPOS;
     else if (!(p_min > 0.0f)) bad = PB_ST_PMIN_NONPOS;
     const float root = sh[1];
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    const bool batch_p2 = (batch & (batch - 1)) == 0;             // (k + u) / batch == (k + u) * (1 / batch) exactly
+    const double inv_batch = 1.0 / (double)batch;
+    // whole warps iterate together (the line fetch is a warp-wide operation); lanes past n ride along on node 0
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); k0 < n; k0 += stride) {
+        const long long k = k0 + (threadIdx.x & 31);
+        const bool live = k < n;
         if (bad) {
-            idx_out[k] = 0; w_out[k] = 0.0f;
-            if (mass_out) mass_out[k] = 0.0f;
-            if (k == 0) atomicOr(&t.st->status, bad);
+            if (live) {
+                idx_out[k] = 0; w_out[k] = 0.0f;
+                if (mass_out) mass_out[k] = 0.0f;
+                if (k == 0) atomicOr(&t.st->status, bad);
+            }
             continue;
         }
-        const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
-        const float m0 = (mode == 0) ? (float)(0.0 + ((double)p_sum - 0.0) * uk) : stratified_mass(k % batch, uk, batch, p_sum);
+        float m0 = 0.0f;
+        if (live) {
+            const double uk = u ? u[k] : philox_uniform(seed, call, (unsigned long long)k);
+            if (mode == 0) m0 = (float)(0.0 + ((double)p_sum - 0.0) * uk);
+            else if (batch_p2) m0 = (float)__dmul_rn(__dmul_rn(__dadd_rn((double)(k & (batch - 1)), uk), inv_batch), (double)p_sum);
+            else m0 = stratified_mass(k % batch, uk, batch, p_sum);
+        }
         float m = m0;
         const bool over = m > root;
         if (over) m = 0.0f;
@@ -1089,13 +1219,20 @@ __global__ void __launch_bounds__(ST_THREADS) tree_sample_thread_kernel(TreeView
         }
         long long node = hn - (1 << S);                           // index within level S
         float leafv = sh[hn];
-        for (int s = S + 5; s <= t.L; s += 5) thread_line_descend(sum_level(t, s), node, m, leafv);
-        long long i = over ? t.size : node;
-        if (i > len - 1) { i = len - 1; leafv = leaf_ptr(t)[i]; }
-        idx_out[k] = i;
-        w_out[k] = is_weight(leafv, p_min, beta, t);
-        if (mass_out) mass_out[k] = m0;
+        for (int s = S + 5; s <= t.L; s += 5) {
+            float v[32];
+            warp_fetch_lines(sum_level(t, s), node, wbuf, v);
+            thread_line_descend(v, node, m, leafv);
+        }
+        if (live) {
+            long long i = over ? t.size : node;
+            if (i > len - 1) { i = len - 1; leafv = leaf_ptr(t)[i]; }
+            idx_out[k] = i;
+            w_out[k] = is_weight(leafv, p_min, beta, t);
+            if (mass_out) mass_out[k] = m0;
+        }
     }
+    if (threadIdx.x == 0) trace_max(tr_on, TR_SAMPLE_END);
     if (!u) { __syncthreads(); rng_advance(t); }
 }
 
@@ -1113,17 +1250,31 @@ struct GlobalTop {
     long long lo, hi;           // this rank owns strata [lo, hi)
 };
 
+// all_state may sit in peer-mapped memory that other GPUs write: read it past this SM's L1
+__device__ __forceinline__ float ld_state_f32(const float *p)
+{
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ long long ld_state_s64(const long long *p)
+{
+    long long v;
+    asm volatile("ld.volatile.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void build_top(GlobalTop *g, const pb_per_state *all_state, int G)
 {
-    if (threadIdx.x < G) g->psum[G + threadIdx.x] = all_state[threadIdx.x].p_sum;
+    if (threadIdx.x < G) g->psum[G + threadIdx.x] = ld_state_f32(&all_state[threadIdx.x].p_sum);
     __syncthreads();
     for (int n = G >> 1; n >= 1; n >>= 1) {
         if (threadIdx.x < n) g->psum[n + threadIdx.x] = op_sum(g->psum[2 * (n + threadIdx.x)], g->psum[2 * (n + threadIdx.x) + 1]);
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        float m = all_state[0].p_min;
-        for (int r = 1; r < G; ++r) m = op_min(m, all_state[r].p_min);
+        float m = ld_state_f32(&all_state[0].p_min);
+        for (int r = 1; r < G; ++r) m = op_min(m, ld_state_f32(&all_state[r].p_min));
         g->pmin = m;
     }
     __syncthreads();
@@ -1173,12 +1324,46 @@ __device__ long long first_owned(const GlobalTop &g, int G, long long n, int ran
     return hi;
 }
 
+// peer wait (pb_tree_sample_global_peer): the shard states were PUT into this rank's slots by every rank
+// (peer_state_put_kernel, csrc/peer.cu); every CTA waits on the local signal pad until all ranks' puts of the current
+// exchange have landed (bounded: gives up after timeout_ns and raises bit 2 of *status), then reads the slot.
+struct PeerWait {
+    const unsigned long long *flags;      // local pad, channel 2: [src] = number of that rank's completed puts
+    const unsigned long long *epoch;      // local count of this rank's own puts (the exchange to wait for)
+    const unsigned char *slots;           // local state area: slot (2 + (epoch & 1)) holds the blocks of that exchange
+    unsigned int *status;
+    unsigned long long timeout_ns;
+    int slot_bytes;                       // bytes per slot
+};
+
 __global__ void __launch_bounds__(256) global_sample_kernel(TreeView t, const pb_per_state *all_state, int G, int rank,
                                                             long long n_global, const double *u, float beta,
                                                             long long *idx_out, float *w_out, long long *stratum_out,
-                                                            int R)
+                                                            int R, PeerWait pw)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     __shared__ GlobalTop g;
+    if (pw.flags) {
+        const unsigned long long e = *pw.epoch;
+        if (threadIdx.x < G) {
+            // relaxed polls, one acquire fence at the end (an acquire load per poll is a system-scope fence per poll)
+            const volatile unsigned long long *f = pw.flags + threadIdx.x;
+            if (*f < e) {
+                const unsigned long long t0 = global_ns();
+                unsigned spins = 0;
+                while (*f < e) {
+                    if ((++spins & 1023u) == 0 && pw.timeout_ns && global_ns() - t0 > pw.timeout_ns) {
+                        if (pw.status) atomicOr(pw.status, 1u << 2);
+                        break;
+                    }
+                }
+            }
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+        }
+        __syncthreads();
+        all_state = reinterpret_cast<const pb_per_state *>(pw.slots + (size_t)(2 + (e & 1)) * pw.slot_bytes);
+    }
     build_top(&g, all_state, G);
     const unsigned call = (unsigned)t.st->pad[2], seed = (unsigned)t.st->pad[3];
     if (threadIdx.x < 32) {
@@ -1188,7 +1373,7 @@ __global__ void __launch_bounds__(256) global_sample_kernel(TreeView t, const pb
     }
     __syncthreads();
     const long long lo = g.lo, cnt = g.hi - g.lo;
-    const long long len = all_state[rank].len;
+    const long long len = ld_state_s64(&all_state[rank].len);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         t.st->owned_lo = (int)lo; t.st->owned_n = (int)cnt;
         if (cnt > 0 && (len <= 0 || !(g.psum[1] > 0.0f) || !(g.pmin > 0.0f)))
@@ -1247,28 +1432,23 @@ __global__ void tree_export_kernel(TreeView t, int d, float *sum_heap, float *mi
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
-struct Layout { int L, TL, P; long long off[MAX_DEEP], coff[MAX_DEEP]; long long n_sum, n_min, n_cnt, bitmap_off; };
+struct Layout { int L, TL, P; long long off[MAX_DEEP]; long long n_sum, n_min, n_cnt; };
 
 void make_layout(long long cap, Layout *y)
 {
     y->L = pb_ilog2(cap);
     y->P = y->L <= TOP_MAX ? 0 : (y->L - TOP_MAX + 4) / 5;
     y->TL = y->L - 5 * y->P;
-    long long off = 2LL << y->TL, coff = 0;
-    for (int m = 0; m < MAX_DEEP; ++m) { y->off[m] = 0; y->coff[m] = 0; }
+    long long off = 2LL << y->TL;
+    for (int m = 0; m < MAX_DEEP; ++m) y->off[m] = 0;
     y->n_min = off;
     for (int m = 1; m <= y->P; ++m) {
         y->off[m] = off;
         off += 1LL << (y->TL + 5 * m);
-        if (m < y->P) {
-            y->n_min = off;                                       // the min store ends before the leaf level
-            y->coff[m] = coff;
-            coff += 1LL << (y->TL + 5 * m - 5);                   // one counter per line of level TL + 5m
-        }
+        if (m < y->P) y->n_min = off;                             // the min store ends before the leaf level
     }
     y->n_sum = off;
-    y->bitmap_off = coff;                                         // touched-line bitmap behind the arrival counters
-    y->n_cnt = coff + (cap >= 1024 ? cap / 1024 : 1);
+    y->n_cnt = 32;                                                // reserved scratch (no kernel needs a side array any more)
 }
 
 int make_view(const pb_tree *t, TreeView *v)
@@ -1280,9 +1460,8 @@ int make_view(const pb_tree *t, TreeView *v)
     make_layout(t->capacity, &y);
     if (!t->counters) return PB_E_ARG;
     v->sum = t->sum; v->min = t->min; v->owner = t->owner; v->cnt = t->counters; v->st = t->state;
-    v->bitmap = reinterpret_cast<unsigned *>(t->counters + y.bitmap_off);
     v->cap = t->capacity; v->size = t->size; v->L = y.L; v->TL = y.TL; v->P = y.P;
-    for (int m = 0; m < MAX_DEEP; ++m) { v->off[m] = y.off[m]; v->coff[m] = y.coff[m]; }
+    for (int m = 0; m < MAX_DEEP; ++m) v->off[m] = y.off[m];
     v->alpha = t->alpha; v->eps32 = t->eps_f32; v->eps64 = t->eps_f64;
     v->weps = t->weight_eps_in_denominator; v->dp64 = t->default_priority_fp64;
     return PB_OK;
@@ -1296,22 +1475,24 @@ int persistent_grid(long long work_items, int per_cta, int ctas_per_sm)
     return (int)(need < cap ? need : cap);
 }
 
-// every line of every deep level from the leaves up, then the top heap + state (streaming; ext: bulk build source)
+// every line of every deep level from level s_start (default: the leaves) up, then the top heap + state
+// (streaming; ext: bulk build source)
 int launch_rebuild(const TreeView &v, const float *ext, long long n_ext, int mode, long long n_new, long long set_len,
-                   void *stream)
+                   void *stream, int s_start = -1)
 {
-    if (v.P == 0) {
-        if (ext) PB_LAUNCH(tree_fill_leaves_kernel, (unsigned)((v.cap + 255) / 256), 256, 0, stream, v, ext, n_ext);
-        PB_LAUNCH(tree_top_kernel, 1, 512, 0, stream, v, mode, n_new, set_len);
+    if (s_start < 0) s_start = v.L;
+    if (v.P == 0 || s_start <= v.TL) {
+        if (ext) PB_LAUNCH_PDL(tree_fill_leaves_kernel, (unsigned)((v.cap + 255) / 256), 256, 0, stream, v, ext, n_ext);
+        PB_LAUNCH_PDL(tree_top_kernel, 1, 512, 0, stream, v, mode, n_new, set_len);
         return PB_OK;
     }
-    for (int s = v.L; s > v.TL;) {
+    for (int s = s_start; s > v.TL;) {
         int n_lv = (s - v.TL) / 5;
         if (n_lv > 3) n_lv = 3;
         const int fuse = (s - 5 * n_lv <= v.TL) ? 1 : 0;
         const int grid = n_lv == 3 ? persistent_grid(1LL << s, 32 * RB_TILE, 4)
                                    : persistent_grid(1LL << s, RB_TILE * (RB_THREADS / 32), 8);
-        PB_LAUNCH(tree_rebuild_kernel, grid, RB_THREADS, 0, stream, v, s, n_lv, s == v.L ? ext : (const float *)nullptr,
+        PB_LAUNCH_PDL(tree_rebuild_kernel, grid, RB_THREADS, 0, stream, v, s, n_lv, s == v.L ? ext : (const float *)nullptr,
                   n_ext, fuse, mode, n_new, set_len);
         s -= 5 * n_lv;
     }
@@ -1331,56 +1512,41 @@ int launch_update(const pb_tree *t, long long n, const long long *idx, const flo
         if (n > v.size) return PB_E_ARG;
         sorted = (2 * n <= v.size);     // a contiguous run of slots; a long one may wrap onto lines it already touched
     }
-    // Three regimes.  (1) small sorted batches (one learner batch, the ring's extends): ONE launch, leaders + arrival
-    // counters.  (2) anything else up to cap/16 entries: mark (dedup tags + touched-line bitmap), leaf scatter, sparse
-    // rebuild -- cost proportional to the batch.  (3) beyond that: scatter the leaves and stream the whole leaf array.
+    const int nb = (int)((n + 255) / 256);
+    // Trees without a deep level (capacity <= 512): the leaves ARE the heap's bottom level.
     if (v.P == 0) {
         if (sorted) {
-            const int grid = persistent_grid(n, CHAIN_THREADS / 32, 2);
-            PB_LAUNCH(upd_chain_kernel, grid, CHAIN_THREADS, 0, stream, v, n, idx, val, mode, idx_out);
-            return PB_OK;
+            PB_LAUNCH_PDL(upd_leaf_sorted_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out);
+        } else {
+            if (n > LEAF_TAG_MAX_N) return PB_E_UNSUPPORTED;
+            PB_LAUNCH_PDL(upd_mark_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out);
+            PB_LAUNCH_PDL(upd_leaf_kernel, nb, 256, 0, stream, v, n, idx, val, mode, (long long *)nullptr);
         }
-        if (n > LEAF_TAG_MAX_N) return PB_E_UNSUPPORTED;
-        const int nb0 = (int)((n + 255) / 256);
-        PB_LAUNCH(upd_mark_kernel, nb0, 256, 0, stream, v, n, idx, val, mode, idx_out, 0);
-        PB_LAUNCH(upd_leaf_kernel, nb0, 256, 0, stream, v, n, idx, val, mode, (long long *)nullptr);
-        PB_LAUNCH(tree_top_kernel, 1, 512, 0, stream, v, mode, n, -1LL);
+        PB_LAUNCH_PDL(tree_top_kernel, 1, 512, 0, stream, v, mode, n, -1LL);
         return PB_OK;
     }
-    if (sorted && n <= CHAIN_MAX_N) {
-        const int grid = persistent_grid(n, CHAIN_THREADS / 32, 2);
-        PB_LAUNCH(upd_chain_kernel, grid, CHAIN_THREADS, 0, stream, v, n, idx, val, mode, idx_out);
-        return PB_OK;
+    // Three regimes, each a LINE phase (touched leaf lines -> nodes of level L-5) followed by the streaming rebuild of
+    // the small tree above level L-5 (its last CTA rebuilds the top heap and the state block):
+    //   (1) sorted batches (one learner batch, the ring's extends): the line leaders apply their runs -- 2 launches;
+    //   (2) anything else below cap/16 entries: mark (dedup tags on the leaf slots), entry-driven lines -- 3 launches;
+    //   (3) beyond that: scatter the leaves and stream the whole leaf array.
+    if (sorted && n <= SORTED_LINES_MAX_N) {
+        const int grid = (int)((n + LS_THREADS - 1) / LS_THREADS);
+        PB_LAUNCH_PDL(upd_lines_sorted_kernel, grid, LS_THREADS, 0, stream, v, n, idx, val, mode, idx_out);
+        return launch_rebuild(v, nullptr, 0, mode, n, -1, stream, v.L - 5);
     }
-    const int nb = (int)((n + 255) / 256);
     if (n < v.cap / 16 && n <= LEAF_TAG_MAX_N) {
-        PB_LAUNCH(upd_mark_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out, 1);
-        PB_LAUNCH(upd_leaf_kernel, nb, 256, 0, stream, v, n, idx, val, mode, (long long *)nullptr);
-        const long long spans = v.cap >= 32768 ? v.cap >> 15 : 1;
-        const int fuse = v.P <= 3 ? 1 : 0;
-        PB_LAUNCH(tree_rebuild_sparse_kernel, (int)(spans < 2048 ? spans : 2048), SPR_THREADS, 0, stream, v, mode, n, fuse);
-        if (!fuse) {
-            // deeper trees: levels L-15 .. TL by the streaming pass over the (small) array of level L-15
-            TreeView u2 = v;
-            for (int s2 = v.L - 15; s2 > v.TL;) {
-                int n_lv = (s2 - v.TL) / 5;
-                if (n_lv > 3) n_lv = 3;
-                const int f2 = (s2 - 5 * n_lv <= v.TL) ? 1 : 0;
-                const int grid = n_lv == 3 ? persistent_grid(1LL << s2, 32 * RB_TILE, 4)
-                                           : persistent_grid(1LL << s2, RB_TILE * (RB_THREADS / 32), 8);
-                PB_LAUNCH(tree_rebuild_kernel, grid, RB_THREADS, 0, stream, u2, s2, n_lv, (const float *)nullptr, 0LL, f2,
-                          mode, n, -1LL);
-                s2 -= 5 * n_lv;
-            }
-        }
-        return PB_OK;
+        PB_LAUNCH_PDL(upd_mark_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out);
+        PB_LAUNCH_PDL(upd_lines_tagged_kernel, (int)((n + LT_THREADS - 1) / LT_THREADS), LT_THREADS, 0, stream, v, n, idx, val,
+                      mode);
+        return launch_rebuild(v, nullptr, 0, mode, n, -1, stream, v.L - 5);
     }
     if (sorted) {
-        PB_LAUNCH(upd_leaf_sorted_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out);
+        PB_LAUNCH_PDL(upd_leaf_sorted_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out);
     } else {
         if (n > LEAF_TAG_MAX_N) return PB_E_UNSUPPORTED;        // the dedup tags are NaN payloads: 2^23 - 2 of them
-        PB_LAUNCH(upd_mark_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out, 0);
-        PB_LAUNCH(upd_leaf_kernel, nb, 256, 0, stream, v, n, idx, val, mode, (long long *)nullptr);
+        PB_LAUNCH_PDL(upd_mark_kernel, nb, 256, 0, stream, v, n, idx, val, mode, idx_out);
+        PB_LAUNCH_PDL(upd_leaf_kernel, nb, 256, 0, stream, v, n, idx, val, mode, (long long *)nullptr);
     }
     return launch_rebuild(v, nullptr, 0, mode, n, -1, stream);
 }
@@ -1473,27 +1639,25 @@ int pb_tree_sample_batches(const pb_tree *t, long long n_batches, long long batc
     if (n >= (1LL << 31) || (n > 0 && (!idx_out || !weight_out))) return PB_E_ARG;
     if (n == 0) return PB_OK;
     if (n > 16384 && v.L >= 10) {
-        // throughput mode: a thread per sample over a shared-memory heap of the top S levels (S = the deepest stored
-        // level <= 14)
-        int S = v.TL;
-        while (S + 5 <= v.L && S + 5 <= 14) S += 5;
-        const size_t smem = sizeof(float) * (2ull << S);
+        // throughput mode: a thread per sample over a shared-memory heap of the top S = TL + 5 (<= 14) levels
+        const int S = v.TL + 5;
+        const size_t smem = sizeof(float) * (2ull << S) + (ST_THREADS / 32) * 4096;      // top heap + a line buffer per warp
         static PbPerDeviceOnce attr_set;
         if (!attr_set.done()) {
             cudaError_t e = cudaFuncSetAttribute(tree_sample_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)(sizeof(float) * (2ull << 14)));
+                                                 (int)(sizeof(float) * (2ull << 14) + (ST_THREADS / 32) * 4096));
             if (e != cudaSuccess) return (int)e;
             attr_set.mark();
         }
         const int per_sm = smem > 100 * 1024 ? 1 : 2;
-        PB_LAUNCH(tree_sample_thread_kernel, persistent_grid(n, ST_THREADS, per_sm), ST_THREADS, smem, stream, v, n, batch, u,
+        PB_LAUNCH_PDL(tree_sample_thread_kernel, persistent_grid(n, ST_THREADS, per_sm), ST_THREADS, smem, stream, v, n, batch, u,
                   mode, beta, idx_out, weight_out, mass_out, S);
         return PB_OK;
     }
     // one learner batch: one 8-lane descent chain per group, 4 samples per warp (latency)
     const int R = 1;
     const int sgrid = persistent_grid(n, 8 * 4 * R, 6);
-    PB_LAUNCH(tree_sample_kernel, sgrid, 256, 0, stream, v, n, batch, u, mode, beta, idx_out, weight_out, mass_out, R);
+    PB_LAUNCH_PDL(tree_sample_kernel, sgrid, 256, 0, stream, v, n, batch, u, mode, beta, idx_out, weight_out, mass_out, R);
     return PB_OK;
 }
 
@@ -1515,9 +1679,51 @@ int pb_tree_sample_global(const pb_tree *t, int n_ranks, int rank, const pb_per_
     if (n_global > 0 && (!idx_out || !weight_out)) return PB_E_ARG;
     if (n_global == 0) return PB_OK;
     const int R = n_global <= 16384 ? 1 : 8;
-    PB_LAUNCH(global_sample_kernel, persistent_grid(n_global, 8 * 4 * R, 6), 256, 0, stream, v, all_state, n_ranks, rank,
-              n_global, u, beta, idx_out, weight_out, stratum_out, R);
+    PeerWait pw = {};
+    PB_LAUNCH_PDL(global_sample_kernel, persistent_grid(n_global, 8 * 4 * R, 6), 256, 0, stream, v, all_state, n_ranks, rank,
+              n_global, u, beta, idx_out, weight_out, stratum_out, R, pw);
     return PB_OK;
+}
+
+int pb_tree_sample_global_peer(const pb_tree *t, const pb_peer_group *g, long long n_global, const double *u, float beta,
+                               long long *idx_out, float *weight_out, long long *stratum_out, void *stream)
+{
+    TreeView v;
+    int rc = make_view(t, &v);
+    if (rc) return rc;
+    if (!g || g->world < 1 || g->world > PB_PEER_MAX || !pb_is_pow2(g->world) || g->rank < 0 || g->rank >= g->world)
+        return PB_E_ARG;
+    if (!g->flags[g->rank] || !g->state[g->rank] || !g->epoch || n_global < 0) return PB_E_ARG;
+    if (n_global > 0 && (!idx_out || !weight_out)) return PB_E_ARG;
+    if (n_global == 0) return PB_OK;
+    const int R = n_global <= 16384 ? 1 : 8;
+    PeerWait pw;
+    pw.flags = g->flags[g->rank] + 2 * PB_PEER_MAX;
+    pw.epoch = g->epoch + 2;
+    pw.slots = g->state[g->rank];
+    pw.status = g->status;
+    pw.timeout_ns = g->timeout_ns;
+    pw.slot_bytes = PB_PEER_MAX * 64;
+    PB_LAUNCH_PDL(global_sample_kernel, persistent_grid(n_global, 8 * 4 * R, 6), 256, 0, stream, v,
+                  (const pb_per_state *)nullptr, g->world, g->rank, n_global, u, beta, idx_out, weight_out, stratum_out, R, pw);
+    return PB_OK;
+}
+
+int pb_tree_trace(int enable, unsigned long long *out, int n_out)
+{
+    // synchronous (measurement runs only): copy out the marks, clear them, switch marking on / off
+    unsigned long long host[TRACE_SLOTS];
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyFromSymbol(host, g_trace, sizeof(host));
+    if (e != cudaSuccess) return (int)e;
+    if (out) for (int k = 0; k < n_out && k < TRACE_SLOTS; ++k) out[k] = host[k];
+    for (int k = 0; k < TRACE_SLOTS; ++k) host[k] = 0;
+    e = cudaMemcpyToSymbol(g_trace, host, sizeof(host));
+    if (e != cudaSuccess) return (int)e;
+    const int on = enable ? 1 : 0;
+    e = cudaMemcpyToSymbol(g_trace_on, &on, sizeof(on));
+    return e == cudaSuccess ? PB_OK : (int)e;
 }
 
 int pb_tree_export(const pb_tree *t, float *sum_heap, float *min_heap, void *stream)

@@ -166,6 +166,23 @@ class PrioritizedTree:
                                                    _lib.ptr(stratum_out), self._stream()), "pb_tree_sample_global")
         return idx_out, weight_out
 
+    def sample_global_peer(self, peer, n_global, u, beta=None, idx_out=None, weight_out=None, stratum_out=None):
+        """``sample_global`` on the shard states of the latest ``PeerGroup.state_put`` exchange: the kernel itself waits
+        (bounded) until every rank's put has landed in this rank's peer-mapped slot -- no separate barrier launch."""
+        import ctypes as C
+        n_global = int(n_global)
+        if idx_out is None:
+            idx_out = torch.empty(n_global, dtype=torch.int64, device=self.device)
+        if weight_out is None:
+            weight_out = torch.empty(n_global, dtype=torch.float32, device=self.device)
+        beta = self._beta if beta is None else float(beta)
+        assert u is None or (u.dtype == torch.float64 and u.is_cuda)
+        _lib.check(self._lib.pb_tree_sample_global_peer(self._ref, C.byref(peer.c), n_global, _lib.ptr(u), beta,
+                                                        idx_out.data_ptr(), weight_out.data_ptr(),
+                                                        _lib.ptr(stratum_out), self._stream()),
+                   "pb_tree_sample_global_peer")
+        return idx_out, weight_out
+
     def seed(self, seed, call=0):
         """Key of the in-kernel Philox generator (all ranks of a sharded buffer must share it)."""
         self._seed = int(seed) & 0x7FFFFFFF

@@ -95,9 +95,13 @@ class LearnerStep:
                     from .peer import PeerGroup
                     self.peer = PeerGroup.create(self.pg, self.rank, self.world_size, opt.numel, d)
                     opt.attach_peer_group(self.peer)
-                    # ONE handshake per step: the shard states ride on the gradient exchange's barrier and are used by
-                    # the NEXT step's global sampling
-                    opt.peer_state = self.tree.state
+                    # The shard states travel by PUT right after the priority write-back (no rank waits there) and the
+                    # global sampling kernel waits for them itself: the exchange hides behind the backward pass, and the
+                    # gradient exchange + clip + Adam is one launch whose CTAs wait on the signal pad themselves.
+                    self.state_by_put = os.environ.get("PB_PEER_STATE_PUT", "1") != "0"
+                    if not self.state_by_put:
+                        # one handshake per step: the states ride on the gradient exchange's barrier (one step stale)
+                        opt.peer_state = self.tree.state
                     self.all_state = self.peer.all_state
                     self._states_synced = False
                 except Exception as e:                                   # e.g. ranks on different boxes
@@ -106,6 +110,8 @@ class LearnerStep:
             if self.peer is None:
                 opt.allreduce = lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
             self.exchange = "peer" if self.peer is not None else "nccl"
+        if self.peer is None:
+            self.state_by_put = False
         self.launches_per_step = None
         self._side = None
         self._trace = None               # enable_trace(): device buffer of timeline marks
@@ -172,7 +178,10 @@ class LearnerStep:
         on its gradient exchange for the next step; this primes the first step and re-synchronises after anything
         outside the step changed a tree (ingest, a manual priority update)."""
         if self.peer is not None:
-            self.peer.state_allgather(self.tree.state)
+            if self.state_by_put:
+                self.peer.state_put(self.tree.state)
+            else:
+                self.peer.state_allgather(self.tree.state)
             self._states_synced = True
 
     def _sample_gather(self, u, out, tag=""):
@@ -183,9 +192,14 @@ class LearnerStep:
                 import torch.distributed as dist
                 dist.all_gather_into_tensor(self.all_state.view(-1), tree.state, group=self.pg)
                 self._mark(tag + "shard_states_gathered")
-            # peer path: all_state was gathered by the previous step's exchange (or sync_shard_states)
-            tree.sample_global(self.world_size, self.rank, self.all_state, self.B_global, u,
-                               idx_out=out["idx"], weight_out=out["weight"], stratum_out=self.stratum)
+            if self.state_by_put:
+                # the kernel waits for the latest put of every rank (this step's tail, or sync_shard_states)
+                tree.sample_global_peer(self.peer, self.B_global, u, idx_out=out["idx"], weight_out=out["weight"],
+                                        stratum_out=self.stratum)
+            else:
+                # all_state was gathered by the previous step's exchange (or sync_shard_states)
+                tree.sample_global(self.world_size, self.rank, self.all_state, self.B_global, u,
+                                   idx_out=out["idx"], weight_out=out["weight"], stratum_out=self.stratum)
         else:
             tree.sample(self.B, u=u, idx_out=out["idx"], weight_out=out["weight"])
         self._mark(tag + "sampled")
@@ -209,7 +223,8 @@ class LearnerStep:
         tree, ring, agent, b = self.tree, self.ring, self.agent, self.buffer
         u = None if draw else self.u            # None: uniforms are drawn inside the sampling kernel
         u_sel = consume and getattr(self, "_u_in_block", False)
-        dp_peer = self.peer is not None
+        dp_peer = self.peer is not None and not self.state_by_put       # states ride on the gradient exchange
+        dp_put = self.peer is not None and self.state_by_put
         mark = self._mark
         mark("start")
         if self.prefetch:
@@ -247,6 +262,9 @@ class LearnerStep:
                 if consume:
                     self.ingest.consume_tree()         # default priorities of the new steps, after the write-back
                     self._side.wait_stream(side2)
+                if dp_put:
+                    self.peer.state_put(tree.state)            # this shard's new state -> every rank; nobody waits here
+                    mark("tail:state_put")
                 if self.prefetch and u_sel:
                     self.ingest.select_uniforms(self.u, after_counter_inc=True)
                 if self.prefetch and not dp_peer:
@@ -288,10 +306,12 @@ class LearnerStep:
                 cur.wait_stream(self._side)
         else:
             if dp_peer:
-                raise _lib.PbError("PB_OVERLAP_WRITEBACK=0 is a single-GPU tuning switch")
+                raise _lib.PbError("PB_OVERLAP_WRITEBACK=0 needs the put-based state exchange under data parallelism")
             tree.update_priority(idx, self.td, sorted=self.sorted)
             if consume:
                 self.ingest.consume()
+            if dp_put:
+                self.peer.state_put(tree.state)
             if self.prefetch:
                 if u_sel:
                     self.ingest.select_uniforms(self.u, after_counter_inc=True)

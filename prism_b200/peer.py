@@ -1,7 +1,7 @@
 """PeerGroup -- the host side of csrc/peer.cu: one peer-mapped block per rank (NVLink / NVSwitch, CUDA IPC).
 
 Layout of a rank's block (bytes):  grad [2 x n floats, double-buffered] | reduced [n floats] | flags [64 u64] |
-norm_parts [8 f64] | state [2 x 8 x 64 B] | epochs [2 x u64] | status [u32].  ``torch.distributed`` is only used once, to exchange the 64-byte IPC handles; no
+norm_parts [8 f64] | state [4 x 8 x 64 B] | epochs [3 x u64] | status [u32].  ``torch.distributed`` is only used once, to exchange the 64-byte IPC handles; no
 collective library call remains on the per-step path.
 
 ``PeerGroup.loopback(world, n, device)`` builds ``world`` groups inside ONE process on one GPU (plain pointers to
@@ -15,6 +15,7 @@ import torch
 from . import _lib
 
 
+FUSED_EXCHANGE = __import__("os").environ.get("PB_PEER_FUSED", "1") != "0"   # one-launch exchange + Adam for small arenas
 ONE_SHOT_MAX_BYTES = 32 * 1024 * 1024      # n * 4 * world up to which the one-shot (single barrier) all-reduce is used
 WAIT_TIMEOUT_S = float(__import__("os").environ.get("PB_PEER_TIMEOUT_S", "20"))   # bound of every cross-GPU flag wait
 
@@ -31,7 +32,7 @@ def _layout(n):
     off = {"grad": 0, "grad_stride_bytes": n_bytes, "reduced": 2 * n_bytes, "flags": 3 * n_bytes}
     off["norm_parts"] = off["flags"] + 64 * 8
     off["state"] = off["norm_parts"] + 64
-    off["epoch"] = off["state"] + 2 * _lib.PB_PEER_MAX * 64
+    off["epoch"] = off["state"] + 4 * _lib.PB_PEER_MAX * 64      # slots 0-1: state_allgather, 2-3: state_put
     off["status"] = off["epoch"] + 64
     off["total"] = off["epoch"] + 256
     return off
@@ -124,6 +125,11 @@ class PeerGroup:
         self._n_gathers += 1
         return self.all_state
 
+    def state_put(self, state):
+        """Non-blocking half of the shard-state exchange: this rank's 64-byte tree state goes to every rank; the wait
+        happens inside the next ``PrioritizedTree.sample_global_peer`` (every rank must call both, in the same order)."""
+        _lib.check(_lib.load().pb_peer_state_put(C.byref(self.c), state.data_ptr(), self._stream()), "pb_peer_state_put")
+
     def grad_in_flight(self):
         """The half of the gradient arena the next exchange reads (eager calls only: under graph replay the device
         counter decides, see pb_pack_grads_parity)."""
@@ -147,6 +153,17 @@ class PeerGroup:
         there, beside the pulls and the optimizer sweep)."""
         lib, st = _lib.load(), self._stream()
         mark = mark or (lambda name: None)                        # timeline marks of LearnerStep.enable_trace()
+        if (FUSED_EXCHANGE and state is None and after_exchange is None
+                and self.n <= int(lib.pb_peer_allreduce_adam_max_n()) and self.n * 4 * self.world <= ONE_SHOT_MAX_BYTES):
+            # small arena, nothing riding on the handshake: handshake + pulls + global norm + clip + Adam in ONE launch
+            _lib.check(lib.pb_peer_allreduce_adam(C.byref(self.c), self.n, opt.arena.data_ptr(), opt.exp_avg.data_ptr(),
+                                                  opt.exp_avg_sq.data_ptr(), opt.step_count.data_ptr(), opt.lr,
+                                                  opt.betas[0], opt.betas[1], opt.eps, opt.max_grad_norm,
+                                                  opt.partials.data_ptr(), opt.norm_out.data_ptr(), st),
+                       "pb_peer_allreduce_adam")
+            self._n_gathers += 1                                  # channel 1 advanced: the other half of the arena is next
+            mark("opt:applied")
+            return
         self.state_allgather(self._dummy_state if state is None else state)     # every rank packed its gradient
         mark("opt:exchanged")
         if after_exchange is not None:

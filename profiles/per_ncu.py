@@ -17,8 +17,8 @@ g.manual_seed(1)
 tree = PrioritizedTree(N, device=dev, mode="stratified")
 leaves = torch.empty(N, device=dev).exponential_(1.0, generator=g).add_(1e-8).sqrt_()
 tree.build(leaves)
-reps = int(os.environ.get("PER_NCU_REPS", "3"))
-for K in (1, 64):
+reps = int(os.environ.get("PER_NCU_REPS", "2"))
+for K in (1, 16, 64):
     n = K * B
     u = torch.rand(n, dtype=torch.float64, device=dev, generator=g)
     idx = torch.empty(n, dtype=torch.int64, device=dev)

@@ -34,7 +34,11 @@ def test_two_ranks_equal_one_rank_on_the_union_batch(tmp_path, prefetch):
     r0, r1 = (torch.load(out2 + ".rank%d" % r, weights_only=False) for r in (0, 1))
     assert r0["exchange"] == "peer", "the ranks could not map each other's memory: peer path not exercised"
     assert torch.equal(r0["arena"], r1["arena"]), "replicas diverged"
-    assert np.allclose(r0["losses"], one["losses"], rtol=2e-5, atol=1e-7), (r0["losses"], one["losses"])
+    # a rank reports ITS part of the loss: the mean over its B_pad static rows (padding rows weigh 0).  The union's loss
+    # is the mean over the global batch: sum of the ranks' parts rescaled by B_pad / B_global (= FlatAdam.grad_scale)
+    B_pad, B_global = r0["B_pad"], one["B_pad"]
+    both = (np.asarray(r0["losses"]) + np.asarray(r1["losses"])) * (B_pad / B_global)
+    assert np.allclose(both, one["losses"], rtol=2e-5, atol=1e-7), (r0["losses"], r1["losses"], one["losses"])
     err = float((r0["arena"] - one["arena"]).abs().max() / one["arena"].abs().max())
     assert err < 2e-5, err
     # priorities written back by the two shards == the union tree's leaves

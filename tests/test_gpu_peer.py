@@ -32,6 +32,23 @@ def test_peer_allreduce_adam_matches_single_rank_step(world, n, one_shot, monkey
     from prism_b200 import _lib, peer as peer_mod
     from prism_b200.peer import PeerGroup
     monkeypatch.setattr(peer_mod, "ONE_SHOT_MAX_BYTES", (1 << 40) if one_shot else 0)
+    monkeypatch.setattr(peer_mod, "FUSED_EXCHANGE", False)     # the multi-launch schedules; the fused one: next test
+    _run_allreduce_adam(world, n)
+
+
+@pytest.mark.parametrize("world,n", [(2, 4096), (4, 4096), (8, 4096), (2, 100_000), (4, 100_000), (2, 400_004)])
+def test_peer_fused_allreduce_adam_matches_single_rank_step(world, n, monkeypatch):
+    """Small arenas: handshake + pulls + global norm + clip + Adam as ONE launch per rank (peer_allreduce_adam_kernel).
+    Sizes are bounded here because the loopback ranks share one GPU: every rank's CTAs must be resident at once (in the
+    multi-process set-up each rank has its own GPU; tests/test_gpu_multiprocess.py runs that)."""
+    from prism_b200 import peer as peer_mod
+    monkeypatch.setattr(peer_mod, "FUSED_EXCHANGE", True)
+    _run_allreduce_adam(world, n)
+
+
+def _run_allreduce_adam(world, n):
+    from prism_b200 import _lib
+    from prism_b200.peer import PeerGroup
     lib = _lib.load()
     groups = PeerGroup.loopback(world, n, DEV)
     g = torch.Generator(device=DEV).manual_seed(n + world)
@@ -85,6 +102,47 @@ def test_peer_state_allgather_and_barrier():
         want = torch.stack(states)
         for r in range(world):
             assert torch.equal(groups[r].all_state, want)
+
+
+def test_state_put_and_in_kernel_wait_equal_the_gathered_states():
+    """The put-based shard-state exchange of LearnerStep: every rank PUTS its state block to every rank (nobody waits),
+    the global sampling kernel waits for the puts itself.  4 loopback shards, three rounds with priority updates in
+    between: indices / weights / owned strata identical to sample_global on the stacked states."""
+    import numpy as np
+    from prism_b200 import PrioritizedTree
+    from prism_b200.peer import PeerGroup
+    world, C, B = 4, 4096, 256
+    groups = PeerGroup.loopback(world, 1024, DEV)
+    streams = [torch.cuda.Stream(device=DEV) for _ in range(world)]
+    rng = np.random.default_rng(5)
+    shards = []
+    for r in range(world):
+        t = PrioritizedTree(C, device=DEV, mode="stratified")
+        t.build(torch.from_numpy(np.sqrt(rng.exponential(1.0 + r, C).astype(np.float32) + 1e-8)).to(DEV))
+        shards.append(t)
+    out = [(torch.empty(B, dtype=torch.int64, device=DEV), torch.empty(B, device=DEV),
+            torch.empty(B, dtype=torch.int64, device=DEV)) for _ in range(world)]
+    ref = [(torch.empty(B, dtype=torch.int64, device=DEV), torch.empty(B, device=DEV),
+            torch.empty(B, dtype=torch.int64, device=DEV)) for _ in range(world)]
+    for it in range(3):
+        u = torch.from_numpy(rng.random(B)).to(DEV)
+        prio = [torch.from_numpy(rng.exponential(2.0, B).astype(np.float32)).to(DEV) for _ in range(world)]
+        torch.cuda.synchronize()
+        all_state = torch.stack([t.state for t in shards]).contiguous()
+        for r in range(world):
+            shards[r].sample_global(world, r, all_state, B, u, idx_out=ref[r][0], weight_out=ref[r][1], stratum_out=ref[r][2])
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                groups[r].state_put(shards[r].state)
+                shards[r].sample_global_peer(groups[r], B, u, idx_out=out[r][0], weight_out=out[r][1], stratum_out=out[r][2])
+        torch.cuda.synchronize()
+        for r in range(world):
+            groups[r].check()
+            for a, b in zip(out[r], ref[r]):
+                assert torch.equal(a, b), (it, r)
+            n = shards[r].state_host()["owned_n"]
+            shards[r].update_priority(out[r][0][:n], prio[r][:n], sorted=True)
 
 
 def test_a_missing_rank_times_out_instead_of_hanging(monkeypatch):
