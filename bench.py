@@ -273,7 +273,7 @@ def kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src):
     rows["per_gather (store_gather_kernel)"] = (time_kernel(lambda: ring.gather(idx, buf._obs, buf._next_obs, buf._reward,
                                                                                  buf._gamma, buf._nonterminal, buf._action), 50, torch),
                                                 B * (2 * D + 2 * Dout + 43))
-    rows["per_update (upd_chain_kernel, one launch)"] = (time_kernel(lambda: tree.update_priority(idx, prio, sorted=True), 50, torch),
+    rows["per_update (upd_lines_sorted_kernel + tree_rebuild_kernel)"] = (time_kernel(lambda: tree.update_priority(idx, prio, sorted=True), 50, torch),
                                                      B * (16 * L + 20))
     snap = opt.snapshot()
     rows["clip+adam (pack_grads + adam_clip)"] = (time_kernel(lambda: opt.step(refresh_table=False), 50, torch),
@@ -311,8 +311,8 @@ def kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src):
         roof = {"bound": "tensor", "kernel": dom, "achieved": d["achieved_tflops"], "peak": bf16, "unit": "TFLOP/s",
                 "frac": d["frac_of_bf16_tensor_peak"], "traffic": traffic, "traffic_source": traffic_file,
                 "peak_source": peak_src,
-                "note": "batch-256 fp32 layer (134 MFLOP, 2.3 MB): latency-bound by construction -- 128 CTAs x 4 K "
-                        "iterations; the reference computes it in fp32, so the kernel runs on the FFMA pipe and the bf16 "
+                "note": "batch-256 fp32 layer (134 MFLOP, 2.3 MB): latency-bound by construction -- 128 CTAs, each fetching its "
+                        "whole K slice at once; the reference computes it in fp32, so the kernel runs on the FFMA pipe and the bf16 "
                         "tensor peak is only the nominal denominator.  Layers from 2e8 FLOP up run on tcgen05 (3xTF32): "
                         "see extras.tc_gemm for their tensor-pipe roofline and extras.per_microbench for the HBM-bound "
                         "PER kernels"}
@@ -509,7 +509,7 @@ def config_rooflines(extras, hbm_gbs, tf32_peak):
                              "us": k["us"], "single_batch_us": pm.get("sample+update_16M_B4096", {}).get("us")}
     k = extras.get("sharded_per_configs3") or pm.get("shard_8M_global_sample+update_B4096")
     if k and "us_per_iteration" in k:
-        out["configs[3]"] = {"kernel": "global_sample_kernel + upd_chain_kernel per 2^23-leaf shard", "bound": "hbm",
+        out["configs[3]"] = {"kernel": "global_sample_kernel + upd_lines_sorted_kernel + tree_rebuild_kernel per 2^23-leaf shard", "bound": "hbm",
                              "achieved": k["achieved_gbs"], "peak": hbm_gbs, "unit": "GB/s",
                              "frac": k.get("frac_of_one_gpu_hbm"), "us": k["us_per_iteration"]}
     r = tc_row("iqn_hidden_32768x512x3136_fwd", "tc_gemm_kernel (IQN hidden layer 32768x512x3136)")

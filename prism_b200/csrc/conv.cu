@@ -97,12 +97,27 @@ __global__ void __launch_bounds__(1024) conv3x3_relu_bwd_kernel(ConvDims d, cons
             if (e < nw) {
                 const int oc = e / (d.C * 9), r = e - oc * d.C * 9, c = r / 9, k = r - c * 9, ky = k / 3, kx = k - ky * 3;
                 const float *g = sg + oc * plane;
-                for (int y = 0; y < d.OH; ++y)
-                    for (int xx = 0; xx < d.OW; ++xx)
-                        a = fmaf(g[y * d.OW + xx], sx[((y + ky) * d.W + (xx + kx)) * d.C + c], a);
+                // four independent FMA chains (one 64-tap dependent chain per element was the kernel's latency)
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                for (int y = 0; y < d.OH; ++y) {
+                    const float *gy = g + y * d.OW, *xy = sx + ((y + ky) * d.W + kx) * d.C + c;
+                    int xx = 0;
+                    for (; xx + 3 < d.OW; xx += 4) {
+                        a0 = fmaf(gy[xx], xy[xx * d.C], a0);
+                        a1 = fmaf(gy[xx + 1], xy[(xx + 1) * d.C], a1);
+                        a2 = fmaf(gy[xx + 2], xy[(xx + 2) * d.C], a2);
+                        a3 = fmaf(gy[xx + 3], xy[(xx + 3) * d.C], a3);
+                    }
+                    for (; xx < d.OW; ++xx) a0 = fmaf(gy[xx], xy[xx * d.C], a0);
+                }
+                a = (a0 + a1) + (a2 + a3);
             } else {
                 const float *g = sg + (e - nw) * plane;
-                for (int p = 0; p < plane; ++p) a += g[p];
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                int p = 0;
+                for (; p + 3 < plane; p += 4) { a0 += g[p]; a1 += g[p + 1]; a2 += g[p + 2]; a3 += g[p + 3]; }
+                for (; p < plane; ++p) a0 += g[p];
+                a = (a0 + a1) + (a2 + a3);
             }
             acc[q] += a;
         }

@@ -52,22 +52,19 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return t;
 }
 
-// Poll a flag in (local) peer-mapped memory until it reaches e: relaxed volatile loads (L2 round trips) in the loop,
-// ONE acquire fence at system scope when the value is there -- an acquire load per iteration costs a system-scope
-// fence each time and delays the detection by as much.  Bounded by timeout_ns (0 = forever); false on a timeout.
+// Poll a flag in (local) peer-mapped memory until it reaches e (acquire loads at system scope; relaxed polls + one
+// fence.acq_rel.sys measured slower: 26 vs 17 us for the fused exchange at 2 GPUs).  Bounded by timeout_ns
+// (0 = forever); false on a timeout.
 __device__ __forceinline__ bool wait_flag_sys(const unsigned long long *p, unsigned long long e, unsigned long long timeout_ns)
 {
-    const volatile unsigned long long *vp = p;
-    bool ok = true;
-    if (*vp < e) {
+    if (ld_acquire_sys(p) < e) {
         const unsigned long long t0 = global_timer_ns();
         unsigned spins = 0;
-        while (*vp < e) {
-            if ((++spins & 1023u) == 0 && timeout_ns && global_timer_ns() - t0 > timeout_ns) { ok = false; break; }
+        while (ld_acquire_sys(p) < e) {
+            if ((++spins & 1023u) == 0 && timeout_ns && global_timer_ns() - t0 > timeout_ns) return false;
         }
     }
-    asm volatile("fence.acq_rel.sys;" ::: "memory");
-    return ok;
+    return true;
 }
 
 // one warp: lane i signals rank i and waits for rank i.  Two independent CHANNELS (own flags, own epoch): calls on

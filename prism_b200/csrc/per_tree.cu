@@ -1347,19 +1347,21 @@ __global__ void __launch_bounds__(256) global_sample_kernel(TreeView t, const pb
     if (pw.flags) {
         const unsigned long long e = *pw.epoch;
         if (threadIdx.x < G) {
-            // relaxed polls, one acquire fence at the end (an acquire load per poll is a system-scope fence per poll)
-            const volatile unsigned long long *f = pw.flags + threadIdx.x;
-            if (*f < e) {
+            const unsigned long long *f = pw.flags + threadIdx.x;
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v < e) {
                 const unsigned long long t0 = global_ns();
                 unsigned spins = 0;
-                while (*f < e) {
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                    if (v >= e) break;
                     if ((++spins & 1023u) == 0 && pw.timeout_ns && global_ns() - t0 > pw.timeout_ns) {
                         if (pw.status) atomicOr(pw.status, 1u << 2);
                         break;
                     }
                 }
             }
-            asm volatile("fence.acq_rel.sys;" ::: "memory");
         }
         __syncthreads();
         all_state = reinterpret_cast<const pb_per_state *>(pw.slots + (size_t)(2 + (e & 1)) * pw.slot_bytes);
