@@ -22,7 +22,9 @@ namespace {
 
 using namespace pb;
 
-constexpr int TM = 64, TN = 64, TK = 32, PAD = 4;   // 2 x (A,B) stages of 32 x 68 floats = 34 KB; C tile aliases them
+constexpr int TM = 64, TN = 64, TK = 32, PAD = 4;   // NS x (A,B) stages of 32 x 68 floats (17 KB each); C tile aliases them
+constexpr int NS = 4;                               // stages: a split's whole K range (<= NS chunks) is fetched at once
+constexpr int GEMM_SMEM = NS * 2 * TK * (TM + PAD) * 4;
 
 struct GemmArgs {
     const float *A, *B, *bias, *mask;
@@ -103,13 +105,18 @@ __device__ __forceinline__ void store_tile(float (*S)[TM + PAD], const float (&r
 }
 
 // C[i][j] = epilogue( sum_seg sum_k A(i,k) B(k,j) )   grid: (n tiles, m tiles * batch, splits); cluster (1,1,splits)
-template <bool A_KMAJOR, bool B_KMAJOR, bool ROWSUM>
-__global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g)
+// FLIGHT: a split's whole K range (3..NS chunks) is fetched before the first chunk is consumed (NS stages of shared
+// memory, 3 CTAs per SM: the step runs three such forward GEMMs -- online, bootstrap x 2 -- on parallel graph branches and
+// all 384 CTAs must stay resident); otherwise the classic two-stage pipeline (4 CTAs per SM: the two backward GEMMs of
+// a layer, 512 CTAs, run side by side).
+template <bool A_KMAJOR, bool B_KMAJOR, bool ROWSUM, bool FLIGHT>
+__global__ void __launch_bounds__(256, FLIGHT ? 3 : 4) gemm_kernel(GemmArgs g)
 {
-    __shared__ __align__(16) float tiles[2 * 2 * TK * (TM + PAD)];
+    extern __shared__ __align__(16) float tiles[];
     __shared__ float Rs[TM];
     float (*As)[TK][TM + PAD] = reinterpret_cast<float (*)[TK][TM + PAD]>(tiles);
-    float (*Bs)[TK][TN + PAD] = reinterpret_cast<float (*)[TK][TN + PAD]>(tiles + 2 * TK * (TM + PAD));
+    constexpr int STAGES = FLIGHT ? NS : 2;
+    float (*Bs)[TK][TN + PAD] = reinterpret_cast<float (*)[TK][TN + PAD]>(tiles + STAGES * TK * (TM + PAD));
     float (*Cs)[TN + PAD] = reinterpret_cast<float (*)[TN + PAD]>(tiles);      // reused once the K loop is over
 
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -127,10 +134,9 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g)
 
     float acc[4][4] = {};
     float rs[4] = {};
-    float ra[2][4], rb[2][4];
     const bool want_rowsum = ROWSUM && g.colsum != nullptr && blockIdx.x == 0;
 
-    auto fetch = [&](int it) {
+    auto fetch = [&](int it, float (&ra)[2][4], float (&rb)[2][4]) {
         const int seg = it / chunks_per_seg, k0 = (it % chunks_per_seg) * TK;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -138,27 +144,19 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g)
             load_tile<B_KMAJOR>(rb[h], B + seg * g.b_ss, nullptr, g.ldb, j0, k0, g.N, g.K, t, h);
         }
     };
-    auto stash = [&](int b) {
+    auto stash = [&](int b, const float (&ra)[2][4], const float (&rb)[2][4]) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             store_tile<A_KMAJOR>(As[b], ra[h], t, h);
             store_tile<B_KMAJOR>(Bs[b], rb[h], t, h);
         }
     };
-    int buf = 0;
-    if (it0 < it1) {
-        fetch(it0);
-        stash(0);
-    }
-    __syncthreads();
-    for (int it = it0; it < it1; ++it) {
-        const bool more = it + 1 < it1;
-        if (more) fetch(it + 1);
+    auto compute = [&](int b) {
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
-            const float4 a = *reinterpret_cast<const float4 *>(&As[buf][k][ty << 2]);
-            const float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx << 2]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            const float4 a = *reinterpret_cast<const float4 *>(&As[b][k][ty << 2]);
+            const float4 bb = *reinterpret_cast<const float4 *>(&Bs[b][k][tx << 2]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
 #pragma unroll
@@ -166,9 +164,39 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g)
                 if (ROWSUM) rs[r] += av[r];
             }
         }
-        if (more) stash(buf ^ 1);
+    };
+    if (FLIGHT) {
+        // the split's whole K range fits the stages: EVERY global load is requested before the first one is consumed
+        // (one memory latency per launch instead of one per chunk -- these layers are latency-, not FLOP-bound),
+        // then one barrier and an uninterrupted FFMA loop
+        float ra[STAGES][2][4], rb[STAGES][2][4];
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            if (it0 + s < it1) fetch(it0 + s, ra[s], rb[s]);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            if (it0 + s < it1) stash(s, ra[s], rb[s]);
         __syncthreads();
-        buf ^= 1;
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            if (it0 + s < it1) compute(s);
+        __syncthreads();                                           // the C tile aliases the stages
+    } else {
+        float ra[2][4], rb[2][4];
+        int buf = 0;
+        if (it0 < it1) {
+            fetch(it0, ra, rb);
+            stash(0, ra, rb);
+        }
+        __syncthreads();
+        for (int it = it0; it < it1; ++it) {
+            const bool more = it + 1 < it1;
+            if (more) fetch(it + 1, ra, rb);
+            compute(buf);
+            if (more) stash(buf ^ 1, ra, rb);
+            __syncthreads();
+            buf ^= 1;
+        }
     }
 
     float *C = g.C + batch * g.c_bs;
@@ -245,6 +273,9 @@ int pick_splits(long long tiles, int total_chunks)
     return s;
 }
 
+template <bool AK, bool BK, bool ROWSUM, bool FLIGHT>
+int launch_gemm_v(GemmArgs g, int batch, int n_tiles, void *stream);
+
 template <bool AK, bool BK, bool ROWSUM>
 int launch_gemm(GemmArgs g, int batch, void *stream)
 {
@@ -252,25 +283,44 @@ int launch_gemm(GemmArgs g, int batch, void *stream)
     const int n_tiles = (g.N + TN - 1) / TN;
     const int total_chunks = g.n_seg * ((g.K + TK - 1) / TK);
     g.splits = pick_splits((long long)g.m_tiles * n_tiles * batch, total_chunks);
+    const int per = (total_chunks + g.splits - 1) / g.splits;      // chunks per split
+    static int flight_ok = -1;                                     // PB_GEMM_FLIGHT=0: two-stage pipeline everywhere
+    if (flight_ok < 0) { const char *e = getenv("PB_GEMM_FLIGHT"); flight_ok = (e && e[0] == '0') ? 0 : 1; }
+    if (flight_ok && per >= 3 && per <= NS) return launch_gemm_v<AK, BK, ROWSUM, true>(g, batch, n_tiles, stream);
+    return launch_gemm_v<AK, BK, ROWSUM, false>(g, batch, n_tiles, stream);
+}
+
+template <bool AK, bool BK, bool ROWSUM, bool FLIGHT>
+int launch_gemm_v(GemmArgs g, int batch, int n_tiles, void *stream)
+{
+    constexpr int SMEM = (FLIGHT ? NS : 2) * 2 * TK * (TM + PAD) * 4;
     if (g.splits > 8) {
         static PbPerDeviceOnce allowed;             // one flag per template instantiation
         if (!allowed.done()) {
-            cudaError_t ea = cudaFuncSetAttribute(gemm_kernel<AK, BK, ROWSUM>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            cudaError_t ea = cudaFuncSetAttribute(gemm_kernel<AK, BK, ROWSUM, FLIGHT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             if (ea != cudaSuccess) return (int)ea;
             allowed.mark();
+        }
+    }
+    {
+        static PbPerDeviceOnce smem_set;            // one flag per template instantiation
+        if (!smem_set.done()) {
+            cudaError_t es = cudaFuncSetAttribute(gemm_kernel<AK, BK, ROWSUM, FLIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+            if (es != cudaSuccess) return (int)es;
+            smem_set.mark();
         }
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n_tiles, (unsigned)(g.m_tiles * batch), (unsigned)g.splits);
     cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = SMEM;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)g.splits;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<AK, BK, ROWSUM>, g);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<AK, BK, ROWSUM, FLIGHT>, g);
     g_pb_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return (int)e;
     e = cudaGetLastError();

@@ -80,14 +80,16 @@ __global__ void __launch_bounds__(256) narrow_fwd_kernel(long long M, int N, int
     }
 }
 
-// backward: thread t owns input columns 2t, 2t+1 (blockDim = J/2); rows are staged 32 at a time.
+// backward: thread t owns input columns 2t, 2t+1 (blockDim = J/2); rows are staged rpc (<= 32) at a time -- 32 for the
+// (T*B)-row IQN layers (few partials), 4 at learner-batch sizes (a 256-row layer on 8 CTAs of 32 serial rows each was
+// 11 us of pure load latency on the step's critical path).
 //   dx[m][j]  = sum_n dy[m][n] W[n][j]          (W column pair in registers)
 //   dWp[cta][n][j] = sum_{m in cta} dy[m][n] x[m][j],  dbp[cta][n] = sum_{m in cta} dy[m][n]
 template <int NP>
 __global__ void __launch_bounds__(512) narrow_bwd_kernel(long long M, int N, int J, const float *__restrict__ x,
                                                          long long x_hs, const float *__restrict__ w,
                                                          const float *__restrict__ dy, float *__restrict__ dx,
-                                                         float *__restrict__ dWp, float *__restrict__ dbp)
+                                                         float *__restrict__ dWp, float *__restrict__ dbp, int rpc)
 {
     __shared__ float sdy[32 * NP];
     // grid.y = heads (dx is per head: (K, M, J); the caller sums it over the heads when they share x)
@@ -105,30 +107,37 @@ __global__ void __launch_bounds__(512) narrow_bwd_kernel(long long M, int N, int
         acc[n] = make_float2(0.f, 0.f);
     }
     float db = 0.0f;
-    const long long chunks = (M + 31) / 32;
+    const long long chunks = (M + rpc - 1) / rpc;
     for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
-        const long long m0 = ch * 32;
-        const int rows = (int)((M - m0) < 32 ? (M - m0) : 32);
+        const long long m0 = ch * rpc;
+        const int rows = (int)((M - m0) < rpc ? (M - m0) : rpc);
         __syncthreads();
-        for (int e = t; e < 32 * NP; e += blockDim.x) {
+        for (int e = t; e < rpc * NP; e += blockDim.x) {
             const int r = e / NP, n = e - r * NP;
             sdy[e] = (r < rows && n < N) ? dy[(m0 + r) * N + n] : 0.0f;
         }
         __syncthreads();
         if (t < NP) {
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) db += sdy[r * NP + t];
+            for (int r = 0; r < rows; ++r) db += sdy[r * NP + t];
         }
-        for (int r = 0; r < rows; ++r) {
-            const float2 xv = *reinterpret_cast<const float2 *>(x + (size_t)(m0 + r) * J + j);
-            float2 d = make_float2(0.f, 0.f);
+        for (int r0 = 0; r0 < rows; r0 += 4) {                      // four rows' loads in flight
+            float2 xv[4];
 #pragma unroll
-            for (int n = 0; n < NP; ++n) {
-                const float g = sdy[r * NP + n];
-                d.x += g * wr[n].x; d.y += g * wr[n].y;
-                acc[n].x += g * xv.x; acc[n].y += g * xv.y;
+            for (int u = 0; u < 4; ++u)
+                xv[u] = r0 + u < rows ? *reinterpret_cast<const float2 *>(x + (size_t)(m0 + r0 + u) * J + j) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u;
+                if (r >= rows) break;
+                float2 d = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int n = 0; n < NP; ++n) {
+                    const float g = sdy[r * NP + n];
+                    d.x += g * wr[n].x; d.y += g * wr[n].y;
+                    acc[n].x += g * xv[u].x; acc[n].y += g * xv[u].y;
+                }
+                if (dx) *reinterpret_cast<float2 *>(dx + (size_t)(m0 + r) * J + j) = d;
             }
-            if (dx) *reinterpret_cast<float2 *>(dx + (size_t)(m0 + r) * J + j) = d;
         }
     }
     if (dWp) {
@@ -218,9 +227,12 @@ int pb_narrow_linear_supported(long long M, int N, int J)
     return 1;
 }
 
+static int narrow_rpc(long long M) { return M <= 2048 ? 4 : 32; }
+
 int pb_narrow_linear_bwd_blocks(long long M)
 {
-    long long nb = (M + 31) / 32;
+    const int rpc = narrow_rpc(M);
+    long long nb = (M + rpc - 1) / rpc;
     const long long cap = (long long)pb_sm_count() * 2;
     if (nb > cap) nb = cap;
     return (int)(nb < 1 ? 1 : nb);
@@ -271,14 +283,15 @@ int pb_narrow_linear_bwd(int K, long long M, int N, int J, const float *x, long 
     if ((dW || db) && !partials) return PB_E_ARG;
     if ((((uintptr_t)x) | ((uintptr_t)w) | ((uintptr_t)dx) | ((uintptr_t)partials)) & 7) return PB_E_ARG;
     const int nb = pb_narrow_linear_bwd_blocks(M);
+    const int rpc = narrow_rpc(M);
     float *dWp = (dW || db) ? partials : nullptr;
     float *dbp = (dW || db) ? partials + (size_t)K * nb * N * J : nullptr;
     const dim3 grid((unsigned)nb, (unsigned)K);
     switch (narrow_np(N)) {
-        case 4: PB_LAUNCH(narrow_bwd_kernel<4>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp); break;
-        case 8: PB_LAUNCH(narrow_bwd_kernel<8>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp); break;
-        case 16: PB_LAUNCH(narrow_bwd_kernel<16>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp); break;
-        default: PB_LAUNCH(narrow_bwd_kernel<32>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp); break;
+        case 4: PB_LAUNCH(narrow_bwd_kernel<4>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp, rpc); break;
+        case 8: PB_LAUNCH(narrow_bwd_kernel<8>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp, rpc); break;
+        case 16: PB_LAUNCH(narrow_bwd_kernel<16>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp, rpc); break;
+        default: PB_LAUNCH(narrow_bwd_kernel<32>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp, rpc); break;
     }
     if (dW) {
         const long long n = (long long)N * J;

@@ -744,46 +744,35 @@ __global__ void __launch_bounds__(LT_THREADS) upd_lines_tagged_kernel(TreeView t
     if (j < n) i = entry_index(t, idx, j, mode, mode == MODE_EXTEND ? t.st->seq : 0);
     const bool live = i >= 0 && i < t.size;
     const long long line = live ? i >> 5 : 0;
-    float4 xf[8];
-    warp_fetch_lines_raw(leaf, line, wbuf_all + (threadIdx.x >> 5) * 256, xf);     // the warp's 32 lines, fetched together
+    float4 v[8];                                                  // the line; NaN-tagged slots carry entry numbers
+    warp_fetch_lines_raw(leaf, line, wbuf_all + (threadIdx.x >> 5) * 256, v);      // the warp's 32 lines, fetched together
     if (live) {
-        int4 x[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            x[k] = make_int4(__float_as_int(xf[k].x), __float_as_int(xf[k].y), __float_as_int(xf[k].z), __float_as_int(xf[k].w));
         unsigned tagged = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            tagged |= (x[k].x >= LEAF_TAG ? 1u : 0u) << (4 * k);
-            tagged |= (x[k].y >= LEAF_TAG ? 1u : 0u) << (4 * k + 1);
-            tagged |= (x[k].z >= LEAF_TAG ? 1u : 0u) << (4 * k + 2);
-            tagged |= (x[k].w >= LEAF_TAG ? 1u : 0u) << (4 * k + 3);
+            tagged |= (__float_as_int(v[k].x) >= LEAF_TAG ? 1u : 0u) << (4 * k);
+            tagged |= (__float_as_int(v[k].y) >= LEAF_TAG ? 1u : 0u) << (4 * k + 1);
+            tagged |= (__float_as_int(v[k].z) >= LEAF_TAG ? 1u : 0u) << (4 * k + 2);
+            tagged |= (__float_as_int(v[k].w) >= LEAF_TAG ? 1u : 0u) << (4 * k + 3);
         }
+        // the slot at dynamic position p of the register copy (32 selects)
+        auto slot = [&](int p) {
+            float r = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                r = p == 4 * k ? v[k].x : r;
+                r = p == 4 * k + 1 ? v[k].y : r;
+                r = p == 4 * k + 2 ? v[k].z : r;
+                r = p == 4 * k + 3 ? v[k].w : r;
+            }
+            return r;
+        };
         const int p0 = __ffs(tagged) - 1;                         // -1: everything resolved already
-        int first = 0;                                            // the tag in the lowest tagged slot
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            first = p0 == 4 * k ? x[k].x : first;
-            first = p0 == 4 * k + 1 ? x[k].y : first;
-            first = p0 == 4 * k + 2 ? x[k].z : first;
-            first = p0 == 4 * k + 3 ? x[k].w : first;
-        }
-        if (p0 >= 0 && first == LEAF_TAG + (int)j) {
-            float4 v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                v[k] = make_float4(__int_as_float(x[k].x), __int_as_float(x[k].y), __int_as_float(x[k].z), __int_as_float(x[k].w));
+        if (p0 >= 0 && __float_as_int(slot(p0)) == LEAF_TAG + (int)j) {       // my tag sits in the lowest tagged slot: leader
             while (tagged) {                                      // one or two per line; ONE copy of the entry code
                 const int pos = __ffs(tagged) - 1;
                 tagged &= tagged - 1;
-                int tag = first;                                  // the tag this thread SAW in slot pos (its snapshot)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    tag = pos == 4 * k ? x[k].x : tag;
-                    tag = pos == 4 * k + 1 ? x[k].y : tag;
-                    tag = pos == 4 * k + 2 ? x[k].z : tag;
-                    tag = pos == 4 * k + 3 ? x[k].w : tag;
-                }
+                const int tag = __float_as_int(slot(pos));        // the tag this thread SAW in slot pos (its snapshot)
                 const float nv = entry_leaf(t, val, (long long)(tag - LEAF_TAG), mode, defp);
                 leaf[(line << 5) + pos] = nv;
 #pragma unroll
@@ -938,9 +927,13 @@ __device__ __forceinline__ float is_weight(float leaf, float p_min, float beta, 
 {
     float denom = t.weps ? __fadd_rn(p_min, t.eps32) : p_min;
     float ratio = __fdiv_rn(leaf, denom);
-    // np.power(fp32, -beta) -> libm powf (< 1 ulp); evaluate in double and round once (beta = 0.5, the value the learner
-    // forces, learner.py:105-107: 1 / sqrt in double, same rounding, a fifth of the instructions)
-    if (beta == 0.5f) return (float)__ddiv_rn(1.0, __dsqrt_rn((double)ratio));
+    // np.power(fp32, -beta) -> libm powf (< 1 ulp).  beta = 0.5 (the value the learner forces, learner.py:105-107):
+    // hardware rsqrt + one Newton step in fp32 -- within 2 ulp of powf (the parity bar on IS weights is 1e-6 relative;
+    // tests/test_gpu_per.py), a tenth of the instructions of the fp64 evaluation that every other beta takes.
+    if (beta == 0.5f) {
+        const float y = rsqrtf(ratio);
+        return y * fmaf(-0.5f * ratio * y, y, 1.5f);
+    }
     return (float)pow_cold((double)ratio, -(double)beta);
 }
 
@@ -1078,8 +1071,12 @@ __device__ __forceinline__ void warp_fetch_lines(const float *__restrict__ lvl, 
     }
 }
 
-// one line (32 nodes of a stored level, children of `node`) in registers: go right and subtract iff mass > left, 5 times
-__device__ __forceinline__ void thread_line_descend(const float (&v)[32], long long &node, float &m, float &leaf)
+// one line (32 nodes of a stored level, children of `node`): go right and subtract iff mass > left, 5 times.  The three
+// upper levels come from tree-order sums in registers (v: the line); the two lower ones from ONE 128-bit read of the
+// line's copy that warp_fetch_lines left in shared memory (row: this lane's 8 swizzled chunks) -- a dynamic index is a
+// shared-memory address, not a cascade of 37 selects.
+__device__ __forceinline__ void thread_line_descend(const float (&v)[32], const float4 *row, long long &node, float &m,
+                                                    float &leaf)
 {
     float t16[16], t8[8], t4[4], t2[2];
 #pragma unroll
@@ -1102,27 +1099,12 @@ __device__ __forceinline__ void thread_line_descend(const float (&v)[32], long l
     }
     pos <<= 1;
     if (m > l) { m = __fsub_rn(m, l); pos |= 1; }
-    {   // t16[2 pos], pos in 0..7
-        const float a0 = (pos & 1) ? t16[2] : t16[0], a1 = (pos & 1) ? t16[6] : t16[4];
-        const float a2 = (pos & 1) ? t16[10] : t16[8], a3 = (pos & 1) ? t16[14] : t16[12];
-        const float b0 = (pos & 2) ? a1 : a0, b1 = (pos & 2) ? a3 : a2;
-        l = (pos & 4) ? b1 : b0;
-    }
+    // pos in 0..7 names the 128-bit chunk {v[4 pos] .. v[4 pos + 3]}: its two pairs are the last two levels
+    const float4 c = row[pos ^ (lane_id() & 7)];
+    l = op_sum(c.x, c.y);                                         // == t16[2 pos]
+    float lo = c.x, hi = c.y;
     pos <<= 1;
-    if (m > l) { m = __fsub_rn(m, l); pos |= 1; }
-    float lo, hi;                                                 // v[2 pos], v[2 pos + 1], pos in 0..15
-    {
-        float e[8], o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { e[i] = (pos & 1) ? v[4 * i + 2] : v[4 * i]; o[i] = (pos & 1) ? v[4 * i + 3] : v[4 * i + 1]; }
-        float e2[4], o2[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { e2[i] = (pos & 2) ? e[2 * i + 1] : e[2 * i]; o2[i] = (pos & 2) ? o[2 * i + 1] : o[2 * i]; }
-        const float e3a = (pos & 4) ? e2[1] : e2[0], e3b = (pos & 4) ? e2[3] : e2[2];
-        const float o3a = (pos & 4) ? o2[1] : o2[0], o3b = (pos & 4) ? o2[3] : o2[2];
-        lo = (pos & 8) ? e3b : e3a;
-        hi = (pos & 8) ? o3b : o3a;
-    }
+    if (m > l) { m = __fsub_rn(m, l); pos |= 1; lo = c.z; hi = c.w; }
     pos <<= 1;
     leaf = lo;
     if (m > lo) { m = __fsub_rn(m, lo); pos |= 1; leaf = hi; }
@@ -1222,7 +1204,7 @@ __global__ void __launch_bounds__(ST_THREADS) tree_sample_thread_kernel(TreeView
         for (int s = S + 5; s <= t.L; s += 5) {
             float v[32];
             warp_fetch_lines(sum_level(t, s), node, wbuf, v);
-            thread_line_descend(v, node, m, leafv);
+            thread_line_descend(v, wbuf + (threadIdx.x & 31) * 8, node, m, leafv);
         }
         if (live) {
             long long i = over ? t.size : node;

@@ -688,7 +688,7 @@ int pick_bk(int bn, int K)
     return (bn == 256 && K >= 256) ? 16 : 32;    // 4 x 48 KB stages instead of 2 x 96 KB once the K loop is long
 }
 
-constexpr int TC_CHAIN_FLOATS = 1024;
+constexpr int TC_CHAIN_FLOATS = 2048;
 
 // modelled cost (SM clocks) of one K block and one epilogue at tile width bn: the MMA time and the shared-memory
 // traffic (12 operand reads + the split pass) whichever is larger -- see DESIGN.md section 4
@@ -775,7 +775,9 @@ int pb_tc_gemm(int batch, int kbatches, int M, int N, int K,
         g.per_cta = ((tiles + grid - 1) / grid) * kb_total;
     }
     grid = (g.work + g.per_cta - 1) / g.per_cta;
-    // accumulation chains of at most ~1024 floats of K once a tile's K loop is twice that (see SegIter)
+    // accumulation chains of at most ~2048 floats of K once a tile's K loop is twice that (see SegIter): the K = 32768
+    // weight gradients; the K = 3136 forward / input-gradient GEMMs keep one chain (their drift, ~3e-5 worst case,
+    // is inside the 1e-4 parity bar, and chunking them costs 18 % of their time)
     if ((long long)kb_total * bk >= 2 * TC_CHAIN_FLOATS && workspace &&
         SLOTS_PER_CTA * grid * BM * best_bn <= workspace_floats)
         g.kc = TC_CHAIN_FLOATS / bk;

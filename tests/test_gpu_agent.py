@@ -361,9 +361,9 @@ def test_tc_gemm_matches_fp64(batch, kbatches, M, N, K, a_major, b_major, act, s
 def test_tc_gemm_long_k_chains_do_not_drift(M, N, K, a_major, b_major):
     """The tensor core accumulates with truncation: one chain of K / 8 * 3 MMAs over same-signed products drifts by
     ~7e-4 at K = 32768 (the configs[4] weight gradient: dW = dZ^T X over 32768 rows) -- measured -4.2e-5 per 2048 floats
-    of K.  pb_tc_gemm caps a chain at 1024 floats of K and adds the chunks in round-to-nearest fp32 (csrc/tc_gemm.cu,
-    SegIter): 3e-5 on operands whose products all have the same sign, the worst case for a truncating adder (mixed
-    signs, as in the layers' real operands, sit below the 2e-5 of the short-K tests)."""
+    of K.  pb_tc_gemm caps a chain at 2048 floats of K (once K >= 4096) and adds the chunks in round-to-nearest fp32
+    (csrc/tc_gemm.cu, SegIter): 6e-5 on operands whose products all have the same sign, the worst case for a truncating
+    adder (mixed signs, as in the layers' real operands, sit below the 2e-5 of the short-K tests)."""
     from prism_b200.agents import ops
     g = torch.Generator().manual_seed(M + N + K)
     a = torch.randn((1, K, M) if a_major else (1, M, K), generator=g).abs_()
@@ -376,7 +376,7 @@ def test_tc_gemm_long_k_chains_do_not_drift(M, N, K, a_major, b_major):
     ref = torch.bmm(al, bl.transpose(1, 2))
     err = (out.cpu().double() - ref) / ref.abs().max()
     print("long-K chain: max |err| %.2e, mean signed err %.2e" % (float(err.abs().max()), float(err.mean())))
-    assert float(err.abs().max()) < 3e-5
+    assert float(err.abs().max()) < 6e-5
 
 
 @pytest.mark.parametrize("M,N,K,rows", [(2048, 1024, 64, 64), (640, 328, 64, 10), (384, 18, 512, 384)])
