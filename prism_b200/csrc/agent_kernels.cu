@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(128) ens_loss_kernel(int B, int A, int K, cons
                                                        const float *__restrict__ row_weight, float grad_scale,
                                                        float *__restrict__ loss_out, float *__restrict__ grad_q)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int b = blockIdx.x * (blockDim.x >> 5) + warp;
     if (b >= B) return;
@@ -213,6 +215,8 @@ __global__ void __launch_bounds__(1024) loss_combine_kernel(int B, const float *
                                                             float q_scale, const float *__restrict__ q_offset,
                                                             float *__restrict__ total_out, float *__restrict__ td_out)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     __shared__ float part[32];
     float acc = 0.0f;
     const float off = q_offset ? *q_offset : 0.0f;
@@ -250,6 +254,8 @@ __global__ void __launch_bounds__(ADAM_THREADS) pack_grads_kernel(const long lon
                                                                   long long stride, float *__restrict__ partial,
                                                                   long long *__restrict__ step_count)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     __shared__ double part[ADAM_THREADS / 32];
     if (epoch) flat += (long long)(*epoch & 1ull) * stride;      // double-buffered arena of the peer exchange
     const int t = blockIdx.y;
@@ -335,6 +341,8 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_clip_kernel(long long n, fl
                                                                  float max_grad_norm, const float *__restrict__ partial,
                                                                  int n_partials, float *__restrict__ norm_out)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     __shared__ double red[ADAM_THREADS / 32];
     __shared__ float s_coef;
     double acc = 0.0;
@@ -425,7 +433,7 @@ int pb_ens_q_loss(int B, int A, int K, const float *q_cur, const float *q_next_o
     if (B == 0) return PB_OK;
     if (!q_cur || !q_next_online || !q_next_target || !action || !ret || !gdn || !loss_out || !grad_q_cur)
         return PB_E_ARG;
-    PB_LAUNCH(ens_loss_kernel, (unsigned)((B + 3) / 4), 128, 0, stream, B, A, K, q_cur, q_next_online, q_next_target,
+    PB_LAUNCH_PDL_CHAIN(ens_loss_kernel, (unsigned)((B + 3) / 4), 128, 0, stream, B, A, K, q_cur, q_next_online, q_next_target,
               action, ret, gdn, nonterminal, loss_weight, row_weight, grad_scale, loss_out, grad_q_cur);
     return PB_OK;
 }
@@ -456,7 +464,7 @@ int pb_loss_combine(int B, const float *dist, const float *q, const float *w, fl
                     float *total_out, float *td_out, void *stream)
 {
     if (B <= 0 || (!dist && !q)) return PB_E_ARG;
-    PB_LAUNCH(loss_combine_kernel, 1, 1024, 0, stream, B, dist, q, w, q_scale, q_offset, total_out, td_out);
+    PB_LAUNCH_PDL_CHAIN(loss_combine_kernel, 1, 1024, 0, stream, B, dist, q, w, q_scale, q_offset, total_out, td_out);
     return PB_OK;
 }
 
@@ -479,7 +487,7 @@ int pb_pack_grads_parity(int n_tensors, const long long *table, float scale, flo
     if (per > 128) per = 128;
     if (per < PACK_BLOCKS_PER_TENSOR) per = PACK_BLOCKS_PER_TENSOR;
     dim3 grid((unsigned)per, (unsigned)n_tensors);
-    PB_LAUNCH(pack_grads_kernel, grid, ADAM_THREADS, 0, stream, table, scale, flat, epoch, stride, partial_scratch,
+    PB_LAUNCH_PDL_CHAIN(pack_grads_kernel, grid, ADAM_THREADS, 0, stream, table, scale, flat, epoch, stride, partial_scratch,
               step_count);
     if (n_partials_out_h) *n_partials_out_h = n_tensors * per;
     return PB_OK;
@@ -512,7 +520,7 @@ int pb_adam_clip_apply(long long n, float *param, const float *grad, float *exp_
     if (nb < 1) nb = 1;
     const long long cap = (long long)pb_sm_count() * 4;
     if (nb > cap) nb = cap;
-    PB_LAUNCH(adam_clip_kernel, (unsigned)nb, ADAM_THREADS, 0, stream, n, param, grad, exp_avg, exp_avg_sq, step_count,
+    PB_LAUNCH_PDL_CHAIN(adam_clip_kernel, (unsigned)nb, ADAM_THREADS, 0, stream, n, param, grad, exp_avg, exp_avg_sq, step_count,
               lr, beta1, beta2, adam_eps, max_grad_norm, partial_scratch, n_partials, norm_out);
     return PB_OK;
 }

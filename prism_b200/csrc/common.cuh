@@ -22,8 +22,13 @@ extern std::atomic<long long> g_pb_launches;
 // graph branch it is captured on) is still running; it must call pb::pdl_wait() before touching anything the
 // predecessor wrote.  Chains of short dependent kernels (the priority store's sample -> mark -> lines -> rebuild) save
 // the launch latency at every boundary.  PB_NO_PDL=1 launches them the ordinary way.
+// Two groups: the priority-store kernels (PB_LAUNCH_PDL; on by default) and the kernels of the agent's update chain
+// (PB_LAUNCH_PDL_CHAIN; OFF by default: measured -- a dependent kernel that is resident early holds SM slots while it
+// waits, and in the step graph those slots belong to the GEMMs of the parallel branches: 86.8 vs 83.8 us per step).
+// PB_PDL=all | per | none selects; PB_NO_PDL=1 is "none".
 bool pb_pdl_enabled();
-#define PB_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                               \
+bool pb_pdl_chain_enabled();
+#define PB_LAUNCH_PDL_IF(enabled, kernel, grid, block, smem, stream, ...)                   \
     do {                                                                                    \
         cudaLaunchConfig_t pb_cfg_ = {};                                                    \
         pb_cfg_.gridDim = dim3(grid); pb_cfg_.blockDim = dim3(block);                       \
@@ -31,11 +36,15 @@ bool pb_pdl_enabled();
         cudaLaunchAttribute pb_at_[1];                                                      \
         pb_at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                  \
         pb_at_[0].val.programmaticStreamSerializationAllowed = 1;                           \
-        pb_cfg_.attrs = pb_at_; pb_cfg_.numAttrs = pb_pdl_enabled() ? 1 : 0;                \
+        pb_cfg_.attrs = pb_at_; pb_cfg_.numAttrs = (enabled) ? 1 : 0;                       \
         cudaError_t pb_e_ = cudaLaunchKernelEx(&pb_cfg_, kernel, __VA_ARGS__);              \
         g_pb_launches.fetch_add(1, std::memory_order_relaxed);                              \
         if (pb_e_ != cudaSuccess) return (int)pb_e_;                                        \
     } while (0)
+#define PB_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                               \
+    PB_LAUNCH_PDL_IF(pb_pdl_enabled(), kernel, grid, block, smem, stream, __VA_ARGS__)
+#define PB_LAUNCH_PDL_CHAIN(kernel, grid, block, smem, stream, ...)                         \
+    PB_LAUNCH_PDL_IF(pb_pdl_chain_enabled(), kernel, grid, block, smem, stream, __VA_ARGS__)
 
 static inline int pb_ilog2(long long v) { int l = 0; while ((1LL << l) < v) ++l; return l; }
 static inline bool pb_is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }

@@ -30,15 +30,33 @@ __global__ void __launch_bounds__(256) conv3x3_relu_fwd_kernel(ConvDims d, const
                                                                const float *__restrict__ w,
                                                                const float *__restrict__ bias, float *__restrict__ out)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     extern __shared__ __align__(16) float sm[];
     const int nx = d.H * d.W * d.C, ocp = (d.OC + OCG - 1) / OCG * OCG, taps = d.C * 9;
     float *sw = sm, *sx = sm + taps * ocp;               // sw first: keeps it 16-byte aligned
     const int b = blockIdx.x;
     const float *xb = x + (size_t)b * nx;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) sx[i] = xb[i];
-    for (int i = threadIdx.x; i < taps * ocp; i += blockDim.x) {
-        const int tap = i / ocp, oc = i - tap * ocp;     // tap = c*9 + ky*3 + kx
-        sw[i] = oc < d.OC ? w[oc * taps + tap] : 0.0f;
+    // staging with every global load requested before the first shared-memory store (a load -> store loop of up to 7
+    // dependent round trips per thread was a third of this kernel)
+    {
+        const int nwp = taps * ocp;
+        for (int i0 = threadIdx.x; i0 < nx || i0 < nwp; i0 += 8 * blockDim.x) {
+            float fx[8], fw[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * blockDim.x;
+                fx[u] = i < nx ? xb[i] : 0.0f;
+                const int tap = i / ocp, oc = i - tap * ocp;     // tap = c*9 + ky*3 + kx
+                fw[u] = (i < nwp && oc < d.OC) ? w[oc * taps + tap] : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < nx) sx[i] = fx[u];
+                if (i < nwp) sw[i] = fw[u];
+            }
+        }
     }
     __syncthreads();
     const int plane = d.OH * d.OW, groups = ocp / OCG;
@@ -69,16 +87,22 @@ __global__ void __launch_bounds__(256) conv3x3_relu_fwd_kernel(ConvDims d, const
     }
 }
 
-// partial[g][e], e in [0, OC*C*9) = dW, e in [OC*C*9, OC*C*9+OC) = db, for the samples of CTA g
-__global__ void __launch_bounds__(1024) conv3x3_relu_bwd_kernel(ConvDims d, const float *__restrict__ x,
+// partial[g][e], e in [0, OC*C*9) = dW, e in [OC*C*9, OC*C*9+OC) = db, for the samples of CTA g.
+// Thread -> (tap, output channel) with the CHANNEL fastest, and the masked output gradient staged position-major
+// ([p][oc]): the threads of a warp read consecutive words of the gradient and one or two broadcast words of the frame per
+// tap -- both shared-memory reads of the inner FMA are conflict-free (element-major threads over a channel-major
+// gradient strided the frame reads by 6 and 60 words: 17 us on the step's critical path).
+__global__ void __launch_bounds__(512) conv3x3_relu_bwd_kernel(ConvDims d, const float *__restrict__ x,
                                                                const float *__restrict__ out,
                                                                const float *__restrict__ dout,
                                                                float *__restrict__ partial)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     extern __shared__ float sm[];
     const int nx = d.H * d.W * d.C, plane = d.OH * d.OW, n_out = d.OC * plane;
-    float *sx = sm, *sg = sm + nx;
-    const int nw = d.OC * d.C * 9, ne = nw + d.OC;
+    float *sx = sm, *sg = sm + nx;                           // sg[p * OC + oc]
+    const int taps = d.C * 9, nw = d.OC * taps, ne = nw + d.OC;
     float acc[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[q] = 0.0f;
@@ -87,45 +111,49 @@ __global__ void __launch_bounds__(1024) conv3x3_relu_bwd_kernel(ConvDims d, cons
         const float *xb = x + (size_t)b * nx;
         for (int i = threadIdx.x; i < nx; i += blockDim.x) sx[i] = xb[i];
         const float *ob = out + (size_t)b * n_out, *gb = dout + (size_t)b * n_out;
-        for (int i = threadIdx.x; i < n_out; i += blockDim.x) sg[i] = ob[i] > 0.0f ? gb[i] : 0.0f;   // ReLU mask
+        for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
+            const int oc = i / plane, p = i - oc * plane;
+            sg[p * d.OC + oc] = ob[i] > 0.0f ? gb[i] : 0.0f;  // ReLU mask
+        }
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const int e = threadIdx.x + q * blockDim.x;
-            if (e >= ne) break;
-            float a = 0.0f;
-            if (e < nw) {
-                const int oc = e / (d.C * 9), r = e - oc * d.C * 9, c = r / 9, k = r - c * 9, ky = k / 3, kx = k - ky * 3;
-                const float *g = sg + oc * plane;
-                // four independent FMA chains (one 64-tap dependent chain per element was the kernel's latency)
-                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            const int u = threadIdx.x + q * blockDim.x;      // u = tap * OC + oc for the weights, nw + oc for the bias
+            if (u >= ne) break;
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            if (u < nw) {
+                const int tap = u / d.OC, oc = u - tap * d.OC, c = tap / 9, k = tap - c * 9, ky = k / 3, kx = k - ky * 3;
+                const float *g = sg + oc;
                 for (int y = 0; y < d.OH; ++y) {
-                    const float *gy = g + y * d.OW, *xy = sx + ((y + ky) * d.W + kx) * d.C + c;
+                    const float *gy = g + y * d.OW * d.OC, *xy = sx + ((y + ky) * d.W + kx) * d.C + c;
                     int xx = 0;
                     for (; xx + 3 < d.OW; xx += 4) {
-                        a0 = fmaf(gy[xx], xy[xx * d.C], a0);
-                        a1 = fmaf(gy[xx + 1], xy[(xx + 1) * d.C], a1);
-                        a2 = fmaf(gy[xx + 2], xy[(xx + 2) * d.C], a2);
-                        a3 = fmaf(gy[xx + 3], xy[(xx + 3) * d.C], a3);
+                        a0 = fmaf(gy[xx * d.OC], xy[xx * d.C], a0);
+                        a1 = fmaf(gy[(xx + 1) * d.OC], xy[(xx + 1) * d.C], a1);
+                        a2 = fmaf(gy[(xx + 2) * d.OC], xy[(xx + 2) * d.C], a2);
+                        a3 = fmaf(gy[(xx + 3) * d.OC], xy[(xx + 3) * d.C], a3);
                     }
-                    for (; xx < d.OW; ++xx) a0 = fmaf(gy[xx], xy[xx * d.C], a0);
+                    for (; xx < d.OW; ++xx) a0 = fmaf(gy[xx * d.OC], xy[xx * d.C], a0);
                 }
-                a = (a0 + a1) + (a2 + a3);
             } else {
-                const float *g = sg + (e - nw) * plane;
-                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                const float *g = sg + (u - nw);
                 int p = 0;
-                for (; p + 3 < plane; p += 4) { a0 += g[p]; a1 += g[p + 1]; a2 += g[p + 2]; a3 += g[p + 3]; }
-                for (; p < plane; ++p) a0 += g[p];
-                a = (a0 + a1) + (a2 + a3);
+                for (; p + 3 < plane; p += 4) {
+                    a0 += g[p * d.OC]; a1 += g[(p + 1) * d.OC]; a2 += g[(p + 2) * d.OC]; a3 += g[(p + 3) * d.OC];
+                }
+                for (; p < plane; ++p) a0 += g[p * d.OC];
             }
-            acc[q] += a;
+            acc[q] += (a0 + a1) + (a2 + a3);
         }
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const int e = threadIdx.x + q * blockDim.x;
-        if (e < ne) partial[(size_t)blockIdx.x * ne + e] = acc[q];
+        const int u = threadIdx.x + q * blockDim.x;
+        if (u >= ne) break;
+        // back to the weight layout (OC, C, 3, 3): e = oc * taps + tap
+        int e = u;
+        if (u < nw) { const int tap = u / d.OC, oc = u - tap * d.OC; e = oc * taps + tap; }
+        partial[(size_t)blockIdx.x * ne + e] = acc[q];
     }
 }
 
@@ -134,6 +162,8 @@ __global__ void __launch_bounds__(256) conv_bwd_reduce_kernel(int n_groups, int 
                                                               const float *__restrict__ partial,
                                                               float *__restrict__ dw, float *__restrict__ db)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, ne = nw + n_bias;
     if (e >= ne) return;
     float a = 0.0f;
@@ -168,7 +198,7 @@ int pb_conv3x3_relu_fwd(int B, int H, int W, int C, int OC, const float *x, cons
     if (smem > 48 * 1024) return PB_E_UNSUPPORTED;
     const int items = d.OH * d.OW * (ocp / 8);
     const int threads = items >= 256 ? 256 : (items + 31) / 32 * 32;
-    PB_LAUNCH(conv3x3_relu_fwd_kernel, (unsigned)B, threads, smem, stream, d, x, w, bias, out);
+    PB_LAUNCH_PDL_CHAIN(conv3x3_relu_fwd_kernel, (unsigned)B, threads, smem, stream, d, x, w, bias, out);
     return PB_OK;
 }
 
@@ -184,13 +214,13 @@ int pb_conv3x3_relu_bwd(int B, int H, int W, int C, int OC, const float *x, cons
     const int groups = pb_conv3x3_relu_bwd_groups(B);
     const size_t smem = sizeof(float) * (size_t)(H * W * C + OC * d.OH * d.OW);
     if (smem > 48 * 1024) return PB_E_UNSUPPORTED;
-    // one gradient element per thread when they fit (880 for the MinAtar embedding): the 64-tap dependent FMA chain
-    // per element is the kernel's latency
+    // two gradient elements per thread for the MinAtar embedding (880 elements, 512 threads): several CTAs per SM, so
+    // one CTA's staging loads overlap another's FMA loop and the 256 per-sample CTAs are resident in one wave
     const int ne_all = OC * C * 9 + OC;
-    const int bthreads = ne_all > 512 ? 1024 : (ne_all > 256 ? 512 : 256);
-    PB_LAUNCH(conv3x3_relu_bwd_kernel, (unsigned)groups, bthreads, smem, stream, d, x, out, dout, partial_scratch);
+    const int bthreads = ne_all > 256 ? 512 : 256;
+    PB_LAUNCH_PDL_CHAIN(conv3x3_relu_bwd_kernel, (unsigned)groups, bthreads, smem, stream, d, x, out, dout, partial_scratch);
     const int ne = OC * C * 9 + OC;
-    PB_LAUNCH(conv_bwd_reduce_kernel, (unsigned)((ne + 7) / 8), 256, 0, stream, groups, OC * C * 9, OC,
+    PB_LAUNCH_PDL_CHAIN(conv_bwd_reduce_kernel, (unsigned)((ne + 7) / 8), 256, 0, stream, groups, OC * C * 9, OC,
               partial_scratch, dw, db);
     return PB_OK;
 }

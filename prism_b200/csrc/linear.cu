@@ -22,9 +22,10 @@ namespace {
 
 using namespace pb;
 
-constexpr int TM = 64, TN = 64, TK = 32, PAD = 4;   // NS x (A,B) stages of 32 x 68 floats (17 KB each); C tile aliases them
+constexpr int TM = 64, TN = 64, TK = 32, PAD = 8;   // NS x (A,B) stages of 32 x 72 floats (18 KB each; a row stride of 72 words
+                                                    // makes the tensor-core fragment loads conflict-free); C tile aliases them
 constexpr int NS = 4;                               // stages: a split's whole K range (<= NS chunks) is fetched at once
-constexpr int GEMM_SMEM = NS * 2 * TK * (TM + PAD) * 4;
+
 
 struct GemmArgs {
     const float *A, *B, *bias, *mask;
@@ -109,9 +110,29 @@ __device__ __forceinline__ void store_tile(float (*S)[TM + PAD], const float (&r
 // memory, 3 CTAs per SM: the step runs three such forward GEMMs -- online, bootstrap x 2 -- on parallel graph branches and
 // all 384 CTAs must stay resident); otherwise the classic two-stage pipeline (4 CTAs per SM: the two backward GEMMs of
 // a layer, 512 CTAs, run side by side).
-template <bool A_KMAJOR, bool B_KMAJOR, bool ROWSUM, bool FLIGHT>
+//
+// TC: the products run on the tensor cores as 3xTF32 (mma.sync m16n8k8; every operand is split in registers into a TF32
+// hi part and its fp32 residual lo, and each k step issues lo.hi + hi.lo + hi.hi into fp32 accumulators -- error ~1e-6,
+// the same recipe as csrc/tc_gemm.cu): a third of the issue slots of the FFMA loop, which is what bounds the step's
+// three concurrent forward GEMMs (0.4 GFLOP on the FFMA pipe).  These tiles are far too small and too many for the
+// persistent tcgen05 kernel (one 128 x N tile per SM, 200 KB of shared memory: it serialised the step's graph branches).
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
+{
+    hi = __float_as_uint(x) & 0xFFFFE000u;                       // the 19 bits the tensor core reads
+    lo = __float_as_uint(x - __uint_as_float(hi));                // exact; the tensor core reads ITS top 19 bits
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR, bool ROWSUM, bool FLIGHT, bool TC>
 __global__ void __launch_bounds__(256, FLIGHT ? 3 : 4) gemm_kernel(GemmArgs g)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     extern __shared__ __align__(16) float tiles[];
     __shared__ float Rs[TM];
     float (*As)[TK][TM + PAD] = reinterpret_cast<float (*)[TK][TM + PAD]>(tiles);
@@ -151,17 +172,46 @@ __global__ void __launch_bounds__(256, FLIGHT ? 3 : 4) gemm_kernel(GemmArgs g)
             store_tile<B_KMAJOR>(Bs[b], rb[h], t, h);
         }
     };
+    // tensor-core path: warp w owns rows wm .. wm+15, columns wn .. wn+31 of the tile (one m16 x four n8 fragments)
+    const int lane = t & 31, gq = lane >> 2, tq = lane & 3;
+    const int wm = ((t >> 5) & 3) * 16, wn = (t >> 7) * 32;
+    float cf[4][4] = {};
+    float rsum = 0.f;                                              // ROWSUM on the TC path: thread t < 64 sums row t
     auto compute = [&](int b) {
+        if (TC) {
 #pragma unroll
-        for (int k = 0; k < TK; ++k) {
-            const float4 a = *reinterpret_cast<const float4 *>(&As[b][k][ty << 2]);
-            const float4 bb = *reinterpret_cast<const float4 *>(&Bs[b][k][tx << 2]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+            for (int k0 = 0; k0 < TK; k0 += 8) {
+                uint32_t ah[4], al[4];
+                split_tf32(As[b][k0 + tq][wm + gq], ah[0], al[0]);
+                split_tf32(As[b][k0 + tq][wm + gq + 8], ah[1], al[1]);
+                split_tf32(As[b][k0 + tq + 4][wm + gq], ah[2], al[2]);
+                split_tf32(As[b][k0 + tq + 4][wm + gq + 8], ah[3], al[3]);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+                for (int nt = 0; nt < 4; ++nt) {
+                    uint32_t bh[2], bl[2];
+                    split_tf32(Bs[b][k0 + tq][wn + nt * 8 + gq], bh[0], bl[0]);
+                    split_tf32(Bs[b][k0 + tq + 4][wn + nt * 8 + gq], bh[1], bl[1]);
+                    mma_tf32(cf[nt], al, bh);                      // small terms first
+                    mma_tf32(cf[nt], ah, bl);
+                    mma_tf32(cf[nt], ah, bh);
+                }
+            }
+            if (ROWSUM && t < TM) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
-                if (ROWSUM) rs[r] += av[r];
+                for (int k = 0; k < TK; ++k) rsum += As[b][k][t];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < TK; ++k) {
+                const float4 a = *reinterpret_cast<const float4 *>(&As[b][k][ty << 2]);
+                const float4 bb = *reinterpret_cast<const float4 *>(&Bs[b][k][tx << 2]);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+                    if (ROWSUM) rs[r] += av[r];
+                }
             }
         }
     };
@@ -199,6 +249,24 @@ __global__ void __launch_bounds__(256, FLIGHT ? 3 : 4) gemm_kernel(GemmArgs g)
         }
     }
 
+    if (TC) {
+        // fragments -> the C tile (it aliases the stages: every warp is past its last read, see the barriers above) ->
+        // the 4 x 4 thread tiles the epilogue and the split-K reduction work with
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            *reinterpret_cast<float2 *>(&Cs[wm + gq][wn + nt * 8 + 2 * tq]) = make_float2(cf[nt][0], cf[nt][1]);
+            *reinterpret_cast<float2 *>(&Cs[wm + gq + 8][wn + nt * 8 + 2 * tq]) = make_float2(cf[nt][2], cf[nt][3]);
+        }
+        if (ROWSUM && t < TM) Rs[t] = rsum;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float4 v = *reinterpret_cast<const float4 *>(&Cs[(ty << 2) + r][tx << 2]);
+            acc[r][0] = v.x; acc[r][1] = v.y; acc[r][2] = v.z; acc[r][3] = v.w;
+            if (ROWSUM) rs[r] = Rs[(ty << 2) + r];
+        }
+        __syncthreads();                                           // the split-K path rewrites the C tile below
+    }
     float *C = g.C + batch * g.c_bs;
     const float *bias = g.bias ? g.bias + batch * g.bias_bs : nullptr;
     auto emit = [&](int i, int j, float v) {
@@ -273,7 +341,7 @@ int pick_splits(long long tiles, int total_chunks)
     return s;
 }
 
-template <bool AK, bool BK, bool ROWSUM, bool FLIGHT>
+template <bool AK, bool BK, bool ROWSUM, bool FLIGHT, bool TC>
 int launch_gemm_v(GemmArgs g, int batch, int n_tiles, void *stream);
 
 template <bool AK, bool BK, bool ROWSUM>
@@ -286,18 +354,25 @@ int launch_gemm(GemmArgs g, int batch, void *stream)
     const int per = (total_chunks + g.splits - 1) / g.splits;      // chunks per split
     static int flight_ok = -1;                                     // PB_GEMM_FLIGHT=0: two-stage pipeline everywhere
     if (flight_ok < 0) { const char *e = getenv("PB_GEMM_FLIGHT"); flight_ok = (e && e[0] == '0') ? 0 : 1; }
-    if (flight_ok && per >= 3 && per <= NS) return launch_gemm_v<AK, BK, ROWSUM, true>(g, batch, n_tiles, stream);
-    return launch_gemm_v<AK, BK, ROWSUM, false>(g, batch, n_tiles, stream);
+    static int tc_ok = -1;                                         // PB_GEMM_MMA=0: FFMA products (fp32 exactly)
+    if (tc_ok < 0) { const char *e = getenv("PB_GEMM_MMA"); tc_ok = (e && e[0] == '0') ? 0 : 1; }
+    const bool flight = flight_ok && per >= 3 && per <= NS;
+    if (tc_ok) {
+        if (flight) return launch_gemm_v<AK, BK, ROWSUM, true, true>(g, batch, n_tiles, stream);
+        return launch_gemm_v<AK, BK, ROWSUM, false, true>(g, batch, n_tiles, stream);
+    }
+    if (flight) return launch_gemm_v<AK, BK, ROWSUM, true, false>(g, batch, n_tiles, stream);
+    return launch_gemm_v<AK, BK, ROWSUM, false, false>(g, batch, n_tiles, stream);
 }
 
-template <bool AK, bool BK, bool ROWSUM, bool FLIGHT>
+template <bool AK, bool BK, bool ROWSUM, bool FLIGHT, bool TC>
 int launch_gemm_v(GemmArgs g, int batch, int n_tiles, void *stream)
 {
     constexpr int SMEM = (FLIGHT ? NS : 2) * 2 * TK * (TM + PAD) * 4;
     if (g.splits > 8) {
         static PbPerDeviceOnce allowed;             // one flag per template instantiation
         if (!allowed.done()) {
-            cudaError_t ea = cudaFuncSetAttribute(gemm_kernel<AK, BK, ROWSUM, FLIGHT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            cudaError_t ea = cudaFuncSetAttribute(gemm_kernel<AK, BK, ROWSUM, FLIGHT, TC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             if (ea != cudaSuccess) return (int)ea;
             allowed.mark();
         }
@@ -305,7 +380,7 @@ int launch_gemm_v(GemmArgs g, int batch, int n_tiles, void *stream)
     {
         static PbPerDeviceOnce smem_set;            // one flag per template instantiation
         if (!smem_set.done()) {
-            cudaError_t es = cudaFuncSetAttribute(gemm_kernel<AK, BK, ROWSUM, FLIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+            cudaError_t es = cudaFuncSetAttribute(gemm_kernel<AK, BK, ROWSUM, FLIGHT, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
             if (es != cudaSuccess) return (int)es;
             smem_set.mark();
         }
@@ -315,12 +390,14 @@ int launch_gemm_v(GemmArgs g, int batch, int n_tiles, void *stream)
     cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)g.splits;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see PB_LAUNCH_PDL; the kernel waits itself
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<AK, BK, ROWSUM, FLIGHT>, g);
+    cfg.numAttrs = pb_pdl_chain_enabled() ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<AK, BK, ROWSUM, FLIGHT, TC>, g);
     g_pb_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return (int)e;
     e = cudaGetLastError();

@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(256) narrow_fwd_kernel(long long M, int N, int
                                                          long long x_hs4, const float4 *__restrict__ w,
                                                          const float *__restrict__ bias, float *__restrict__ y)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     extern __shared__ float4 ws[];
     // grid.y = heads: head k works on x + k * x_hs (x_hs = 0: the heads share x), W + k * N * J, bias + k * N, y + k * M * N
     x += (size_t)blockIdx.y * x_hs4;
@@ -91,6 +93,8 @@ __global__ void __launch_bounds__(512) narrow_bwd_kernel(long long M, int N, int
                                                          const float *__restrict__ dy, float *__restrict__ dx,
                                                          float *__restrict__ dWp, float *__restrict__ dbp, int rpc)
 {
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
     __shared__ float sdy[32 * NP];
     // grid.y = heads (dx is per head: (K, M, J); the caller sums it over the heads when they share x)
     x += (size_t)blockIdx.y * x_hs;
@@ -148,16 +152,31 @@ __global__ void __launch_bounds__(512) narrow_bwd_kernel(long long M, int N, int
     if (dbp && t < N) dbp[(size_t)blockIdx.x * N + t] = db;
 }
 
-// out[e] = sum_b part[b][e], fixed order
-__global__ void partial_reduce_kernel(int nblocks, long long n, const float *__restrict__ part, float *__restrict__ out)
+
+// dW and db of the narrow backward in ONE launch (two dependent launches sat on the step's critical path):
+// e < n_w: dW[e] = sum_b wpart[b][e];  else db[e - n_w] = sum_b bpart[b][e - n_w]; four partial sums in flight
+__global__ void narrow_reduce_kernel(int nblocks, long long n_w, int n_b, const float *__restrict__ wpart,
+                                     const float *__restrict__ bpart, float *__restrict__ dW, float *__restrict__ db)
 {
-    part += (size_t)blockIdx.y * nblocks * n;                      // grid.y = heads
-    out += (size_t)blockIdx.y * n;
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
+    wpart += (size_t)blockIdx.y * nblocks * n_w;                  // grid.y = heads
+    bpart += (size_t)blockIdx.y * nblocks * n_b;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    float a = 0.0f;
-    for (int b = 0; b < nblocks; ++b) a += part[(size_t)b * n + e];
-    out[e] = a;
+    if (e >= n_w + n_b) return;
+    const bool is_w = e < n_w;
+    const float *src = is_w ? wpart + e : bpart + (e - n_w);
+    const long long stride = is_w ? n_w : n_b;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    int b = 0;
+    for (; b + 3 < nblocks; b += 4) {
+        a0 += src[(size_t)b * stride]; a1 += src[(size_t)(b + 1) * stride];
+        a2 += src[(size_t)(b + 2) * stride]; a3 += src[(size_t)(b + 3) * stride];
+    }
+    for (; b < nblocks; ++b) a0 += src[(size_t)b * stride];
+    const float a = (a0 + a1) + (a2 + a3);
+    if (is_w) { if (dW) dW[(size_t)blockIdx.y * n_w + e] = a; }
+    else if (db) db[(size_t)blockIdx.y * n_b + (e - n_w)] = a;
 }
 
 __global__ void sum_heads_kernel(int K, long long n4, const float4 *__restrict__ in, float4 *__restrict__ out)
@@ -262,7 +281,7 @@ int pb_narrow_linear_fwd(int K, long long M, int N, int J, const float *x, long 
             if (e != cudaSuccess) return (int)e;                                                                   \
             once.mark();                                                                                           \
         }                                                                                                          \
-        PB_LAUNCH(narrow_fwd_kernel<NP>, grid, 256, smem, stream, M, N, J / 4, x4, x_head_stride / 4, w4, bias, y); \
+        PB_LAUNCH_PDL_CHAIN(narrow_fwd_kernel<NP>, grid, 256, smem, stream, M, N, J / 4, x4, x_head_stride / 4, w4, bias, y); \
     } while (0)
     switch (narrow_np(N)) {
         case 4: PB_NARROW_FWD(4); break;
@@ -288,16 +307,16 @@ int pb_narrow_linear_bwd(int K, long long M, int N, int J, const float *x, long 
     float *dbp = (dW || db) ? partials + (size_t)K * nb * N * J : nullptr;
     const dim3 grid((unsigned)nb, (unsigned)K);
     switch (narrow_np(N)) {
-        case 4: PB_LAUNCH(narrow_bwd_kernel<4>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp, rpc); break;
-        case 8: PB_LAUNCH(narrow_bwd_kernel<8>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp, rpc); break;
-        case 16: PB_LAUNCH(narrow_bwd_kernel<16>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp, rpc); break;
-        default: PB_LAUNCH(narrow_bwd_kernel<32>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp, rpc); break;
+        case 4: PB_LAUNCH_PDL_CHAIN(narrow_bwd_kernel<4>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp, rpc); break;
+        case 8: PB_LAUNCH_PDL_CHAIN(narrow_bwd_kernel<8>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp, rpc); break;
+        case 16: PB_LAUNCH_PDL_CHAIN(narrow_bwd_kernel<16>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp, rpc); break;
+        default: PB_LAUNCH_PDL_CHAIN(narrow_bwd_kernel<32>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp, rpc); break;
     }
-    if (dW) {
+    if (dW || db) {
         const long long n = (long long)N * J;
-        PB_LAUNCH(partial_reduce_kernel, dim3((unsigned)((n + 255) / 256), (unsigned)K), 256, 0, stream, nb, n, dWp, dW);
+        PB_LAUNCH_PDL_CHAIN(narrow_reduce_kernel, dim3((unsigned)((n + N + 255) / 256), (unsigned)K), 256, 0, stream, nb, n, N, dWp, dbp,
+                  dW, db);
     }
-    if (db) PB_LAUNCH(partial_reduce_kernel, dim3(1, (unsigned)K), 256, 0, stream, nb, (long long)N, dbp, db);
     return PB_OK;
 }
 

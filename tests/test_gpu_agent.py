@@ -295,6 +295,10 @@ def test_fused_linear_matches_torch(K, M, N, J, shared, relu):
     xe = xr.unsqueeze(0).expand(K, M, J) if shared else xr
     yr = torch.baddbmm(br.unsqueeze(1), xe, wr.transpose(1, 2))
     if relu:
+        # a ReLU mask is a step function: a pre-activation within rounding of 0 may legitimately come out on the other
+        # side on the GPU (3xTF32 products, fp32 sums) and that unit's whole gradient row moves.  Gradients are judged
+        # away from the kinks: units that close to 0 receive no upstream gradient.
+        gy = gy * (yr.detach().abs() > 1e-4).float()
         yr = yr.relu()
     yr.backward(gy.double())
     xd, wd, bd = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
