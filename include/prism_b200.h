@@ -497,6 +497,9 @@ long long pb_peer_allreduce_adam_max_n(void);
 int pb_peer_allreduce_adam(const pb_peer_group *g, long long n, float *param, float *exp_avg, float *exp_avg_sq,
                            long long *step_count, float lr, float beta1, float beta2, float adam_eps, float max_grad_norm,
                            float *partial_scratch, float *norm_out, void *stream);
+/* HOST, synchronous, measurement runs only: phase marks of pb_peer_allreduce_adam's kernel (%globaltimer ns: 0 CTA 0
+ * starts, 1 handshake done, 2 pulled + summed, 3 the CTAs met, 4 Adam applied; latest CTA each), cleared on read. */
+int pb_peer_trace(int enable, unsigned long long *out, int n_out);
 /* Non-blocking half of the shard-state exchange (channel 2): this rank's 64-byte state block goes into slot
  * 2 + (count & 1) of every rank's state area and this rank's flag is raised there.  The matching wait is inside
  * pb_tree_sample_global_peer.  The state area holds 4 slots of PB_PEER_MAX x 64 bytes (0-1: pb_peer_state_allgather). */

@@ -133,6 +133,7 @@ SIGNATURES = {
     "pb_peer_allreduce_adam_max_n": [],
     "pb_peer_allreduce_adam": [_PEER, _LL, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
     "pb_peer_state_put": [_PEER, _P, _P],
+    "pb_peer_trace": [_I, _P, _I],
     "pb_tree_sample_global_peer": [_TREE, _PEER, _LL, _P, _F, _P, _P, _P, _P],
     "pb_layer_norm_supported": [_LL, _I],
     "pb_layer_norm_bwd_blocks": [_LL, _I],

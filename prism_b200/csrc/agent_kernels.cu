@@ -344,11 +344,19 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_clip_kernel(long long n, fl
     pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
     pdl_trigger();
     __shared__ double red[ADAM_THREADS / 32];
-    __shared__ float s_coef;
+    __shared__ float s_coef, s_bc2_sqrt, s_step_size;
     double acc = 0.0;
     for (int k = threadIdx.x; k < n_partials; k += blockDim.x) acc += (double)partial[k];
     acc = warp_sum(acc);
     if (lane_id() == 0) red[threadIdx.x >> 5] = acc;
+    if (threadIdx.x == 32) {
+        // bias corrections: two fp64 pow() -- once per CTA (another warp than the one that finishes the norm), not once
+        // per thread
+        const double step = (double)(*step_count);
+        const float bc1 = (float)(1.0 - pow((double)beta1, step));
+        s_bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
+        s_step_size = lr / bc1;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0;
@@ -363,10 +371,8 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_clip_kernel(long long n, fl
     }
     __syncthreads();
     const float coef = s_coef;
-    const double step = (double)(*step_count);
-    const float bc1 = (float)(1.0 - pow((double)beta1, step));
-    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
-    const float step_size = lr / bc1;
+    const float bc2_sqrt = s_bc2_sqrt;
+    const float step_size = s_step_size;
     auto upd = [&](float &p, float g, float &m, float &v) {
         g *= coef;
         m = m + (g - m) * (1.0f - beta1);                        // exp_avg.lerp_(grad, 1-beta1)

@@ -67,6 +67,14 @@ __device__ __forceinline__ bool wait_flag_sys(const unsigned long long *p, unsig
     return true;
 }
 
+// phase marks for measurement runs (pb_peer_trace): slot <- the latest %globaltimer at which any CTA passed the mark
+__device__ unsigned long long g_ptrace[16];
+__device__ int g_ptrace_on;
+__device__ __forceinline__ void ptrace(int on, int slot)
+{
+    if (on) atomicMax(&g_ptrace[slot], global_timer_ns());
+}
+
 // one warp: lane i signals rank i and waits for rank i.  Two independent CHANNELS (own flags, own epoch): calls on
 // one channel must be issued in the same order by every rank, but they may interleave with the other channel.
 // The wait is BOUNDED: a rank that does not show up within g.timeout_ns (dead process, missed launch) makes the
@@ -273,6 +281,22 @@ __global__ void __launch_bounds__(FA_THREADS) peer_allreduce_adam_kernel(pb_peer
     const int lane = threadIdx.x & 31;
     const unsigned long long e = g.epoch[1] + 1;                      // this exchange (epoch[1] advances at the very end)
     const long long step_now = *step_count + 1;                       // likewise
+    const int tr = __ldg(&g_ptrace_on);
+    if (tr && blockIdx.x == 0 && threadIdx.x == 0) g_ptrace[0] = global_timer_ns();
+    // ---- everything that does not depend on the other ranks is requested BEFORE the wait: the optimizer state of this
+    // thread's first element (the only one for arenas up to one element per thread) and the bias corrections
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 *p4 = reinterpret_cast<float4 *>(param), *m4 = reinterpret_cast<float4 *>(exp_avg),
+           *v4 = reinterpret_cast<float4 *>(exp_avg_sq), *r4 = reinterpret_cast<float4 *>(g.reduced[g.rank]);
+    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), m0 = p0, v0 = p0;
+    if (i0 < n4) { p0 = p4[i0]; m0 = m4[i0]; v0 = v4[i0]; }
+    const double step = (double)step_now;
+    const float bc1 = (float)(1.0 - pow((double)beta1, step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
+    const float step_size = lr / bc1;
+    // (launched as a programmatic dependent of the pack kernel: everything above overlaps its tail)
+    pdl_wait();
     // ---- handshake: CTA 0 tells every rank "my gradient is packed"; every CTA waits for all ranks on the local pad
     if (threadIdx.x < 32) {
         if (blockIdx.x == 0) {
@@ -285,10 +309,9 @@ __global__ void __launch_bounds__(FA_THREADS) peer_allreduce_adam_kernel(pb_peer
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) ptrace(tr, 1);                              // handshake done
     // ---- pull + sum in rank order, kept in registers
-    const long long n4 = n >> 2;
     const long long po = (long long)((e - 1) & 1ull) * g.grad_stride;  // the half packed for this exchange
-    const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float4 sum[FA_U];
     double acc = 0.0;
 #pragma unroll
@@ -309,6 +332,7 @@ __global__ void __launch_bounds__(FA_THREADS) peer_allreduce_adam_kernel(pb_peer
     if (lane == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
+        ptrace(tr, 2);                                                // pulled + summed
         double t = 0.0;
         for (int k = 0; k < FA_THREADS / 32; ++k) t += red[k];
         partials[blockIdx.x] = (float)t;
@@ -318,6 +342,7 @@ __global__ void __launch_bounds__(FA_THREADS) peer_allreduce_adam_kernel(pb_peer
         while (ld_acquire_gpu_u32(&counters[0]) < gridDim.x) { }
     }
     __syncthreads();
+    if (threadIdx.x == 0) ptrace(tr, 3);                              // met the other CTAs
     // ---- global norm: every CTA adds the partials in the same order
     double a2 = 0.0;
     for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) a2 += (double)__ldcg(partials + k);
@@ -337,10 +362,6 @@ __global__ void __launch_bounds__(FA_THREADS) peer_allreduce_adam_kernel(pb_peer
     }
     __syncthreads();
     const float coef = s_coef;
-    const double step = (double)step_now;
-    const float bc1 = (float)(1.0 - pow((double)beta1, step));
-    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
-    const float step_size = lr / bc1;
     auto upd = [&](float &p, float gg, float &m, float &v) {          // same arithmetic as adam_clip_kernel
         gg *= coef;
         m = m + (gg - m) * (1.0f - beta1);
@@ -348,13 +369,12 @@ __global__ void __launch_bounds__(FA_THREADS) peer_allreduce_adam_kernel(pb_peer
         const float denom = sqrtf(v) / bc2_sqrt + adam_eps;
         p = p - step_size * (m / denom);
     };
-    float4 *p4 = reinterpret_cast<float4 *>(param), *m4 = reinterpret_cast<float4 *>(exp_avg),
-           *v4 = reinterpret_cast<float4 *>(exp_avg_sq), *r4 = reinterpret_cast<float4 *>(g.reduced[g.rank]);
 #pragma unroll
     for (int k = 0; k < FA_U; ++k) {
         const long long i = i0 + k * stride;
         if (i < n4) {
-            float4 p = p4[i], m = m4[i], v = v4[i];
+            float4 p = p0, m = m0, v = v0;
+            if (k > 0) { p = p4[i]; m = m4[i]; v = v4[i]; }
             const float4 gr = sum[k];
             upd(p.x, gr.x, m.x, v.x); upd(p.y, gr.y, m.y, v.y); upd(p.z, gr.z, m.z, v.z); upd(p.w, gr.w, m.w, v.w);
             p4[i] = p; m4[i] = m; v4[i] = v;
@@ -363,6 +383,7 @@ __global__ void __launch_bounds__(FA_THREADS) peer_allreduce_adam_kernel(pb_peer
     }
     // ---- the last CTA out closes the exchange: counters back to zero, epoch and step count advanced
     __syncthreads();
+    if (threadIdx.x == 0) ptrace(tr, 4);                              // Adam applied
     if (threadIdx.x == 0) {
         __threadfence();
         s_last = (atomicAdd(&counters[1], 1u) == gridDim.x - 1) ? 1u : 0u;
@@ -552,9 +573,26 @@ int pb_peer_allreduce_adam(const pb_peer_group *g, long long n, float *param, fl
     if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
     unsigned int *counters = reinterpret_cast<unsigned int *>(partial_scratch + 4092);    // zero between calls
-    PB_LAUNCH(peer_allreduce_adam_kernel, (unsigned)nb, FA_THREADS, 0, stream, *g, n, param, exp_avg, exp_avg_sq, step_count,
+    PB_LAUNCH_PDL(peer_allreduce_adam_kernel, (unsigned)nb, FA_THREADS, 0, stream, *g, n, param, exp_avg, exp_avg_sq, step_count,
               lr, beta1, beta2, adam_eps, max_grad_norm, partial_scratch, counters, norm_out);
     return PB_OK;
+}
+
+int pb_peer_trace(int enable, unsigned long long *out, int n_out)
+{
+    // synchronous (measurement runs only): copy out the marks of the fused exchange kernel, clear them, switch marking
+    unsigned long long host[16];
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyFromSymbol(host, g_ptrace, sizeof(host));
+    if (e != cudaSuccess) return (int)e;
+    if (out) for (int k = 0; k < n_out && k < 16; ++k) out[k] = host[k];
+    for (int k = 0; k < 16; ++k) host[k] = 0;
+    e = cudaMemcpyToSymbol(g_ptrace, host, sizeof(host));
+    if (e != cudaSuccess) return (int)e;
+    const int on = enable ? 1 : 0;
+    e = cudaMemcpyToSymbol(g_ptrace_on, &on, sizeof(on));
+    return e == cudaSuccess ? PB_OK : (int)e;
 }
 
 int pb_peer_state_put(const pb_peer_group *g, const void *state64, void *stream)

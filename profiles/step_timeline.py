@@ -73,6 +73,23 @@ def main():
         v = np.asarray(v, dtype=np.float64) / 1e3
         lines.append("  %-28s median %8.1f us   p10 %8.1f   p90 %8.1f" % (name, np.median(v), np.percentile(v, 10),
                                                                           np.percentile(v, 90)))
+    if world > 1 and getattr(step, "peer", None) is not None:
+        # phases INSIDE the one-launch gradient exchange (pb_peer_trace), a few replays, this rank's clock
+        import ctypes as C
+        from prism_b200 import _lib
+        lib = _lib.load()
+        out = (C.c_ulonglong * 16)()
+        rows = []
+        for i in range(10):
+            _lib.check(lib.pb_peer_trace(1, out, 16), "pb_peer_trace")
+            one(8 + args.replays + i)
+            _lib.check(lib.pb_peer_trace(0, out, 16), "pb_peer_trace")
+            if out[0] and out[4]:
+                rows.append([(int(out[k]) - int(out[0])) / 1e3 for k in range(5)])
+        if rows:
+            med = np.median(np.asarray(rows), axis=0)
+            lines.append("  inside the exchange kernel (us from CTA 0's start): handshake done %.1f | pulled + summed %.1f | "
+                         "CTAs met %.1f | Adam applied %.1f" % (med[1], med[2], med[3], med[4]))
     if world > 1:
         for r in range(world):                            # one rank at a time
             if r == rank:
