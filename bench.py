@@ -307,7 +307,7 @@ def kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src):
         # GEMM-shaped work: the tensor / FMA pipes bound it; 3 forward + 2x2 backward launches of this family are ~45 %
         # of the step (profiles/launches_r01d_step.txt).  traffic: dram__bytes_read+write of one launch, ncu --set full
         # (profiles/ncu_full_step_r01.txt, gemm_kernel<1,1,0> grid (4,4,8)).
-        traffic, traffic_file = ncu_traffic("gemm_kernel<1, 1, 0>")
+        traffic, traffic_file = ncu_traffic("gemm_kernel<1, 1, 0,")
         roof = {"bound": "tensor", "kernel": dom, "achieved": d["achieved_tflops"], "peak": bf16, "unit": "TFLOP/s",
                 "frac": d["frac_of_bf16_tensor_peak"], "traffic": traffic, "traffic_source": traffic_file,
                 "peak_source": peak_src,

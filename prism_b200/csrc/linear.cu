@@ -179,6 +179,9 @@ __global__ void __launch_bounds__(256, FLIGHT ? 3 : 4) gemm_kernel(GemmArgs g)
     float rsum = 0.f;                                              // ROWSUM on the TC path: thread t < 64 sums row t
     auto compute = [&](int b) {
         if (TC) {
+            // a warp whose 16 rows lie past M has nothing to add (zero-filled rows): the padded static batch of the
+            // data-parallel step (272 rows: a fifth tile with one live warp row) stays cheap
+            if (i0 + wm < g.M) {
 #pragma unroll
             for (int k0 = 0; k0 < TK; k0 += 8) {
                 uint32_t ah[4], al[4];
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(256, FLIGHT ? 3 : 4) gemm_kernel(GemmArgs g)
                     mma_tf32(cf[nt], ah, bl);
                     mma_tf32(cf[nt], ah, bh);
                 }
+            }
             }
             if (ROWSUM && t < TM) {
 #pragma unroll
@@ -352,8 +356,11 @@ int launch_gemm(GemmArgs g, int batch, void *stream)
     const int total_chunks = g.n_seg * ((g.K + TK - 1) / TK);
     g.splits = pick_splits((long long)g.m_tiles * n_tiles * batch, total_chunks);
     const int per = (total_chunks + g.splits - 1) / g.splits;      // chunks per split
-    static int flight_ok = -1;                                     // PB_GEMM_FLIGHT=0: two-stage pipeline everywhere
-    if (flight_ok < 0) { const char *e = getenv("PB_GEMM_FLIGHT"); flight_ok = (e && e[0] == '0') ? 0 : 1; }
+    // PB_GEMM_FLIGHT=1 selects the in-flight variant for splits of 3-4 chunks.  Off by default: measured equal on one
+    // GPU (the forward GEMMs are issue-, not load-bound) and its 3 CTAs per SM cannot hold the three 160-CTA forward
+    // GEMMs of the data-parallel step (272 padded rows) at once, the two-stage variant's 4 per SM can.
+    static int flight_ok = -1;
+    if (flight_ok < 0) { const char *e = getenv("PB_GEMM_FLIGHT"); flight_ok = (e && e[0] == '1') ? 1 : 0; }
     static int tc_ok = -1;                                         // PB_GEMM_MMA=0: FFMA products (fp32 exactly)
     if (tc_ok < 0) { const char *e = getenv("PB_GEMM_MMA"); tc_ok = (e && e[0] == '0') ? 0 : 1; }
     const bool flight = flight_ok && per >= 3 && per <= NS;

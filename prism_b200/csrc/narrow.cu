@@ -154,29 +154,37 @@ __global__ void __launch_bounds__(512) narrow_bwd_kernel(long long M, int N, int
 
 
 // dW and db of the narrow backward in ONE launch (two dependent launches sat on the step's critical path):
-// e < n_w: dW[e] = sum_b wpart[b][e];  else db[e - n_w] = sum_b bpart[b][e - n_w]; four partial sums in flight
-__global__ void narrow_reduce_kernel(int nblocks, long long n_w, int n_b, const float *__restrict__ wpart,
-                                     const float *__restrict__ bpart, float *__restrict__ dW, float *__restrict__ db)
+// e < n_w: dW[e] = sum_b wpart[b][e];  else db[e - n_w] = sum_b bpart[b][e - n_w].  Eight lanes per element stride over
+// the partials (64 of them at learner-batch sizes: a thread per element was 64 dependent-latency loads deep), combined
+// by three shuffles in a fixed order.
+__global__ void __launch_bounds__(256) narrow_reduce_kernel(int nblocks, long long n_w, int n_b,
+                                                            const float *__restrict__ wpart,
+                                                            const float *__restrict__ bpart, float *__restrict__ dW,
+                                                            float *__restrict__ db)
 {
     pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
     pdl_trigger();
     wpart += (size_t)blockIdx.y * nblocks * n_w;                  // grid.y = heads
     bpart += (size_t)blockIdx.y * nblocks * n_b;
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_w + n_b) return;
-    const bool is_w = e < n_w;
+    const long long e = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
+    const int pl = threadIdx.x & 7;
+    const bool live = e < n_w + n_b, is_w = e < n_w;
     const float *src = is_w ? wpart + e : bpart + (e - n_w);
     const long long stride = is_w ? n_w : n_b;
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-    int b = 0;
-    for (; b + 3 < nblocks; b += 4) {
-        a0 += src[(size_t)b * stride]; a1 += src[(size_t)(b + 1) * stride];
-        a2 += src[(size_t)(b + 2) * stride]; a3 += src[(size_t)(b + 3) * stride];
+    float a0 = 0.0f, a1 = 0.0f;
+    if (live) {
+        int b = pl;
+        for (; b + 8 < nblocks; b += 16) { a0 += src[(size_t)b * stride]; a1 += src[(size_t)(b + 8) * stride]; }
+        if (b < nblocks) a0 += src[(size_t)b * stride];
     }
-    for (; b < nblocks; ++b) a0 += src[(size_t)b * stride];
-    const float a = (a0 + a1) + (a2 + a3);
-    if (is_w) { if (dW) dW[(size_t)blockIdx.y * n_w + e] = a; }
-    else if (db) db[(size_t)blockIdx.y * n_b + (e - n_w)] = a;
+    float a = a0 + a1;
+    a += __shfl_xor_sync(FULL, a, 1);
+    a += __shfl_xor_sync(FULL, a, 2);
+    a += __shfl_xor_sync(FULL, a, 4);
+    if (live && pl == 0) {
+        if (is_w) { if (dW) dW[(size_t)blockIdx.y * n_w + e] = a; }
+        else if (db) db[(size_t)blockIdx.y * n_b + (e - n_w)] = a;
+    }
 }
 
 __global__ void sum_heads_kernel(int K, long long n4, const float4 *__restrict__ in, float4 *__restrict__ out)
@@ -314,7 +322,7 @@ int pb_narrow_linear_bwd(int K, long long M, int N, int J, const float *x, long 
     }
     if (dW || db) {
         const long long n = (long long)N * J;
-        PB_LAUNCH_PDL_CHAIN(narrow_reduce_kernel, dim3((unsigned)((n + N + 255) / 256), (unsigned)K), 256, 0, stream, nb, n, N, dWp, dbp,
+        PB_LAUNCH_PDL_CHAIN(narrow_reduce_kernel, dim3((unsigned)((n + N + 31) / 32), (unsigned)K), 256, 0, stream, nb, n, N, dWp, dbp,
                   dW, db);
     }
     return PB_OK;
