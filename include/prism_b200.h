@@ -370,6 +370,14 @@ int pb_adam_clip_apply(long long n, float *param, const float *grad, float *exp_
                        float beta2, float adam_eps, float max_grad_norm,
                        const float *partial_scratch, int n_partials, float *norm_out,
                        void *stream);
+/* Small arenas (n <= pb_adam_fused_max_n(), at most 64 tensors): pb_pack_grads + pb_adam_clip_apply as ONE launch -- the
+ * gathered gradient stays in registers between the norm (the CTAs of the grid meet at a counter) and the Adam update;
+ * it is also written to `grad` (the flat arena).  table as for pb_pack_grads, tensors in arena order.
+ * partial_scratch: 4096 floats, the last 4 zero between calls.  PB_E_UNSUPPORTED: use the two-launch path. */
+long long pb_adam_fused_max_n(void);
+int pb_adam_fused_step(int n_tensors, const long long *table, float scale, long long n, float *param, float *grad,
+                       float *exp_avg, float *exp_avg_sq, long long *step_count, float lr, float beta1, float beta2,
+                       float adam_eps, float max_grad_norm, float *partial_scratch, float *norm_out, void *stream);
 int pb_adam_clip_step(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
                       long long *step_count, float lr, float beta1, float beta2, float adam_eps,
                       float max_grad_norm, float *norm_out, float *partial_scratch, void *stream);

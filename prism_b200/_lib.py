@@ -108,6 +108,8 @@ SIGNATURES = {
     "pb_ids_select": [_I, _I, _I, _I, _P, _P, _F, _F, _F, _P, _P, _P],
     "pb_greedy_select": [_I, _I, _I, _P, _P, _P],
     "pb_adam_clip_step": [_LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
+    "pb_adam_fused_max_n": [],
+    "pb_adam_fused_step": [_I, _P, _F, _LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
     "pb_pack_grads": [_I, _P, _F, _P, _P, _P, _P, _P],
     "pb_pack_grads_parity": [_I, _P, _F, _P, _P, _LL, _P, _P, _P, _P],
     "pb_grad_sumsq": [_LL, _P, _P, _P, _P, _P],
@@ -168,7 +170,7 @@ SIGNATURES = {
     "pb_wire_index_timesteps": [_P, _LL, _LL, _P, _P],
 }
 _RESTYPES = {"pb_error_string": C.c_char_p, "pb_launch_count": C.c_longlong, "pb_peer_slice": C.c_longlong,
-             "pb_peer_allreduce_adam_max_n": C.c_longlong}
+             "pb_peer_allreduce_adam_max_n": C.c_longlong, "pb_adam_fused_max_n": C.c_longlong}
 
 PB_E_POOL = -4
 ABI_VERSION = 2

@@ -35,6 +35,9 @@ def flatten_parameters(module):
     return arena, offsets
 
 
+FUSED_STEP = __import__("os").environ.get("PB_ADAM_FUSED", "1") != "0"   # one-launch gather + clip + Adam for small arenas
+
+
 class FlatAdam(object):
     def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=0.0, arena=None):
         self._lib = _lib.load()
@@ -81,6 +84,12 @@ class FlatAdam(object):
         self.peer = None                # PeerGroup: gradient exchange fused with clip + Adam over peer memory
         self.peer_state = None          # 64-byte shard state block that rides on the exchange's handshake (LearnerStep)
         self.peer_after_exchange = None  # callable run right after the handshake (LearnerStep: prefetch of the next batch)
+
+    def _fused_max_n(self):
+        m = getattr(self, "_fused_max", None)
+        if m is None:
+            m = self._fused_max = int(self._lib.pb_adam_fused_max_n())
+        return m
 
     def attach_peer_group(self, peer):
         """Route the data-parallel gradient exchange through csrc/peer.cu: the flat gradient arena moves into the
@@ -130,6 +139,16 @@ class FlatAdam(object):
                        "pb_pack_grads_parity")
             mark("opt:packed")
             self.peer.allreduce_adam(self, state=self.peer_state, mark=mark, after_exchange=self.peer_after_exchange)
+            return
+        if self.allreduce is None and FUSED_STEP and len(self.params) <= 64 and self.numel <= self._fused_max_n():
+            # small arena: gather + norm + clip + Adam in ONE launch (the gradient stays in registers)
+            _lib.check(self._lib.pb_adam_fused_step(len(self.params), self.table.data_ptr(), self.grad_scale, self.numel,
+                                                    self.arena.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                                    self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(), self.lr,
+                                                    self.betas[0], self.betas[1], self.eps, self.max_grad_norm,
+                                                    self.partials.data_ptr(), self.norm_out.data_ptr(), stream),
+                       "pb_adam_fused_step")
+            mark("opt:packed")
             return
         if self.allreduce is None:
             _lib.check(self._lib.pb_pack_grads(len(self.params), self.table.data_ptr(), self.grad_scale,

@@ -395,6 +395,155 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_clip_kernel(long long n, fl
             upd(param[i], grad[i], exp_avg[i], exp_avg_sq[i]);
 }
 
+
+// ---------------------------------------------------------------------------------
+// Small arenas, ONE launch for gather + clip_grad_norm_ + Adam (agent.py:73-74): a thread gathers its 128-bit elements
+// of autograd's per-parameter gradients (scaled) INTO REGISTERS (and into the flat gradient arena, for whoever reads
+// it), publishes its CTA's sum of squares, meets the other CTAs of the grid at a counter (all resident: the grid is
+// sized by the occupancy API), derives the norm from the partials in a fixed order and applies Adam to the elements
+// it still holds.  The optimizer state of the first element and the bias corrections are requested before the
+// barrier.  Replaces pack_grads_kernel + adam_clip_kernel (two launches, the gradient written and re-read) on the
+// configs[0] / [1] steps; arenas beyond FUSED_U elements per thread keep the two-launch path.
+// ---------------------------------------------------------------------------------
+constexpr int FUSED_U = 8;
+constexpr int FUSED_MAX_TENSORS = 64;
+
+__global__ void __launch_bounds__(ADAM_THREADS) adam_fused_kernel(const long long *__restrict__ table, int n_tensors,
+                                                                  float scale, long long n, float *__restrict__ param,
+                                                                  float *__restrict__ grad, float *__restrict__ exp_avg,
+                                                                  float *__restrict__ exp_avg_sq,
+                                                                  long long *__restrict__ step_count, float lr,
+                                                                  float beta1, float beta2, float adam_eps,
+                                                                  float max_grad_norm, float *__restrict__ partials,
+                                                                  unsigned int *__restrict__ counters,
+                                                                  float *__restrict__ norm_out)
+{
+    __shared__ long long s_tab[3 * FUSED_MAX_TENSORS];
+    __shared__ double red[ADAM_THREADS / 32];
+    __shared__ float s_coef;
+    __shared__ unsigned s_last;
+    for (int e = threadIdx.x; e < 3 * n_tensors; e += blockDim.x) s_tab[e] = table[e];
+    const long long step_now = *step_count + 1;
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 *p4 = reinterpret_cast<float4 *>(param), *m4 = reinterpret_cast<float4 *>(exp_avg),
+           *v4 = reinterpret_cast<float4 *>(exp_avg_sq), *g4 = reinterpret_cast<float4 *>(grad);
+    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), m0 = p0, v0 = p0;
+    if (i0 < n4) { p0 = p4[i0]; m0 = m4[i0]; v0 = v4[i0]; }
+    const double step = (double)step_now;
+    const float bc1 = (float)(1.0 - pow((double)beta1, step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
+    const float step_size = lr / bc1;
+    __syncthreads();
+    // ---- gather: arena offset -> (tensor, offset within it); tensors are laid out in table order, 16-byte aligned
+    float4 gsum[FUSED_U];
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < FUSED_U; ++k) {
+        const long long i = i0 + k * stride;
+        gsum[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n4) {
+            const long long o = i << 2;
+            int t = 0;
+            for (int q = 1; q < n_tensors; ++q) t = s_tab[3 * q + 1] <= o ? q : t;
+            const float *src = reinterpret_cast<const float *>(s_tab[3 * t]);
+            const long long within = o - s_tab[3 * t + 1], numel = s_tab[3 * t + 2];
+            float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (src != nullptr && within < numel) {
+                if (within + 3 < numel && ((reinterpret_cast<uintptr_t>(src + within) & 15) == 0)) {
+                    gv = *reinterpret_cast<const float4 *>(src + within);
+                } else {
+                    gv.x = src[within];
+                    gv.y = within + 1 < numel ? src[within + 1] : 0.f;
+                    gv.z = within + 2 < numel ? src[within + 2] : 0.f;
+                    gv.w = within + 3 < numel ? src[within + 3] : 0.f;
+                }
+                gv.x *= scale; gv.y *= scale; gv.z *= scale; gv.w *= scale;
+            }
+            gsum[k] = gv;
+            g4[i] = gv;
+            acc += (double)(gv.x * gv.x + gv.y * gv.y) + (double)(gv.z * gv.z + gv.w * gv.w);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane_id() == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < ADAM_THREADS / 32; ++k) t += red[k];
+        partials[blockIdx.x] = (float)t;
+        __threadfence();
+        atomicAdd(&counters[0], 1u);
+        unsigned seen;
+        do {                                                          // meet the other CTAs of this grid (all resident)
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&counters[0]) : "memory");
+        } while (seen < gridDim.x);
+    }
+    __syncthreads();
+    double a2 = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) a2 += (double)__ldcg(partials + k);
+    a2 = warp_sum(a2);
+    __syncthreads();                                                  // red[] is reused
+    if (lane_id() == 0) red[threadIdx.x >> 5] = a2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < ADAM_THREADS / 32; ++k) t += red[k];
+        const float total_norm = (float)sqrt(t);
+        float coef = max_grad_norm / (total_norm + 1e-6f);            // clip_grad_norm_
+        coef = coef > 1.0f ? 1.0f : coef;
+        if (!(max_grad_norm > 0.0f)) coef = 1.0f;
+        s_coef = coef;
+        if (blockIdx.x == 0 && norm_out) { norm_out[0] = total_norm; norm_out[1] = coef; }
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    auto upd = [&](float &p, float gg, float &m, float &v) {          // same arithmetic as adam_clip_kernel
+        gg *= coef;
+        m = m + (gg - m) * (1.0f - beta1);
+        v = v * beta2 + (1.0f - beta2) * gg * gg;
+        const float denom = sqrtf(v) / bc2_sqrt + adam_eps;
+        p = p - step_size * (m / denom);
+    };
+#pragma unroll
+    for (int k = 0; k < FUSED_U; ++k) {
+        const long long i = i0 + k * stride;
+        if (i < n4) {
+            float4 p = p0, m = m0, v = v0;
+            if (k > 0) { p = p4[i]; m = m4[i]; v = v4[i]; }
+            const float4 gr = gsum[k];
+            upd(p.x, gr.x, m.x, v.x); upd(p.y, gr.y, m.y, v.y); upd(p.z, gr.z, m.z, v.z); upd(p.w, gr.w, m.w, v.w);
+            p4[i] = p; m4[i] = m; v4[i] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&counters[1], 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        counters[0] = 0u; counters[1] = 0u;
+        *step_count = step_now;
+    }
+}
+
+static int fused_max_blocks()
+{
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    int c = cached[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adam_fused_kernel, ADAM_THREADS, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    c = pb_sm_count() * per_sm;
+    cached[dev].store(c, std::memory_order_relaxed);
+    return c;
+}
+
 }  // namespace
 
 extern "C" {
@@ -538,7 +687,29 @@ int pb_optimizer_preload(void)
     cudaError_t e = cudaFuncGetAttributes(&a, adam_clip_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pack_grads_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, grad_sumsq_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, adam_fused_kernel);
     return e == cudaSuccess ? PB_OK : (int)e;
+}
+
+long long pb_adam_fused_max_n(void) { return (long long)fused_max_blocks() * ADAM_THREADS * FUSED_U * 4; }
+
+int pb_adam_fused_step(int n_tensors, const long long *table, float scale, long long n, float *param, float *grad,
+                       float *exp_avg, float *exp_avg_sq, long long *step_count, float lr, float beta1, float beta2,
+                       float adam_eps, float max_grad_norm, float *partial_scratch, float *norm_out, void *stream)
+{
+    if (n_tensors <= 0 || !table || n <= 0 || (n % 4) != 0 || !param || !grad || !exp_avg || !exp_avg_sq || !step_count ||
+        !partial_scratch)
+        return PB_E_ARG;
+    if (n_tensors > FUSED_MAX_TENSORS || n > pb_adam_fused_max_n()) return PB_E_UNSUPPORTED;
+    if ((((uintptr_t)param) | ((uintptr_t)grad) | ((uintptr_t)exp_avg) | ((uintptr_t)exp_avg_sq)) & 15) return PB_E_ARG;
+    long long nb = ((n >> 2) + ADAM_THREADS - 1) / ADAM_THREADS;
+    const long long cap = fused_max_blocks();
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+    unsigned int *counters = reinterpret_cast<unsigned int *>(partial_scratch + 4092);    // zero between calls
+    PB_LAUNCH(adam_fused_kernel, (unsigned)nb, ADAM_THREADS, 0, stream, table, n_tensors, scale, n, param, grad, exp_avg,
+              exp_avg_sq, step_count, lr, beta1, beta2, adam_eps, max_grad_norm, partial_scratch, counters, norm_out);
+    return PB_OK;
 }
 
 int pb_adam_clip_step(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq,

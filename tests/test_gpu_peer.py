@@ -36,9 +36,10 @@ def test_peer_allreduce_adam_matches_single_rank_step(world, n, one_shot, monkey
     _run_allreduce_adam(world, n)
 
 
-@pytest.mark.parametrize("world,n", [(2, 4096), (4, 4096), (8, 4096), (2, 100_000), (4, 100_000), (2, 400_004)])
+@pytest.mark.parametrize("world,n", [(2, 4096), (4, 4096), (8, 4096), (8, 40_000), (2, 100_000), (4, 100_000), (2, 400_004)])
 def test_peer_fused_allreduce_adam_matches_single_rank_step(world, n, monkeypatch):
-    """Small arenas: handshake + pulls + global norm + clip + Adam as ONE launch per rank (peer_allreduce_adam_kernel).
+    """Small arenas: handshake + pulls + global norm + clip + Adam as ONE launch per rank (peer_allreduce_adam_kernel):
+    one-shot pulls up to 4 ranks, two-phase (reduce-scatter by pull, all-gather by push, a second flag round) at 8.
     Sizes are bounded here because the loopback ranks share one GPU: every rank's CTAs must be resident at once (in the
     multi-process set-up each rank has its own GPU; tests/test_gpu_multiprocess.py runs that)."""
     from prism_b200 import peer as peer_mod
