@@ -379,7 +379,6 @@ __global__ void __launch_bounds__(FA_THREADS) peer_allreduce_adam_kernel(pb_peer
         for (int p = 0; p < g.world; ++p) *reinterpret_cast<float4 *>(g.reduced[p] + (j << 2)) = s4;
         acc += (double)(s4.x * s4.x + s4.y * s4.y) + (double)(s4.z * s4.z + s4.w * s4.w);
     }
-    __threadfence_system();                                           // this thread's pushes, before anything is signalled
     acc = warp_sum(acc);
     if (lane == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
@@ -388,7 +387,9 @@ __global__ void __launch_bounds__(FA_THREADS) peer_allreduce_adam_kernel(pb_peer
         double t = 0.0;
         for (int k = 0; k < FA_THREADS / 32; ++k) t += red[k];
         partials[blockIdx.x] = (float)t;
-        __threadfence();
+        // ONE system-scope fence per CTA: the barrier above ordered every thread's pushes before it (cumulativity);
+        // a fence per thread measured +12 us
+        __threadfence_system();
         atomicAdd(&counters[0], 1u);
     }
     if (blockIdx.x == 0 && threadIdx.x < 32) {
@@ -620,6 +621,19 @@ static int fa_max_blocks()
     return c;
 }
 
+int pb_peer_two_phase_min(int set)
+{
+    static std::atomic<int> two_min{-1};
+    if (set >= 0) two_min.store(set);
+    int v = two_min.load();
+    if (v < 0) {
+        const char *e = getenv("PB_PEER_TWO_PHASE");
+        v = e ? atoi(e) : 0;
+        two_min.store(v);
+    }
+    return v;
+}
+
 long long pb_peer_allreduce_adam_max_n(void) { return (long long)fa_max_blocks() * FA_THREADS * FA_U * 4; }
 
 int pb_peer_allreduce_adam(const pb_peer_group *g, long long n, float *param, float *exp_avg, float *exp_avg_sq,
@@ -640,10 +654,10 @@ int pb_peer_allreduce_adam(const pb_peer_group *g, long long n, float *param, fl
     if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
     unsigned int *counters = reinterpret_cast<unsigned int *>(partial_scratch + 4092);    // zero between calls
-    // 8 ranks: two-phase (reduce-scatter by pull, all-gather by push) -- pulling 7 whole arenas measured 16 us more than
-    // the 4-rank step.  PB_PEER_TWO_PHASE=<min world> moves the switch (0: never).
-    static int two_min = -1;
-    if (two_min < 0) { const char *e = getenv("PB_PEER_TWO_PHASE"); two_min = e ? atoi(e) : 8; }
+    // two-phase (reduce-scatter by pull, all-gather by push) from pb_peer_two_phase_min() ranks on.  OFF by default:
+    // measured at 8 GPUs it equals the one-shot schedule (129.8 vs 128.7 us per step: what the step pays from 4 to 8
+    // ranks is waiting for the slowest of 8, not NVLink volume) and at 2 GPUs it costs a second flag round (+12 us).
+    const int two_min = pb_peer_two_phase_min(-1);
     int two_phase = (two_min > 0 && g->world >= two_min) ? 1 : 0;
     if (two_phase) {
         for (int p = 0; p < g->world; ++p)
