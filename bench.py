@@ -412,6 +412,38 @@ def ncu_traffic(kernel_substr):
     return best
 
 
+def ncu_per_traffic():
+    """{K: DRAM bytes (read + written) of ONE sample + write-back iteration at K batches in flight}, from the committed
+    `ncu --set full` capture of profiles/per_ncu.py (profiles/ncu_full_per_r02.txt: after the bulk build the kernels of
+    K = 1, 16, 64 follow, two repetitions each; the second one is read).  {} when the file is absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_full_per_r02.txt")
+    try:
+        lines = open(path).read().splitlines()[1:]
+    except OSError:
+        return {}
+    import re
+    rows = []
+    for ln in lines:
+        m = re.match(r"\s*(\d+)\s+(\S+)\s.*?\(\d+,\d+,\d+\)\s+\(\d+,\d+,\d+\)\s+([0-9.]+)\s+(\d+)\s+(\d+)", ln)
+        if m:
+            rows.append((m.group(2), float(m.group(4)) + float(m.group(5))))
+    # an iteration starts at every sampling kernel; iterations come in pairs (two repetitions per K)
+    iters, cur = [], None
+    for name, b in rows:
+        if "tree_sample" in name:
+            cur = [b]
+            iters.append(cur)
+        elif cur is not None and ("upd_" in name or "tree_rebuild" in name):
+            cur.append(b)
+            if "tree_rebuild" in name:
+                cur = None
+    out = {}
+    for K, i in zip((1, 16, 64), (1, 3, 5)):
+        if i < len(iters):
+            out[K] = int(sum(iters[i]))
+    return out
+
+
 def measure_tf32_peak(device, torch):
     """Dense TF32 TFLOP/s of this GPU: the library GEMM on 8192^3 fp32 operands with TF32 allowed (best of 5) -- the
     denominator of the 3xTF32 kernels' roofline, measured instead of assumed (bf16 / 2)."""
@@ -575,6 +607,7 @@ def per_microbench(device, torch, hbm_gbs):
     # K batches of 4096 in flight: ONE sampling launch draws K stratified batches against the current tree, ONE
     # write-back call applies the K*4096 priorities (later batches win, like K successive reference calls)
     B = 4096
+    traffic = ncu_per_traffic()
     for K in (1, 4, 16, 64):
         n = K * B
         u = torch.rand(n, dtype=torch.float64, device=device, generator=g)
@@ -596,7 +629,8 @@ def per_microbench(device, torch, hbm_gbs):
             "batches_in_flight": K, "us": round(sec * 1e6, 2), "transitions_per_s": round(n / sec, 1),
             "algorithmic_bytes": nbytes, "achieved_gbs": round(nbytes / sec / 1e9, 2),
             "frac": round(nbytes / sec / 1e9 / hbm_gbs, 5), "sample_us": round(s_sec * 1e6, 2),
-            "update_us": round(u_sec * 1e6, 2)}
+            "update_us": round(u_sec * 1e6, 2),
+            "traffic": traffic.get(K), "traffic_source": "profiles/ncu_full_per_r02.txt" if K in traffic else None}
     for B in (65536, 1 << 20):                              # one large stratified (sorted) batch
         u = torch.rand(B, dtype=torch.float64, device=device, generator=g)
         idx = torch.empty(B, dtype=torch.int64, device=device)

@@ -327,6 +327,15 @@ int pb_ens_q_loss(int B, int A, int K, const float *q_cur, const float *q_next_o
                   const float *gdn, const uint8_t *nonterminal, float loss_weight,
                   const float *row_weight, float grad_scale, float *loss_out, float *grad_q_cur,
                   void *stream);
+/* pb_ens_q_loss whose LAST CTA also does pb_loss_combine (one launch less on the step's critical path):
+ * *total_out = mean_b(dist_b * w_b) + mean_b(q'_b * w_b), q'_b = q_scale * (loss_b - *q_offset); td_out as pb_loss_combine.
+ * dist (B per-row distributional losses, may be NULL) must be complete in stream order.  ticket: one device word,
+ * zero between calls. */
+int pb_ens_q_loss_total(int B, int A, int K, const float *q_cur, const float *q_next_online, const float *q_next_target,
+                        const long long *action, const float *ret, const float *gdn, const uint8_t *nonterminal,
+                        float loss_weight, const float *row_weight, float grad_scale, float *loss_out, float *grad_q_cur,
+                        const float *dist, float q_scale, const float *q_offset, float *total_out, float *td_out,
+                        unsigned int *ticket, void *stream);
 
 /* IDSActionSelector.generate_action_probs + select_action
  * (prism/agents/action_selectors.py:125-176), deterministic branch.

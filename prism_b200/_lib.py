@@ -105,6 +105,7 @@ SIGNATURES = {
     "pb_iqn_cos_basis": [_LL, _I, _P, _P, _P],
     "pb_iqn_qh_loss": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _P, _F, _P, _P, _P],
     "pb_ens_q_loss": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _F, _P, _F, _P, _P, _P],
+    "pb_ens_q_loss_total": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _F, _P, _F, _P, _P, _P, _F, _P, _P, _P, _P, _P],
     "pb_ids_select": [_I, _I, _I, _I, _P, _P, _F, _F, _F, _P, _P, _P],
     "pb_greedy_select": [_I, _I, _I, _P, _P, _P],
     "pb_adam_clip_step": [_LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],

@@ -693,6 +693,16 @@ def unit_gradient(device):
     return t
 
 
+_LOSS_TICKET = {}
+
+
+def _loss_ticket(device):
+    t = _LOSS_TICKET.get(device)
+    if t is None:
+        t = _LOSS_TICKET[device] = torch.zeros(1, dtype=torch.int32, device=device)
+    return t
+
+
 class _FusedTotalLoss(torch.autograd.Function):
     """total = mean(dist*w) + mean(q'*w) straight from the quantile / ensemble tables: loss heads, PER
     weighting, TD mix and the gradients w.r.t. z_cur / q_cur (already scaled by w_b/B) in 3 launches;
@@ -718,19 +728,23 @@ class _FusedTotalLoss(torch.autograd.Function):
                                           ret_c.data_ptr(), gamma_c.data_ptr(), _lib.ptr(nt), float(kappa),
                                           float(dist_weight), _lib.ptr(w_c), 1.0 / B, dist.data_ptr(), gz.data_ptr(),
                                           stream), "pb_iqn_qh_loss")
+        total = torch.empty((), dtype=torch.float32, device=dev)
+        td = torch.empty(B, dtype=torch.float32, device=dev)
         if q_cur is not None:
             qc = _c(q_cur)
             K, _, A = qc.shape
             mse = torch.empty(B, dtype=torch.float32, device=dev)
             gq = torch.empty_like(qc)
-            _lib.check(lib.pb_ens_q_loss(B, A, K, qc.data_ptr(), _c(q_on).data_ptr(), _c(q_tg).data_ptr(),
-                                         action_c.data_ptr(), ret_c.data_ptr(), gamma_c.data_ptr(), _lib.ptr(nt), 1.0,
-                                         _lib.ptr(w_c), float(q_weight) / B, mse.data_ptr(), gq.data_ptr(), stream),
-                       "pb_ens_q_loss")
-        total = torch.empty((), dtype=torch.float32, device=dev)
-        td = torch.empty(B, dtype=torch.float32, device=dev)
-        _lib.check(lib.pb_loss_combine(B, _lib.ptr(dist), _lib.ptr(mse), _lib.ptr(w_c), float(q_weight),
-                                       _lib.ptr(q_offset), total.data_ptr(), td.data_ptr(), stream), "pb_loss_combine")
+            # the ensemble loss kernel's last CTA also combines the heads' losses into the PER-weighted total and the TD
+            # mix (agent.py:58-64): one launch less on the step's critical path
+            _lib.check(lib.pb_ens_q_loss_total(B, A, K, qc.data_ptr(), _c(q_on).data_ptr(), _c(q_tg).data_ptr(),
+                                               action_c.data_ptr(), ret_c.data_ptr(), gamma_c.data_ptr(), _lib.ptr(nt), 1.0,
+                                               _lib.ptr(w_c), float(q_weight) / B, mse.data_ptr(), gq.data_ptr(),
+                                               _lib.ptr(dist), float(q_weight), _lib.ptr(q_offset), total.data_ptr(),
+                                               td.data_ptr(), _loss_ticket(dev).data_ptr(), stream), "pb_ens_q_loss_total")
+        else:
+            _lib.check(lib.pb_loss_combine(B, _lib.ptr(dist), None, _lib.ptr(w_c), float(q_weight),
+                                           _lib.ptr(q_offset), total.data_ptr(), td.data_ptr(), stream), "pb_loss_combine")
         ctx.save_for_backward(gz, gq)
         ctx.set_materialize_grads(False)      # no zero-fill launches for the non-differentiable outputs
         outs = (total, dist if dist is not None else td.new_empty(0), mse if mse is not None else td.new_empty(0), td)

@@ -103,6 +103,8 @@ __global__ void __launch_bounds__(128) qh_loss_kernel(int B, int T, int Tp, int 
 // ---------------------------------------------------------------------------------
 // ensemble MSE loss: one warp per batch row, lanes over heads.  tables are [K][B][A].
 // ---------------------------------------------------------------------------------
+// ticket != NULL: the LAST CTA to finish also does what loss_combine_kernel does (total = mean(dist * w) + mean(q' * w)
+// with q' = q_scale * (loss - *q_offset), td_b = the TD mix) -- one launch less on the step's critical path.
 __global__ void __launch_bounds__(128) ens_loss_kernel(int B, int A, int K, const float *__restrict__ q_cur,
                                                        const float *__restrict__ q_next_online,
                                                        const float *__restrict__ q_next_target,
@@ -110,32 +112,59 @@ __global__ void __launch_bounds__(128) ens_loss_kernel(int B, int A, int K, cons
                                                        const float *__restrict__ ret, const float *__restrict__ gdn,
                                                        const uint8_t *__restrict__ nonterm, float loss_weight,
                                                        const float *__restrict__ row_weight, float grad_scale,
-                                                       float *__restrict__ loss_out, float *__restrict__ grad_q)
+                                                       float *__restrict__ loss_out, float *__restrict__ grad_q,
+                                                       const float *__restrict__ dist, float q_scale,
+                                                       const float *__restrict__ q_offset, float *__restrict__ total_out,
+                                                       float *__restrict__ td_out, unsigned int *__restrict__ ticket)
 {
     pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int b = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (b >= B) return;
-    const int act = (int)action[b];
-    const float R = ret[b], g = nonterm ? __fmul_rn(gdn[b], nonterm[b] ? 1.0f : 0.0f) : gdn[b];
-    const float gs = (row_weight ? row_weight[b] : 1.0f) * grad_scale * loss_weight * 2.0f / (float)K;
-    float acc = 0.0f;
-    for (int k = lane; k < K; k += 32) {
-        const size_t row = ((size_t)k * B + b) * A;
-        int best = 0;
-        float bv = q_next_online[row];
-        for (int a = 1; a < A; ++a) {
-            float v = q_next_online[row + a];
-            if (v > bv) { bv = v; best = a; }                    // argmax(dim=-2), first index (q_ensemble.py:70)
+    if (b < B) {
+        const int act = (int)action[b];
+        const float R = ret[b], g = nonterm ? __fmul_rn(gdn[b], nonterm[b] ? 1.0f : 0.0f) : gdn[b];
+        const float gs = (row_weight ? row_weight[b] : 1.0f) * grad_scale * loss_weight * 2.0f / (float)K;
+        float acc = 0.0f;
+        for (int k = lane; k < K; k += 32) {
+            const size_t row = ((size_t)k * B + b) * A;
+            int best = 0;
+            float bv = q_next_online[row];
+            for (int a = 1; a < A; ++a) {
+                float v = q_next_online[row + a];
+                if (v > bv) { bv = v; best = a; }                    // argmax(dim=-2), first index (q_ensemble.py:70)
+            }
+            const float yk = __fadd_rn(R, __fmul_rn(q_next_target[row + best], g));  // (:80)
+            const float diff = q_cur[row + act] - yk;
+            acc += diff * diff;                                      // MSELoss(reduction='none') (:84)
+            for (int a = 0; a < A; ++a) grad_q[row + a] = (a == act) ? gs * diff : 0.0f;
         }
-        const float yk = __fadd_rn(R, __fmul_rn(q_next_target[row + best], g));  // (:80)
-        const float diff = q_cur[row + act] - yk;
-        acc += diff * diff;                                      // MSELoss(reduction='none') (:84)
-        for (int a = 0; a < A; ++a) grad_q[row + a] = (a == act) ? gs * diff : 0.0f;
+        acc = warp_sum(acc);
+        if (lane == 0) loss_out[b] = acc / (float)K * loss_weight;
+    }
+    if (!ticket) return;
+    __shared__ unsigned s_last;
+    __shared__ float part[4];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+        if (s_last) { __threadfence(); *ticket = 0u; }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    float acc = 0.0f;
+    const float off = q_offset ? *q_offset : 0.0f;
+    for (int r = threadIdx.x; r < B; r += blockDim.x) {
+        const float wb = row_weight ? row_weight[r] : 1.0f;
+        const float d = dist ? dist[r] : 0.0f, qq = q_scale * (__ldcg(loss_out + r) - off);
+        acc += d * wb + qq * wb;
+        if (td_out) td_out[r] = dist ? (d * 0.5f + qq * 0.5f) : fabsf(qq);
     }
     acc = warp_sum(acc);
-    if (lane == 0) loss_out[b] = acc / (float)K * loss_weight;
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0 && total_out) *total_out = (part[0] + part[1] + part[2] + part[3]) / (float)B;
 }
 
 // ---------------------------------------------------------------------------------
@@ -589,7 +618,25 @@ int pb_ens_q_loss(int B, int A, int K, const float *q_cur, const float *q_next_o
     if (!q_cur || !q_next_online || !q_next_target || !action || !ret || !gdn || !loss_out || !grad_q_cur)
         return PB_E_ARG;
     PB_LAUNCH_PDL_CHAIN(ens_loss_kernel, (unsigned)((B + 3) / 4), 128, 0, stream, B, A, K, q_cur, q_next_online, q_next_target,
-              action, ret, gdn, nonterminal, loss_weight, row_weight, grad_scale, loss_out, grad_q_cur);
+              action, ret, gdn, nonterminal, loss_weight, row_weight, grad_scale, loss_out, grad_q_cur,
+              (const float *)nullptr, 1.0f, (const float *)nullptr, (float *)nullptr, (float *)nullptr, (unsigned int *)nullptr);
+    return PB_OK;
+}
+
+int pb_ens_q_loss_total(int B, int A, int K, const float *q_cur, const float *q_next_online, const float *q_next_target,
+                        const long long *action, const float *ret, const float *gdn, const uint8_t *nonterminal,
+                        float loss_weight, const float *row_weight, float grad_scale, float *loss_out, float *grad_q_cur,
+                        const float *dist, float q_scale, const float *q_offset, float *total_out, float *td_out,
+                        unsigned int *ticket, void *stream)
+{
+    if (B < 0 || A <= 0 || K <= 0) return PB_E_ARG;
+    if (B == 0) return PB_OK;
+    if (!q_cur || !q_next_online || !q_next_target || !action || !ret || !gdn || !loss_out || !grad_q_cur || !total_out ||
+        !ticket)
+        return PB_E_ARG;
+    PB_LAUNCH_PDL_CHAIN(ens_loss_kernel, (unsigned)((B + 3) / 4), 128, 0, stream, B, A, K, q_cur, q_next_online, q_next_target,
+              action, ret, gdn, nonterminal, loss_weight, row_weight, grad_scale, loss_out, grad_q_cur, dist, q_scale,
+              q_offset, total_out, td_out, ticket);
     return PB_OK;
 }
 
