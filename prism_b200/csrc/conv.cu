@@ -10,6 +10,7 @@
 // accumulates its share in registers, partial sums are combined by a second tiny launch in a fixed
 // order (deterministic).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -157,6 +158,130 @@ __global__ void __launch_bounds__(512) conv3x3_relu_bwd_kernel(ConvDims d, const
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Backward on the tensor cores, 16 output channels (every MinAtar embedding): for one sample
+//     dW[oc][tap] = sum_p dY[oc][p] * Xcol[p][tap],   db[oc] = sum_p dY[oc][p]
+// is a 16 x (taps + 1) x (OH*OW) product (the bias is one more column, of ones): m16n8k8 3xTF32 MMAs -- the masked
+// gradient is the A operand (rows padded to 68 words: conflict-free fragment loads), the frame is gathered into B
+// fragments through two small offset tables (position -> frame word, tap -> frame word).  One CTA of 4 warps per
+// sample: staged together (8 rounds of loads in flight), the warps split the n-tiles.  ~0.2 MFLOP per sample: the FMA
+// kernel above spends its time on 2 shared-memory reads per FMA.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void conv_mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void conv_split_tf32(float x, uint32_t &hi, uint32_t &lo)
+{
+    hi = __float_as_uint(x) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+constexpr int CM_WARPS = 4;                 // warps per CTA: they share one sample and split its n-tiles
+constexpr int CM_MAX_NT = 12;               // n-tiles of 8 columns: taps + 1 <= 96 (C <= 10)
+constexpr int CM_GSTRIDE = 68;              // words per gradient row in shared memory
+
+template <int NT>
+__global__ void __launch_bounds__(CM_WARPS * 32) conv3x3_relu_bwd_mma_kernel(ConvDims d, const float *__restrict__ x,
+                                                                            const float *__restrict__ out,
+                                                                            const float *__restrict__ dout,
+                                                                            float *__restrict__ partial, int n_groups)
+{
+    pdl_wait();                                                   // programmatic dependent launch (PB_LAUNCH_PDL)
+    pdl_trigger();
+    extern __shared__ float sm[];
+    constexpr int NTW = (NT + CM_WARPS - 1) / CM_WARPS;            // n-tiles per warp
+    const int nx = d.H * d.W * d.C, plane = d.OH * d.OW, taps = d.C * 9, ne = 16 * taps + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+    float *sx = sm, *sg = sx + nx;
+    // offset tables: pos_off[p] = frame word of output position p's window origin; tap_off[tap] = frame word of the
+    // tap inside the window, -1 for the bias column, -2 past it
+    int *pos_off = reinterpret_cast<int *>(sg + 16 * CM_GSTRIDE), *tap_off = pos_off + plane;
+    for (int p = threadIdx.x; p < plane; p += blockDim.x) pos_off[p] = ((p / d.OW) * d.W + (p % d.OW)) * d.C;
+    for (int tp = threadIdx.x; tp < NT * 8; tp += blockDim.x) {
+        int v = -2;
+        if (tp < taps) { const int c = tp / 9, k = tp - c * 9; v = ((k / 3) * d.W + (k % 3)) * d.C + c; }
+        else if (tp == taps) v = -1;
+        tap_off[tp] = v;
+    }
+    float cf[NTW][4];
+#pragma unroll
+    for (int j = 0; j < NTW; ++j) cf[j][0] = cf[j][1] = cf[j][2] = cf[j][3] = 0.0f;
+    const int g = blockIdx.x;                                      // this CTA's partial
+    for (int b = g; b < d.B; b += n_groups) {
+        __syncthreads();
+        const float *xb = x + (size_t)b * nx, *ob = out + (size_t)b * 16 * plane, *gb = dout + (size_t)b * 16 * plane;
+        // staging with the loads of 8 rounds in flight
+        for (int i0 = threadIdx.x; i0 < nx; i0 += 8 * blockDim.x) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < nx ? xb[i] : 0.0f; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; if (i < nx) sx[i] = v[u]; }
+        }
+        for (int i0 = threadIdx.x; i0 < 16 * plane; i0 += 8 * blockDim.x) {
+            float vo[8], vg[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * blockDim.x;
+                vo[u] = i < 16 * plane ? ob[i] : 0.0f;
+                vg[u] = i < 16 * plane ? gb[i] : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < 16 * plane) {
+                    const int oc = i / plane, p = i - oc * plane;
+                    sg[oc * CM_GSTRIDE + p] = vo[u] > 0.0f ? vg[u] : 0.0f;   // ReLU mask
+                }
+            }
+        }
+        __syncthreads();
+        int toff[NTW];
+#pragma unroll
+        for (int j = 0; j < NTW; ++j) { const int nt = warp + j * CM_WARPS; toff[j] = nt < NT ? tap_off[nt * 8 + gq] : -2; }
+        for (int k0 = 0; k0 < plane; k0 += 8) {
+            uint32_t ah[4], al[4];
+            conv_split_tf32(sg[gq * CM_GSTRIDE + k0 + tq], ah[0], al[0]);
+            conv_split_tf32(sg[(gq + 8) * CM_GSTRIDE + k0 + tq], ah[1], al[1]);
+            conv_split_tf32(sg[gq * CM_GSTRIDE + k0 + tq + 4], ah[2], al[2]);
+            conv_split_tf32(sg[(gq + 8) * CM_GSTRIDE + k0 + tq + 4], ah[3], al[3]);
+            const int p0 = pos_off[k0 + tq], p1 = pos_off[k0 + tq + 4];
+#pragma unroll
+            for (int j = 0; j < NTW; ++j) {
+                if (warp + j * CM_WARPS >= NT) break;              // warp-uniform
+                const int to = toff[j];
+                const float b0 = to >= 0 ? sx[p0 + to] : (to == -1 ? 1.0f : 0.0f);
+                const float b1 = to >= 0 ? sx[p1 + to] : (to == -1 ? 1.0f : 0.0f);
+                uint32_t bh[2], bl[2];
+                conv_split_tf32(b0, bh[0], bl[0]);
+                conv_split_tf32(b1, bh[1], bl[1]);
+                conv_mma_tf32(cf[j], al, bh);
+                conv_mma_tf32(cf[j], ah, bl);
+                conv_mma_tf32(cf[j], ah, bh);
+            }
+        }
+    }
+    if (g < n_groups) {
+        // fragment (row gq / gq + 8 = output channel, columns 2 tq, 2 tq + 1 of n-tile nt = tap) -> partial[g][e]:
+        // e = oc * taps + tap for the weights, 16 * taps + oc for the bias column
+        float *pg = partial + (size_t)g * ne;
+#pragma unroll
+        for (int j = 0; j < NTW; ++j) {
+            const int nt = warp + j * CM_WARPS;
+            if (nt >= NT) break;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int oc = gq + (q >> 1) * 8, tp = nt * 8 + 2 * tq + (q & 1);
+                if (tp < taps) pg[oc * taps + tp] = cf[j][q];
+                else if (tp == taps) pg[16 * taps + oc] = cf[j][q];
+            }
+        }
+    }
+}
+
 // one warp per gradient element: lanes stride over the per-CTA partials, fixed-order shuffle reduction
 __global__ void __launch_bounds__(256) conv_bwd_reduce_kernel(int n_groups, int nw, int n_bias,
                                                               const float *__restrict__ partial,
@@ -212,6 +337,30 @@ int pb_conv3x3_relu_bwd(int B, int H, int W, int C, int OC, const float *x, cons
     if (rc) return rc;
     if (!x || !out || !dout || !partial_scratch || !dw) return PB_E_ARG;
     const int groups = pb_conv3x3_relu_bwd_groups(B);
+    const int ne = OC * C * 9 + OC;
+    {
+        // 16 output channels, output plane a multiple of 8: the tensor-core kernel (PB_CONV_MMA=0: the FMA kernel)
+        static int mma_ok = -1;
+        if (mma_ok < 0) { const char *e = getenv("PB_CONV_MMA"); mma_ok = (e && e[0] == '0') ? 0 : 1; }
+        const int plane = d.OH * d.OW, nt = (C * 9 + 1 + 7) / 8;
+        const size_t msmem = sizeof(float) * (size_t)(H * W * C + 16 * CM_GSTRIDE + plane + nt * 8);
+        if (mma_ok && OC == 16 && (plane % 8) == 0 && plane <= 64 && nt >= 5 && nt <= CM_MAX_NT && msmem <= 48 * 1024) {
+            const unsigned grid = (unsigned)groups;
+#define PB_CONV_MMA_CASE(NTV)                                                                                      \
+            case NTV: PB_LAUNCH_PDL_CHAIN(conv3x3_relu_bwd_mma_kernel<NTV>, grid, CM_WARPS * 32, msmem, stream, d, x, out, \
+                                          dout, partial_scratch, groups); break;
+            switch (nt) {
+                PB_CONV_MMA_CASE(5) PB_CONV_MMA_CASE(6) PB_CONV_MMA_CASE(7) PB_CONV_MMA_CASE(8) PB_CONV_MMA_CASE(9)
+                PB_CONV_MMA_CASE(10) PB_CONV_MMA_CASE(11) PB_CONV_MMA_CASE(12)
+                default: goto fma_path;
+            }
+#undef PB_CONV_MMA_CASE
+            PB_LAUNCH_PDL_CHAIN(conv_bwd_reduce_kernel, (unsigned)((ne + 7) / 8), 256, 0, stream, groups, OC * C * 9, OC,
+                                partial_scratch, dw, db);
+            return PB_OK;
+        }
+    }
+fma_path:
     const size_t smem = sizeof(float) * (size_t)(H * W * C + OC * d.OH * d.OW);
     if (smem > 48 * 1024) return PB_E_UNSUPPORTED;
     // two gradient elements per thread for the MinAtar embedding (880 elements, 512 threads): several CTAs per SM, so
@@ -219,7 +368,6 @@ int pb_conv3x3_relu_bwd(int B, int H, int W, int C, int OC, const float *x, cons
     const int ne_all = OC * C * 9 + OC;
     const int bthreads = ne_all > 256 ? 512 : 256;
     PB_LAUNCH_PDL_CHAIN(conv3x3_relu_bwd_kernel, (unsigned)groups, bthreads, smem, stream, d, x, out, dout, partial_scratch);
-    const int ne = OC * C * 9 + OC;
     PB_LAUNCH_PDL_CHAIN(conv_bwd_reduce_kernel, (unsigned)((ne + 7) / 8), 256, 0, stream, groups, OC * C * 9, OC,
               partial_scratch, dw, db);
     return PB_OK;
