@@ -620,6 +620,9 @@ int pb_narrow_linear_fwd(int K, long long M, int N, int J, const float *x, long 
                          const float *bias, float *y, void *stream);
 int pb_narrow_linear_bwd(int K, long long M, int N, int J, const float *x, long long x_head_stride, const float *w,
                          const float *dy, float *dx, float *dW, float *db, float *partials, void *stream);
+/* pb_narrow_linear_bwd with partials given and dW = db = NULL writes the per-CTA partial sums only; this finishes them
+ * (dW / db optional) on any stream ordered after that call -- the weight-gradient branch of the learner step graph. */
+int pb_narrow_linear_bwd_reduce(int K, long long M, int N, int J, const float *partials, float *dW, float *db, void *stream);
 
 /* out[i] = sum_k in[k][i], i < n (n % 4 == 0): gradients of an input shared by K heads (q_ensemble.py:44-48) */
 int pb_sum_heads(int K, long long n, const float *in, float *out, void *stream);

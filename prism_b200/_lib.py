@@ -150,6 +150,7 @@ SIGNATURES = {
     "pb_narrow_linear_bwd_blocks": [_LL],
     "pb_narrow_linear_fwd": [_I, _LL, _I, _I, _P, _LL, _P, _P, _P, _P],
     "pb_narrow_linear_bwd": [_I, _LL, _I, _I, _P, _LL, _P, _P, _P, _P, _P, _P, _P],
+    "pb_narrow_linear_bwd_reduce": [_I, _LL, _I, _I, _P, _P, _P, _P],
     "pb_sum_heads": [_I, _LL, _P, _P, _P],
     "pb_iqn_draw_cos_basis": [_LL, _I, _P, _P, _P, _P],
     "pb_relu_bwd_bias_strips": [_LL],

@@ -221,6 +221,42 @@ def _side_stream(device):
     return fork_stream(device, "bwd")
 
 
+# Weight-gradient branches and their joins.  A layer's dW (and db) feed nothing but the optimizer, so inside the captured
+# learner step the branch that computes them does not have to rejoin the backward pass before the next layer starts:
+# LearnerStep defers the joins to just before the optimizer step (mode 2).  That is only sound when autograd hands the
+# very tensor the branch writes to the parameter as its .grad (no accumulation kernel on the main stream), so the step's
+# first warm-up iteration runs in mode 1: joins stay where they are, the gradient addresses are recorded, and
+# LearnerStep checks them against the parameters' .grad before it turns mode 2 on.  Mode 0 (default): join in place.
+_JOINS = {"mode": 0, "streams": [], "ptrs": []}
+
+
+def defer_joins(mode):
+    _JOINS["mode"], _JOINS["streams"], _JOINS["ptrs"] = int(mode), [], []
+
+
+def finish_deferred(device):
+    """Join every deferred branch into the current stream; returns the recorded gradient addresses."""
+    cur = torch.cuda.current_stream(device)
+    seen = set()
+    for s in _JOINS["streams"]:
+        if s.cuda_stream not in seen and s.cuda_stream != cur.cuda_stream:
+            seen.add(s.cuda_stream)
+            cur.wait_stream(s)
+    ptrs = _JOINS["ptrs"]
+    defer_joins(0)
+    return ptrs
+
+
+def _join_or_defer(side, device, *grads):
+    mode = _JOINS["mode"]
+    if mode:
+        _JOINS["ptrs"].extend(g.data_ptr() for g in grads if g is not None)     # addresses: a reference would block the steal
+    if mode == 2:
+        _JOINS["streams"].append(side)
+    else:
+        torch.cuda.current_stream(device).wait_stream(side)
+
+
 class _Linear(torch.autograd.Function):
     """Y = act(X W^T + b), batched over heads.  X: (M, J) shared or (K, M, J); W: (K, N, J); b: (K, N)."""
 
@@ -272,7 +308,7 @@ class _Linear(torch.autograd.Function):
             _lib.check(lib.pb_linear_bwd_input(K, M, N, J, dy.data_ptr(), mask, wc.data_ptr(), int(ctx.shared),
                                                dx.data_ptr(), stream), "pb_linear_bwd_input")
         if side is not None:
-            torch.cuda.current_stream(dy.device).wait_stream(side)
+            _join_or_defer(side, dy.device, dw, db)
         if TRACE_MARK is not None:
             TRACE_MARK("bwd:linear K%d M%d N%d J%d" % (K, M, N, J))
         return dx, dw, db, None
@@ -404,9 +440,18 @@ class _NarrowLinear(torch.autograd.Function):
         partials = None
         if want_dw or want_db:
             partials = torch.empty(K * lib.pb_narrow_linear_bwd_blocks(M) * (N * J + N), dtype=torch.float32, device=dy.device)
+        # inside the learner step graph the dW / db reduction goes to the weight-gradient branch (see _JOINS)
+        split = partials is not None and want_dx and _JOINS["mode"] and PARALLEL_BACKWARD and not SERIAL_GRAPH
         _lib.check(lib.pb_narrow_linear_bwd(K, M, N, J, xc.data_ptr(), 0 if ctx.shared else M * J, wc.data_ptr(), dy.data_ptr(),
-                                            _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(partials), _stream(dy)),
-                   "pb_narrow_linear_bwd")
+                                            _lib.ptr(dx), None if split else _lib.ptr(dw), None if split else _lib.ptr(db),
+                                            _lib.ptr(partials), _stream(dy)), "pb_narrow_linear_bwd")
+        if split:
+            side = _side_stream(dy.device)
+            side.wait_stream(torch.cuda.current_stream(dy.device))
+            with torch.cuda.stream(side):
+                _lib.check(lib.pb_narrow_linear_bwd_reduce(K, M, N, J, partials.data_ptr(), _lib.ptr(dw), _lib.ptr(db),
+                                                           side.cuda_stream), "pb_narrow_linear_bwd_reduce")
+            _join_or_defer(side, dy.device, dw, db)
         if want_dx and ctx.shared:
             dx = sum_leading(dx)                                   # the heads share their input
         return dx, dw, db

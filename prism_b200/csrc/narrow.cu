@@ -302,7 +302,9 @@ int pb_narrow_linear_fwd(int K, long long M, int N, int J, const float *x, long 
 }
 
 // per head: dx (K, M, J; optional) = dy . W ; dW (K, N, J; optional) = dy^T . x ; db (K, N; optional) = column sums of dy.
-// partials: K * pb_narrow_linear_bwd_blocks(M) * (N * J + N) floats of scratch.
+// partials: K * pb_narrow_linear_bwd_blocks(M) * (N * J + N) floats of scratch.  With partials given but dW = db = NULL
+// only the per-CTA partial sums are written: pb_narrow_linear_bwd_reduce (below) finishes them, on any stream ordered
+// after this call -- LearnerStep puts it on the weight-gradient branch of its graph.
 int pb_narrow_linear_bwd(int K, long long M, int N, int J, const float *x, long long x_head_stride, const float *w,
                          const float *dy, float *dx, float *dW, float *db, float *partials, void *stream)
 {
@@ -311,8 +313,8 @@ int pb_narrow_linear_bwd(int K, long long M, int N, int J, const float *x, long 
     if ((((uintptr_t)x) | ((uintptr_t)w) | ((uintptr_t)dx) | ((uintptr_t)partials)) & 7) return PB_E_ARG;
     const int nb = pb_narrow_linear_bwd_blocks(M);
     const int rpc = narrow_rpc(M);
-    float *dWp = (dW || db) ? partials : nullptr;
-    float *dbp = (dW || db) ? partials + (size_t)K * nb * N * J : nullptr;
+    float *dWp = partials;
+    float *dbp = partials ? partials + (size_t)K * nb * N * J : nullptr;
     const dim3 grid((unsigned)nb, (unsigned)K);
     switch (narrow_np(N)) {
         case 4: PB_LAUNCH_PDL_CHAIN(narrow_bwd_kernel<4>, grid, J / 2, 0, stream, M, N, J, x, x_head_stride, w, dy, dx, dWp, dbp, rpc); break;
@@ -325,6 +327,18 @@ int pb_narrow_linear_bwd(int K, long long M, int N, int J, const float *x, long 
         PB_LAUNCH_PDL_CHAIN(narrow_reduce_kernel, dim3((unsigned)((n + N + 31) / 32), (unsigned)K), 256, 0, stream, nb, n, N, dWp, dbp,
                   dW, db);
     }
+    return PB_OK;
+}
+
+// the second half of pb_narrow_linear_bwd: dW (K, N, J; optional) and db (K, N; optional) from the partial sums
+int pb_narrow_linear_bwd_reduce(int K, long long M, int N, int J, const float *partials, float *dW, float *db, void *stream)
+{
+    if (K < 1 || K > 65535 || !pb_narrow_linear_supported(M, N, J) || !partials) return PB_E_ARG;
+    if (!dW && !db) return PB_OK;
+    const int nb = pb_narrow_linear_bwd_blocks(M);
+    const long long n = (long long)N * J;
+    PB_LAUNCH_PDL_CHAIN(narrow_reduce_kernel, dim3((unsigned)((n + N + 31) / 32), (unsigned)K), 256, 0, stream, nb, n, N, partials,
+                        partials + (size_t)K * nb * N * J, dW, db);
     return PB_OK;
 }
 

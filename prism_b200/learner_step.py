@@ -117,6 +117,8 @@ class LearnerStep:
         self._trace = None               # enable_trace(): device buffer of timeline marks
         import os as _os
         self.overlap_write_back = _os.environ.get("PB_OVERLAP_WRITEBACK", "1") != "0"
+        self._defer_mode, self._defer_ok = 0, False             # weight-gradient joins: see _capture / ops._JOINS
+        self._defer_enabled = _os.environ.get("PB_DEFER_WGRAD", "1") != "0"
 
     # ------------------------------------------------------------------------------------
     def _setup_prefetch(self):
@@ -271,7 +273,17 @@ class LearnerStep:
                     self._sample_gather(u, self._shadow, tag="tail:")      # next iteration's batch
                     mark("tail:next_batch_ready")
 
-        dl, ql, total, td = agent._loss_and_backward(self.batch, w, agent.target_model, after_loss=write_back)
+        # weight-gradient branches rejoin before the optimizer, not inside backward (agents/ops.py: _JOINS)
+        _ops.defer_joins(self._defer_mode)
+        try:
+            dl, ql, total, td = agent._loss_and_backward(self.batch, w, agent.target_model, after_loss=write_back)
+        finally:
+            wgrad_ptrs = _ops.finish_deferred(self.device)
+        if self._defer_mode == 1:
+            opt = agent.optimizer
+            params = opt.params if hasattr(opt, "params") else [p for g in opt.param_groups for p in g["params"]]
+            held = {p.grad.data_ptr() for p in params if p.grad is not None}
+            self._defer_ok = all(q in held for q in wgrad_ptrs)
         agent._static_distribution_loss, agent._static_q_loss, agent._static_total_loss = dl, ql, total
         mark("backward_done")
         if dp_peer:
@@ -487,7 +499,9 @@ class LearnerStep:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            for _ in range(3):
+            for it in range(3):
+                # first iteration: probe whether the weight-gradient joins can move to the optimizer (ops._JOINS)
+                self._defer_mode = (1 if it == 0 else (2 if self._defer_ok else 0)) if self._defer_enabled else 0
                 self._body(refresh_table=True, draw=draw)
         torch.cuda.current_stream(self.device).wait_stream(side)
         if flat:
@@ -503,8 +517,11 @@ class LearnerStep:
         self.graph = None                                   # release the previous graph's pool before capturing anew
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
-            self._body(refresh_table=False, draw=draw, consume=consume)
+        try:
+            with torch.cuda.graph(self.graph):
+                self._body(refresh_table=False, draw=draw, consume=consume)
+        finally:
+            self._defer_mode = 0                                # eager steps join in place
         self.launches_per_step = _lib.launch_count() - before
         if flat:
             opt.refresh_grad_table()
