@@ -417,6 +417,10 @@ int pb_linear_bwd_input(int K, int M, int N, int J, const float *dY, const float
                         int sum_heads, float *dX, void *stream);
 int pb_linear_bwd_weight(int K, int M, int N, int J, const float *dY, const float *Ymask, const float *X,
                          long long x_head_stride, float *dW, float *db, void *stream);
+/* Measurement runs only (synchronous): phase marks (%globaltimer, ns) of the cluster split-K kernel's launches since the
+ * last call -- out[0] earliest CTA start, out[1..6] latest CTA past: first chunk staged, K loop, partial tile written,
+ * cluster barrier, split-K sum + epilogue, exit barrier -- then reset, and marking switched on / off. */
+int pb_gemm_trace(int enable, unsigned long long *out, int n_out);
 
 /* Dense layers on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, operands
  * staged by TMA; csrc/tc_gemm.cu).  Every fp32 operand is split on the fly into TF32 hi + lo parts and each

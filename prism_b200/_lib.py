@@ -87,6 +87,7 @@ SIGNATURES = {
     "pb_tree_init": [_TREE, _P],
     "pb_tree_export": [_TREE, _P, _P, _P],
     "pb_tree_trace": [_I, _P, _I],
+    "pb_gemm_trace": [_I, _P, _I],
     "pb_tree_sample_batches": [_TREE, _LL, _LL, _P, _I, _F, _P, _P, _P, _P],
     "pb_tree_build": [_TREE, _P, _LL, _P],
     "pb_tree_stats": [_TREE, _P],

@@ -22,10 +22,26 @@ constexpr int MAX_OUT = 32 * 14 * 14;
 
 struct ConvDims { int B, H, W, C, OC, OH, OW; };
 
-// One CTA per observation.  Shared memory: the frame (H*W*C) and the filter bank transposed to
+// One CTA per observation.  Shared memory: the frame and the filter bank transposed to
 // [c][ky][kx][oc] so that a thread reads the OCG = 8 consecutive output channels of one tap as two
 // float4.  Thread = (output position, group of 8 output channels): 1 frame load feeds 8 FMAs.
+// The frame is staged channel-major with its rows pitched to frame_pitch(W) words ([c][y][pitch]): the lanes of a warp
+// are 32 consecutive output positions (4 rows of 8 for MinAtar) reading one tap, and with a pitch of 8 mod 16 those
+// rows land on disjoint banks.  Channels-last as in global memory ((y*W + x)*C + c) the same read was 2-4-way
+// conflicted, and the conflicts -- not the FMAs -- set this kernel's time (three of them run concurrently per step).
 constexpr int OCG = 8;
+
+__host__ __device__ inline int frame_pitch(int W) { return ((W + 7) / 16) * 16 + 8; }   // smallest >= W with pitch % 16 == 8
+
+// channels-last word i of a frame -> its word in the staged layout.  mC, mW = div_magic(C), div_magic(W): the staging
+// loop maps 8 words per thread, and two runtime divisions each were a third of the forward kernel's instructions.
+__device__ __forceinline__ unsigned div_magic(int d) { return 0xFFFFFFFFu / (unsigned)d + 1u; }   // n / d == umulhi(n, magic), n < 2^32 / d
+__device__ __forceinline__ int frame_slot(int i, int H, int W, int C, int P, unsigned mC, unsigned mW)
+{
+    const int pix = (int)__umulhi((unsigned)i, mC), c = i - pix * C;
+    const int y = (int)__umulhi((unsigned)pix, mW), x = pix - y * W;
+    return (c * H + y) * P + x;
+}
 
 __global__ void __launch_bounds__(256) conv3x3_relu_fwd_kernel(ConvDims d, const float *__restrict__ x,
                                                                const float *__restrict__ w,
@@ -35,6 +51,8 @@ __global__ void __launch_bounds__(256) conv3x3_relu_fwd_kernel(ConvDims d, const
     pdl_trigger();
     extern __shared__ __align__(16) float sm[];
     const int nx = d.H * d.W * d.C, ocp = (d.OC + OCG - 1) / OCG * OCG, taps = d.C * 9;
+    const int P = frame_pitch(d.W), cstride = d.H * P;
+    const unsigned mC = div_magic(d.C), mW = div_magic(d.W), mO = div_magic(ocp);
     float *sw = sm, *sx = sm + taps * ocp;               // sw first: keeps it 16-byte aligned
     const int b = blockIdx.x;
     const float *xb = x + (size_t)b * nx;
@@ -48,13 +66,13 @@ __global__ void __launch_bounds__(256) conv3x3_relu_fwd_kernel(ConvDims d, const
             for (int u = 0; u < 8; ++u) {
                 const int i = i0 + u * blockDim.x;
                 fx[u] = i < nx ? xb[i] : 0.0f;
-                const int tap = i / ocp, oc = i - tap * ocp;     // tap = c*9 + ky*3 + kx
+                const int tap = (int)__umulhi((unsigned)i, mO), oc = i - tap * ocp;     // tap = c*9 + ky*3 + kx
                 fw[u] = (i < nwp && oc < d.OC) ? w[oc * taps + tap] : 0.0f;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int i = i0 + u * blockDim.x;
-                if (i < nx) sx[i] = fx[u];
+                if (i < nx) sx[frame_slot(i, d.H, d.W, d.C, P, mC, mW)] = fx[u];
                 if (i < nwp) sw[i] = fw[u];
             }
         }
@@ -69,9 +87,9 @@ __global__ void __launch_bounds__(256) conv3x3_relu_fwd_kernel(ConvDims d, const
         for (int q = 0; q < OCG; ++q) acc[q] = 0.0f;
         for (int ky = 0; ky < 3; ++ky)
             for (int kx = 0; kx < 3; ++kx) {
-                const float *px = sx + ((y + ky) * d.W + (xx + kx)) * d.C;
+                const float *px = sx + (y + ky) * P + (xx + kx);
                 for (int c = 0; c < d.C; ++c) {
-                    const float v = px[c];
+                    const float v = px[c * cstride];
                     const float4 *wv = reinterpret_cast<const float4 *>(sw + (c * 9 + ky * 3 + kx) * ocp + g * OCG);
                     const float4 w0 = wv[0], w1 = wv[1];
                     acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
@@ -194,15 +212,17 @@ __global__ void __launch_bounds__(CM_WARPS * 32) conv3x3_relu_bwd_mma_kernel(Con
     extern __shared__ float sm[];
     constexpr int NTW = (NT + CM_WARPS - 1) / CM_WARPS;            // n-tiles per warp
     const int nx = d.H * d.W * d.C, plane = d.OH * d.OW, taps = d.C * 9, ne = 16 * taps + 16;
+    const int P = frame_pitch(d.W), cstride = d.H * P;            // frame staged [c][y][pitch]: see frame_pitch
+    const unsigned mC = div_magic(d.C), mW = div_magic(d.W);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
-    float *sx = sm, *sg = sx + nx;
+    float *sx = sm, *sg = sx + cstride * d.C;
     // offset tables: pos_off[p] = frame word of output position p's window origin; tap_off[tap] = frame word of the
     // tap inside the window, -1 for the bias column, -2 past it
     int *pos_off = reinterpret_cast<int *>(sg + 16 * CM_GSTRIDE), *tap_off = pos_off + plane;
-    for (int p = threadIdx.x; p < plane; p += blockDim.x) pos_off[p] = ((p / d.OW) * d.W + (p % d.OW)) * d.C;
+    for (int p = threadIdx.x; p < plane; p += blockDim.x) pos_off[p] = (p / d.OW) * P + (p % d.OW);
     for (int tp = threadIdx.x; tp < NT * 8; tp += blockDim.x) {
         int v = -2;
-        if (tp < taps) { const int c = tp / 9, k = tp - c * 9; v = ((k / 3) * d.W + (k % 3)) * d.C + c; }
+        if (tp < taps) { const int c = tp / 9, k = tp - c * 9; v = c * cstride + (k / 3) * P + (k % 3); }
         else if (tp == taps) v = -1;
         tap_off[tp] = v;
     }
@@ -219,7 +239,10 @@ __global__ void __launch_bounds__(CM_WARPS * 32) conv3x3_relu_bwd_mma_kernel(Con
 #pragma unroll
             for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < nx ? xb[i] : 0.0f; }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; if (i < nx) sx[i] = v[u]; }
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < nx) sx[frame_slot(i, d.H, d.W, d.C, P, mC, mW)] = v[u];
+            }
         }
         for (int i0 = threadIdx.x; i0 < 16 * plane; i0 += 8 * blockDim.x) {
             float vo[8], vg[8];
@@ -319,7 +342,7 @@ int pb_conv3x3_relu_fwd(int B, int H, int W, int C, int OC, const float *x, cons
     if (rc) return rc;
     if (!x || !w || !out) return PB_E_ARG;
     const int ocp = (OC + 7) / 8 * 8;
-    const size_t smem = sizeof(float) * (size_t)(H * W * C + ocp * C * 9);
+    const size_t smem = sizeof(float) * (size_t)(H * frame_pitch(W) * C + ocp * C * 9);
     if (smem > 48 * 1024) return PB_E_UNSUPPORTED;
     const int items = d.OH * d.OW * (ocp / 8);
     const int threads = items >= 256 ? 256 : (items + 31) / 32 * 32;
@@ -343,7 +366,7 @@ int pb_conv3x3_relu_bwd(int B, int H, int W, int C, int OC, const float *x, cons
         static int mma_ok = -1;
         if (mma_ok < 0) { const char *e = getenv("PB_CONV_MMA"); mma_ok = (e && e[0] == '0') ? 0 : 1; }
         const int plane = d.OH * d.OW, nt = (C * 9 + 1 + 7) / 8;
-        const size_t msmem = sizeof(float) * (size_t)(H * W * C + 16 * CM_GSTRIDE + plane + nt * 8);
+        const size_t msmem = sizeof(float) * (size_t)(H * frame_pitch(W) * C + 16 * CM_GSTRIDE + plane + nt * 8);
         if (mma_ok && OC == 16 && (plane % 8) == 0 && plane <= 64 && nt >= 5 && nt <= CM_MAX_NT && msmem <= 48 * 1024) {
             const unsigned grid = (unsigned)groups;
 #define PB_CONV_MMA_CASE(NTV)                                                                                      \
