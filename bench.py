@@ -297,7 +297,7 @@ def kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src):
         out[k] = {"us": round(sec * 1e6, 2), "algorithmic_bytes": int(nbytes), "achieved_gbs": round(gbs, 2),
                   "frac": round(gbs / hbm_gbs, 5)}
     bf16 = tensor_peak()
-    out["q_head_fc1_fwd (gemm_kernel, %dx%dx%d fp32 FFMA, cluster split-K)" % (B, H_, F_)] = {
+    out["q_head_fc1_fwd (gemm_async_kernel, %dx%dx%d 3xTF32 mma.sync, cluster split-K)" % (B, H_, F_)] = {
         "us": round(t_fc * 1e6, 2), "algorithmic_flops": int(fc_flops), "algorithmic_bytes": int(fc_bytes),
         "achieved_tflops": round(fc_flops / t_fc / 1e12, 3), "achieved_gbs": round(fc_bytes / t_fc / 1e9, 2),
         "frac_of_bf16_tensor_peak": round(fc_flops / t_fc / 1e12 / bf16, 5), "frac": round(fc_bytes / t_fc / 1e9 / hbm_gbs, 5)}
@@ -306,14 +306,18 @@ def kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src):
     if "algorithmic_flops" in d:
         # GEMM-shaped work: the tensor / FMA pipes bound it; 3 forward + 2x2 backward launches of this family are ~45 %
         # of the step (profiles/launches_r01d_step.txt).  traffic: dram__bytes_read+write of one launch, ncu --set full
-        # (profiles/ncu_full_step_r01.txt, gemm_kernel<1,1,0> grid (4,4,8)).
-        traffic, traffic_file = ncu_traffic("gemm_kernel<1, 1, 0,")
+        # (profiles/ncu_full_step_r02b.txt, gemm_async_kernel<1,1,0,4> grid (4,4,8); before the cp.async kernel:
+        # ncu_full_step_r02.txt, gemm_kernel<1,1,0>).
+        traffic, traffic_file = ncu_traffic("gemm_async_kernel<1, 1, 0,")
+        if traffic is None:
+            traffic, traffic_file = ncu_traffic("gemm_kernel<1, 1, 0,")
         roof = {"bound": "tensor", "kernel": dom, "achieved": d["achieved_tflops"], "peak": bf16, "unit": "TFLOP/s",
                 "frac": d["frac_of_bf16_tensor_peak"], "traffic": traffic, "traffic_source": traffic_file,
                 "peak_source": peak_src,
-                "note": "batch-256 fp32 layer (134 MFLOP, 2.3 MB): latency-bound by construction -- 128 CTAs, each fetching its "
-                        "whole K slice at once; the reference computes it in fp32, so the kernel runs on the FFMA pipe and the bf16 "
-                        "tensor peak is only the nominal denominator.  Layers from 2e8 FLOP up run on tcgen05 (3xTF32): "
+                "note": "batch-256 fp32 layer (134 MFLOP, 2.3 MB): latency-bound by construction -- 128 CTAs in clusters of 8, "
+                        "each fetching its whole K slice by cp.async at entry; the reference computes it in fp32, so the "
+                        "products are 3xTF32 on the legacy mma.sync path (3 MMAs per product) and the bf16 tensor peak is "
+                        "only the nominal denominator.  Layers from 2e8 FLOP up run on tcgen05 (3xTF32): "
                         "see extras.tc_gemm for their tensor-pipe roofline and extras.per_microbench for the HBM-bound "
                         "PER kernels"}
     else:
