@@ -276,7 +276,7 @@ def kernel_rooflines(step, buf, agent, torch, hbm_gbs, peak_src):
     rows["per_update (upd_lines_sorted_kernel + tree_rebuild_kernel)"] = (time_kernel(lambda: tree.update_priority(idx, prio, sorted=True), 50, torch),
                                                      B * (16 * L + 20))
     snap = opt.snapshot()
-    rows["clip+adam (pack_grads + adam_clip)"] = (time_kernel(lambda: opt.step(refresh_table=False), 50, torch),
+    rows["gather+clip+adam (adam_fused_kernel, one launch)"] = (time_kernel(lambda: opt.step(refresh_table=False), 50, torch),
                                                   opt.numel * 4 * (2 + 1 + 2 + 2 + 2))   # pack r/w, sumsq fused, p/m/v r+w, g read
     opt.restore(snap)
     opt.allreduce = saved_allreduce

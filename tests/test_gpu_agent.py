@@ -281,10 +281,14 @@ def test_learner_step_graph_after_eager_update():
 @pytest.mark.parametrize("K,M,N,J,shared,relu", [
     (1, 256, 256, 1024, True, True), (1, 256, 4, 256, False, False), (10, 64, 256, 1024, True, True),
     (10, 64, 3, 256, False, False), (3, 37, 19, 50, False, True), (1, 2048, 256, 1024, True, True),
-    (4, 5, 7, 3, True, False), (1, 512, 512, 3136, True, True)])
+    (4, 5, 7, 3, True, False), (1, 512, 512, 3136, True, True),
+    # 16-byte aligned operands with ragged tiles: the cp.async kernel's zero-filled row / column / k tails (272 rows = the
+    # padded data-parallel batch); (3, 37, 19, 50) and (4, 5, 7, 3) above are unaligned: the register-staged kernel
+    (2, 272, 200, 1000, False, True), (1, 100, 36, 68, True, True), (3, 64, 64, 36, False, False)])
 def test_fused_linear_matches_torch(K, M, N, J, shared, relu):
-    """pb_linear_{fwd,bwd_input,bwd_weight} (cluster split-K SIMT GEMM with fused bias/ReLU/mask/bias-grad)
-    against torch fp64 math; tolerance 1e-5 relative of the tensor's max (fp32 accumulation order)."""
+    """pb_linear_{fwd,bwd_input,bwd_weight} (cluster split-K GEMM, 3xTF32 products, fused bias/ReLU/mask/bias-grad;
+    cp.async operand tiles when aligned, register-staged otherwise) against torch fp64 math; tolerance 2e-5 relative of
+    the tensor's max (fp32 accumulation order)."""
     from prism_b200.agents import ops
     g = torch.Generator().manual_seed(K * 1000 + M + N + J)
     x = torch.randn((M, J) if shared else (K, M, J), generator=g)
@@ -499,15 +503,23 @@ def test_fused_layer_norm_matches_fp64(rows, F_):
     assert rel_err(ln.bias.grad.cpu().numpy(), ref.bias.grad.numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("native", [True, False])
 @pytest.mark.parametrize("host_u", [False, True])
 @pytest.mark.parametrize("use_graph", [True, False])
-def test_fused_ingest_step_equals_separate_push_then_step(use_graph, host_u):
+def test_fused_ingest_step_equals_separate_push_then_step(use_graph, host_u, native, monkeypatch):
     """LearnerStep.step(ingest=...) scatters the new steps inside the step graph (after the priority write-back,
     concurrently with backward) from double-buffered staging blocks.  Same uniforms, same data: it must produce the
-    same losses, parameters, ring and trees as `step(); push(new steps)` run one after the other."""
+    same losses, parameters, ring and trees as `step(); push(new steps)` run one after the other.  Both host stagings:
+    one C call (pb_store_stage_block, the default) and the numpy assignments."""
     import prism_b200
+    from prism_b200.experience import ring as ring_mod
     from prism_b200.learner_step import LearnerStep
     from oracle.gen_golden import make_script
+    monkeypatch.setattr(ring_mod, "NATIVE_STAGE", native)
+    taken = []
+    orig = ring_mod.IngestSlot._fill_native
+    monkeypatch.setattr(ring_mod.IngestSlot, "_fill_native",
+                        lambda self, *a: taken.append(orig(self, *a)) or taken[-1])
     cap, B, obs_shape, A, n_new, iters = 256, 16, (10, 10, 6), 4, 4, 9
     S = make_script(5, n_streams=4, n_steps=200 + n_new * iters, obs_shape=obs_shape, p_done=0.05, p_trunc=0.03, n_actions=A)
     succ = np.where(S["trunc"][:, None], S["final_obs"], S["next_obs"])
@@ -543,6 +555,7 @@ def test_fused_ingest_step_equals_separate_push_then_step(use_graph, host_u):
                 ring.obs.clone(), ring.next_link.clone())
 
     a, b = run(True), run(False)
+    assert (len(taken) > 0 and all(taken)) if native else not taken     # the staging path under test really ran
     assert a[0] == b[0]
     assert torch.equal(a[1], b[1])
     assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
