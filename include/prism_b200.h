@@ -57,6 +57,10 @@ int pb_stream_wait_event(void *stream, void *event);
 int pb_copy_h2d_async(void *dst, const void *src, long long bytes, void *stream);
 int pb_copy_d2h_async(void *dst, const void *src, long long bytes, void *stream);
 int pb_copy_d2d_async(void *dst, const void *src, long long bytes, void *stream);
+/* one host call per iteration of the fused ingest: copy_stream waits for after_event (NULL: none), copies the pinned
+ * block src -> dst, records copied_event; main_stream waits for copied_event */
+int pb_staged_copy_submit(void *copy_stream, void *after_event, void *dst, const void *src, long long bytes,
+                          void *copied_event, void *main_stream);
 const char *pb_error_string(int code);
 /* number of kernels this library has launched in this process (bench: gpu_launches) */
 long long   pb_launch_count(void);

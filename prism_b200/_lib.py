@@ -80,6 +80,7 @@ SIGNATURES = {
     "pb_event_synchronize": [_P],
     "pb_stream_wait_event": [_P, _P],
     "pb_copy_h2d_async": [_P, _P, _LL, _P],
+    "pb_staged_copy_submit": [_P, _P, _P, _P, _LL, _P, _P],
     "pb_copy_d2h_async": [_P, _P, _LL, _P],
     "pb_copy_d2d_async": [_P, _P, _LL, _P],
     "pb_tree_layout": [_LL, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),

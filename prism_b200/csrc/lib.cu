@@ -82,6 +82,21 @@ int pb_copy_d2h_async(void *dst, const void *src, long long bytes, void *stream)
     return (int)cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
 }
 
+// The fused ingest's per-iteration submission as ONE host call: on copy_stream wait for after_event (NULL: nothing to wait
+// for), copy the pinned block to the device, record copied_event; main_stream then waits for copied_event.
+int pb_staged_copy_submit(void *copy_stream, void *after_event, void *dst, const void *src, long long bytes,
+                          void *copied_event, void *main_stream)
+{
+    if (!dst || !src || bytes < 0 || !copied_event) return PB_E_ARG;
+    cudaStream_t cs = (cudaStream_t)copy_stream;
+    cudaError_t e = cudaSuccess;
+    if (after_event) e = cudaStreamWaitEvent(cs, (cudaEvent_t)after_event, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess) e = cudaEventRecord((cudaEvent_t)copied_event, cs);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)main_stream, (cudaEvent_t)copied_event, 0);
+    return (int)e;
+}
+
 int pb_copy_d2d_async(void *dst, const void *src, long long bytes, void *stream)
 {
     if (!dst || !src || bytes < 0) return PB_E_ARG;

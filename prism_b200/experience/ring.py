@@ -419,13 +419,12 @@ class FusedIngest:
         self.slots[p].fill(stream_ids, obs, action, reward, done, trunc, next_obs)
         if u is not None:
             self.slots[p].h_u_np[:] = u
-        if self._consumed_valid[p]:
-            lib.pb_stream_wait_event(self._copy_handle, self.consumed[p])
         dst, src, nbytes = self._ptrs[p]
-        _lib.check(lib.pb_copy_h2d_async(dst, src, nbytes, self._copy_handle), "pb_copy_h2d_async")
-        lib.pb_event_record(self.copied[p], self._copy_handle)
+        rc = lib.pb_staged_copy_submit(self._copy_handle, self.consumed[p] if self._consumed_valid[p] else None, dst, src,
+                                       nbytes, self.copied[p], main_stream)
+        if rc:
+            _lib.check(rc, "pb_staged_copy_submit")
         self._copied_valid[p] = True
-        lib.pb_stream_wait_event(main_stream, self.copied[p])
         return p
 
     def plan_block(self, stream_ids, obs, action, reward, done, trunc, next_obs, u=None):
